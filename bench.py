@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- RFNO-3D 128^3 training-step throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--precision fp32|tf32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one full training step (forward, MSE, backward, gradient all-reduce for N>1, AdamW)
+of RationalFourierOperator3D(modes 32^3, width 64, rational order (4,4), 4 layers) on a batch of 8
+synthetic random-spectrum turbulence fields per GPU at 128^3 (BASELINE.json configs[1]; weak scaling).
+Rank 0 prints ONE JSON line.  --impl reference times the oracle's CPU restatement of the
+reference's PyTorch path on the host cores (the reference is pure Python and is not on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(modes=(32, 32, 32), width=64, rational_order=(4, 4), n_layers=4, grid=128, batch_per_gpu=8)
+METRIC = "RFNO-3D 128^3 train samples/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data: random-spectrum turbulence (data/turbulence_dataset.py:155-194 of the reference)
+# ------------------------------------------------------------------------------------------------
+def turbulence_batch(batch: int, n: int, seed: int, device, kmax: float = 32.0) -> torch.Tensor:
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    k1 = torch.fft.fftfreq(n, 1.0 / n)
+    kz1 = torch.fft.rfftfreq(n, 1.0 / n)
+    kx, ky, kz = torch.meshgrid(k1, k1, kz1, indexing="ij")
+    kk = torch.stack([kx, ky, kz]).to(device)
+    kmag = torch.sqrt((kk ** 2).sum(0))
+    amp = torch.where((kmag >= 1) & (kmag <= kmax), kmag.clamp(min=1.0) ** (-5.0 / 6.0), torch.zeros_like(kmag))
+    dealias = ((kx.abs() < n / 3) & (ky.abs() < n / 3) & (kz.abs() < n / 3)).to(device)
+    out = []
+    for _ in range(batch):
+        noise = torch.randn(2, 3, n, n, n // 2 + 1, generator=g).to(device)
+        u_hat = torch.complex(noise[0], noise[1]) * amp
+        div = (kk * u_hat).sum(0) / (kmag ** 2).clamp(min=1.0)
+        u_hat = (u_hat - kk * div) * dealias                      # Leray projection + 2/3 mask
+        u_hat[:, 0, 0, 0] = 0                                     # zero mean flow
+        u = torch.fft.irfftn(u_hat, s=(n, n, n), dim=[-3, -2, -1])
+        out.append(u / u.std().clamp(min=1e-12))
+    return torch.stack(out).float()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm_load = sorted(sm)[len(sm) // 4:] if sm else []          # drop the idle quarter
+        return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference's PyTorch path, bounded sample
+# ------------------------------------------------------------------------------------------------
+CPU_OUT_SLICE = 8      # output channels of one layer evaluated per CPU step (of 64)
+
+
+def cpu_layer_slice_seconds(reps: int, warmup: int):
+    """One RationalFourierLayer fwd+bwd on ONE sample [1,64,128,128,128], restricted to CPU_OUT_SLICE of
+    the 64 output channels (the cost is dominated by the O*I*M polynomial evaluation and its backward,
+    which is linear in the number of output channels).  Returns per-rep seconds."""
+    from oracle import spectral_oracle as so
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1234)
+    C, modes, n = CFG["width"], CFG["modes"], CFG["grid"]
+    P, Q = so.init_rational_coeffs(CPU_OUT_SLICE, C, CFG["rational_order"])
+    P.requires_grad_(True)
+    Q.requires_grad_(True)
+    x = turbulence_batch(1, n, 42, "cpu")[:, :1].expand(1, C, n, n, n).contiguous().requires_grad_(True)
+    mx, my, mz = modes
+    mzh = mz // 2 + 1
+    mask = so.decay_mask(modes)
+
+    def step():
+        # same op sequence as the reference layer (rational_fourier.py:150-172) for a slice of out channels
+        x_ft = torch.fft.rfftn(x, dim=[-3, -2, -1])
+        R, _, _ = so.rational_transfer(P, Q, modes, 1e-6)
+        corner = x_ft[:, :, :mx, :my, :mzh]
+        mixed = torch.einsum("bixyz,oixyz->boxyz", corner, R.to(corner.dtype))
+        damped = mixed * mask
+        e0 = torch.sum(torch.abs(mixed) ** 2, dim=(-3, -2, -1), keepdim=True)
+        e1 = torch.sum(torch.abs(damped) ** 2, dim=(-3, -2, -1), keepdim=True)
+        damped = damped * torch.sqrt((e0 + 1e-6) / (e1 + 1e-6))
+        out_ft = torch.zeros(1, CPU_OUT_SLICE, n, n, n // 2 + 1, dtype=x_ft.dtype)
+        out_ft[:, :, :mx, :my, :mzh] = damped
+        out = torch.fft.irfftn(out_ft, s=(n, n, n), dim=[-3, -2, -1])
+        out.square().mean().backward()
+        x.grad = P.grad = Q.grad = None
+
+    times = []
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def cpu_samples_per_s(slice_seconds: float) -> float:
+    """Extrapolate the bounded sample to the full training step of one sample: 64/CPU_OUT_SLICE slices per
+    layer x 4 layers (pointwise conv / GELU / optimizer excluded, so this flatters the CPU)."""
+    per_sample = slice_seconds * (CFG["width"] / CPU_OUT_SLICE) * CFG["n_layers"]
+    return 1.0 / per_sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times = cpu_layer_slice_seconds(args.steps, args.warmup)
+    per = sum(times) / len(times)
+    val = cpu_samples_per_s(per)
+    sample = (f"{CPU_OUT_SLICE}/64 output channels of one RationalFourierLayer fwd+bwd on one [1,64,128,128,128] "
+              f"sample per step, scaled x{CFG['width'] // CPU_OUT_SLICE} x{CFG['n_layers']} layers; pointwise ops excluded")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus, "fp32"),
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int, precision: str) -> dict:
+    return {"workload": "RationalFourierOperator3D modes=(32,32,32) width=64 rational_order=(4,4) n_layers=4, "
+                        "128^3 synthetic random-spectrum turbulence, batch 8 per GPU, fwd+MSE+bwd+AdamW(lr 1e-3, wd 1e-4), AMP off",
+            "global_batch": CFG["batch_per_gpu"] * n_gpus, "grid": [CFG["grid"]] * 3, "parallelism": f"dp{n_gpus}",
+            "transform_precision": precision,
+            "l2": "per-step activations (4.3 GB per tensor) exceed the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch.distributed as dist
+    import pde_fluid_phi_b200 as pb
+    from pde_fluid_phi_b200 import _cabi
+    from pde_fluid_phi_b200.distributed import allreduce_gradients
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched through torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pb.load_library()
+
+    n, B = CFG["grid"], args.batch or CFG["batch_per_gpu"]
+    torch.manual_seed(1234)
+    model = pb.RationalFourierOperator3D(modes=CFG["modes"], width=CFG["width"], n_layers=CFG["n_layers"],
+                                         rational_order=CFG["rational_order"]).to(dev)
+    model.set_precision(args.precision)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    x = turbulence_batch(B, n, 42 + rank, dev)
+    y = turbulence_batch(B, n, 1042 + rank, dev)
+    hx, hy = x.cpu().pin_memory(), y.cpu().pin_memory()
+    h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(xd, yd):
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(model(xd), yd)
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(model.parameters(), world)
+        opt.step()
+        return loss
+
+    def step_e2e():
+        xd = hx.to(dev, non_blocking=True)
+        yd = hy.to(dev, non_blocking=True)
+        loss = step(xd, yd)
+        h_loss.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step(x, y)
+    # ---- timed region 1: inputs resident in HBM ---------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _cabi.profile(enable=True, reset=True)
+    total_ms = timed(lambda: step(x, y), args.steps)
+    prof = _cabi.profile_report(timed=True)
+    _cabi.profile(enable=False, reset=True)
+    clocks = sampler.stop() if rank == 0 else {}
+    # ---- timed region 2: end to end, host buffers ----------------------------------------------------
+    step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+    final_loss = float(h_loss)
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = B * world / (ms_per_step * 1e-3)
+        e2e_value = B * world / (e2e_ms / args.steps * 1e-3)
+        launches = sum(v[0] for v in prof.values())
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        # dominant kernel: the fused (z,y) analysis stage.  Algorithmic bytes per launch:
+        # read the [B*C, N, N, N] fp32 activation once + write the [B*C, N, my, mzh] complex intermediate.
+        C, (mx, my, mz) = CFG["width"], CFG["modes"]
+        mzh = mz // 2 + 1
+        names = {"fp32": "analysis_zy_kernel", "tf32": "analysis_zy_tc_kernel"}
+        dom = names[args.precision]
+        per_kernel = {k: {"launches": v[0], "ms_total": round(v[1], 3), "share_of_step": round(v[1] / total_ms, 4)}
+                      for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        roof = None
+        if dom in prof and prof[dom][1] > 0:
+            alg_bytes = 4.0 * B * C * n ** 3 + 8.0 * B * C * n * my * mzh
+            avg_ms = prof[dom][1] / prof[dom][0]
+            achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": which,
+                    "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(avg_ms, 4)}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            t = cpu_layer_slice_seconds(reps=2, warmup=1)
+            per = sum(t) / len(t)
+            cpu = {"value": cpu_samples_per_s(per), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{CPU_OUT_SLICE}/64 output channels of one RationalFourierLayer fwd+bwd on one "
+                             f"[1,64,128,128,128] sample ({per:.2f} s), scaled x{CFG['width'] // CPU_OUT_SLICE} x{CFG['n_layers']} "
+                             "layers; pointwise ops excluded"}
+        line = {"metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+                "data": "synthetic", "config": workload_config(world, args.precision),
+                "e2e": {"value": round(e2e_value, 3), "unit": "samples/s",
+                        "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 4, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "kernels": per_kernel, "final_loss": final_loss}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PDEPHI_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only; invalidates the metric)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+/*
+ * pdephi_b200.h -- C ABI of the B200-native spectral-convolution hot path of PDE-Fluid-Phi.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer on the
+ * plan's / current CUDA device unless stated otherwise; complex tensors are interleaved
+ * (re, im) float pairs, i.e. the memory layout of torch.complex64.  All functions are
+ * asynchronous on `stream` (a cudaStream_t passed as void*), never synchronise the host,
+ * never allocate persistent memory except the plan's constant twiddle tables, and return
+ * PDEPHI_OK or an error code; pdephi_last_error() gives the message of the calling thread's
+ * last failure.
+ *
+ * The reference is 100 % Python and has no FFI: the seam these entry points replace is the
+ * body of two nn.Module.forward methods and their autograd backward (paths below are relative
+ * to /root/reference/src/pde_fluid_phi):
+ *
+ *   RationalFourierLayer.forward   operators/rational_fourier.py:150-172
+ *   SpectralConv3D.forward         operators/spectral_layers.py:46-78
+ *
+ * Notation: B batch, I/O in/out channels, grid Nx,Ny,Nz (z contiguous), retained modes
+ * mx,my,mz, mzh = mz/2+1, M = mx*my*mzh.
+ */
+#ifndef PDEPHI_B200_H
+#define PDEPHI_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDEPHI_VERSION 100 /* 0.1.0 */
+
+typedef struct pdephi_plan_s* pdephi_plan_t;
+typedef void* pdephi_stream_t; /* cudaStream_t */
+
+enum pdephi_status {
+  PDEPHI_OK = 0,
+  PDEPHI_ERR_INVALID = 1,     /* bad argument (null pointer, size mismatch, modes > grid ...) */
+  PDEPHI_ERR_UNSUPPORTED = 2, /* valid but not implemented (e.g. rational order outside 2..4) */
+  PDEPHI_ERR_CUDA = 3,        /* a CUDA runtime call or launch failed */
+  PDEPHI_ERR_WORKSPACE = 4    /* workspace too small */
+};
+
+/* Arithmetic of the transform stages.  The channel mix, R(k) evaluation and projection always
+ * run in IEEE fp32 with the reference's rounding order (bit-identical P, Q, R). */
+enum pdephi_precision {
+  PDEPHI_PREC_FP32 = 0, /* fp32 FFMA contractions; parity gate 1e-5 */
+  PDEPHI_PREC_TF32 = 1  /* tcgen05 kind::tf32 contractions, fp32 accumulate; parity gate 2e-3 */
+};
+
+/* Which member of a transform pair.
+ *  analysis : FORWARD = pruned rfftn                      ADJOINT = backward of synthesis(FORWARD)
+ *  synthesis: FORWARD = zero-padded irfftn (1/N, C2R)     ADJOINT = backward of analysis(FORWARD) */
+enum pdephi_direction { PDEPHI_FORWARD = 0, PDEPHI_ADJOINT = 1 };
+
+int pdephi_version(void);
+const char* pdephi_last_error(void);
+
+/* ---- plan: constant DFT twiddle tables for one (grid, modes) pair on one device ------------- */
+int pdephi_plan_create(pdephi_plan_t* plan, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh);
+int pdephi_plan_destroy(pdephi_plan_t plan);
+/* bytes of scratch the two transforms need for `BC` (= batch*channels) volumes */
+size_t pdephi_plan_workspace_bytes(pdephi_plan_t plan, long long BC);
+
+/* ---- K1: pruned real-to-complex analysis transform ------------------------------------------
+ * replaces torch.fft.rfftn(x, dim=[-3,-2,-1])[:, :, :mx, :my, :mzh]
+ *          (rational_fourier.py:161 + :107, spectral_layers.py:59 + :63)
+ *   x [BC, Nx, Ny, Nz] float  ->  X [BC, mx, my, mzh] complex
+ * ADJOINT additionally multiplies by c_kz/(Nx*Ny*Nz): the backward of K3(FORWARD). */
+int pdephi_analysis_r2c(pdephi_plan_t plan, const float* x, float* X, long long BC, int direction,
+                        int precision, void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
+/* ---- K3: pruned complex-to-real synthesis transform, fused scaling and skip adds ------------
+ * replaces zeros_like/zeros + slice-assign + torch.fft.irfftn(out_ft, s=x.shape[-3:])
+ *          (rational_fourier.py:116-117,170, stability.py:85-86, spectral_layers.py:69-76)
+ *   Z [BC, mx, my, mzh] complex  ->  out [BC, Nx, Ny, Nz] float
+ *   out = S(Z * mode_scale[k] * row_scale[bc]) + addend0 + addend1
+ * mode_scale [M] (StabilityProjection decay mask), row_scale (element bc at
+ * row_scale[bc*row_scale_stride], the energy-conservation factor), addend0/1 [BC,Nx,Ny,Nz]
+ * (the block's "+ x_local + x", rational_fourier.py:271) may each be NULL.
+ * FORWARD has irfftn semantics (imaginary part of the kz=0 / Nyquist bins ignored, 1/N);
+ * ADJOINT is the plain unnormalised Re sum: the backward of K1(FORWARD). */
+int pdephi_synthesis_c2r(pdephi_plan_t plan, const float* Z, float* out, const float* addend0,
+                         const float* addend1, const float* mode_scale, const float* row_scale,
+                         long long row_scale_stride, long long BC, int direction, int precision,
+                         void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
+/* ---- K2: rational channel mix + StabilityProjection statistics ------------------------------
+ * replaces RationalFourierLayer.rational_multiply (rational_fourier.py:73-119) and the two
+ * energy reductions of StabilityProjection (stability.py:90-103).
+ *   X [B, I, M] complex, P [O, I, op,op,op], Q [O, I, oq,oq,oq] float,
+ *   monoP [TP, M], monoQ [TQ, M]: monomial tables kx^a ky^b kz^c in the reference's loop order
+ *   (rational_fourier.py:135-144), mask [M] decay mask (stability.py:40-57).
+ *   Y [B, O, M] complex   = sum_i R[o,i,k] X[b,i,k],  R = P(k) / (Q(k) + eps)  (unmasked, unscaled)
+ *   stats [B*O, 4] float  = { a = sum|Y|^2 + proj_eps, b = sum mask^2|Y|^2 + proj_eps, s = sqrt(a/b), 0 }
+ * The projected modes are Z = mask * s * Y; K3 applies that scaling on the fly. */
+int pdephi_rational_mix_fwd(const float* X, const float* P, const float* Q, const float* monoP,
+                            const float* monoQ, int order_p, int order_q, float eps, const float* mask,
+                            float proj_eps, float* Y, float* stats, int B, int I, int O, long long M,
+                            pdephi_stream_t stream);
+
+/* Backward of Z = mask*s*Y (stability.py:59-103) :  dZ [B*O, M] complex -> dY [B*O, M] complex */
+int pdephi_projection_bwd(const float* dZ, const float* Y, const float* mask, const float* stats,
+                          float* dY, long long rows, long long M, pdephi_stream_t stream);
+
+/* Backward of the rational mix: dX [B,I,M] complex, dP [O,I,op^3], dQ [O,I,oq^3] (entries with
+ * a+b+c >= order are written as zeros, as autograd does).  Deterministic two-stage reduction. */
+size_t pdephi_rational_mix_bwd_workspace_bytes(int order_p, int order_q, int I, int O, long long M);
+int pdephi_rational_mix_bwd(const float* X, const float* dY, const float* P, const float* Q,
+                            const float* monoP, const float* monoQ, int order_p, int order_q, float eps,
+                            float* dX, float* dP, float* dQ, int B, int I, int O, long long M,
+                            void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
+/* ---- K2': complex channel mix of SpectralConv3D (spectral_layers.py:66) ---------------------
+ *   W [O, I, mxy, mz] complex parameter; only kz < mzh is used (oracle convention 2).
+ *   Y[b,o,k] = sum_i W[o,i,k] X[b,i,k];   dX = sum_o conj(W) dY;   dW = sum_b conj(X) dY (0 for kz>=mzh) */
+int pdephi_complex_mix_fwd(const float* X, const float* W, float* Y, int B, int I, int O, long long mxy,
+                           int mzh, int mz, pdephi_stream_t stream);
+int pdephi_complex_mix_bwd(const float* X, const float* W, const float* dY, float* dX, float* dW, int B,
+                           int I, int O, long long mxy, int mzh, int mz, pdephi_stream_t stream);
+
+/* ---- per-kernel launch counters and CUDA-event timing (measurement support for bench.py) ------
+ * Launches are always counted.  With timing enabled every kernel launch is bracketed by a pair of
+ * cudaEvents on the launching stream; pdephi_profile_query synchronises on them and returns the
+ * launch count and summed device time since the last reset. */
+int pdephi_profile_enable(int on);
+int pdephi_profile_reset(void);
+int pdephi_profile_num_kernels(void);
+const char* pdephi_profile_kernel_name(int kernel_id);
+int pdephi_profile_query(int kernel_id, long long* launches, double* total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDEPHI_B200_H */

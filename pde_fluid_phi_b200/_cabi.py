@@ -1,0 +1,124 @@
+"""ctypes binding of libpdephi_b200.so (include/pdephi_b200.h).
+
+The library is the product: there is no Python / torch fallback.  If the shared object is
+missing the first use raises, loudly, with the build command.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpdephi_b200.so")
+_lib = None
+_lock = threading.RLock()
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = range(5)
+PREC_FP32, PREC_TF32 = 0, 1
+FORWARD, ADJOINT = 0, 1
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+
+# name -> (restype, argtypes); mirrors include/pdephi_b200.h one to one
+SIGNATURES = {
+    "pdephi_version": (c_int, []),
+    "pdephi_last_error": (c_char_p, []),
+    "pdephi_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "pdephi_plan_destroy": (c_int, [c_void_p]),
+    "pdephi_plan_workspace_bytes": (c_size_t, [c_void_p, c_longlong]),
+    "pdephi_analysis_r2c": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pdephi_synthesis_c2r": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                     c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pdephi_rational_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
+                                        c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p]),
+    "pdephi_projection_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p]),
+    "pdephi_rational_mix_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_longlong]),
+    "pdephi_rational_mix_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                        c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_size_t,
+                                        c_void_p]),
+    "pdephi_complex_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_void_p]),
+    "pdephi_complex_mix_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong,
+                                       c_int, c_int, c_void_p]),
+    "pdephi_profile_enable": (c_int, [c_int]),
+    "pdephi_profile_reset": (c_int, []),
+    "pdephi_profile_num_kernels": (c_int, []),
+    "pdephi_profile_kernel_name": (c_char_p, [c_int]),
+    "pdephi_profile_query": (c_int, [c_int, ctypes.POINTER(c_longlong), ctypes.POINTER(ctypes.c_double)]),
+}
+
+
+class PdephiError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(_LIB_PATH):
+                raise PdephiError(
+                    f"{_LIB_PATH} is missing: the CUDA library has not been built and there is no fallback path. "
+                    "Build it with `python -m pde_fluid_phi_b200.build` (needs nvcc, sm_100a).")
+            lib = ctypes.CDLL(_LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc == OK:
+        return
+    msg = load().pdephi_last_error().decode("utf-8", "replace")
+    if rc == ERR_INVALID:
+        raise ValueError(f"pdephi {what}: {msg}")
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(f"pdephi {what}: {msg}")
+    raise PdephiError(f"pdephi {what} failed (code {rc}): {msg}")
+
+
+_plans = {}
+
+
+def get_plan(device_index: int, grid, modes_h):
+    """Cached plan handle for (device, grid, (mx,my,mzh)); twiddle tables live for the process lifetime."""
+    key = (int(device_index), tuple(int(v) for v in grid), tuple(int(v) for v in modes_h))
+    h = _plans.get(key)
+    if h is None:
+        with _lock:
+            h = _plans.get(key)
+            if h is None:
+                handle = c_void_p()
+                check(load().pdephi_plan_create(ctypes.byref(handle), key[0], *key[1], *key[2]), "plan_create")
+                h = handle
+                _plans[key] = h
+    return h
+
+
+def profile(enable: bool = True, reset: bool = True):
+    lib = load()
+    if reset:
+        lib.pdephi_profile_reset()
+    lib.pdephi_profile_enable(1 if enable else 0)
+
+
+def profile_report(timed: bool = True):
+    """{kernel name: (launches, total device ms)} since the last reset (synchronises on recorded events)."""
+    lib = load()
+    out = {}
+    for i in range(lib.pdephi_profile_num_kernels()):
+        n = c_longlong(0)
+        ms = ctypes.c_double(0.0)
+        check(lib.pdephi_profile_query(i, ctypes.byref(n), ctypes.byref(ms) if timed else None), "profile_query")
+        if n.value:
+            out[lib.pdephi_profile_kernel_name(i).decode()] = (n.value, ms.value)
+    return out

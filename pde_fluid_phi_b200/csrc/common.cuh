@@ -1,0 +1,96 @@
+// Shared helpers for the pdephi_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pdephi_b200.h"
+
+namespace pdephi {
+
+// thread-local error message returned by pdephi_last_error()
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+
+#define PDEPHI_CUDA(call)                                                                         \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return ::pdephi::fail(PDEPHI_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                  \
+  } while (0)
+
+#define PDEPHI_LAUNCH_CHECK(name)                                                                 \
+  do {                                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess)                                                                       \
+      return ::pdephi::fail(PDEPHI_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define PDEPHI_REQUIRE(cond, ...)                                   \
+  do {                                                              \
+    if (!(cond)) return ::pdephi::fail(PDEPHI_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+struct Plan {
+  int device;
+  int Nx, Ny, Nz, mx, my, mzh;
+  // e^{-i theta} tables for the analysis direction, e^{+i theta} for synthesis; (re, im) pairs.
+  float2* az[2];  // [Nz][mzh]  analysis z twiddles; [1] carries c_kz/(NxNyNz)
+  float2* ay;     // [Ny][my]
+  float2* ax;     // [Nx][mx]
+  float2* sx;     // [mx][Nx]
+  float2* sy;     // [my][Ny]
+  float2* sz[2];  // [mzh][Nz]  synthesis z twiddles (w cos, w sin); [0] carries c_kz/(NxNyNz)
+  void* arena;    // one allocation backing all tables
+  int num_sms;
+  size_t smem_optin;
+};
+
+enum KernelId {
+  K_ANALYSIS_ZY = 0, K_ANALYSIS_X, K_SYNTHESIS_X, K_SYNTHESIS_ZY, K_ANALYSIS_ZY_TC, K_SYNTHESIS_ZY_TC,
+  K_RATIONAL_MIX, K_RATIONAL_MIX_T, K_PROJ_STATS, K_PROJ_BWD, K_RATIONAL_DPQ, K_DPQ_REDUCE,
+  K_COMPLEX_MIX, K_COMPLEX_MIX_T, K_COMPLEX_DW, K_COUNT
+};
+void prof_begin(int id, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+struct ProfScope {
+  int id; cudaStream_t st;
+  ProfScope(int i, cudaStream_t s) : id(i), st(s) { prof_begin(id, st); }
+  ~ProfScope() { prof_end(id, st); }
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ void cfma(float2& acc, float2 a, float2 b) {
+  acc.x = fmaf(a.x, b.x, acc.x);
+  acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y);
+  acc.y = fmaf(a.y, b.x, acc.y);
+}
+
+// fixed-order block reduction of a double; result valid in thread 0 (and broadcast through smem)
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* red /* [THREADS/32] */) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) t += red[i];
+    red[0] = t;
+  }
+  __syncthreads();
+  t = red[0];
+  return t;
+}
+
+}  // namespace pdephi

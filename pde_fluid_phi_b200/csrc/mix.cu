@@ -1,0 +1,598 @@
+// K2: per-mode channel mix kernels.
+//
+//  * rational mix (RationalFourierLayer.rational_multiply, rational_fourier.py:73-119): the real
+//    transfer function R[o,i,k] = P(k)/(Q(k)+eps) is evaluated on the fly, in registers, with the
+//    reference's exact rounding order (one rounded product and one rounded add per monomial, IEEE
+//    division; rational_fourier.py:135-146,101,104), so P, Q and R are bit-identical to the
+//    reference's and the 285 MB R tensor is never materialised.
+//  * StabilityProjection statistics and backward (stability.py:59-103).
+//  * complex mix of SpectralConv3D (spectral_layers.py:66).
+//
+// All reductions are fixed-order (no float atomics): the reference's tests require bit-repeatable
+// losses (tests/test_comprehensive.py:575-647).
+#include "common.cuh"
+
+namespace pdephi {
+
+constexpr int MAX_T = 20;  // monomials of order 4
+struct MonoOffsets {
+  int p[MAX_T];
+  int q[MAX_T];
+};
+static inline int tri(int ord) { return ord * (ord + 1) * (ord + 2) / 6; }
+template <int ORD>
+struct Tri {
+  static constexpr int T = ORD * (ORD + 1) * (ORD + 2) / 6;
+  static constexpr int TP4 = (T + 3) / 4 * 4;
+};
+static void fill_offsets(int ord, int* off) {
+  int n = 0;
+  for (int a = 0; a < ord; ++a)
+    for (int b = 0; b < ord; ++b)
+      for (int c = 0; c < ord; ++c)
+        if (a + b + c < ord) off[n++] = (a * ord + b) * ord + c;
+}
+
+// R = P/(Q+eps) with the reference's stepwise fp32 rounding.  cp/cq: coefficients, mp/mq: monomials.
+template <int TPN, int TQN>
+__device__ __forceinline__ float eval_R(const float* cp, const float* cq, const float* mp, const float* mq, float eps,
+                                        float* qe_out) {
+  float p = 0.f, q = 0.f;
+#pragma unroll
+  for (int t = 0; t < TPN; ++t) p = __fadd_rn(p, __fmul_rn(cp[t], mp[t]));
+#pragma unroll
+  for (int t = 0; t < TQN; ++t) q = __fadd_rn(q, __fmul_rn(cq[t], mq[t]));
+  const float qe = __fadd_rn(q, eps);
+  if (qe_out) *qe_out = qe;
+  return __fdiv_rn(p, qe);
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[b][u][k] = sum_v R(u,v)[k] * in[b][v][k]     (TR=false: (o,i)=(u,v);  TR=true: (o,i)=(v,u))
+// thread = one mode k (coalesced along k), UT output channels x BT batch entries per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int MIX_THREADS = 128;
+constexpr int UT = 4;
+constexpr int BT = 8;
+
+template <int OP, int OQ, bool TR>
+__global__ void __launch_bounds__(MIX_THREADS)
+rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float* __restrict__ P,
+                    const float* __restrict__ Q, const float* __restrict__ monoP, const float* __restrict__ monoQ,
+                    float eps, int B, int U, int V, long long M, MonoOffsets offs) {
+  constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
+  constexpr int TP4 = Tri<OP>::TP4, TQ4 = Tri<OQ>::TP4;
+  extern __shared__ __align__(16) float smem[];
+  float* cPs = smem;                            // [UT][V][TP4]
+  float* cQs = smem + (size_t)UT * V * TP4;     // [UT][V][TQ4]
+  const int u0 = blockIdx.y * UT;
+  const int O = TR ? V : U, I = TR ? U : V;
+  (void)O;
+  for (int idx = threadIdx.x; idx < UT * V * TP4; idx += MIX_THREADS) {
+    const int t = idx % TP4, uv = idx / TP4, v = uv % V, ul = uv / V;
+    const int u = min(u0 + ul, U - 1);
+    const int o = TR ? v : u, i = TR ? u : v;
+    cPs[idx] = (t < TPN) ? __ldg(P + ((size_t)o * I + i) * (OP * OP * OP) + offs.p[t]) : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < UT * V * TQ4; idx += MIX_THREADS) {
+    const int t = idx % TQ4, uv = idx / TQ4, v = uv % V, ul = uv / V;
+    const int u = min(u0 + ul, U - 1);
+    const int o = TR ? v : u, i = TR ? u : v;
+    cQs[idx] = (t < TQN) ? __ldg(Q + ((size_t)o * I + i) * (OQ * OQ * OQ) + offs.q[t]) : 0.f;
+  }
+  __syncthreads();
+
+  const long long k = (long long)blockIdx.x * MIX_THREADS + threadIdx.x;
+  const long long kc = k < M ? k : M - 1;
+  float mp[TP4], mqs[(OP == OQ) ? 1 : TQ4];
+#pragma unroll
+  for (int t = 0; t < TP4; ++t) mp[t] = (t < TPN) ? __ldg(monoP + (size_t)t * M + kc) : 0.f;
+  if (OP != OQ) {
+#pragma unroll
+    for (int t = 0; t < TQ4; ++t) mqs[t] = (t < TQN) ? __ldg(monoQ + (size_t)t * M + kc) : 0.f;
+  }
+  const float* mq = (OP == OQ) ? mp : mqs;
+
+  for (int b0 = 0; b0 < B; b0 += BT) {
+    float2 acc[UT][BT];
+#pragma unroll
+    for (int ul = 0; ul < UT; ++ul)
+#pragma unroll
+      for (int j = 0; j < BT; ++j) acc[ul][j] = make_float2(0.f, 0.f);
+    for (int v = 0; v < V; ++v) {
+      float2 xin[BT];
+#pragma unroll
+      for (int j = 0; j < BT; ++j)
+        xin[j] = (b0 + j < B) ? __ldg(in + ((size_t)(b0 + j) * V + v) * M + kc) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int ul = 0; ul < UT; ++ul) {
+        float cp[TP4], cq[TQ4];
+        const float4* p4 = reinterpret_cast<const float4*>(cPs + ((size_t)ul * V + v) * TP4);
+        const float4* q4 = reinterpret_cast<const float4*>(cQs + ((size_t)ul * V + v) * TQ4);
+#pragma unroll
+        for (int t = 0; t < TP4 / 4; ++t) {
+          const float4 c = p4[t];
+          cp[4 * t] = c.x; cp[4 * t + 1] = c.y; cp[4 * t + 2] = c.z; cp[4 * t + 3] = c.w;
+        }
+#pragma unroll
+        for (int t = 0; t < TQ4 / 4; ++t) {
+          const float4 c = q4[t];
+          cq[4 * t] = c.x; cq[4 * t + 1] = c.y; cq[4 * t + 2] = c.z; cq[4 * t + 3] = c.w;
+        }
+        const float R = eval_R<TPN, TQN>(cp, cq, mp, mq, eps, nullptr);
+#pragma unroll
+        for (int j = 0; j < BT; ++j) {
+          acc[ul][j].x = fmaf(R, xin[j].x, acc[ul][j].x);
+          acc[ul][j].y = fmaf(R, xin[j].y, acc[ul][j].y);
+        }
+      }
+    }
+    if (k < M) {
+#pragma unroll
+      for (int ul = 0; ul < UT; ++ul)
+#pragma unroll
+        for (int j = 0; j < BT; ++j)
+          if (u0 + ul < U && b0 + j < B) out[((size_t)(b0 + j) * U + u0 + ul) * M + k] = acc[ul][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// StabilityProjection statistics: one CTA per (b,o) row.  stats = {a, b, s, 0}
+// ---------------------------------------------------------------------------------------------
+constexpr int ROW_THREADS = 256;
+__global__ void __launch_bounds__(ROW_THREADS)
+projection_stats_kernel(const float2* __restrict__ Y, const float* __restrict__ mask, float proj_eps,
+                        float* __restrict__ stats, long long M) {
+  __shared__ double red[ROW_THREADS / 32];
+  const size_t row = blockIdx.x;
+  const float2* y = Y + row * (size_t)M;
+  float e0 = 0.f, e1 = 0.f;
+  double E0 = 0.0, E1 = 0.0;
+  int n = 0;
+  for (long long k = threadIdx.x; k < M; k += ROW_THREADS) {
+    const float2 v = __ldg(y + k);
+    const float m = __ldg(mask + k);
+    const float a2 = fmaf(v.x, v.x, v.y * v.y);
+    e0 += a2;
+    e1 = fmaf(m * m, a2, e1);
+    if (++n == 64) { E0 += e0; E1 += e1; e0 = e1 = 0.f; n = 0; }  // short fp32 runs, fp64 carry
+  }
+  E0 += e0;
+  E1 += e1;
+  E0 = block_sum<ROW_THREADS>(E0, red);
+  E1 = block_sum<ROW_THREADS>(E1, red);
+  if (threadIdx.x == 0) {
+    const float a = (float)E0 + proj_eps, b = (float)E1 + proj_eps;
+    stats[row * 4 + 0] = a;
+    stats[row * 4 + 1] = b;
+    stats[row * 4 + 2] = sqrtf(a / b);
+    stats[row * 4 + 3] = 0.f;
+  }
+}
+
+// backward of Z = mask*s*Y:  dY = m s dZ + G s (1/a - m^2/b) Y,  G = sum_k Re(conj(dZ) m Y)
+__global__ void __launch_bounds__(ROW_THREADS)
+projection_bwd_kernel(const float2* __restrict__ dZ, const float2* __restrict__ Y, const float* __restrict__ mask,
+                      const float* __restrict__ stats, float2* __restrict__ dY, long long M) {
+  __shared__ double red[ROW_THREADS / 32];
+  const size_t row = blockIdx.x;
+  const float2* y = Y + row * (size_t)M;
+  const float2* dz = dZ + row * (size_t)M;
+  float g = 0.f;
+  double Gd = 0.0;
+  int n = 0;
+  for (long long k = threadIdx.x; k < M; k += ROW_THREADS) {
+    const float2 v = __ldg(y + k), d = __ldg(dz + k);
+    g = fmaf(__ldg(mask + k), fmaf(d.x, v.x, d.y * v.y), g);
+    if (++n == 64) { Gd += g; g = 0.f; n = 0; }
+  }
+  Gd += g;
+  Gd = block_sum<ROW_THREADS>(Gd, red);
+  const float a = stats[row * 4 + 0], b = stats[row * 4 + 1], s = stats[row * 4 + 2];
+  const float Gs = (float)Gd * s;
+  const float ia = 1.f / a, ib = 1.f / b;
+  float2* o = dY + row * (size_t)M;
+  for (long long k = threadIdx.x; k < M; k += ROW_THREADS) {
+    const float2 v = __ldg(y + k), d = __ldg(dz + k);
+    const float m = __ldg(mask + k);
+    const float c0 = m * s, c1 = Gs * (ia - m * m * ib);
+    o[k] = make_float2(fmaf(c0, d.x, c1 * v.x), fmaf(c0, d.y, c1 * v.y));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dP / dQ: thread = one (o,i) pair, coefficients and 2T accumulators in registers, loop over a
+// k range; X / dY / monomial tiles staged through shared memory.  Stage 1 writes per-k-split
+// partials, stage 2 sums them in fixed order and scatters into the [O,I,ord^3] gradients.
+//   dR[o,i,k] = sum_b Re(conj(X[b,i,k]) dY[b,o,k]);  g = dR/Qe;  dP_t += g mono_t;  dQ_t += -g R mono_t
+// ---------------------------------------------------------------------------------------------
+constexpr int DPQ_THREADS = 256;
+constexpr int KT = 8;
+constexpr int KTP = KT + 1;
+
+template <int OP, int OQ>
+__global__ void __launch_bounds__(DPQ_THREADS)
+rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, const float* __restrict__ P,
+                    const float* __restrict__ Q, const float* __restrict__ monoP, const float* __restrict__ monoQ,
+                    float eps, float* __restrict__ partial, int B, int I, int O, long long M, long long kchunk,
+                    int nOmax, MonoOffsets offs) {
+  constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
+  extern __shared__ __align__(16) float smem[];
+  float2* Xs = reinterpret_cast<float2*>(smem);                 // [BT][I][KTP]
+  float2* Ys = Xs + (size_t)BT * I * KTP;                        // [BT][nOmax][KTP]
+  float* mPs = reinterpret_cast<float*>(Ys + (size_t)BT * nOmax * KTP);  // [TPN][KT]
+  float* mQs = mPs + TPN * KT;                                   // [TQN][KT]
+
+  const long long npairs = (long long)O * I;
+  const long long q0 = (long long)blockIdx.x * DPQ_THREADS;
+  const long long qraw = q0 + threadIdx.x;
+  const bool valid = qraw < npairs;
+  const long long q = valid ? qraw : npairs - 1;
+  const int o = (int)(q / I), i = (int)(q % I);
+  const int o_lo = (int)(q0 / I);
+  const int o_hi = (int)min((long long)O - 1, (q0 + DPQ_THREADS - 1) / I);
+  const int nO = o_hi - o_lo + 1;
+
+  float cp[TPN], cq[TQN], ap[TPN], aq[TQN];
+#pragma unroll
+  for (int t = 0; t < TPN; ++t) { cp[t] = __ldg(P + (size_t)q * (OP * OP * OP) + offs.p[t]); ap[t] = 0.f; }
+#pragma unroll
+  for (int t = 0; t < TQN; ++t) { cq[t] = __ldg(Q + (size_t)q * (OQ * OQ * OQ) + offs.q[t]); aq[t] = 0.f; }
+
+  const long long k_lo = (long long)blockIdx.y * kchunk;
+  const long long k_hi = min(M, k_lo + kchunk);
+  for (long long k0 = k_lo; k0 < k_hi; k0 += KT) {
+    float dR[KT];
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) dR[kk] = 0.f;
+    for (int b0 = 0; b0 < B; b0 += BT) {
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < BT * I * KT; idx += DPQ_THREADS) {
+        const int kk = idx % KT, r = idx / KT, ii = r % I, bb = r / I;
+        const long long k = k0 + kk;
+        float2 v = make_float2(0.f, 0.f);
+        if (b0 + bb < B && k < k_hi) v = __ldg(X + ((size_t)(b0 + bb) * I + ii) * M + k);
+        Xs[(size_t)r * KTP + kk] = v;
+      }
+      for (int idx = threadIdx.x; idx < BT * nO * KT; idx += DPQ_THREADS) {
+        const int kk = idx % KT, r = idx / KT, oo = r % nO, bb = r / nO;
+        const long long k = k0 + kk;
+        float2 v = make_float2(0.f, 0.f);
+        if (b0 + bb < B && k < k_hi) v = __ldg(dY + ((size_t)(b0 + bb) * O + o_lo + oo) * M + k);
+        Ys[((size_t)bb * nOmax + oo) * KTP + kk] = v;
+      }
+      if (b0 == 0) {
+        for (int idx = threadIdx.x; idx < (TPN + TQN) * KT; idx += DPQ_THREADS) {
+          const int kk = idx % KT, t = idx / KT;
+          const long long k = min(k0 + kk, M - 1);
+          if (t < TPN) mPs[t * KT + kk] = __ldg(monoP + (size_t)t * M + k);
+          else mQs[(t - TPN) * KT + kk] = __ldg(monoQ + (size_t)(t - TPN) * M + k);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int bb = 0; bb < BT; ++bb) {
+        const float2* xr = Xs + ((size_t)bb * I + i) * KTP;
+        const float2* yr = Ys + ((size_t)bb * nOmax + (o - o_lo)) * KTP;
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+          const float2 xv = xr[kk], yv = yr[kk];
+          dR[kk] = fmaf(xv.x, yv.x, dR[kk]);
+          dR[kk] = fmaf(xv.y, yv.y, dR[kk]);
+        }
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      if (k0 + kk < k_hi) {
+        float mp[TPN], mq[TQN];
+#pragma unroll
+        for (int t = 0; t < TPN; ++t) mp[t] = mPs[t * KT + kk];
+#pragma unroll
+        for (int t = 0; t < TQN; ++t) mq[t] = mQs[t * KT + kk];
+        float qe;
+        const float R = eval_R<TPN, TQN>(cp, cq, mp, mq, eps, &qe);
+        const float g = __fdiv_rn(dR[kk], qe);
+        const float h = -g * R;
+#pragma unroll
+        for (int t = 0; t < TPN; ++t) ap[t] = fmaf(g, mp[t], ap[t]);
+#pragma unroll
+        for (int t = 0; t < TQN; ++t) aq[t] = fmaf(h, mq[t], aq[t]);
+      }
+    }
+  }
+  if (valid) {
+    float* dst = partial + ((size_t)blockIdx.y * npairs + q) * (TPN + TQN);
+#pragma unroll
+    for (int t = 0; t < TPN; ++t) dst[t] = ap[t];
+#pragma unroll
+    for (int t = 0; t < TQN; ++t) dst[TPN + t] = aq[t];
+  }
+}
+
+__global__ void dpq_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dP, float* __restrict__ dQ,
+                                  int KS, long long npairs, int op, int oq, int TPN, int TQN, MonoOffsets offs) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= npairs) return;
+  const int op3 = op * op * op, oq3 = oq * oq * oq;
+  float* p = dP + (size_t)q * op3;
+  float* r = dQ + (size_t)q * oq3;
+  for (int e = 0; e < op3; ++e) p[e] = 0.f;
+  for (int e = 0; e < oq3; ++e) r[e] = 0.f;
+  for (int t = 0; t < TPN + TQN; ++t) {
+    double s = 0.0;
+    for (int ks = 0; ks < KS; ++ks) s += (double)partial[((size_t)ks * npairs + q) * (TPN + TQN) + t];
+    if (t < TPN) p[offs.p[t]] = (float)s;
+    else r[offs.q[t - TPN]] = (float)s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// complex mix (SpectralConv3D).  W [O][I][mxy][mz] complex, only kz < mzh used.
+//   fwd  : out[b][u][k] = sum_v W(u,v)[k] in[b][v][k]            (TR=false, CONJ=false)
+//   dX   : out[b][u][k] = sum_v conj(W(v,u)[k]) in[b][v][k]      (TR=true,  CONJ=true)
+// ---------------------------------------------------------------------------------------------
+template <bool TR>
+__global__ void __launch_bounds__(MIX_THREADS)
+complex_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ W, int B, int U,
+                   int V, long long mxy, int mzh, int mz) {
+  const long long M = mxy * mzh;
+  const long long k = (long long)blockIdx.x * MIX_THREADS + threadIdx.x;
+  const long long kc = k < M ? k : M - 1;
+  const long long kxy = kc / mzh;
+  const int kz = (int)(kc - kxy * mzh);
+  const size_t wk = (size_t)kxy * mz + kz;
+  const size_t Wm = (size_t)mxy * mz;
+  const int u0 = blockIdx.y * UT;
+  const int I = TR ? U : V;
+  for (int b0 = 0; b0 < B; b0 += BT) {
+    float2 acc[UT][BT];
+#pragma unroll
+    for (int ul = 0; ul < UT; ++ul)
+#pragma unroll
+      for (int j = 0; j < BT; ++j) acc[ul][j] = make_float2(0.f, 0.f);
+    for (int v = 0; v < V; ++v) {
+      float2 xin[BT];
+#pragma unroll
+      for (int j = 0; j < BT; ++j)
+        xin[j] = (b0 + j < B) ? __ldg(in + ((size_t)(b0 + j) * V + v) * M + kc) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int ul = 0; ul < UT; ++ul) {
+        const int u = min(u0 + ul, U - 1);
+        const int o = TR ? v : u, i = TR ? u : v;
+        float2 w = __ldg(W + ((size_t)o * I + i) * Wm + wk);
+        if (TR) w.y = -w.y;
+#pragma unroll
+        for (int j = 0; j < BT; ++j) cfma(acc[ul][j], w, xin[j]);
+      }
+    }
+    if (k < M) {
+#pragma unroll
+      for (int ul = 0; ul < UT; ++ul)
+#pragma unroll
+        for (int j = 0; j < BT; ++j)
+          if (u0 + ul < U && b0 + j < B) out[((size_t)(b0 + j) * U + u0 + ul) * M + k] = acc[ul][j];
+    }
+  }
+}
+
+// dW[o][i][kxy][kz] = sum_b conj(X[b,i,k]) dY[b,o,k] for kz < mzh, 0 for kz >= mzh.
+constexpr int WT = 4;
+__global__ void __launch_bounds__(MIX_THREADS)
+complex_dw_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, float2* __restrict__ dW, int B, int I,
+                  int O, long long mxy, int mzh, int mz) {
+  const long long Mw = mxy * mz, M = mxy * mzh;
+  const long long kw = (long long)blockIdx.x * MIX_THREADS + threadIdx.x;
+  if (kw >= Mw) return;
+  const long long kxy = kw / mz;
+  const int kz = (int)(kw - kxy * mz);
+  const int o0 = blockIdx.y * WT, i0 = blockIdx.z * WT;
+  float2 acc[WT][WT];
+#pragma unroll
+  for (int a = 0; a < WT; ++a)
+#pragma unroll
+    for (int c = 0; c < WT; ++c) acc[a][c] = make_float2(0.f, 0.f);
+  if (kz < mzh) {
+    const long long k = kxy * mzh + kz;
+    for (int b = 0; b < B; ++b) {
+      float2 xv[WT], yv[WT];
+#pragma unroll
+      for (int c = 0; c < WT; ++c) {
+        xv[c] = __ldg(X + ((size_t)b * I + min(i0 + c, I - 1)) * M + k);
+        xv[c].y = -xv[c].y;
+      }
+#pragma unroll
+      for (int a = 0; a < WT; ++a) yv[a] = __ldg(dY + ((size_t)b * O + min(o0 + a, O - 1)) * M + k);
+#pragma unroll
+      for (int a = 0; a < WT; ++a)
+#pragma unroll
+        for (int c = 0; c < WT; ++c) cfma(acc[a][c], xv[c], yv[a]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < WT; ++a)
+#pragma unroll
+    for (int c = 0; c < WT; ++c)
+      if (o0 + a < O && i0 + c < I) dW[((size_t)(o0 + a) * I + i0 + c) * Mw + kw] = acc[a][c];
+}
+
+// ------------------------------- host-side dispatch -------------------------------------------
+template <int OP, int OQ, bool TR>
+static int launch_mix(const float2* in, float2* out, const float* P, const float* Q, const float* monoP,
+                      const float* monoQ, float eps, int B, int U, int V, long long M, const MonoOffsets& offs,
+                      cudaStream_t st) {
+  const size_t smem = (size_t)UT * V * (Tri<OP>::TP4 + Tri<OQ>::TP4) * sizeof(float);
+  auto k = rational_mix_kernel<OP, OQ, TR>;
+  if (smem > 48 * 1024) PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (U + UT - 1) / UT);
+  {
+    ProfScope ps(TR ? K_RATIONAL_MIX_T : K_RATIONAL_MIX, st);
+    k<<<grid, MIX_THREADS, smem, st>>>(in, out, P, Q, monoP, monoQ, eps, B, U, V, M, offs);
+  }
+  PDEPHI_LAUNCH_CHECK("rational_mix_kernel");
+  return PDEPHI_OK;
+}
+
+template <bool TR>
+static int dispatch_mix(int op, int oq, const float2* in, float2* out, const float* P, const float* Q,
+                        const float* monoP, const float* monoQ, float eps, int B, int U, int V, long long M,
+                        cudaStream_t st) {
+  MonoOffsets offs;
+  memset(&offs, 0, sizeof(offs));
+  fill_offsets(op, offs.p);
+  fill_offsets(oq, offs.q);
+#define CASE(a, b) \
+  if (op == a && oq == b) return launch_mix<a, b, TR>(in, out, P, Q, monoP, monoQ, eps, B, U, V, M, offs, st);
+  CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 2) CASE(3, 3) CASE(3, 4) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+#undef CASE
+  return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) outside the supported range 2..4", op, oq);
+}
+
+static void dpq_geometry(int I, int O, long long M, int* pair_blocks, int* KS, long long* kchunk, int* nOmax) {
+  const long long npairs = (long long)O * I;
+  *pair_blocks = (int)((npairs + DPQ_THREADS - 1) / DPQ_THREADS);
+  long long ks = (4 * 148 + *pair_blocks - 1) / *pair_blocks;
+  const long long max_ks = (M + 63) / 64;
+  if (ks > max_ks) ks = max_ks;
+  if (ks < 1) ks = 1;
+  long long chunk = (M + ks - 1) / ks;
+  chunk = (chunk + KT - 1) / KT * KT;
+  *KS = (int)((M + chunk - 1) / chunk);
+  *kchunk = chunk;
+  *nOmax = (DPQ_THREADS - 1) / I + 2;
+  if (*nOmax > O) *nOmax = O;
+}
+
+template <int OP, int OQ>
+static int launch_dpq(const float2* X, const float2* dY, const float* P, const float* Q, const float* monoP,
+                      const float* monoQ, float eps, float* dP, float* dQ, int B, int I, int O, long long M,
+                      float* partial, const MonoOffsets& offs, cudaStream_t st) {
+  int pair_blocks, KS, nOmax;
+  long long kchunk;
+  dpq_geometry(I, O, M, &pair_blocks, &KS, &kchunk, &nOmax);
+  constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
+  const size_t smem = ((size_t)BT * I * KTP + (size_t)BT * nOmax * KTP) * sizeof(float2) + (TPN + TQN) * KT * sizeof(float);
+  auto k = rational_dpq_kernel<OP, OQ>;
+  if (smem > 200 * 1024) return fail(PDEPHI_ERR_UNSUPPORTED, "rational_mix_bwd: %d input channels exceed shared memory", I);
+  if (smem > 48 * 1024) PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope ps(K_RATIONAL_DPQ, st);
+    k<<<dim3(pair_blocks, KS), DPQ_THREADS, smem, st>>>(X, dY, P, Q, monoP, monoQ, eps, partial, B, I, O, M, kchunk,
+                                                       nOmax, offs);
+  }
+  PDEPHI_LAUNCH_CHECK("rational_dpq_kernel");
+  const long long npairs = (long long)O * I;
+  {
+    ProfScope ps(K_DPQ_REDUCE, st);
+    dpq_reduce_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, st>>>(partial, dP, dQ, KS, npairs, OP, OQ, TPN, TQN, offs);
+  }
+  PDEPHI_LAUNCH_CHECK("dpq_reduce_kernel");
+  return PDEPHI_OK;
+}
+
+}  // namespace pdephi
+
+using namespace pdephi;
+
+extern "C" int pdephi_rational_mix_fwd(const float* X, const float* P, const float* Q, const float* monoP,
+                                       const float* monoQ, int order_p, int order_q, float eps, const float* mask,
+                                       float proj_eps, float* Y, float* stats, int B, int I, int O, long long M,
+                                       pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(X && P && Q && monoP && monoQ && mask && Y && stats, "rational_mix_fwd: null pointer");
+  PDEPHI_REQUIRE(B > 0 && I > 0 && O > 0 && M > 0, "rational_mix_fwd: non-positive size");
+  PDEPHI_REQUIRE((long long)B * O <= 0x7fffffffLL, "rational_mix_fwd: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = dispatch_mix<false>(order_p, order_q, (const float2*)X, (float2*)Y, P, Q, monoP, monoQ, eps, B, O, I, M, st);
+  if (rc) return rc;
+  {
+    ProfScope ps(K_PROJ_STATS, st);
+    projection_stats_kernel<<<(unsigned)(B * O), ROW_THREADS, 0, st>>>((const float2*)Y, mask, proj_eps, stats, M);
+  }
+  PDEPHI_LAUNCH_CHECK("projection_stats_kernel");
+  return PDEPHI_OK;
+}
+
+extern "C" int pdephi_projection_bwd(const float* dZ, const float* Y, const float* mask, const float* stats, float* dY,
+                                     long long rows, long long M, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(dZ && Y && mask && stats && dY, "projection_bwd: null pointer");
+  PDEPHI_REQUIRE(rows > 0 && M > 0 && rows <= 0x7fffffffLL, "projection_bwd: bad size");
+  {
+    ProfScope ps(K_PROJ_BWD, (cudaStream_t)stream);
+    projection_bwd_kernel<<<(unsigned)rows, ROW_THREADS, 0, (cudaStream_t)stream>>>((const float2*)dZ, (const float2*)Y,
+                                                                                     mask, stats, (float2*)dY, M);
+  }
+  PDEPHI_LAUNCH_CHECK("projection_bwd_kernel");
+  return PDEPHI_OK;
+}
+
+extern "C" size_t pdephi_rational_mix_bwd_workspace_bytes(int order_p, int order_q, int I, int O, long long M) {
+  if (I <= 0 || O <= 0 || M <= 0 || order_p < 1 || order_q < 1) return 0;
+  int pair_blocks, KS, nOmax;
+  long long kchunk;
+  dpq_geometry(I, O, M, &pair_blocks, &KS, &kchunk, &nOmax);
+  return align_up((size_t)KS * O * I * (tri(order_p) + tri(order_q)) * sizeof(float), 256);
+}
+
+extern "C" int pdephi_rational_mix_bwd(const float* X, const float* dY, const float* P, const float* Q,
+                                       const float* monoP, const float* monoQ, int order_p, int order_q, float eps,
+                                       float* dX, float* dP, float* dQ, int B, int I, int O, long long M,
+                                       void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(X && dY && P && Q && monoP && monoQ && dX && dP && dQ, "rational_mix_bwd: null pointer");
+  PDEPHI_REQUIRE(B > 0 && I > 0 && O > 0 && M > 0, "rational_mix_bwd: non-positive size");
+  const size_t need = pdephi_rational_mix_bwd_workspace_bytes(order_p, order_q, I, O, M);
+  if (!workspace || workspace_bytes < need)
+    return fail(PDEPHI_ERR_WORKSPACE, "rational_mix_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = dispatch_mix<true>(order_p, order_q, (const float2*)dY, (float2*)dX, P, Q, monoP, monoQ, eps, B, I, O, M, st);
+  if (rc) return rc;
+  MonoOffsets offs;
+  memset(&offs, 0, sizeof(offs));
+  fill_offsets(order_p, offs.p);
+  fill_offsets(order_q, offs.q);
+#define CASE(a, b)                                                                                          \
+  if (order_p == a && order_q == b)                                                                         \
+    return launch_dpq<a, b>((const float2*)X, (const float2*)dY, P, Q, monoP, monoQ, eps, dP, dQ, B, I, O, M, \
+                            (float*)workspace, offs, st);
+  CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 2) CASE(3, 3) CASE(3, 4) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+#undef CASE
+  return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) outside the supported range 2..4", order_p, order_q);
+}
+
+extern "C" int pdephi_complex_mix_fwd(const float* X, const float* W, float* Y, int B, int I, int O, long long mxy,
+                                      int mzh, int mz, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(X && W && Y, "complex_mix_fwd: null pointer");
+  PDEPHI_REQUIRE(B > 0 && I > 0 && O > 0 && mxy > 0 && mzh > 0 && mz >= mzh, "complex_mix_fwd: bad size");
+  const long long M = mxy * mzh;
+  dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (O + UT - 1) / UT);
+  {
+    ProfScope ps(K_COMPLEX_MIX, (cudaStream_t)stream);
+    complex_mix_kernel<false><<<grid, MIX_THREADS, 0, (cudaStream_t)stream>>>((const float2*)X, (float2*)Y,
+                                                                             (const float2*)W, B, O, I, mxy, mzh, mz);
+  }
+  PDEPHI_LAUNCH_CHECK("complex_mix_kernel");
+  return PDEPHI_OK;
+}
+
+extern "C" int pdephi_complex_mix_bwd(const float* X, const float* W, const float* dY, float* dX, float* dW, int B,
+                                      int I, int O, long long mxy, int mzh, int mz, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(X && W && dY && dX && dW, "complex_mix_bwd: null pointer");
+  PDEPHI_REQUIRE(B > 0 && I > 0 && O > 0 && mxy > 0 && mzh > 0 && mz >= mzh, "complex_mix_bwd: bad size");
+  PDEPHI_REQUIRE((O + WT - 1) / WT <= 65535 && (I + WT - 1) / WT <= 65535, "complex_mix_bwd: too many channels");
+  const long long M = mxy * mzh, Mw = mxy * mz;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (I + UT - 1) / UT);
+  {
+    ProfScope ps(K_COMPLEX_MIX_T, st);
+    complex_mix_kernel<true><<<grid, MIX_THREADS, 0, st>>>((const float2*)dY, (float2*)dX, (const float2*)W, B, I, O, mxy,
+                                                          mzh, mz);
+  }
+  PDEPHI_LAUNCH_CHECK("complex_mix_kernel(dX)");
+  dim3 gw((unsigned)((Mw + MIX_THREADS - 1) / MIX_THREADS), (O + WT - 1) / WT, (I + WT - 1) / WT);
+  {
+    ProfScope ps(K_COMPLEX_DW, st);
+    complex_dw_kernel<<<gw, MIX_THREADS, 0, st>>>((const float2*)X, (const float2*)dY, (float2*)dW, B, I, O, mxy, mzh, mz);
+  }
+  PDEPHI_LAUNCH_CHECK("complex_dw_kernel");
+  return PDEPHI_OK;
+}

@@ -1,0 +1,262 @@
+"""Host side of the hot path: thin wrappers over the C ABI and the two autograd Functions.
+
+torch is used for what the reference uses it for around this seam -- device memory, the current
+stream, autograd bookkeeping -- and nothing else: every FLOP of the spectral layer runs in
+libpdephi_b200.so.  CPU tensors raise; there is no fallback.
+
+Replaces the bodies of RationalFourierLayer.forward (operators/rational_fourier.py:150-172) and
+SpectralConv3D.forward (operators/spectral_layers.py:46-78) and the autograd graph behind them.
+"""
+from __future__ import annotations
+
+import itertools
+from ctypes import c_void_p
+from typing import Optional, Sequence, Tuple
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _cabi
+
+
+def _p(t: Optional[torch.Tensor]):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str, complex_ok: bool = False):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: the pdephi_b200 spectral path is CUDA-only (no CPU fallback)")
+    want = (torch.float32, torch.complex64) if complex_ok else (torch.float32,)
+    if t.dtype not in want:
+        raise RuntimeError(f"{name} has dtype {t.dtype}; the pdephi_b200 spectral path computes in float32 only")
+
+
+def monomial_exponents(order: int):
+    """(a,b,c), a+b+c < order, in the loop order of rational_fourier.py:135-138."""
+    return [e for e in itertools.product(range(order), repeat=3) if sum(e) < order]
+
+
+def monomial_table(modes: Sequence[int], order: int) -> torch.Tensor:
+    """mono[t, k] = kx^a ky^b kz^c over the retained box, built with the same torch ops as
+    rational_fourier.py:144 so every entry is the float the reference multiplies by."""
+    mx, my, mz = modes
+    kx, ky, kz = torch.meshgrid(torch.arange(mx, dtype=torch.float32), torch.arange(my, dtype=torch.float32),
+                                torch.arange(mz // 2 + 1, dtype=torch.float32), indexing="ij")
+    rows = [((kx ** a) * (ky ** b) * (kz ** c)).reshape(-1) for a, b, c in monomial_exponents(order)]
+    return torch.stack(rows).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# raw ops (no autograd)
+# ------------------------------------------------------------------------------------------------
+def analysis(x: torch.Tensor, modes_h: Tuple[int, int, int], direction: int = _cabi.FORWARD,
+             precision: int = _cabi.PREC_FP32) -> torch.Tensor:
+    """K1.  x [B,C,Nx,Ny,Nz] float32 -> [B,C,mx,my,mzh] complex64 (pruned rfftn / adjoint of synthesis)."""
+    _require_cuda_f32(x, "x")
+    if x.dim() != 5:
+        raise ValueError(f"expected a [B,C,Nx,Ny,Nz] tensor, got shape {tuple(x.shape)}")
+    x = x.contiguous()
+    B, C = x.shape[:2]
+    grid = tuple(x.shape[2:])
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        plan = _cabi.get_plan(x.device.index, grid, modes_h)
+        X = torch.empty((B, C, *modes_h), dtype=torch.complex64, device=x.device)
+        nbytes = lib.pdephi_plan_workspace_bytes(plan, B * C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _cabi.check(lib.pdephi_analysis_r2c(plan, _p(x), _p(X), B * C, direction, precision, _p(ws), nbytes, _stream()),
+                    "analysis_r2c")
+    return X
+
+
+def synthesis(Z: torch.Tensor, grid: Tuple[int, int, int], mode_scale: Optional[torch.Tensor] = None,
+              row_scale: Optional[torch.Tensor] = None, addend0: Optional[torch.Tensor] = None,
+              addend1: Optional[torch.Tensor] = None, direction: int = _cabi.FORWARD,
+              precision: int = _cabi.PREC_FP32) -> torch.Tensor:
+    """K3.  Z [B,C,mx,my,mzh] complex64 -> [B,C,Nx,Ny,Nz] float32, out = S(Z*mode_scale*row_scale) + addends.
+
+    row_scale: float32 1-D (possibly strided) view with one element per volume, e.g. ``stats[:, 2]``.
+    """
+    _require_cuda_f32(Z, "Z", complex_ok=True)
+    if Z.dim() != 5 or not Z.is_complex():
+        raise ValueError(f"expected a complex [B,C,mx,my,mzh] tensor, got {Z.dtype} {tuple(Z.shape)}")
+    Z = Z.contiguous()
+    B, C = Z.shape[:2]
+    modes_h = tuple(Z.shape[2:])
+    rs_stride = 0
+    if row_scale is not None:
+        if row_scale.numel() != B * C or row_scale.dim() != 1:
+            raise ValueError("row_scale must be a 1-D view with one element per (batch, channel)")
+        rs_stride = row_scale.stride(0)
+    for a in (addend0, addend1):
+        if a is not None:
+            _require_cuda_f32(a, "addend")
+            if tuple(a.shape) != (B, C, *grid):
+                raise ValueError(f"addend shape {tuple(a.shape)} != {(B, C, *grid)}")
+    a0 = addend0.contiguous() if addend0 is not None else None
+    a1 = addend1.contiguous() if addend1 is not None else None
+    lib = _cabi.load()
+    with torch.cuda.device(Z.device):
+        plan = _cabi.get_plan(Z.device.index, grid, modes_h)
+        out = torch.empty((B, C, *grid), dtype=torch.float32, device=Z.device)
+        nbytes = lib.pdephi_plan_workspace_bytes(plan, B * C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=Z.device)
+        _cabi.check(lib.pdephi_synthesis_c2r(plan, _p(Z), _p(out), _p(a0), _p(a1), _p(mode_scale), _p(row_scale),
+                                             rs_stride, B * C, direction, precision, _p(ws), nbytes, _stream()),
+                    "synthesis_c2r")
+    return out
+
+
+def rational_mix_fwd(X, P, Q, monoP, monoQ, eps: float, mask, proj_eps: float):
+    """K2.  Returns Y [B,O,mx,my,mzh] complex64 (unprojected) and stats [B*O,4] = {a, b, s, 0}."""
+    B, I = X.shape[:2]
+    O = P.shape[0]
+    M = X[0, 0].numel()
+    lib = _cabi.load()
+    with torch.cuda.device(X.device):
+        Y = torch.empty((B, O, *X.shape[2:]), dtype=torch.complex64, device=X.device)
+        stats = torch.empty((B * O, 4), dtype=torch.float32, device=X.device)
+        _cabi.check(lib.pdephi_rational_mix_fwd(_p(X), _p(P), _p(Q), _p(monoP), _p(monoQ), P.shape[-1], Q.shape[-1],
+                                                eps, _p(mask), proj_eps, _p(Y), _p(stats), B, I, O, M, _stream()),
+                    "rational_mix_fwd")
+    return Y, stats
+
+
+def projection_bwd(dZ, Y, mask, stats):
+    rows = Y.shape[0] * Y.shape[1]
+    M = Y[0, 0].numel()
+    lib = _cabi.load()
+    with torch.cuda.device(Y.device):
+        dY = torch.empty_like(Y)
+        _cabi.check(lib.pdephi_projection_bwd(_p(dZ), _p(Y), _p(mask), _p(stats), _p(dY), rows, M, _stream()),
+                    "projection_bwd")
+    return dY
+
+
+def rational_mix_bwd(X, dY, P, Q, monoP, monoQ, eps: float):
+    B, I = X.shape[:2]
+    O = P.shape[0]
+    M = X[0, 0].numel()
+    lib = _cabi.load()
+    with torch.cuda.device(X.device):
+        dX = torch.empty_like(X)
+        dP = torch.empty_like(P)
+        dQ = torch.empty_like(Q)
+        nbytes = lib.pdephi_rational_mix_bwd_workspace_bytes(P.shape[-1], Q.shape[-1], I, O, M)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
+        _cabi.check(lib.pdephi_rational_mix_bwd(_p(X), _p(dY), _p(P), _p(Q), _p(monoP), _p(monoQ), P.shape[-1],
+                                                Q.shape[-1], eps, _p(dX), _p(dP), _p(dQ), B, I, O, M, _p(ws), nbytes,
+                                                _stream()), "rational_mix_bwd")
+    return dX, dP, dQ
+
+
+def complex_mix_fwd(X, W, mzh: int):
+    B, I = X.shape[:2]
+    O = W.shape[0]
+    mx, my, mz = W.shape[2:]
+    lib = _cabi.load()
+    with torch.cuda.device(X.device):
+        Y = torch.empty((B, O, mx, my, mzh), dtype=torch.complex64, device=X.device)
+        _cabi.check(lib.pdephi_complex_mix_fwd(_p(X), _p(W), _p(Y), B, I, O, mx * my, mzh, mz, _stream()),
+                    "complex_mix_fwd")
+    return Y
+
+
+def complex_mix_bwd(X, W, dY, mzh: int):
+    B, I = X.shape[:2]
+    O = W.shape[0]
+    mx, my, mz = W.shape[2:]
+    lib = _cabi.load()
+    with torch.cuda.device(X.device):
+        dX = torch.empty_like(X)
+        dW = torch.empty_like(W)
+        _cabi.check(lib.pdephi_complex_mix_bwd(_p(X), _p(W), _p(dY), _p(dX), _p(dW), B, I, O, mx * my, mzh, mz,
+                                               _stream()), "complex_mix_bwd")
+    return dX, dW
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions
+# ------------------------------------------------------------------------------------------------
+class RationalSpectralFn(torch.autograd.Function):
+    """out = irfftn(StabilityProjection(R(k) mix(rfftn(x)[corner]))) [+ skip0 + x].
+
+    Saves only the retained modes (X, Y: 71 MB each at the 128^3 / width-64 / batch-8 config) instead
+    of the reference's full spectra.  Backward formulas: SURVEY.md section 8a.
+    """
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, P, Q, mask, monoP, monoQ, modes, eps, precision, skip0, residual):
+        for t, n in ((x, "x"), (P, "P_coeffs"), (Q, "Q_coeffs")):
+            _require_cuda_f32(t, n)
+        mx, my, mz = modes
+        modes_h = (mx, my, mz // 2 + 1)
+        grid = tuple(x.shape[2:])
+        P = P.contiguous()
+        Q = Q.contiguous()
+        X = analysis(x, modes_h, _cabi.FORWARD, precision)
+        Y, stats = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps)
+        out = synthesis(Y, grid, mask, stats[:, 2], skip0, x if residual else None, _cabi.FORWARD, precision)
+        ctx.save_for_backward(X, Y, stats, P, Q, mask, monoP, monoQ)
+        ctx.meta = (modes_h, grid, eps, precision, skip0 is not None, bool(residual))
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, g):
+        X, Y, stats, P, Q, mask, monoP, monoQ = ctx.saved_tensors
+        modes_h, grid, eps, precision, has0, residual = ctx.meta
+        g = g.contiguous()
+        need_x, need_P, need_Q = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dx = dP = dQ = None
+        if need_x or need_P or need_Q:
+            dZ = analysis(g, modes_h, _cabi.ADJOINT, precision)
+            dY = projection_bwd(dZ, Y, mask, stats)
+            dX, dP, dQ = rational_mix_bwd(X, dY, P, Q, monoP, monoQ, eps)
+            if need_x:   # the residual branch's gradient (g itself) rides in the synthesis epilogue
+                dx = synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision)
+        return (dx, dP if need_P else None, dQ if need_Q else None, None, None, None, None, None, None,
+                g if has0 else None, None)
+
+
+class ComplexSpectralFn(torch.autograd.Function):
+    """out = irfftn(pad(einsum(rfftn(x)[corner], W[..., :mzh]))) [+ skip0 + x]  (SpectralConv3D)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, W, modes, precision, skip0, residual):
+        _require_cuda_f32(x, "x")
+        _require_cuda_f32(W, "weights", complex_ok=True)
+        mx, my, mz = modes
+        modes_h = (mx, my, mz // 2 + 1)
+        grid = tuple(x.shape[2:])
+        W = W.contiguous()
+        X = analysis(x, modes_h, _cabi.FORWARD, precision)
+        Y = complex_mix_fwd(X, W, modes_h[2])
+        out = synthesis(Y, grid, None, None, skip0, x if residual else None, _cabi.FORWARD, precision)
+        ctx.save_for_backward(X, W)
+        ctx.meta = (modes_h, grid, precision, skip0 is not None, bool(residual))
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, g):
+        X, W = ctx.saved_tensors
+        modes_h, grid, precision, has0, residual = ctx.meta
+        g = g.contiguous()
+        dx = dW = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dY = analysis(g, modes_h, _cabi.ADJOINT, precision)
+            dX, dW = complex_mix_bwd(X, W, dY, modes_h[2])
+            if ctx.needs_input_grad[0]:
+                dx = synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision)
+        return dx, dW if ctx.needs_input_grad[1] else None, None, None, g if has0 else None, None

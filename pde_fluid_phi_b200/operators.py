@@ -1,0 +1,193 @@
+"""Drop-in mirrors of the reference's spectral operator modules.
+
+Same class names, constructor signatures, parameter / buffer names, shapes and RNG consumption
+order as the reference (so ``torch.manual_seed`` reproduces its weights and ``state_dict``s
+interchange), with ``forward`` rerouted to the sm_100a kernels behind ``pde_fluid_phi_b200.functional``.
+
+  RationalFourierLayer   <- operators/rational_fourier.py:19-172
+  StabilityProjection    <- operators/stability.py:14-103
+  SpectralConv3D         <- operators/spectral_layers.py:17-78
+  get_grid               <- utils/spectral_utils.py:16-45
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .functional import ComplexSpectralFn, RationalSpectralFn, monomial_exponents, monomial_table
+
+_default_precision = "fp32"
+
+
+def set_default_precision(precision: str) -> None:
+    """'fp32' (FFMA contractions, 1e-5 parity gate) or 'tf32' (tcgen05 contractions, 2e-3 gate)."""
+    global _default_precision
+    if precision not in _cabi.PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_cabi.PRECISIONS)}")
+    _default_precision = precision
+
+
+def get_default_precision() -> str:
+    return _default_precision
+
+
+def get_grid(modes: Tuple[int, int, int], device: Union[str, torch.device] = "cpu",
+             dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Integer wavenumbers of the retained box, [3, mx, my, mz//2+1] (kx, ky, kz planes)."""
+    mx, my, mz = modes
+    axes = [torch.arange(n, device=device, dtype=dtype) for n in (mx, my, mz // 2 + 1)]
+    return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=0)
+
+
+def _check_input(x: torch.Tensor, channels: int, modes, who: str):
+    if not isinstance(x, torch.Tensor) or x.dim() != 5:
+        raise ValueError(f"{who}: expected a [batch, channels, Nx, Ny, Nz] tensor, got "
+                         f"{tuple(x.shape) if isinstance(x, torch.Tensor) else type(x)}")
+    if x.shape[1] != channels:
+        raise RuntimeError(f"{who}: input has {x.shape[1]} channels, layer was built for {channels}")
+    mx, my, mz = modes
+    nx, ny, nz = x.shape[2:]
+    if mx > nx or my > ny or mz // 2 + 1 > nz // 2 + 1:
+        raise RuntimeError(f"{who}: modes {tuple(modes)} do not fit the half-spectrum of a {(nx, ny, nz)} grid")
+
+
+class StabilityProjection(nn.Module):
+    """Decay mask (1+|k|^2)^(-decay_rate/2) plus per-(batch, channel) energy-conserving rescale.
+
+    Inside RationalFourierLayer.forward the projection is fused into the mix / synthesis kernels.
+    Calling this module directly (a full-spectrum tensor in, full-spectrum tensor out, as the
+    reference's adaptive subclass does) runs the same arithmetic as plain tensor ops.
+    """
+
+    def __init__(self, modes: Tuple[int, int, int], decay_rate: float = 2.0, eps: float = 1e-6,
+                 energy_conserving: bool = True):
+        super().__init__()
+        self.modes = modes
+        self.decay_rate = decay_rate
+        self.eps = eps
+        self.energy_conserving = energy_conserving
+        self.register_buffer("decay_mask", self._create_decay_mask())
+
+    def _create_decay_mask(self) -> torch.Tensor:
+        kx, ky, kz = get_grid(self.modes)
+        k_mag = torch.sqrt(kx ** 2 + ky ** 2 + kz ** 2)
+        return (1 + k_mag ** 2) ** (-self.decay_rate / 2)
+
+    def forward(self, x_ft: torch.Tensor) -> torch.Tensor:
+        mx, my, mz = self.modes
+        box = (slice(None), slice(None), slice(0, mx), slice(0, my), slice(0, mz // 2 + 1))
+        kept = x_ft[box]
+        damped = kept * self.decay_mask.to(x_ft.device)
+        if self.energy_conserving:
+            damped = self._enforce_energy_conservation(kept, damped)
+        out = x_ft.clone()
+        out[box] = damped
+        return out
+
+    def _enforce_energy_conservation(self, x_original: torch.Tensor, x_projected: torch.Tensor) -> torch.Tensor:
+        dims = (-3, -2, -1)
+        e0 = x_original.abs().pow(2).sum(dim=dims, keepdim=True)
+        e1 = x_projected.abs().pow(2).sum(dim=dims, keepdim=True)
+        return x_projected * torch.sqrt((e0 + self.eps) / (e1 + self.eps))
+
+
+class RationalFourierLayer(nn.Module):
+    """R(k) = P(k)/Q(k) spectral layer; forward runs K1 -> K2 -> K3 of libpdephi_b200.so."""
+
+    def __init__(self, in_channels: int, out_channels: int, modes: Tuple[int, int, int],
+                 rational_order: Tuple[int, int] = (4, 4), stability_eps: float = 1e-6, init_scale: float = 0.02):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.modes = modes
+        self.rational_order = rational_order
+        self.stability_eps = stability_eps
+        self.precision: Optional[str] = None     # None -> module-level default
+        self._init_rational_coefficients(init_scale)
+        self.stability_projection = StabilityProjection(modes=modes, decay_rate=2.0, eps=stability_eps)
+        self.register_buffer("k_grid", get_grid(modes, device="cpu"))
+        # kernel-side constants; non-persistent so state_dict keys equal the reference's
+        self.register_buffer("_mono_p", monomial_table(modes, rational_order[0]), persistent=False)
+        self.register_buffer("_mono_q", monomial_table(modes, rational_order[1]), persistent=False)
+
+    def _init_rational_coefficients(self, scale: float):
+        p, q = self.rational_order
+        self.P_coeffs = nn.Parameter(torch.randn(self.out_channels, self.in_channels, p, p, p) * scale)
+        self.Q_coeffs = nn.Parameter(torch.randn(self.out_channels, self.in_channels, q, q, q) * scale)
+        with torch.no_grad():
+            self.Q_coeffs[..., 0, 0, 0] = self.Q_coeffs[..., 0, 0, 0].abs() + 1.0
+
+    # ---- torch-op methods kept for callers that use them directly on full spectra ---------------
+    def _evaluate_polynomial(self, coeffs: torch.Tensor, k_x: torch.Tensor, k_y: torch.Tensor,
+                             k_z: torch.Tensor) -> torch.Tensor:
+        total = torch.zeros(coeffs.shape[:2] + k_x.shape, device=coeffs.device, dtype=coeffs.dtype)
+        for a, b, c in monomial_exponents(coeffs.shape[-1]):
+            total = total + coeffs[:, :, a, b, c, None, None, None] * ((k_x ** a) * (k_y ** b) * (k_z ** c))
+        return total
+
+    def rational_multiply(self, x_ft: torch.Tensor) -> torch.Tensor:
+        mx, my, mz = self.modes
+        box = (slice(None), slice(None), slice(0, mx), slice(0, my), slice(0, mz // 2 + 1))
+        kx, ky, kz = self.k_grid.to(x_ft.device)
+        transfer = self._evaluate_polynomial(self.P_coeffs, kx, ky, kz) / (
+            self._evaluate_polynomial(self.Q_coeffs, kx, ky, kz) + self.stability_eps)
+        kept = x_ft[box]
+        out = torch.zeros_like(x_ft)
+        out[box] = torch.einsum("bixyz,oixyz->boxyz", kept, transfer.to(kept.dtype))
+        return out
+
+    # ---- the hot path ---------------------------------------------------------------------------
+    def _precision_code(self) -> int:
+        return _cabi.PRECISIONS[self.precision or _default_precision]
+
+    def _run(self, x, skip0, residual):
+        _check_input(x, self.in_channels, self.modes, "RationalFourierLayer")
+        if self.in_channels != self.out_channels:
+            raise RuntimeError("RationalFourierLayer needs in_channels == out_channels (as the reference does)")
+        return RationalSpectralFn.apply(x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
+                                        self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
+                                        self._precision_code(), skip0, residual)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self._run(x, None, False)
+
+    def forward_fused(self, x: torch.Tensor, x_local: torch.Tensor) -> torch.Tensor:
+        """layer(x) + x_local + x with both adds fused into the synthesis kernel's epilogue
+        (the block body of rational_fourier.py:263-271 minus the activation)."""
+        return self._run(x, x_local, True)
+
+
+class SpectralConv3D(nn.Module):
+    """Classic FNO spectral convolution with a complex [O, I, mx, my, mz] weight.
+
+    The einsum contracts against ``weights[..., :mz//2+1]`` (oracle convention 2 of SURVEY.md
+    section 8c; the unmodified reference forward raises for mz > 2); entries with kz >= mz//2+1 receive zero
+    gradient.  For mz in {1, 2} this is exactly the reference.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, modes: Tuple[int, int, int], init_scale: float = 0.02):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.modes = modes
+        self.precision: Optional[str] = None
+        self.weights = nn.Parameter(torch.randn(out_channels, in_channels, *modes, dtype=torch.cfloat) * init_scale)
+
+    def _precision_code(self) -> int:
+        return _cabi.PRECISIONS[self.precision or _default_precision]
+
+    def _run(self, x, skip0, residual):
+        _check_input(x, self.in_channels, self.modes, "SpectralConv3D")
+        if residual and self.in_channels != self.out_channels:
+            raise RuntimeError("fused residual needs in_channels == out_channels")
+        return ComplexSpectralFn.apply(x, self.weights, tuple(self.modes), self._precision_code(), skip0, residual)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self._run(x, None, False)
+
+    def forward_fused(self, x: torch.Tensor, x_local: torch.Tensor) -> torch.Tensor:
+        """conv(x) + x_local + x, adds fused into the synthesis epilogue (models/fno3d.py:91-97)."""
+        return self._run(x, x_local, True)

@@ -1,0 +1,50 @@
+"""world_size-2 gloo test of the data-parallel gradient path (host logic; the GPU box runs NCCL)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pde_fluid_phi_b200.distributed import allreduce_gradients, broadcast_parameters
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                       # different weights per rank before the broadcast
+    lin = torch.nn.Linear(3, 2)
+    w = torch.nn.Parameter(torch.randn(2, 2, 3, dtype=torch.cfloat))   # stands in for SpectralConv3D.weights
+    mod = torch.nn.Module()
+    mod.lin, mod.w = lin, w
+    broadcast_parameters(mod, src=0)
+    torch.manual_seed(7 + rank)                         # different data per rank
+    x = torch.randn(4, 3)
+    loss = (lin(x) ** 2).mean() + (w * torch.randn(2, 2, 3, dtype=torch.cfloat)).abs().pow(2).sum()
+    loss.backward()
+    local = [p.grad.clone() for p in mod.parameters()]
+    allreduce_gradients(mod.parameters(), world)
+    out[rank] = dict(local=local, reduced=[p.grad.clone() for p in mod.parameters()],
+                     weights=[p.detach().clone() for p in mod.parameters()])
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    for a, b in zip(r0["weights"], r1["weights"]):
+        assert torch.equal(a, b)                        # broadcast made the replicas identical
+    for l0, l1, g0, g1 in zip(r0["local"], r1["local"], r0["reduced"], r1["reduced"]):
+        assert torch.equal(g0, g1)                      # same averaged gradient on both ranks
+        assert torch.allclose(g0, (l0 + l1) / 2, rtol=1e-6, atol=1e-7)
+        assert g0.dtype == l0.dtype                     # complex64 stays complex64

@@ -1,0 +1,102 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every declared
+symbol, the mirrored modules reproduce the reference's parameters / state_dict under the same
+seed, the kept torch-op methods agree with the oracle, and CPU tensors are refused loudly."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import pde_fluid_phi_b200 as pb
+from pde_fluid_phi_b200 import _cabi
+from pde_fluid_phi_b200.functional import monomial_table
+from oracle import dense_fp64 as d64
+from oracle import spectral_oracle as so
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "pdephi_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(pdephi_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(_cabi.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pdephi_b200.h but not exported"
+    assert sorted(_cabi.SIGNATURES) == declared        # the ctypes table mirrors the header one to one
+    assert pb.load_library().pdephi_version() == 100
+
+
+def test_argument_errors_without_gpu():
+    lib = pb.load_library()
+    # null-pointer / size validation happens before any CUDA call
+    rc = lib.pdephi_rational_mix_fwd(None, None, None, None, None, 4, 4, 1e-6, None, 1e-6, None, None, 1, 1, 1, 1, None)
+    assert rc == _cabi.ERR_INVALID
+    assert b"null pointer" in lib.pdephi_last_error()
+    assert lib.pdephi_plan_workspace_bytes(None, 4) == 0
+    assert lib.pdephi_rational_mix_bwd_workspace_bytes(4, 4, 64, 64, 17408) > 0
+
+
+@pytest.mark.parametrize("name,factory", [
+    ("rfl_c4_m4_n8_default", lambda: pb.RationalFourierLayer(4, 4, (4, 4, 4))),
+    ("rfl_c3_m648_n161220_order43", lambda: pb.RationalFourierLayer(3, 3, (6, 4, 8), rational_order=(4, 3))),
+    ("sc3d_c4_m4_n8_sliced", lambda: pb.SpectralConv3D(4, 4, (4, 4, 4))),
+    ("rfno3d_w8_m4_l2_n8", lambda: pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=2, rational_order=(3, 3))),
+    ("fno3d_w8_m4_l2_n8_sliced", lambda: pb.FNO3D(modes=(4, 4, 4), width=8, n_layers=2)),
+])
+def test_same_seed_same_state_dict_as_reference(name, factory):
+    z = load_golden(name)
+    torch.manual_seed(1234)
+    module = factory()
+    sd = module.state_dict()
+    ref_keys = sorted(k[3:] for k in z if k.startswith("sd:"))
+    assert sorted(sd.keys()) == ref_keys
+    for k in ref_keys:
+        assert np.array_equal(sd[k].numpy(), z["sd:" + k]), k
+
+
+def test_state_dict_round_trip_from_reference_checkpoint():
+    z = load_golden("rfno3d_w8_m4_l2_n8")
+    torch.manual_seed(99)
+    model = pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=2, rational_order=(3, 3))
+    model.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("sd:")}, strict=True)
+    assert np.array_equal(model.rational_layers[1].Q_coeffs.detach().numpy(), z["sd:rational_layers.1.Q_coeffs"])
+
+
+def test_cpu_tensors_are_refused():
+    layer = pb.RationalFourierLayer(2, 2, (4, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        layer(torch.randn(1, 2, 8, 8, 8))
+    conv = pb.SpectralConv3D(2, 2, (4, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        conv(torch.randn(1, 2, 8, 8, 8))
+    with pytest.raises(RuntimeError):          # channel mismatch, as the reference (tests/test_integration.py:415-427)
+        layer(torch.randn(1, 3, 8, 8, 8))
+    with pytest.raises(ValueError):
+        layer(torch.randn(2, 8, 8, 8))
+    with pytest.raises(RuntimeError):          # grid smaller than modes
+        layer(torch.randn(1, 2, 4, 4, 4)[:, :, :2])
+
+
+def test_kept_torch_methods_match_oracle():
+    """rational_multiply / stability_projection on full spectra (called directly by a reference subclass)."""
+    z = load_golden("rfl_c4_m4_n8_default")
+    layer = pb.RationalFourierLayer(4, 4, (4, 4, 4))
+    layer.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("sd:")})
+    x_ft = torch.fft.rfftn(torch.from_numpy(z["x"]), dim=[-3, -2, -1])
+    with torch.no_grad():
+        got = layer.stability_projection(layer.rational_multiply(x_ft))
+        P, Q = torch.from_numpy(z["sd:P_coeffs"]), torch.from_numpy(z["sd:Q_coeffs"])
+        want = so.stability_projection(so.rational_multiply(x_ft, P, Q, (4, 4, 4), 1e-6), (4, 4, 4), 1e-6)
+        out = torch.fft.irfftn(got, s=(8, 8, 8), dim=[-3, -2, -1])
+    assert torch.equal(got, want)
+    assert so.rel_l2(out, torch.from_numpy(z["out"])) < 1e-6
+
+
+def test_monomial_table_is_exact():
+    modes = (6, 4, 8)
+    mono64, exps = d64.monomials(modes, 4)
+    t = monomial_table(modes, 4).numpy()
+    assert t.shape == (20, 6 * 4 * 5)
+    assert np.array_equal(t.astype(np.float64), mono64.reshape(20, -1))
