@@ -158,8 +158,8 @@ def init_spectral_weights(channels_out: int, channels_in: int, modes: Modes, sca
 
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     """||a-b|| / ||b|| over the whole tensor (complex ok)."""
-    a = torch.as_tensor(a)
-    b = torch.as_tensor(b)
+    a = torch.as_tensor(a).detach()
+    b = torch.as_tensor(b).detach()
     num = torch.linalg.vector_norm((a - b).reshape(-1).to(torch.complex128 if a.is_complex() else torch.float64))
     den = torch.linalg.vector_norm(b.reshape(-1).to(torch.complex128 if b.is_complex() else torch.float64))
     return float(num / den) if float(den) > 0 else float(num)
