@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/pdephi_b200.h"
@@ -46,7 +47,16 @@ struct Plan {
   void* arena;    // one allocation backing all tables
   int num_sms;
   size_t smem_optin;
+  // tcgen05 path: twiddle operands as swizzled K-major shared-memory images (transforms_tc.cu)
+  int tc_ok;
+  void* tc_arena;
+  float* tc_b1[2];  // analysis z  [48][Nz]
+  float* tc_a2;     // analysis y  [64][Ny]
+  float* tc_ay;     // synthesis y [Ny][64]
+  float* tc_bz[2];  // synthesis z [Nz][64]
 };
+int tc_plan_init(Plan* p);
+void tc_plan_destroy(Plan* p);
 
 enum KernelId {
   K_ANALYSIS_ZY = 0, K_ANALYSIS_X, K_SYNTHESIS_X, K_SYNTHESIS_ZY, K_ANALYSIS_ZY_TC, K_SYNTHESIS_ZY_TC,

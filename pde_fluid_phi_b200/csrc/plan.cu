@@ -134,6 +134,10 @@ extern "C" int pdephi_plan_create(pdephi_plan_t* out, int device, int Nx, int Ny
   gen(p->sz[0], mzh, Nz, Nz, false, +1.0, 1);
   gen(p->sz[1], mzh, Nz, Nz, false, +1.0, 0);
   PDEPHI_LAUNCH_CHECK("twiddle_kernel");
+  {
+    int rc = tc_plan_init(p);
+    if (rc) return rc;
+  }
   PDEPHI_CUDA(cudaDeviceSynchronize());  // plan creation is the one synchronous call
   PDEPHI_CUDA(cudaSetDevice(cur));
   *out = (pdephi_plan_t)p;
@@ -144,6 +148,7 @@ extern "C" int pdephi_plan_destroy(pdephi_plan_t h) {
   if (!h) return PDEPHI_OK;
   Plan* p = (Plan*)h;
   if (p->arena) cudaFree(p->arena);
+  tc_plan_destroy(p);
   delete p;
   return PDEPHI_OK;
 }

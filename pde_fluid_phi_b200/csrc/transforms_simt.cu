@@ -236,6 +236,31 @@ static int pick_group(int mzh) {
   return best;
 }
 
+int xstage_analysis(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st) {
+  const int P = p->my * p->mzh;
+  if (BC > 65535) return fail(PDEPHI_ERR_UNSUPPORTED, "analysis: batch*channels > 65535");
+  dim3 grid((P + 63) / 64, (unsigned)BC, (p->mx + 4 * XT - 1) / (4 * XT));
+  {
+    ProfScope ps(K_ANALYSIS_X, st);
+    xstage_kernel<false><<<grid, dim3(64, 4), 0, st>>>(ws, X, p->ax, p->Nx, p->mx, P, nullptr, nullptr, 0);
+  }
+  PDEPHI_LAUNCH_CHECK("xstage_kernel(analysis)");
+  return PDEPHI_OK;
+}
+
+int xstage_synthesis(const Plan* p, const float2* Z, float2* ws, const float* mode_scale, const float* row_scale,
+                     long long rs_stride, long long BC, cudaStream_t st) {
+  const int P = p->my * p->mzh;
+  if (BC > 65535) return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis: batch*channels > 65535");
+  dim3 grid((P + 63) / 64, (unsigned)BC, (p->Nx + 4 * XT - 1) / (4 * XT));
+  {
+    ProfScope ps(K_SYNTHESIS_X, st);
+    xstage_kernel<true><<<grid, dim3(64, 4), 0, st>>>(Z, ws, p->sx, p->mx, p->Nx, P, mode_scale, row_scale, rs_stride);
+  }
+  PDEPHI_LAUNCH_CHECK("xstage_kernel(synthesis)");
+  return PDEPHI_OK;
+}
+
 int analysis_simt(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws,
                   cudaStream_t st) {
   const int Ny = p->Ny, Nz = p->Nz, my = p->my, mzh = p->mzh;
@@ -269,29 +294,17 @@ int analysis_simt(const Plan* p, const float* x, float2* X, long long BC, int di
   }
 #undef LAUNCH_A
   PDEPHI_LAUNCH_CHECK("analysis_zy_kernel");
-  const int P = my * mzh;
-  dim3 grid((P + 63) / 64, (unsigned)BC, (p->mx + 4 * XT - 1) / (4 * XT));
-  if (BC > 65535) return fail(PDEPHI_ERR_UNSUPPORTED, "analysis: batch*channels > 65535");
-  {
-    ProfScope ps(K_ANALYSIS_X, st);
-    xstage_kernel<false><<<grid, dim3(64, 4), 0, st>>>(ws, X, p->ax, p->Nx, p->mx, P, nullptr, nullptr, 0);
-  }
-  PDEPHI_LAUNCH_CHECK("xstage_kernel(analysis)");
-  return PDEPHI_OK;
+  return xstage_analysis(p, ws, X, BC, st);
 }
 
 int synthesis_simt(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1,
                    const float* mode_scale, const float* row_scale, long long rs_stride, long long BC,
                    int direction, float2* ws, cudaStream_t st) {
   const int Ny = p->Ny, Nz = p->Nz, my = p->my, mzh = p->mzh;
-  const int P = my * mzh;
-  if (BC > 65535) return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis: batch*channels > 65535");
-  dim3 grid((P + 63) / 64, (unsigned)BC, (p->Nx + 4 * XT - 1) / (4 * XT));
   {
-    ProfScope ps(K_SYNTHESIS_X, st);
-    xstage_kernel<true><<<grid, dim3(64, 4), 0, st>>>(Z, ws, p->sx, p->mx, p->Nx, P, mode_scale, row_scale, rs_stride);
+    int rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
+    if (rc) return rc;
   }
-  PDEPHI_LAUNCH_CHECK("xstage_kernel(synthesis)");
   const size_t smem = ((size_t)my * mzh + (size_t)Ny * mzh) * sizeof(float2);
   if (smem > p->smem_optin)
     return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis: %d y rows x %d kz modes do not fit shared memory", Ny, mzh);

@@ -1,16 +1,634 @@
-// K1 / K3, TF32 path: tcgen05 tensor-core contractions with TMA-staged operands (sm_100a).
+// K1 / K3, TF32 path: the fused (z,y) stages as tcgen05 tensor-core contractions (sm_100a).
+//
+// One persistent, warp-specialised CTA per SM walks the (volume, x) planes.
+//
+//  analysis  (plane [Ny=128][Nz] fp32, TMA-staged, double buffered)
+//     GEMM1  D1[y, c]   = plane[y, z] . B1[c, z]^T        M=128 N=48 K=Nz    (c: re kz | im kz)
+//     epi-1  D1 (TMEM) -> registers -> cvt.rna.tf32 -> B2 operand tile in shared memory
+//     GEMM2  D2[m, c]   = A2[m, y] . B2[c, y]^T           M=64  N=40 K=128   (m: cos ky | sin ky)
+//     epi-2  D2 (TMEM) -> registers -> complex combine -> T2[ky, kz] to the workspace
+//
+//  synthesis (plane of U[ky, kz] complex from the workspace)
+//     build  By operand tile [c, k] from U (re/-im/im/re blocks), cvt.rna.tf32
+//     GEMM-Y V[y, c]    = Ay[y, k] . By[c, k]^T           M=128 N=48 K=64    (k: cos ky | sin ky)
+//     GEMM-Z out[y, z]  = V[y, c] (A from TMEM) . Bz[z, c]^T   M=128 N=Nz K=40
+//     epi    out (TMEM) -> registers -> shared-memory transpose -> (+ addends) -> coalesced stores
+//
+// Twiddle operands are built once per plan, already in the 128-byte-swizzled K-major shared-memory
+// image the UMMA descriptors expect, rounded to TF32 with round-to-nearest.  The x stage and the
+// channel mix stay fp32.  Replaces torch.fft.rfftn / irfftn of rational_fourier.py:161,170.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace pdephi {
+namespace tc {
 
-bool tc_supported(const Plan*) { return false; }
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-int analysis_tc(const Plan*, const float*, float2*, long long, int, float2*, cudaStream_t) {
-  return fail(PDEPHI_ERR_UNSUPPORTED, "analysis_tc: not built");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int synthesis_tc(const Plan*, const float2*, float*, const float*, const float*, const float*, const float*, long long,
-                 long long, int, float2*, cudaStream_t) {
-  return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis_tc: not built");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("pdephi: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups `sbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                         // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;    // stride byte offset
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of element (row r, k) inside a K-major SW128 operand image with R rows; k-blocks of 32 floats
+__host__ __device__ __forceinline__ uint32_t swz_off(int R, int r, int k) {
+  const int kb = k >> 5, kk = k & 31;
+  return (uint32_t)(kb * R * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((((kk >> 2) ^ (r & 7)) & 7) << 4) + (kk & 3) * 4);
+}
+
+constexpr int ROWS_B = 48;     // rows reserved for the (re kz | im kz) operand tiles
+constexpr int N1 = 48;         // GEMM1 / GEMM-Y N
+constexpr int N2 = 40;         // GEMM2 N and GEMM-Z K (>= 2*mzh)
+constexpr int M2 = 64;         // GEMM2 M
+constexpr int SIN0 = 32;       // first sine row / column of the y-stage twiddle operands
+constexpr int E_LD = 41;
+
+// ------------------------------------------------------------------------------------------------
+// constant operand images (plan creation)
+// ------------------------------------------------------------------------------------------------
+// kind 0: analysis B1 [48 rows c][K=Nz]      c<mzh: w cos(2 pi c z/Nz), mzh<=c<2mzh: -w sin
+// kind 1: analysis A2 [64 rows m][K=Ny]      m<my: cos(2 pi m y/Ny), 32<=m<32+my: sin
+// kind 2: synthesis Ay [128 rows y][K=64]    k<my: cos(2 pi k y/Ny), 32<=k<32+my: sin
+// kind 3: synthesis Bz [Nz rows z][K=64]     c<mzh: w cos(2 pi c z/Nz), mzh<=c<2mzh: -w sin, else 0
+__global__ void tc_image_kernel(float* __restrict__ img, int kind, int R, int K, int N, int m, int weight_mode, int nyq,
+                                double inv_total, double comp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * K) return;
+  const int r = idx / K, k = idx % K;
+  int mode = -1, pos = 0, sine = 0;
+  if (kind == 0) { pos = k; if (r < m) mode = r; else if (r < 2 * m) { mode = r - m; sine = 1; } }
+  if (kind == 1) { pos = k; if (r < m) mode = r; else if (r >= SIN0 && r < SIN0 + m) { mode = r - SIN0; sine = 1; } }
+  if (kind == 2) { pos = r; if (k < m) mode = k; else if (k >= SIN0 && k < SIN0 + m) { mode = k - SIN0; sine = 1; } }
+  if (kind == 3) { pos = r; if (k < m) mode = k; else if (k < 2 * m) { mode = k - m; sine = 1; } }
+  double v = 0.0;
+  if (mode >= 0) {
+    double s, c;
+    sincospi(2.0 * (double)(((long long)mode * pos) % N) / (double)N, &s, &c);
+    double w = 1.0;
+    if (weight_mode == 1) w = ((mode == 0 || mode == nyq) ? 1.0 : 2.0) * inv_total;
+    v = sine ? ((kind == 0 || kind == 3) ? -w * s : s) : ((kind == 0 || kind == 3) ? w * c : c);
+    v *= comp;
+  }
+  img[swz_off(R, r, k) / 4] = to_tf32((float)v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// analysis kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int A_THREADS = 192;
+struct ASmem {
+  uint32_t a1[2], b1, a2, b2, e, bars, tmem_slot, total;
+};
+__host__ __device__ inline ASmem analysis_smem(int NKB) {
+  ASmem s;
+  uint32_t o = 0;
+  s.a1[0] = o; o += NKB * 16384;
+  s.a1[1] = o; o += NKB * 16384;
+  s.b1 = o; o += NKB * ROWS_B * 128;
+  s.a2 = o; o += 4 * M2 * 128;
+  s.b2 = o; o += 4 * ROWS_B * 128;
+  s.e = o; o += 10752;
+  s.bars = o; o += 64;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+enum { AB_FULL0 = 0, AB_FULL1, AB_EMPTY0, AB_EMPTY1, AB_D1FULL, AB_B2FULL, AB_D2FULL, AB_D2EMPTY };
+
+__global__ void __launch_bounds__(A_THREADS, 1)
+analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __restrict__ T2, const float* __restrict__ B1img,
+                      const float* __restrict__ A2img, int planes, int NKB, int my, int mzh) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const ASmem L = analysis_smem(NKB);
+  const uint32_t bar0 = base + L.bars;
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  {
+    const float4* s1 = reinterpret_cast<const float4*>(B1img);
+    float4* d1 = reinterpret_cast<float4*>(sm + L.b1);
+    for (int i = threadIdx.x; i < NKB * ROWS_B * 128 / 16; i += A_THREADS) d1[i] = __ldg(s1 + i);
+    const float4* s2 = reinterpret_cast<const float4*>(A2img);
+    float4* d2 = reinterpret_cast<float4*>(sm + L.a2);
+    for (int i = threadIdx.x; i < 4 * M2 * 128 / 16; i += A_THREADS) d2[i] = __ldg(s2 + i);
+    float4* z = reinterpret_cast<float4*>(sm + L.b2);
+    for (int i = threadIdx.x; i < 4 * ROWS_B * 128 / 16; i += A_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar(AB_FULL0), 1); mbar_init(bar(AB_FULL1), 1);
+    mbar_init(bar(AB_EMPTY0), 1); mbar_init(bar(AB_EMPTY1), 1);
+    mbar_init(bar(AB_D1FULL), 1); mbar_init(bar(AB_B2FULL), 128);
+    mbar_init(bar(AB_D2FULL), 1); mbar_init(bar(AB_D2EMPTY), 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + 64;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
+        const int s = it & 1;
+        mbar_wait(bar(AB_EMPTY0 + s), ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar(AB_FULL0 + s), (uint32_t)NKB * 16384u);
+        for (int kb = 0; kb < NKB; ++kb)
+          tma_load_2d(base + L.a1[s] + kb * 16384, &tmap_x, bar(AB_FULL0 + s), kb * 32, p * 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t id1 = umma_idesc(128, N1), id2 = umma_idesc(M2, N2);
+      int it = 0;
+      for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
+        const int s = it & 1;
+        mbar_wait(bar(AB_FULL0 + s), (it >> 1) & 1);
+        tc_fence_after();
+        for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem_d1, umma_desc(base + L.a1[s] + kb * 16384 + k * 32, 1024),
+                   umma_desc(base + L.b1 + kb * ROWS_B * 128 + k * 32, 1024), id1, (kb | k) ? 1u : 0u);
+        mma_commit(bar(AB_EMPTY0 + s));
+        mma_commit(bar(AB_D1FULL));
+        mbar_wait(bar(AB_B2FULL), it & 1);
+        mbar_wait(bar(AB_D2EMPTY), (it & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem_d2, umma_desc(base + L.a2 + kb * M2 * 128 + k * 32, 1024),
+                   umma_desc(base + L.b2 + kb * ROWS_B * 128 + k * 32, 1024), id2, (kb | k) ? 1u : 0u);
+        mma_commit(bar(AB_D2FULL));
+      }
+    }
+  } else {
+    // ===== epilogue warps (2..5): TMEM quarter q = warp % 4 =====
+    const int q = warp & 3;
+    const int et = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* E = reinterpret_cast<float*>(sm + L.e);
+    const int ncol = 2 * mzh;
+    int it = 0;
+    for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
+      // ---- epi-1: D1 row y = 32q+lane -> B2[c][y] ------------------------------------------------
+      mbar_wait(bar(AB_D1FULL), it & 1);
+      tc_fence_after();
+      float v[40];
+      tmem_ld32(tmem_d1 + lane_base, v);
+      tmem_ld8(tmem_d1 + lane_base + 32, v + 32);
+      tmem_ld_wait();
+      {
+        uint8_t* b2 = sm + L.b2 + q * (ROWS_B * 128);   // k-block q holds y in [32q, 32q+32)
+        const uint32_t kin = (uint32_t)(lane & 3) * 4;
+#pragma unroll
+        for (int c = 0; c < 40; ++c) {
+          if (c < ncol) {
+            const uint32_t off = (uint32_t)((c >> 3) * 1024 + (c & 7) * 128 + ((((lane >> 2) ^ (c & 7)) & 7) << 4)) + kin;
+            *reinterpret_cast<float*>(b2 + off) = to_tf32(v[c]);
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar(AB_B2FULL));
+      // ---- epi-2: D2 rows 16q..16q+15 (lanes 0..15 of this quarter) -> E -> combine -> T2 ----------
+      mbar_wait(bar(AB_D2FULL), it & 1);
+      tc_fence_after();
+      tmem_ld32(tmem_d2 + lane_base, v);
+      tmem_ld8(tmem_d2 + lane_base + 32, v + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar(AB_D2EMPTY));
+      epi_bar_sync();                                   // previous plane's readers of E are done
+      if (lane < 16) {
+        float* er = E + (16 * q + lane) * E_LD;
+#pragma unroll
+        for (int c = 0; c < 40; ++c) er[c] = v[c];
+      }
+      epi_bar_sync();
+      float2* outp = T2 + (size_t)p * my * mzh;
+      for (int idx = et; idx < my * mzh; idx += 128) {
+        const int ky = idx / mzh, kz = idx - ky * mzh;
+        const float cr = E[ky * E_LD + kz], ci = E[ky * E_LD + mzh + kz];
+        const float sr = E[(SIN0 + ky) * E_LD + kz], si = E[(SIN0 + ky) * E_LD + mzh + kz];
+        outp[idx] = make_float2(cr + si, ci - sr);      // (C - iS)(re + i im)
+      }
+    }
+  }
+  // ---- teardown -----------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthesis kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int S_THREADS = 256;
+constexpr int ST_LD = 68;
+struct SSmem {
+  uint32_t ay, bz, by[2], stage, bars, tmem_slot, total;
+};
+__host__ __device__ inline SSmem synthesis_smem(int Nz) {
+  SSmem s;
+  uint32_t o = 0;
+  s.ay = o; o += 2 * 128 * 128;
+  s.bz = o; o += 2 * Nz * 128;
+  s.by[0] = o; o += 2 * ROWS_B * 128;
+  s.by[1] = o; o += 2 * ROWS_B * 128;
+  s.stage = o; o += 4 * 32 * ST_LD * 4;
+  s.bars = o; o += 128;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+enum { SB_BYFULL0 = 0, SB_BYFULL1, SB_BYEMPTY0, SB_BYEMPTY1, SB_DVFULL, SB_OUTFULL0, SB_OUTFULL1, SB_OUTEMPTY0 /*+1*/ };
+
+template <int NZ>
+__global__ void __launch_bounds__(S_THREADS, 1)
+synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, const float* __restrict__ add0,
+                       const float* __restrict__ add1, const float* __restrict__ Ayimg, const float* __restrict__ Bzimg,
+                       int planes, int my, int mzh) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const SSmem L = synthesis_smem(NZ);
+  const uint32_t bar0 = base + L.bars;
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  {
+    const float4* s1 = reinterpret_cast<const float4*>(Ayimg);
+    float4* d1 = reinterpret_cast<float4*>(sm + L.ay);
+    for (int i = threadIdx.x; i < 2 * 128 * 128 / 16; i += S_THREADS) d1[i] = __ldg(s1 + i);
+    const float4* s2 = reinterpret_cast<const float4*>(Bzimg);
+    float4* d2 = reinterpret_cast<float4*>(sm + L.bz);
+    for (int i = threadIdx.x; i < 2 * NZ * 128 / 16; i += S_THREADS) d2[i] = __ldg(s2 + i);
+    float4* z = reinterpret_cast<float4*>(sm + L.by[0]);
+    for (int i = threadIdx.x; i < 2 * 2 * ROWS_B * 128 / 16; i += S_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar(SB_BYFULL0), 64); mbar_init(bar(SB_BYFULL1), 64);
+    mbar_init(bar(SB_BYEMPTY0), 1); mbar_init(bar(SB_BYEMPTY1), 1);
+    mbar_init(bar(SB_DVFULL), 1);
+    mbar_init(bar(SB_OUTFULL0), 1); mbar_init(bar(SB_OUTFULL1), 1);
+    mbar_init(bar(SB_OUTEMPTY0), 128); mbar_init(bar(SB_OUTEMPTY0 + 1), 128);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(base + L.tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const uint32_t tmem_v = tmem;                       // 48 columns
+  const uint32_t tmem_out[2] = {tmem + 128, tmem + 256};
+
+  if (warp == 0) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idy = umma_idesc(128, N1), idz = umma_idesc(128, NZ);
+      int it = 0;
+      for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(bar(SB_BYFULL0 + b), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem_v, umma_desc(base + L.ay + kb * 16384 + k * 32, 1024),
+                   umma_desc(base + L.by[b] + kb * ROWS_B * 128 + k * 32, 1024), idy, (kb | k) ? 1u : 0u);
+        mma_commit(bar(SB_BYEMPTY0 + b));
+        mma_commit(bar(SB_DVFULL));
+        mbar_wait(bar(SB_DVFULL), it & 1);            // V complete in TMEM before it is read as the A operand
+        mbar_wait(bar(SB_OUTEMPTY0 + b), ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < N2 / 8; ++j)
+          mma_ts(tmem_out[b], tmem_v + 8 * j, umma_desc(base + L.bz + (j >> 2) * NZ * 128 + (j & 3) * 32, 1024), idz,
+                 j ? 1u : 0u);
+        mma_commit(bar(SB_OUTFULL0 + b));
+      }
+    }
+  } else if (warp >= 6) {
+    // ===== By builders (64 threads): U[ky][kz] -> [[re, im], [-im, re]] operand tile =====
+    const int bt = (warp - 6) * 32 + lane;
+    int it = 0;
+    for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
+      const int b = it & 1;
+      mbar_wait(bar(SB_BYEMPTY0 + b), ((it >> 1) & 1) ^ 1);
+      const float2* up = U + (size_t)p * my * mzh;
+      uint8_t* by = sm + L.by[b];
+      for (int idx = bt; idx < my * mzh; idx += 64) {
+        const int ky = idx / mzh, kz = idx - ky * mzh;
+        const float2 u = __ldg(up + idx);
+        const float re = to_tf32(u.x), im = to_tf32(u.y);
+        *reinterpret_cast<float*>(by + swz_off(ROWS_B, kz, ky)) = re;
+        *reinterpret_cast<float*>(by + swz_off(ROWS_B, mzh + kz, ky)) = im;
+        *reinterpret_cast<float*>(by + swz_off(ROWS_B, kz, SIN0 + ky)) = -im;
+        *reinterpret_cast<float*>(by + swz_off(ROWS_B, mzh + kz, SIN0 + ky)) = re;
+      }
+      fence_proxy_async();
+      mbar_arrive(bar(SB_BYFULL0 + b));
+    }
+  } else if (warp >= 2) {
+    // ===== epilogue warps (2..5) =====
+    const int q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* st = reinterpret_cast<float*>(sm + L.stage) + q * 32 * ST_LD;
+    constexpr int NCH = NZ / 64;
+    int it = 0;
+    for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
+      const int b = it & 1;
+      mbar_wait(bar(SB_OUTFULL0 + b), (it >> 1) & 1);
+      tc_fence_after();
+      const size_t pbase = (size_t)p * 128 * NZ;
+#pragma unroll
+      for (int h = 0; h < NCH; ++h) {
+        float v[64];
+        tmem_ld32(tmem_out[b] + lane_base + h * 64, v);
+        tmem_ld32(tmem_out[b] + lane_base + h * 64 + 32, v + 32);
+        tmem_ld_wait();
+        if (h == NCH - 1) {
+          tc_fence_before();
+          mbar_arrive(bar(SB_OUTEMPTY0 + b));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+#pragma unroll 4
+        for (int r2 = 0; r2 < 16; ++r2) {
+          const int row = 2 * r2 + (lane >> 4), c4 = lane & 15;
+          float4 o = *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
+          const size_t g = pbase + (size_t)(32 * q + row) * NZ + h * 64 + 4 * c4;
+          if (add0) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(add0 + g));
+            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+          }
+          if (add1) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(add1 + g));
+            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+          }
+          *reinterpret_cast<float4*>(out + g) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+bool tc_supported(const Plan* p) {
+  return p->tc_ok != 0;
+}
+
+// called from pdephi_plan_create (device already selected)
+int tc_plan_init(Plan* p) {
+  p->tc_ok = 0;
+  const bool shape_ok = p->Ny == 128 && (p->Nz == 64 || p->Nz == 128) && p->my <= 32 && 2 * p->mzh <= tc::N2;
+  if (!shape_ok) return PDEPHI_OK;
+  const int NKB = p->Nz / 32;
+  const size_t nB1 = (size_t)NKB * tc::ROWS_B * 32, nA2 = 4 * tc::M2 * 32, nAy = 2 * 128 * 32, nBz = (size_t)2 * p->Nz * 32;
+  const size_t total = (2 * nB1 + nA2 + nAy + 2 * nBz) * sizeof(float);
+  PDEPHI_CUDA(cudaMalloc(&p->tc_arena, total));
+  PDEPHI_CUDA(cudaMemset(p->tc_arena, 0, total));
+  float* f = (float*)p->tc_arena;
+  p->tc_b1[0] = f; f += nB1;
+  p->tc_b1[1] = f; f += nB1;
+  p->tc_a2 = f; f += nA2;
+  p->tc_ay = f; f += nAy;
+  p->tc_bz[0] = f; f += nBz;
+  p->tc_bz[1] = f; f += nBz;
+  const double inv_total = 1.0 / ((double)p->Nx * p->Ny * p->Nz);
+  const int nyq = (p->Nz % 2 == 0 && p->mzh - 1 == p->Nz / 2) ? p->Nz / 2 : -1;
+  // The tensor core drops the low 13 mantissa bits of an fp32 operand it reads itself (the TMA-staged
+  // plane, the TMEM-resident V): a mean relative bias of -2^-11.  It is folded into the constant operand
+  // of the same contraction so the data path keeps round-to-nearest statistics.  PDEPHI_TF32_COMP=0 disables.
+  const char* env = getenv("PDEPHI_TF32_COMP");
+  const double comp = (env && env[0] == '0') ? 1.0 : 1.0 + 1.0 / 2048.0;
+  auto gen = [&](float* img, int kind, int R, int K, int N, int m, int wm, double c) {
+    const int n = R * K;
+    tc::tc_image_kernel<<<(n + 255) / 256, 256>>>(img, kind, R, K, N, m, wm, nyq, inv_total, c);
+  };
+  gen(p->tc_b1[0], 0, tc::ROWS_B, p->Nz, p->Nz, p->mzh, 0, comp);
+  gen(p->tc_b1[1], 0, tc::ROWS_B, p->Nz, p->Nz, p->mzh, 1, comp);
+  gen(p->tc_a2, 1, tc::M2, 128, p->Ny, p->my, 0, 1.0);
+  gen(p->tc_ay, 2, 128, 64, p->Ny, p->my, 0, 1.0);
+  gen(p->tc_bz[0], 3, p->Nz, 64, p->Nz, p->mzh, 1, comp);
+  gen(p->tc_bz[1], 3, p->Nz, 64, p->Nz, p->mzh, 0, comp);
+  PDEPHI_LAUNCH_CHECK("tc_image_kernel");
+  if (!encode_fn()) return PDEPHI_OK;   // no driver entry point: TF32 path stays off
+  p->tc_ok = 1;
+  return PDEPHI_OK;
+}
+
+void tc_plan_destroy(Plan* p) {
+  if (p->tc_arena) cudaFree(p->tc_arena);
+  p->tc_arena = nullptr;
+}
+
+int xstage_analysis(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st);
+int xstage_synthesis(const Plan* p, const float2* Z, float2* ws, const float* mode_scale, const float* row_scale,
+                     long long rs_stride, long long BC, cudaStream_t st);
+
+int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws, cudaStream_t st) {
+  const size_t planes = (size_t)BC * p->Nx;
+  if (planes * 128 > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "analysis_tc: too many rows for the tensor map");
+  if (reinterpret_cast<uintptr_t>(x) & 15) return fail(PDEPHI_ERR_INVALID, "analysis_tc: x must be 16-byte aligned");
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)p->Nz, (cuuint64_t)planes * 128};
+  const cuuint64_t strides[1] = {(cuuint64_t)p->Nz * sizeof(float)};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PDEPHI_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  const int NKB = p->Nz / 32;
+  const tc::ASmem L = tc::analysis_smem(NKB);
+  const size_t smem = L.total + 1024;
+  auto k = tc::analysis_zy_tc_kernel;
+  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)(planes < (size_t)p->num_sms ? planes : (size_t)p->num_sms);
+  {
+    ProfScope ps(K_ANALYSIS_ZY_TC, st);
+    k<<<grid, tc::A_THREADS, smem, st>>>(tmap, ws, p->tc_b1[direction], p->tc_a2, (int)planes, NKB, p->my, p->mzh);
+  }
+  PDEPHI_LAUNCH_CHECK("analysis_zy_tc_kernel");
+  return xstage_analysis(p, ws, X, BC, st);
+}
+
+int synthesis_tc(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1,
+                 const float* mode_scale, const float* row_scale, long long rs_stride, long long BC, int direction,
+                 float2* ws, cudaStream_t st) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(out) || !al16(add0) || !al16(add1)) return fail(PDEPHI_ERR_INVALID, "synthesis_tc: buffers must be 16-byte aligned");
+  int rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
+  if (rc) return rc;
+  const size_t planes = (size_t)BC * p->Nx;
+  if (planes > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis_tc: too many planes");
+  const tc::SSmem L = tc::synthesis_smem(p->Nz);
+  const size_t smem = L.total + 1024;
+  const int grid = (int)(planes < (size_t)p->num_sms ? planes : (size_t)p->num_sms);
+  if (p->Nz == 128) {
+    auto k = tc::synthesis_zy_tc_kernel<128>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_SYNTHESIS_ZY_TC, st);
+    k<<<grid, tc::S_THREADS, smem, st>>>(ws, out, add0, add1, p->tc_ay, p->tc_bz[direction], (int)planes, p->my, p->mzh);
+  } else {
+    auto k = tc::synthesis_zy_tc_kernel<64>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_SYNTHESIS_ZY_TC, st);
+    k<<<grid, tc::S_THREADS, smem, st>>>(ws, out, add0, add1, p->tc_ay, p->tc_bz[direction], (int)planes, p->my, p->mzh);
+  }
+  PDEPHI_LAUNCH_CHECK("synthesis_zy_tc_kernel");
+  return PDEPHI_OK;
 }
 
 }  // namespace pdephi
