@@ -93,23 +93,26 @@ int pdephi_synthesis_c2r(pdephi_plan_t plan, const float* Z, float* out, const f
  *   (rational_fourier.py:135-144), mask [M] decay mask (stability.py:40-57).
  *   Y [B, O, M] complex   = sum_i R[o,i,k] X[b,i,k],  R = P(k) / (Q(k) + eps)  (unmasked, unscaled)
  *   stats [B*O, 4] float  = { a = sum|Y|^2 + proj_eps, b = sum mask^2|Y|^2 + proj_eps, s = sqrt(a/b), 0 }
- * The projected modes are Z = mask * s * Y; K3 applies that scaling on the fly. */
+ * The projected modes are Z = mask * s * Y; K3 applies that scaling on the fly.
+ * R_out / Qe_out [O, I, M] float (both or neither; may be NULL for inference): the transfer function and
+ * Q(k)+eps, materialised once per forward so the backward streams them instead of re-evaluating. */
 int pdephi_rational_mix_fwd(const float* X, const float* P, const float* Q, const float* monoP,
                             const float* monoQ, int order_p, int order_q, float eps, const float* mask,
-                            float proj_eps, float* Y, float* stats, int B, int I, int O, long long M,
-                            pdephi_stream_t stream);
+                            float proj_eps, float* Y, float* stats, float* R_out, float* Qe_out, int B, int I,
+                            int O, long long M, pdephi_stream_t stream);
 
 /* Backward of Z = mask*s*Y (stability.py:59-103) :  dZ [B*O, M] complex -> dY [B*O, M] complex */
 int pdephi_projection_bwd(const float* dZ, const float* Y, const float* mask, const float* stats,
                           float* dY, long long rows, long long M, pdephi_stream_t stream);
 
-/* Backward of the rational mix: dX [B,I,M] complex, dP [O,I,op^3], dQ [O,I,oq^3] (entries with
- * a+b+c >= order are written as zeros, as autograd does).  Deterministic two-stage reduction. */
+/* Backward of the rational mix from the materialised R, Qe of the forward: dX [B,I,M] complex,
+ * dP [O,I,op^3], dQ [O,I,oq^3] (entries with a+b+c >= order are written as zeros, as autograd does).
+ * Deterministic two-stage reduction. */
 size_t pdephi_rational_mix_bwd_workspace_bytes(int order_p, int order_q, int I, int O, long long M);
-int pdephi_rational_mix_bwd(const float* X, const float* dY, const float* P, const float* Q,
-                            const float* monoP, const float* monoQ, int order_p, int order_q, float eps,
-                            float* dX, float* dP, float* dQ, int B, int I, int O, long long M,
-                            void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+int pdephi_rational_mix_bwd(const float* X, const float* dY, const float* R, const float* Qe,
+                            const float* monoP, const float* monoQ, int order_p, int order_q, float* dX,
+                            float* dP, float* dQ, int B, int I, int O, long long M, void* workspace,
+                            size_t workspace_bytes, pdephi_stream_t stream);
 
 /* ---- K2': complex channel mix of SpectralConv3D (spectral_layers.py:66) ---------------------
  *   W [O, I, mxy, mz] complex parameter; only kz < mzh is used (oracle convention 2).

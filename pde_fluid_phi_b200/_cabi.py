@@ -30,10 +30,11 @@ SIGNATURES = {
     "pdephi_synthesis_c2r": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                      c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pdephi_rational_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
-                                        c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p]),
+                                        c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong,
+                                        c_void_p]),
     "pdephi_projection_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p]),
     "pdephi_rational_mix_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_longlong]),
-    "pdephi_rational_mix_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+    "pdephi_rational_mix_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_size_t,
                                         c_void_p]),
     "pdephi_complex_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_void_p]),

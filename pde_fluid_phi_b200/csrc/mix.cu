@@ -59,7 +59,8 @@ template <int OP, int OQ, bool TR>
 __global__ void __launch_bounds__(MIX_THREADS)
 rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float* __restrict__ P,
                     const float* __restrict__ Q, const float* __restrict__ monoP, const float* __restrict__ monoQ,
-                    float eps, int B, int U, int V, long long M, MonoOffsets offs) {
+                    float eps, float* __restrict__ Rout, float* __restrict__ Qeout, int B, int U, int V, long long M,
+                    MonoOffsets offs) {
   constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
   constexpr int TP4 = Tri<OP>::TP4, TQ4 = Tri<OQ>::TP4;
   extern __shared__ __align__(16) float smem[];
@@ -119,7 +120,13 @@ rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, con
           const float4 c = q4[t];
           cq[4 * t] = c.x; cq[4 * t + 1] = c.y; cq[4 * t + 2] = c.z; cq[4 * t + 3] = c.w;
         }
-        const float R = eval_R<TPN, TQN>(cp, cq, mp, mq, eps, nullptr);
+        float qe;
+        const float R = eval_R<TPN, TQN>(cp, cq, mp, mq, eps, &qe);
+        if (!TR && Rout && b0 == 0 && k < M && u0 + ul < U) {   // materialise R and Q+eps once for the backward
+          const size_t ri = ((size_t)(u0 + ul) * V + v) * M + k;
+          Rout[ri] = R;
+          Qeout[ri] = qe;
+        }
 #pragma unroll
         for (int j = 0; j < BT; ++j) {
           acc[ul][j].x = fmaf(R, xin[j].x, acc[ul][j].x);
@@ -202,8 +209,52 @@ projection_bwd_kernel(const float2* __restrict__ dZ, const float2* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// dP / dQ: thread = one (o,i) pair, coefficients and 2T accumulators in registers, loop over a
-// k range; X / dY / monomial tiles staged through shared memory.  Stage 1 writes per-k-split
+// dX[b][i][k] = sum_o R[o][i][k] dY[b][o][k] from the materialised R: a streaming kernel, R is read
+// exactly once (thread = mode k, IT input channels x BT batch entries per thread).
+// ---------------------------------------------------------------------------------------------
+constexpr int IT = 4;
+__global__ void __launch_bounds__(MIX_THREADS)
+mix_from_R_kernel(const float2* __restrict__ dY, float2* __restrict__ dX, const float* __restrict__ R, int B, int I,
+                  int O, long long M) {
+  const long long k = (long long)blockIdx.x * MIX_THREADS + threadIdx.x;
+  const long long kc = k < M ? k : M - 1;
+  const int i0 = blockIdx.y * IT;
+  for (int b0 = 0; b0 < B; b0 += BT) {
+    float2 acc[IT][BT];
+#pragma unroll
+    for (int a = 0; a < IT; ++a)
+#pragma unroll
+      for (int j = 0; j < BT; ++j) acc[a][j] = make_float2(0.f, 0.f);
+#pragma unroll 2
+    for (int o = 0; o < O; ++o) {
+      float r[IT];
+#pragma unroll
+      for (int a = 0; a < IT; ++a) r[a] = __ldg(R + ((size_t)o * I + min(i0 + a, I - 1)) * M + kc);
+      float2 g[BT];
+#pragma unroll
+      for (int j = 0; j < BT; ++j)
+        g[j] = (b0 + j < B) ? __ldg(dY + ((size_t)(b0 + j) * O + o) * M + kc) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < IT; ++a)
+#pragma unroll
+        for (int j = 0; j < BT; ++j) {
+          acc[a][j].x = fmaf(r[a], g[j].x, acc[a][j].x);
+          acc[a][j].y = fmaf(r[a], g[j].y, acc[a][j].y);
+        }
+    }
+    if (k < M) {
+#pragma unroll
+      for (int a = 0; a < IT; ++a)
+#pragma unroll
+        for (int j = 0; j < BT; ++j)
+          if (i0 + a < I && b0 + j < B) dX[((size_t)(b0 + j) * I + i0 + a) * M + k] = acc[a][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dP / dQ: thread = one (o,i) pair with its 2T accumulators in registers, looping over a k range;
+// X / dY / R / Q+eps / monomial tiles staged through shared memory.  Stage 1 writes per-k-split
 // partials, stage 2 sums them in fixed order and scatters into the [O,I,ord^3] gradients.
 //   dR[o,i,k] = sum_b Re(conj(X[b,i,k]) dY[b,o,k]);  g = dR/Qe;  dP_t += g mono_t;  dQ_t += -g R mono_t
 // ---------------------------------------------------------------------------------------------
@@ -213,16 +264,21 @@ constexpr int KTP = KT + 1;
 
 template <int OP, int OQ>
 __global__ void __launch_bounds__(DPQ_THREADS)
-rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, const float* __restrict__ P,
-                    const float* __restrict__ Q, const float* __restrict__ monoP, const float* __restrict__ monoQ,
-                    float eps, float* __restrict__ partial, int B, int I, int O, long long M, long long kchunk,
-                    int nOmax, MonoOffsets offs) {
+rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, const float* __restrict__ R,
+                    const float* __restrict__ Qe, const float* __restrict__ monoP, const float* __restrict__ monoQ,
+                    float* __restrict__ partial, int B, int I, int O, long long M, long long kchunk, int nOmax) {
   constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
+  constexpr int TP4 = Tri<OP>::TP4, TQ4 = Tri<OQ>::TP4;
+  constexpr bool SAME = (OP == OQ);
   extern __shared__ __align__(16) float smem[];
   float2* Xs = reinterpret_cast<float2*>(smem);                 // [BT][I][KTP]
   float2* Ys = Xs + (size_t)BT * I * KTP;                        // [BT][nOmax][KTP]
-  float* mPs = reinterpret_cast<float*>(Ys + (size_t)BT * nOmax * KTP);  // [TPN][KT]
-  float* mQs = mPs + TPN * KT;                                   // [TQN][KT]
+  size_t f2 = (size_t)BT * I * KTP + (size_t)BT * nOmax * KTP;
+  f2 += (f2 & 1);                                                // keep the float4-read monomial tiles 16-byte aligned
+  float* Rs = reinterpret_cast<float*>(Xs + f2);                 // [256][KTP]
+  float* Qs = Rs + DPQ_THREADS * KTP;                            // [256][KTP]
+  float* mPs = Qs + DPQ_THREADS * KTP;                           // [KT][TP4]   (16-byte aligned: see host)
+  float* mQs = mPs + KT * TP4;                                   // [KT][TQ4]
 
   const long long npairs = (long long)O * I;
   const long long q0 = (long long)blockIdx.x * DPQ_THREADS;
@@ -234,11 +290,11 @@ rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY,
   const int o_hi = (int)min((long long)O - 1, (q0 + DPQ_THREADS - 1) / I);
   const int nO = o_hi - o_lo + 1;
 
-  float cp[TPN], cq[TQN], ap[TPN], aq[TQN];
+  float ap[TPN], aq[TQN];
 #pragma unroll
-  for (int t = 0; t < TPN; ++t) { cp[t] = __ldg(P + (size_t)q * (OP * OP * OP) + offs.p[t]); ap[t] = 0.f; }
+  for (int t = 0; t < TPN; ++t) ap[t] = 0.f;
 #pragma unroll
-  for (int t = 0; t < TQN; ++t) { cq[t] = __ldg(Q + (size_t)q * (OQ * OQ * OQ) + offs.q[t]); aq[t] = 0.f; }
+  for (int t = 0; t < TQN; ++t) aq[t] = 0.f;
 
   const long long k_lo = (long long)blockIdx.y * kchunk;
   const long long k_hi = min(M, k_lo + kchunk);
@@ -263,11 +319,21 @@ rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY,
         Ys[((size_t)bb * nOmax + oo) * KTP + kk] = v;
       }
       if (b0 == 0) {
-        for (int idx = threadIdx.x; idx < (TPN + TQN) * KT; idx += DPQ_THREADS) {
-          const int kk = idx % KT, t = idx / KT;
+        for (int idx = threadIdx.x; idx < DPQ_THREADS * KT; idx += DPQ_THREADS) {
+          const int kk = idx % KT, pr = idx / KT;
+          const long long qq = min(q0 + pr, npairs - 1);
           const long long k = min(k0 + kk, M - 1);
-          if (t < TPN) mPs[t * KT + kk] = __ldg(monoP + (size_t)t * M + k);
-          else mQs[(t - TPN) * KT + kk] = __ldg(monoQ + (size_t)(t - TPN) * M + k);
+          Rs[pr * KTP + kk] = __ldg(R + (size_t)qq * M + k);
+          Qs[pr * KTP + kk] = __ldg(Qe + (size_t)qq * M + k);
+        }
+        for (int idx = threadIdx.x; idx < KT * (TP4 + (SAME ? 0 : TQ4)); idx += DPQ_THREADS) {
+          const bool isq = idx >= KT * TP4;
+          const int j = isq ? idx - KT * TP4 : idx;
+          const int T4 = isq ? TQ4 : TP4, TN = isq ? TQN : TPN;
+          const int kk = j / T4, t = j % T4;
+          const long long k = min(k0 + kk, M - 1);
+          const float v = (t < TN) ? __ldg((isq ? monoQ : monoP) + (size_t)t * M + k) : 0.f;
+          (isq ? mQs : mPs)[j] = v;
         }
       }
       __syncthreads();
@@ -286,19 +352,31 @@ rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY,
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk) {
       if (k0 + kk < k_hi) {
-        float mp[TPN], mq[TQN];
-#pragma unroll
-        for (int t = 0; t < TPN; ++t) mp[t] = mPs[t * KT + kk];
-#pragma unroll
-        for (int t = 0; t < TQN; ++t) mq[t] = mQs[t * KT + kk];
-        float qe;
-        const float R = eval_R<TPN, TQN>(cp, cq, mp, mq, eps, &qe);
+        const float rr = Rs[threadIdx.x * KTP + kk], qe = Qs[threadIdx.x * KTP + kk];
         const float g = __fdiv_rn(dR[kk], qe);
-        const float h = -g * R;
+        const float h = -g * rr;
+        const float4* p4 = reinterpret_cast<const float4*>(mPs + kk * TP4);
+        const float4* q4 = reinterpret_cast<const float4*>((SAME ? mPs : mQs) + kk * (SAME ? TP4 : TQ4));
 #pragma unroll
-        for (int t = 0; t < TPN; ++t) ap[t] = fmaf(g, mp[t], ap[t]);
+        for (int t4 = 0; t4 < TP4 / 4; ++t4) {
+          const float4 m = p4[t4];
+          const float mm[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-        for (int t = 0; t < TQN; ++t) aq[t] = fmaf(h, mq[t], aq[t]);
+          for (int e = 0; e < 4; ++e) {
+            if (4 * t4 + e < TPN) ap[4 * t4 + e] = fmaf(g, mm[e], ap[4 * t4 + e]);
+            if (SAME && 4 * t4 + e < TQN) aq[4 * t4 + e] = fmaf(h, mm[e], aq[4 * t4 + e]);
+          }
+        }
+        if (!SAME) {
+#pragma unroll
+          for (int t4 = 0; t4 < TQ4 / 4; ++t4) {
+            const float4 m = q4[t4];
+            const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (4 * t4 + e < TQN) aq[4 * t4 + e] = fmaf(h, mm[e], aq[4 * t4 + e]);
+          }
+        }
       }
     }
   }
@@ -418,41 +496,27 @@ complex_dw_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, f
 }
 
 // ------------------------------- host-side dispatch -------------------------------------------
-template <int OP, int OQ, bool TR>
+template <int OP, int OQ>
 static int launch_mix(const float2* in, float2* out, const float* P, const float* Q, const float* monoP,
-                      const float* monoQ, float eps, int B, int U, int V, long long M, const MonoOffsets& offs,
-                      cudaStream_t st) {
+                      const float* monoQ, float eps, float* Rout, float* Qeout, int B, int U, int V, long long M,
+                      const MonoOffsets& offs, cudaStream_t st) {
   const size_t smem = (size_t)UT * V * (Tri<OP>::TP4 + Tri<OQ>::TP4) * sizeof(float);
-  auto k = rational_mix_kernel<OP, OQ, TR>;
+  auto k = rational_mix_kernel<OP, OQ, false>;
+  if (smem > 200 * 1024) return fail(PDEPHI_ERR_UNSUPPORTED, "rational_mix_fwd: %d input channels exceed shared memory", V);
   if (smem > 48 * 1024) PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (U + UT - 1) / UT);
   {
-    ProfScope ps(TR ? K_RATIONAL_MIX_T : K_RATIONAL_MIX, st);
-    k<<<grid, MIX_THREADS, smem, st>>>(in, out, P, Q, monoP, monoQ, eps, B, U, V, M, offs);
+    ProfScope ps(K_RATIONAL_MIX, st);
+    k<<<grid, MIX_THREADS, smem, st>>>(in, out, P, Q, monoP, monoQ, eps, Rout, Qeout, B, U, V, M, offs);
   }
   PDEPHI_LAUNCH_CHECK("rational_mix_kernel");
   return PDEPHI_OK;
 }
 
-template <bool TR>
-static int dispatch_mix(int op, int oq, const float2* in, float2* out, const float* P, const float* Q,
-                        const float* monoP, const float* monoQ, float eps, int B, int U, int V, long long M,
-                        cudaStream_t st) {
-  MonoOffsets offs;
-  memset(&offs, 0, sizeof(offs));
-  fill_offsets(op, offs.p);
-  fill_offsets(oq, offs.q);
-#define CASE(a, b) \
-  if (op == a && oq == b) return launch_mix<a, b, TR>(in, out, P, Q, monoP, monoQ, eps, B, U, V, M, offs, st);
-  CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 2) CASE(3, 3) CASE(3, 4) CASE(4, 2) CASE(4, 3) CASE(4, 4)
-#undef CASE
-  return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) outside the supported range 2..4", op, oq);
-}
-
 static void dpq_geometry(int I, int O, long long M, int* pair_blocks, int* KS, long long* kchunk, int* nOmax) {
   const long long npairs = (long long)O * I;
   *pair_blocks = (int)((npairs + DPQ_THREADS - 1) / DPQ_THREADS);
-  long long ks = (4 * 148 + *pair_blocks - 1) / *pair_blocks;
+  long long ks = (6 * 148 + *pair_blocks - 1) / *pair_blocks;
   const long long max_ks = (M + 63) / 64;
   if (ks > max_ks) ks = max_ks;
   if (ks < 1) ks = 1;
@@ -465,21 +529,23 @@ static void dpq_geometry(int I, int O, long long M, int* pair_blocks, int* KS, l
 }
 
 template <int OP, int OQ>
-static int launch_dpq(const float2* X, const float2* dY, const float* P, const float* Q, const float* monoP,
-                      const float* monoQ, float eps, float* dP, float* dQ, int B, int I, int O, long long M,
-                      float* partial, const MonoOffsets& offs, cudaStream_t st) {
+static int launch_dpq(const float2* X, const float2* dY, const float* R, const float* Qe, const float* monoP,
+                      const float* monoQ, float* dP, float* dQ, int B, int I, int O, long long M, float* partial,
+                      const MonoOffsets& offs, cudaStream_t st) {
   int pair_blocks, KS, nOmax;
   long long kchunk;
   dpq_geometry(I, O, M, &pair_blocks, &KS, &kchunk, &nOmax);
   constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
-  const size_t smem = ((size_t)BT * I * KTP + (size_t)BT * nOmax * KTP) * sizeof(float2) + (TPN + TQN) * KT * sizeof(float);
+  // float2 tiles (8-byte units) then float tiles; 2*DPQ_THREADS*KTP floats = even count keeps mPs 16-byte aligned
+  size_t f2 = (size_t)BT * I * KTP + (size_t)BT * nOmax * KTP;
+  if (f2 & 1) f2 += 1;
+  const size_t smem = f2 * sizeof(float2) + (2 * (size_t)DPQ_THREADS * KTP + KT * (Tri<OP>::TP4 + Tri<OQ>::TP4)) * sizeof(float);
   auto k = rational_dpq_kernel<OP, OQ>;
   if (smem > 200 * 1024) return fail(PDEPHI_ERR_UNSUPPORTED, "rational_mix_bwd: %d input channels exceed shared memory", I);
   if (smem > 48 * 1024) PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope ps(K_RATIONAL_DPQ, st);
-    k<<<dim3(pair_blocks, KS), DPQ_THREADS, smem, st>>>(X, dY, P, Q, monoP, monoQ, eps, partial, B, I, O, M, kchunk,
-                                                       nOmax, offs);
+    k<<<dim3(pair_blocks, KS), DPQ_THREADS, smem, st>>>(X, dY, R, Qe, monoP, monoQ, partial, B, I, O, M, kchunk, nOmax);
   }
   PDEPHI_LAUNCH_CHECK("rational_dpq_kernel");
   const long long npairs = (long long)O * I;
@@ -495,15 +561,28 @@ static int launch_dpq(const float2* X, const float2* dY, const float* P, const f
 
 using namespace pdephi;
 
+#define ORDER_CASES CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 2) CASE(3, 3) CASE(3, 4) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+
 extern "C" int pdephi_rational_mix_fwd(const float* X, const float* P, const float* Q, const float* monoP,
                                        const float* monoQ, int order_p, int order_q, float eps, const float* mask,
-                                       float proj_eps, float* Y, float* stats, int B, int I, int O, long long M,
-                                       pdephi_stream_t stream) {
+                                       float proj_eps, float* Y, float* stats, float* R_out, float* Qe_out, int B,
+                                       int I, int O, long long M, pdephi_stream_t stream) {
   PDEPHI_REQUIRE(X && P && Q && monoP && monoQ && mask && Y && stats, "rational_mix_fwd: null pointer");
+  PDEPHI_REQUIRE((R_out == nullptr) == (Qe_out == nullptr), "rational_mix_fwd: R_out and Qe_out must both be given or both be NULL");
   PDEPHI_REQUIRE(B > 0 && I > 0 && O > 0 && M > 0, "rational_mix_fwd: non-positive size");
   PDEPHI_REQUIRE((long long)B * O <= 0x7fffffffLL, "rational_mix_fwd: too many rows");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = dispatch_mix<false>(order_p, order_q, (const float2*)X, (float2*)Y, P, Q, monoP, monoQ, eps, B, O, I, M, st);
+  MonoOffsets offs;
+  memset(&offs, 0, sizeof(offs));
+  fill_offsets(order_p, offs.p);
+  fill_offsets(order_q, offs.q);
+  int rc = -1;
+#define CASE(a, b)                                                                                                   \
+  if (order_p == a && order_q == b)                                                                                  \
+    rc = launch_mix<a, b>((const float2*)X, (float2*)Y, P, Q, monoP, monoQ, eps, R_out, Qe_out, B, O, I, M, offs, st);
+  ORDER_CASES
+#undef CASE
+  if (rc == -1) return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) outside the supported range 2..4", order_p, order_q);
   if (rc) return rc;
   {
     ProfScope ps(K_PROJ_STATS, st);
@@ -534,27 +613,31 @@ extern "C" size_t pdephi_rational_mix_bwd_workspace_bytes(int order_p, int order
   return align_up((size_t)KS * O * I * (tri(order_p) + tri(order_q)) * sizeof(float), 256);
 }
 
-extern "C" int pdephi_rational_mix_bwd(const float* X, const float* dY, const float* P, const float* Q,
-                                       const float* monoP, const float* monoQ, int order_p, int order_q, float eps,
-                                       float* dX, float* dP, float* dQ, int B, int I, int O, long long M,
-                                       void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
-  PDEPHI_REQUIRE(X && dY && P && Q && monoP && monoQ && dX && dP && dQ, "rational_mix_bwd: null pointer");
+extern "C" int pdephi_rational_mix_bwd(const float* X, const float* dY, const float* R, const float* Qe,
+                                       const float* monoP, const float* monoQ, int order_p, int order_q, float* dX,
+                                       float* dP, float* dQ, int B, int I, int O, long long M, void* workspace,
+                                       size_t workspace_bytes, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(X && dY && R && Qe && monoP && monoQ && dX && dP && dQ, "rational_mix_bwd: null pointer");
   PDEPHI_REQUIRE(B > 0 && I > 0 && O > 0 && M > 0, "rational_mix_bwd: non-positive size");
   const size_t need = pdephi_rational_mix_bwd_workspace_bytes(order_p, order_q, I, O, M);
   if (!workspace || workspace_bytes < need)
     return fail(PDEPHI_ERR_WORKSPACE, "rational_mix_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = dispatch_mix<true>(order_p, order_q, (const float2*)dY, (float2*)dX, P, Q, monoP, monoQ, eps, B, I, O, M, st);
-  if (rc) return rc;
+  {
+    dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (I + IT - 1) / IT);
+    ProfScope ps(K_RATIONAL_MIX_T, st);
+    mix_from_R_kernel<<<grid, MIX_THREADS, 0, st>>>((const float2*)dY, (float2*)dX, R, B, I, O, M);
+  }
+  PDEPHI_LAUNCH_CHECK("mix_from_R_kernel");
   MonoOffsets offs;
   memset(&offs, 0, sizeof(offs));
   fill_offsets(order_p, offs.p);
   fill_offsets(order_q, offs.q);
 #define CASE(a, b)                                                                                          \
   if (order_p == a && order_q == b)                                                                         \
-    return launch_dpq<a, b>((const float2*)X, (const float2*)dY, P, Q, monoP, monoQ, eps, dP, dQ, B, I, O, M, \
+    return launch_dpq<a, b>((const float2*)X, (const float2*)dY, R, Qe, monoP, monoQ, dP, dQ, B, I, O, M,    \
                             (float*)workspace, offs, st);
-  CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 2) CASE(3, 3) CASE(3, 4) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+  ORDER_CASES
 #undef CASE
   return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) outside the supported range 2..4", order_p, order_q);
 }

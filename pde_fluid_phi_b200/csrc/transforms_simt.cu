@@ -102,42 +102,80 @@ analysis_zy_kernel(const float* __restrict__ x, float2* __restrict__ T2, const f
 //   analysis : out[kx][p] = sum_x tw[x][kx] * in[x][p]        (tw = ax [Nx][mx])
 //   synthesis: out[x][p]  = sum_kx tw[kx][x] * in[kx][p]*scale (tw = sx [mx][Nx])
 // Both are "out[r][p] = sum_k tw[k][r] * in[k][p]" with R output rows and K contracted rows.
+// A warp owns XT output rows x 64 modes (2 per lane, one 128-bit load per k); the twiddles of the
+// CTA's row range sit in shared memory and are read as warp-wide broadcasts, so the inner loop is
+// 4 LDS.128 + 1 LDG.128 per 64 FFMA.
 // ---------------------------------------------------------------------------------------------
-constexpr int XT = 8;  // output rows per thread
+constexpr int XT = 8;   // output rows per warp
+constexpr int XW = 8;   // warps (row groups) per CTA
 template <bool SCALED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * XW)
 xstage_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ tw, int K, int R,
               int P, const float* __restrict__ mode_scale, const float* __restrict__ row_scale,
               long long row_scale_stride) {
-  const int p = blockIdx.x * 64 + threadIdx.x;
+  extern __shared__ __align__(16) float2 tws[];      // [K][XT*XW] twiddles of this CTA's rows
+  const int lane = threadIdx.x, wy = threadIdx.y;
   const size_t bc = blockIdx.y;
-  const int r0 = (blockIdx.z * 4 + threadIdx.y) * XT;
-  if (p >= P || r0 >= R) return;
-  int ri[XT];
+  const int rblk = blockIdx.z * (XT * XW);
+  for (int i = wy * 32 + lane; i < K * XT * XW; i += 32 * blockDim.y) {
+    const int k = i / (XT * XW), j = i - k * (XT * XW);
+    tws[i] = (rblk + j < R) ? __ldg(tw + (size_t)k * R + rblk + j) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int r0 = rblk + wy * XT;
+  if (r0 >= R) return;
+  const int p0 = (blockIdx.x * 32 + lane) * 2;
+  const bool pair = ((P & 1) == 0);                   // 128-bit path needs 16-byte aligned rows
+  const bool v0 = p0 < P, v1 = p0 + 1 < P;
+  float2 acc0[XT], acc1[XT];
 #pragma unroll
-  for (int j = 0; j < XT; ++j) ri[j] = min(r0 + j, R - 1);
-  float2 acc[XT];
-#pragma unroll
-  for (int j = 0; j < XT; ++j) acc[j] = make_float2(0.f, 0.f);
-  const float2* inp = in + bc * (size_t)K * P + p;
+  for (int j = 0; j < XT; ++j) acc0[j] = acc1[j] = make_float2(0.f, 0.f);
+  const float2* inp = in + bc * (size_t)K * P;
   float rs = 1.f;
   if (SCALED && row_scale) rs = __ldg(row_scale + bc * row_scale_stride);
+  const int pc0 = v0 ? p0 : 0, pc1 = v1 ? p0 + 1 : pc0;
 #pragma unroll 2
   for (int k = 0; k < K; ++k) {
-    float2 v = __ldg(inp + (size_t)k * P);
-    if (SCALED) {
-      const float sc = mode_scale ? __ldg(mode_scale + (size_t)k * P + p) * rs : rs;
-      v.x *= sc;
-      v.y *= sc;
+    float2 a, b;
+    if (pair && v1) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(inp + (size_t)k * P + p0));
+      a = make_float2(q.x, q.y);
+      b = make_float2(q.z, q.w);
+    } else {
+      a = __ldg(inp + (size_t)k * P + pc0);
+      b = __ldg(inp + (size_t)k * P + pc1);
     }
-    const float2* trow = tw + (size_t)k * R;
+    if (SCALED) {
+      float s0 = rs, s1 = rs;
+      if (mode_scale) {
+        s0 *= __ldg(mode_scale + (size_t)k * P + pc0);
+        s1 *= __ldg(mode_scale + (size_t)k * P + pc1);
+      }
+      a.x *= s0; a.y *= s0; b.x *= s1; b.y *= s1;
+    }
+    const float4* t4 = reinterpret_cast<const float4*>(tws + (size_t)k * (XT * XW) + wy * XT);
 #pragma unroll
-    for (int j = 0; j < XT; ++j) cfma(acc[j], __ldg(trow + ri[j]), v);
+    for (int j = 0; j < XT / 2; ++j) {
+      const float4 t = t4[j];
+      const float2 ta = make_float2(t.x, t.y), tb = make_float2(t.z, t.w);
+      cfma(acc0[2 * j], ta, a);
+      cfma(acc1[2 * j], ta, b);
+      cfma(acc0[2 * j + 1], tb, a);
+      cfma(acc1[2 * j + 1], tb, b);
+    }
   }
-  float2* outp = out + bc * (size_t)R * P + p;
+  float2* outp = out + bc * (size_t)R * P;
 #pragma unroll
-  for (int j = 0; j < XT; ++j)
-    if (r0 + j < R) outp[(size_t)(r0 + j) * P] = acc[j];
+  for (int j = 0; j < XT; ++j) {
+    if (r0 + j < R) {
+      if (pair && v1) {
+        *reinterpret_cast<float4*>(outp + (size_t)(r0 + j) * P + p0) = make_float4(acc0[j].x, acc0[j].y, acc1[j].x, acc1[j].y);
+      } else {
+        if (v0) outp[(size_t)(r0 + j) * P + p0] = acc0[j];
+        if (v1) outp[(size_t)(r0 + j) * P + p0 + 1] = acc1[j];
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -236,29 +274,38 @@ static int pick_group(int mzh) {
   return best;
 }
 
-int xstage_analysis(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st) {
-  const int P = p->my * p->mzh;
-  if (BC > 65535) return fail(PDEPHI_ERR_UNSUPPORTED, "analysis: batch*channels > 65535");
-  dim3 grid((P + 63) / 64, (unsigned)BC, (p->mx + 4 * XT - 1) / (4 * XT));
-  {
+static int launch_xstage(bool scaled, const float2* in, float2* out, const float2* tw, int K, int R, int P,
+                         const float* mode_scale, const float* row_scale, long long rs_stride, long long BC,
+                         size_t smem_optin, cudaStream_t st) {
+  if (BC > 65535) return fail(PDEPHI_ERR_UNSUPPORTED, "x stage: batch*channels > 65535");
+  const size_t smem = (size_t)K * XT * XW * sizeof(float2);
+  if (smem > smem_optin) return fail(PDEPHI_ERR_UNSUPPORTED, "x stage: %d contracted rows exceed shared memory", K);
+  dim3 grid((P + 63) / 64, (unsigned)BC, (R + XT * XW - 1) / (XT * XW));
+  const int rows_here = R < XT * XW ? R : XT * XW;
+  dim3 block(32, (rows_here + XT - 1) / XT);
+  if (scaled) {
+    auto k = xstage_kernel<true>;
+    if (smem > 48 * 1024) PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_SYNTHESIS_X, st);
+    k<<<grid, block, smem, st>>>(in, out, tw, K, R, P, mode_scale, row_scale, rs_stride);
+  } else {
+    auto k = xstage_kernel<false>;
+    if (smem > 48 * 1024) PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_ANALYSIS_X, st);
-    xstage_kernel<false><<<grid, dim3(64, 4), 0, st>>>(ws, X, p->ax, p->Nx, p->mx, P, nullptr, nullptr, 0);
+    k<<<grid, block, smem, st>>>(in, out, tw, K, R, P, nullptr, nullptr, 0);
   }
-  PDEPHI_LAUNCH_CHECK("xstage_kernel(analysis)");
+  PDEPHI_LAUNCH_CHECK("xstage_kernel");
   return PDEPHI_OK;
+}
+
+int xstage_analysis(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st) {
+  return launch_xstage(false, ws, X, p->ax, p->Nx, p->mx, p->my * p->mzh, nullptr, nullptr, 0, BC, p->smem_optin, st);
 }
 
 int xstage_synthesis(const Plan* p, const float2* Z, float2* ws, const float* mode_scale, const float* row_scale,
                      long long rs_stride, long long BC, cudaStream_t st) {
-  const int P = p->my * p->mzh;
-  if (BC > 65535) return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis: batch*channels > 65535");
-  dim3 grid((P + 63) / 64, (unsigned)BC, (p->Nx + 4 * XT - 1) / (4 * XT));
-  {
-    ProfScope ps(K_SYNTHESIS_X, st);
-    xstage_kernel<true><<<grid, dim3(64, 4), 0, st>>>(Z, ws, p->sx, p->mx, p->Nx, P, mode_scale, row_scale, rs_stride);
-  }
-  PDEPHI_LAUNCH_CHECK("xstage_kernel(synthesis)");
-  return PDEPHI_OK;
+  return launch_xstage(true, Z, ws, p->sx, p->mx, p->Nx, p->my * p->mzh, mode_scale, row_scale, rs_stride, BC,
+                       p->smem_optin, st);
 }
 
 int analysis_simt(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws,

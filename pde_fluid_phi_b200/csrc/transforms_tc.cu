@@ -343,9 +343,11 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
 
 // ------------------------------------------------------------------------------------------------
 // synthesis kernel
+//   warp 0: MMA issuer + TMEM owner, warps 2..9: epilogue (TMEM quarter = warp % 4, column half = (warp-2)/4),
+//   warps 10..11: By builders.  12 warps so that the epilogue keeps ~64 KB of addend loads in flight per SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int S_THREADS = 256;
-constexpr int ST_LD = 68;
+constexpr int S_THREADS = 384;
+constexpr int S_EPI_WARPS = 8;
 struct SSmem {
   uint32_t ay, bz, by[2], stage, bars, tmem_slot, total;
 };
@@ -356,13 +358,15 @@ __host__ __device__ inline SSmem synthesis_smem(int Nz) {
   s.bz = o; o += 2 * Nz * 128;
   s.by[0] = o; o += 2 * ROWS_B * 128;
   s.by[1] = o; o += 2 * ROWS_B * 128;
-  s.stage = o; o += 4 * 32 * ST_LD * 4;
+  s.stage = o; o += S_EPI_WARPS * 32 * (Nz / 2 + 4) * 4;
   s.bars = o; o += 128;
   s.tmem_slot = o; o += 64;
   s.total = o;
   return s;
 }
 enum { SB_BYFULL0 = 0, SB_BYFULL1, SB_BYEMPTY0, SB_BYEMPTY1, SB_DVFULL, SB_OUTFULL0, SB_OUTFULL1, SB_OUTEMPTY0 /*+1*/ };
+
+__device__ __forceinline__ float4 ldg_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 
 template <int NZ>
 __global__ void __launch_bounds__(S_THREADS, 1)
@@ -393,7 +397,7 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
     mbar_init(bar(SB_BYEMPTY0), 1); mbar_init(bar(SB_BYEMPTY1), 1);
     mbar_init(bar(SB_DVFULL), 1);
     mbar_init(bar(SB_OUTFULL0), 1); mbar_init(bar(SB_OUTFULL1), 1);
-    mbar_init(bar(SB_OUTEMPTY0), 128); mbar_init(bar(SB_OUTEMPTY0 + 1), 128);
+    mbar_init(bar(SB_OUTEMPTY0), S_EPI_WARPS * 32); mbar_init(bar(SB_OUTEMPTY0 + 1), S_EPI_WARPS * 32);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(base + L.tmem_slot, 512);
@@ -433,9 +437,9 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
         mma_commit(bar(SB_OUTFULL0 + b));
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 2 + S_EPI_WARPS) {
     // ===== By builders (64 threads): U[ky][kz] -> [[re, im], [-im, re]] operand tile =====
-    const int bt = (warp - 6) * 32 + lane;
+    const int bt = (warp - 2 - S_EPI_WARPS) * 32 + lane;
     int it = 0;
     for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
       const int b = it & 1;
@@ -455,46 +459,52 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
       mbar_arrive(bar(SB_BYFULL0 + b));
     }
   } else if (warp >= 2) {
-    // ===== epilogue warps (2..5) =====
-    const int q = warp & 3;
+    // ===== epilogue warps =====
+    constexpr int CW = NZ / 2;                 // columns per warp (64 or 32)
+    constexpr int LD = CW + 4;                 // padded staging row
+    constexpr int LPR = CW / 4;                // lanes per output row (one float4 each)
+    constexpr int RPI = 32 / LPR;              // rows per warp-wide instruction (2 or 4)
+    constexpr int NIT = 32 / RPI;              // 16 or 8
+    constexpr int G = 8;                       // row instructions whose addend loads are issued together
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float* st = reinterpret_cast<float*>(sm + L.stage) + q * 32 * ST_LD;
-    constexpr int NCH = NZ / 64;
+    float* st = reinterpret_cast<float*>(sm + L.stage) + (warp - 2) * 32 * LD;
+    const int rsub = lane / LPR, c4 = lane % LPR;
     int it = 0;
     for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
       const int b = it & 1;
       mbar_wait(bar(SB_OUTFULL0 + b), (it >> 1) & 1);
       tc_fence_after();
-      const size_t pbase = (size_t)p * 128 * NZ;
+      float v[CW];
+      tmem_ld32(tmem_out[b] + lane_base + half * CW, v);
+      if (CW == 64) tmem_ld32(tmem_out[b] + lane_base + half * CW + 32, v + (CW == 64 ? 32 : 0));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar(SB_OUTEMPTY0 + b));
+      __syncwarp();
 #pragma unroll
-      for (int h = 0; h < NCH; ++h) {
-        float v[64];
-        tmem_ld32(tmem_out[b] + lane_base + h * 64, v);
-        tmem_ld32(tmem_out[b] + lane_base + h * 64 + 32, v + 32);
-        tmem_ld_wait();
-        if (h == NCH - 1) {
-          tc_fence_before();
-          mbar_arrive(bar(SB_OUTEMPTY0 + b));
+      for (int j = 0; j < CW / 4; ++j)
+        *reinterpret_cast<float4*>(st + lane * LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      const size_t gbase = (size_t)p * 128 * NZ + (size_t)(32 * q + rsub) * NZ + half * CW + 4 * c4;
+#pragma unroll
+      for (int g0 = 0; g0 < NIT; g0 += G) {
+        float4 a0v[G], a1v[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const size_t g = gbase + (size_t)((g0 + j) * RPI) * NZ;
+          a0v[j] = add0 ? ldg_stream(add0 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+          a1v[j] = add1 ? ldg_stream(add1 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-#pragma unroll 4
-        for (int r2 = 0; r2 < 16; ++r2) {
-          const int row = 2 * r2 + (lane >> 4), c4 = lane & 15;
-          float4 o = *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
-          const size_t g = pbase + (size_t)(32 * q + row) * NZ + h * 64 + 4 * c4;
-          if (add0) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(add0 + g));
-            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-          }
-          if (add1) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(add1 + g));
-            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-          }
-          *reinterpret_cast<float4*>(out + g) = o;
+        for (int j = 0; j < G; ++j) {
+          const int row = (g0 + j) * RPI + rsub;
+          float4 o = *reinterpret_cast<const float4*>(st + row * LD + 4 * c4);
+          o.x = (o.x + a0v[j].x) + a1v[j].x;
+          o.y = (o.y + a0v[j].y) + a1v[j].y;
+          o.z = (o.z + a0v[j].z) + a1v[j].z;
+          o.w = (o.w + a0v[j].w) + a1v[j].w;
+          __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)((g0 + j) * RPI) * NZ), o);
         }
       }
     }

@@ -113,8 +113,9 @@ def synthesis(Z: torch.Tensor, grid: Tuple[int, int, int], mode_scale: Optional[
     return out
 
 
-def rational_mix_fwd(X, P, Q, monoP, monoQ, eps: float, mask, proj_eps: float):
-    """K2.  Returns Y [B,O,mx,my,mzh] complex64 (unprojected) and stats [B*O,4] = {a, b, s, 0}."""
+def rational_mix_fwd(X, P, Q, monoP, monoQ, eps: float, mask, proj_eps: float, keep_transfer: bool = False):
+    """K2.  Returns Y [B,O,mx,my,mzh] complex64 (unprojected), stats [B*O,4] = {a, b, s, 0} and, when
+    ``keep_transfer``, the materialised R and Q+eps [O,I,mx,my,mzh] the backward streams."""
     B, I = X.shape[:2]
     O = P.shape[0]
     M = X[0, 0].numel()
@@ -122,10 +123,14 @@ def rational_mix_fwd(X, P, Q, monoP, monoQ, eps: float, mask, proj_eps: float):
     with torch.cuda.device(X.device):
         Y = torch.empty((B, O, *X.shape[2:]), dtype=torch.complex64, device=X.device)
         stats = torch.empty((B * O, 4), dtype=torch.float32, device=X.device)
+        R = Qe = None
+        if keep_transfer:
+            R = torch.empty((O, I, *X.shape[2:]), dtype=torch.float32, device=X.device)
+            Qe = torch.empty_like(R)
         _cabi.check(lib.pdephi_rational_mix_fwd(_p(X), _p(P), _p(Q), _p(monoP), _p(monoQ), P.shape[-1], Q.shape[-1],
-                                                eps, _p(mask), proj_eps, _p(Y), _p(stats), B, I, O, M, _stream()),
-                    "rational_mix_fwd")
-    return Y, stats
+                                                eps, _p(mask), proj_eps, _p(Y), _p(stats), _p(R), _p(Qe), B, I, O, M,
+                                                _stream()), "rational_mix_fwd")
+    return Y, stats, R, Qe
 
 
 def projection_bwd(dZ, Y, mask, stats):
@@ -139,19 +144,21 @@ def projection_bwd(dZ, Y, mask, stats):
     return dY
 
 
-def rational_mix_bwd(X, dY, P, Q, monoP, monoQ, eps: float):
+def rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes):
+    """Backward of K2 from the materialised transfer function; coeff_shapes = (P.shape, Q.shape)."""
     B, I = X.shape[:2]
-    O = P.shape[0]
+    O = R.shape[0]
     M = X[0, 0].numel()
+    p_shape, q_shape = coeff_shapes
     lib = _cabi.load()
     with torch.cuda.device(X.device):
         dX = torch.empty_like(X)
-        dP = torch.empty_like(P)
-        dQ = torch.empty_like(Q)
-        nbytes = lib.pdephi_rational_mix_bwd_workspace_bytes(P.shape[-1], Q.shape[-1], I, O, M)
+        dP = torch.empty(p_shape, dtype=torch.float32, device=X.device)
+        dQ = torch.empty(q_shape, dtype=torch.float32, device=X.device)
+        nbytes = lib.pdephi_rational_mix_bwd_workspace_bytes(p_shape[-1], q_shape[-1], I, O, M)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
-        _cabi.check(lib.pdephi_rational_mix_bwd(_p(X), _p(dY), _p(P), _p(Q), _p(monoP), _p(monoQ), P.shape[-1],
-                                                Q.shape[-1], eps, _p(dX), _p(dP), _p(dQ), B, I, O, M, _p(ws), nbytes,
+        _cabi.check(lib.pdephi_rational_mix_bwd(_p(X), _p(dY), _p(R), _p(Qe), _p(monoP), _p(monoQ), p_shape[-1],
+                                                q_shape[-1], _p(dX), _p(dP), _p(dQ), B, I, O, M, _p(ws), nbytes,
                                                 _stream()), "rational_mix_bwd")
     return dX, dP, dQ
 
@@ -187,8 +194,9 @@ def complex_mix_bwd(X, W, dY, mzh: int):
 class RationalSpectralFn(torch.autograd.Function):
     """out = irfftn(StabilityProjection(R(k) mix(rfftn(x)[corner]))) [+ skip0 + x].
 
-    Saves only the retained modes (X, Y: 71 MB each at the 128^3 / width-64 / batch-8 config) instead
-    of the reference's full spectra.  Backward formulas: SURVEY.md section 8a.
+    Saves only the retained modes (X, Y: 71 MB each at the 128^3 / width-64 / batch-8 config) and the
+    transfer function (R, Q+eps: 285 MB each) instead of the reference's full spectra and polynomial graph
+    (~19 GB per layer).  Backward formulas: SURVEY.md section 8a.
     """
 
     @staticmethod
@@ -202,25 +210,27 @@ class RationalSpectralFn(torch.autograd.Function):
         P = P.contiguous()
         Q = Q.contiguous()
         X = analysis(x, modes_h, _cabi.FORWARD, precision)
-        Y, stats = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps)
+        need_grad = any(ctx.needs_input_grad[:3])
+        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
         out = synthesis(Y, grid, mask, stats[:, 2], skip0, x if residual else None, _cabi.FORWARD, precision)
-        ctx.save_for_backward(X, Y, stats, P, Q, mask, monoP, monoQ)
-        ctx.meta = (modes_h, grid, eps, precision, skip0 is not None, bool(residual))
+        if need_grad:
+            ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ)
+        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, skip0 is not None, bool(residual))
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     @once_differentiable
     def backward(ctx, g):
-        X, Y, stats, P, Q, mask, monoP, monoQ = ctx.saved_tensors
-        modes_h, grid, eps, precision, has0, residual = ctx.meta
+        X, Y, stats, R, Qe, mask, monoP, monoQ = ctx.saved_tensors
+        modes_h, grid, coeff_shapes, precision, has0, residual = ctx.meta
         g = g.contiguous()
         need_x, need_P, need_Q = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dx = dP = dQ = None
         if need_x or need_P or need_Q:
             dZ = analysis(g, modes_h, _cabi.ADJOINT, precision)
             dY = projection_bwd(dZ, Y, mask, stats)
-            dX, dP, dQ = rational_mix_bwd(X, dY, P, Q, monoP, monoQ, eps)
+            dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
             if need_x:   # the residual branch's gradient (g itself) rides in the synthesis epilogue
                 dx = synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision)
         return (dx, dP if need_P else None, dQ if need_Q else None, None, None, None, None, None, None,

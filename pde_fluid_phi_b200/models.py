@@ -57,9 +57,11 @@ class StabilityConstraints:
 
 def _lift(x: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
     """The reference's rearrange -> Linear -> rearrange (rational_fourier.py:258-260,274-276) as one
-    channels-first contraction W @ x: same result, no permuted copies, output contiguous [B,C,X,Y,Z]."""
-    b, _, *grid = x.shape
-    y = torch.matmul(linear.weight, x.reshape(b, x.shape[1], -1))
+    channels-first batched contraction W @ x[b]: same result, no permuted copies, output contiguous
+    [B,C,X,Y,Z].  (torch.matmul would fold the batch into one mm and transpose-copy the activation.)"""
+    b, c, *grid = x.shape
+    w = linear.weight.unsqueeze(0).expand(b, -1, -1)
+    y = torch.bmm(w, x.reshape(b, c, -1))
     if linear.bias is not None:
         y = y + linear.bias[:, None]
     return y.reshape(b, -1, *grid)

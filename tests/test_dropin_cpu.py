@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_argument_errors_without_gpu():
     lib = pb.load_library()
     # null-pointer / size validation happens before any CUDA call
-    rc = lib.pdephi_rational_mix_fwd(None, None, None, None, None, 4, 4, 1e-6, None, 1e-6, None, None, 1, 1, 1, 1, None)
+    rc = lib.pdephi_rational_mix_fwd(None, None, None, None, None, 4, 4, 1e-6, None, 1e-6, None, None, None, None, 1, 1, 1, 1, None)
     assert rc == _cabi.ERR_INVALID
     assert b"null pointer" in lib.pdephi_last_error()
     assert lib.pdephi_plan_workspace_bytes(None, 4) == 0

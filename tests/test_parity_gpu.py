@@ -127,11 +127,14 @@ def test_transfer_function_is_bit_identical(modes, order):
     for i in range(C):
         X[i, i] = 1.0
     mask = so.decay_mask(modes).reshape(-1).to(DEV)
-    Y, _ = pf.rational_mix_fwd(X.to(DEV), P.to(DEV), Q.to(DEV), pf.monomial_table(modes, order[0]).to(DEV),
-                               pf.monomial_table(modes, order[1]).to(DEV), 1e-6, mask, 1e-6)
+    Y, _, Rm, Qem = pf.rational_mix_fwd(X.to(DEV), P.to(DEV), Q.to(DEV), pf.monomial_table(modes, order[0]).to(DEV),
+                                        pf.monomial_table(modes, order[1]).to(DEV), 1e-6, mask, 1e-6, keep_transfer=True)
     got = Y.real.permute(1, 0, 2, 3, 4).cpu()          # [o, i, ...]
     assert torch.equal(got, R)
     assert torch.count_nonzero(Y.imag) == 0
+    # the materialised copies the backward streams are the same bits
+    _, _, Qe = so.rational_transfer(P, Q, modes, 1e-6)
+    assert torch.equal(Rm.cpu(), R) and torch.equal(Qem.cpu(), Qe)
 
 
 # ------------------------------------------------------------------------------------------------
