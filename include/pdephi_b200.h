@@ -58,6 +58,12 @@ const char* pdephi_last_error(void);
 
 /* ---- plan: constant DFT twiddle tables for one (grid, modes) pair on one device ------------- */
 int pdephi_plan_create(pdephi_plan_t* plan, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh);
+/* Plan for an x slab [x_offset, x_offset+Nx) of a grid with Nx_total planes (slab-decomposed transform over
+ * several GPUs): K1 then returns the slab's partial sums of the retained modes (summing them over the slabs
+ * gives the transform of the whole volume) and K3 returns the slab's rows of the synthesis; the 1/N of the
+ * normalised directions uses Nx_total. */
+int pdephi_plan_create_slab(pdephi_plan_t* plan, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh,
+                            int Nx_total, int x_offset);
 int pdephi_plan_destroy(pdephi_plan_t plan);
 /* bytes of scratch the two transforms need for `BC` (= batch*channels) volumes */
 size_t pdephi_plan_workspace_bytes(pdephi_plan_t plan, long long BC);
@@ -121,6 +127,17 @@ int pdephi_complex_mix_fwd(const float* X, const float* W, float* Y, int B, int 
                            int mzh, int mz, pdephi_stream_t stream);
 int pdephi_complex_mix_bwd(const float* X, const float* W, const float* dY, float* dX, float* dW, int B,
                            int I, int O, long long mxy, int mzh, int mz, pdephi_stream_t stream);
+
+/* ---- channels-first pointwise linear maps: the models' lift / project ------------------------
+ * replaces rearrange -> nn.Linear -> rearrange (rational_fourier.py:258-260,274-276; fno3d.py:86-88,100-102)
+ *   out[b,o,s] = bias[o] + sum_c W[o,c] x[b,c,s]      x [B,Cin,S], W [Cout,Cin], out [B,Cout,S]
+ * transpose_w != 0 uses W as [Cin,Cout] (the input-gradient map).  One of Cin, Cout must be <= 8, S % 4 == 0.
+ * wgrad: dW[o,c] = sum_{b,s} g[b,o,s] x[b,c,s], dbias[o] = sum_{b,s} g[b,o,s]; deterministic two-stage sum. */
+int pdephi_pointwise_linear(const float* x, const float* W, const float* bias, float* out, int B, int Cin,
+                            int Cout, long long S, int transpose_w, pdephi_stream_t stream);
+size_t pdephi_pointwise_wgrad_workspace_bytes(int Cin, int Cout, long long S);
+int pdephi_pointwise_wgrad(const float* x, const float* g, float* dW, float* dbias, int B, int Cin, int Cout,
+                           long long S, void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
 
 /* ---- per-kernel launch counters and CUDA-event timing (measurement support for bench.py) ------
  * Launches are always counted.  With timing enabled every kernel launch is bracketed by a pair of

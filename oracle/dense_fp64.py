@@ -28,6 +28,21 @@ def twiddle(N: int, m: int, sign: float) -> np.ndarray:
     return np.cos(ang) + 1j * sign * np.sin(ang)
 
 
+def twiddle_slab(N_total: int, m: int, sign: float, offset: int, n_local: int) -> np.ndarray:
+    """Rows [offset, offset+n_local) of twiddle(N_total, m, sign): the x twiddles of one slab."""
+    return twiddle(N_total, m, sign)[:, offset:offset + n_local]
+
+
+def analysis_slab(x_slab: np.ndarray, modes_h: Modes, nx_total: int, x_offset: int) -> np.ndarray:
+    """Partial pruned spectrum contributed by the x slab [x_offset, x_offset+Nx_local): summing it over the
+    slabs of a volume gives analysis(volume) (linearity of the x-stage sum)."""
+    mx, my, mzh = modes_h
+    nxl, Ny, Nz = x_slab.shape[-3:]
+    t = np.einsum("...xyz,kz->...xyk", x_slab, twiddle(Nz, mzh, -1.0))
+    t = np.einsum("...xyk,jy->...xjk", t, twiddle(Ny, my, -1.0))
+    return np.einsum("...xjk,ix->...ijk", t, twiddle_slab(nx_total, mx, -1.0, x_offset, nxl))
+
+
 def hermitian_weights(Nz: int, mzh: int) -> np.ndarray:
     """c_kz of the C2R step of irfftn: 1 at kz=0 and at the Nyquist bin, 2 elsewhere.
 

@@ -24,6 +24,7 @@ SIGNATURES = {
     "pdephi_version": (c_int, []),
     "pdephi_last_error": (c_char_p, []),
     "pdephi_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "pdephi_plan_create_slab": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "pdephi_plan_destroy": (c_int, [c_void_p]),
     "pdephi_plan_workspace_bytes": (c_size_t, [c_void_p, c_longlong]),
     "pdephi_analysis_r2c": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
@@ -40,6 +41,10 @@ SIGNATURES = {
     "pdephi_complex_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_void_p]),
     "pdephi_complex_mix_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong,
                                        c_int, c_int, c_void_p]),
+    "pdephi_pointwise_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_void_p]),
+    "pdephi_pointwise_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_longlong]),
+    "pdephi_pointwise_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p,
+                                       c_size_t, c_void_p]),
     "pdephi_profile_enable": (c_int, [c_int]),
     "pdephi_profile_reset": (c_int, []),
     "pdephi_profile_num_kernels": (c_int, []),
@@ -90,16 +95,18 @@ def check(rc: int, what: str = ""):
 _plans = {}
 
 
-def get_plan(device_index: int, grid, modes_h):
-    """Cached plan handle for (device, grid, (mx,my,mzh)); twiddle tables live for the process lifetime."""
-    key = (int(device_index), tuple(int(v) for v in grid), tuple(int(v) for v in modes_h))
+def get_plan(device_index: int, grid, modes_h, slab=None):
+    """Cached plan handle for (device, grid, (mx,my,mzh)[, (Nx_total, x_offset)]); tables live for the process lifetime."""
+    grid = tuple(int(v) for v in grid)
+    slab = (grid[0], 0) if slab is None else (int(slab[0]), int(slab[1]))
+    key = (int(device_index), grid, tuple(int(v) for v in modes_h), slab)
     h = _plans.get(key)
     if h is None:
         with _lock:
             h = _plans.get(key)
             if h is None:
                 handle = c_void_p()
-                check(load().pdephi_plan_create(ctypes.byref(handle), key[0], *key[1], *key[2]), "plan_create")
+                check(load().pdephi_plan_create_slab(ctypes.byref(handle), key[0], *key[1], *key[2], *key[3]), "plan_create")
                 h = handle
                 _plans[key] = h
     return h

@@ -22,9 +22,10 @@ int fail(int code, const char* fmt, ...) {
 // ---- launch counters / event timing -------------------------------------------------------------
 static const char* const kKernelNames[K_COUNT] = {
     "analysis_zy_kernel", "xstage_kernel(analysis)", "xstage_kernel(synthesis)", "synthesis_zy_kernel",
-    "analysis_zy_tc_kernel", "synthesis_zy_tc_kernel", "rational_mix_kernel", "rational_mix_kernel(transposed)",
+    "analysis_zy_tc_kernel", "synthesis_zy_tc_kernel", "rational_mix_kernel", "mix_from_R_kernel",
     "projection_stats_kernel", "projection_bwd_kernel", "rational_dpq_kernel", "dpq_reduce_kernel",
-    "complex_mix_kernel", "complex_mix_kernel(transposed)", "complex_dw_kernel"};
+    "complex_mix_kernel", "complex_mix_kernel(transposed)", "complex_dw_kernel", "pointwise_linear_kernel",
+    "pointwise_wgrad_kernel"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 static std::atomic<long long> g_launches[K_COUNT];
 static std::atomic<bool> g_prof_on{false};
@@ -60,13 +61,14 @@ void prof_end(int id, cudaStream_t st) {
 
 // table[a][b] = w(k) * (cos, sgn*sin)(2 pi k n / N); k_is_col selects which index is the mode.
 // The product k*n is reduced mod N in integers so the angle is exact to fp64 rounding.
-__global__ void twiddle_kernel(float2* __restrict__ out, int rows, int cols, int N, bool k_is_col, double sgn,
-                               int weight_mode /*0 none, 1 hermitian c_k/total*/, int Nz_even_nyq, double inv_total) {
+__global__ void twiddle_kernel(float2* __restrict__ out, int rows, int cols, int N, int n_offset, bool k_is_col,
+                               double sgn, int weight_mode /*0 none, 1 hermitian c_k/total*/, int Nz_even_nyq,
+                               double inv_total) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
   const int r = idx / cols, c = idx % cols;
   const int k = k_is_col ? c : r;
-  const int n = k_is_col ? r : c;
+  const int n = (k_is_col ? r : c) + n_offset;
   const long long kn = ((long long)k * n) % N;
   double s, co;
   sincospi(2.0 * (double)kn / (double)N, &s, &co);
@@ -86,11 +88,18 @@ extern "C" int pdephi_version(void) { return PDEPHI_VERSION; }
 extern "C" const char* pdephi_last_error(void) { return err_buf(); }
 
 extern "C" int pdephi_plan_create(pdephi_plan_t* out, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh) {
+  return pdephi_plan_create_slab(out, device, Nx, Ny, Nz, mx, my, mzh, Nx, 0);
+}
+
+extern "C" int pdephi_plan_create_slab(pdephi_plan_t* out, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh,
+                                       int Nx_total, int x_offset) {
   PDEPHI_REQUIRE(out != nullptr, "plan_create: null output handle");
   PDEPHI_REQUIRE(Nx > 0 && Ny > 0 && Nz > 0 && mx > 0 && my > 0 && mzh > 0, "plan_create: non-positive size");
-  PDEPHI_REQUIRE(mx <= Nx && my <= Ny && mzh <= Nz / 2 + 1,
+  PDEPHI_REQUIRE(x_offset >= 0 && x_offset + Nx <= Nx_total, "plan_create: x slab [%d, %d) outside [0, %d)", x_offset,
+                 x_offset + Nx, Nx_total);
+  PDEPHI_REQUIRE(mx <= Nx_total && my <= Ny && mzh <= Nz / 2 + 1,
                  "plan_create: retained modes (%d,%d,%d) exceed the half-spectrum of grid (%d,%d,%d)", mx, my, mzh,
-                 Nx, Ny, Nz);
+                 Nx_total, Ny, Nz);
   int cur = -1;
   PDEPHI_CUDA(cudaGetDevice(&cur));
   PDEPHI_CUDA(cudaSetDevice(device));
@@ -98,6 +107,7 @@ extern "C" int pdephi_plan_create(pdephi_plan_t* out, int device, int Nx, int Ny
   memset(p, 0, sizeof(Plan));
   p->device = device;
   p->Nx = Nx; p->Ny = Ny; p->Nz = Nz; p->mx = mx; p->my = my; p->mzh = mzh;
+  p->Nx_total = Nx_total; p->x_offset = x_offset;
   cudaDeviceProp prop;
   PDEPHI_CUDA(cudaGetDeviceProperties(&prop, device));
   p->num_sms = prop.multiProcessorCount;
@@ -119,20 +129,20 @@ extern "C" int pdephi_plan_create(pdephi_plan_t* out, int device, int Nx, int Ny
   p->sz[0] = (float2*)(base + off[6]);
   p->sz[1] = (float2*)(base + off[7]);
 
-  const double inv_total = 1.0 / ((double)Nx * (double)Ny * (double)Nz);
+  const double inv_total = 1.0 / ((double)Nx_total * (double)Ny * (double)Nz);
   const int nyq = (Nz % 2 == 0 && mzh - 1 == Nz / 2) ? Nz / 2 : -1;
-  auto gen = [&](float2* t, int rows, int cols, int N, bool k_is_col, double sgn, int wm) {
+  auto gen = [&](float2* t, int rows, int cols, int N, int off, bool k_is_col, double sgn, int wm) {
     const int n = rows * cols;
-    twiddle_kernel<<<(n + 255) / 256, 256>>>(t, rows, cols, N, k_is_col, sgn, wm, nyq, inv_total);
+    twiddle_kernel<<<(n + 255) / 256, 256>>>(t, rows, cols, N, off, k_is_col, sgn, wm, nyq, inv_total);
   };
-  gen(p->az[0], Nz, mzh, Nz, true, -1.0, 0);
-  gen(p->az[1], Nz, mzh, Nz, true, -1.0, 1);
-  gen(p->ay, Ny, my, Ny, true, -1.0, 0);
-  gen(p->ax, Nx, mx, Nx, true, -1.0, 0);
-  gen(p->sx, mx, Nx, Nx, false, +1.0, 0);
-  gen(p->sy, my, Ny, Ny, false, +1.0, 0);
-  gen(p->sz[0], mzh, Nz, Nz, false, +1.0, 1);
-  gen(p->sz[1], mzh, Nz, Nz, false, +1.0, 0);
+  gen(p->az[0], Nz, mzh, Nz, 0, true, -1.0, 0);
+  gen(p->az[1], Nz, mzh, Nz, 0, true, -1.0, 1);
+  gen(p->ay, Ny, my, Ny, 0, true, -1.0, 0);
+  gen(p->ax, Nx, mx, Nx_total, x_offset, true, -1.0, 0);      // slab rows carry their global x index
+  gen(p->sx, mx, Nx, Nx_total, x_offset, false, +1.0, 0);
+  gen(p->sy, my, Ny, Ny, 0, false, +1.0, 0);
+  gen(p->sz[0], mzh, Nz, Nz, 0, false, +1.0, 1);
+  gen(p->sz[1], mzh, Nz, Nz, 0, false, +1.0, 0);
   PDEPHI_LAUNCH_CHECK("twiddle_kernel");
   {
     int rc = tc_plan_init(p);

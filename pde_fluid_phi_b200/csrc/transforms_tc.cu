@@ -555,7 +555,7 @@ int tc_plan_init(Plan* p) {
   p->tc_ay = f; f += nAy;
   p->tc_bz[0] = f; f += nBz;
   p->tc_bz[1] = f; f += nBz;
-  const double inv_total = 1.0 / ((double)p->Nx * p->Ny * p->Nz);
+  const double inv_total = 1.0 / ((double)p->Nx_total * p->Ny * p->Nz);
   const int nyq = (p->Nz % 2 == 0 && p->mzh - 1 == p->Nz / 2) ? p->Nz / 2 : -1;
   // The tensor core drops the low 13 mantissa bits of an fp32 operand it reads itself (the TMA-staged
   // plane, the TMEM-resident V): a mean relative bias of -2^-11.  It is folded into the constant operand

@@ -56,8 +56,11 @@ def monomial_table(modes: Sequence[int], order: int) -> torch.Tensor:
 # raw ops (no autograd)
 # ------------------------------------------------------------------------------------------------
 def analysis(x: torch.Tensor, modes_h: Tuple[int, int, int], direction: int = _cabi.FORWARD,
-             precision: int = _cabi.PREC_FP32) -> torch.Tensor:
-    """K1.  x [B,C,Nx,Ny,Nz] float32 -> [B,C,mx,my,mzh] complex64 (pruned rfftn / adjoint of synthesis)."""
+             precision: int = _cabi.PREC_FP32, slab=None) -> torch.Tensor:
+    """K1.  x [B,C,Nx,Ny,Nz] float32 -> [B,C,mx,my,mzh] complex64 (pruned rfftn / adjoint of synthesis).
+
+    slab = (Nx_total, x_offset): x is the slab [x_offset, x_offset+Nx) of a larger grid and the result is
+    that slab's partial sum of the modes."""
     _require_cuda_f32(x, "x")
     if x.dim() != 5:
         raise ValueError(f"expected a [B,C,Nx,Ny,Nz] tensor, got shape {tuple(x.shape)}")
@@ -66,7 +69,7 @@ def analysis(x: torch.Tensor, modes_h: Tuple[int, int, int], direction: int = _c
     grid = tuple(x.shape[2:])
     lib = _cabi.load()
     with torch.cuda.device(x.device):
-        plan = _cabi.get_plan(x.device.index, grid, modes_h)
+        plan = _cabi.get_plan(x.device.index, grid, modes_h, slab)
         X = torch.empty((B, C, *modes_h), dtype=torch.complex64, device=x.device)
         nbytes = lib.pdephi_plan_workspace_bytes(plan, B * C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
@@ -78,7 +81,7 @@ def analysis(x: torch.Tensor, modes_h: Tuple[int, int, int], direction: int = _c
 def synthesis(Z: torch.Tensor, grid: Tuple[int, int, int], mode_scale: Optional[torch.Tensor] = None,
               row_scale: Optional[torch.Tensor] = None, addend0: Optional[torch.Tensor] = None,
               addend1: Optional[torch.Tensor] = None, direction: int = _cabi.FORWARD,
-              precision: int = _cabi.PREC_FP32) -> torch.Tensor:
+              precision: int = _cabi.PREC_FP32, slab=None) -> torch.Tensor:
     """K3.  Z [B,C,mx,my,mzh] complex64 -> [B,C,Nx,Ny,Nz] float32, out = S(Z*mode_scale*row_scale) + addends.
 
     row_scale: float32 1-D (possibly strided) view with one element per volume, e.g. ``stats[:, 2]``.
@@ -103,7 +106,7 @@ def synthesis(Z: torch.Tensor, grid: Tuple[int, int, int], mode_scale: Optional[
     a1 = addend1.contiguous() if addend1 is not None else None
     lib = _cabi.load()
     with torch.cuda.device(Z.device):
-        plan = _cabi.get_plan(Z.device.index, grid, modes_h)
+        plan = _cabi.get_plan(Z.device.index, grid, modes_h, slab)
         out = torch.empty((B, C, *grid), dtype=torch.float32, device=Z.device)
         nbytes = lib.pdephi_plan_workspace_bytes(plan, B * C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=Z.device)
@@ -191,6 +194,27 @@ def complex_mix_bwd(X, W, dY, mzh: int):
 # ------------------------------------------------------------------------------------------------
 # autograd Functions
 # ------------------------------------------------------------------------------------------------
+def _slab_args(slab, x):
+    """slab = None | (process_group, Nx_total): this rank holds x planes [rank*Nx, (rank+1)*Nx) of the grid."""
+    if slab is None:
+        return None, None, 1
+    import torch.distributed as dist
+    group, nx_total = slab
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nx = x.shape[2]
+    if nx * world != nx_total:
+        raise ValueError(f"slab decomposition needs Nx_total == world * local Nx, got {nx_total} vs {world} * {nx}")
+    return group, (nx_total, rank * nx), world
+
+
+def _allreduce_modes(X, group):
+    """Sum the slabs' partial spectra: the one collective of the slab-decomposed transform (NCCL over NVLink)."""
+    import torch.distributed as dist
+    dist.all_reduce(torch.view_as_real(X), op=dist.ReduceOp.SUM, group=group)
+    return X
+
+
+
 class RationalSpectralFn(torch.autograd.Function):
     """out = irfftn(StabilityProjection(R(k) mix(rfftn(x)[corner]))) [+ skip0 + x].
 
@@ -201,21 +225,25 @@ class RationalSpectralFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, P, Q, mask, monoP, monoQ, modes, eps, precision, skip0, residual):
+    def forward(ctx, x, P, Q, mask, monoP, monoQ, modes, eps, precision, skip0, residual, slab=None):
         for t, n in ((x, "x"), (P, "P_coeffs"), (Q, "Q_coeffs")):
             _require_cuda_f32(t, n)
         mx, my, mz = modes
         modes_h = (mx, my, mz // 2 + 1)
         grid = tuple(x.shape[2:])
+        group, slab_plan, world = _slab_args(slab, x)
         P = P.contiguous()
         Q = Q.contiguous()
-        X = analysis(x, modes_h, _cabi.FORWARD, precision)
+        X = analysis(x, modes_h, _cabi.FORWARD, precision, slab_plan)
+        if group is not None:
+            _allreduce_modes(X, group)          # partial sums over the x slabs -> every rank holds the full modes
         need_grad = any(ctx.needs_input_grad[:3])
         Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
-        out = synthesis(Y, grid, mask, stats[:, 2], skip0, x if residual else None, _cabi.FORWARD, precision)
+        out = synthesis(Y, grid, mask, stats[:, 2], skip0, x if residual else None, _cabi.FORWARD, precision, slab_plan)
         if need_grad:
             ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ)
-        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, skip0 is not None, bool(residual))
+        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, skip0 is not None, bool(residual),
+                    group, slab_plan, world)
         return out
 
     @staticmethod
@@ -223,18 +251,25 @@ class RationalSpectralFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         X, Y, stats, R, Qe, mask, monoP, monoQ = ctx.saved_tensors
-        modes_h, grid, coeff_shapes, precision, has0, residual = ctx.meta
+        modes_h, grid, coeff_shapes, precision, has0, residual, group, slab_plan, world = ctx.meta
         g = g.contiguous()
         need_x, need_P, need_Q = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dx = dP = dQ = None
         if need_x or need_P or need_Q:
-            dZ = analysis(g, modes_h, _cabi.ADJOINT, precision)
+            dZ = analysis(g, modes_h, _cabi.ADJOINT, precision, slab_plan)
+            if group is not None:
+                _allreduce_modes(dZ, group)
             dY = projection_bwd(dZ, Y, mask, stats)
             dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
+            if world > 1:
+                # every rank computed the complete coefficient gradient from the replicated modes; pre-divide so the
+                # SUM all-reduce that completes the slab-local gradients of the pointwise layers leaves it unchanged
+                dP.div_(world)
+                dQ.div_(world)
             if need_x:   # the residual branch's gradient (g itself) rides in the synthesis epilogue
-                dx = synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision)
+                dx = synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision, slab_plan)
         return (dx, dP if need_P else None, dQ if need_Q else None, None, None, None, None, None, None,
-                g if has0 else None, None)
+                g if has0 else None, None, None)
 
 
 class ComplexSpectralFn(torch.autograd.Function):
@@ -242,18 +277,21 @@ class ComplexSpectralFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, W, modes, precision, skip0, residual):
+    def forward(ctx, x, W, modes, precision, skip0, residual, slab=None):
         _require_cuda_f32(x, "x")
         _require_cuda_f32(W, "weights", complex_ok=True)
         mx, my, mz = modes
         modes_h = (mx, my, mz // 2 + 1)
         grid = tuple(x.shape[2:])
+        group, slab_plan, world = _slab_args(slab, x)
         W = W.contiguous()
-        X = analysis(x, modes_h, _cabi.FORWARD, precision)
+        X = analysis(x, modes_h, _cabi.FORWARD, precision, slab_plan)
+        if group is not None:
+            _allreduce_modes(X, group)
         Y = complex_mix_fwd(X, W, modes_h[2])
-        out = synthesis(Y, grid, None, None, skip0, x if residual else None, _cabi.FORWARD, precision)
+        out = synthesis(Y, grid, None, None, skip0, x if residual else None, _cabi.FORWARD, precision, slab_plan)
         ctx.save_for_backward(X, W)
-        ctx.meta = (modes_h, grid, precision, skip0 is not None, bool(residual))
+        ctx.meta = (modes_h, grid, precision, skip0 is not None, bool(residual), group, slab_plan, world)
         return out
 
     @staticmethod
@@ -261,12 +299,70 @@ class ComplexSpectralFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         X, W = ctx.saved_tensors
-        modes_h, grid, precision, has0, residual = ctx.meta
+        modes_h, grid, precision, has0, residual, group, slab_plan, world = ctx.meta
         g = g.contiguous()
         dx = dW = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            dY = analysis(g, modes_h, _cabi.ADJOINT, precision)
+            dY = analysis(g, modes_h, _cabi.ADJOINT, precision, slab_plan)
+            if group is not None:
+                _allreduce_modes(dY, group)
             dX, dW = complex_mix_bwd(X, W, dY, modes_h[2])
+            if world > 1:
+                dW.div_(world)
             if ctx.needs_input_grad[0]:
-                dx = synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision)
-        return dx, dW if ctx.needs_input_grad[1] else None, None, None, g if has0 else None, None
+                dx = synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision, slab_plan)
+        return dx, dW if ctx.needs_input_grad[1] else None, None, None, g if has0 else None, None, None
+
+
+class PointwiseLinearFn(torch.autograd.Function):
+    """Channels-first pointwise linear map y[b,o,s] = bias[o] + sum_c W[o,c] x[b,c,s] (the models' lift / project).
+
+    Equivalent to the reference's rearrange -> nn.Linear -> rearrange without the two transposed copies."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias):
+        _require_cuda_f32(x, "x")
+        x = x.contiguous()
+        weight = weight.contiguous()
+        B, Cin = x.shape[:2]
+        Cout = weight.shape[0]
+        S = x[0, 0].numel()
+        lib = _cabi.load()
+        with torch.cuda.device(x.device):
+            out = torch.empty((B, Cout, *x.shape[2:]), dtype=torch.float32, device=x.device)
+            _cabi.check(lib.pdephi_pointwise_linear(_p(x), _p(weight), _p(bias), _p(out), B, Cin, Cout, S, 0, _stream()),
+                        "pointwise_linear")
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        B, Cin = x.shape[:2]
+        Cout = weight.shape[0]
+        S = x[0, 0].numel()
+        lib = _cabi.load()
+        dx = dW = db = None
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                _cabi.check(lib.pdephi_pointwise_linear(_p(g), _p(weight), _p(None), _p(dx), B, Cout, Cin, S, 1, _stream()),
+                            "pointwise_linear(dx)")
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                dW = torch.empty_like(weight)
+                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+                nbytes = lib.pdephi_pointwise_wgrad_workspace_bytes(Cin, Cout, S)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                _cabi.check(lib.pdephi_pointwise_wgrad(_p(x), _p(g), _p(dW), _p(db), B, Cin, Cout, S, _p(ws), nbytes,
+                                                       _stream()), "pointwise_wgrad")
+        return dx, dW, db
+
+
+def pointwise_linear_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x[0, 0].numel() % 4 == 0
+            and min(weight.shape[0], weight.shape[1]) <= 8)

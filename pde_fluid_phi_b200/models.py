@@ -6,8 +6,8 @@
 Constructor signatures, sub-module / parameter names and the order in which the global RNG is
 consumed match the reference, so ``torch.manual_seed(s); Model(...)`` gives the same weights and
 checkpoints load either way.  Per block the spectral layer, the two skip adds and (inside the
-layer) the projection run in libpdephi_b200.so; the 1x1x1 convolution, GELU and the lift /
-project Linears stay with torch ("next" rows N1, N2).
+layer) the projection run in libpdephi_b200.so, as do the lift / project Linears (SURVEY.md section 8f
+row N2); the 1x1x1 convolution and GELU stay with torch (row N1).
 """
 from __future__ import annotations
 
@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .functional import PointwiseLinearFn, pointwise_linear_supported
 from .operators import RationalFourierLayer, SpectralConv3D
 
 
@@ -57,14 +58,11 @@ class StabilityConstraints:
 
 def _lift(x: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
     """The reference's rearrange -> Linear -> rearrange (rational_fourier.py:258-260,274-276) as one
-    channels-first batched contraction W @ x[b]: same result, no permuted copies, output contiguous
-    [B,C,X,Y,Z].  (torch.matmul would fold the batch into one mm and transpose-copy the activation.)"""
-    b, c, *grid = x.shape
-    w = linear.weight.unsqueeze(0).expand(b, -1, -1)
-    y = torch.bmm(w, x.reshape(b, c, -1))
-    if linear.bias is not None:
-        y = y + linear.bias[:, None]
-    return y.reshape(b, -1, *grid)
+    channels-first contraction on the [B,C,X,Y,Z] layout: same result, no permuted copies.  Runs in
+    libpdephi_b200.so (pointwise.cu); shapes it does not cover use the reference's own torch formulation."""
+    if pointwise_linear_supported(x, linear.weight):
+        return PointwiseLinearFn.apply(x, linear.weight, linear.bias)
+    return linear(x.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
 
 
 def _reset_pointwise(module: nn.Module):

@@ -42,7 +42,7 @@ def get_grid(modes: Tuple[int, int, int], device: Union[str, torch.device] = "cp
     return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=0)
 
 
-def _check_input(x: torch.Tensor, channels: int, modes, who: str):
+def _check_input(x: torch.Tensor, channels: int, modes, who: str, slab=None):
     if not isinstance(x, torch.Tensor) or x.dim() != 5:
         raise ValueError(f"{who}: expected a [batch, channels, Nx, Ny, Nz] tensor, got "
                          f"{tuple(x.shape) if isinstance(x, torch.Tensor) else type(x)}")
@@ -50,6 +50,8 @@ def _check_input(x: torch.Tensor, channels: int, modes, who: str):
         raise RuntimeError(f"{who}: input has {x.shape[1]} channels, layer was built for {channels}")
     mx, my, mz = modes
     nx, ny, nz = x.shape[2:]
+    if slab is not None:
+        nx = slab[1]                      # x is one slab of a grid with Nx_total planes
     if mx > nx or my > ny or mz // 2 + 1 > nz // 2 + 1:
         raise RuntimeError(f"{who}: modes {tuple(modes)} do not fit the half-spectrum of a {(nx, ny, nz)} grid")
 
@@ -106,6 +108,7 @@ class RationalFourierLayer(nn.Module):
         self.rational_order = rational_order
         self.stability_eps = stability_eps
         self.precision: Optional[str] = None     # None -> module-level default
+        self.slab = None                         # (process_group, Nx_total) for the slab-decomposed transform
         self._init_rational_coefficients(init_scale)
         self.stability_projection = StabilityProjection(modes=modes, decay_rate=2.0, eps=stability_eps)
         self.register_buffer("k_grid", get_grid(modes, device="cpu"))
@@ -144,12 +147,12 @@ class RationalFourierLayer(nn.Module):
         return _cabi.PRECISIONS[self.precision or _default_precision]
 
     def _run(self, x, skip0, residual):
-        _check_input(x, self.in_channels, self.modes, "RationalFourierLayer")
+        _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
         if self.in_channels != self.out_channels:
             raise RuntimeError("RationalFourierLayer needs in_channels == out_channels (as the reference does)")
         return RationalSpectralFn.apply(x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
                                         self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
-                                        self._precision_code(), skip0, residual)
+                                        self._precision_code(), skip0, residual, self.slab)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._run(x, None, False)
@@ -174,16 +177,18 @@ class SpectralConv3D(nn.Module):
         self.out_channels = out_channels
         self.modes = modes
         self.precision: Optional[str] = None
+        self.slab = None
         self.weights = nn.Parameter(torch.randn(out_channels, in_channels, *modes, dtype=torch.cfloat) * init_scale)
 
     def _precision_code(self) -> int:
         return _cabi.PRECISIONS[self.precision or _default_precision]
 
     def _run(self, x, skip0, residual):
-        _check_input(x, self.in_channels, self.modes, "SpectralConv3D")
+        _check_input(x, self.in_channels, self.modes, "SpectralConv3D", self.slab)
         if residual and self.in_channels != self.out_channels:
             raise RuntimeError("fused residual needs in_channels == out_channels")
-        return ComplexSpectralFn.apply(x, self.weights, tuple(self.modes), self._precision_code(), skip0, residual)
+        return ComplexSpectralFn.apply(x, self.weights, tuple(self.modes), self._precision_code(), skip0, residual,
+                                       self.slab)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._run(x, None, False)

@@ -48,3 +48,32 @@ def test_gradient_allreduce_two_ranks():
         assert torch.equal(g0, g1)                      # same averaged gradient on both ranks
         assert torch.allclose(g0, (l0 + l1) / 2, rtol=1e-6, atol=1e-7)
         assert g0.dtype == l0.dtype                     # complex64 stays complex64
+
+
+def _slab_worker(rank, world, port, out):
+    """Slab-decomposed analysis: local partial spectrum (oracle arithmetic) + one all-reduce == full transform."""
+    import numpy as np
+    from oracle import dense_fp64 as d64
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2, 3, 8, 6, 10))            # same volume on every rank; each takes its x slab
+    nxl = x.shape[2] // world
+    mh = (4, 3, 4)
+    part = d64.analysis_slab(x[:, :, rank * nxl:(rank + 1) * nxl], mh, x.shape[2], rank * nxl)
+    t = torch.view_as_real(torch.from_numpy(part).contiguous())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    out[rank] = (torch.view_as_complex(t).numpy(), d64.analysis(x, mh))
+    dist.destroy_process_group()
+
+
+def test_slab_partial_spectra_allreduce_two_ranks():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_slab_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    import numpy as np
+    for r in range(world):
+        got, want = out[r]
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-12
