@@ -139,6 +139,18 @@ size_t pdephi_pointwise_wgrad_workspace_bytes(int Cin, int Cout, long long S);
 int pdephi_pointwise_wgrad(const float* x, const float* g, float* dW, float* dbias, int B, int Cin, int Cout,
                            long long S, void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
 
+/* ---- fused block tail of a width-64 operator model (tcgen05 TF32 channel GEMM + epilogue) -----
+ * replaces Conv3d 1x1x1 + the two residual adds + exact GELU of rational_fourier.py:268-271 / fno3d.py:93-97
+ *   fwd:  u = spec + (Wc h + bc) + h,  hout = gelu(u)            h, spec, u, hout [B,64,S];  Wc [64,64]
+ *   bwd:  gu = g * gelu'(u),  t = gu + Wc^T gu,  dWc = sum_{b,s} gu (x) h,  dbc = sum_{b,s} gu
+ * Needs 64 channels and S % 128 == 0 (PDEPHI_ERR_UNSUPPORTED otherwise). */
+int pdephi_block_tail_fwd(const float* h, const float* spec, const float* Wc, const float* bc, float* u,
+                          float* hout, int B, int C, long long S, pdephi_stream_t stream);
+size_t pdephi_block_tail_bwd_workspace_bytes(int C);
+int pdephi_block_tail_bwd(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t,
+                          float* dWc, float* dbc, int B, int C, long long S, void* workspace,
+                          size_t workspace_bytes, pdephi_stream_t stream);
+
 /* ---- per-kernel launch counters and CUDA-event timing (measurement support for bench.py) ------
  * Launches are always counted.  With timing enabled every kernel launch is bracketed by a pair of
  * cudaEvents on the launching stream; pdephi_profile_query synchronises on them and returns the

@@ -45,6 +45,11 @@ SIGNATURES = {
     "pdephi_pointwise_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_longlong]),
     "pdephi_pointwise_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p,
                                        c_size_t, c_void_p]),
+    "pdephi_block_tail_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong,
+                                      c_void_p]),
+    "pdephi_block_tail_bwd_workspace_bytes": (c_size_t, [c_int]),
+    "pdephi_block_tail_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                      c_int, c_longlong, c_void_p, c_size_t, c_void_p]),
     "pdephi_profile_enable": (c_int, [c_int]),
     "pdephi_profile_reset": (c_int, []),
     "pdephi_profile_num_kernels": (c_int, []),

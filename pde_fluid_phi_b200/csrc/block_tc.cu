@@ -1,0 +1,453 @@
+// Block tail of the operator models, fused and on the tensor cores:
+//   forward   u = spec + (Wc h + bc) + h ;  h' = gelu(u)            (rational_fourier.py:268-271, fno3d.py:93-97)
+//   backward  gu = g' gelu'(u) ;  t = gu + Wc^T gu ;  dWc = sum_s gu (x) h ;  dbc = sum_s gu
+// for a width-64 model on the channels-first [B, 64, S] layout.  A tile is 128 spatial points x 64 channels,
+// TMA-staged as four [64 channel rows][32 points] boxes with 128-byte swizzle: that one shared-memory image is
+// the MN-major A operand of the channel GEMM  D[128 points x 64] = tile^T . Wc^T  (tcgen05 kind::tf32, TMEM
+// accumulator) and, in the backward, also the K-major operands of the weight-gradient GEMM accumulated in
+// TMEM across all tiles of a persistent CTA.  Replaces cuDNN conv fwd/bwd + bias reductions + GELU fwd/bwd +
+// residual / gradient-accumulation adds (about 56 GB of HBM traffic per layer) with two passes (21.5 GB each).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace pdephi {
+namespace blk {
+using namespace tcptx;
+
+constexpr int C = 64;            // channels (model width)
+constexpr int TS = 128;          // spatial points per tile
+constexpr int BOX = C * 128;     // bytes of one [64 rows][32 floats] box
+constexpr int TILE = 4 * BOX;    // 32 KB
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 32 * (2 + EPI_WARPS);
+
+// MN-major operand (M or N contiguous): atoms of 32 elements along MN are `lbo` bytes apart, 8-row K groups 1024 B
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of (channel row r, point s in [0,128)) inside a tile
+__device__ __forceinline__ uint32_t tile_off(int r, int s) {
+  return (uint32_t)((s >> 5) * BOX + r * 128 + (((((s & 31) >> 2) ^ (r & 7)) & 7) << 4) + (s & 3) * 4);
+}
+__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float u) {
+  return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+}
+// W image: K-major [64 rows][K = 64], element (r, k) = TRANSPOSE ? W[k][r] : W[r][k], RN-rounded to TF32
+__device__ __forceinline__ void build_w_image(uint8_t* dst, const float* __restrict__ W, bool transpose, int tid, int nthr) {
+  for (int i = tid; i < C * C; i += nthr) {
+    const int r = i >> 6, k = i & 63;
+    const float v = transpose ? __ldg(W + k * C + r) : __ldg(W + i);
+    *reinterpret_cast<float*>(dst + swz_off(C, r, k)) = to_tf32(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+constexpr int F_STAGES = 3;
+struct FSmem { uint32_t stage[F_STAGES], w, bias, bars, tmem_slot, total; };
+__host__ __device__ inline FSmem fwd_smem() {
+  FSmem s; uint32_t o = 0;
+  for (int i = 0; i < F_STAGES; ++i) { s.stage[i] = o; o += 2 * TILE; }
+  s.w = o; o += 2 * BOX;
+  s.bias = o; o += 256;
+  s.bars = o; o += 128;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+enum { FB_FULL = 0, FB_EMPTY = F_STAGES, FB_DFULL = 2 * F_STAGES, FB_DEMPTY = 2 * F_STAGES + 2 };
+
+__global__ void __launch_bounds__(THREADS, 1)
+block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_spec,
+                      const float* __restrict__ Wc, const float* __restrict__ bc, float* __restrict__ u_out,
+                      float* __restrict__ h_out, long long tiles_per_batch, long long ntiles, long long S) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const FSmem L = fwd_smem();
+  auto bar = [&](int i) { return base + L.bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  build_w_image(sm + L.w, Wc, false, threadIdx.x, THREADS);
+  if (threadIdx.x < C) reinterpret_cast<float*>(sm + L.bias)[threadIdx.x] = bc ? __ldg(bc + threadIdx.x) : 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < F_STAGES; ++i) { mbar_init(bar(FB_FULL + i), 1); mbar_init(bar(FB_EMPTY + i), 1 + EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(FB_DFULL + i), 1); mbar_init(bar(FB_DEMPTY + i), EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      long long it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = (int)(it % F_STAGES);
+        const uint32_t ph = (uint32_t)((it / F_STAGES) & 1);
+        mbar_wait(bar(FB_EMPTY + s), ph ^ 1);
+        mbar_arrive_expect_tx(bar(FB_FULL + s), 2 * TILE);
+        const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tma_load_2d(base + L.stage[s] + j * BOX, &tmap_h, bar(FB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
+          tma_load_2d(base + L.stage[s] + TILE + j * BOX, &tmap_spec, bar(FB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id = idesc_tf32(TS, C, 1, 0);
+      long long it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = (int)(it % F_STAGES), d = (int)(it & 1);
+        mbar_wait(bar(FB_FULL + s), (uint32_t)((it / F_STAGES) & 1));
+        mbar_wait(bar(FB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < C / 8; ++k)
+          mma_ss(tmem + d * C, umma_desc_mn(base + L.stage[s] + k * 1024, BOX),
+                 umma_desc(base + L.w + (k >> 2) * BOX + (k & 3) * 32, 1024), id, k ? 1u : 0u);
+        mma_commit(bar(FB_EMPTY + s));
+        mma_commit(bar(FB_DFULL + d));
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float* bs = reinterpret_cast<const float*>(sm + L.bias);
+    long long it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = (int)(it % F_STAGES), d = (int)(it & 1);
+      mbar_wait(bar(FB_DFULL + d), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + d * C + lane_base + half * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(FB_DEMPTY + d));
+      const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
+      const uint8_t* th = sm + L.stage[s];
+      const uint8_t* tsp = th + TILE;
+      const size_t g0 = ((size_t)b * C) * S + s0 + 32 * q + lane;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int o = half * 32 + j;
+        const uint32_t off = tile_off(o, 32 * q + lane);
+        const float hv = *reinterpret_cast<const float*>(th + off);
+        const float sv = *reinterpret_cast<const float*>(tsp + off);
+        const float u = (sv + (v[j] + bs[o])) + hv;
+        __stcs(u_out + g0 + (size_t)o * S, u);
+        h_out[g0 + (size_t)o * S] = gelu_f(u);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(FB_EMPTY + s));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+constexpr int B_STAGES = 2;
+struct BSmem { uint32_t stage[B_STAGES], wt, red, bars, tmem_slot, total; };
+__host__ __device__ inline BSmem bwd_smem() {
+  BSmem s; uint32_t o = 0;
+  for (int i = 0; i < B_STAGES; ++i) { s.stage[i] = o; o += 3 * TILE; }   // g' (becomes gu), u, h
+  s.wt = o; o += 2 * BOX;
+  s.red = o; o += 4 * C * 4;
+  s.bars = o; o += 128;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2 * B_STAGES + 1, BB_TEMPTY = 2 * B_STAGES + 2,
+       BB_DWDONE = 2 * B_STAGES + 3 };
+
+__global__ void __launch_bounds__(THREADS, 1)
+block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_u,
+                      const __grid_constant__ CUtensorMap tmap_h, const float* __restrict__ Wc, float* __restrict__ gu_out,
+                      float* __restrict__ t_out, float* __restrict__ partial, long long tiles_per_batch, long long ntiles,
+                      long long S) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const BSmem L = bwd_smem();
+  auto bar = [&](int i) { return base + L.bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  build_w_image(sm + L.wt, Wc, true, threadIdx.x, THREADS);      // rows c, K = o : (Wc^T)
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), 1); mbar_init(bar(BB_EMPTY + i), 1 + EPI_WARPS); }
+    mbar_init(bar(BB_GUREADY), EPI_WARPS);
+    mbar_init(bar(BB_TFULL), 1);
+    mbar_init(bar(BB_TEMPTY), EPI_WARPS);
+    mbar_init(bar(BB_DWDONE), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const uint32_t tmem_t = tmem, tmem_dw = tmem + C;
+  const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      long long it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = (int)(it % B_STAGES);
+        mbar_wait(bar(BB_EMPTY + s), (uint32_t)(((it / B_STAGES) & 1) ^ 1));
+        mbar_arrive_expect_tx(bar(BB_FULL + s), 3 * TILE);
+        const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tma_load_2d(base + L.stage[s] + j * BOX, &tmap_g, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
+          tma_load_2d(base + L.stage[s] + TILE + j * BOX, &tmap_u, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
+          tma_load_2d(base + L.stage[s] + 2 * TILE + j * BOX, &tmap_h, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_t = idesc_tf32(TS, C, 1, 0);     // T[128 x 64] = GU^T (MN-major A) . WcT (K-major B)
+      constexpr uint32_t id_w = idesc_tf32(C, C, 0, 0);      // dW[64 x 64] += GU (K-major A) . H (K-major B)
+      long long it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = (int)(it % B_STAGES);
+        mbar_wait(bar(BB_GUREADY), (uint32_t)(it & 1));      // gu written in place over g' (implies TMA landed)
+        mbar_wait(bar(BB_TEMPTY), (uint32_t)((it & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t gu = base + L.stage[s], hh = base + L.stage[s] + 2 * TILE;
+#pragma unroll
+        for (int k = 0; k < C / 8; ++k)
+          mma_ss(tmem_t, umma_desc_mn(gu + k * 1024, BOX), umma_desc(base + L.wt + (k >> 2) * BOX + (k & 3) * 32, 1024), id_t,
+                 k ? 1u : 0u);
+        mma_commit(bar(BB_TFULL));
+#pragma unroll
+        for (int k = 0; k < TS / 8; ++k)
+          mma_ss(tmem_dw, umma_desc(gu + (k >> 2) * BOX + (k & 3) * 32, 1024), umma_desc(hh + (k >> 2) * BOX + (k & 3) * 32, 1024),
+                 id_w, (it | k) ? 1u : 0u);
+        mma_commit(bar(BB_EMPTY + s));
+      }
+      mma_commit(bar(BB_DWDONE));
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float db[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) db[j] = 0.f;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = (int)(it % B_STAGES);
+      mbar_wait(bar(BB_FULL + s), (uint32_t)((it / B_STAGES) & 1));
+      const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
+      uint8_t* tg = sm + L.stage[s];
+      const uint8_t* tu = tg + TILE;
+      const size_t g0 = ((size_t)b * C) * S + s0 + 32 * q + lane;
+      // ---- step 1: gu = g' * gelu'(u), in place (this warp: channels [32*half, +32), points [32q, +32)) ----
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int o = half * 32 + j;
+        const uint32_t off = tile_off(o, 32 * q + lane);
+        const float gv = *reinterpret_cast<const float*>(tg + off);
+        const float uv = *reinterpret_cast<const float*>(tu + off);
+        const float r = gv * gelu_grad_f(uv);
+        *reinterpret_cast<float*>(tg + off) = r;
+        gu_out[g0 + (size_t)o * S] = r;
+        db[j] += r;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BB_GUREADY));
+      // ---- epilogue: t[c][s] = (Wc^T gu)[c][s] + gu[c][s] --------------------------------------------
+      mbar_wait(bar(BB_TFULL), (uint32_t)(it & 1));
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem_t + lane_base + half * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BB_TEMPTY));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = half * 32 + j;
+        const float r = *reinterpret_cast<const float*>(tg + tile_off(c, 32 * q + lane));
+        __stcs(t_out + g0 + (size_t)c * S, v[j] + r);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BB_EMPTY + s));
+    }
+    // ---- per-CTA partials: dbias (registers -> warp shuffle -> 4 quarter-warps summed in order) and dW (TMEM) ----
+    float* red = reinterpret_cast<float*>(sm + L.red);      // [4 quarters][64]
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = db[j];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+      if (lane == 0) red[q * C + half * 32 + j] = x;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* pout = partial + (size_t)blockIdx.x * (C * C + C);
+    if (warp == 2 && my_tiles >= 0) {
+      for (int o = lane; o < C; o += 32) pout[C * C + o] = (red[o] + red[C + o]) + (red[2 * C + o] + red[3 * C + o]);
+    }
+    if (my_tiles > 0) {
+      mbar_wait(bar(BB_DWDONE), 0);
+      tc_fence_after();
+      if (half == 0) {                 // M = 64 accumulator: rows 16q..16q+15 live in lanes 0..15 of quarter q
+        float w0[32], w1[32];
+        tmem_ld32(tmem_dw + lane_base, w0);
+        tmem_ld32(tmem_dw + lane_base + 32, w1);
+        tmem_ld_wait();
+        if (lane < 16) {
+          float* row = pout + (size_t)(16 * q + lane) * C;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { row[c] = w0[c]; row[32 + c] = w1[c]; }
+        }
+      }
+    } else if (half == 0 && lane < 16) {
+      float* row = pout + (size_t)(16 * q + lane) * C;
+      for (int c = 0; c < C; ++c) row[c] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+__global__ void block_tail_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db,
+                                         int nparts) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * C + C) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * (C * C + C) + idx];
+  if (idx < C * C) dW[idx] = (float)s;
+  else if (db) db[idx - C * C] = (float)s;
+}
+
+}  // namespace blk
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder();
+
+static int make_map(CUtensorMap* m, const float* p, long long rows, long long S) {
+  const cuuint64_t dims[2] = {(cuuint64_t)S, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)S * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t)blk::C};
+  const cuuint32_t estr[2] = {1, 1};
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return fail(PDEPHI_ERR_UNSUPPORTED, "block_tail: cuTensorMapEncodeTiled is not available");
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PDEPHI_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return PDEPHI_OK;
+}
+
+static int check_shape(int B, int Cc, long long S, const char* who) {
+  PDEPHI_REQUIRE(B > 0 && S > 0, "%s: non-positive size", who);
+  if (Cc != blk::C || S % blk::TS != 0 || (long long)B * Cc > 0x7fffffffLL || S > 0x7fffffffLL)
+    return fail(PDEPHI_ERR_UNSUPPORTED, "%s: needs 64 channels and a spatial size divisible by 128 (got C=%d, S=%lld)", who, Cc, S);
+  return PDEPHI_OK;
+}
+
+static int num_sms() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+}  // namespace pdephi
+
+using namespace pdephi;
+
+extern "C" int pdephi_block_tail_fwd(const float* h, const float* spec, const float* Wc, const float* bc, float* u,
+                                     float* hout, int B, int Cc, long long S, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(h && spec && Wc && u && hout, "block_tail_fwd: null pointer");
+  int rc = check_shape(B, Cc, S, "block_tail_fwd");
+  if (rc) return rc;
+  CUtensorMap mh, ms;
+  if ((rc = make_map(&mh, h, (long long)B * Cc, S))) return rc;
+  if ((rc = make_map(&ms, spec, (long long)B * Cc, S))) return rc;
+  const long long tpb = S / blk::TS, ntiles = tpb * B;
+  const size_t smem = blk::fwd_smem().total + 1024;
+  auto k = blk::block_tail_fwd_kernel;
+  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sms = num_sms();
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    ProfScope ps(K_BLOCK_TAIL_FWD, st);
+    k<<<grid, blk::THREADS, smem, st>>>(mh, ms, Wc, bc, u, hout, tpb, ntiles, S);
+  }
+  PDEPHI_LAUNCH_CHECK("block_tail_fwd_kernel");
+  return PDEPHI_OK;
+}
+
+extern "C" size_t pdephi_block_tail_bwd_workspace_bytes(int Cc) {
+  if (Cc != blk::C) return 0;
+  return align_up((size_t)1024 * (blk::C * blk::C + blk::C) * sizeof(float), 256);   // up to 1024 CTAs of partials
+}
+
+extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t,
+                                     float* dWc, float* dbc, int B, int Cc, long long S, void* workspace,
+                                     size_t workspace_bytes, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(g && u && h && Wc && gu && t && dWc, "block_tail_bwd: null pointer");
+  int rc = check_shape(B, Cc, S, "block_tail_bwd");
+  if (rc) return rc;
+  const size_t need = pdephi_block_tail_bwd_workspace_bytes(Cc);
+  if (!workspace || workspace_bytes < need) return fail(PDEPHI_ERR_WORKSPACE, "block_tail_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
+  CUtensorMap mg, mu, mh;
+  if ((rc = make_map(&mg, g, (long long)B * Cc, S))) return rc;
+  if ((rc = make_map(&mu, u, (long long)B * Cc, S))) return rc;
+  if ((rc = make_map(&mh, h, (long long)B * Cc, S))) return rc;
+  const long long tpb = S / blk::TS, ntiles = tpb * B;
+  const size_t smem = blk::bwd_smem().total + 1024;
+  auto k = blk::block_tail_bwd_kernel;
+  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = num_sms();
+  if (sms > 1024) sms = 1024;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    ProfScope ps(K_BLOCK_TAIL_BWD, st);
+    k<<<grid, blk::THREADS, smem, st>>>(mg, mu, mh, Wc, gu, t, (float*)workspace, tpb, ntiles, S);
+  }
+  PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
+  {
+    ProfScope ps(K_BLOCK_TAIL_BWD, st);
+    blk::block_tail_reduce_kernel<<<(blk::C * blk::C + blk::C + 127) / 128, 128, 0, st>>>((const float*)workspace, dWc, dbc, grid);
+  }
+  PDEPHI_LAUNCH_CHECK("block_tail_reduce_kernel");
+  return PDEPHI_OK;
+}

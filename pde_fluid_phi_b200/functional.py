@@ -191,20 +191,55 @@ def complex_mix_bwd(X, W, dY, mzh: int):
     return dX, dW
 
 
+def block_tail_fwd(h, spec, Wc, bc):
+    """u = spec + (Wc h + bc) + h, hout = gelu(u) on [B,64,...] tensors (tcgen05 TF32 channel GEMM, fused epilogue)."""
+    B, C = h.shape[:2]
+    S = h[0, 0].numel()
+    lib = _cabi.load()
+    with torch.cuda.device(h.device):
+        u = torch.empty_like(h)
+        hout = torch.empty_like(h)
+        _cabi.check(lib.pdephi_block_tail_fwd(_p(h), _p(spec), _p(Wc), _p(bc), _p(u), _p(hout), B, C, S, _stream()),
+                    "block_tail_fwd")
+    return u, hout
+
+
+def block_tail_bwd(g, u, h, Wc, want_bias: bool):
+    """gu = g gelu'(u), t = gu + Wc^T gu, dWc = sum gu (x) h, dbc = sum gu."""
+    B, C = h.shape[:2]
+    S = h[0, 0].numel()
+    lib = _cabi.load()
+    with torch.cuda.device(h.device):
+        gu = torch.empty_like(h)
+        t = torch.empty_like(h)
+        dW = torch.empty((C, C), dtype=torch.float32, device=h.device)
+        db = torch.empty(C, dtype=torch.float32, device=h.device) if want_bias else None
+        nbytes = lib.pdephi_block_tail_bwd_workspace_bytes(C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+        _cabi.check(lib.pdephi_block_tail_bwd(_p(g), _p(u), _p(h), _p(Wc), _p(gu), _p(t), _p(dW), _p(db), B, C, S, _p(ws),
+                                              nbytes, _stream()), "block_tail_bwd")
+    return gu, t, dW, db
+
+
+def block_tail_supported(h: torch.Tensor, precision: int) -> bool:
+    return (h.is_cuda and h.dtype == torch.float32 and h.dim() == 5 and h.shape[1] == 64
+            and h[0, 0].numel() % 128 == 0 and precision == _cabi.PREC_TF32)
+
+
 # ------------------------------------------------------------------------------------------------
 # autograd Functions
 # ------------------------------------------------------------------------------------------------
 def _slab_args(slab, x):
     """slab = None | (process_group, Nx_total): this rank holds x planes [rank*Nx, (rank+1)*Nx) of the grid."""
     if slab is None:
-        return None, None, 1
+        return False, None, 1
     import torch.distributed as dist
     group, nx_total = slab
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     nx = x.shape[2]
     if nx * world != nx_total:
         raise ValueError(f"slab decomposition needs Nx_total == world * local Nx, got {nx_total} vs {world} * {nx}")
-    return group, (nx_total, rank * nx), world
+    return (group if group is not None else dist.group.WORLD), (nx_total, rank * nx), world
 
 
 def _allreduce_modes(X, group):
@@ -235,7 +270,7 @@ class RationalSpectralFn(torch.autograd.Function):
         P = P.contiguous()
         Q = Q.contiguous()
         X = analysis(x, modes_h, _cabi.FORWARD, precision, slab_plan)
-        if group is not None:
+        if group:
             _allreduce_modes(X, group)          # partial sums over the x slabs -> every rank holds the full modes
         need_grad = any(ctx.needs_input_grad[:3])
         Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
@@ -257,7 +292,7 @@ class RationalSpectralFn(torch.autograd.Function):
         dx = dP = dQ = None
         if need_x or need_P or need_Q:
             dZ = analysis(g, modes_h, _cabi.ADJOINT, precision, slab_plan)
-            if group is not None:
+            if group:
                 _allreduce_modes(dZ, group)
             dY = projection_bwd(dZ, Y, mask, stats)
             dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
@@ -286,7 +321,7 @@ class ComplexSpectralFn(torch.autograd.Function):
         group, slab_plan, world = _slab_args(slab, x)
         W = W.contiguous()
         X = analysis(x, modes_h, _cabi.FORWARD, precision, slab_plan)
-        if group is not None:
+        if group:
             _allreduce_modes(X, group)
         Y = complex_mix_fwd(X, W, modes_h[2])
         out = synthesis(Y, grid, None, None, skip0, x if residual else None, _cabi.FORWARD, precision, slab_plan)
@@ -304,7 +339,7 @@ class ComplexSpectralFn(torch.autograd.Function):
         dx = dW = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             dY = analysis(g, modes_h, _cabi.ADJOINT, precision, slab_plan)
-            if group is not None:
+            if group:
                 _allreduce_modes(dY, group)
             dX, dW = complex_mix_bwd(X, W, dY, modes_h[2])
             if world > 1:
@@ -366,3 +401,91 @@ class PointwiseLinearFn(torch.autograd.Function):
 def pointwise_linear_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x[0, 0].numel() % 4 == 0
             and min(weight.shape[0], weight.shape[1]) <= 8)
+
+
+class RationalBlockFn(torch.autograd.Function):
+    """One whole block of RationalFourierOperator3D: h' = gelu(RationalFourierLayer(h) + Conv1x1(h) + h)
+    (rational_fourier.py:263-271) as K1 -> K2 -> K3 -> fused block tail, with a hand-written backward that
+    needs no autograd-side accumulation passes (the three branch gradients of h meet in K3's epilogue)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, h, P, Q, mask, monoP, monoQ, modes, eps, precision, Wc, bc, slab=None):
+        for t, n in ((h, "x"), (P, "P_coeffs"), (Q, "Q_coeffs"), (Wc, "conv weight")):
+            _require_cuda_f32(t, n)
+        h = h.contiguous()
+        mx, my, mz = modes
+        modes_h = (mx, my, mz // 2 + 1)
+        grid = tuple(h.shape[2:])
+        group, slab_plan, world = _slab_args(slab, h)
+        P, Q, Wc = P.contiguous(), Q.contiguous(), Wc.contiguous()
+        X = analysis(h, modes_h, _cabi.FORWARD, precision, slab_plan)
+        if group:
+            _allreduce_modes(X, group)
+        need_grad = any(ctx.needs_input_grad)
+        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
+        spec = synthesis(Y, grid, mask, stats[:, 2], None, None, _cabi.FORWARD, precision, slab_plan)
+        u, hout = block_tail_fwd(h, spec, Wc, bc)
+        if need_grad:
+            ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc)
+        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, bc is not None, group, slab_plan, world)
+        return hout
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, g):
+        X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc = ctx.saved_tensors
+        modes_h, grid, coeff_shapes, precision, has_bias, group, slab_plan, world = ctx.meta
+        gu, t, dWc, dbc = block_tail_bwd(g.contiguous(), u, h, Wc, has_bias)
+        dZ = analysis(gu, modes_h, _cabi.ADJOINT, precision, slab_plan)
+        if group:
+            _allreduce_modes(dZ, group)
+        dY = projection_bwd(dZ, Y, mask, stats)
+        dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
+        if world > 1:
+            dP.div_(world)
+            dQ.div_(world)
+        dh = synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision, slab_plan)
+        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None)
+
+
+class ComplexBlockFn(torch.autograd.Function):
+    """One whole block of FNO3D: h' = gelu(SpectralConv3D(h) + Conv1x1(h) + h) (models/fno3d.py:91-97)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, h, W, modes, precision, Wc, bc, slab=None):
+        _require_cuda_f32(h, "x")
+        _require_cuda_f32(W, "weights", complex_ok=True)
+        h = h.contiguous()
+        mx, my, mz = modes
+        modes_h = (mx, my, mz // 2 + 1)
+        grid = tuple(h.shape[2:])
+        group, slab_plan, world = _slab_args(slab, h)
+        W, Wc = W.contiguous(), Wc.contiguous()
+        X = analysis(h, modes_h, _cabi.FORWARD, precision, slab_plan)
+        if group:
+            _allreduce_modes(X, group)
+        Y = complex_mix_fwd(X, W, modes_h[2])
+        spec = synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, precision, slab_plan)
+        u, hout = block_tail_fwd(h, spec, Wc, bc)
+        ctx.save_for_backward(X, W, u, h, Wc)
+        ctx.meta = (modes_h, grid, precision, bc is not None, group, slab_plan, world)
+        return hout
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, g):
+        X, W, u, h, Wc = ctx.saved_tensors
+        modes_h, grid, precision, has_bias, group, slab_plan, world = ctx.meta
+        gu, t, dWc, dbc = block_tail_bwd(g.contiguous(), u, h, Wc, has_bias)
+        dY = analysis(gu, modes_h, _cabi.ADJOINT, precision, slab_plan)
+        if group:
+            _allreduce_modes(dY, group)
+        dX, dW = complex_mix_bwd(X, W, dY, modes_h[2])
+        if world > 1:
+            dW.div_(world)
+        dh = synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision, slab_plan)
+        return dh, dW, None, None, dWc.view_as(Wc), dbc, None

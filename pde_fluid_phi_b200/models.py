@@ -110,9 +110,12 @@ class RationalFourierOperator3D(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         h = _lift(x, self.input_proj)
+        gelu = self.activation is F.gelu
         for spectral, local in zip(self.rational_layers, self.local_convs):
-            # spectral(h) + local(h) + h in one pass: both adds ride in the synthesis kernel's epilogue
-            h = self.activation(spectral.forward_fused(h, local(h)))
+            if gelu and spectral.block_supported(h, local):
+                h = spectral.forward_block(h, local)          # whole block in the library (TF32 path, width 64)
+            else:   # spectral(h) + local(h) + h in one pass: both adds ride in the synthesis kernel's epilogue
+                h = self.activation(spectral.forward_fused(h, local(h)))
         out = _lift(h, self.output_proj)
         return self.final_activation(out) if self.final_activation is not None else out
 
@@ -203,8 +206,12 @@ class FNO3D(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         h = _lift(x, self.input_proj)
+        gelu = self.activation is F.gelu
         for spectral, local in zip(self.spectral_layers, self.local_layers):
-            h = self.activation(spectral.forward_fused(h, local(h)))
+            if gelu and spectral.block_supported(h, local):
+                h = spectral.forward_block(h, local)
+            else:
+                h = self.activation(spectral.forward_fused(h, local(h)))
         out = _lift(h, self.output_proj)
         return self.final_activation(out) if self.final_activation is not None else out
 

@@ -17,7 +17,8 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .functional import ComplexSpectralFn, RationalSpectralFn, monomial_exponents, monomial_table
+from .functional import (ComplexBlockFn, ComplexSpectralFn, RationalBlockFn, RationalSpectralFn, block_tail_supported,
+                         monomial_exponents, monomial_table)
 
 _default_precision = "fp32"
 
@@ -162,6 +163,20 @@ class RationalFourierLayer(nn.Module):
         (the block body of rational_fourier.py:263-271 minus the activation)."""
         return self._run(x, x_local, True)
 
+    def block_supported(self, x: torch.Tensor, conv: nn.Module) -> bool:
+        return (isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.groups == 1
+                and conv.in_channels == conv.out_channels == self.in_channels == self.out_channels
+                and block_tail_supported(x, self._precision_code()))
+
+    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d) -> torch.Tensor:
+        """gelu(layer(x) + conv(x) + x): the whole block of rational_fourier.py:263-271 in the library
+        (TF32 path, width 64): spectral layer, then the 1x1x1 convolution as a tcgen05 channel GEMM whose
+        epilogue applies bias, both residual adds and the exact GELU."""
+        _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
+        return RationalBlockFn.apply(x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
+                                     self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
+                                     self._precision_code(), conv.weight, conv.bias, self.slab)
+
 
 class SpectralConv3D(nn.Module):
     """Classic FNO spectral convolution with a complex [O, I, mx, my, mz] weight.
@@ -196,3 +211,14 @@ class SpectralConv3D(nn.Module):
     def forward_fused(self, x: torch.Tensor, x_local: torch.Tensor) -> torch.Tensor:
         """conv(x) + x_local + x, adds fused into the synthesis epilogue (models/fno3d.py:91-97)."""
         return self._run(x, x_local, True)
+
+    def block_supported(self, x: torch.Tensor, conv: nn.Module) -> bool:
+        return (isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.groups == 1
+                and conv.in_channels == conv.out_channels == self.in_channels == self.out_channels
+                and block_tail_supported(x, self._precision_code()))
+
+    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d) -> torch.Tensor:
+        """gelu(spectral_conv(x) + conv(x) + x): the whole block of models/fno3d.py:91-97 in the library."""
+        _check_input(x, self.in_channels, self.modes, "SpectralConv3D", self.slab)
+        return ComplexBlockFn.apply(x, self.weights, tuple(self.modes), self._precision_code(), conv.weight, conv.bias,
+                                    self.slab)

@@ -414,3 +414,65 @@ def test_slab_parallel_two_gpus():
     for r in range(2):
         e_out, e_grad = out[r]
         assert e_out < 1e-5 and e_grad < 5e-5, (r, e_out, e_grad)
+
+
+def test_fused_block_tail_vs_torch():
+    """The tcgen05 block tail (1x1x1 conv + residual adds + exact GELU, forward and backward) against the torch ops it
+    replaces, on the same spectral output; TF32 gate."""
+    torch.manual_seed(31)
+    B, C, grid = 2, 64, (8, 8, 16)
+    conv = torch.nn.Conv3d(C, C, 1).to(DEV)
+    h = torch.randn(B, C, *grid, device=DEV, requires_grad=True)
+    spec = torch.randn(B, C, *grid, device=DEV, requires_grad=True)
+    g = torch.randn(B, C, *grid, device=DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.nn.functional.gelu(spec + conv(h) + h)
+        ref.backward(g)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    u, hout = pf.block_tail_fwd(h.detach(), spec.detach(), conv.weight.detach().reshape(C, C).contiguous(), conv.bias.detach())
+    assert rel(hout, ref) < TOL["tf32"]
+    assert rel(u, (spec + conv(h) + h)) < TOL["tf32"]
+    gu, t, dW, db = pf.block_tail_bwd(g, u, h.detach(), conv.weight.detach().reshape(C, C).contiguous(), True)
+    assert rel(gu, spec.grad) < TOL["tf32"]                  # d/d spec = g * gelu'(u)
+    assert rel(t, h.grad) < TOL["tf32"]                      # d/d h (conv + residual branches)
+    assert rel(dW, conv.weight.grad.reshape(C, C)) < TOL["tf32"]
+    assert rel(db, conv.bias.grad) < TOL["tf32"]
+
+
+def test_whole_block_model_tf32_vs_unfused():
+    """RationalFourierOperator3D at width 64 takes the fused-block route in TF32 mode; compare with the unfused route
+    (same kernels for the spectral part, torch for conv / GELU) on outputs and every parameter gradient."""
+    torch.manual_seed(33)
+    modes, grid = (8, 16, 16), (4, 128, 64)
+    if not tc_ok(grid, modes):
+        pytest.skip("tcgen05 path not available")
+    model = pb.RationalFourierOperator3D(modes=modes, width=64, n_layers=2).to(DEV).set_precision("tf32")
+    with torch.no_grad():
+        for layer in model.rational_layers:      # conditioned weights keep the comparison well posed
+            q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+            layer.Q_coeffs.mul_(1e-4)
+            layer.Q_coeffs[..., 0, 0, 0] = q0
+            layer.P_coeffs.mul_(1e-2)
+    x = torch.randn(2, 3, *grid, device=DEV)
+    y = torch.randn(2, 3, *grid, device=DEV)
+    assert model.rational_layers[0].block_supported(torch.empty(2, 64, *grid, device=DEV), model.local_convs[0])
+    loss = torch.nn.functional.mse_loss(model(x), y)
+    loss.backward()
+    fused = {n: p.grad.clone() for n, p in model.named_parameters()}
+    out_fused = model(x).detach()
+    model.zero_grad()
+    model.activation = lambda t: torch.nn.functional.gelu(t)        # not F.gelu itself -> unfused route
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        loss2 = torch.nn.functional.mse_loss(model(x), y)
+        loss2.backward()
+        out_ref = model(x).detach()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel(out_fused, out_ref) < 3e-3
+    for n, p in model.named_parameters():
+        assert rel(fused[n], p.grad) < 5e-3, n
