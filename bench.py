@@ -178,10 +178,10 @@ def run_reference(args):
 
 def workload_config(n_gpus: int, precision: str) -> dict:
     return {"workload": "RationalFourierOperator3D modes=(32,32,32) width=64 rational_order=(4,4) n_layers=4, "
-                        "128^3 synthetic random-spectrum turbulence, batch 8 per GPU, fwd+MSE+bwd+AdamW(lr 1e-3, wd 1e-4), AMP off",
+                        "128^3 synthetic random-spectrum turbulence, batch 8 per GPU, fwd+MSE+bwd+clip_grad_norm(1.0)+AdamW(lr 1e-3 with the trainer's linear warm-up over 1e5 steps, wd 1e-4), AMP off",
             "global_batch": CFG["batch_per_gpu"] * n_gpus, "grid": [CFG["grid"]] * 3, "parallelism": f"dp{n_gpus}",
             "transform_precision": precision,
-            "init": "reference init (seed 1234) with non-constant Q_coeffs x1e-4 and P_coeffs x1e-2 so the 4-layer loss stays finite",
+            "init": "reference init (seed 1234) with non-constant Q_coeffs x1e-4 and P_coeffs x1e-4 (activations O(1)); the default init has poles of R(k) inside the retained box and overflows in 4 layers, in the reference too",
             "l2": "per-step activations (4.3 GB per tensor) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -219,20 +219,31 @@ def run_native(args):
             q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
             layer.Q_coeffs.mul_(1e-4)
             layer.Q_coeffs[..., 0, 0, 0] = q0
-            layer.P_coeffs.mul_(1e-2)
+            layer.P_coeffs.mul_(1e-4)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
     x = turbulence_batch(B, n, 42 + rank, dev)
     y = turbulence_batch(B, n, 1042 + rank, dev)
     hx, hy = x.cpu().pin_memory(), y.cpu().pin_memory()
     h_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
+    # The reference's train step (training/stability_trainer.py:170-210): zero_grad, loss, backward, clip_grad_norm_,
+    # AdamW step, linear LR warm-up (warmup_epochs=10 of an assumed 10k-batch epoch -> 1e5 steps: AdamW's sign-like
+    # first steps move every Q coefficient by ~lr, and 1e-6 * k^3 (k up to 31) is already enough to put a pole of
+    # R(k) inside the retained box, so the reference parameterisation only trains with a long warm-up).
+    state = {"n": 0}
+    params = [p for p in model.parameters()]
+
     def step(xd, yd):
         opt.zero_grad(set_to_none=True)
         loss = torch.nn.functional.mse_loss(model(xd), yd)
         loss.backward()
         if world > 1:
-            allreduce_gradients(model.parameters(), world)
+            allreduce_gradients(params, world)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
+        state["n"] += 1
+        for gparam in opt.param_groups:
+            gparam["lr"] = min(1.0, (state["n"] + 1) / 1e5) * 1e-3
         return loss
 
     def step_e2e():
@@ -260,8 +271,11 @@ def run_native(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    first_loss = None
     for _ in range(max(args.warmup, 3)):
-        step(x, y)
+        l0 = step(x, y)
+        if first_loss is None:
+            first_loss = float(l0.detach())
     # ---- timed region 1: inputs resident in HBM ---------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
@@ -318,7 +332,7 @@ def run_native(args):
                 "e2e": {"value": round(e2e_value, 3), "unit": "samples/s",
                         "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "kernels": per_kernel, "final_loss": final_loss}
+                "kernels": per_kernel, "first_loss": first_loss, "final_loss": final_loss}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

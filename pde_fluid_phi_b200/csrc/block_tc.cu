@@ -23,22 +23,28 @@ constexpr int TILE = 4 * BOX;    // 32 KB
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 
-// MN-major operand (M or N contiguous): atoms of 32 elements along MN are `lbo` bytes apart, 8-row K groups 1024 B
+// MN-major TF32 operand (M or N contiguous).  32-bit MN-major operands exist only in the "128B swizzle with
+// 32-byte atoms" layout (UMMA LayoutType 1 = SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+// atoms of 32 elements along MN are `lbo` bytes apart, K rows are 128 B apart in groups of 4 (512 B).
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)(512u >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// byte offset of (channel row r, point s in [0,128)) inside a tile
+// byte offset of (channel row r, point s in [0,128)) inside a tile staged with 32-byte-atom swizzle (MN-major use)
 __device__ __forceinline__ uint32_t tile_off(int r, int s) {
+  return (uint32_t)((s >> 5) * BOX + r * 128 + (((((s & 31) >> 3) ^ (r & 3)) & 3) << 5) + (s & 7) * 4);
+}
+// same element in a tile with the standard 16-byte-chunk 128B swizzle (K-major use)
+__device__ __forceinline__ uint32_t tile_off_k(int r, int s) {
   return (uint32_t)((s >> 5) * BOX + r * 128 + (((((s & 31) >> 2) ^ (r & 7)) & 7) << 4) + (s & 3) * 4);
 }
 __device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
@@ -49,7 +55,8 @@ __device__ __forceinline__ float gelu_grad_f(float u) {
 __device__ __forceinline__ void build_w_image(uint8_t* dst, const float* __restrict__ W, bool transpose, int tid, int nthr) {
   for (int i = tid; i < C * C; i += nthr) {
     const int r = i >> 6, k = i & 63;
-    const float v = transpose ? __ldg(W + k * C + r) : __ldg(W + i);
+    // (1 + 2^-11): the data operand of this GEMM is truncated to TF32 by the tensor core (mean bias -2^-11)
+    const float v = (transpose ? __ldg(W + k * C + r) : __ldg(W + i)) * 1.00048828125f;
     *reinterpret_cast<float*>(dst + swz_off(C, r, k)) = to_tf32(v);
   }
 }
@@ -175,7 +182,7 @@ constexpr int B_STAGES = 2;
 struct BSmem { uint32_t stage[B_STAGES], wt, red, bars, tmem_slot, total; };
 __host__ __device__ inline BSmem bwd_smem() {
   BSmem s; uint32_t o = 0;
-  for (int i = 0; i < B_STAGES; ++i) { s.stage[i] = o; o += 3 * TILE; }   // g' (becomes gu), u, h
+  for (int i = 0; i < B_STAGES; ++i) { s.stage[i] = o; o += 3 * TILE; }   // g' (-> gu, MN layout), h (K layout), u (-> gu, K layout)
   s.wt = o; o += 2 * BOX;
   s.red = o; o += 4 * C * 4;
   s.bars = o; o += 128;
@@ -187,8 +194,8 @@ enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2
        BB_DWDONE = 2 * B_STAGES + 3 };
 
 __global__ void __launch_bounds__(THREADS, 1)
-block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_u,
-                      const __grid_constant__ CUtensorMap tmap_h, const float* __restrict__ Wc, float* __restrict__ gu_out,
+block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_h,
+                      const __grid_constant__ CUtensorMap tmap_u, const float* __restrict__ Wc, float* __restrict__ gu_out,
                       float* __restrict__ t_out, float* __restrict__ partial, long long tiles_per_batch, long long ntiles,
                       long long S) {
   extern __shared__ uint8_t smem_raw[];
@@ -228,8 +235,8 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           tma_load_2d(base + L.stage[s] + j * BOX, &tmap_g, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
-          tma_load_2d(base + L.stage[s] + TILE + j * BOX, &tmap_u, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
-          tma_load_2d(base + L.stage[s] + 2 * TILE + j * BOX, &tmap_h, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
+          tma_load_2d(base + L.stage[s] + TILE + j * BOX, &tmap_h, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
+          tma_load_2d(base + L.stage[s] + 2 * TILE + j * BOX, &tmap_u, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
         }
       }
     }
@@ -243,7 +250,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
         mbar_wait(bar(BB_GUREADY), (uint32_t)(it & 1));      // gu written in place over g' (implies TMA landed)
         mbar_wait(bar(BB_TEMPTY), (uint32_t)((it & 1) ^ 1));
         tc_fence_after();
-        const uint32_t gu = base + L.stage[s], hh = base + L.stage[s] + 2 * TILE;
+        const uint32_t gu = base + L.stage[s], hh = gu + TILE, guk = gu + 2 * TILE;
 #pragma unroll
         for (int k = 0; k < C / 8; ++k)
           mma_ss(tmem_t, umma_desc_mn(gu + k * 1024, BOX), umma_desc(base + L.wt + (k >> 2) * BOX + (k & 3) * 32, 1024), id_t,
@@ -251,7 +258,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
         mma_commit(bar(BB_TFULL));
 #pragma unroll
         for (int k = 0; k < TS / 8; ++k)
-          mma_ss(tmem_dw, umma_desc(gu + (k >> 2) * BOX + (k & 3) * 32, 1024), umma_desc(hh + (k >> 2) * BOX + (k & 3) * 32, 1024),
+          mma_ss(tmem_dw, umma_desc(guk + (k >> 2) * BOX + (k & 3) * 32, 1024), umma_desc(hh + (k >> 2) * BOX + (k & 3) * 32, 1024),
                  id_w, (it | k) ? 1u : 0u);
         mma_commit(bar(BB_EMPTY + s));
       }
@@ -266,20 +273,22 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
     long long it = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = (int)(it % B_STAGES);
-      mbar_wait(bar(BB_FULL + s), (uint32_t)((it / B_STAGES) & 1));
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       uint8_t* tg = sm + L.stage[s];
-      const uint8_t* tu = tg + TILE;
+      uint8_t* tgk = tg + 2 * TILE;
       const size_t g0 = ((size_t)b * C) * S + s0 + 32 * q + lane;
-      // ---- step 1: gu = g' * gelu'(u), in place (this warp: channels [32*half, +32), points [32q, +32)) ----
+      // ---- step 1: gu = g' * gelu'(u) (this warp: channels [32*half, +32), points [32q, +32)).  gu replaces g' in place
+      //      (MN layout, operand of the Wc^T gu GEMM) and u in place (K layout, operand of the dWc GEMM), and goes to HBM ----
+      mbar_wait(bar(BB_FULL + s), (uint32_t)((it / B_STAGES) & 1));
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int o = half * 32 + j;
-        const uint32_t off = tile_off(o, 32 * q + lane);
+        const uint32_t off = tile_off(o, 32 * q + lane), offk = tile_off_k(o, 32 * q + lane);
         const float gv = *reinterpret_cast<const float*>(tg + off);
-        const float uv = *reinterpret_cast<const float*>(tu + off);
+        const float uv = *reinterpret_cast<const float*>(tgk + offk);
         const float r = gv * gelu_grad_f(uv);
         *reinterpret_cast<float*>(tg + off) = r;
+        *reinterpret_cast<float*>(tgk + offk) = to_tf32(r);
         gu_out[g0 + (size_t)o * S] = r;
         db[j] += r;
       }
@@ -348,7 +357,7 @@ __global__ void block_tail_reduce_kernel(const float* __restrict__ partial, floa
   if (idx >= C * C + C) return;
   double s = 0.0;
   for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * (C * C + C) + idx];
-  if (idx < C * C) dW[idx] = (float)s;
+  if (idx < C * C) dW[idx] = (float)(s * 1.00048828125);   // h is truncated to TF32 by the tensor core in the dWc GEMM
   else if (db) db[idx - C * C] = (float)s;
 }
 
@@ -359,7 +368,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tensor_map_encoder();
 
-static int make_map(CUtensorMap* m, const float* p, long long rows, long long S) {
+static int make_map(CUtensorMap* m, const float* p, long long rows, long long S, bool atom32) {
   const cuuint64_t dims[2] = {(cuuint64_t)S, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)S * sizeof(float)};
   const cuuint32_t box[2] = {32, (cuuint32_t)blk::C};
@@ -367,8 +376,8 @@ static int make_map(CUtensorMap* m, const float* p, long long rows, long long S)
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return fail(PDEPHI_ERR_UNSUPPORTED, "block_tail: cuTensorMapEncodeTiled is not available");
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PDEPHI_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return PDEPHI_OK;
 }
@@ -397,8 +406,8 @@ extern "C" int pdephi_block_tail_fwd(const float* h, const float* spec, const fl
   int rc = check_shape(B, Cc, S, "block_tail_fwd");
   if (rc) return rc;
   CUtensorMap mh, ms;
-  if ((rc = make_map(&mh, h, (long long)B * Cc, S))) return rc;
-  if ((rc = make_map(&ms, spec, (long long)B * Cc, S))) return rc;
+  if ((rc = make_map(&mh, h, (long long)B * Cc, S, true))) return rc;
+  if ((rc = make_map(&ms, spec, (long long)B * Cc, S, true))) return rc;
   const long long tpb = S / blk::TS, ntiles = tpb * B;
   const size_t smem = blk::fwd_smem().total + 1024;
   auto k = blk::block_tail_fwd_kernel;
@@ -427,10 +436,10 @@ extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float
   if (rc) return rc;
   const size_t need = pdephi_block_tail_bwd_workspace_bytes(Cc);
   if (!workspace || workspace_bytes < need) return fail(PDEPHI_ERR_WORKSPACE, "block_tail_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
-  CUtensorMap mg, mu, mh;
-  if ((rc = make_map(&mg, g, (long long)B * Cc, S))) return rc;
-  if ((rc = make_map(&mu, u, (long long)B * Cc, S))) return rc;
-  if ((rc = make_map(&mh, h, (long long)B * Cc, S))) return rc;
+  CUtensorMap mg, mh, mu;
+  if ((rc = make_map(&mg, g, (long long)B * Cc, S, true))) return rc;     // becomes gu: MN-major operand of the Wc^T gu GEMM
+  if ((rc = make_map(&mh, h, (long long)B * Cc, S, false))) return rc;    // K-major operand of the dWc GEMM
+  if ((rc = make_map(&mu, u, (long long)B * Cc, S, false))) return rc;    // becomes gu: K-major operand of the dWc GEMM
   const long long tpb = S / blk::TS, ntiles = tpb * B;
   const size_t smem = blk::bwd_smem().total + 1024;
   auto k = blk::block_tail_bwd_kernel;
@@ -441,7 +450,7 @@ extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope ps(K_BLOCK_TAIL_BWD, st);
-    k<<<grid, blk::THREADS, smem, st>>>(mg, mu, mh, Wc, gu, t, (float*)workspace, tpb, ntiles, S);
+    k<<<grid, blk::THREADS, smem, st>>>(mg, mh, mu, Wc, gu, t, (float*)workspace, tpb, ntiles, S);
   }
   PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
   {

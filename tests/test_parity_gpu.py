@@ -446,7 +446,7 @@ def test_whole_block_model_tf32_vs_unfused():
     """RationalFourierOperator3D at width 64 takes the fused-block route in TF32 mode; compare with the unfused route
     (same kernels for the spectral part, torch for conv / GELU) on outputs and every parameter gradient."""
     torch.manual_seed(33)
-    modes, grid = (8, 16, 16), (4, 128, 64)
+    modes, grid = (8, 16, 16), (8, 128, 64)
     if not tc_ok(grid, modes):
         pytest.skip("tcgen05 path not available")
     model = pb.RationalFourierOperator3D(modes=modes, width=64, n_layers=2).to(DEV).set_precision("tf32")
