@@ -220,7 +220,7 @@ def run_native(args):
             layer.Q_coeffs.mul_(1e-4)
             layer.Q_coeffs[..., 0, 0, 0] = q0
             layer.P_coeffs.mul_(1e-4)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3 / 1e5, weight_decay=1e-4)   # warm-up value of step 0
     x = turbulence_batch(B, n, 42 + rank, dev)
     y = turbulence_batch(B, n, 1042 + rank, dev)
     hx, hy = x.cpu().pin_memory(), y.cpu().pin_memory()
