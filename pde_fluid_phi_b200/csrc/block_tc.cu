@@ -366,14 +366,14 @@ __global__ void block_tail_reduce_kernel(const float* __restrict__ partial, floa
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn tensor_map_encoder();
+EncodeTiledFn tensor_map_encoder(const void* device_ptr);
 
 static int make_map(CUtensorMap* m, const float* p, long long rows, long long S, bool atom32) {
   const cuuint64_t dims[2] = {(cuuint64_t)S, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)S * sizeof(float)};
   const cuuint32_t box[2] = {32, (cuuint32_t)blk::C};
   const cuuint32_t estr[2] = {1, 1};
-  EncodeTiledFn enc = tensor_map_encoder();
+  EncodeTiledFn enc = tensor_map_encoder(p);
   if (!enc) return fail(PDEPHI_ERR_UNSUPPORTED, "block_tail: cuTensorMapEncodeTiled is not available");
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,

@@ -404,9 +404,14 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn tensor_map_encoder();
-static EncodeTiledFn encode_fn() { return tensor_map_encoder(); }
-EncodeTiledFn tensor_map_encoder() {
+EncodeTiledFn tensor_map_encoder(const void* device_ptr);
+static EncodeTiledFn encode_fn(const void* device_ptr = nullptr) { return tensor_map_encoder(device_ptr); }
+// cuTensorMapEncodeTiled is a driver-API call and needs the primary context current on the calling thread; an
+// autograd worker thread may not have touched the runtime yet (CUDA_ERROR_INVALID_CONTEXT).  cudaSetDevice binds it.
+EncodeTiledFn tensor_map_encoder(const void* device_ptr) {
+  cudaPointerAttributes attr;
+  if (device_ptr && cudaPointerGetAttributes(&attr, device_ptr) == cudaSuccess && attr.type == cudaMemoryTypeDevice)
+    cudaSetDevice(attr.device);
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -480,7 +485,7 @@ int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int dire
   const cuuint64_t strides[1] = {(cuuint64_t)p->Nz * sizeof(float)};
   const cuuint32_t box[2] = {32, 128};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
+  CUresult r = encode_fn(x)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PDEPHI_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
