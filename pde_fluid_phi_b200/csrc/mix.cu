@@ -213,7 +213,7 @@ projection_bwd_kernel(const float2* __restrict__ dZ, const float2* __restrict__ 
 // exactly once (thread = mode k, IT input channels x BT batch entries per thread).
 // ---------------------------------------------------------------------------------------------
 constexpr int IT = 4;
-__global__ void __launch_bounds__(MIX_THREADS)
+__global__ void __launch_bounds__(MIX_THREADS, 4)
 mix_from_R_kernel(const float2* __restrict__ dY, float2* __restrict__ dX, const float* __restrict__ R, int B, int I,
                   int O, long long M) {
   const long long k = (long long)blockIdx.x * MIX_THREADS + threadIdx.x;
@@ -259,7 +259,7 @@ mix_from_R_kernel(const float2* __restrict__ dY, float2* __restrict__ dX, const 
 //   dR[o,i,k] = sum_b Re(conj(X[b,i,k]) dY[b,o,k]);  g = dR/Qe;  dP_t += g mono_t;  dQ_t += -g R mono_t
 // ---------------------------------------------------------------------------------------------
 constexpr int DPQ_THREADS = 256;
-constexpr int KT = 8;
+constexpr int KT = 8;   // (staging index math assumes KT == 8)
 constexpr int KTP = KT + 1;
 
 template <int OP, int OQ>
@@ -304,23 +304,30 @@ rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY,
     for (int kk = 0; kk < KT; ++kk) dR[kk] = 0.f;
     for (int b0 = 0; b0 < B; b0 += BT) {
       __syncthreads();
-      for (int idx = threadIdx.x; idx < BT * I * KT; idx += DPQ_THREADS) {
-        const int kk = idx % KT, r = idx / KT, ii = r % I, bb = r / I;
-        const long long k = k0 + kk;
-        float2 v = make_float2(0.f, 0.f);
-        if (b0 + bb < B && k < k_hi) v = __ldg(X + ((size_t)(b0 + bb) * I + ii) * M + k);
-        Xs[(size_t)r * KTP + kk] = v;
-      }
-      for (int idx = threadIdx.x; idx < BT * nO * KT; idx += DPQ_THREADS) {
-        const int kk = idx % KT, r = idx / KT, oo = r % nO, bb = r / nO;
-        const long long k = k0 + kk;
-        float2 v = make_float2(0.f, 0.f);
-        if (b0 + bb < B && k < k_hi) v = __ldg(dY + ((size_t)(b0 + bb) * O + o_lo + oo) * M + k);
-        Ys[((size_t)bb * nOmax + oo) * KTP + kk] = v;
+      // (no runtime divisions in the staging loops: KT is a power of two, the batch entry is an explicit loop)
+#pragma unroll
+      for (int bb = 0; bb < BT; ++bb) {
+        const bool bok = b0 + bb < B;
+        const float2* xsrc = X + (size_t)(bok ? b0 + bb : 0) * I * M;
+        for (int idx = threadIdx.x; idx < I * KT; idx += DPQ_THREADS) {
+          const int kk = idx & (KT - 1), ii = idx >> 3;
+          const long long k = k0 + kk;
+          float2 v = make_float2(0.f, 0.f);
+          if (bok && k < k_hi) v = __ldg(xsrc + (size_t)ii * M + k);
+          Xs[((size_t)bb * I + ii) * KTP + kk] = v;
+        }
+        const float2* ysrc = dY + ((size_t)(bok ? b0 + bb : 0) * O + o_lo) * M;
+        for (int idx = threadIdx.x; idx < nO * KT; idx += DPQ_THREADS) {
+          const int kk = idx & (KT - 1), oo = idx >> 3;
+          const long long k = k0 + kk;
+          float2 v = make_float2(0.f, 0.f);
+          if (bok && k < k_hi) v = __ldg(ysrc + (size_t)oo * M + k);
+          Ys[((size_t)bb * nOmax + oo) * KTP + kk] = v;
+        }
       }
       if (b0 == 0) {
         for (int idx = threadIdx.x; idx < DPQ_THREADS * KT; idx += DPQ_THREADS) {
-          const int kk = idx % KT, pr = idx / KT;
+          const int kk = idx & (KT - 1), pr = idx >> 3;
           const long long qq = min(q0 + pr, npairs - 1);
           const long long k = min(k0 + kk, M - 1);
           Rs[pr * KTP + kk] = __ldg(R + (size_t)qq * M + k);
@@ -389,21 +396,19 @@ rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY,
   }
 }
 
+// one thread per (pair, monomial): coalesced over the 2T partials of a pair, fixed-order sum over the k splits;
+// dP / dQ are zero-filled beforehand so the unused (a+b+c >= order) entries read 0 like autograd's
 __global__ void dpq_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dP, float* __restrict__ dQ,
                                   int KS, long long npairs, int op, int oq, int TPN, int TQN, MonoOffsets offs) {
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= npairs) return;
-  const int op3 = op * op * op, oq3 = oq * oq * oq;
-  float* p = dP + (size_t)q * op3;
-  float* r = dQ + (size_t)q * oq3;
-  for (int e = 0; e < op3; ++e) p[e] = 0.f;
-  for (int e = 0; e < oq3; ++e) r[e] = 0.f;
-  for (int t = 0; t < TPN + TQN; ++t) {
-    double s = 0.0;
-    for (int ks = 0; ks < KS; ++ks) s += (double)partial[((size_t)ks * npairs + q) * (TPN + TQN) + t];
-    if (t < TPN) p[offs.p[t]] = (float)s;
-    else r[offs.q[t - TPN]] = (float)s;
-  }
+  const int TT = TPN + TQN;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npairs * TT) return;
+  const long long q = idx / TT;
+  const int t = (int)(idx - q * TT);
+  double s = 0.0;
+  for (int ks = 0; ks < KS; ++ks) s += (double)__ldg(partial + (size_t)ks * npairs * TT + idx);
+  if (t < TPN) dP[(size_t)q * (op * op * op) + offs.p[t]] = (float)s;
+  else dQ[(size_t)q * (oq * oq * oq) + offs.q[t - TPN]] = (float)s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -549,9 +554,12 @@ static int launch_dpq(const float2* X, const float2* dY, const float* R, const f
   }
   PDEPHI_LAUNCH_CHECK("rational_dpq_kernel");
   const long long npairs = (long long)O * I;
+  PDEPHI_CUDA(cudaMemsetAsync(dP, 0, (size_t)npairs * OP * OP * OP * sizeof(float), st));
+  PDEPHI_CUDA(cudaMemsetAsync(dQ, 0, (size_t)npairs * OQ * OQ * OQ * sizeof(float), st));
   {
     ProfScope ps(K_DPQ_REDUCE, st);
-    dpq_reduce_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, st>>>(partial, dP, dQ, KS, npairs, OP, OQ, TPN, TQN, offs);
+    const long long n = npairs * (TPN + TQN);
+    dpq_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, dP, dQ, KS, npairs, OP, OQ, TPN, TQN, offs);
   }
   PDEPHI_LAUNCH_CHECK("dpq_reduce_kernel");
   return PDEPHI_OK;

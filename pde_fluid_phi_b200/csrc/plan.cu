@@ -25,7 +25,8 @@ static const char* const kKernelNames[K_COUNT] = {
     "analysis_zy_tc_kernel", "synthesis_zy_tc_kernel", "rational_mix_kernel", "mix_from_R_kernel",
     "projection_stats_kernel", "projection_bwd_kernel", "rational_dpq_kernel", "dpq_reduce_kernel",
     "complex_mix_kernel", "complex_mix_kernel(transposed)", "complex_dw_kernel", "pointwise_linear_kernel",
-    "pointwise_wgrad_kernel", "block_tail_fwd_kernel", "block_tail_bwd_kernel"};
+    "pointwise_wgrad_kernel", "block_tail_fwd_kernel", "block_tail_bwd_kernel", "analysis_x_tc_kernel",
+    "synthesis_x_tc_kernel", "scale_modes_kernel"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 static std::atomic<long long> g_launches[K_COUNT];
 static std::atomic<bool> g_prof_on{false};
@@ -147,6 +148,8 @@ extern "C" int pdephi_plan_create_slab(pdephi_plan_t* out, int device, int Nx, i
   {
     int rc = tc_plan_init(p);
     if (rc) return rc;
+    rc = xtc_plan_init(p);
+    if (rc) return rc;
   }
   PDEPHI_CUDA(cudaDeviceSynchronize());  // plan creation is the one synchronous call
   PDEPHI_CUDA(cudaSetDevice(cur));
@@ -159,6 +162,7 @@ extern "C" int pdephi_plan_destroy(pdephi_plan_t h) {
   Plan* p = (Plan*)h;
   if (p->arena) cudaFree(p->arena);
   tc_plan_destroy(p);
+  xtc_plan_destroy(p);
   delete p;
   return PDEPHI_OK;
 }
@@ -166,8 +170,10 @@ extern "C" int pdephi_plan_destroy(pdephi_plan_t h) {
 extern "C" size_t pdephi_plan_workspace_bytes(pdephi_plan_t h, long long BC) {
   if (!h || BC <= 0) return 0;
   const Plan* p = (const Plan*)h;
-  // intermediate between the fused (z,y) stage and the x stage: [BC, Nx, my, mzh] complex
-  return align_up((size_t)BC * p->Nx * p->my * p->mzh * sizeof(float2), 256);
+  // intermediate between the fused (z,y) stage and the x stage: [BC, Nx, my, mzh] complex, followed by a
+  // [BC, mx, my, mzh] complex scratch for the projected modes of the tensor-core synthesis x stage
+  return align_up((size_t)BC * p->Nx * p->my * p->mzh * sizeof(float2), 1024) +
+         align_up((size_t)BC * p->mx * p->my * p->mzh * sizeof(float2), 1024);
 }
 
 extern "C" int pdephi_profile_enable(int on) {

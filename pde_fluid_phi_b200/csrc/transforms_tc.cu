@@ -475,6 +475,11 @@ void tc_plan_destroy(Plan* p) {
 int xstage_analysis(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st);
 int xstage_synthesis(const Plan* p, const float2* Z, float2* ws, const float* mode_scale, const float* row_scale,
                      long long rs_stride, long long BC, cudaStream_t st);
+bool xstage_analysis_tc_ok(const Plan* p);
+bool xstage_synthesis_tc_ok(const Plan* p);
+int xstage_analysis_tc(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st);
+int xstage_synthesis_tc(const Plan* p, const float2* Z, float2* ws, float2* scratch, const float* mode_scale,
+                        const float* row_scale, long long rs_stride, long long BC, cudaStream_t st);
 
 int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws, cudaStream_t st) {
   const size_t planes = (size_t)BC * p->Nx;
@@ -500,6 +505,7 @@ int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int dire
     k<<<grid, tc::A_THREADS, smem, st>>>(tmap, ws, p->tc_b1[direction], p->tc_a2, (int)planes, NKB, p->my, p->mzh);
   }
   PDEPHI_LAUNCH_CHECK("analysis_zy_tc_kernel");
+  if (xstage_analysis_tc_ok(p)) return xstage_analysis_tc(p, ws, X, BC, st);
   return xstage_analysis(p, ws, X, BC, st);
 }
 
@@ -508,7 +514,14 @@ int synthesis_tc(const Plan* p, const float2* Z, float* out, const float* add0, 
                  float2* ws, cudaStream_t st) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(out) || !al16(add0) || !al16(add1)) return fail(PDEPHI_ERR_INVALID, "synthesis_tc: buffers must be 16-byte aligned");
-  int rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
+  int rc;
+  if (xstage_synthesis_tc_ok(p)) {
+    float2* scratch = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) +
+                                                align_up((size_t)BC * p->Nx * p->my * p->mzh * sizeof(float2), 1024));
+    rc = xstage_synthesis_tc(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st);
+  } else {
+    rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
+  }
   if (rc) return rc;
   const size_t planes = (size_t)BC * p->Nx;
   if (planes > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis_tc: too many planes");

@@ -143,7 +143,9 @@ def test_transfer_function_is_bit_identical(modes, order):
 SHAPES = [((16, 16, 16), (8, 8, 8)), ((16, 12, 20), (6, 4, 8)), ((9, 7, 11), (5, 3, 6)), ((8, 8, 8), (8, 8, 8)),
           ((32, 32, 32), (8, 8, 8)), ((64, 64, 64), (16, 16, 16)), ((16, 16, 1), (8, 8, 1)), ((24, 40, 36), (12, 10, 14)),
           # tensor-core shapes (Ny = 128, Nz in {64, 128}); the last one runs more planes than SMs
-          ((2, 128, 128), (2, 32, 32)), ((4, 128, 64), (4, 16, 24)), ((5, 128, 128), (3, 20, 38)), ((80, 128, 128), (8, 32, 32))]
+          ((2, 128, 128), (2, 32, 32)), ((4, 128, 64), (4, 16, 24)), ((5, 128, 128), (3, 20, 38)), ((80, 128, 128), (8, 32, 32)),
+          # tensor-core x stage as well (Nx % 32 == 0 for analysis, Nx == 128 for synthesis, even my*mzh)
+          ((128, 128, 128), (32, 32, 32)), ((64, 128, 64), (16, 16, 24)), ((32, 128, 128), (5, 7, 9)), ((128, 128, 64), (9, 6, 10))]
 
 
 @pytest.mark.parametrize("grid,modes", SHAPES)
