@@ -253,43 +253,99 @@ mix_from_R_kernel(const float2* __restrict__ dY, float2* __restrict__ dX, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// dP / dQ: thread = one (o,i) pair with its 2T accumulators in registers, looping over a k range;
-// X / dY / R / Q+eps / monomial tiles staged through shared memory.  Stage 1 writes per-k-split
-// partials, stage 2 sums them in fixed order and scatters into the [O,I,ord^3] gradients.
-//   dR[o,i,k] = sum_b Re(conj(X[b,i,k]) dY[b,o,k]);  g = dR/Qe;  dP_t += g mono_t;  dQ_t += -g R mono_t
+// dP / dQ in two phases (both deterministic, fixed-order sums):
+//   phase A  G[o,i,k] = dR / Qe,  dR[o,i,k] = sum_b Re(conj(X[b,i,k]) dY[b,o,k])      (thread = mode k, streaming)
+//   phase B  dP[o,i,t] = sum_k G mono_t(k),   dQ[o,i,t] = sum_k (-G R) mono_t(k)        (thread = (o,i) pair)
+// Phase B keeps the 2T accumulators of a pair in registers, stages [256 pairs x KT] tiles of G and R and the
+// monomial tile through shared memory, writes per-k-split partials; dpq_reduce_kernel sums them in fixed order.
 // ---------------------------------------------------------------------------------------------
+constexpr int GO = 4;   // output channels per CTA of phase A
+constexpr int GI = 2;   // input channels per inner step
+template <bool SINGLE>  // SINGLE: B <= BT, the dY values of the CTA's output channels stay in registers
+__global__ void __launch_bounds__(MIX_THREADS, 4)
+rational_g_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, const float* __restrict__ Qe,
+                  float* __restrict__ G, int B, int I, int O, long long M) {
+  const long long k = (long long)blockIdx.x * MIX_THREADS + threadIdx.x;
+  const long long kc = k < M ? k : M - 1;
+  const int o0 = blockIdx.y * GO;
+  float2 y[GO][BT];
+  if (SINGLE) {
+#pragma unroll
+    for (int a = 0; a < GO; ++a)
+#pragma unroll
+      for (int j = 0; j < BT; ++j)
+        y[a][j] = (j < B) ? __ldg(dY + ((size_t)j * O + min(o0 + a, O - 1)) * M + kc) : make_float2(0.f, 0.f);
+  }
+  const size_t iM = (size_t)I * M;
+  const float2* xk = X + kc;                            // + (b*I + i)*M
+  const size_t orow = (size_t)o0 * iM + (size_t)k;      // G / Qe index of (o0, i=0, k)
+#pragma unroll 2
+  for (int i0 = 0; i0 < I; i0 += GI) {
+    float dR[GO][GI];
+#pragma unroll
+    for (int a = 0; a < GO; ++a)
+#pragma unroll
+      for (int c = 0; c < GI; ++c) dR[a][c] = 0.f;
+    for (int b0 = 0; b0 < B; b0 += BT) {
+      if (!SINGLE) {
+#pragma unroll
+        for (int a = 0; a < GO; ++a)
+#pragma unroll
+          for (int j = 0; j < BT; ++j)
+            y[a][j] = (b0 + j < B) ? __ldg(dY + ((size_t)(b0 + j) * O + min(o0 + a, O - 1)) * M + kc) : make_float2(0.f, 0.f);
+      }
+      float2 xv[GI][BT];
+#pragma unroll
+      for (int c = 0; c < GI; ++c) {
+        const float2* xi = xk + (size_t)min(i0 + c, I - 1) * M + (size_t)b0 * iM;
+#pragma unroll
+        for (int j = 0; j < BT; ++j)   // entries beyond B multiply a zero dY: clamp the address, skip the predicate
+          xv[c][j] = __ldg(xi + (size_t)min(j, B - 1 - b0) * iM);
+      }
+#pragma unroll
+      for (int a = 0; a < GO; ++a)
+#pragma unroll
+        for (int c = 0; c < GI; ++c)
+#pragma unroll
+          for (int j = 0; j < BT; ++j) {
+            dR[a][c] = fmaf(xv[c][j].x, y[a][j].x, dR[a][c]);
+            dR[a][c] = fmaf(xv[c][j].y, y[a][j].y, dR[a][c]);
+          }
+      if (SINGLE) break;
+    }
+    if (k < M) {
+#pragma unroll
+      for (int a = 0; a < GO; ++a)
+#pragma unroll
+        for (int c = 0; c < GI; ++c)
+          if (o0 + a < O && i0 + c < I) {
+            const size_t ri = orow + (size_t)a * iM + (size_t)(i0 + c) * M;
+            G[ri] = __fdiv_rn(dR[a][c], __ldg(Qe + ri));
+          }
+    }
+  }
+}
+
 constexpr int DPQ_THREADS = 256;
-constexpr int KT = 8;   // (staging index math assumes KT == 8)
+constexpr int KT = 16;   // modes per staged tile (staging index math assumes a power of two)
 constexpr int KTP = KT + 1;
 
 template <int OP, int OQ>
-__global__ void __launch_bounds__(DPQ_THREADS)
-rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, const float* __restrict__ R,
-                    const float* __restrict__ Qe, const float* __restrict__ monoP, const float* __restrict__ monoQ,
-                    float* __restrict__ partial, int B, int I, int O, long long M, long long kchunk, int nOmax) {
+__global__ void __launch_bounds__(DPQ_THREADS, 2)
+rational_dpq_kernel(const float* __restrict__ G, const float* __restrict__ R, const float* __restrict__ monoP,
+                    const float* __restrict__ monoQ, float* __restrict__ partial, long long npairs, long long M,
+                    long long kchunk) {
   constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
   constexpr int TP4 = Tri<OP>::TP4, TQ4 = Tri<OQ>::TP4;
   constexpr bool SAME = (OP == OQ);
-  extern __shared__ __align__(16) float smem[];
-  float2* Xs = reinterpret_cast<float2*>(smem);                 // [BT][I][KTP]
-  float2* Ys = Xs + (size_t)BT * I * KTP;                        // [BT][nOmax][KTP]
-  size_t f2 = (size_t)BT * I * KTP + (size_t)BT * nOmax * KTP;
-  f2 += (f2 & 1);                                                // keep the float4-read monomial tiles 16-byte aligned
-  float* Rs = reinterpret_cast<float*>(Xs + f2);                 // [256][KTP]
-  float* Qs = Rs + DPQ_THREADS * KTP;                            // [256][KTP]
-  float* mPs = Qs + DPQ_THREADS * KTP;                           // [KT][TP4]   (16-byte aligned: see host)
-  float* mQs = mPs + KT * TP4;                                   // [KT][TQ4]
+  __shared__ __align__(16) float Gs[DPQ_THREADS * KTP];
+  __shared__ __align__(16) float Rs[DPQ_THREADS * KTP];
+  __shared__ __align__(16) float mPs[KT * TP4];
+  __shared__ __align__(16) float mQs[SAME ? 4 : KT * TQ4];
 
-  const long long npairs = (long long)O * I;
   const long long q0 = (long long)blockIdx.x * DPQ_THREADS;
   const long long qraw = q0 + threadIdx.x;
   const bool valid = qraw < npairs;
-  const long long q = valid ? qraw : npairs - 1;
-  const int o = (int)(q / I), i = (int)(q % I);
-  const int o_lo = (int)(q0 / I);
-  const int o_hi = (int)min((long long)O - 1, (q0 + DPQ_THREADS - 1) / I);
-  const int nO = o_hi - o_lo + 1;
-
   float ap[TPN], aq[TQN];
 #pragma unroll
   for (int t = 0; t < TPN; ++t) ap[t] = 0.f;
@@ -299,96 +355,67 @@ rational_dpq_kernel(const float2* __restrict__ X, const float2* __restrict__ dY,
   const long long k_lo = (long long)blockIdx.y * kchunk;
   const long long k_hi = min(M, k_lo + kchunk);
   for (long long k0 = k_lo; k0 < k_hi; k0 += KT) {
-    float dR[KT];
+    __syncthreads();
+    {
+      float gv[KT], rv[KT];
 #pragma unroll
-    for (int kk = 0; kk < KT; ++kk) dR[kk] = 0.f;
-    for (int b0 = 0; b0 < B; b0 += BT) {
-      __syncthreads();
-      // (no runtime divisions in the staging loops: KT is a power of two, the batch entry is an explicit loop)
-#pragma unroll
-      for (int bb = 0; bb < BT; ++bb) {
-        const bool bok = b0 + bb < B;
-        const float2* xsrc = X + (size_t)(bok ? b0 + bb : 0) * I * M;
-        for (int idx = threadIdx.x; idx < I * KT; idx += DPQ_THREADS) {
-          const int kk = idx & (KT - 1), ii = idx >> 3;
-          const long long k = k0 + kk;
-          float2 v = make_float2(0.f, 0.f);
-          if (bok && k < k_hi) v = __ldg(xsrc + (size_t)ii * M + k);
-          Xs[((size_t)bb * I + ii) * KTP + kk] = v;
-        }
-        const float2* ysrc = dY + ((size_t)(bok ? b0 + bb : 0) * O + o_lo) * M;
-        for (int idx = threadIdx.x; idx < nO * KT; idx += DPQ_THREADS) {
-          const int kk = idx & (KT - 1), oo = idx >> 3;
-          const long long k = k0 + kk;
-          float2 v = make_float2(0.f, 0.f);
-          if (bok && k < k_hi) v = __ldg(ysrc + (size_t)oo * M + k);
-          Ys[((size_t)bb * nOmax + oo) * KTP + kk] = v;
-        }
+      for (int j = 0; j < KT; ++j) {                 // DPQ_THREADS*KT elements, KT per thread, all loads first
+        const int idx = threadIdx.x + j * DPQ_THREADS;
+        const int kk = idx & (KT - 1), pr = idx / KT;
+        const long long qq = min(q0 + pr, npairs - 1);
+        const long long k = k0 + kk;
+        const bool ok = k < k_hi;
+        gv[j] = ok ? __ldg(G + (size_t)qq * M + k) : 0.f;   // 0 beyond the chunk: contributes nothing
+        rv[j] = ok ? __ldg(R + (size_t)qq * M + k) : 0.f;
       }
-      if (b0 == 0) {
-        for (int idx = threadIdx.x; idx < DPQ_THREADS * KT; idx += DPQ_THREADS) {
-          const int kk = idx & (KT - 1), pr = idx >> 3;
-          const long long qq = min(q0 + pr, npairs - 1);
-          const long long k = min(k0 + kk, M - 1);
-          Rs[pr * KTP + kk] = __ldg(R + (size_t)qq * M + k);
-          Qs[pr * KTP + kk] = __ldg(Qe + (size_t)qq * M + k);
-        }
-        for (int idx = threadIdx.x; idx < KT * (TP4 + (SAME ? 0 : TQ4)); idx += DPQ_THREADS) {
-          const bool isq = idx >= KT * TP4;
-          const int j = isq ? idx - KT * TP4 : idx;
-          const int T4 = isq ? TQ4 : TP4, TN = isq ? TQN : TPN;
-          const int kk = j / T4, t = j % T4;
-          const long long k = min(k0 + kk, M - 1);
-          const float v = (t < TN) ? __ldg((isq ? monoQ : monoP) + (size_t)t * M + k) : 0.f;
-          (isq ? mQs : mPs)[j] = v;
-        }
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        const int idx = threadIdx.x + j * DPQ_THREADS;
+        const int kk = idx & (KT - 1), pr = idx / KT;
+        Gs[pr * KTP + kk] = gv[j];
+        Rs[pr * KTP + kk] = rv[j];
       }
-      __syncthreads();
-#pragma unroll
-      for (int bb = 0; bb < BT; ++bb) {
-        const float2* xr = Xs + ((size_t)bb * I + i) * KTP;
-        const float2* yr = Ys + ((size_t)bb * nOmax + (o - o_lo)) * KTP;
-#pragma unroll
-        for (int kk = 0; kk < KT; ++kk) {
-          const float2 xv = xr[kk], yv = yr[kk];
-          dR[kk] = fmaf(xv.x, yv.x, dR[kk]);
-          dR[kk] = fmaf(xv.y, yv.y, dR[kk]);
-        }
+      for (int idx = threadIdx.x; idx < KT * (TP4 + (SAME ? 0 : TQ4)); idx += DPQ_THREADS) {
+        const bool isq = idx >= KT * TP4;
+        const int j = isq ? idx - KT * TP4 : idx;
+        const int T4 = isq ? TQ4 : TP4, TN = isq ? TQN : TPN;
+        const int kk = j / T4, t = j % T4;
+        const long long k = min(k0 + kk, M - 1);
+        const float v = (t < TN) ? __ldg((isq ? monoQ : monoP) + (size_t)t * M + k) : 0.f;
+        (isq ? mQs : mPs)[j] = v;
       }
     }
+    __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk) {
-      if (k0 + kk < k_hi) {
-        const float rr = Rs[threadIdx.x * KTP + kk], qe = Qs[threadIdx.x * KTP + kk];
-        const float g = __fdiv_rn(dR[kk], qe);
-        const float h = -g * rr;
-        const float4* p4 = reinterpret_cast<const float4*>(mPs + kk * TP4);
-        const float4* q4 = reinterpret_cast<const float4*>((SAME ? mPs : mQs) + kk * (SAME ? TP4 : TQ4));
+      const float g = Gs[threadIdx.x * KTP + kk];
+      const float h = -g * Rs[threadIdx.x * KTP + kk];
+      const float4* p4 = reinterpret_cast<const float4*>(mPs + kk * TP4);
 #pragma unroll
-        for (int t4 = 0; t4 < TP4 / 4; ++t4) {
-          const float4 m = p4[t4];
+      for (int t4 = 0; t4 < TP4 / 4; ++t4) {
+        const float4 m = p4[t4];
+        const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (4 * t4 + e < TPN) ap[4 * t4 + e] = fmaf(g, mm[e], ap[4 * t4 + e]);
+          if (SAME && 4 * t4 + e < TQN) aq[4 * t4 + e] = fmaf(h, mm[e], aq[4 * t4 + e]);
+        }
+      }
+      if (!SAME) {
+        const float4* q4 = reinterpret_cast<const float4*>(mQs + kk * TQ4);
+#pragma unroll
+        for (int t4 = 0; t4 < TQ4 / 4; ++t4) {
+          const float4 m = q4[t4];
           const float mm[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (4 * t4 + e < TPN) ap[4 * t4 + e] = fmaf(g, mm[e], ap[4 * t4 + e]);
-            if (SAME && 4 * t4 + e < TQN) aq[4 * t4 + e] = fmaf(h, mm[e], aq[4 * t4 + e]);
-          }
-        }
-        if (!SAME) {
-#pragma unroll
-          for (int t4 = 0; t4 < TQ4 / 4; ++t4) {
-            const float4 m = q4[t4];
-            const float mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (4 * t4 + e < TQN) aq[4 * t4 + e] = fmaf(h, mm[e], aq[4 * t4 + e]);
-          }
+          for (int e = 0; e < 4; ++e)
+            if (4 * t4 + e < TQN) aq[4 * t4 + e] = fmaf(h, mm[e], aq[4 * t4 + e]);
         }
       }
     }
   }
   if (valid) {
-    float* dst = partial + ((size_t)blockIdx.y * npairs + q) * (TPN + TQN);
+    float* dst = partial + ((size_t)blockIdx.y * npairs + qraw) * (TPN + TQN);
 #pragma unroll
     for (int t = 0; t < TPN; ++t) dst[t] = ap[t];
 #pragma unroll
@@ -518,7 +545,7 @@ static int launch_mix(const float2* in, float2* out, const float* P, const float
   return PDEPHI_OK;
 }
 
-static void dpq_geometry(int I, int O, long long M, int* pair_blocks, int* KS, long long* kchunk, int* nOmax) {
+static void dpq_geometry(int I, int O, long long M, int* pair_blocks, int* KS, long long* kchunk) {
   const long long npairs = (long long)O * I;
   *pair_blocks = (int)((npairs + DPQ_THREADS - 1) / DPQ_THREADS);
   long long ks = (6 * 148 + *pair_blocks - 1) / *pair_blocks;
@@ -529,31 +556,36 @@ static void dpq_geometry(int I, int O, long long M, int* pair_blocks, int* KS, l
   chunk = (chunk + KT - 1) / KT * KT;
   *KS = (int)((M + chunk - 1) / chunk);
   *kchunk = chunk;
-  *nOmax = (DPQ_THREADS - 1) / I + 2;
-  if (*nOmax > O) *nOmax = O;
+}
+static size_t dpq_partial_bytes(int op, int oq, int I, int O, long long M) {
+  int pair_blocks, KS;
+  long long kchunk;
+  dpq_geometry(I, O, M, &pair_blocks, &KS, &kchunk);
+  return align_up((size_t)KS * O * I * (tri(op) + tri(oq)) * sizeof(float), 256);
 }
 
 template <int OP, int OQ>
 static int launch_dpq(const float2* X, const float2* dY, const float* R, const float* Qe, const float* monoP,
                       const float* monoQ, float* dP, float* dQ, int B, int I, int O, long long M, float* partial,
-                      const MonoOffsets& offs, cudaStream_t st) {
-  int pair_blocks, KS, nOmax;
+                      float* G, const MonoOffsets& offs, cudaStream_t st) {
+  int pair_blocks, KS;
   long long kchunk;
-  dpq_geometry(I, O, M, &pair_blocks, &KS, &kchunk, &nOmax);
+  dpq_geometry(I, O, M, &pair_blocks, &KS, &kchunk);
   constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
-  // float2 tiles (8-byte units) then float tiles; 2*DPQ_THREADS*KTP floats = even count keeps mPs 16-byte aligned
-  size_t f2 = (size_t)BT * I * KTP + (size_t)BT * nOmax * KTP;
-  if (f2 & 1) f2 += 1;
-  const size_t smem = f2 * sizeof(float2) + (2 * (size_t)DPQ_THREADS * KTP + KT * (Tri<OP>::TP4 + Tri<OQ>::TP4)) * sizeof(float);
-  auto k = rational_dpq_kernel<OP, OQ>;
-  if (smem > 200 * 1024) return fail(PDEPHI_ERR_UNSUPPORTED, "rational_mix_bwd: %d input channels exceed shared memory", I);
-  if (smem > 48 * 1024) PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long npairs = (long long)O * I;
+  if ((O + GO - 1) / GO > 65535) return fail(PDEPHI_ERR_UNSUPPORTED, "rational_mix_bwd: too many output channels");
+  {
+    dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (O + GO - 1) / GO);
+    ProfScope ps(K_RATIONAL_G, st);
+    if (B <= BT) rational_g_kernel<true><<<grid, MIX_THREADS, 0, st>>>(X, dY, Qe, G, B, I, O, M);
+    else rational_g_kernel<false><<<grid, MIX_THREADS, 0, st>>>(X, dY, Qe, G, B, I, O, M);
+  }
+  PDEPHI_LAUNCH_CHECK("rational_g_kernel");
   {
     ProfScope ps(K_RATIONAL_DPQ, st);
-    k<<<dim3(pair_blocks, KS), DPQ_THREADS, smem, st>>>(X, dY, R, Qe, monoP, monoQ, partial, B, I, O, M, kchunk, nOmax);
+    rational_dpq_kernel<OP, OQ><<<dim3(pair_blocks, KS), DPQ_THREADS, 0, st>>>(G, R, monoP, monoQ, partial, npairs, M, kchunk);
   }
   PDEPHI_LAUNCH_CHECK("rational_dpq_kernel");
-  const long long npairs = (long long)O * I;
   PDEPHI_CUDA(cudaMemsetAsync(dP, 0, (size_t)npairs * OP * OP * OP * sizeof(float), st));
   PDEPHI_CUDA(cudaMemsetAsync(dQ, 0, (size_t)npairs * OQ * OQ * OQ * sizeof(float), st));
   {
@@ -615,10 +647,8 @@ extern "C" int pdephi_projection_bwd(const float* dZ, const float* Y, const floa
 
 extern "C" size_t pdephi_rational_mix_bwd_workspace_bytes(int order_p, int order_q, int I, int O, long long M) {
   if (I <= 0 || O <= 0 || M <= 0 || order_p < 1 || order_q < 1) return 0;
-  int pair_blocks, KS, nOmax;
-  long long kchunk;
-  dpq_geometry(I, O, M, &pair_blocks, &KS, &kchunk, &nOmax);
-  return align_up((size_t)KS * O * I * (tri(order_p) + tri(order_q)) * sizeof(float), 256);
+  // per-k-split partials of dP/dQ followed by the G = dR/Qe matrix [O, I, M]
+  return dpq_partial_bytes(order_p, order_q, I, O, M) + align_up((size_t)O * I * M * sizeof(float), 256);
 }
 
 extern "C" int pdephi_rational_mix_bwd(const float* X, const float* dY, const float* R, const float* Qe,
@@ -641,10 +671,11 @@ extern "C" int pdephi_rational_mix_bwd(const float* X, const float* dY, const fl
   memset(&offs, 0, sizeof(offs));
   fill_offsets(order_p, offs.p);
   fill_offsets(order_q, offs.q);
+  float* Gbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + dpq_partial_bytes(order_p, order_q, I, O, M));
 #define CASE(a, b)                                                                                          \
   if (order_p == a && order_q == b)                                                                         \
     return launch_dpq<a, b>((const float2*)X, (const float2*)dY, R, Qe, monoP, monoQ, dP, dQ, B, I, O, M,    \
-                            (float*)workspace, offs, st);
+                            (float*)workspace, Gbuf, offs, st);
   ORDER_CASES
 #undef CASE
   return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) outside the supported range 2..4", order_p, order_q);

@@ -26,7 +26,7 @@ static const char* const kKernelNames[K_COUNT] = {
     "projection_stats_kernel", "projection_bwd_kernel", "rational_dpq_kernel", "dpq_reduce_kernel",
     "complex_mix_kernel", "complex_mix_kernel(transposed)", "complex_dw_kernel", "pointwise_linear_kernel",
     "pointwise_wgrad_kernel", "block_tail_fwd_kernel", "block_tail_bwd_kernel", "analysis_x_tc_kernel",
-    "synthesis_x_tc_kernel", "scale_modes_kernel"};
+    "synthesis_x_tc_kernel", "scale_modes_kernel", "rational_g_kernel"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 static std::atomic<long long> g_launches[K_COUNT];
 static std::atomic<bool> g_prof_on{false};
