@@ -226,10 +226,13 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
 // ------------------------------------------------------------------------------------------------
 // synthesis kernel
 //   warp 0: MMA issuer + TMEM owner, warps 2..9: epilogue (TMEM quarter = warp % 4, column half = (warp-2)/4),
-//   warps 10..11: By builders.  12 warps so that the epilogue keeps ~64 KB of addend loads in flight per SM.
+//   warps 10..13: By builders.  The epilogue warps keep ~64 KB of addend loads in flight per SM; the builders
+//   issue all their loads of a plane before the first store (a serial load->store loop was the kernel's bound).
 // ------------------------------------------------------------------------------------------------
-constexpr int S_THREADS = 384;
 constexpr int S_EPI_WARPS = 8;
+constexpr int S_BUILD_WARPS = 4;
+constexpr int S_BUILD_NE = 5;    // elements of U per builder thread: my*mzh <= 32*20 = 640 = 128*5
+constexpr int S_THREADS = 32 * (2 + S_EPI_WARPS + S_BUILD_WARPS);
 struct SSmem {
   uint32_t ay, bz, by[2], stage, bars, tmem_slot, total;
 };
@@ -275,7 +278,7 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
     for (int i = threadIdx.x; i < 2 * 2 * ROWS_B * 128 / 16; i += S_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (threadIdx.x == 0) {
-    mbar_init(bar(SB_BYFULL0), 64); mbar_init(bar(SB_BYFULL1), 64);
+    mbar_init(bar(SB_BYFULL0), 32 * S_BUILD_WARPS); mbar_init(bar(SB_BYFULL1), 32 * S_BUILD_WARPS);
     mbar_init(bar(SB_BYEMPTY0), 1); mbar_init(bar(SB_BYEMPTY1), 1);
     mbar_init(bar(SB_DVFULL), 1);
     mbar_init(bar(SB_OUTFULL0), 1); mbar_init(bar(SB_OUTFULL1), 1);
@@ -320,22 +323,38 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
       }
     }
   } else if (warp >= 2 + S_EPI_WARPS) {
-    // ===== By builders (64 threads): U[ky][kz] -> [[re, im], [-im, re]] operand tile =====
+    // ===== By builders (128 threads): U[ky][kz] -> [[re, im], [-im, re]] operand tile =====
     const int bt = (warp - 2 - S_EPI_WARPS) * 32 + lane;
+    const int nel = my * mzh;
+    // the element -> operand-offset map is the same for every plane: compute it once
+    uint32_t o_re[S_BUILD_NE], o_im[S_BUILD_NE], o_nim[S_BUILD_NE], o_re2[S_BUILD_NE];
+#pragma unroll
+    for (int j = 0; j < S_BUILD_NE; ++j) {
+      const int idx = min(bt + j * 32 * S_BUILD_WARPS, nel - 1);
+      const int ky = idx / mzh, kz = idx - ky * mzh;
+      o_re[j] = swz_off(ROWS_B, kz, ky);
+      o_im[j] = swz_off(ROWS_B, mzh + kz, ky);
+      o_nim[j] = swz_off(ROWS_B, kz, SIN0 + ky);
+      o_re2[j] = swz_off(ROWS_B, mzh + kz, SIN0 + ky);
+    }
     int it = 0;
     for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
       const int b = it & 1;
+      const float2* up = U + (size_t)p * nel;
+      float2 u[S_BUILD_NE];
+#pragma unroll
+      for (int j = 0; j < S_BUILD_NE; ++j) u[j] = __ldg(up + min(bt + j * 32 * S_BUILD_WARPS, nel - 1));   // before the wait
       mbar_wait(bar(SB_BYEMPTY0 + b), ((it >> 1) & 1) ^ 1);
-      const float2* up = U + (size_t)p * my * mzh;
       uint8_t* by = sm + L.by[b];
-      for (int idx = bt; idx < my * mzh; idx += 64) {
-        const int ky = idx / mzh, kz = idx - ky * mzh;
-        const float2 u = __ldg(up + idx);
-        const float re = to_tf32(u.x), im = to_tf32(u.y);
-        *reinterpret_cast<float*>(by + swz_off(ROWS_B, kz, ky)) = re;
-        *reinterpret_cast<float*>(by + swz_off(ROWS_B, mzh + kz, ky)) = im;
-        *reinterpret_cast<float*>(by + swz_off(ROWS_B, kz, SIN0 + ky)) = -im;
-        *reinterpret_cast<float*>(by + swz_off(ROWS_B, mzh + kz, SIN0 + ky)) = re;
+#pragma unroll
+      for (int j = 0; j < S_BUILD_NE; ++j) {
+        if (bt + j * 32 * S_BUILD_WARPS < nel) {
+          const float re = to_tf32(u[j].x), im = to_tf32(u[j].y);
+          *reinterpret_cast<float*>(by + o_re[j]) = re;
+          *reinterpret_cast<float*>(by + o_im[j]) = im;
+          *reinterpret_cast<float*>(by + o_nim[j]) = -im;
+          *reinterpret_cast<float*>(by + o_re2[j]) = re;
+        }
       }
       fence_proxy_async();
       mbar_arrive(bar(SB_BYFULL0 + b));
