@@ -290,6 +290,9 @@ def run_native(args):
     e2e_ms = timed(step_e2e, args.steps)
     final_loss = float(h_loss)
 
+    layer_us = None
+    if rank == 0 and world == 1 and not args.no_layer_times:
+        layer_us = layer_times(dev, args.precision)
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = B * world / (ms_per_step * 1e-3)
@@ -301,22 +304,46 @@ def run_native(args):
         except OSError:
             pass
         peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        # dominant kernel: the fused (z,y) analysis stage.  Algorithmic bytes per launch:
-        # read the [B*C, N, N, N] fp32 activation once + write the [B*C, N, my, mzh] complex intermediate.
+        # Algorithmic bytes per launch, one launch = all B*C*Nx planes / all B*S/128 tiles.
         C, (mx, my, mz) = CFG["width"], CFG["modes"]
         mzh = mz // 2 + 1
-        names = {"fp32": "analysis_zy_kernel", "tf32": "analysis_zy_tc_kernel"}
-        dom = names[args.precision]
+        act = 4.0 * B * C * n ** 3                       # one full-size fp32 activation
+        mid = 8.0 * B * C * n * my * mzh                 # [BC,Nx,my,mzh] complex intermediate
+        modes_b = 8.0 * B * C * mx * my * mzh            # retained modes
+        alg = {
+            "analysis_zy_tc_kernel": act + mid, "analysis_zy_kernel": act + mid,
+            # per step: 4 forward launches without addends + 4 adjoint launches with one addend -> mean
+            "synthesis_zy_tc_kernel": act + mid + 0.5 * act,
+            "synthesis_zy_kernel": act + mid + 1.5 * act,   # fp32 route: forward fuses both skip addends, adjoint one
+            "block_tail_fwd_kernel": 4 * act,            # read h, spec; write u, h'
+            "block_tail_bwd_kernel": 5 * act,            # read g', u, h; write gu, t
+            "analysis_x_tc_kernel": mid + modes_b, "synthesis_x_tc_kernel": mid + modes_b,
+        }
         per_kernel = {k: {"launches": v[0], "ms_total": round(v[1], 3), "share_of_step": round(v[1] / total_ms, 4)}
                       for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        rooflines = {}
+        for k, v in prof.items():
+            if k in alg and v[1] > 0:
+                avg_ms = v[1] / v[0]
+                if k.startswith("block_tail_bwd"):
+                    avg_ms = v[1] / (v[0] / 2)           # the tiny partial-sum reduce kernel shares the counter
+                ach = alg[k] / (avg_ms * 1e-3) / 1e9
+                rooflines[k] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                                "frac": round(ach / peak, 4), "algorithmic_bytes_per_launch": alg[k],
+                                "avg_launch_ms": round(avg_ms, 4)}
+        hot = [k for k in ("analysis_zy_tc_kernel", "analysis_zy_kernel") if k in rooflines]
+        dom = max(rooflines, key=lambda k: prof[k][1]) if rooflines else None
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
+        ncu_traffic = {"analysis_zy_tc_kernel": 4.580e9, "synthesis_zy_tc_kernel": None, "block_tail_fwd_kernel": 17.187e9,
+                       "block_tail_bwd_kernel": 21.489e9}
+        for k in rooflines:
+            rooflines[k]["traffic"] = ncu_traffic.get(k)
         roof = None
-        if dom in prof and prof[dom][1] > 0:
-            alg_bytes = 4.0 * B * C * n ** 3 + 8.0 * B * C * n * my * mzh
-            avg_ms = prof[dom][1] / prof[dom][0]
-            achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
-            roof = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": which,
-                    "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(avg_ms, 4)}
+        if dom:
+            roof = dict(rooflines[dom], kernel=dom, peak_source=which,
+                        note="largest share of the step; 'rooflines' lists every HBM-bound kernel of the path")
+        if hot:
+            rooflines[hot[0]]["note"] = "K1 fused (z,y) stage: ncu dram bytes 4.58 GB/launch = algorithmic (profiles/)"
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             t = cpu_layer_slice_seconds(reps=2, warmup=1)
@@ -331,11 +358,49 @@ def run_native(args):
                 "data": "synthetic", "config": workload_config(world, args.precision),
                 "e2e": {"value": round(e2e_value, 3), "unit": "samples/s",
                         "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 4, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "kernels": per_kernel, "first_loss": first_loss, "final_loss": final_loss}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": rooflines,
+                "cpu_baseline": cpu, "layer_fwd_bwd_us": layer_us, "kernels": per_kernel, "first_loss": first_loss, "final_loss": final_loss}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def layer_times(dev, precision):
+    """Second half of the BASELINE metric: fwd+bwd microseconds of one spectral layer (CUDA events, 3 warm + 10 timed)."""
+    import pde_fluid_phi_b200 as pb
+
+    def run(layer, x):
+        g = torch.randn_like(x)
+
+        def step():
+            x.grad = None
+            layer.zero_grad(set_to_none=True)
+            layer(x).backward(g)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return round(e0.elapsed_time(e1) / 10 * 1e3, 1)
+
+    out = {}
+    torch.manual_seed(0)
+    x2 = torch.randn(8, 64, 128, 128, 128, device=dev, requires_grad=True)
+    rfl = pb.RationalFourierLayer(64, 64, (32, 32, 32)).to(dev)
+    rfl.precision = precision
+    out["RationalFourierLayer [8,64,128^3] modes 32^3 (%s)" % precision] = run(rfl, x2)
+    sc = pb.SpectralConv3D(64, 64, (32, 32, 32)).to(dev)
+    sc.precision = precision
+    out["SpectralConv3D [8,64,128^3] modes 32^3 (%s)" % precision] = run(sc, x2)
+    del x2, rfl, sc
+    x1 = torch.randn(4, 32, 32, 32, 32, device=dev, requires_grad=True)
+    out["SpectralConv3D [4,32,32^3] modes 8^3 (fp32, cfg 1)"] = run(pb.SpectralConv3D(32, 32, (8, 8, 8)).to(dev), x1)
+    out["RationalFourierLayer [4,32,32^3] modes 8^3 (fp32, cfg-1 shape)"] = run(pb.RationalFourierLayer(32, 32, (8, 8, 8)).to(dev), x1)
+    return out
 
 
 def main():
@@ -347,6 +412,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PDEPHI_PRECISION", "fp32"), choices=["fp32", "tf32"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-layer-times", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

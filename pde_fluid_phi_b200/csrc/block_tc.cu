@@ -20,7 +20,8 @@ constexpr int C = 64;            // channels (model width)
 constexpr int TS = 128;          // spatial points per tile
 constexpr int BOX = C * 128;     // bytes of one [64 rows][32 floats] box
 constexpr int TILE = 4 * BOX;    // 32 KB
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;    // 4 TMEM quarters x 4 channel groups: enough warps to hide LDS / MUFU latency
+constexpr int CPW = C / (EPI_WARPS / 4);   // channels per epilogue warp (16)
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 
 // MN-major TF32 operand (M or N contiguous).  32-bit MN-major operands exist only in the "128B swizzle with
@@ -47,9 +48,29 @@ __device__ __forceinline__ uint32_t tile_off(int r, int s) {
 __device__ __forceinline__ uint32_t tile_off_k(int r, int s) {
   return (uint32_t)((s >> 5) * BOX + r * 128 + (((((s & 31) >> 2) ^ (r & 7)) & 7) << 4) + (s & 3) * 4);
 }
-__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+// Exact (erf) GELU and its derivative from one exponential: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7,
+// i.e. fp32 rounding level) with e^{-x^2} = e^{-u^2/2} shared with the Gaussian density of the derivative.  The
+// epilogues are issue-bound, so ~14 instructions here instead of libm erff's ~25 matter.
+__device__ __forceinline__ void gelu_parts(float u, float& cdf, float& e) {
+  const float x = fabsf(u) * 0.70710678118654752f;
+  e = __expf(-0.5f * u * u);                                   // e^{-x^2}
+  const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * e;                    // 0.5 * erfc(|x|)
+  cdf = u >= 0.f ? 1.f - half_erfc : half_erfc;                // Phi(u) = 0.5 (1 + erf(u / sqrt 2))
+}
+__device__ __forceinline__ float gelu_f(float u) {
+  float cdf, e;
+  gelu_parts(u, cdf, e);
+  return u * cdf;
+}
 __device__ __forceinline__ float gelu_grad_f(float u) {
-  return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+  float cdf, e;
+  gelu_parts(u, cdf, e);
+  return fmaf(u * 0.3989422804014327f, e, cdf);
 }
 // W image: K-major [64 rows][K = 64], element (r, k) = TRANSPOSE ? W[k][r] : W[r][k], RN-rounded to TF32
 __device__ __forceinline__ void build_w_image(uint8_t* dst, const float* __restrict__ W, bool transpose, int tid, int nthr) {
@@ -138,16 +159,22 @@ block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_c
       }
     }
   } else {
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const float* bs = reinterpret_cast<const float*>(sm + L.bias);
+    float bsr[CPW];
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) bsr[j] = reinterpret_cast<const float*>(sm + L.bias)[part * CPW + j];
+    // element (channel row o = part*CPW + j, point 32q + lane): the swizzle term depends on o & 3 = j & 3 only
+    uint32_t xc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xc[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 3) ^ r) & 3) << 5) + (lane & 7) * 4);
     long long it = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = (int)(it % F_STAGES), d = (int)(it & 1);
       mbar_wait(bar(FB_DFULL + d), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem + d * C + lane_base + half * 32, v);
+      float v[CPW];
+      tmem_ld16(tmem + d * C + lane_base + part * CPW, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -155,16 +182,19 @@ block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_c
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       const uint8_t* th = sm + L.stage[s];
       const uint8_t* tsp = th + TILE;
-      const size_t g0 = ((size_t)b * C) * S + s0 + 32 * q + lane;
+      const size_t g0 = ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
+      float* up = u_out + g0;
+      float* hp = h_out + g0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int o = half * 32 + j;
-        const uint32_t off = tile_off(o, 32 * q + lane);
+      for (int j = 0; j < CPW; ++j) {
+        const uint32_t off = xc[j & 3] + j * 128;
         const float hv = *reinterpret_cast<const float*>(th + off);
         const float sv = *reinterpret_cast<const float*>(tsp + off);
-        const float u = (sv + (v[j] + bs[o])) + hv;
-        __stcs(u_out + g0 + (size_t)o * S, u);
-        h_out[g0 + (size_t)o * S] = gelu_f(u);
+        const float u = (sv + (v[j] + bsr[j])) + hv;
+        __stcs(up, u);
+        *hp = gelu_f(u);
+        up += S;
+        hp += S;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(FB_EMPTY + s));
@@ -190,8 +220,10 @@ __host__ __device__ inline BSmem bwd_smem() {
   s.total = o;
   return s;
 }
-enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2 * B_STAGES + 1, BB_TEMPTY = 2 * B_STAGES + 2,
-       BB_DWDONE = 2 * B_STAGES + 3 };
+// GUREADY / TFULL / TEMPTY are per parity of the tile index (two each): the compute warps run step 1 of tile i+1
+// before the epilogue of tile i, so two tiles are in flight between them and the MMA warp.
+enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2 * B_STAGES + 2, BB_TEMPTY = 2 * B_STAGES + 4,
+       BB_DWDONE = 2 * B_STAGES + 6 };
 
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_h,
@@ -208,20 +240,22 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
 
   build_w_image(sm + L.wt, Wc, true, threadIdx.x, THREADS);      // rows c, K = o : (Wc^T)
   if (threadIdx.x == 0) {
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), 1); mbar_init(bar(BB_EMPTY + i), 1 + EPI_WARPS); }
-    mbar_init(bar(BB_GUREADY), EPI_WARPS);
-    mbar_init(bar(BB_TFULL), 1);
-    mbar_init(bar(BB_TEMPTY), EPI_WARPS);
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), 1); mbar_init(bar(BB_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(BB_GUREADY + i), EPI_WARPS);
+      mbar_init(bar(BB_TFULL + i), 1);
+      mbar_init(bar(BB_TEMPTY + i), EPI_WARPS);
+    }
     mbar_init(bar(BB_DWDONE), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(base + L.tmem_slot, 128);
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, 256);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
-  const uint32_t tmem_t = tmem, tmem_dw = tmem + C;
+  const uint32_t tmem_t[2] = {tmem, tmem + C}, tmem_dw = tmem + 2 * C;
   const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 0) {
@@ -247,15 +281,17 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
       long long it = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int s = (int)(it % B_STAGES);
-        mbar_wait(bar(BB_GUREADY), (uint32_t)(it & 1));      // gu written in place over g' (implies TMA landed)
-        mbar_wait(bar(BB_TEMPTY), (uint32_t)((it & 1) ^ 1));
+        const int d = (int)(it & 1);
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        mbar_wait(bar(BB_GUREADY + d), ph);                  // gu written in place over g' (implies TMA landed)
+        mbar_wait(bar(BB_TEMPTY + d), ph ^ 1);
         tc_fence_after();
         const uint32_t gu = base + L.stage[s], hh = gu + TILE, guk = gu + 2 * TILE;
 #pragma unroll
         for (int k = 0; k < C / 8; ++k)
-          mma_ss(tmem_t, umma_desc_mn(gu + k * 1024, BOX), umma_desc(base + L.wt + (k >> 2) * BOX + (k & 3) * 32, 1024), id_t,
+          mma_ss(tmem_t[d], umma_desc_mn(gu + k * 1024, BOX), umma_desc(base + L.wt + (k >> 2) * BOX + (k & 3) * 32, 1024), id_t,
                  k ? 1u : 0u);
-        mma_commit(bar(BB_TFULL));
+        mma_commit(bar(BB_TFULL + d));
 #pragma unroll
         for (int k = 0; k < TS / 8; ++k)
           mma_ss(tmem_dw, umma_desc(guk + (k >> 2) * BOX + (k & 3) * 32, 1024), umma_desc(hh + (k >> 2) * BOX + (k & 3) * 32, 1024),
@@ -265,64 +301,72 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
       mma_commit(bar(BB_DWDONE));
     }
   } else {
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float db[32];
+    float db[CPW];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) db[j] = 0.f;
-    long long it = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int s = (int)(it % B_STAGES);
+    for (int j = 0; j < CPW; ++j) db[j] = 0.f;
+    // static shared-memory offsets of this thread's elements: row o = part*CPW + j, point 32q + lane.  The swizzle term
+    // depends on o & 3 (32-byte-atom layout) or o & 7 (16-byte-chunk layout), i.e. on j only (CPW is a multiple of 8).
+    uint32_t xc[4], xk[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xc[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 3) ^ r) & 3) << 5) + (lane & 7) * 4);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) xk[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 2) ^ r) & 7) << 4) + (lane & 3) * 4);
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long t = blockIdx.x + it * gridDim.x;
+      const int s = (int)(it % B_STAGES), d = (int)(it & 1);
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       uint8_t* tg = sm + L.stage[s];
       uint8_t* tgk = tg + 2 * TILE;
-      const size_t g0 = ((size_t)b * C) * S + s0 + 32 * q + lane;
-      // ---- step 1: gu = g' * gelu'(u) (this warp: channels [32*half, +32), points [32q, +32)).  gu replaces g' in place
-      //      (MN layout, operand of the Wc^T gu GEMM) and u in place (K layout, operand of the dWc GEMM), and goes to HBM ----
+      const size_t g0 = ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
+      // ---- step 1: gu = g' * gelu'(u) (this warp: channels [16*part, +16), points [32q, +32)).  gu replaces g' in place
+      //      (MN layout, operand of the Wc^T gu GEMM) and u in place (K layout, operand of the dWc GEMM), goes to HBM, and
+      //      stays in registers for the epilogue ----
       mbar_wait(bar(BB_FULL + s), (uint32_t)((it / B_STAGES) & 1));
+      float r[CPW];
+      float* gp = gu_out + g0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int o = half * 32 + j;
-        const uint32_t off = tile_off(o, 32 * q + lane), offk = tile_off_k(o, 32 * q + lane);
+      for (int j = 0; j < CPW; ++j) {
+        const uint32_t off = xc[j & 3] + j * 128, offk = xk[j & 7] + j * 128;
         const float gv = *reinterpret_cast<const float*>(tg + off);
         const float uv = *reinterpret_cast<const float*>(tgk + offk);
-        const float r = gv * gelu_grad_f(uv);
-        *reinterpret_cast<float*>(tg + off) = r;
-        *reinterpret_cast<float*>(tgk + offk) = to_tf32(r);
-        gu_out[g0 + (size_t)o * S] = r;
-        db[j] += r;
+        r[j] = gv * gelu_grad_f(uv);
+        *reinterpret_cast<float*>(tg + off) = r[j];
+        *reinterpret_cast<float*>(tgk + offk) = to_tf32(r[j]);
+        *gp = r[j];
+        gp += S;
+        db[j] += r[j];
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BB_GUREADY));
-      // ---- epilogue: t[c][s] = (Wc^T gu)[c][s] + gu[c][s] --------------------------------------------
-      mbar_wait(bar(BB_TFULL), (uint32_t)(it & 1));
+      if (lane == 0) mbar_arrive(bar(BB_GUREADY + d));
+      // ---- epilogue: t[c][s] = (Wc^T gu)[c][s] + gu[c][s] ----
+      mbar_wait(bar(BB_TFULL + d), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem_t + lane_base + half * 32, v);
+      float v[CPW];
+      tmem_ld16(tmem_t[d] + lane_base + part * CPW, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BB_TEMPTY));
+      if (lane == 0) mbar_arrive(bar(BB_TEMPTY + d));
+      float* tp = t_out + g0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = half * 32 + j;
-        const float r = *reinterpret_cast<const float*>(tg + tile_off(c, 32 * q + lane));
-        __stcs(t_out + g0 + (size_t)c * S, v[j] + r);
+      for (int j = 0; j < CPW; ++j) {
+        __stcs(tp, v[j] + r[j]);
+        tp += S;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BB_EMPTY + s));
     }
     // ---- per-CTA partials: dbias (registers -> warp shuffle -> 4 quarter-warps summed in order) and dW (TMEM) ----
     float* red = reinterpret_cast<float*>(sm + L.red);      // [4 quarters][64]
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < CPW; ++j) {
       float x = db[j];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-      if (lane == 0) red[q * C + half * 32 + j] = x;
+      if (lane == 0) red[q * C + part * CPW + j] = x;
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     float* pout = partial + (size_t)blockIdx.x * (C * C + C);
     if (warp == 2 && my_tiles >= 0) {
       for (int o = lane; o < C; o += 32) pout[C * C + o] = (red[o] + red[C + o]) + (red[2 * C + o] + red[3 * C + o]);
@@ -330,7 +374,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
     if (my_tiles > 0) {
       mbar_wait(bar(BB_DWDONE), 0);
       tc_fence_after();
-      if (half == 0) {                 // M = 64 accumulator: rows 16q..16q+15 live in lanes 0..15 of quarter q
+      if (part == 0) {                 // M = 64 accumulator: rows 16q..16q+15 live in lanes 0..15 of quarter q
         float w0[32], w1[32];
         tmem_ld32(tmem_dw + lane_base, w0);
         tmem_ld32(tmem_dw + lane_base + 32, w1);
@@ -341,14 +385,14 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
           for (int c = 0; c < 32; ++c) { row[c] = w0[c]; row[32 + c] = w1[c]; }
         }
       }
-    } else if (half == 0 && lane < 16) {
+    } else if (part == 0 && lane < 16) {
       float* row = pout + (size_t)(16 * q + lane) * C;
       for (int c = 0; c < C; ++c) row[c] = 0.f;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 128);
+  if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
 __global__ void block_tail_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db,

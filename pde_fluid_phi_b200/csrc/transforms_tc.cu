@@ -78,12 +78,13 @@ __host__ __device__ inline ASmem analysis_smem(int NKB) {
   s.a2 = o; o += 4 * M2 * 128;
   s.b2 = o; o += 4 * ROWS_B * 128;
   s.e = o; o += 10752;
-  s.bars = o; o += 64;
+  s.bars = o; o += 128;
   s.tmem_slot = o; o += 64;
   s.total = o;
   return s;
 }
-enum { AB_FULL0 = 0, AB_FULL1, AB_EMPTY0, AB_EMPTY1, AB_D1FULL, AB_B2FULL, AB_D2FULL, AB_D2EMPTY };
+enum { AB_FULL0 = 0, AB_FULL1, AB_EMPTY0, AB_EMPTY1, AB_D1FULL0, AB_D1FULL1, AB_D1EMPTY0, AB_D1EMPTY1, AB_B2FULL, AB_D2FULL,
+       AB_D2EMPTY };
 
 __global__ void __launch_bounds__(A_THREADS, 1)
 analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __restrict__ T2, const float* __restrict__ B1img,
@@ -111,17 +112,19 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
   if (threadIdx.x == 0) {
     mbar_init(bar(AB_FULL0), 1); mbar_init(bar(AB_FULL1), 1);
     mbar_init(bar(AB_EMPTY0), 1); mbar_init(bar(AB_EMPTY1), 1);
-    mbar_init(bar(AB_D1FULL), 1); mbar_init(bar(AB_B2FULL), 128);
+    mbar_init(bar(AB_D1FULL0), 1); mbar_init(bar(AB_D1FULL1), 1);
+    mbar_init(bar(AB_D1EMPTY0), 128); mbar_init(bar(AB_D1EMPTY1), 128);
+    mbar_init(bar(AB_B2FULL), 128);
     mbar_init(bar(AB_D2FULL), 1); mbar_init(bar(AB_D2EMPTY), 128);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(base + L.tmem_slot, 128);
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, 256);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
-  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + 64;
+  const uint32_t tmem_d1[2] = {tmem, tmem + 64}, tmem_d2 = tmem + 128;   // D1 double buffered: GEMM1 runs a plane ahead
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -139,18 +142,24 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t id1 = umma_idesc(128, N1), id2 = umma_idesc(M2, N2);
-      int it = 0;
-      for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
-        const int s = it & 1;
-        mbar_wait(bar(AB_FULL0 + s), (it >> 1) & 1);
+      const int n_my = blockIdx.x < planes ? (planes - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      auto gemm1 = [&](int i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(bar(AB_FULL0 + s), ph);
+        mbar_wait(bar(AB_D1EMPTY0 + s), ph ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < NKB; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            mma_ss(tmem_d1, umma_desc(base + L.a1[s] + kb * 16384 + k * 32, 1024),
+            mma_ss(tmem_d1[s], umma_desc(base + L.a1[s] + kb * 16384 + k * 32, 1024),
                    umma_desc(base + L.b1 + kb * ROWS_B * 128 + k * 32, 1024), id1, (kb | k) ? 1u : 0u);
         mma_commit(bar(AB_EMPTY0 + s));
-        mma_commit(bar(AB_D1FULL));
+        mma_commit(bar(AB_D1FULL0 + s));
+      };
+      if (n_my > 0) gemm1(0);
+      for (int it = 0; it < n_my; ++it) {
+        if (it + 1 < n_my) gemm1(it + 1);            // z stage of the next plane overlaps this plane's epilogues
         mbar_wait(bar(AB_B2FULL), it & 1);
         mbar_wait(bar(AB_D2EMPTY), (it & 1) ^ 1);
         tc_fence_after();
@@ -173,12 +182,14 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
     int it = 0;
     for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
       // ---- epi-1: D1 row y = 32q+lane -> B2[c][y] ------------------------------------------------
-      mbar_wait(bar(AB_D1FULL), it & 1);
+      mbar_wait(bar(AB_D1FULL0 + (it & 1)), (it >> 1) & 1);
       tc_fence_after();
       float v[40];
-      tmem_ld32(tmem_d1 + lane_base, v);
-      tmem_ld8(tmem_d1 + lane_base + 32, v + 32);
+      tmem_ld32(tmem_d1[it & 1] + lane_base, v);
+      tmem_ld8(tmem_d1[it & 1] + lane_base + 32, v + 32);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar(AB_D1EMPTY0 + (it & 1)));
       {
         uint8_t* b2 = sm + L.b2 + q * (ROWS_B * 128);   // k-block q holds y in [32q, 32q+32)
         const uint32_t kin = (uint32_t)(lane & 3) * 4;
@@ -220,7 +231,7 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
   // ---- teardown -----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 128);
+  if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
