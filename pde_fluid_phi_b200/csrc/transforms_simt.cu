@@ -19,10 +19,21 @@ constexpr int ZY_THREADS = 256;
 template <int G, bool VEC4>
 __global__ void __launch_bounds__(ZY_THREADS)
 analysis_zy_kernel(const float* __restrict__ x, float2* __restrict__ T2, const float2* __restrict__ az,
-                   const float2* __restrict__ ay, int Ny, int Nz, int my, int mzh, int YC, int ldx) {
+                   const float2* __restrict__ ay, int Ny, int Nz, int my, int mzh, int YC, int ldx, int tw_smem) {
   extern __shared__ __align__(16) float smem[];
   float2* T1s = reinterpret_cast<float2*>(smem);                         // [Ny][mzh]
   float* Xs = smem + ((2 * (size_t)Ny * mzh + 3) / 4) * 4;                // [YC][ldx]
+  // twiddle tables staged in shared memory when they fit (tw_smem): warp-wide broadcast LDS instead of LDG
+  const float2* azs = az;
+  const float2* ays = ay;
+  if (tw_smem) {
+    float2* a = reinterpret_cast<float2*>(Xs + (size_t)YC * ldx + ((size_t)YC * ldx & 1));
+    float2* b = a + (size_t)Nz * mzh;
+    for (int i = threadIdx.x; i < Nz * mzh; i += ZY_THREADS) a[i] = __ldg(az + i);
+    for (int i = threadIdx.x; i < Ny * my; i += ZY_THREADS) b[i] = __ldg(ay + i);
+    azs = a;
+    ays = b;
+  }
   const size_t plane = blockIdx.x;
   const float* xp = x + plane * (size_t)Ny * Nz;
   const int NG = (mzh + G - 1) / G;
@@ -60,10 +71,10 @@ analysis_zy_kernel(const float* __restrict__ x, float2* __restrict__ T2, const f
           const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
           for (int dz = 0; dz < 4; ++dz) {
-            const float2* trow = az + (size_t)(z + dz) * mzh;
+            const float2* trow = azs + (size_t)(z + dz) * mzh;
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-              const float2 tw = __ldg(trow + kzi[j]);
+              const float2 tw = trow[kzi[j]];
               acc[j].x = fmaf(xs[dz], tw.x, acc[j].x);
               acc[j].y = fmaf(xs[dz], tw.y, acc[j].y);
             }
@@ -72,10 +83,10 @@ analysis_zy_kernel(const float* __restrict__ x, float2* __restrict__ T2, const f
       } else {
         for (int z = 0; z < Nz; ++z) {
           const float xv = xr[z];
-          const float2* trow = az + (size_t)z * mzh;
+          const float2* trow = azs + (size_t)z * mzh;
 #pragma unroll
           for (int j = 0; j < G; ++j) {
-            const float2 tw = __ldg(trow + kzi[j]);
+            const float2 tw = trow[kzi[j]];
             acc[j].x = fmaf(xv, tw.x, acc[j].x);
             acc[j].y = fmaf(xv, tw.y, acc[j].y);
           }
@@ -92,7 +103,7 @@ analysis_zy_kernel(const float* __restrict__ x, float2* __restrict__ T2, const f
     const int ky = it / mzh, kz = it - ky * mzh;
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll 4
-    for (int y = 0; y < Ny; ++y) cfma(acc, __ldg(ay + (size_t)y * my + ky), T1s[(size_t)y * mzh + kz]);
+    for (int y = 0; y < Ny; ++y) cfma(acc, ays[(size_t)y * my + ky], T1s[(size_t)y * mzh + kz]);
     outp[it] = acc;
   }
 }
@@ -186,11 +197,21 @@ xstage_kernel(const float2* __restrict__ in, float2* __restrict__ out, const flo
 template <bool VEC4>
 __global__ void __launch_bounds__(ZY_THREADS)
 synthesis_zy_kernel(const float2* __restrict__ U, float* __restrict__ out, const float* __restrict__ add0,
-                    const float* __restrict__ add1, const float2* __restrict__ sy, const float2* __restrict__ sz,
-                    int Ny, int Nz, int my, int mzh) {
+                    const float* __restrict__ add1, const float2* __restrict__ sy_g, const float2* __restrict__ sz_g,
+                    int Ny, int Nz, int my, int mzh, int tw_smem) {
   extern __shared__ __align__(16) float smem[];
   float2* Us = reinterpret_cast<float2*>(smem);        // [my][mzh]
   float2* Vs = Us + (size_t)my * mzh;                  // [Ny][mzh]
+  const float2* sy = sy_g;
+  const float2* sz = sz_g;
+  if (tw_smem) {                                       // twiddles in shared memory (16-byte aligned for the float4 reads)
+    float2* a = Vs + (((size_t)Ny * mzh + (size_t)my * mzh + 1) & ~(size_t)1) - (size_t)my * mzh;
+    float2* b = a + (((size_t)mzh * Nz + 1) & ~(size_t)1);
+    for (int i = threadIdx.x; i < mzh * Nz; i += ZY_THREADS) a[i] = __ldg(sz_g + i);
+    for (int i = threadIdx.x; i < my * Ny; i += ZY_THREADS) b[i] = __ldg(sy_g + i);
+    sz = a;
+    sy = b;
+  }
   const size_t plane = blockIdx.x;
   const float2* up = U + plane * (size_t)my * mzh;
   for (int i = threadIdx.x; i < my * mzh; i += ZY_THREADS) Us[i] = __ldg(up + i);
@@ -199,7 +220,7 @@ synthesis_zy_kernel(const float2* __restrict__ U, float* __restrict__ out, const
     const int y = it / mzh, kz = it - y * mzh;
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll 4
-    for (int ky = 0; ky < my; ++ky) cfma(acc, __ldg(sy + (size_t)ky * Ny + y), Us[ky * mzh + kz]);
+    for (int ky = 0; ky < my; ++ky) cfma(acc, sy[(size_t)ky * Ny + y], Us[ky * mzh + kz]);
     Vs[it] = acc;
   }
   __syncthreads();
@@ -216,7 +237,7 @@ synthesis_zy_kernel(const float2* __restrict__ U, float* __restrict__ out, const
         const float2 v0 = Vs[(size_t)y0 * mzh + kz];
         const float2 v1 = Vs[(size_t)y1 * mzh + kz];
         const float4* t4 = reinterpret_cast<const float4*>(sz + (size_t)kz * Nz + z0);
-        const float4 ta = __ldg(t4), tb = __ldg(t4 + 1);
+        const float4 ta = t4[0], tb = t4[1];
         const float2 t[4] = {make_float2(ta.x, ta.y), make_float2(ta.z, ta.w), make_float2(tb.x, tb.y),
                              make_float2(tb.z, tb.w)};
 #pragma unroll
@@ -251,7 +272,7 @@ synthesis_zy_kernel(const float2* __restrict__ U, float* __restrict__ out, const
       float a = 0.f;
       for (int kz = 0; kz < mzh; ++kz) {
         const float2 v = Vs[(size_t)y * mzh + kz];
-        const float2 t = __ldg(sz + (size_t)kz * Nz + z);
+        const float2 t = sz[(size_t)kz * Nz + z];
         a = fmaf(v.x, t.x, a);
         a = fmaf(-v.y, t.y, a);
       }
@@ -322,7 +343,10 @@ int analysis_simt(const Plan* p, const float* x, float2* X, long long BC, int di
   while (YC > 32 && t1_floats * 4 + (size_t)YC * ldx * 4 > budget) YC = (YC + 1) / 2;
   YC = min(Ny, (YC + 31) / 32 * 32);
   while (YC > 1 && t1_floats * 4 + (size_t)YC * ldx * 4 > p->smem_optin) YC -= 1;
-  const size_t smem = t1_floats * 4 + (size_t)YC * ldx * 4;
+  size_t smem = t1_floats * 4 + (size_t)YC * ldx * 4;
+  const size_t tw_bytes = 8 + ((size_t)Nz * mzh + (size_t)Ny * my) * sizeof(float2);
+  const int tw_smem = (smem + tw_bytes <= 110 * 1024) ? 1 : 0;      // keep two CTAs per SM
+  if (tw_smem) smem += tw_bytes;
   const size_t planes = (size_t)BC * p->Nx;
   if (planes > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "analysis: too many planes");
   const int G = pick_group(mzh);
@@ -332,7 +356,7 @@ int analysis_simt(const Plan* p, const float* x, float2* X, long long BC, int di
     auto k = analysis_zy_kernel<GG, VV>;                                                                   \
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
     ProfScope ps(K_ANALYSIS_ZY, st);                                                                       \
-    k<<<(unsigned)planes, ZY_THREADS, smem, st>>>(x, ws, az, p->ay, Ny, Nz, my, mzh, YC, ldx);             \
+    k<<<(unsigned)planes, ZY_THREADS, smem, st>>>(x, ws, az, p->ay, Ny, Nz, my, mzh, YC, ldx, tw_smem);    \
   } while (0)
   if (vec4) {
     if (G == 2) LAUNCH_A(2, true); else if (G == 3) LAUNCH_A(3, true); else LAUNCH_A(4, true);
@@ -352,9 +376,12 @@ int synthesis_simt(const Plan* p, const float2* Z, float* out, const float* add0
     int rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
     if (rc) return rc;
   }
-  const size_t smem = ((size_t)my * mzh + (size_t)Ny * mzh) * sizeof(float2);
+  size_t smem = ((size_t)my * mzh + (size_t)Ny * mzh) * sizeof(float2);
   if (smem > p->smem_optin)
     return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis: %d y rows x %d kz modes do not fit shared memory", Ny, mzh);
+  const size_t tw_bytes = 32 + ((size_t)mzh * Nz + (size_t)my * Ny) * sizeof(float2);
+  const int tw_smem = (smem + tw_bytes <= 110 * 1024) ? 1 : 0;
+  if (tw_smem) smem += tw_bytes;
   const size_t planes = (size_t)BC * p->Nx;
   if (planes > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis: too many planes");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -364,12 +391,12 @@ int synthesis_simt(const Plan* p, const float2* Z, float* out, const float* add0
     auto k = synthesis_zy_kernel<true>;
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_SYNTHESIS_ZY, st);
-    k<<<(unsigned)planes, ZY_THREADS, smem, st>>>(ws, out, add0, add1, p->sy, sz, Ny, Nz, my, mzh);
+    k<<<(unsigned)planes, ZY_THREADS, smem, st>>>(ws, out, add0, add1, p->sy, sz, Ny, Nz, my, mzh, tw_smem);
   } else {
     auto k = synthesis_zy_kernel<false>;
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_SYNTHESIS_ZY, st);
-    k<<<(unsigned)planes, ZY_THREADS, smem, st>>>(ws, out, add0, add1, p->sy, sz, Ny, Nz, my, mzh);
+    k<<<(unsigned)planes, ZY_THREADS, smem, st>>>(ws, out, add0, add1, p->sy, sz, Ny, Nz, my, mzh, tw_smem);
   }
   PDEPHI_LAUNCH_CHECK("synthesis_zy_kernel");
   return PDEPHI_OK;
