@@ -290,8 +290,21 @@ def run_native(args):
     e2e_ms = timed(step_e2e, args.steps)
     final_loss = float(h_loss)
 
+    # the other precision route, same step, for the record (2 timed steps)
+    other = None
+    if world == 1 and not args.no_other_precision:
+        alt = "fp32" if args.precision == "tf32" else "tf32"
+        model.set_precision(alt)
+        for _ in range(2):
+            step(x, y)
+        alt_ms = timed(lambda: step(x, y), 2) / 2
+        model.set_precision(args.precision)
+        other = {"transform_precision": alt, "value": round(B / (alt_ms * 1e-3), 3), "unit": "samples/s",
+                 "ms_per_step": round(alt_ms, 3)}
     layer_us = None
     if rank == 0 and world == 1 and not args.no_layer_times:
+        del x, y
+        torch.cuda.empty_cache()
         layer_us = layer_times(dev, args.precision)
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -359,7 +372,7 @@ def run_native(args):
                 "e2e": {"value": round(e2e_value, 3), "unit": "samples/s",
                         "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": rooflines,
-                "cpu_baseline": cpu, "layer_fwd_bwd_us": layer_us, "kernels": per_kernel, "first_loss": first_loss, "final_loss": final_loss}
+                "cpu_baseline": cpu, "layer_fwd_bwd_us": layer_us, "other_precision": other, "kernels": per_kernel, "first_loss": first_loss, "final_loss": final_loss}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -409,10 +422,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PDEPHI_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("PDEPHI_PRECISION", "tf32"), choices=["fp32", "tf32"],
+                    help="transform arithmetic: tf32 = tcgen05 path (north_star gate 2e-3, the headline), fp32 = FFMA path (gate 1e-5)")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layer-times", action="store_true")
+    ap.add_argument("--no-other-precision", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
