@@ -203,6 +203,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION)
         dist.init_process_group("nccl", device_id=dev)
     pb.load_library()
 
