@@ -1,0 +1,189 @@
+"""The reference's own hot-path tests, re-stated against the drop-in modules on the GPU.
+
+Each test cites the reference test it mirrors (paths relative to /root/reference/tests).  Assertions the reference
+itself fails (layer energy ratio, rollout finiteness at default init) are kept in the form that is actually true of
+the reference: they are checked on the conditioned weight set.
+"""
+import io
+
+import pytest
+import torch
+
+import pde_fluid_phi_b200 as pb
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _condition(model):
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, pb.RationalFourierLayer):
+                q0 = m.Q_coeffs[..., 0, 0, 0].clone()
+                m.Q_coeffs.mul_(1e-4)
+                m.Q_coeffs[..., 0, 0, 0] = q0
+                m.P_coeffs.mul_(1e-3)
+    return model
+
+
+def test_layer_init_shapes_and_forward():
+    """test_operators.py:49-71: parameter shapes, same-shape finite output (W=32, modes 16^3, 64^3, B=2)."""
+    layer = pb.RationalFourierLayer(32, 32, (16, 16, 16), rational_order=(4, 4)).to(DEV)
+    assert layer.P_coeffs.shape == (32, 32, 4, 4, 4) and layer.Q_coeffs.shape == (32, 32, 4, 4, 4)
+    assert layer.k_grid.shape == (3, 16, 16, 9)
+    x = torch.randn(2, 32, 64, 64, 64, device=DEV)
+    y = layer(x)
+    assert y.shape == x.shape and torch.isfinite(y).all()
+
+
+def test_layer_gradients_exist_and_finite():
+    """test_operators.py:91-108."""
+    layer = pb.RationalFourierLayer(8, 8, (8, 8, 8)).to(DEV)
+    x = torch.randn(2, 8, 16, 16, 16, device=DEV, requires_grad=True)
+    layer(x).sum().backward()
+    for g in (x.grad, layer.P_coeffs.grad, layer.Q_coeffs.grad):
+        assert g is not None and torch.isfinite(g).all()
+
+
+def test_get_grid_convention():
+    """test_operators.py:294-304: shape (3,8,8,5), k_grid[0,:,0,0] == arange(8)."""
+    g = pb.get_grid((8, 8, 8))
+    assert g.shape == (3, 8, 8, 5)
+    assert torch.equal(g[0, :, 0, 0], torch.arange(8.0)) and torch.equal(g[2, 0, 0, :], torch.arange(5.0))
+
+
+def test_projection_mask_and_energy():
+    """test_operators.py:192-234: mask positive and decaying; energy of the retained modes conserved within 10 %."""
+    proj = pb.StabilityProjection((8, 8, 8), decay_rate=2.0).to(DEV)
+    m = proj.decay_mask
+    assert (m > 0).all() and m[0, 0, 0] == m.max() and m[-1, -1, -1] == m.min()
+    x_ft = torch.fft.rfftn(torch.randn(2, 3, 16, 16, 16, device=DEV), dim=[-3, -2, -1])
+    out = proj(x_ft)
+    e0 = x_ft[:, :, :8, :8, :5].abs().pow(2).sum()
+    e1 = out[:, :, :8, :8, :5].abs().pow(2).sum()
+    assert abs(float(e1 / e0) - 1.0) < 0.1
+
+
+@pytest.mark.parametrize("res,chan,batch", [(16, 1, 1), (32, 3, 2), (8, 3, 4), (16, 3, 4)])
+def test_operator_sizes(res, chan, batch):
+    """test_operators.py:417-438: modes=min(r//2, 8), grids 16^3/32^3/8^3, in=out channels in {1,3}, batch 1/2/4."""
+    m = min(res // 2, 8)
+    op = pb.RationalFourierOperator3D(modes=(m, m, m), width=16, n_layers=2, in_channels=chan, out_channels=chan).to(DEV)
+    y = op(torch.randn(batch, chan, res, res, res, device=DEV))
+    assert y.shape == (batch, chan, res, res, res)
+
+
+def test_determinism_same_seed_and_repeated_steps():
+    """test_operators.py:460-474 and test_comprehensive.py:575-647: same seed -> same output; two identical training
+    steps from the same state -> identical loss (bit-repeatable kernels, no float atomics)."""
+    def build():
+        torch.manual_seed(42)
+        return pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=2).to(DEV)
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 16, 16, 16, device=DEV)
+    y = torch.randn(2, 3, 16, 16, 16, device=DEV)
+    a, b = build(), build()
+    assert torch.equal(a(x), b(x))
+    losses = []
+    for model in (a, b):
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+        opt.zero_grad()
+        loss = torch.nn.functional.mse_loss(model(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(torch.nn.functional.mse_loss(model(x), y)))
+    assert losses[0] == losses[1]
+
+
+def test_small_rfno_forward_backward_all_params_have_grads():
+    """test_core_functionality.py:66-116: modes 4^3 on 8^3; every parameter has a finite gradient; three repeated
+    forwards agree to rtol 1e-5 (here: exactly)."""
+    model = pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=2).to(DEV)
+    x = torch.randn(1, 3, 8, 8, 8, device=DEV)
+    outs = [model(x) for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    outs[0].sum().backward()
+    for n, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_double_precision_is_refused_explicitly():
+    """test_integration.py:367-385 runs model.double(); the CUDA path is float32-only and says so."""
+    model = pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=1).to(DEV).double()
+    with pytest.raises(RuntimeError, match="float32"):
+        model(torch.randn(1, 3, 8, 8, 8, device=DEV, dtype=torch.float64))
+
+
+def test_gradient_norms_bounded_on_conditioned_weights():
+    """test_integration.py:343-365: gradient norm < 100 for every parameter."""
+    torch.manual_seed(1)
+    model = _condition(pb.RationalFourierOperator3D(modes=(8, 8, 8), width=16, n_layers=2)).to(DEV)
+    x = torch.randn(2, 3, 16, 16, 16, device=DEV)
+    torch.nn.functional.mse_loss(model(x), x).backward()
+    for n, p in model.named_parameters():
+        assert float(p.grad.norm()) < 100.0, n
+
+
+def test_checkpoint_round_trip():
+    """test_integration.py:195-233: state_dict save / load -> identical output."""
+    torch.manual_seed(2)
+    model = pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=2).to(DEV)
+    x = torch.randn(1, 3, 8, 8, 8, device=DEV)
+    buf = io.BytesIO()
+    torch.save({"model_state_dict": model.state_dict()}, buf)
+    buf.seek(0)
+    torch.manual_seed(99)
+    clone = pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=2).to(DEV)
+    clone.load_state_dict(torch.load(buf)["model_state_dict"])
+    assert torch.equal(model(x), clone(x))
+
+
+def test_rollout_finite_on_conditioned_weights_and_fno_rollout():
+    """test_operators.py:148-160 / test_integration.py:75-141: rollout shape and finiteness (the reference's own test
+    fails at default init -- NaN; on the conditioned weight set the operator is contractive enough to stay finite)."""
+    torch.manual_seed(3)
+    model = _condition(pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=2)).to(DEV)
+    x0 = torch.randn(1, 3, 16, 16, 16, device=DEV)
+    traj = model.rollout(x0, steps=3, return_trajectory=True)
+    assert traj.shape[0] == 1 and traj.shape[2:] == x0.shape[1:] and torch.isfinite(traj).all()
+    assert set(model.get_stability_monitor()) == {"spectral_radius", "energy_drift", "realizability_violations",
+                                                  "passivity_violations"}
+    fno = pb.FNO3D(modes=(4, 4, 4), width=8, n_layers=2).to(DEV)
+    out = fno.rollout(x0, steps=3)
+    assert out.shape == x0.shape and torch.isfinite(out).all()
+
+
+def test_channel_mismatch_raises_runtime_error():
+    """test_integration.py:415-427 expects RuntimeError / ValueError on bad input."""
+    model = pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=1).to(DEV)
+    with pytest.raises((RuntimeError, ValueError)):
+        model(torch.randn(1, 5, 8, 8, 8, device=DEV))
+    with pytest.raises((RuntimeError, ValueError)):
+        model(torch.randn(3, 8, 8, 8, device=DEV))
+
+
+def test_fno3d_fused_block_route_matches_unfused():
+    """FNO3D at width 64 takes the fused-block route on the TF32 path (models/fno3d.py:91-97 in one Function)."""
+    torch.manual_seed(5)
+    modes, grid = (8, 16, 16), (8, 128, 64)
+    model = pb.FNO3D(modes=modes, width=64, n_layers=2).to(DEV).set_precision("tf32")
+    x = torch.randn(2, 3, *grid, device=DEV)
+    y = torch.randn(2, 3, *grid, device=DEV)
+    if not model.spectral_layers[0].block_supported(torch.empty(2, 64, *grid, device=DEV), model.local_layers[0]):
+        pytest.skip("tcgen05 path not available for this shape")
+    torch.nn.functional.mse_loss(model(x), y).backward()
+    fused = {n: p.grad.clone() for n, p in model.named_parameters()}
+    out_fused = model(x).detach()
+    model.zero_grad()
+    model.activation = lambda t: torch.nn.functional.gelu(t)       # not F.gelu itself -> unfused route
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.nn.functional.mse_loss(model(x), y).backward()
+        out_ref = model(x).detach()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(out_fused, out_ref) < 3e-3
+    for n, p in model.named_parameters():
+        assert rel(fused[n], p.grad) < 5e-3, n
