@@ -358,6 +358,8 @@ class PointwiseLinearFn(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, weight, bias):
         _require_cuda_f32(x, "x")
+        if x.dim() < 3 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+            raise RuntimeError(f"pointwise linear: input {tuple(x.shape)} does not match weight {tuple(weight.shape)}")
         x = x.contiguous()
         weight = weight.contiguous()
         B, Cin = x.shape[:2]

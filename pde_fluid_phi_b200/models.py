@@ -60,6 +60,10 @@ def _lift(x: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
     """The reference's rearrange -> Linear -> rearrange (rational_fourier.py:258-260,274-276) as one
     channels-first contraction on the [B,C,X,Y,Z] layout: same result, no permuted copies.  Runs in
     libpdephi_b200.so (pointwise.cu); shapes it does not cover use the reference's own torch formulation."""
+    if x.dim() != 5:
+        raise ValueError(f"expected a [batch, channels, Nx, Ny, Nz] field, got shape {tuple(x.shape)}")
+    if x.shape[1] != linear.in_features:
+        raise RuntimeError(f"input has {x.shape[1]} channels, the model was built for {linear.in_features}")
     if pointwise_linear_supported(x, linear.weight):
         return PointwiseLinearFn.apply(x, linear.weight, linear.bias)
     return linear(x.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
