@@ -295,7 +295,7 @@ def run_native(args):
     # the other precision route, same step, for the record (2 timed steps)
     other = None
     if world == 1 and not args.no_other_precision:
-        alt = "fp32" if args.precision == "tf32" else "tf32"
+        alt = "auto" if args.precision == "tf32" else "tf32"    # "auto" = the modules' default: fp32-grade (split-TF32 tcgen05)
         model.set_precision(alt)
         for _ in range(2):
             step(x, y)
@@ -326,7 +326,9 @@ def run_native(args):
         mid = 8.0 * B * C * n * my * mzh                 # [BC,Nx,my,mzh] complex intermediate
         modes_b = 8.0 * B * C * mx * my * mzh            # retained modes
         alg = {
-            "analysis_zy_tc_kernel": act + mid, "analysis_zy_kernel": act + mid,
+            "analysis_zy_tc_kernel": act + mid, "analysis_zy_kernel": act + mid, "analysis_zy_tc3_kernel": act + mid,
+            "synthesis_zy_tc3_kernel": act + mid + 1.5 * act,   # unfused block route: forward fuses both skip addends, adjoint one
+            "analysis_x_tc3_kernel": mid + modes_b, "synthesis_x_tc3_kernel": mid + modes_b,
             # per step: 4 forward launches without addends + 4 adjoint launches with one addend -> mean
             "synthesis_zy_tc_kernel": act + mid + 0.5 * act,
             "synthesis_zy_kernel": act + mid + 1.5 * act,   # fp32 route: forward fuses both skip addends, adjoint one
@@ -346,7 +348,7 @@ def run_native(args):
                 rooflines[k] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                                 "frac": round(ach / peak, 4), "algorithmic_bytes_per_launch": alg[k],
                                 "avg_launch_ms": round(avg_ms, 4)}
-        hot = [k for k in ("analysis_zy_tc_kernel", "analysis_zy_kernel") if k in rooflines]
+        hot = [k for k in ("analysis_zy_tc_kernel", "analysis_zy_tc3_kernel", "analysis_zy_kernel") if k in rooflines]
         dom = max(rooflines, key=lambda k: prof[k][1]) if rooflines else None
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
         ncu_traffic = {"analysis_zy_tc_kernel": 4.580e9, "synthesis_zy_tc_kernel": None, "block_tail_fwd_kernel": 17.187e9,
@@ -369,7 +371,7 @@ def run_native(args):
                              "layers; pointwise ops excluded"}
         line = {"metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+                "scaling": "weak", "vs_baseline": None, "dtype": {"tf32": "tf32", "fp32": "f32"}.get(args.precision, "tf32x3 (fp32-grade)"),
                 "data": "synthetic", "config": workload_config(world, args.precision),
                 "e2e": {"value": round(e2e_value, 3), "unit": "samples/s",
                         "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 4, "d2h_bytes_per_step": 4},
@@ -424,8 +426,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PDEPHI_PRECISION", "tf32"), choices=["fp32", "tf32"],
-                    help="transform arithmetic: tf32 = tcgen05 path (north_star gate 2e-3, the headline), fp32 = FFMA path (gate 1e-5)")
+    ap.add_argument("--precision", default=os.environ.get("PDEPHI_PRECISION", "tf32"), choices=["auto", "fp32", "tf32x3", "tf32"],
+                    help="transform arithmetic: tf32 = single-pass tcgen05 (north_star gate 2e-3, the headline); auto = fp32-grade "
+                         "(gate 1e-5): split-TF32 tcgen05 (tf32x3) on tensor-core shapes, FFMA (fp32) elsewhere")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layer-times", action="store_true")

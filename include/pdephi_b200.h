@@ -45,7 +45,9 @@ enum pdephi_status {
  * run in IEEE fp32 with the reference's rounding order (bit-identical P, Q, R). */
 enum pdephi_precision {
   PDEPHI_PREC_FP32 = 0, /* fp32 FFMA contractions; parity gate 1e-5 */
-  PDEPHI_PREC_TF32 = 1  /* tcgen05 kind::tf32 contractions, fp32 accumulate; parity gate 2e-3 */
+  PDEPHI_PREC_TF32 = 1, /* tcgen05 kind::tf32 contractions, fp32 accumulate; parity gate 2e-3 */
+  PDEPHI_PREC_TF32X3 = 2 /* tcgen05 split contractions: every fp32 operand as a (hi, lo) TF32 pair, three MMAs per
+                            product, fp32 accumulate -- fp32-grade results at tensor-core speed; parity gate 1e-5 */
 };
 
 /* Which member of a transform pair.
@@ -65,6 +67,9 @@ int pdephi_plan_create(pdephi_plan_t* plan, int device, int Nx, int Ny, int Nz, 
 int pdephi_plan_create_slab(pdephi_plan_t* plan, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh,
                             int Nx_total, int x_offset);
 int pdephi_plan_destroy(pdephi_plan_t plan);
+/* 1 if the plan's (grid, modes) shape is covered by the kernels of `precision` (FP32 covers every shape; the
+ * tensor-core routes need Ny = 128, Nz in {64,128}, my <= 32, mzh <= 20), else 0 */
+int pdephi_plan_supports(pdephi_plan_t plan, int precision);
 /* bytes of scratch the two transforms need for `BC` (= batch*channels) volumes */
 size_t pdephi_plan_workspace_bytes(pdephi_plan_t plan, long long BC);
 

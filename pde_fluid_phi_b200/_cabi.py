@@ -15,9 +15,10 @@ _lib = None
 _lock = threading.RLock()
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = range(5)
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+PREC_AUTO = -1    # host-side only: TF32X3 where the plan supports it, FP32 (FFMA) elsewhere -- both meet the 1e-5 gate
 FORWARD, ADJOINT = 0, 1
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
 
 # name -> (restype, argtypes); mirrors include/pdephi_b200.h one to one
 SIGNATURES = {
@@ -27,6 +28,7 @@ SIGNATURES = {
     "pdephi_plan_create_slab": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "pdephi_plan_destroy": (c_int, [c_void_p]),
     "pdephi_plan_workspace_bytes": (c_size_t, [c_void_p, c_longlong]),
+    "pdephi_plan_supports": (c_int, [c_void_p, c_int]),
     "pdephi_analysis_r2c": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pdephi_synthesis_c2r": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                      c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
@@ -115,6 +117,13 @@ def get_plan(device_index: int, grid, modes_h, slab=None):
                 h = handle
                 _plans[key] = h
     return h
+
+
+def resolve_precision(plan, precision: int) -> int:
+    """PREC_AUTO -> the fastest route that meets the fp32 parity gate for this plan's shape."""
+    if precision != PREC_AUTO:
+        return precision
+    return PREC_TF32X3 if load().pdephi_plan_supports(plan, PREC_TF32X3) else PREC_FP32
 
 
 def profile(enable: bool = True, reset: bool = True):

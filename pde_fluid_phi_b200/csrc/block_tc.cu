@@ -126,7 +126,7 @@ block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_c
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       long long it = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int s = (int)(it % F_STAGES);
@@ -142,7 +142,7 @@ block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       constexpr uint32_t id = idesc_tf32(TS, C, 1, 0);
       long long it = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -259,7 +259,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
   const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       long long it = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int s = (int)(it % B_STAGES);
@@ -275,7 +275,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       constexpr uint32_t id_t = idesc_tf32(TS, C, 1, 0);     // T[128 x 64] = GU^T (MN-major A) . WcT (K-major B)
       constexpr uint32_t id_w = idesc_tf32(C, C, 0, 0);      // dW[64 x 64] += GU (K-major A) . H (K-major B)
       long long it = 0;

@@ -61,16 +61,31 @@ struct Plan {
   float* xtc_ax;    // analysis  [64][Nx]   (cos rows | sin rows)
   float* xtc_sc;    // synthesis [Nx][32]   cos
   float* xtc_ss;    // synthesis [Nx][32]   sin
+  // split (hi, lo) TF32 operands of the fp32-grade tensor-core path (transforms_tc3.cu, xstage_tc.cu)
+  int tc3_ok;
+  void* tc3_arena;
+  float* tc3_b1[2];     // analysis z  [dir]  per k-block: hi rows 0..39 | lo rows 40..79, [Nz] columns
+  float* tc3_a2;        // analysis y  plain [128][Ny]: rows 0..63 hi, 64..127 lo (TMEM-resident)
+  float* tc3_ay[2];     // synthesis y [hi|lo] [Ny][64]
+  float* tc3_bz[2][2];  // synthesis z [dir][hi|lo] [Nz][64]
+  int xtc3_a_ok, xtc3_s_ok;
+  void* xtc3_arena;
+  float* xtc3_ax[2];
+  float* xtc3_sc[2];
+  float* xtc3_ss[2];
 };
 int tc_plan_init(Plan* p);
 void tc_plan_destroy(Plan* p);
 int xtc_plan_init(Plan* p);
 void xtc_plan_destroy(Plan* p);
+int tc3_plan_init(Plan* p);
+void tc3_plan_destroy(Plan* p);
 
 enum KernelId {
   K_ANALYSIS_ZY = 0, K_ANALYSIS_X, K_SYNTHESIS_X, K_SYNTHESIS_ZY, K_ANALYSIS_ZY_TC, K_SYNTHESIS_ZY_TC,
   K_RATIONAL_MIX, K_RATIONAL_MIX_T, K_PROJ_STATS, K_PROJ_BWD, K_RATIONAL_DPQ, K_DPQ_REDUCE,
-  K_COMPLEX_MIX, K_COMPLEX_MIX_T, K_COMPLEX_DW, K_POINTWISE_LINEAR, K_POINTWISE_WGRAD, K_BLOCK_TAIL_FWD, K_BLOCK_TAIL_BWD, K_ANALYSIS_X_TC, K_SYNTHESIS_X_TC, K_SCALE_MODES, K_RATIONAL_G, K_COUNT
+  K_COMPLEX_MIX, K_COMPLEX_MIX_T, K_COMPLEX_DW, K_POINTWISE_LINEAR, K_POINTWISE_WGRAD, K_BLOCK_TAIL_FWD, K_BLOCK_TAIL_BWD, K_ANALYSIS_X_TC, K_SYNTHESIS_X_TC, K_SCALE_MODES, K_RATIONAL_G,
+  K_ANALYSIS_ZY_TC3, K_SYNTHESIS_ZY_TC3, K_ANALYSIS_X_TC3, K_SYNTHESIS_X_TC3, K_COUNT
 };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);

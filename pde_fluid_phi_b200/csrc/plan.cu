@@ -26,7 +26,8 @@ static const char* const kKernelNames[K_COUNT] = {
     "projection_stats_kernel", "projection_bwd_kernel", "rational_dpq_kernel", "dpq_reduce_kernel",
     "complex_mix_kernel", "complex_mix_kernel(transposed)", "complex_dw_kernel", "pointwise_linear_kernel",
     "pointwise_wgrad_kernel", "block_tail_fwd_kernel", "block_tail_bwd_kernel", "analysis_x_tc_kernel",
-    "synthesis_x_tc_kernel", "scale_modes_kernel", "rational_g_kernel"};
+    "synthesis_x_tc_kernel", "scale_modes_kernel", "rational_g_kernel", "analysis_zy_tc3_kernel",
+    "synthesis_zy_tc3_kernel", "analysis_x_tc3_kernel", "synthesis_x_tc3_kernel"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 static std::atomic<long long> g_launches[K_COUNT];
 static std::atomic<bool> g_prof_on{false};
@@ -150,6 +151,8 @@ extern "C" int pdephi_plan_create_slab(pdephi_plan_t* out, int device, int Nx, i
     if (rc) return rc;
     rc = xtc_plan_init(p);
     if (rc) return rc;
+    rc = tc3_plan_init(p);
+    if (rc) return rc;
   }
   PDEPHI_CUDA(cudaDeviceSynchronize());  // plan creation is the one synchronous call
   PDEPHI_CUDA(cudaSetDevice(cur));
@@ -163,6 +166,7 @@ extern "C" int pdephi_plan_destroy(pdephi_plan_t h) {
   if (p->arena) cudaFree(p->arena);
   tc_plan_destroy(p);
   xtc_plan_destroy(p);
+  tc3_plan_destroy(p);
   delete p;
   return PDEPHI_OK;
 }

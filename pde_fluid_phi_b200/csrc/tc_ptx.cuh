@@ -81,6 +81,35 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bde
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Warp-uniform issue helpers: the whole warp runs the (uniform) control flow and address arithmetic, one elected
+// lane issues.  Branching on lane == 0 around the issue loop instead makes every descriptor a divergent value that
+// has to be moved into uniform registers with an ELECT / R2UR.BROADCAST loop per MMA (~16 instructions each).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// `issue` != 0 in exactly one lane: the predicate lives inside the asm so the statement itself stays in uniform control flow
+__device__ __forceinline__ void mma_ss_w(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_w(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_w(uint32_t bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(issue)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -110,6 +139,30 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM (lane = this warp's quarter + laneid, 32 / 16 consecutive columns)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+          taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// the part of an fp32 value the tensor core sees when it reads it as a TF32 operand (low 13 mantissa bits dropped)
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 __device__ __forceinline__ float to_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -127,6 +180,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo) {
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return d;
 }
+// The same descriptor as two 32-bit words, so an issue loop can step the address field with one 32-bit add:
+// a byte offset `o` (multiple of 16, no carry out of the 14-bit field) is `lo + (o >> 4)`.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 // instruction descriptor: D fp32, A/B tf32, both K-major
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

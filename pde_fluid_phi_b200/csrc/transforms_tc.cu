@@ -128,7 +128,7 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       int it = 0;
       for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
         const int s = it & 1;
@@ -140,7 +140,7 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       constexpr uint32_t id1 = umma_idesc(128, N1), id2 = umma_idesc(M2, N2);
       const int n_my = blockIdx.x < planes ? (planes - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       auto gemm1 = [&](int i) {
@@ -307,7 +307,7 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
 
   if (warp == 0) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       constexpr uint32_t idy = umma_idesc(128, N1), idz = umma_idesc(128, NZ);
       int it = 0;
       for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {

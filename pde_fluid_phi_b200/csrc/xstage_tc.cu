@@ -55,34 +55,72 @@ __global__ void ximage_kernel(float* __restrict__ img, int kind, int R, int K, i
   img[swz_off(R, r, k) / 4] = to_tf32((float)v);
 }
 
+// same images as (hi, lo) TF32 pairs for the split (fp32-grade) contractions of transforms_tc3.cu
+__global__ void ximage_hilo_kernel(float* __restrict__ hi, float* __restrict__ lo, int kind, int R, int K, int Nt, int off, int m) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * K) return;
+  const int r = idx / K, k = idx % K;
+  int mode = -1, pos = 0, sine = 0;
+  if (kind == 0) { pos = k + off; if (r < m) mode = r; else if (r >= SIN0 && r < SIN0 + m) { mode = r - SIN0; sine = 1; } }
+  else { pos = r + off; sine = (kind == 2); if (k < m) mode = k; }
+  double v = 0.0;
+  if (mode >= 0) {
+    double s, c;
+    sincospi(2.0 * (double)(((long long)mode * pos) % Nt) / (double)Nt, &s, &c);
+    v = sine ? s : c;
+  }
+  const float h = to_tf32((float)v);
+  hi[swz_off(R, r, k) / 4] = h;
+  lo[swz_off(R, r, k) / 4] = to_tf32((float)(v - (double)h));
+}
+
+// in-place split of a staged data operand: every element becomes its lo part (see transforms_tc3.cu)
+__device__ __forceinline__ void split_in_place(float4* blk, int n4, int tid, int nthr) {
+  for (int i = tid; i < n4; i += nthr) {
+    float4 v = blk[i];
+    v.x = to_tf32(v.x - tf32_trunc(v.x));
+    v.y = to_tf32(v.y - tf32_trunc(v.y));
+    v.z = to_tf32(v.z - tf32_trunc(v.z));
+    v.w = to_tf32(v.w - tf32_trunc(v.w));
+    blk[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // analysis x stage
 // ------------------------------------------------------------------------------------------------
 constexpr int AX_THREADS = 192;
+constexpr int X3_SPLIT_THREADS = 128;
 constexpr int AX_STAGES = 4;
 constexpr int E_LD = 66;
-struct AXSmem { uint32_t stage[AX_STAGES], a, e, bars, tmem_slot, total; };
-__host__ __device__ inline AXSmem ax_smem(int Nx) {
+struct AXSmem { uint32_t stage[AX_STAGES], a, alo, e, bars, tmem_slot, total; };
+__host__ __device__ inline AXSmem ax_smem(int Nx, bool x3 = false) {
   AXSmem s; uint32_t o = 0;
   for (int i = 0; i < AX_STAGES; ++i) { s.stage[i] = o; o += 2 * Nx * 128; }
   s.a = o; o += (Nx / 32) * 64 * 128;
+  s.alo = o; if (x3) o += (Nx / 32) * 64 * 128;
   s.e = o; o += 64 * E_LD * 4 + 128;
   o = (o + 127) & ~127u;
-  s.bars = o; o += 128;
+  s.bars = o; o += 256;
   s.tmem_slot = o; o += 64;
   s.total = o;
   return s;
 }
-enum { AXB_FULL = 0, AXB_EMPTY = AX_STAGES, AXB_DFULL = 2 * AX_STAGES, AXB_DEMPTY = 2 * AX_STAGES + 2 };
+enum { AXB_FULL = 0, AXB_EMPTY = AX_STAGES, AXB_DFULL = 2 * AX_STAGES, AXB_DEMPTY = 2 * AX_STAGES + 2,
+       AXB_HIDONE = 2 * AX_STAGES + 4, AXB_LOREADY = 3 * AX_STAGES + 4 };
 
-__global__ void __launch_bounds__(AX_THREADS, 1)
+// X3: split contraction A.B = Ahi.Braw + Alo.Braw + Ahi.Blo; the data stage is rewritten in place as its lo part by
+// four extra warps between the second and third pass.
+template <bool X3>
+__global__ void __launch_bounds__(AX_THREADS + (X3 ? X3_SPLIT_THREADS : 0), 1)
 analysis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_t2, float2* __restrict__ X, const float* __restrict__ Aimg,
-                     int Nx, int mx, int P, int ntn, long long ntiles) {
+                     const float* __restrict__ Aloimg, int Nx, int mx, int P, int ntn, long long ntiles) {
+  constexpr int NTHR = AX_THREADS + (X3 ? X3_SPLIT_THREADS : 0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const AXSmem L = ax_smem(Nx);
+  const AXSmem L = ax_smem(Nx, X3);
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t box = (uint32_t)Nx * 128;
@@ -90,10 +128,18 @@ analysis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_t2, float2* __rest
   {
     const float4* s1 = reinterpret_cast<const float4*>(Aimg);
     float4* d1 = reinterpret_cast<float4*>(sm + L.a);
-    for (int i = threadIdx.x; i < (Nx / 32) * 64 * 128 / 16; i += AX_THREADS) d1[i] = __ldg(s1 + i);
+    for (int i = threadIdx.x; i < (Nx / 32) * 64 * 128 / 16; i += NTHR) d1[i] = __ldg(s1 + i);
+    if (X3) {
+      const float4* s2 = reinterpret_cast<const float4*>(Aloimg);
+      float4* d2 = reinterpret_cast<float4*>(sm + L.alo);
+      for (int i = threadIdx.x; i < (Nx / 32) * 64 * 128 / 16; i += NTHR) d2[i] = __ldg(s2 + i);
+    }
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < AX_STAGES; ++i) { mbar_init(bar(AXB_FULL + i), 1); mbar_init(bar(AXB_EMPTY + i), 1); }
+    for (int i = 0; i < AX_STAGES; ++i) {
+      mbar_init(bar(AXB_FULL + i), 1); mbar_init(bar(AXB_EMPTY + i), 1);
+      mbar_init(bar(AXB_HIDONE + i), 1); mbar_init(bar(AXB_LOREADY + i), X3_SPLIT_THREADS);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(AXB_DFULL + i), 1); mbar_init(bar(AXB_DEMPTY + i), 4); }
     fence_barrier_init();
   }
@@ -105,7 +151,7 @@ analysis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_t2, float2* __rest
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       long long it = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int s = (int)(it % AX_STAGES);
@@ -118,20 +164,62 @@ analysis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_t2, float2* __rest
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       constexpr uint32_t id = idesc(64, NT, 0, 1);
-      long long it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = (int)(it % AX_STAGES), d = (int)(it & 1);
-        mbar_wait(bar(AXB_FULL + s), (uint32_t)((it / AX_STAGES) & 1));
-        mbar_wait(bar(AXB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
-        tc_fence_after();
-        for (int k = 0; k < Nx / 8; ++k)
-          mma_ss(tmem + d * NT, umma_desc(base + L.a + (k >> 2) * (64 * 128) + (k & 3) * 32, 1024),
-                 desc_mn(base + L.stage[s] + k * 1024, box), id, k ? 1u : 0u);
-        mma_commit(bar(AXB_EMPTY + s));
-        mma_commit(bar(AXB_DFULL + d));
+      if (!X3) {
+        long long it = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+          const int s = (int)(it % AX_STAGES), d = (int)(it & 1);
+          mbar_wait(bar(AXB_FULL + s), (uint32_t)((it / AX_STAGES) & 1));
+          mbar_wait(bar(AXB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
+          tc_fence_after();
+          for (int k = 0; k < Nx / 8; ++k)
+            mma_ss(tmem + d * NT, umma_desc(base + L.a + (k >> 2) * (64 * 128) + (k & 3) * 32, 1024),
+                   desc_mn(base + L.stage[s] + k * 1024, box), id, k ? 1u : 0u);
+          mma_commit(bar(AXB_EMPTY + s));
+          mma_commit(bar(AXB_DFULL + d));
+        }
+      } else {
+        const long long n_my = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        auto hi_pass = [&](long long it) {
+          const int s = (int)(it % AX_STAGES), d = (int)(it & 1);
+          mbar_wait(bar(AXB_FULL + s), (uint32_t)((it / AX_STAGES) & 1));
+          mbar_wait(bar(AXB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
+          tc_fence_after();
+          for (int k = 0; k < Nx / 8; ++k)
+            mma_ss(tmem + d * NT, umma_desc(base + L.a + (k >> 2) * (64 * 128) + (k & 3) * 32, 1024),
+                   desc_mn(base + L.stage[s] + k * 1024, box), id, k ? 1u : 0u);
+          for (int k = 0; k < Nx / 8; ++k)
+            mma_ss(tmem + d * NT, umma_desc(base + L.alo + (k >> 2) * (64 * 128) + (k & 3) * 32, 1024),
+                   desc_mn(base + L.stage[s] + k * 1024, box), id, 1u);
+          mma_commit(bar(AXB_HIDONE + s));
+        };
+        auto lo_pass = [&](long long it) {
+          const int s = (int)(it % AX_STAGES), d = (int)(it & 1);
+          mbar_wait(bar(AXB_LOREADY + s), (uint32_t)((it / AX_STAGES) & 1));
+          tc_fence_after();
+          for (int k = 0; k < Nx / 8; ++k)
+            mma_ss(tmem + d * NT, umma_desc(base + L.a + (k >> 2) * (64 * 128) + (k & 3) * 32, 1024),
+                   desc_mn(base + L.stage[s] + k * 1024, box), id, 1u);
+          mma_commit(bar(AXB_EMPTY + s));
+          mma_commit(bar(AXB_DFULL + d));
+        };
+        if (n_my > 0) hi_pass(0);
+        for (long long it = 0; it < n_my; ++it) {
+          if (it + 1 < n_my) hi_pass(it + 1);
+          lo_pass(it);
+        }
       }
+    }
+  } else if (X3 && warp >= AX_THREADS / 32) {
+    const int tid = threadIdx.x - AX_THREADS;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = (int)(it % AX_STAGES);
+      mbar_wait(bar(AXB_HIDONE + s), (uint32_t)((it / AX_STAGES) & 1));
+      split_in_place(reinterpret_cast<float4*>(sm + L.stage[s]), (int)(2 * box / 16), tid, X3_SPLIT_THREADS);
+      fence_proxy_async();
+      mbar_arrive(bar(AXB_LOREADY + s));
     }
   } else {
     const int q = warp & 3;
@@ -183,20 +271,23 @@ constexpr int SX_EPI = 8;
 constexpr int SX_THREADS = 32 * (2 + SX_EPI);
 constexpr int SX_STAGES = 4;
 constexpr int SX_LD = 36;
-struct SXSmem { uint32_t stage[SX_STAGES], ac, as, stg, bars, tmem_slot, total; };
-__host__ __device__ inline SXSmem sx_smem() {
+struct SXSmem { uint32_t stage[SX_STAGES], ac, as, aclo, aslo, stg, bars, tmem_slot, total; };
+__host__ __device__ inline SXSmem sx_smem(bool x3 = false) {
   SXSmem s; uint32_t o = 0;
   for (int i = 0; i < SX_STAGES; ++i) { s.stage[i] = o; o += 2 * 32 * 128; }
   s.ac = o; o += 128 * 128;
   s.as = o; o += 128 * 128;
+  s.aclo = o; if (x3) o += 128 * 128;
+  s.aslo = o; if (x3) o += 128 * 128;
   s.stg = o; o += SX_EPI * 32 * SX_LD * 4;
   o = (o + 127) & ~127u;
-  s.bars = o; o += 128;
+  s.bars = o; o += 256;
   s.tmem_slot = o; o += 64;
   s.total = o;
   return s;
 }
-enum { SXB_FULL = 0, SXB_EMPTY = SX_STAGES, SXB_DFULL = 2 * SX_STAGES, SXB_DEMPTY = 2 * SX_STAGES + 2 };
+enum { SXB_FULL = 0, SXB_EMPTY = SX_STAGES, SXB_DFULL = 2 * SX_STAGES, SXB_DEMPTY = 2 * SX_STAGES + 2,
+       SXB_HIDONE = 2 * SX_STAGES + 4, SXB_LOREADY = 3 * SX_STAGES + 4 };
 
 // Z' = Y * mode_scale[k] * row_scale[bc]   (StabilityProjection's mask and energy factor), into the workspace
 __global__ void scale_modes_kernel(const float2* __restrict__ Y, float2* __restrict__ Z, const float* __restrict__ mode_scale,
@@ -210,14 +301,17 @@ __global__ void scale_modes_kernel(const float2* __restrict__ Y, float2* __restr
   Z[i] = make_float2(v.x * s, v.y * s);
 }
 
-__global__ void __launch_bounds__(SX_THREADS, 1)
+template <bool X3>
+__global__ void __launch_bounds__(SX_THREADS + (X3 ? X3_SPLIT_THREADS : 0), 1)
 synthesis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, float* __restrict__ U, const float* __restrict__ Acimg,
-                      const float* __restrict__ Asimg, int Nx, int mx, int P, int ntn, int nmt, long long ntiles) {
+                      const float* __restrict__ Asimg, const float* __restrict__ Acloimg, const float* __restrict__ Asloimg,
+                      int Nx, int mx, int P, int ntn, int nmt, long long ntiles) {
+  constexpr int NTHR = SX_THREADS + (X3 ? X3_SPLIT_THREADS : 0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const SXSmem L = sx_smem();
+  const SXSmem L = sx_smem(X3);
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t box = 32 * 128;
@@ -226,10 +320,20 @@ synthesis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, float* __restr
     const float4* s2 = reinterpret_cast<const float4*>(Asimg);
     float4* d1 = reinterpret_cast<float4*>(sm + L.ac);
     float4* d2 = reinterpret_cast<float4*>(sm + L.as);
-    for (int i = threadIdx.x; i < 128 * 128 / 16; i += SX_THREADS) { d1[i] = __ldg(s1 + i); d2[i] = __ldg(s2 + i); }
+    for (int i = threadIdx.x; i < 128 * 128 / 16; i += NTHR) { d1[i] = __ldg(s1 + i); d2[i] = __ldg(s2 + i); }
+    if (X3) {
+      const float4* s3 = reinterpret_cast<const float4*>(Acloimg);
+      const float4* s4 = reinterpret_cast<const float4*>(Asloimg);
+      float4* d3 = reinterpret_cast<float4*>(sm + L.aclo);
+      float4* d4 = reinterpret_cast<float4*>(sm + L.aslo);
+      for (int i = threadIdx.x; i < 128 * 128 / 16; i += NTHR) { d3[i] = __ldg(s3 + i); d4[i] = __ldg(s4 + i); }
+    }
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SX_STAGES; ++i) { mbar_init(bar(SXB_FULL + i), 1); mbar_init(bar(SXB_EMPTY + i), 1); }
+    for (int i = 0; i < SX_STAGES; ++i) {
+      mbar_init(bar(SXB_FULL + i), 1); mbar_init(bar(SXB_EMPTY + i), 1);
+      mbar_init(bar(SXB_HIDONE + i), 1); mbar_init(bar(SXB_LOREADY + i), X3_SPLIT_THREADS);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(SXB_DFULL + i), 1); mbar_init(bar(SXB_DEMPTY + i), SX_EPI); }
     fence_barrier_init();
   }
@@ -242,7 +346,7 @@ synthesis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, float* __restr
   const long long per_mt = ntiles / nmt;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       long long it = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int s = (int)(it % SX_STAGES);
@@ -255,23 +359,70 @@ synthesis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, float* __restr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
       constexpr uint32_t id = idesc(128, NT, 0, 1);
-      long long it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = (int)(it % SX_STAGES), d = (int)(it & 1);
-        mbar_wait(bar(SXB_FULL + s), (uint32_t)((it / SX_STAGES) & 1));
-        mbar_wait(bar(SXB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
-        tc_fence_after();
+      if (!X3) {
+        long long it = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+          const int s = (int)(it % SX_STAGES), d = (int)(it & 1);
+          mbar_wait(bar(SXB_FULL + s), (uint32_t)((it / SX_STAGES) & 1));
+          mbar_wait(bar(SXB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t bd = desc_mn(base + L.stage[s] + k * 1024, box);
-          mma_ss(tmem + d * 128, umma_desc(base + L.ac + k * 32, 1024), bd, id, k ? 1u : 0u);
-          mma_ss(tmem + d * 128 + NT, umma_desc(base + L.as + k * 32, 1024), bd, id, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = desc_mn(base + L.stage[s] + k * 1024, box);
+            mma_ss(tmem + d * 128, umma_desc(base + L.ac + k * 32, 1024), bd, id, k ? 1u : 0u);
+            mma_ss(tmem + d * 128 + NT, umma_desc(base + L.as + k * 32, 1024), bd, id, k ? 1u : 0u);
+          }
+          mma_commit(bar(SXB_EMPTY + s));
+          mma_commit(bar(SXB_DFULL + d));
         }
-        mma_commit(bar(SXB_EMPTY + s));
-        mma_commit(bar(SXB_DFULL + d));
+      } else {
+        const long long n_my = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        auto hi_pass = [&](long long it) {
+          const int s = (int)(it % SX_STAGES), d = (int)(it & 1);
+          mbar_wait(bar(SXB_FULL + s), (uint32_t)((it / SX_STAGES) & 1));
+          mbar_wait(bar(SXB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = desc_mn(base + L.stage[s] + k * 1024, box);
+            mma_ss(tmem + d * 128, umma_desc(base + L.ac + k * 32, 1024), bd, id, k ? 1u : 0u);
+            mma_ss(tmem + d * 128 + NT, umma_desc(base + L.as + k * 32, 1024), bd, id, k ? 1u : 0u);
+            mma_ss(tmem + d * 128, umma_desc(base + L.aclo + k * 32, 1024), bd, id, 1u);
+            mma_ss(tmem + d * 128 + NT, umma_desc(base + L.aslo + k * 32, 1024), bd, id, 1u);
+          }
+          mma_commit(bar(SXB_HIDONE + s));
+        };
+        auto lo_pass = [&](long long it) {
+          const int s = (int)(it % SX_STAGES), d = (int)(it & 1);
+          mbar_wait(bar(SXB_LOREADY + s), (uint32_t)((it / SX_STAGES) & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = desc_mn(base + L.stage[s] + k * 1024, box);
+            mma_ss(tmem + d * 128, umma_desc(base + L.ac + k * 32, 1024), bd, id, 1u);
+            mma_ss(tmem + d * 128 + NT, umma_desc(base + L.as + k * 32, 1024), bd, id, 1u);
+          }
+          mma_commit(bar(SXB_EMPTY + s));
+          mma_commit(bar(SXB_DFULL + d));
+        };
+        if (n_my > 0) hi_pass(0);
+        for (long long it = 0; it < n_my; ++it) {
+          if (it + 1 < n_my) hi_pass(it + 1);
+          lo_pass(it);
+        }
       }
+    }
+  } else if (X3 && warp >= SX_THREADS / 32) {
+    const int tid = threadIdx.x - SX_THREADS;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = (int)(it % SX_STAGES);
+      mbar_wait(bar(SXB_HIDONE + s), (uint32_t)((it / SX_STAGES) & 1));
+      split_in_place(reinterpret_cast<float4*>(sm + L.stage[s]), (int)(2 * box / 16), tid, X3_SPLIT_THREADS);
+      fence_proxy_async();
+      mbar_arrive(bar(SXB_LOREADY + s));
     }
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -354,12 +505,36 @@ int xtc_plan_init(Plan* p) {
   if (!tensor_map_encoder(nullptr)) return PDEPHI_OK;
   p->xtc_a_ok = a_ok;
   p->xtc_s_ok = s_ok;
+  // (hi, lo) images of the same twiddles for the split fp32-grade contractions
+  p->xtc3_a_ok = p->xtc3_s_ok = 0;
+  p->xtc3_arena = nullptr;
+  const bool a3_ok = a_ok && xtc::ax_smem(p->Nx, true).total + 1024 <= p->smem_optin;
+  const bool s3_ok = s_ok && xtc::sx_smem(true).total + 1024 <= p->smem_optin;
+  if (!a3_ok && !s3_ok) return PDEPHI_OK;
+  PDEPHI_CUDA(cudaMalloc(&p->xtc3_arena, 2 * (nA + 2 * nS) * sizeof(float)));
+  PDEPHI_CUDA(cudaMemset(p->xtc3_arena, 0, 2 * (nA + 2 * nS) * sizeof(float)));
+  f = (float*)p->xtc3_arena;
+  for (int h = 0; h < 2; ++h) { p->xtc3_ax[h] = f; f += nA; }
+  for (int h = 0; h < 2; ++h) { p->xtc3_sc[h] = f; f += nS; }
+  for (int h = 0; h < 2; ++h) { p->xtc3_ss[h] = f; f += nS; }
+  auto gen3 = [&](float* hi, float* lo, int kind, int R, int K) {
+    const int n = R * K;
+    xtc::ximage_hilo_kernel<<<(n + 255) / 256, 256>>>(hi, lo, kind, R, K, p->Nx_total, p->x_offset, p->mx);
+  };
+  gen3(p->xtc3_ax[0], p->xtc3_ax[1], 0, 64, p->Nx);
+  gen3(p->xtc3_sc[0], p->xtc3_sc[1], 1, p->Nx, 32);
+  gen3(p->xtc3_ss[0], p->xtc3_ss[1], 2, p->Nx, 32);
+  PDEPHI_LAUNCH_CHECK("ximage_hilo_kernel");
+  p->xtc3_a_ok = a3_ok;
+  p->xtc3_s_ok = s3_ok;
   return PDEPHI_OK;
 }
 
 void xtc_plan_destroy(Plan* p) {
   if (p->xtc_arena) cudaFree(p->xtc_arena);
   p->xtc_arena = nullptr;
+  if (p->xtc3_arena) cudaFree(p->xtc3_arena);
+  p->xtc3_arena = nullptr;
 }
 
 static int make_row_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, int box_rows) {
@@ -376,8 +551,10 @@ static int make_row_map(CUtensorMap* m, const void* ptr, long long rows, long lo
 
 bool xstage_analysis_tc_ok(const Plan* p) { return p->xtc_a_ok != 0; }
 bool xstage_synthesis_tc_ok(const Plan* p) { return p->xtc_s_ok != 0; }
+bool xstage_analysis_tc3_ok(const Plan* p) { return p->xtc3_a_ok != 0; }
+bool xstage_synthesis_tc3_ok(const Plan* p) { return p->xtc3_s_ok != 0; }
 
-int xstage_analysis_tc(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st) {
+static int xstage_analysis_launch(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st, bool x3) {
   const int P = p->my * p->mzh;
   const long long rows = BC * p->Nx;
   if (rows > 0x7fffffffLL) return fail(PDEPHI_ERR_UNSUPPORTED, "x stage: too many rows");
@@ -386,21 +563,33 @@ int xstage_analysis_tc(const Plan* p, const float2* ws, float2* X, long long BC,
   if (rc) return rc;
   const int ntn = (2 * P + xtc::NT - 1) / xtc::NT;
   const long long ntiles = BC * ntn;
-  const size_t smem = xtc::ax_smem(p->Nx).total + 1024;
-  auto k = xtc::analysis_x_tc_kernel;
-  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = xtc::ax_smem(p->Nx, x3).total + 1024;
   const int grid = (int)(ntiles < p->num_sms ? ntiles : p->num_sms);
-  {
+  if (x3) {
+    auto k = xtc::analysis_x_tc_kernel<true>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ANALYSIS_X_TC3, st);
+    k<<<grid, xtc::AX_THREADS + xtc::X3_SPLIT_THREADS, smem, st>>>(map, X, p->xtc3_ax[0], p->xtc3_ax[1], p->Nx, p->mx, P, ntn,
+                                                                  ntiles);
+  } else {
+    auto k = xtc::analysis_x_tc_kernel<false>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_ANALYSIS_X_TC, st);
-    k<<<grid, xtc::AX_THREADS, smem, st>>>(map, X, p->xtc_ax, p->Nx, p->mx, P, ntn, ntiles);
+    k<<<grid, xtc::AX_THREADS, smem, st>>>(map, X, p->xtc_ax, nullptr, p->Nx, p->mx, P, ntn, ntiles);
   }
   PDEPHI_LAUNCH_CHECK("analysis_x_tc_kernel");
   return PDEPHI_OK;
 }
+int xstage_analysis_tc(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st) {
+  return xstage_analysis_launch(p, ws, X, BC, st, false);
+}
+int xstage_analysis_tc3(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st) {
+  return xstage_analysis_launch(p, ws, X, BC, st, true);
+}
 
 // Z -> (optional scaling into `scratch`) -> U (workspace)
-int xstage_synthesis_tc(const Plan* p, const float2* Z, float2* ws, float2* scratch, const float* mode_scale,
-                        const float* row_scale, long long rs_stride, long long BC, cudaStream_t st) {
+static int xstage_synthesis_launch(const Plan* p, const float2* Z, float2* ws, float2* scratch, const float* mode_scale,
+                                   const float* row_scale, long long rs_stride, long long BC, cudaStream_t st, bool x3) {
   const int P = p->my * p->mzh;
   const long long M = (long long)p->mx * P;
   const float2* src = Z;
@@ -421,16 +610,31 @@ int xstage_synthesis_tc(const Plan* p, const float2* Z, float2* ws, float2* scra
   const int ntn = (2 * P + xtc::NT - 1) / xtc::NT;
   const int nmt = p->Nx / 128;
   const long long ntiles = BC * ntn * nmt;
-  const size_t smem = xtc::sx_smem().total + 1024;
-  auto k = xtc::synthesis_x_tc_kernel;
-  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = xtc::sx_smem(x3).total + 1024;
   const int grid = (int)(ntiles < p->num_sms ? ntiles : p->num_sms);
-  {
+  if (x3) {
+    auto k = xtc::synthesis_x_tc_kernel<true>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_SYNTHESIS_X_TC3, st);
+    k<<<grid, xtc::SX_THREADS + xtc::X3_SPLIT_THREADS, smem, st>>>(map, (float*)ws, p->xtc3_sc[0], p->xtc3_ss[0], p->xtc3_sc[1],
+                                                                  p->xtc3_ss[1], p->Nx, p->mx, P, ntn, nmt, ntiles);
+  } else {
+    auto k = xtc::synthesis_x_tc_kernel<false>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_SYNTHESIS_X_TC, st);
-    k<<<grid, xtc::SX_THREADS, smem, st>>>(map, (float*)ws, p->xtc_sc, p->xtc_ss, p->Nx, p->mx, P, ntn, nmt, ntiles);
+    k<<<grid, xtc::SX_THREADS, smem, st>>>(map, (float*)ws, p->xtc_sc, p->xtc_ss, nullptr, nullptr, p->Nx, p->mx, P, ntn, nmt,
+                                           ntiles);
   }
   PDEPHI_LAUNCH_CHECK("synthesis_x_tc_kernel");
   return PDEPHI_OK;
+}
+int xstage_synthesis_tc(const Plan* p, const float2* Z, float2* ws, float2* scratch, const float* mode_scale,
+                        const float* row_scale, long long rs_stride, long long BC, cudaStream_t st) {
+  return xstage_synthesis_launch(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st, false);
+}
+int xstage_synthesis_tc3(const Plan* p, const float2* Z, float2* ws, float2* scratch, const float* mode_scale,
+                         const float* row_scale, long long rs_stride, long long BC, cudaStream_t st) {
+  return xstage_synthesis_launch(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st, true);
 }
 
 }  // namespace pdephi

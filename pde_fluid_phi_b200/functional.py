@@ -56,7 +56,7 @@ def monomial_table(modes: Sequence[int], order: int) -> torch.Tensor:
 # raw ops (no autograd)
 # ------------------------------------------------------------------------------------------------
 def analysis(x: torch.Tensor, modes_h: Tuple[int, int, int], direction: int = _cabi.FORWARD,
-             precision: int = _cabi.PREC_FP32, slab=None) -> torch.Tensor:
+             precision: int = _cabi.PREC_AUTO, slab=None) -> torch.Tensor:
     """K1.  x [B,C,Nx,Ny,Nz] float32 -> [B,C,mx,my,mzh] complex64 (pruned rfftn / adjoint of synthesis).
 
     slab = (Nx_total, x_offset): x is the slab [x_offset, x_offset+Nx) of a larger grid and the result is
@@ -70,6 +70,7 @@ def analysis(x: torch.Tensor, modes_h: Tuple[int, int, int], direction: int = _c
     lib = _cabi.load()
     with torch.cuda.device(x.device):
         plan = _cabi.get_plan(x.device.index, grid, modes_h, slab)
+        precision = _cabi.resolve_precision(plan, precision)
         X = torch.empty((B, C, *modes_h), dtype=torch.complex64, device=x.device)
         nbytes = lib.pdephi_plan_workspace_bytes(plan, B * C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
@@ -81,7 +82,7 @@ def analysis(x: torch.Tensor, modes_h: Tuple[int, int, int], direction: int = _c
 def synthesis(Z: torch.Tensor, grid: Tuple[int, int, int], mode_scale: Optional[torch.Tensor] = None,
               row_scale: Optional[torch.Tensor] = None, addend0: Optional[torch.Tensor] = None,
               addend1: Optional[torch.Tensor] = None, direction: int = _cabi.FORWARD,
-              precision: int = _cabi.PREC_FP32, slab=None) -> torch.Tensor:
+              precision: int = _cabi.PREC_AUTO, slab=None) -> torch.Tensor:
     """K3.  Z [B,C,mx,my,mzh] complex64 -> [B,C,Nx,Ny,Nz] float32, out = S(Z*mode_scale*row_scale) + addends.
 
     row_scale: float32 1-D (possibly strided) view with one element per volume, e.g. ``stats[:, 2]``.
@@ -107,6 +108,7 @@ def synthesis(Z: torch.Tensor, grid: Tuple[int, int, int], mode_scale: Optional[
     lib = _cabi.load()
     with torch.cuda.device(Z.device):
         plan = _cabi.get_plan(Z.device.index, grid, modes_h, slab)
+        precision = _cabi.resolve_precision(plan, precision)
         out = torch.empty((B, C, *grid), dtype=torch.float32, device=Z.device)
         nbytes = lib.pdephi_plan_workspace_bytes(plan, B * C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=Z.device)

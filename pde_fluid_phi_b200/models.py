@@ -107,7 +107,7 @@ class RationalFourierOperator3D(nn.Module):
         _reset_pointwise(self)
 
     def set_precision(self, precision: Optional[str]):
-        """'fp32' | 'tf32' | None (module default) for every spectral layer of this model."""
+        """'auto' | 'fp32' | 'tf32x3' | 'tf32' | None (module default) for every spectral layer of this model."""
         for layer in self.rational_layers:
             layer.precision = precision
         return self

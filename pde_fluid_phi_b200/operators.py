@@ -20,11 +20,18 @@ from . import _cabi
 from .functional import (ComplexBlockFn, ComplexSpectralFn, RationalBlockFn, RationalSpectralFn, block_tail_supported,
                          monomial_exponents, monomial_table)
 
-_default_precision = "fp32"
+_default_precision = "auto"
 
 
 def set_default_precision(precision: str) -> None:
-    """'fp32' (FFMA contractions, 1e-5 parity gate) or 'tf32' (tcgen05 contractions, 2e-3 gate)."""
+    """Arithmetic of the transform stages.
+
+    'auto'   (default) fp32-grade, parity gate 1e-5: split-TF32 tcgen05 contractions ('tf32x3') on the shapes
+             the tensor-core kernels cover, FFMA ('fp32') everywhere else
+    'fp32'   FFMA contractions, any shape
+    'tf32x3' tcgen05, every operand as a (hi, lo) TF32 pair, three MMAs per product
+    'tf32'   tcgen05 single-pass TF32, parity gate 2e-3; with width 64 the whole block runs fused
+    """
     global _default_precision
     if precision not in _cabi.PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(_cabi.PRECISIONS)}")

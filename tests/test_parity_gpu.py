@@ -17,7 +17,7 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-5, "tf32": 2e-3}
+TOL = {"fp32": 1e-5, "tf32": 2e-3, "tf32x3": 1e-5, "auto": 1e-5}
 DEV = "cuda"
 
 
@@ -27,16 +27,11 @@ def rel(a, b):
     return so.rel_l2(a, b)
 
 
-def tc_ok(grid, modes):
-    """Shapes the tcgen05 TF32 path accepts (the library reports the rest as unsupported)."""
+def tc_ok(grid, modes, precision=_cabi.PREC_TF32):
+    """Shapes the tcgen05 paths accept (the library reports the rest as unsupported)."""
     lib = pb.load_library()
-    x = torch.zeros(1, 1, *grid, device=DEV)
-    try:
-        pf.analysis(x, (modes[0], modes[1], modes[2] // 2 + 1), _cabi.FORWARD, _cabi.PREC_TF32)
-        torch.cuda.synchronize()
-        return True
-    except NotImplementedError:
-        return False
+    plan = _cabi.get_plan(torch.cuda.current_device(), grid, (modes[0], modes[1], modes[2] // 2 + 1))
+    return bool(lib.pdephi_plan_supports(plan, precision))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -149,9 +144,9 @@ SHAPES = [((16, 16, 16), (8, 8, 8)), ((16, 12, 20), (6, 4, 8)), ((9, 7, 11), (5,
 
 
 @pytest.mark.parametrize("grid,modes", SHAPES)
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x3"])
 def test_transforms_vs_fp64_spec(grid, modes, precision):
-    if precision == "tf32" and not tc_ok(grid, modes):
+    if precision != "fp32" and not tc_ok(grid, modes, _cabi.PRECISIONS[precision]):
         pytest.skip("shape not covered by the tcgen05 path")
     prec = _cabi.PRECISIONS[precision]
     rng = np.random.default_rng(0)
@@ -203,11 +198,12 @@ def test_cfg2_shape_vs_torch_fft():
     mh = (32, 32, 17)
     x = torch.randn(1, 2, *grid, device=DEV)
     ref = torch.fft.rfftn(x.double(), dim=[-3, -2, -1])[:, :, :32, :32, :17]
-    assert rel(pf.analysis(x, mh), ref) < 1e-5
     Z = torch.randn(1, 2, *mh, device=DEV, dtype=torch.complex64)
     full = torch.zeros(1, 2, 128, 128, 65, dtype=torch.complex128, device=DEV)
     full[:, :, :32, :32, :17] = Z
-    assert rel(pf.synthesis(Z, grid).double(), torch.fft.irfftn(full, s=grid, dim=[-3, -2, -1])) < 1e-5
+    for prec in (_cabi.PREC_AUTO, _cabi.PREC_FP32, _cabi.PREC_TF32X3):       # every fp32-grade route: gate 1e-5
+        assert rel(pf.analysis(x, mh, precision=prec), ref) < 1e-5
+        assert rel(pf.synthesis(Z, grid, precision=prec).double(), torch.fft.irfftn(full, s=grid, dim=[-3, -2, -1])) < 1e-5
     if tc_ok(grid, modes):
         assert rel(pf.analysis(x, mh, precision=_cabi.PREC_TF32), ref) < 2e-3
         assert rel(pf.synthesis(Z, grid, precision=_cabi.PREC_TF32).double(),
@@ -283,10 +279,12 @@ def test_fused_block_matches_unfused_and_is_deterministic():
     assert torch.equal(again, fused) and torch.equal(x.grad, gx) and torch.equal(layer.P_coeffs.grad, gP)
 
 
-def test_tf32_layer_gate():
-    """The tcgen05 path on the headline layer shape family: <= 2e-3 against the oracle on outputs and grads."""
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3", "fp32"])
+def test_tensor_core_layer_gates(precision):
+    """The headline layer shape family against the oracle on outputs and grads: <= 2e-3 on the single-pass TF32
+    route, <= 1e-5 on the split-TF32 route (and on the FFMA route beside it)."""
     C, modes, grid = 8, (32, 32, 32), (128, 128, 128)
-    if not tc_ok(grid, modes):
+    if precision != "fp32" and not tc_ok(grid, modes, _cabi.PRECISIONS[precision]):
         pytest.skip("tcgen05 path not available for this shape")
     torch.manual_seed(21)
     layer = pb.RationalFourierLayer(C, C, modes)
@@ -302,15 +300,15 @@ def test_tf32_layer_gate():
     out_o = so.rational_fourier_layer(xo, P, Q, modes, 1e-6)
     out_o.backward(g)
     layer = layer.to(DEV)
-    layer.precision = "tf32"
+    layer.precision = precision
     xg = x.to(DEV).requires_grad_(True)
     out = layer(xg)
     out.backward(g.to(DEV))
     errs = dict(out=rel(out, out_o), dx=rel(xg.grad, xo.grad), dP=rel(layer.P_coeffs.grad, P.grad),
                 dQ=rel(layer.Q_coeffs.grad, Q.grad))
-    print("\ntf32 layer errors", errs)
+    print(f"\n{precision} layer errors", errs)
     for k, v in errs.items():
-        assert v < TOL["tf32"], (k, v)
+        assert v < TOL[precision], (k, v)
 
 
 def test_amp_and_double_are_explicit():
@@ -345,11 +343,12 @@ def test_pointwise_linear_vs_torch(B, Cin, Cout, grid):
 
 
 @pytest.mark.parametrize("grid,modes,nslab,precision", [((16, 12, 20), (6, 4, 8), 2, "fp32"), ((32, 32, 32), (8, 8, 8), 4, "fp32"),
-                                                        ((8, 128, 128), (8, 16, 16), 2, "tf32")])
+                                                        ((8, 128, 128), (8, 16, 16), 2, "tf32"), ((8, 128, 128), (8, 16, 16), 2, "tf32x3"),
+                                                        ((256, 128, 64), (12, 16, 24), 2, "tf32x3")])
 def test_slab_plans_on_one_gpu(grid, modes, nslab, precision):
     """The slab-decomposed transform, ranks emulated sequentially on one GPU: partial spectra of the x slabs sum
     to the transform of the whole volume, and each slab's synthesis equals its rows of the whole synthesis."""
-    if precision == "tf32" and not tc_ok(grid, modes):
+    if precision != "fp32" and not tc_ok(grid, modes, _cabi.PRECISIONS[precision]):
         pytest.skip("shape not covered by the tcgen05 path")
     prec = _cabi.PRECISIONS[precision]
     torch.manual_seed(9)
