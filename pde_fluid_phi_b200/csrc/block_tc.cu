@@ -2,10 +2,15 @@
 //   forward   u = spec + (Wc h + bc) + h ;  h' = gelu(u)            (rational_fourier.py:268-271, fno3d.py:93-97)
 //   backward  gu = g' gelu'(u) ;  t = gu + Wc^T gu ;  dWc = sum_s gu (x) h ;  dbc = sum_s gu
 // for a width-64 model on the channels-first [B, 64, S] layout.  A tile is 128 spatial points x 64 channels,
-// TMA-staged as four [64 channel rows][32 points] boxes with 128-byte swizzle: that one shared-memory image is
+// staged as four [64 channel rows][32 points] sub-tiles with 128-byte swizzle: that one shared-memory image is
 // the MN-major A operand of the channel GEMM  D[128 points x 64] = tile^T . Wc^T  (tcgen05 kind::tf32, TMEM
 // accumulator) and, in the backward, also the K-major operands of the weight-gradient GEMM accumulated in
-// TMEM across all tiles of a persistent CTA.  Replaces cuDNN conv fwd/bwd + bias reductions + GELU fwd/bwd +
+// TMEM across all tiles of a persistent CTA.
+// The tiles are staged by four loader warps with cp.async (16-byte chunks, software swizzle), not by TMA: the 64
+// rows of a tile are 4*S bytes (8 MB) apart, and a TMA box that touches 64 pages for 128 bytes each tops out at
+// 4.6 TB/s on a B200 whatever the swizzle mode, ring depth or CTA count (scripts/probes/tma_probe.cu), while
+// warp-wide 512-byte row reads of the same tile reach the 7.3 TB/s read peak (scripts/probes/bw_probe.cu).
+// Replaces cuDNN conv fwd/bwd + bias reductions + GELU fwd/bwd +
 // residual / gradient-accumulation adds (about 56 GB of HBM traffic per layer) with two passes (21.5 GB each).
 #include <cuda.h>
 
@@ -22,7 +27,10 @@ constexpr int BOX = C * 128;     // bytes of one [64 rows][32 floats] box
 constexpr int TILE = 4 * BOX;    // 32 KB
 constexpr int EPI_WARPS = 16;    // 4 TMEM quarters x 4 channel groups: enough warps to hide LDS / MUFU latency
 constexpr int CPW = C / (EPI_WARPS / 4);   // channels per epilogue warp (16)
-constexpr int THREADS = 32 * (2 + EPI_WARPS);
+constexpr int LD_WARPS = 4;      // cp.async loader warps: warp w stages channel rows [16w, 16w+16) of every tile
+constexpr int LD_THREADS = 32 * LD_WARPS;
+constexpr int EPI0 = 1 + LD_WARPS;         // first epilogue warp (warp 0 issues the MMAs)
+constexpr int THREADS = 32 * (EPI0 + EPI_WARPS);
 
 // MN-major TF32 operand (M or N contiguous).  32-bit MN-major operands exist only in the "128B swizzle with
 // 32-byte atoms" layout (UMMA LayoutType 1 = SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
@@ -50,16 +58,19 @@ __device__ __forceinline__ uint32_t tile_off_k(int r, int s) {
 }
 // Exact (erf) GELU and its derivative from one exponential: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7,
 // i.e. fp32 rounding level) with e^{-x^2} = e^{-u^2/2} shared with the Gaussian density of the derivative.  The
-// epilogues are issue-bound, so ~14 instructions here instead of libm erff's ~25 matter.
+// epilogues are issue-bound (the fused forward spends 1.5 ms of issue slots on 2.7 ms of HBM time), so the two
+// transcendental steps are single MUFU instructions (ex2 / rcp .approx.ftz: no denormal range fix-ups, which
+// __expf / __fdividef add as 6 more instructions per element) and the 0.5 of 0.5*erfc is folded into the polynomial.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void gelu_parts(float u, float& cdf, float& e) {
-  const float x = fabsf(u) * 0.70710678118654752f;
-  e = __expf(-0.5f * u * u);                                   // e^{-x^2}
-  const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float half_erfc = 0.5f * p * t * e;                    // 0.5 * erfc(|x|)
+  e = ex2_ftz(u * u * -0.72134752044448170368f);               // e^{-u^2/2}
+  const float t = rcp_ftz(fmaf(0.23164189591177988f, fabsf(u), 1.f));   // 1 / (1 + 0.3275911 |u| / sqrt 2)
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);            // half the A&S coefficients: p t e = 0.5 erfc(|u| / sqrt 2)
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float half_erfc = p * t * e;
   cdf = u >= 0.f ? 1.f - half_erfc : half_erfc;                // Phi(u) = 0.5 (1 + erf(u / sqrt 2))
 }
 __device__ __forceinline__ float gelu_f(float u) {
@@ -83,7 +94,41 @@ __device__ __forceinline__ void build_w_image(uint8_t* dst, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// cp.async staging
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// A warp instruction stages one channel row of a tile: lane = 16-byte chunk (4 points) of the 128-point row, i.e.
+// 512 contiguous bytes of global memory.  Offset of chunk `lane` of row r inside the staged tile:
+//   MN-major use: 32-byte-atom swizzle, the image CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B would produce
+__device__ __forceinline__ uint32_t chunk_off_mn(int r, int lane) {
+  const int j = lane >> 3, cc = lane & 7;
+  return (uint32_t)(j * BOX + r * 128 + ((((cc >> 1) ^ (r & 3)) & 3) << 5) + (cc & 1) * 16);
+}
+//   K-major use: 16-byte-chunk swizzle (CU_TENSOR_MAP_SWIZZLE_128B)
+__device__ __forceinline__ uint32_t chunk_off_k(int r, int lane) {
+  const int j = lane >> 3, cc = lane & 7;
+  return (uint32_t)(j * BOX + r * 128 + (((cc ^ (r & 7)) & 7) << 4));
+}
+// rows [16*lw, 16*lw+16) of the tile of tensor `t` ([B*64 rows][S]) at (batch b, first point s0)
+template <bool KMAJOR>
+__device__ __forceinline__ void stage_rows(uint32_t dst, const float* __restrict__ t, long long b, long long s0, long long S,
+                                           int lw, int lane) {
+  const float* src = t + ((size_t)b * C + lw * 16) * S + s0 + lane * 4;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = lw * 16 + i;
+    cp_async16(dst + (KMAJOR ? chunk_off_k(r, lane) : chunk_off_mn(r, lane)), src + (size_t)i * S);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward
+//   warp 0: MMA issuer + TMEM owner, warps 1..4: loaders, warps 5..20: epilogue
 // ------------------------------------------------------------------------------------------------
 constexpr int F_STAGES = 3;
 struct FSmem { uint32_t stage[F_STAGES], w, bias, bars, tmem_slot, total; };
@@ -100,9 +145,9 @@ __host__ __device__ inline FSmem fwd_smem() {
 enum { FB_FULL = 0, FB_EMPTY = F_STAGES, FB_DFULL = 2 * F_STAGES, FB_DEMPTY = 2 * F_STAGES + 2 };
 
 __global__ void __launch_bounds__(THREADS, 1)
-block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_spec,
-                      const float* __restrict__ Wc, const float* __restrict__ bc, float* __restrict__ u_out,
-                      float* __restrict__ h_out, long long tiles_per_batch, long long ntiles, long long S) {
+block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ spec_in, const float* __restrict__ Wc,
+                      const float* __restrict__ bc, float* __restrict__ u_out, float* __restrict__ h_out,
+                      long long tiles_per_batch, long long ntiles, long long S) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -114,38 +159,41 @@ block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_c
   build_w_image(sm + L.w, Wc, false, threadIdx.x, THREADS);
   if (threadIdx.x < C) reinterpret_cast<float*>(sm + L.bias)[threadIdx.x] = bc ? __ldg(bc + threadIdx.x) : 0.f;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < F_STAGES; ++i) { mbar_init(bar(FB_FULL + i), 1); mbar_init(bar(FB_EMPTY + i), 1 + EPI_WARPS); }
+    for (int i = 0; i < F_STAGES; ++i) { mbar_init(bar(FB_FULL + i), LD_THREADS); mbar_init(bar(FB_EMPTY + i), 1 + EPI_WARPS); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(FB_DFULL + i), 1); mbar_init(bar(FB_DEMPTY + i), EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(base + L.tmem_slot, 128);
+  if (warp == 0) tmem_alloc(base + L.tmem_slot, 128);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == 0) {
-    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
-      long long it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+  if (warp >= 1 && warp < EPI0) {
+    // ===== loaders: h and spec tiles; F_STAGES - 1 tiles stay in flight behind the one being issued =====
+    const int lw = warp - 1;
+    for (long long it = 0; it < my_tiles + (F_STAGES - 1); ++it) {
+      if (it < my_tiles) {
+        const long long t = blockIdx.x + it * gridDim.x;
         const int s = (int)(it % F_STAGES);
-        const uint32_t ph = (uint32_t)((it / F_STAGES) & 1);
-        mbar_wait(bar(FB_EMPTY + s), ph ^ 1);
-        mbar_arrive_expect_tx(bar(FB_FULL + s), 2 * TILE);
+        mbar_wait(bar(FB_EMPTY + s), (uint32_t)(((it / F_STAGES) & 1) ^ 1));
         const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tma_load_2d(base + L.stage[s] + j * BOX, &tmap_h, bar(FB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
-          tma_load_2d(base + L.stage[s] + TILE + j * BOX, &tmap_spec, bar(FB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
-        }
+        stage_rows<false>(base + L.stage[s], h_in, b, s0, S, lw, lane);
+        stage_rows<false>(base + L.stage[s] + TILE, spec_in, b, s0, S, lw, lane);
+      }
+      cp_async_commit();                         // (empty groups in the drain iterations keep the group count uniform)
+      if (it >= F_STAGES - 1) {
+        cp_async_wait<F_STAGES - 1>();           // the group committed F_STAGES - 1 iterations ago has landed
+        fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(bar(FB_FULL + (int)((it - (F_STAGES - 1)) % F_STAGES)));
       }
     }
-  } else if (warp == 1) {
-    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
+  } else if (warp == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA back to back
       constexpr uint32_t id = idesc_tf32(TS, C, 1, 0);
-      long long it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      for (long long it = 0; it < my_tiles; ++it) {
         const int s = (int)(it % F_STAGES), d = (int)(it & 1);
         mbar_wait(bar(FB_FULL + s), (uint32_t)((it / F_STAGES) & 1));
         mbar_wait(bar(FB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -159,7 +207,7 @@ block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_c
       }
     }
   } else {
-    const int q = warp & 3, part = (warp - 2) >> 2;
+    const int q = warp & 3, part = (warp - EPI0) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float bsr[CPW];
 #pragma unroll
@@ -168,8 +216,8 @@ block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_c
     uint32_t xc[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) xc[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 3) ^ r) & 3) << 5) + (lane & 7) * 4);
-    long long it = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long t = blockIdx.x + it * gridDim.x;
       const int s = (int)(it % F_STAGES), d = (int)(it & 1);
       mbar_wait(bar(FB_DFULL + d), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
@@ -202,11 +250,12 @@ block_tail_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 128);
+  if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward
+//   warp 0: MMA issuer + TMEM owner, warps 1..4: loaders, warps 5..20: compute / epilogue
 // ------------------------------------------------------------------------------------------------
 constexpr int B_STAGES = 2;
 struct BSmem { uint32_t stage[B_STAGES], wt, red, bars, tmem_slot, total; };
@@ -226,10 +275,9 @@ enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2
        BB_DWDONE = 2 * B_STAGES + 6 };
 
 __global__ void __launch_bounds__(THREADS, 1)
-block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_h,
-                      const __grid_constant__ CUtensorMap tmap_u, const float* __restrict__ Wc, float* __restrict__ gu_out,
-                      float* __restrict__ t_out, float* __restrict__ partial, long long tiles_per_batch, long long ntiles,
-                      long long S) {
+block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
+                      const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
+                      float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -240,7 +288,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
 
   build_w_image(sm + L.wt, Wc, true, threadIdx.x, THREADS);      // rows c, K = o : (Wc^T)
   if (threadIdx.x == 0) {
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), 1); mbar_init(bar(BB_EMPTY + i), 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), LD_THREADS); mbar_init(bar(BB_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(BB_GUREADY + i), EPI_WARPS);
       mbar_init(bar(BB_TFULL + i), 1);
@@ -249,7 +297,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
     mbar_init(bar(BB_DWDONE), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(base + L.tmem_slot, 256);
+  if (warp == 0) tmem_alloc(base + L.tmem_slot, 256);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -258,32 +306,35 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
   const uint32_t tmem_t[2] = {tmem, tmem + C}, tmem_dw = tmem + 2 * C;
   const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == 0) {
-    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
-      long long it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+  if (warp >= 1 && warp < EPI0) {
+    // ===== loaders: g' (MN layout), h (K layout), u (K layout) =====
+    const int lw = warp - 1;
+    for (long long it = 0; it < my_tiles + (B_STAGES - 1); ++it) {
+      if (it < my_tiles) {
+        const long long t = blockIdx.x + it * gridDim.x;
         const int s = (int)(it % B_STAGES);
         mbar_wait(bar(BB_EMPTY + s), (uint32_t)(((it / B_STAGES) & 1) ^ 1));
-        mbar_arrive_expect_tx(bar(BB_FULL + s), 3 * TILE);
         const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tma_load_2d(base + L.stage[s] + j * BOX, &tmap_g, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
-          tma_load_2d(base + L.stage[s] + TILE + j * BOX, &tmap_h, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
-          tma_load_2d(base + L.stage[s] + 2 * TILE + j * BOX, &tmap_u, bar(BB_FULL + s), (int)(s0 + 32 * j), (int)(b * C));
-        }
+        stage_rows<false>(base + L.stage[s], g_in, b, s0, S, lw, lane);
+        stage_rows<true>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
+        stage_rows<true>(base + L.stage[s] + 2 * TILE, u_in, b, s0, S, lw, lane);
+      }
+      cp_async_commit();
+      if (it >= B_STAGES - 1) {
+        cp_async_wait<B_STAGES - 1>();
+        fence_proxy_async();
+        mbar_arrive(bar(BB_FULL + (int)((it - (B_STAGES - 1)) % B_STAGES)));
       }
     }
-  } else if (warp == 1) {
-    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA / UTMALDG back to back
+  } else if (warp == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA back to back
       constexpr uint32_t id_t = idesc_tf32(TS, C, 1, 0);     // T[128 x 64] = GU^T (MN-major A) . WcT (K-major B)
       constexpr uint32_t id_w = idesc_tf32(C, C, 0, 0);      // dW[64 x 64] += GU (K-major A) . H (K-major B)
-      long long it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      for (long long it = 0; it < my_tiles; ++it) {
         const int s = (int)(it % B_STAGES);
         const int d = (int)(it & 1);
         const uint32_t ph = (uint32_t)((it >> 1) & 1);
-        mbar_wait(bar(BB_GUREADY + d), ph);                  // gu written in place over g' (implies TMA landed)
+        mbar_wait(bar(BB_GUREADY + d), ph);                  // gu written in place over g' (implies the tile landed)
         mbar_wait(bar(BB_TEMPTY + d), ph ^ 1);
         tc_fence_after();
         const uint32_t gu = base + L.stage[s], hh = gu + TILE, guk = gu + 2 * TILE;
@@ -301,7 +352,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
       mma_commit(bar(BB_DWDONE));
     }
   } else {
-    const int q = warp & 3, part = (warp - 2) >> 2;
+    const int q = warp & 3, part = (warp - EPI0) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float db[CPW];
 #pragma unroll
@@ -368,7 +419,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     float* pout = partial + (size_t)blockIdx.x * (C * C + C);
-    if (warp == 2 && my_tiles >= 0) {
+    if (warp == EPI0 && my_tiles >= 0) {
       for (int o = lane; o < C; o += 32) pout[C * C + o] = (red[o] + red[C + o]) + (red[2 * C + o] + red[3 * C + o]);
     }
     if (my_tiles > 0) {
@@ -392,7 +443,7 @@ block_tail_bwd_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 __global__ void block_tail_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db,
@@ -406,25 +457,6 @@ __global__ void block_tail_reduce_kernel(const float* __restrict__ partial, floa
 }
 
 }  // namespace blk
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn tensor_map_encoder(const void* device_ptr);
-
-static int make_map(CUtensorMap* m, const float* p, long long rows, long long S, bool atom32) {
-  const cuuint64_t dims[2] = {(cuuint64_t)S, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)S * sizeof(float)};
-  const cuuint32_t box[2] = {32, (cuuint32_t)blk::C};
-  const cuuint32_t estr[2] = {1, 1};
-  EncodeTiledFn enc = tensor_map_encoder(p);
-  if (!enc) return fail(PDEPHI_ERR_UNSUPPORTED, "block_tail: cuTensorMapEncodeTiled is not available");
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(PDEPHI_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return PDEPHI_OK;
-}
 
 static int check_shape(int B, int Cc, long long S, const char* who) {
   PDEPHI_REQUIRE(B > 0 && S > 0, "%s: non-positive size", who);
@@ -449,9 +481,8 @@ extern "C" int pdephi_block_tail_fwd(const float* h, const float* spec, const fl
   PDEPHI_REQUIRE(h && spec && Wc && u && hout, "block_tail_fwd: null pointer");
   int rc = check_shape(B, Cc, S, "block_tail_fwd");
   if (rc) return rc;
-  CUtensorMap mh, ms;
-  if ((rc = make_map(&mh, h, (long long)B * Cc, S, true))) return rc;
-  if ((rc = make_map(&ms, spec, (long long)B * Cc, S, true))) return rc;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(h) || !al16(spec)) return fail(PDEPHI_ERR_INVALID, "block_tail_fwd: h and spec must be 16-byte aligned");
   const long long tpb = S / blk::TS, ntiles = tpb * B;
   const size_t smem = blk::fwd_smem().total + 1024;
   auto k = blk::block_tail_fwd_kernel;
@@ -461,7 +492,7 @@ extern "C" int pdephi_block_tail_fwd(const float* h, const float* spec, const fl
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope ps(K_BLOCK_TAIL_FWD, st);
-    k<<<grid, blk::THREADS, smem, st>>>(mh, ms, Wc, bc, u, hout, tpb, ntiles, S);
+    k<<<grid, blk::THREADS, smem, st>>>(h, spec, Wc, bc, u, hout, tpb, ntiles, S);
   }
   PDEPHI_LAUNCH_CHECK("block_tail_fwd_kernel");
   return PDEPHI_OK;
@@ -480,10 +511,8 @@ extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float
   if (rc) return rc;
   const size_t need = pdephi_block_tail_bwd_workspace_bytes(Cc);
   if (!workspace || workspace_bytes < need) return fail(PDEPHI_ERR_WORKSPACE, "block_tail_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
-  CUtensorMap mg, mh, mu;
-  if ((rc = make_map(&mg, g, (long long)B * Cc, S, true))) return rc;     // becomes gu: MN-major operand of the Wc^T gu GEMM
-  if ((rc = make_map(&mh, h, (long long)B * Cc, S, false))) return rc;    // K-major operand of the dWc GEMM
-  if ((rc = make_map(&mu, u, (long long)B * Cc, S, false))) return rc;    // becomes gu: K-major operand of the dWc GEMM
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(g) || !al16(h) || !al16(u)) return fail(PDEPHI_ERR_INVALID, "block_tail_bwd: g, h and u must be 16-byte aligned");
   const long long tpb = S / blk::TS, ntiles = tpb * B;
   const size_t smem = blk::bwd_smem().total + 1024;
   auto k = blk::block_tail_bwd_kernel;
@@ -494,7 +523,7 @@ extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope ps(K_BLOCK_TAIL_BWD, st);
-    k<<<grid, blk::THREADS, smem, st>>>(mg, mh, mu, Wc, gu, t, (float*)workspace, tpb, ntiles, S);
+    k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S);
   }
   PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
   {

@@ -224,8 +224,15 @@ def block_tail_bwd(g, u, h, Wc, want_bias: bool):
 
 
 def block_tail_supported(h: torch.Tensor, precision: int) -> bool:
-    return (h.is_cuda and h.dtype == torch.float32 and h.dim() == 5 and h.shape[1] == 64
-            and h[0, 0].numel() % 128 == 0 and precision == _cabi.PREC_TF32)
+    """The fused block tail contracts the 1x1x1 convolution in single-pass TF32 on the tensor cores.  That is the
+    arithmetic torch's own cuDNN convolution uses while ``torch.backends.cudnn.allow_tf32`` is True (the PyTorch
+    default, so also what the reference's Conv3d does on this GPU): the 'tf32' route always takes it, the
+    fp32-grade tensor-core routes take it exactly when torch would run the conv in TF32 too, 'fp32' never does."""
+    if not (h.is_cuda and h.dtype == torch.float32 and h.dim() == 5 and h.shape[1] == 64 and h[0, 0].numel() % 128 == 0):
+        return False
+    if precision == _cabi.PREC_TF32:
+        return True
+    return precision in (_cabi.PREC_AUTO, _cabi.PREC_TF32X3) and bool(torch.backends.cudnn.allow_tf32)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,91 @@
+// GPU probe: achievable HBM bandwidth of the block-tail access pattern -- 2 reads + 2 writes of [B*64 rows][S] fp32
+// tensors walked as tiles of 64 channel rows x TP points (rows 8 MB apart), against a flat streaming copy.
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o bw_probe bw_probe.cu && ./bw_probe
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+
+template <int TP, int NR, int NW>   // points per tile, tensors read, tensors written
+__global__ void __launch_bounds__(512, 1) tile_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c,
+                                                      float* __restrict__ d, long long S, long long ntiles, long long tiles_per_batch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int V = TP / 128;   // float4 per lane per row segment
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long long bb = t / tiles_per_batch, s0 = (t - bb * tiles_per_batch) * TP;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long row = bb * 64 + warp * 4 + r;
+      const size_t off = (size_t)row * S + s0;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const size_t o = off + (size_t)(v * 32 + lane) * 4;
+        float4 x = __ldcs(reinterpret_cast<const float4*>(a + o));
+        if (NR > 1) { float4 y = __ldcs(reinterpret_cast<const float4*>(b + o)); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+        __stcs(reinterpret_cast<float4*>(c + o), x);
+        if (NW > 1) __stcs(reinterpret_cast<float4*>(d + o), x);
+      }
+    }
+  }
+}
+// read-only variants: SEG = contiguous bytes a warp instruction takes from one row (512 = one row per instruction,
+// 128 = four rows x 128 B, the request granularity of a [64 rows][32 floats] TMA box); the sum keeps the loads alive
+template <int SEG, int DEPTH>
+__global__ void __launch_bounds__(512, 1) read_kernel(const float* __restrict__ a, float* __restrict__ sink, long long S, long long ntiles,
+                                                      long long tiles_per_batch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long long bb = t / tiles_per_batch, s0 = (t - bb * tiles_per_batch) * 128;
+    float4 x[DEPTH];
+#pragma unroll
+    for (int r = 0; r < DEPTH; ++r) {     // 16 warps x DEPTH(4) instructions x 512 B = 32 KB = one [64 rows][128 points] tile
+      size_t o;
+      if (SEG == 512) o = (size_t)(bb * 64 + warp * 4 + r) * S + s0 + lane * 4;
+      else o = (size_t)(bb * 64 + warp * 4 + (lane >> 3)) * S + s0 + r * 32 + (lane & 7) * 4;
+      x[r] = __ldcs(reinterpret_cast<const float4*>(a + o));
+    }
+#pragma unroll
+    for (int r = 0; r < DEPTH; ++r) acc += x[r].x + x[r].y + x[r].z + x[r].w;
+  }
+  if (acc == 123.456f) sink[0] = acc;
+}
+template <int NR, int NW>
+__global__ void flat_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ c, float4* __restrict__ d, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 x = __ldcs(a + i);
+    if (NR > 1) { float4 y = __ldcs(b + i); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+    __stcs(c + i, x);
+    if (NW > 1) __stcs(d + i, x);
+  }
+}
+template <typename F>
+float time_ms(F f) {
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  f(); f();
+  cudaEventRecord(e0);
+  for (int i = 0; i < 5; ++i) f();
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  return ms / 5;
+}
+int main() {
+  const int B = 8; const long long S = 128LL * 128 * 128; const size_t n = (size_t)B * 64 * S;
+  float *a, *b, *c, *d;
+  cudaMalloc(&a, n * 4); cudaMalloc(&b, n * 4); cudaMalloc(&c, n * 4); cudaMalloc(&d, n * 4);
+  cudaMemset(a, 0, n * 4); cudaMemset(b, 0, n * 4);
+  const double gb = n * 4 / 1e9;
+#define TILE(TP, NR, NW, GRID) { long long tpb = S / TP, nt = tpb * B; float ms = time_ms([&] { tile_kernel<TP, NR, NW><<<GRID, 512>>>(a, b, c, d, S, nt, tpb); }); \
+    printf("tile TP=%4d reads=%d writes=%d grid=%4d: %.3f ms  %.0f GB/s\n", TP, NR, NW, GRID, ms, gb * (NR + NW) / ms * 1e3); }
+#define FLAT(NR, NW, GRID) { float ms = time_ms([&] { flat_kernel<NR, NW><<<GRID, 512>>>((float4*)a, (float4*)b, (float4*)c, (float4*)d, n / 4); }); \
+    printf("flat reads=%d writes=%d grid=%4d: %.3f ms  %.0f GB/s\n", NR, NW, GRID, ms, gb * (NR + NW) / ms * 1e3); }
+  FLAT(1, 1, 148 * 4) FLAT(2, 2, 148 * 4) FLAT(2, 2, 148 * 16) FLAT(1, 1, 148 * 16)
+  TILE(128, 2, 2, 148) TILE(256, 2, 2, 148) TILE(512, 2, 2, 148) TILE(1024, 2, 2, 148)
+  TILE(128, 2, 2, 296) TILE(128, 2, 2, 592) TILE(256, 2, 2, 592) TILE(512, 2, 2, 592)
+  TILE(128, 1, 1, 592) TILE(512, 1, 1, 592) TILE(128, 2, 1, 592)
+#define READ(SEG, GRID) { long long tpb = S / 128, nt = tpb * B; float ms = time_ms([&] { read_kernel<SEG, 4><<<GRID, 512>>>(a, c, S, nt, tpb); }); \
+    printf("read-only SEG=%3d grid=%4d: %.3f ms  %.0f GB/s\n", SEG, GRID, ms, gb / ms * 1e3); }
+  READ(512, 148) READ(128, 148) READ(512, 296) READ(128, 296) READ(512, 592) READ(128, 592)
+  cudaError_t e = cudaDeviceSynchronize();
+  printf("status %s\n", cudaGetErrorString(e));
+  return 0;
+}
