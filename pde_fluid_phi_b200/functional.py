@@ -259,6 +259,50 @@ def _allreduce_modes(X, group):
 
 
 
+class PrunedAnalysisFn(torch.autograd.Function):
+    """K1 alone with autograd: X = rfftn(x)[..., :mx, :my, :mzh].  Backward is the ADJOINT synthesis."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, modes_h, precision):
+        ctx.meta = (tuple(x.shape[2:]), precision)
+        return analysis(x, tuple(modes_h), _cabi.FORWARD, precision)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, gX):
+        grid, precision = ctx.meta
+        return synthesis(gX.contiguous(), grid, direction=_cabi.ADJOINT, precision=precision), None, None
+
+
+class PrunedSynthesisFn(torch.autograd.Function):
+    """K3 alone with autograd: out = irfftn(zero-pad(Z), s=grid).  Backward is the ADJOINT analysis."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, Z, grid, precision):
+        ctx.meta = (tuple(Z.shape[2:]), precision)
+        return synthesis(Z, tuple(grid), direction=_cabi.FORWARD, precision=precision)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, g):
+        modes_h, precision = ctx.meta
+        return analysis(g.contiguous(), modes_h, _cabi.ADJOINT, precision), None, None
+
+
+def spectral_resample(x: torch.Tensor, modes_h: Tuple[int, int, int], grid: Tuple[int, int, int],
+                      precision: int = _cabi.PREC_AUTO) -> torch.Tensor:
+    """irfftn(rfftn(x)[..., :mx, :my, :mzh] zero-padded to `grid`'s half-spectrum, s=grid): one K1 + K3 pair with
+    different input and output grids.  Covers the reference's spectral down-sampling (rfno.py:119-130: modes = the whole
+    coarse half-spectrum), up-sampling (rfno.py:132-149: modes = the whole input half-spectrum) and the 2/3-rule
+    de-aliasing of the rollout loop (rational_fourier.py:392-412: same grid, modes = the retained box), without
+    materialising a full spectrum."""
+    return PrunedSynthesisFn.apply(PrunedAnalysisFn.apply(x, tuple(modes_h), precision), tuple(grid), precision)
+
+
 class RationalSpectralFn(torch.autograd.Function):
     """out = irfftn(StabilityProjection(R(k) mix(rfftn(x)[corner]))) [+ skip0 + x].
 

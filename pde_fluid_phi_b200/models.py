@@ -17,7 +17,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .functional import PointwiseLinearFn, pointwise_linear_supported
+from . import _cabi
+from .functional import PointwiseLinearFn, pointwise_linear_supported, spectral_resample
 from .operators import RationalFourierLayer, SpectralConv3D
 
 
@@ -123,38 +124,57 @@ class RationalFourierOperator3D(nn.Module):
         out = _lift(h, self.output_proj)
         return self.final_activation(out) if self.final_activation is not None else out
 
-    # ---- inference-time rollout (rational_fourier.py:284-412); same hot path, forward only -------
+    # ---- inference-time rollout (rational_fourier.py:284-412) ---------------------
+    # Same results as the reference loop, without its host round trips: the CFL timestep, the running time and the
+    # "target time reached" test stay on the device (the reference reads max|u| back with .item() once per step and
+    # the constraints read four metrics back per call), and the 2/3 de-aliasing is one pruned K1 + K3 pair instead of
+    # a full rfftn / irfftn.  Once the target time is reached the remaining iterations leave the state untouched
+    # (torch.where), which is what the reference's `break` does.
     def rollout(self, initial_condition: torch.Tensor, steps: int, return_trajectory: bool = False,
                 adaptive_timestep: bool = True, max_cfl: float = 0.5) -> torch.Tensor:
         state = initial_condition
         trajectory = [state.clone()] if return_trajectory else None
-        dt = total_time = target_time = 0.0
-        if adaptive_timestep:
-            dt = self._compute_adaptive_timestep(state, max_cfl)
-            target_time = steps * dt
+        if not adaptive_timestep:
+            for step in range(steps):
+                with (torch.no_grad() if step > 0 else torch.enable_grad()):
+                    state = self._apply_dealiasing(self.stability_constraints.apply(self.forward(state)))
+                    if return_trajectory:
+                        trajectory.append(state.clone())
+            return torch.stack(trajectory, dim=1) if return_trajectory else state
+
+        dt = self._adaptive_timestep(state, max_cfl)                 # float64 device scalars (the reference's Python floats)
+        target_time = steps * dt
+        total_time = torch.zeros_like(dt)
+        actives = []
         for step in range(steps):
-            if adaptive_timestep:
-                dt = min(dt, self._compute_adaptive_timestep(state, max_cfl))
-                if total_time >= target_time:
-                    break
-                if total_time + dt > target_time:
-                    dt = target_time - total_time
+            dt = torch.minimum(dt, self._adaptive_timestep(state, max_cfl))
+            active = total_time < target_time                        # the reference breaks out of the loop when this fails
+            dt = torch.where(total_time + dt > target_time, target_time - total_time, dt)
             with (torch.no_grad() if step > 0 else torch.enable_grad()):
-                state = self._rk4_step(state, dt) if (adaptive_timestep and step > 0) else self.forward(state)
-                state = self.stability_constraints.apply(state)
-                state = self._apply_dealiasing(state)
+                new = self._rk4_step(state, dt) if step > 0 else self.forward(state)
+                new = self._apply_dealiasing(self.stability_constraints.apply(new))
+                state = torch.where(active, new, state)
                 if return_trajectory:
                     trajectory.append(state.clone())
-            if adaptive_timestep:
-                total_time += dt
-        return torch.stack(trajectory, dim=1) if return_trajectory else state
+            total_time = torch.where(active, total_time + dt, total_time)
+            actives.append(active)
+        if return_trajectory:
+            # the reference's trajectory stops growing at the break: drop the frozen tail (one host read, after the loop)
+            taken = int(torch.stack(actives).sum()) if actives else 0
+            return torch.stack(trajectory[:1 + taken], dim=1)
+        return state
+
+    def _adaptive_timestep(self, u: torch.Tensor, max_cfl: float) -> torch.Tensor:
+        """CFL timestep as a float64 device scalar: max_cfl * dx / (max |u| + 1e-8), dx = 1 / Nx."""
+        with torch.no_grad():
+            u_max = torch.sqrt((u * u).sum(dim=1)).max().double()
+            return (max_cfl * (1.0 / u.shape[-3])) / (u_max + 1e-8)
 
     def _compute_adaptive_timestep(self, u: torch.Tensor, max_cfl: float) -> float:
-        with torch.no_grad():
-            u_max = float(torch.sqrt((u * u).sum(dim=1)).max())
-        return float(max_cfl * (1.0 / u.shape[-3]) / (u_max + 1e-8))
+        """Host-float variant with the reference's signature (rational_fourier.py:356-372); syncs."""
+        return float(self._adaptive_timestep(u, max_cfl))
 
-    def _rk4_step(self, u: torch.Tensor, dt: float) -> torch.Tensor:
+    def _rk4_step(self, u: torch.Tensor, dt) -> torch.Tensor:
         k1 = self.forward(u)
         k2 = self.forward(u + 0.5 * dt * k1)
         k3 = self.forward(u + 0.5 * dt * k2)
@@ -162,14 +182,14 @@ class RationalFourierOperator3D(nn.Module):
         return u + (dt / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
 
     def _apply_dealiasing(self, u: torch.Tensor) -> torch.Tensor:
-        """2/3 rule on the full spectrum (not part of the pruned hot path; rational_fourier.py:392-412)."""
+        """2/3 rule (rational_fourier.py:392-412): the reference zeroes every index >= 2N/3 of the half-spectrum, i.e.
+        it keeps the box [0, 2Nx/3) x [0, 2Ny/3) x [0, 2(Nz/2+1)/3) -- exactly a pruned analysis / synthesis pair."""
+        nx, ny, nz = u.shape[-3:]
+        keep = ((2 * nx) // 3, (2 * ny) // 3, (2 * (nz // 2 + 1)) // 3)
         with torch.no_grad():
-            u_ft = torch.fft.rfftn(u, dim=[-3, -2, -1])
-            nx, ny, nzh = u_ft.shape[-3:]
-            u_ft[:, :, (2 * nx) // 3:, :, :] = 0
-            u_ft[:, :, :, (2 * ny) // 3:, :] = 0
-            u_ft[:, :, :, :, (2 * nzh) // 3:] = 0
-            return torch.fft.irfftn(u_ft, s=u.shape[-3:], dim=[-3, -2, -1])
+            if not u.is_cuda or min(keep) < 1:
+                raise RuntimeError("rollout de-aliasing runs on the CUDA path only and needs at least a 2-point grid per axis")
+            return spectral_resample(u.float(), keep, (nx, ny, nz))
 
     def get_stability_monitor(self) -> dict:
         return self.stability_constraints.get_metrics()
@@ -228,3 +248,114 @@ class FNO3D(nn.Module):
                 if return_trajectory:
                     trajectory.append(state.clone())
         return torch.stack(trajectory, dim=1) if return_trajectory else state
+
+
+class RationalFNO(nn.Module):
+    """RationalFourierOperator3D plus a half-resolution branch, blended 0.7 / 0.3 (models/rfno.py:18-117; SURVEY.md
+    section 8f row N4 -- the model the reference's CLI trains by default).
+
+    Same constructor, sub-module names (``rational_fno``, ``coarse_processor``) and RNG order as the reference.  The
+    spectral down- and up-sampling of the coarse branch (rfno.py:119-149) are pruned K1 / K3 pairs with different
+    input and output grids (``functional.spectral_resample``) instead of full rfftn / irfftn round trips.
+    """
+
+    def __init__(self, modes: Tuple[int, int, int] = (32, 32, 32), width: int = 64, n_layers: int = 4, in_channels: int = 3,
+                 out_channels: int = 3, rational_order: Tuple[int, int] = (4, 4), activation: str = "gelu",
+                 final_activation: Optional[str] = None, stability_weight: float = 0.01, spectral_reg_weight: float = 0.001,
+                 multi_scale: bool = True, **kwargs):
+        super().__init__()
+        self.modes = modes
+        self.width = width
+        self.n_layers = n_layers
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.multi_scale = multi_scale
+        self.rational_fno = RationalFourierOperator3D(modes=modes, width=width, n_layers=n_layers, in_channels=in_channels,
+                                                      out_channels=out_channels, rational_order=rational_order,
+                                                      activation=activation, final_activation=final_activation)
+        if multi_scale:
+            self.coarse_modes = tuple(m // 2 for m in modes)
+            self.fine_modes = modes
+            self.coarse_processor = RationalFourierOperator3D(modes=self.coarse_modes, width=width // 2, n_layers=2,
+                                                              in_channels=in_channels, out_channels=out_channels,
+                                                              rational_order=(2, 2))
+        self.stability_constraints = StabilityConstraints(method="rational_decay", decay_rate=2.0, passivity_constraint=True,
+                                                          realizability=True)
+        self.stability_weight = stability_weight
+        self.spectral_reg_weight = spectral_reg_weight
+        self.training_metrics: Dict[str, float] = {}
+
+    def set_precision(self, precision: Optional[str]):
+        self.rational_fno.set_precision(precision)
+        if self.multi_scale:
+            self.coarse_processor.set_precision(precision)
+        return self
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        out = self.rational_fno(x)
+        if self.multi_scale:
+            coarse = self.coarse_processor(self._downsample(x, factor=2))
+            out = 0.7 * out + 0.3 * self._upsample(coarse, target_shape=tuple(x.shape[-3:]))
+        return self.stability_constraints.apply(out)
+
+    def _downsample(self, x: torch.Tensor, factor: int) -> torch.Tensor:
+        """Keep the [0, N/f) corner of the half-spectrum and invert it on the N/f grid (rfno.py:119-130)."""
+        nx, ny, nz = (n // factor for n in x.shape[-3:])
+        return spectral_resample(x, (nx, ny, nz // 2 + 1), (nx, ny, nz))
+
+    def _upsample(self, x: torch.Tensor, target_shape: Tuple[int, int, int]) -> torch.Tensor:
+        """Zero-pad the whole half-spectrum of x into the target grid's and invert there (rfno.py:132-149)."""
+        nx, ny, nz = x.shape[-3:]
+        return spectral_resample(x, (nx, ny, nz // 2 + 1), tuple(target_shape))
+
+    # ---- loss terms of the reference trainer (rfno.py:151-232): callers of the path, plain tensor ops ----
+    def compute_losses(self, predicted: torch.Tensor, target: torch.Tensor, input_field: torch.Tensor) -> Dict[str, torch.Tensor]:
+        losses = {"data": F.mse_loss(predicted, target), "divergence": self._divergence_loss(predicted),
+                  "energy_conservation": self._energy_conservation_loss(input_field, predicted),
+                  "spectral_reg": self._spectral_regularization(predicted)}
+        radius = self.stability_constraints.get_metrics()["spectral_radius"]
+        losses["stability"] = torch.tensor(radius, device=predicted.device, requires_grad=True)
+        losses["total"] = (losses["data"] + 0.1 * losses["divergence"] + 0.05 * losses["energy_conservation"]
+                           + self.spectral_reg_weight * losses["spectral_reg"] + self.stability_weight * losses["stability"])
+        return losses
+
+    @staticmethod
+    def _divergence_loss(u: torch.Tensor) -> torch.Tensor:
+        div = torch.gradient(u[:, 0], dim=-3)[0] + torch.gradient(u[:, 1], dim=-2)[0] + torch.gradient(u[:, 2], dim=-1)[0]
+        return div.pow(2).mean()
+
+    @staticmethod
+    def _energy_conservation_loss(u_initial: torch.Tensor, u_final: torch.Tensor) -> torch.Tensor:
+        e0 = 0.5 * u_initial.pow(2).sum(dim=(-3, -2, -1))
+        e1 = 0.5 * u_final.pow(2).sum(dim=(-3, -2, -1))
+        return ((e1 - e0).abs() / (e0 + 1e-8)).mean()
+
+    @staticmethod
+    def _spectral_regularization(u: torch.Tensor) -> torch.Tensor:
+        u_ft = torch.fft.rfftn(u, dim=[-3, -2, -1])
+        density = u_ft.abs().pow(2).sum(dim=1)
+        nx, ny, nz = u.shape[-3:]
+        kx, ky, kz = torch.meshgrid(torch.fft.fftfreq(nx, device=u.device), torch.fft.fftfreq(ny, device=u.device),
+                                    torch.fft.rfftfreq(nz, device=u.device), indexing="ij")
+        high = (torch.sqrt(kx ** 2 + ky ** 2 + kz ** 2) > min(nx, ny, nz) // 4).to(density.dtype)
+        return (density * high).sum() / (density.sum() + 1e-8)
+
+    def rollout(self, initial_condition: torch.Tensor, steps: int, return_trajectory: bool = False,
+                stability_check: bool = True) -> torch.Tensor:
+        state = initial_condition
+        trajectory = [state.clone()] if return_trajectory else None
+        for step in range(steps):
+            with torch.no_grad():
+                state = self.forward(state)
+                if stability_check and self.stability_constraints.get_metrics()["spectral_radius"] > 1.0:
+                    print(f"Warning: Unstable at step {step}")
+                    break
+                if return_trajectory:
+                    trajectory.append(state.clone())
+        return torch.stack(trajectory, dim=1) if return_trajectory else state
+
+    def get_stability_monitor(self) -> Dict[str, float]:
+        return self.stability_constraints.get_metrics()
+
+    def create_trainer(self, **kwargs):
+        return RationalFourierOperator3D.create_trainer(self, **kwargs)

@@ -183,5 +183,39 @@ def main():
               {"modes": (4, 4, 4), "n_layers": 2, "width": 8})
 
 
+def main_next_rows():
+    """Fixtures for the 'next' rows of SURVEY.md section 8f: the rollout loop (N3) and RationalFNO's coarse branch (N4)."""
+    from pde_fluid_phi.models.rfno import RationalFNO
+
+    # --- N4: RationalFNO with the spectral down / up-sampling branch ---------------------------
+    torch.manual_seed(1234)
+    model = RationalFNO(modes=(4, 4, 4), width=8, n_layers=2, rational_order=(3, 3), multi_scale=True)
+    torch.manual_seed(42)
+    save_case("rfno_model_w8_m4_l2_n16_multiscale", model, torch.randn(2, 3, 16, 16, 16),
+              {"modes": (4, 4, 4), "rational_order": (3, 3), "n_layers": 2, "width": 8})
+
+    # --- N3: rollout (RK4 + CFL timestep + constraints + 2/3 de-aliasing) ----------------------
+    torch.manual_seed(1234)
+    op = RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=2, rational_order=(3, 3))
+    torch.manual_seed(42)
+    x = torch.randn(2, 3, 12, 12, 12)
+    blob = {"x": to_np(x)}
+    for n, p in op.state_dict().items():
+        blob["sd:" + n] = to_np(p)
+    with torch.no_grad():
+        blob["traj_adaptive"] = to_np(op.rollout(x, steps=3, return_trajectory=True, adaptive_timestep=True))
+        blob["traj_fixed"] = to_np(op.rollout(x, steps=3, return_trajectory=True, adaptive_timestep=False))
+        blob["final_adaptive_cfl02"] = to_np(op.rollout(x, steps=4, adaptive_timestep=True, max_cfl=0.2))
+        blob["dealias"] = to_np(op._apply_dealiasing(x))
+    for k, v in {"modes": (4, 4, 4), "rational_order": (3, 3), "n_layers": 2, "width": 8}.items():
+        blob["meta:" + k] = np.asarray(v)
+    path = os.path.join(HERE, "rollout_rfno3d_w8_m4_l2_n12.npz")
+    np.savez_compressed(path, **blob)
+    print(f"rollout_rfno3d_w8_m4_l2_n12: trajectory {blob['traj_adaptive'].shape} ({os.path.getsize(path)/1024:.0f} KB)")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "next":
+        main_next_rows()
+    else:
+        main()

@@ -100,3 +100,29 @@ def test_monomial_table_is_exact():
     t = monomial_table(modes, 4).numpy()
     assert t.shape == (20, 6 * 4 * 5)
     assert np.array_equal(t.astype(np.float64), mono64.reshape(20, -1))
+
+
+def test_rational_fno_reproduces_reference_parameters():
+    """N4: same constructor / sub-module names / RNG order as models/rfno.py -> same weights under the same seed,
+    and the reference's state_dict loads strictly."""
+    z = load_golden("rfno_model_w8_m4_l2_n16_multiscale")
+    torch.manual_seed(1234)                                   # the seed tests/golden/make_golden.py used
+    model = pb.RationalFNO(modes=(4, 4, 4), width=8, n_layers=2, rational_order=(3, 3), multi_scale=True)
+    sd = model.state_dict()
+    ref = {k[3:]: v for k, v in z.items() if k.startswith("sd:")}
+    assert sorted(sd) == sorted(ref)
+    for k, v in ref.items():
+        assert np.array_equal(sd[k].numpy(), v), k
+    assert model.coarse_modes == (2, 2, 2) and model.coarse_processor.width == 4
+    with pytest.raises(RuntimeError):                         # CPU tensors are refused, never silently computed
+        model(torch.zeros(1, 3, 16, 16, 16))
+
+
+def test_rollout_fixture_is_self_consistent():
+    """N3 fixture sanity on CPU: frame 0 is the initial condition, and the reference's 2/3 de-aliasing equals the fp64
+    spec of a pruned analysis / synthesis pair on the [0, 2N/3) box (the mask is not Hermitian on the kz = 0 plane, so
+    this also pins the irfftn convention of dropping that plane's imaginary residue)."""
+    z = load_golden("rollout_rfno3d_w8_m4_l2_n12")
+    assert np.array_equal(z["traj_adaptive"][:, 0], z["x"]) and np.array_equal(z["traj_fixed"][:, 0], z["x"])
+    want = d64.synthesis(d64.analysis(z["x"].astype(np.float64), (8, 8, 4)), (12, 12, 12))
+    assert so.rel_l2(torch.from_numpy(z["dealias"]).double(), torch.from_numpy(np.asarray(want))) < 1e-6

@@ -187,3 +187,74 @@ def test_fno3d_fused_block_route_matches_unfused():
     assert rel(out_fused, out_ref) < 3e-3
     for n, p in model.named_parameters():
         assert rel(fused[n], p.grad) < 5e-3, n
+
+
+# ------------------------------------------------------------------------------------------------
+# "next" rows of SURVEY.md section 8f against fixtures produced by the unmodified reference (tests/golden/make_golden.py next)
+# ------------------------------------------------------------------------------------------------
+def _strict_fp32(fn):
+    """Whole-model 1e-5 comparisons: torch's own 1x1x1 convolution must not run in TF32."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        return fn()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_rational_fno_multiscale_vs_reference_golden():
+    """N4: RationalFNO with the spectral down / up-sampling branch, outputs and every gradient."""
+    from conftest import load_golden
+    z = load_golden("rfno_model_w8_m4_l2_n16_multiscale")
+    torch.manual_seed(0)
+    model = pb.RationalFNO(modes=tuple(int(v) for v in z["meta:modes"]), width=int(z["meta:width"]),
+                           n_layers=int(z["meta:n_layers"]), rational_order=tuple(int(v) for v in z["meta:rational_order"]))
+    sd = {k[3:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("sd:")}
+    missing = model.load_state_dict(sd, strict=True)          # same state-dict keys as the reference model
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model = model.to(DEV)
+    x = torch.from_numpy(z["x"]).to(DEV).requires_grad_(True)
+
+    def run():
+        out = model(x)
+        out.backward(torch.from_numpy(z["g"]).to(DEV))
+        return out
+    out = _strict_fp32(run)
+    rel = lambda a, b: float((a.detach().cpu().double() - torch.as_tensor(b).double()).norm() / torch.as_tensor(b).double().norm())
+    assert rel(out, z["out"]) < 1e-5
+    assert rel(x.grad, z["dx"]) < 1e-5
+    for name, p in model.named_parameters():
+        ref = z["grad:" + name]
+        if float(abs(ref).max()) == 0.0:
+            assert float(p.grad.abs().max()) == 0.0
+        else:
+            assert rel(p.grad, ref) < 5e-5, name
+
+
+def test_rollout_vs_reference_golden():
+    """N3: the sync-free rollout loop (RK4, CFL timestep, constraints, pruned 2/3 de-aliasing) reproduces the
+    reference's trajectories."""
+    from conftest import load_golden
+    z = load_golden("rollout_rfno3d_w8_m4_l2_n12")
+    model = pb.RationalFourierOperator3D(modes=tuple(int(v) for v in z["meta:modes"]), width=int(z["meta:width"]),
+                                         n_layers=int(z["meta:n_layers"]),
+                                         rational_order=tuple(int(v) for v in z["meta:rational_order"]))
+    model.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("sd:")})
+    model = model.to(DEV)
+    x = torch.from_numpy(z["x"]).to(DEV)
+    rel = lambda a, b: float((a.detach().cpu().double() - torch.as_tensor(b).double()).norm() / torch.as_tensor(b).double().norm())
+
+    def run():
+        with torch.no_grad():
+            assert rel(model._apply_dealiasing(x), z["dealias"]) < 1e-5
+            ta = model.rollout(x, steps=3, return_trajectory=True, adaptive_timestep=True)
+            tf = model.rollout(x, steps=3, return_trajectory=True, adaptive_timestep=False)
+            fa = model.rollout(x, steps=4, adaptive_timestep=True, max_cfl=0.2)
+        assert tuple(ta.shape) == z["traj_adaptive"].shape and tuple(tf.shape) == z["traj_fixed"].shape
+        # three chained model evaluations (x4 inside each RK4 step): allow the per-call 1e-5 to accumulate
+        assert rel(tf, z["traj_fixed"]) < 5e-5
+        assert rel(ta, z["traj_adaptive"]) < 5e-5
+        assert rel(fa, z["final_adaptive_cfl02"]) < 5e-5
+    _strict_fp32(run)
+    m = model.get_stability_monitor()
+    assert set(m) == {"spectral_radius", "energy_drift", "realizability_violations", "passivity_violations"}
