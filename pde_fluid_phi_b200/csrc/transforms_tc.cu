@@ -65,7 +65,7 @@ __global__ void tc_image_kernel(float* __restrict__ img, int kind, int R, int K,
 // ------------------------------------------------------------------------------------------------
 // analysis kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int A_THREADS = 192;
+constexpr int A_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..5 epi-1 (D1 -> B2), warps 6..9 epi-2 (D2 -> T2)
 struct ASmem {
   uint32_t a1[2], b1, a2, b2, e, bars, tmem_slot, total;
 };
@@ -83,8 +83,8 @@ __host__ __device__ inline ASmem analysis_smem(int NKB) {
   s.total = o;
   return s;
 }
-enum { AB_FULL0 = 0, AB_FULL1, AB_EMPTY0, AB_EMPTY1, AB_D1FULL0, AB_D1FULL1, AB_D1EMPTY0, AB_D1EMPTY1, AB_B2FULL, AB_D2FULL,
-       AB_D2EMPTY };
+enum { AB_FULL0 = 0, AB_FULL1, AB_EMPTY0, AB_EMPTY1, AB_D1FULL0, AB_D1FULL1, AB_D1EMPTY0, AB_D1EMPTY1, AB_B2FULL, AB_B2EMPTY,
+       AB_D2FULL0, AB_D2FULL1, AB_D2EMPTY0, AB_D2EMPTY1 };
 
 __global__ void __launch_bounds__(A_THREADS, 1)
 analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __restrict__ T2, const float* __restrict__ B1img,
@@ -114,8 +114,9 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
     mbar_init(bar(AB_EMPTY0), 1); mbar_init(bar(AB_EMPTY1), 1);
     mbar_init(bar(AB_D1FULL0), 1); mbar_init(bar(AB_D1FULL1), 1);
     mbar_init(bar(AB_D1EMPTY0), 128); mbar_init(bar(AB_D1EMPTY1), 128);
-    mbar_init(bar(AB_B2FULL), 128);
-    mbar_init(bar(AB_D2FULL), 1); mbar_init(bar(AB_D2EMPTY), 128);
+    mbar_init(bar(AB_B2FULL), 128); mbar_init(bar(AB_B2EMPTY), 1);
+    mbar_init(bar(AB_D2FULL0), 1); mbar_init(bar(AB_D2FULL1), 1);
+    mbar_init(bar(AB_D2EMPTY0), 128); mbar_init(bar(AB_D2EMPTY1), 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(base + L.tmem_slot, 256);
@@ -124,7 +125,8 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
-  const uint32_t tmem_d1[2] = {tmem, tmem + 64}, tmem_d2 = tmem + 128;   // D1 double buffered: GEMM1 runs a plane ahead
+  // D1 and D2 double buffered: GEMM1 runs a plane ahead, and the two epilogue warpgroups work on different planes
+  const uint32_t tmem_d1[2] = {tmem, tmem + 64}, tmem_d2[2] = {tmem + 128, tmem + 192};
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -161,27 +163,27 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
       for (int it = 0; it < n_my; ++it) {
         if (it + 1 < n_my) gemm1(it + 1);            // z stage of the next plane overlaps this plane's epilogues
         mbar_wait(bar(AB_B2FULL), it & 1);
-        mbar_wait(bar(AB_D2EMPTY), (it & 1) ^ 1);
+        mbar_wait(bar(AB_D2EMPTY0 + (it & 1)), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            mma_ss(tmem_d2, umma_desc(base + L.a2 + kb * M2 * 128 + k * 32, 1024),
+            mma_ss(tmem_d2[it & 1], umma_desc(base + L.a2 + kb * M2 * 128 + k * 32, 1024),
                    umma_desc(base + L.b2 + kb * ROWS_B * 128 + k * 32, 1024), id2, (kb | k) ? 1u : 0u);
-        mma_commit(bar(AB_D2FULL));
+        mma_commit(bar(AB_B2EMPTY));                  // B2 consumed: epi-1 of the next plane may overwrite it
+        mma_commit(bar(AB_D2FULL0 + (it & 1)));
       }
     }
-  } else {
-    // ===== epilogue warps (2..5): TMEM quarter q = warp % 4 =====
+  } else if (warp < 6) {
+    // ===== epi-1 warps (2..5), TMEM quarter q = warp % 4: D1 row y = 32q+lane -> B2[c][y] =====
+    // (a separate warpgroup from epi-2: with one group doing both, epi-1 -> GEMM2 -> epi-2 of a plane was a serial chain
+    //  of ~2 us per plane on four warps, longer than the plane's 1.5 us of HBM time)
     const int q = warp & 3;
-    const int et = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float* E = reinterpret_cast<float*>(sm + L.e);
     const int ncol = 2 * mzh;
     int it = 0;
     for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
-      // ---- epi-1: D1 row y = 32q+lane -> B2[c][y] ------------------------------------------------
       mbar_wait(bar(AB_D1FULL0 + (it & 1)), (it >> 1) & 1);
       tc_fence_after();
       float v[40];
@@ -190,6 +192,7 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar(AB_D1EMPTY0 + (it & 1)));
+      mbar_wait(bar(AB_B2EMPTY), (it & 1) ^ 1);       // GEMM2 of the previous plane has read B2
       {
         uint8_t* b2 = sm + L.b2 + q * (ROWS_B * 128);   // k-block q holds y in [32q, 32q+32)
         const uint32_t kin = (uint32_t)(lane & 3) * 4;
@@ -204,14 +207,23 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar(AB_B2FULL));
-      // ---- epi-2: D2 rows 16q..16q+15 (lanes 0..15 of this quarter) -> E -> combine -> T2 ----------
-      mbar_wait(bar(AB_D2FULL), it & 1);
+    }
+  } else {
+    // ===== epi-2 warps (6..9): D2 rows 16q..16q+15 (lanes 0..15 of this quarter) -> E -> combine -> T2 =====
+    const int q = warp & 3;
+    const int et = (warp - 6) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* E = reinterpret_cast<float*>(sm + L.e);
+    int it = 0;
+    for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
+      mbar_wait(bar(AB_D2FULL0 + (it & 1)), (it >> 1) & 1);
       tc_fence_after();
-      tmem_ld32(tmem_d2 + lane_base, v);
-      tmem_ld8(tmem_d2 + lane_base + 32, v + 32);
+      float v[40];
+      tmem_ld32(tmem_d2[it & 1] + lane_base, v);
+      tmem_ld8(tmem_d2[it & 1] + lane_base + 32, v + 32);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bar(AB_D2EMPTY));
+      mbar_arrive(bar(AB_D2EMPTY0 + (it & 1)));
       epi_bar_sync();                                   // previous plane's readers of E are done
       if (lane < 16) {
         float* er = E + (16 * q + lane) * E_LD;
