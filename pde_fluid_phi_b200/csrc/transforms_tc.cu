@@ -248,9 +248,14 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
 
 // ------------------------------------------------------------------------------------------------
 // synthesis kernel
-//   warp 0: MMA issuer + TMEM owner, warps 2..9: epilogue (TMEM quarter = warp % 4, column half = (warp-2)/4),
-//   warps 10..13: By builders.  The epilogue warps keep ~64 KB of addend loads in flight per SM; the builders
-//   issue all their loads of a plane before the first store (a serial load->store loop was the kernel's bound).
+//   warp 0: MMA issuer + TMEM owner, warps 2..9: epilogue (TMEM quarter = warp % 4, plane parity = (warp-2)/4),
+//   warps 10..13: By builders.  The builders issue all their loads of a plane before the first store (a serial
+//   load->store loop was the kernel's bound).
+//   Per plane the epilogue moves 64 KB out of TMEM (64 B/clk), through the shared-memory transpose (64 KB in + 64 KB
+//   out at 128 B/clk) and into the store path: ~2600 clocks of SM-internal data movement against ~2900 clocks of HBM
+//   time.  With all eight warps on the same plane those phases ran one after the other (measured: MMA pipeline alone
+//   0.39 ms, + staging 0.69 ms, + stores 0.91 ms); two groups of four warps on alternate planes (one output
+//   accumulator each) keep the TMEM port, the shared-memory port and the store path busy at the same time.
 // ------------------------------------------------------------------------------------------------
 constexpr int S_EPI_WARPS = 8;
 constexpr int S_BUILD_WARPS = 4;
@@ -276,7 +281,7 @@ enum { SB_BYFULL0 = 0, SB_BYFULL1, SB_BYEMPTY0, SB_BYEMPTY1, SB_DVFULL, SB_OUTFU
 
 __device__ __forceinline__ float4 ldg_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 
-template <int NZ>
+template <int NZ, int NADD>   // NADD: number of fused addends (0, 1: add0 only, 2)
 __global__ void __launch_bounds__(S_THREADS, 1)
 synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, const float* __restrict__ add0,
                        const float* __restrict__ add1, const float* __restrict__ Ayimg, const float* __restrict__ Bzimg,
@@ -301,11 +306,11 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
     for (int i = threadIdx.x; i < 2 * 2 * ROWS_B * 128 / 16; i += S_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (threadIdx.x == 0) {
-    mbar_init(bar(SB_BYFULL0), 32 * S_BUILD_WARPS); mbar_init(bar(SB_BYFULL1), 32 * S_BUILD_WARPS);
+    mbar_init(bar(SB_BYFULL0), S_BUILD_WARPS); mbar_init(bar(SB_BYFULL1), S_BUILD_WARPS);   // one arrival per warp
     mbar_init(bar(SB_BYEMPTY0), 1); mbar_init(bar(SB_BYEMPTY1), 1);
     mbar_init(bar(SB_DVFULL), 1);
     mbar_init(bar(SB_OUTFULL0), 1); mbar_init(bar(SB_OUTFULL1), 1);
-    mbar_init(bar(SB_OUTEMPTY0), S_EPI_WARPS * 32); mbar_init(bar(SB_OUTEMPTY0 + 1), S_EPI_WARPS * 32);
+    mbar_init(bar(SB_OUTEMPTY0), S_EPI_WARPS / 2); mbar_init(bar(SB_OUTEMPTY0 + 1), S_EPI_WARPS / 2);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(base + L.tmem_slot, 512);
@@ -380,55 +385,68 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
         }
       }
       fence_proxy_async();
-      mbar_arrive(bar(SB_BYFULL0 + b));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(SB_BYFULL0 + b));
     }
   } else if (warp >= 2) {
-    // ===== epilogue warps =====
-    constexpr int CW = NZ / 2;                 // columns per warp (64 or 32)
+    // ===== epilogue warps: quarter q = warp % 4 (32 rows), group = (warp - 2) / 4 takes the planes of that parity =====
+    constexpr int CW = NZ / 2;                 // columns per round (64 or 32); two rounds per plane
     constexpr int LD = CW + 4;                 // padded staging row
     constexpr int LPR = CW / 4;                // lanes per output row (one float4 each)
     constexpr int RPI = 32 / LPR;              // rows per warp-wide instruction (2 or 4)
     constexpr int NIT = 32 / RPI;              // 16 or 8
     constexpr int G = 8;                       // row instructions whose addend loads are issued together
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, grp = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float* st = reinterpret_cast<float*>(sm + L.stage) + (warp - 2) * 32 * LD;
     const int rsub = lane / LPR, c4 = lane % LPR;
-    int it = 0;
-    for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
-      const int b = it & 1;
-      mbar_wait(bar(SB_OUTFULL0 + b), (it >> 1) & 1);
+    const int n_my = blockIdx.x < planes ? (planes - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    for (int it = grp; it < n_my; it += 2) {
+      const int p = blockIdx.x + it * gridDim.x;
+      mbar_wait(bar(SB_OUTFULL0 + grp), (it >> 1) & 1);
       tc_fence_after();
-      float v[CW];
-      tmem_ld32(tmem_out[b] + lane_base + half * CW, v);
-      if (CW == 64) tmem_ld32(tmem_out[b] + lane_base + half * CW + 32, v + (CW == 64 ? 32 : 0));
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(bar(SB_OUTEMPTY0 + b));
-      __syncwarp();
 #pragma unroll
-      for (int j = 0; j < CW / 4; ++j)
-        *reinterpret_cast<float4*>(st + lane * LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      __syncwarp();
-      const size_t gbase = (size_t)p * 128 * NZ + (size_t)(32 * q + rsub) * NZ + half * CW + 4 * c4;
+      for (int r = 0; r < 2; ++r) {
+        const size_t gbase = (size_t)p * 128 * NZ + (size_t)(32 * q + rsub) * NZ + r * CW + 4 * c4;
+        // addend loads of the first group of rows are issued before the TMEM read, those of the next group before the
+        // current group is consumed (NADD = 1: two register sets): their latency overlaps the on-chip data movement
+        float4 a0v[NADD == 1 ? 2 : 1][G], a1v[G];
+        auto load_addends = [&](int g0, int set) {
 #pragma unroll
-      for (int g0 = 0; g0 < NIT; g0 += G) {
-        float4 a0v[G], a1v[G];
-#pragma unroll
-        for (int j = 0; j < G; ++j) {
-          const size_t g = gbase + (size_t)((g0 + j) * RPI) * NZ;
-          a0v[j] = add0 ? ldg_stream(add0 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-          a1v[j] = add1 ? ldg_stream(add1 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < G; ++j) {
+            const size_t g = gbase + (size_t)((g0 + j) * RPI) * NZ;
+            if (NADD >= 1) a0v[set][j] = ldg_stream(add0 + g);
+            if (NADD == 2) a1v[j] = ldg_stream(add1 + g);
+          }
+        };
+        if (NADD) load_addends(0, 0);
+        float v[CW];
+        tmem_ld32(tmem_out[grp] + lane_base + r * CW, v);
+        if (CW == 64) tmem_ld32(tmem_out[grp] + lane_base + r * CW + 32, v + (CW == 64 ? 32 : 0));
+        tmem_ld_wait();
+        if (r == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(SB_OUTEMPTY0 + grp));
         }
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-          const int row = (g0 + j) * RPI + rsub;
-          float4 o = *reinterpret_cast<const float4*>(st + row * LD + 4 * c4);
-          o.x = (o.x + a0v[j].x) + a1v[j].x;
-          o.y = (o.y + a0v[j].y) + a1v[j].y;
-          o.z = (o.z + a0v[j].z) + a1v[j].z;
-          o.w = (o.w + a0v[j].w) + a1v[j].w;
-          __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)((g0 + j) * RPI) * NZ), o);
+        for (int j = 0; j < CW / 4; ++j)
+          *reinterpret_cast<float4*>(st + lane * LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int g0 = 0; g0 < NIT; g0 += G) {
+          const int set = (NADD == 1) ? ((g0 / G) & 1) : 0;
+          if (NADD == 1 && g0 + G < NIT) load_addends(g0 + G, set ^ 1);
+          if (NADD == 2 && g0) load_addends(g0, 0);
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const int row = (g0 + j) * RPI + rsub;
+            float4 o = *reinterpret_cast<const float4*>(st + row * LD + 4 * c4);
+            if (NADD >= 1) { o.x += a0v[set][j].x; o.y += a0v[set][j].y; o.z += a0v[set][j].z; o.w += a0v[set][j].w; }
+            if (NADD == 2) { o.x += a1v[j].x; o.y += a1v[j].y; o.z += a1v[j].z; o.w += a1v[j].w; }
+            __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)((g0 + j) * RPI) * NZ), o);
+          }
         }
       }
     }
@@ -570,17 +588,21 @@ int synthesis_tc(const Plan* p, const float2* Z, float* out, const float* add0, 
   const tc::SSmem L = tc::synthesis_smem(p->Nz);
   const size_t smem = L.total + 1024;
   const int grid = (int)(planes < (size_t)p->num_sms ? planes : (size_t)p->num_sms);
-  if (p->Nz == 128) {
-    auto k = tc::synthesis_zy_tc_kernel<128>;
-    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_SYNTHESIS_ZY_TC, st);
-    k<<<grid, tc::S_THREADS, smem, st>>>(ws, out, add0, add1, p->tc_ay, p->tc_bz[direction], (int)planes, p->my, p->mzh);
-  } else {
-    auto k = tc::synthesis_zy_tc_kernel<64>;
-    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_SYNTHESIS_ZY_TC, st);
-    k<<<grid, tc::S_THREADS, smem, st>>>(ws, out, add0, add1, p->tc_ay, p->tc_bz[direction], (int)planes, p->my, p->mzh);
+  if (add1 && !add0) { add0 = add1; add1 = nullptr; }
+  const int nadd = (add0 ? 1 : 0) + (add1 ? 1 : 0);
+#define PDEPHI_SYN_LAUNCH(NZV, NA)                                                                                          \
+  {                                                                                                                         \
+    auto k = tc::synthesis_zy_tc_kernel<NZV, NA>;                                                                           \
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                           \
+    ProfScope ps(K_SYNTHESIS_ZY_TC, st);                                                                                    \
+    k<<<grid, tc::S_THREADS, smem, st>>>(ws, out, add0, add1, p->tc_ay, p->tc_bz[direction], (int)planes, p->my, p->mzh); \
   }
+  if (p->Nz == 128) {
+    if (nadd == 0) PDEPHI_SYN_LAUNCH(128, 0) else if (nadd == 1) PDEPHI_SYN_LAUNCH(128, 1) else PDEPHI_SYN_LAUNCH(128, 2)
+  } else {
+    if (nadd == 0) PDEPHI_SYN_LAUNCH(64, 0) else if (nadd == 1) PDEPHI_SYN_LAUNCH(64, 1) else PDEPHI_SYN_LAUNCH(64, 2)
+  }
+#undef PDEPHI_SYN_LAUNCH
   PDEPHI_LAUNCH_CHECK("synthesis_zy_tc_kernel");
   return PDEPHI_OK;
 }

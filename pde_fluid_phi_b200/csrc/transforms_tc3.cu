@@ -371,7 +371,7 @@ enum { S3_BYFULL = 0, S3_BYEMPTY = 2, S3_VFULL = 4, S3_VLOFULL = 6, S3_OUTFULL =
 
 __device__ __forceinline__ float4 ldg_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 
-template <int NZ>
+template <int NZ, int NADD>   // NADD: number of fused addends (0, 1: add0 only, 2)
 __global__ void __launch_bounds__(S3_THREADS, 1)
 synthesis_zy_tc3_kernel(const float2* __restrict__ U, float* __restrict__ out, const float* __restrict__ add0,
                         const float* __restrict__ add1, const float* __restrict__ Ayhi, const float* __restrict__ Aylo,
@@ -401,12 +401,12 @@ synthesis_zy_tc3_kernel(const float2* __restrict__ U, float* __restrict__ out, c
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(S3_BYFULL + i), 32 * S_BUILD_WARPS);
+      mbar_init(bar(S3_BYFULL + i), S_BUILD_WARPS);
       mbar_init(bar(S3_BYEMPTY + i), 1);
       mbar_init(bar(S3_VFULL + i), 1);
       mbar_init(bar(S3_VLOFULL + i), 32 * S_SPLIT_WARPS);
       mbar_init(bar(S3_OUTFULL + i), 1);
-      mbar_init(bar(S3_OUTEMPTY + i), S_EPI_WARPS * 32);
+      mbar_init(bar(S3_OUTEMPTY + i), S_EPI_WARPS / 2);
     }
     fence_barrier_init();
   }
@@ -527,51 +527,54 @@ synthesis_zy_tc3_kernel(const float2* __restrict__ U, float* __restrict__ out, c
         }
       }
       fence_proxy_async();
-      mbar_arrive(bar(S3_BYFULL + b));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(S3_BYFULL + b));
     }
   } else if (warp >= 2) {
-    // ===== epilogue warps: 32 rows x (NZ/2) columns each, in rounds of 32 columns =====
-    constexpr int CW = NZ / 2;                 // columns per warp (64 or 32)
-    constexpr int ROUNDS = CW / 32;
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // ===== epilogue warps: quarter q = warp % 4 (32 rows), group = (warp - 2) / 4 takes the planes of that parity; a plane
+    //       goes out in rounds of 32 columns (see transforms_tc.cu for why the two groups work on different planes) =====
+    constexpr int ROUNDS = NZ / 32;
+    constexpr int G = 8;                         // 8 lanes (one float4 each) per 32-column row segment, 4 rows per instruction
+    const int q = warp & 3, grp = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float* st = reinterpret_cast<float*>(sm + L.stage) + (warp - 2) * 32 * ST_LD;
-    const int rsub = lane >> 3, c4 = lane & 7;   // 8 lanes (one float4 each) per 32-column row segment, 4 rows per instruction
-    int it = 0;
-    for (int p = blockIdx.x; p < planes; p += gridDim.x, ++it) {
-      const int b = it & 1;
-      mbar_wait(bar(S3_OUTFULL + b), (uint32_t)((it >> 1) & 1));
+    const int rsub = lane >> 3, c4 = lane & 7;
+    const int n_my = blockIdx.x < planes ? (planes - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    for (int it = grp; it < n_my; it += 2) {
+      const int p = blockIdx.x + it * gridDim.x;
+      mbar_wait(bar(S3_OUTFULL + grp), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
 #pragma unroll
       for (int r = 0; r < ROUNDS; ++r) {
+        const size_t gbase = (size_t)p * 128 * NZ + (size_t)(32 * q + rsub) * NZ + r * 32 + 4 * c4;
+        float4 a0v[G], a1v[G];
+        if (NADD) {                              // addend loads are in flight during the TMEM read and the transpose
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const size_t g = gbase + (size_t)(j * 4) * NZ;
+            a0v[j] = ldg_stream(add0 + g);
+            if (NADD == 2) a1v[j] = ldg_stream(add1 + g);
+          }
+        }
         float v[32];
-        tmem_ld32(tmem_out[b] + lane_base + half * CW + r * 32, v);
+        tmem_ld32(tmem_out[grp] + lane_base + r * 32, v);
         tmem_ld_wait();
         if (r == ROUNDS - 1) {
           tc_fence_before();
-          mbar_arrive(bar(S3_OUTEMPTY + b));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(S3_OUTEMPTY + grp));
         }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        const size_t gbase = (size_t)p * 128 * NZ + (size_t)(32 * q + rsub) * NZ + half * CW + r * 32 + 4 * c4;
-        float4 a0v[8], a1v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const size_t g = gbase + (size_t)(j * 4) * NZ;
-          a0v[j] = add0 ? ldg_stream(add0 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-          a1v[j] = add1 ? ldg_stream(add1 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < G; ++j) {
           const int row = j * 4 + rsub;
           float4 o = *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
-          o.x = (o.x + a0v[j].x) + a1v[j].x;
-          o.y = (o.y + a0v[j].y) + a1v[j].y;
-          o.z = (o.z + a0v[j].z) + a1v[j].z;
-          o.w = (o.w + a0v[j].w) + a1v[j].w;
+          if (NADD >= 1) { o.x += a0v[j].x; o.y += a0v[j].y; o.z += a0v[j].z; o.w += a0v[j].w; }
+          if (NADD == 2) { o.x += a1v[j].x; o.y += a1v[j].y; o.z += a1v[j].z; o.w += a1v[j].w; }
           __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)(j * 4) * NZ), o);
         }
       }
@@ -691,19 +694,22 @@ int synthesis_tc3(const Plan* p, const float2* Z, float* out, const float* add0,
   if (planes > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis_tc3: too many planes");
   const size_t smem = tc3::s3_smem(p->Nz).total + 1024;
   const int grid = (int)(planes < (size_t)p->num_sms ? planes : (size_t)p->num_sms);
-  if (p->Nz == 128) {
-    auto k = tc3::synthesis_zy_tc3_kernel<128>;
-    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_SYNTHESIS_ZY_TC3, st);
-    k<<<grid, tc3::S3_THREADS, smem, st>>>(ws, out, add0, add1, p->tc3_ay[0], p->tc3_ay[1], p->tc3_bz[direction][0],
-                                           p->tc3_bz[direction][1], (int)planes, p->my, p->mzh);
-  } else {
-    auto k = tc3::synthesis_zy_tc3_kernel<64>;
-    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_SYNTHESIS_ZY_TC3, st);
-    k<<<grid, tc3::S3_THREADS, smem, st>>>(ws, out, add0, add1, p->tc3_ay[0], p->tc3_ay[1], p->tc3_bz[direction][0],
-                                           p->tc3_bz[direction][1], (int)planes, p->my, p->mzh);
+  if (add1 && !add0) { add0 = add1; add1 = nullptr; }
+  const int nadd = (add0 ? 1 : 0) + (add1 ? 1 : 0);
+#define PDEPHI_SYN3_LAUNCH(NZV, NA)                                                                                     \
+  {                                                                                                                     \
+    auto k = tc3::synthesis_zy_tc3_kernel<NZV, NA>;                                                                     \
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
+    ProfScope ps(K_SYNTHESIS_ZY_TC3, st);                                                                               \
+    k<<<grid, tc3::S3_THREADS, smem, st>>>(ws, out, add0, add1, p->tc3_ay[0], p->tc3_ay[1], p->tc3_bz[direction][0],    \
+                                           p->tc3_bz[direction][1], (int)planes, p->my, p->mzh);                        \
   }
+  if (p->Nz == 128) {
+    if (nadd == 0) PDEPHI_SYN3_LAUNCH(128, 0) else if (nadd == 1) PDEPHI_SYN3_LAUNCH(128, 1) else PDEPHI_SYN3_LAUNCH(128, 2)
+  } else {
+    if (nadd == 0) PDEPHI_SYN3_LAUNCH(64, 0) else if (nadd == 1) PDEPHI_SYN3_LAUNCH(64, 1) else PDEPHI_SYN3_LAUNCH(64, 2)
+  }
+#undef PDEPHI_SYN3_LAUNCH
   PDEPHI_LAUNCH_CHECK("synthesis_zy_tc3_kernel");
   return PDEPHI_OK;
 }

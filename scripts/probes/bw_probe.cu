@@ -49,6 +49,22 @@ __global__ void __launch_bounds__(512, 1) read_kernel(const float* __restrict__ 
   }
   if (acc == 123.456f) sink[0] = acc;
 }
+// write-only: THREADS per CTA, each warp instruction stores 512 contiguous bytes (the synthesis epilogue's store shape)
+__global__ void write_kernel(float4* __restrict__ c, size_t n4) {
+  const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) __stcs(c + i, v);
+}
+// plane-wise: CTA b writes plane p = b, b + grid, ... of 64 KB; each of the 8 warps writes 2 rows x 256 B per instruction
+__global__ void __launch_bounds__(256, 1) write_plane_kernel(float* __restrict__ c, long long planes) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, half = warp >> 2, rsub = lane >> 4, c4 = lane & 15;
+  const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+  for (long long p = blockIdx.x; p < planes; p += gridDim.x) {
+    float* base = c + (size_t)p * 128 * 128 + (size_t)(32 * q + rsub) * 128 + half * 64 + 4 * c4;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) __stcs(reinterpret_cast<float4*>(base + (size_t)(2 * g) * 128), v);
+  }
+}
 template <int NR, int NW>
 __global__ void flat_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ c, float4* __restrict__ d, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -85,6 +101,12 @@ int main() {
 #define READ(SEG, GRID) { long long tpb = S / 128, nt = tpb * B; float ms = time_ms([&] { read_kernel<SEG, 4><<<GRID, 512>>>(a, c, S, nt, tpb); }); \
     printf("read-only SEG=%3d grid=%4d: %.3f ms  %.0f GB/s\n", SEG, GRID, ms, gb / ms * 1e3); }
   READ(512, 148) READ(128, 148) READ(512, 296) READ(128, 296) READ(512, 592) READ(128, 592)
+  { const size_t n4 = n / 4; for (int g : {148, 296, 592, 2368}) for (int th : {256, 512, 1024}) {
+      float ms = time_ms([&] { write_kernel<<<g, th>>>((float4*)c, n4); });
+      printf("write-only flat grid=%4d threads=%4d: %.3f ms  %.0f GB/s\n", g, th, ms, gb / ms * 1e3); } }
+  { const long long planes = (long long)(n / (128 * 128)); for (int g : {148, 296}) {
+      float ms = time_ms([&] { write_plane_kernel<<<g, 256>>>(c, planes); });
+      printf("write-only planes grid=%4d: %.3f ms  %.0f GB/s\n", g, ms, gb / ms * 1e3); } }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status %s\n", cudaGetErrorString(e));
   return 0;
