@@ -248,11 +248,34 @@ def run_native(args):
             gparam["lr"] = min(1.0, (state["n"] + 1) / 1e5) * 1e-3
         return loss
 
+    # End-to-end leg: every step copies its own inputs from pinned host memory (2 x 201 MB) and reads the loss back.
+    # The copies run on a side stream into the buffer pair the *next* step will use, as a prefetching data loader
+    # does, so they overlap the current step's kernels; the first step's copy is not overlapped and is inside the
+    # timed region like all the others.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dbuf = [(torch.empty_like(x), torch.empty_like(y)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"i": 0, "primed": False}
+
+    def _prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])           # the step that last read this pair has finished with it
+            dbuf[slot][0].copy_(hx, non_blocking=True)
+            dbuf[slot][1].copy_(hy, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     def step_e2e():
-        xd = hx.to(dev, non_blocking=True)
-        yd = hy.to(dev, non_blocking=True)
-        loss = step(xd, yd)
+        i = e2e_state["i"]
+        if not e2e_state["primed"]:
+            _prefetch(i & 1)
+            e2e_state["primed"] = True
+        _prefetch((i + 1) & 1)                               # next step's inputs, overlapped with this step
+        torch.cuda.current_stream().wait_event(ready[i & 1])
+        loss = step(dbuf[i & 1][0], dbuf[i & 1][1])
+        consumed[i & 1].record(torch.cuda.current_stream())
         h_loss.copy_(loss.detach(), non_blocking=True)
+        e2e_state["i"] = i + 1
         return loss
 
     def barrier():
@@ -288,7 +311,11 @@ def run_native(args):
     _cabi.profile(enable=False, reset=True)
     clocks = sampler.stop() if rank == 0 else {}
     # ---- timed region 2: end to end, host buffers ----------------------------------------------------
-    step_e2e()
+    for ev in consumed:
+        ev.record(torch.cuda.current_stream())
+    step_e2e()                                               # untimed warm-up of the copy path
+    torch.cuda.synchronize()
+    e2e_state["primed"] = False                              # the timed region starts with nothing prefetched
     e2e_ms = timed(step_e2e, args.steps)
     final_loss = float(h_loss)
 

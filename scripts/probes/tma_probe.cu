@@ -56,6 +56,70 @@ tma_kernel(const __grid_constant__ CUtensorMap map, float* sink, long long ntile
   }
 }
 
+// the same ring fed by cp.async loader warps (block_tc.cu): NLW warps, each warp instruction = one 512-byte row
+template <int STAGES, int NLW, int NCONS, int HINT>
+__global__ void __launch_bounds__(32 * (NLW + NCONS), 1)
+cpasync_kernel(const float* __restrict__ a, float* sink, long long S, long long ntiles, long long tiles_per_batch) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  constexpr uint32_t TILEB = 64 * 512;      // 64 rows x 128 points
+  const uint32_t bars = base + STAGES * TILEB;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (STAGES + i); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full(i), NLW * 32); mbar_init(empty(i), NCONS); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (warp < NLW) {
+    constexpr int RPW = 64 / NLW;
+    for (long long it = 0; it < my_tiles + (STAGES - 1); ++it) {
+      if (it < my_tiles) {
+        const long long t = blockIdx.x + it * gridDim.x;
+        const int s = (int)(it % STAGES);
+        mbar_wait(empty(s), (uint32_t)(((it / STAGES) & 1) ^ 1));
+        const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * 128;
+        const float* src = a + ((size_t)b * 64 + warp * RPW) * S + s0 + lane * 4;
+        const uint32_t dst = base + s * TILEB + (warp * RPW) * 512 + lane * 16;
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          if (HINT == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + (size_t)i * S) : "memory");
+          if (HINT == 1) asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + (size_t)i * S) : "memory");
+          if (HINT == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + (size_t)i * S) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (it >= STAGES - 1) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        fence_proxy_async();
+        mbar_arrive(full((int)((it - (STAGES - 1)) % STAGES)));
+      }
+    }
+  } else {
+    for (long long it = 0; it < my_tiles; ++it) {
+      const int s = (int)(it % STAGES);
+      mbar_wait(full(s), (uint32_t)((it / STAGES) & 1));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty(s));
+    }
+  }
+  if (threadIdx.x == 12345) sink[0] = 0.f;
+}
+template <int STAGES, int NLW, int NCONS, int HINT>
+void run_cp(const char* name, const float* a, float* sink, long long rows, long long S, int grid = 148) {
+  const long long tpb = S / 128, ntiles = tpb * (rows / 64);
+  auto k = cpasync_kernel<STAGES, NLW, NCONS, HINT>;
+  const int smem = STAGES * 64 * 512 + 1024 + 256;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  float ms = time_ms([&] { k<<<grid, 32 * (NLW + NCONS), smem>>>(a, sink, S, ntiles, tpb); });
+  cudaError_t e = cudaGetLastError();
+  printf("%-58s loaders %2d stages %d: %.3f ms  %.0f GB/s %s\n", name, NLW, STAGES, ms, rows * S * 4 / 1e9 / ms * 1e3,
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -116,6 +180,15 @@ int main() {
   run<64, 4, 3, 4, true, 1>("block-tail tile, consumers read smem", a, sink, rows, S, 64, SW, L2);
   run<64, 4, 3, 4, false, 1>("block-tail tile, grid 296 (2 CTAs/SM)", a, sink, rows, S, 64, SW, L2, 296);
   run<64, 2, 3, 4, false, 1>("half tile (64 pts), grid 592 (4 CTAs/SM)", a, sink, rows, S, 64, SW, L2, 592);
+  run_cp<3, 4, 4, 1>("cp.async ring, .cg L2::256B", a, sink, rows, S);
+  run_cp<6, 4, 4, 1>("cp.async ring, .cg L2::256B", a, sink, rows, S);
+  run_cp<6, 8, 4, 1>("cp.async ring, .cg L2::256B", a, sink, rows, S);
+  run_cp<6, 16, 4, 1>("cp.async ring, .cg L2::256B", a, sink, rows, S);
+  run_cp<6, 8, 4, 0>("cp.async ring, .cg", a, sink, rows, S);
+  run_cp<6, 8, 4, 2>("cp.async ring, .ca", a, sink, rows, S);
+  run_cp<3, 8, 4, 1>("cp.async ring, .cg L2::256B", a, sink, rows, S);
+  run_cp<3, 16, 4, 1>("cp.async ring, .cg L2::256B", a, sink, rows, S);
+  run_cp<3, 8, 4, 1>("cp.async ring, .cg L2::256B, 2 CTAs/SM", a, sink, rows, S, 296);
   // analysis shape: [BC*Nx*128 rows][128], plane = 128 rows x 128 floats contiguous
   run<128, 4, 2, 4, false, 1>("analysis plane, sw128, 2 stages", a, sink, rows * S / 128, 128, 128, SW, L2);
   run<128, 4, 3, 4, false, 1>("analysis plane, sw128, 3 stages", a, sink, rows * S / 128, 128, 128, SW, L2);
