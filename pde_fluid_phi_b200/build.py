@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libpdephi_b200.so")
-SOURCES = ["plan.cu", "api.cu", "transforms_simt.cu", "transforms_tc.cu", "transforms_tc3.cu", "mix.cu", "pointwise.cu", "block_tc.cu", "xstage_tc.cu"]
+SOURCES = ["plan.cu", "api.cu", "transforms_simt.cu", "transforms_tc.cu", "transforms_tc3.cu", "mix.cu", "pointwise.cu", "block_tc.cu", "xstage_tc.cu", "transforms_gen.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

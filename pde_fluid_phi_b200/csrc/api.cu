@@ -17,6 +17,10 @@ int analysis_tc3(const Plan* p, const float* x, float2* X, long long BC, int dir
 int synthesis_tc3(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1,
                   const float* mode_scale, const float* row_scale, long long rs_stride, long long BC, int direction,
                   float2* ws, cudaStream_t st);
+bool gen_supported(const Plan* p);
+int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int direction, void* ws, cudaStream_t st);
+int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1, const float* mode_scale,
+                  const float* row_scale, long long rs_stride, long long BC, int direction, void* ws, cudaStream_t st);
 }  // namespace pdephi
 
 using namespace pdephi;
@@ -25,7 +29,7 @@ extern "C" int pdephi_plan_supports(pdephi_plan_t plan, int precision) {
   const Plan* p = (const Plan*)plan;
   if (!p) return 0;
   if (precision == PDEPHI_PREC_FP32) return 1;
-  if (precision == PDEPHI_PREC_TF32) return tc_supported(p) ? 1 : 0;
+  if (precision == PDEPHI_PREC_TF32) return (tc_supported(p) || gen_supported(p)) ? 1 : 0;
   if (precision == PDEPHI_PREC_TF32X3) return tc3_supported(p) ? 1 : 0;
   return 0;
 }
@@ -52,6 +56,8 @@ extern "C" int pdephi_analysis_r2c(pdephi_plan_t plan, const float* x, float* X,
   if (rc) return rc;
   PDEPHI_REQUIRE(x && X, "analysis_r2c: null pointer");
   if (precision == PDEPHI_PREC_TF32) {
+    if (!tc_supported(p) && gen_supported(p))
+      return analysis_gen(p, x, (float2*)X, BC, direction, workspace, (cudaStream_t)stream);
     if (!tc_supported(p))
       return fail(PDEPHI_ERR_UNSUPPORTED, "analysis_r2c: TF32 tensor-core path does not support grid (%d,%d,%d) modes (%d,%d,%d)",
                   p->Nx, p->Ny, p->Nz, p->mx, p->my, p->mzh);
@@ -75,6 +81,9 @@ extern "C" int pdephi_synthesis_c2r(pdephi_plan_t plan, const float* Z, float* o
   if (rc) return rc;
   PDEPHI_REQUIRE(Z && out, "synthesis_c2r: null pointer");
   if (precision == PDEPHI_PREC_TF32) {
+    if (!tc_supported(p) && gen_supported(p))
+      return synthesis_gen(p, (const float2*)Z, out, addend0, addend1, mode_scale, row_scale, row_scale_stride, BC, direction,
+                           workspace, (cudaStream_t)stream);
     if (!tc_supported(p))
       return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis_c2r: TF32 tensor-core path does not support grid (%d,%d,%d) modes (%d,%d,%d)",
                   p->Nx, p->Ny, p->Nz, p->mx, p->my, p->mzh);

@@ -34,6 +34,19 @@ int fail(int code, const char* fmt, ...);
     if (!(cond)) return ::pdephi::fail(PDEPHI_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
+// general per-axis tensor-core route (transforms_gen.cu)
+struct GenPlan {
+  int has_mid;              // 1: 3-D problem (z, y, x stages); 0: 2-D problem [Nx, Ny, 1] (y takes the role of z)
+  int zN, zm, ldz, nbm;     // contiguous axis length, its retained modes, padded row length, MMA N of the z analysis
+  int ym;                   // rows of the middle axis carried through the x stage (my, or 1 for 2-D)
+  int mky, mkx;             // K of the axis-synthesis contractions (32 or 64)
+  int za_ring, zs_ring, xa_st, xs_st, ya_st, ys_st;   // pipeline depths that fit shared memory
+  float* za[2];             // z analysis  B images [direction]
+  float* zs[2];             // z synthesis B images [direction]
+  float* ya; float* ysc; float* yss;   // y axis: analysis A (plain [128][Ny]), synthesis cos / sin images
+  float* xa; float* xsc; float* xss;   // x axis
+};
+
 struct Plan {
   int device;
   int Nx, Ny, Nz, mx, my, mzh;
@@ -73,6 +86,9 @@ struct Plan {
   float* xtc3_ax[2];
   float* xtc3_sc[2];
   float* xtc3_ss[2];
+  int gen_ok;
+  void* gen_arena;
+  GenPlan g;
 };
 int tc_plan_init(Plan* p);
 void tc_plan_destroy(Plan* p);
@@ -80,12 +96,16 @@ int xtc_plan_init(Plan* p);
 void xtc_plan_destroy(Plan* p);
 int tc3_plan_init(Plan* p);
 void tc3_plan_destroy(Plan* p);
+int gen_plan_init(Plan* p);
+void gen_plan_destroy(Plan* p);
+size_t gen_workspace_bytes(const Plan* p, long long BC);
 
 enum KernelId {
   K_ANALYSIS_ZY = 0, K_ANALYSIS_X, K_SYNTHESIS_X, K_SYNTHESIS_ZY, K_ANALYSIS_ZY_TC, K_SYNTHESIS_ZY_TC,
   K_RATIONAL_MIX, K_RATIONAL_MIX_T, K_PROJ_STATS, K_PROJ_BWD, K_RATIONAL_DPQ, K_DPQ_REDUCE,
   K_COMPLEX_MIX, K_COMPLEX_MIX_T, K_COMPLEX_DW, K_POINTWISE_LINEAR, K_POINTWISE_WGRAD, K_BLOCK_TAIL_FWD, K_BLOCK_TAIL_BWD, K_ANALYSIS_X_TC, K_SYNTHESIS_X_TC, K_SCALE_MODES, K_RATIONAL_G,
-  K_ANALYSIS_ZY_TC3, K_SYNTHESIS_ZY_TC3, K_ANALYSIS_X_TC3, K_SYNTHESIS_X_TC3, K_COUNT
+  K_ANALYSIS_ZY_TC3, K_SYNTHESIS_ZY_TC3, K_ANALYSIS_X_TC3, K_SYNTHESIS_X_TC3,
+  K_GEN_Z_ANALYSIS, K_GEN_Z_SYNTHESIS, K_GEN_AXIS_ANALYSIS, K_GEN_AXIS_SYNTHESIS, K_COUNT
 };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);

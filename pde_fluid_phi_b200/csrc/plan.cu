@@ -27,7 +27,8 @@ static const char* const kKernelNames[K_COUNT] = {
     "complex_mix_kernel", "complex_mix_kernel(transposed)", "complex_dw_kernel", "pointwise_linear_kernel",
     "pointwise_wgrad_kernel", "block_tail_fwd_kernel", "block_tail_bwd_kernel", "analysis_x_tc_kernel",
     "synthesis_x_tc_kernel", "scale_modes_kernel", "rational_g_kernel", "analysis_zy_tc3_kernel",
-    "synthesis_zy_tc3_kernel", "analysis_x_tc3_kernel", "synthesis_x_tc3_kernel"};
+    "synthesis_zy_tc3_kernel", "analysis_x_tc3_kernel", "synthesis_x_tc3_kernel", "gen_z_analysis_kernel",
+    "gen_z_synthesis_kernel", "gen_axis_analysis_kernel", "gen_axis_synthesis_kernel"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 static std::atomic<long long> g_launches[K_COUNT];
 static std::atomic<bool> g_prof_on{false};
@@ -153,6 +154,8 @@ extern "C" int pdephi_plan_create_slab(pdephi_plan_t* out, int device, int Nx, i
     if (rc) return rc;
     rc = tc3_plan_init(p);
     if (rc) return rc;
+    rc = gen_plan_init(p);
+    if (rc) return rc;
   }
   PDEPHI_CUDA(cudaDeviceSynchronize());  // plan creation is the one synchronous call
   PDEPHI_CUDA(cudaSetDevice(cur));
@@ -167,6 +170,7 @@ extern "C" int pdephi_plan_destroy(pdephi_plan_t h) {
   tc_plan_destroy(p);
   xtc_plan_destroy(p);
   tc3_plan_destroy(p);
+  gen_plan_destroy(p);
   delete p;
   return PDEPHI_OK;
 }
@@ -176,8 +180,11 @@ extern "C" size_t pdephi_plan_workspace_bytes(pdephi_plan_t h, long long BC) {
   const Plan* p = (const Plan*)h;
   // intermediate between the fused (z,y) stage and the x stage: [BC, Nx, my, mzh] complex, followed by a
   // [BC, mx, my, mzh] complex scratch for the projected modes of the tensor-core synthesis x stage
-  return align_up((size_t)BC * p->Nx * p->my * p->mzh * sizeof(float2), 1024) +
-         align_up((size_t)BC * p->mx * p->my * p->mzh * sizeof(float2), 1024);
+  const size_t fused = align_up((size_t)BC * p->Nx * p->my * p->mzh * sizeof(float2), 1024) +
+                       align_up((size_t)BC * p->mx * p->my * p->mzh * sizeof(float2), 1024);
+  // the per-axis tensor-core route (shapes the fused kernels do not cover) stages one more, larger intermediate
+  const size_t general = (p->gen_ok && !p->tc_ok) ? gen_workspace_bytes(p, BC) : 0;
+  return fused > general ? fused : general;
 }
 
 extern "C" int pdephi_profile_enable(int on) {

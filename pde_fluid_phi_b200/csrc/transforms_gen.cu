@@ -1,0 +1,886 @@
+// K1 / K3, TF32 path for the shapes the fused (z,y) kernels of transforms_tc.cu do not cover (grids up to 256 per
+// axis, up to 64 retained modes per axis, 2-D problems [Nx, Ny, 1]): the pruned transforms as ONE tcgen05
+// contraction per axis, every stage a persistent warp-specialised kernel with TMA-staged data operands.
+//
+//   analysis    x [rows][zN] --(z)--> W1 [rows][ldz] --(y)--> W2 [BC*Nx][my][mzh] --(x)--> X [BC][mx][my][mzh]
+//   synthesis   Z --pad/scale--> Zp [BC][mx][ym][ldz/2] --(x)--> U [BC*Nx][ym*ldz] --(y)--> V [rows][ldz] --(z)--> out
+//
+//   z stages   the contracted index is contiguous: plain K-major GEMMs over 128-row tiles,
+//              analysis   D[128 x NB] = tile[128 x zN] . Bz[NB x zN]^T          (columns 2k = re, 2k+1 = im)
+//              synthesis  D[128 x zN] = tile[128 x ldz] . Bs[zN x ldz]^T  (+ addends in the epilogue)
+//   y/x stages the contracted index is the ROW index of a row-major [N rows][cols] matrix per batch item, so a TMA box
+//              [N rows][32 floats] is an MN-major B operand (128-byte swizzle with 32-byte atoms):
+//              analysis   D[128 x 64] = A[(cos k | sin k) x N] . tile[N x 64],  A TMEM-resident, combined through smem
+//              synthesis  D1 = C[128 x mk] . tile[mk x 64],  D2 = S . tile,  combined in registers
+//
+// A 2-D problem (Nz = 1) is the same pipeline with the y axis in the role of the contiguous axis and no middle stage.
+// The intermediate row length ldz = 2*zm rounded up to 4 floats keeps every TMA row stride a multiple of 16 bytes.
+// Replaces torch.fft.rfftn / irfftn of rational_fourier.py:161,170 and spectral_layers.py:59,76 at those shapes.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace pdephi {
+namespace gen {
+using namespace tcptx;
+
+constexpr int KBYTES = 16384;   // one [128 rows][32 floats] k-block
+constexpr int ST_LD = 36;       // padded staging row (32 floats + 4)
+
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo) {   // MN-major TF32 operand, 128B swizzle / 32B atoms
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// constant operand images (plan creation), generated in fp64 and rounded once to TF32
+//   kind 0  z analysis  B  K-major [R = NB rows][K = zN]   row r: mode r>>1, (r&1 ? -w sin : w cos)(2 pi mode k / N)
+//   kind 1  z synthesis B  K-major [R = zN rows][K]        col k: mode k>>1, (k&1 ? -w sin : w cos)(2 pi mode r / N)
+//   kind 2  axis analysis A  plain [128][N]                row r: mode r&63, (r>>6 ? sin : cos)(2 pi mode (k+off) / Nt)
+//   kind 3/4 axis synthesis A K-major [R = N rows][K = mk]  (cos / sin)(2 pi k (r+off) / Nt)
+// wmode 0: w = 1, 1: w = c_k / total (c_k = 1 for k = 0 and Nyquist, else 2), 2: w = 1 / total
+// ------------------------------------------------------------------------------------------------
+__global__ void gen_image_kernel(float* __restrict__ img, int kind, int R, int K, int Nt, int off, int m, int wmode, int nyq,
+                                 double inv_total, double comp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * K) return;
+  const int r = idx / K, k = idx % K;
+  int mode = -1, pos = 0, sine = 0;
+  if (kind == 0) { mode = r >> 1; sine = r & 1; pos = k; }
+  if (kind == 1) { mode = k >> 1; sine = k & 1; pos = r; }
+  if (kind == 2) { mode = r & 63; sine = r >> 6; pos = k + off; }
+  if (kind == 3 || kind == 4) { mode = k; sine = (kind == 4); pos = r + off; }
+  double v = 0.0;
+  if (mode < m) {
+    double s, c;
+    sincospi(2.0 * (double)(((long long)mode * pos) % Nt) / (double)Nt, &s, &c);
+    double w = 1.0;
+    if (wmode == 1) w = ((mode == 0 || mode == nyq) ? 1.0 : 2.0) * inv_total;
+    if (wmode == 2) w = inv_total;
+    v = (kind <= 1) ? (sine ? -w * s : w * c) : (sine ? s : c);
+    v *= comp;
+  }
+  const float f = to_tf32((float)v);
+  if (kind == 2) img[(size_t)r * K + k] = f;
+  else img[swz_off(R, r, k) / 4] = f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// z analysis: W[row][0..ldz) = sum_z x[row][z] . Bz[c][z]
+//   warp 0 TMA producer (k-block ring), warp 1 MMA issuer, warps 2..5 epilogue (TMEM quarter = warp % 4)
+// ------------------------------------------------------------------------------------------------
+constexpr int ZA_THREADS = 192;
+constexpr int MAX_RING = 8;
+struct ZASmem { uint32_t ring, bimg, stg, bars, tmem_slot, total; int nring; };
+__host__ __device__ inline ZASmem za_smem(int NKB, int NBm, int nring) {
+  ZASmem s; uint32_t o = 0;
+  s.nring = nring;
+  s.ring = o; o += (uint32_t)nring * KBYTES;
+  s.bimg = o; o += (uint32_t)NKB * NBm * 128;
+  s.stg = o; o += 4 * 32 * ST_LD * 4;
+  s.bars = o; o += 256;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+enum { ZB_FULL = 0, ZB_EMPTY = MAX_RING, ZB_DFULL = 2 * MAX_RING, ZB_DEMPTY = 2 * MAX_RING + 2 };
+
+__global__ void __launch_bounds__(ZA_THREADS, 1)
+gen_z_analysis_kernel(const __grid_constant__ CUtensorMap tmap_x, float* __restrict__ W, const float* __restrict__ Bimg,
+                      int ntiles, int NKB, int NBm, int ldz, int nring) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const ZASmem L = za_smem(NKB, NBm, nring);
+  auto bar = [&](int i) { return base + L.bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const float4* s1 = reinterpret_cast<const float4*>(Bimg);
+    float4* d1 = reinterpret_cast<float4*>(sm + L.bimg);
+    for (int i = threadIdx.x; i < NKB * NBm * 128 / 16; i += ZA_THREADS) d1[i] = __ldg(s1 + i);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_RING; ++i) { mbar_init(bar(ZB_FULL + i), 1); mbar_init(bar(ZB_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(ZB_DFULL + i), 1); mbar_init(bar(ZB_DEMPTY + i), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 1;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait(bar(ZB_EMPTY + s), ph);
+          mbar_arrive_expect_tx(bar(ZB_FULL + s), KBYTES);
+          tma_load_2d(base + L.ring + s * KBYTES, &tmap_x, bar(ZB_FULL + s), kb * 32, t * 128);
+          if (++s == nring) { s = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t id = idesc(128, NBm, 0, 0);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int d = it & 1;
+        mbar_wait(bar(ZB_DEMPTY + d), ((it >> 1) & 1) ^ 1);
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait(bar(ZB_FULL + s), ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem + d * 128, umma_desc(base + L.ring + s * KBYTES + k * 32, 1024),
+                   umma_desc(base + L.bimg + kb * NBm * 128 + k * 32, 1024), id, (kb | k) ? 1u : 0u);
+          mma_commit(bar(ZB_EMPTY + s));
+          if (++s == nring) { s = 0; ph ^= 1; }
+        }
+        mma_commit(bar(ZB_DFULL + d));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* st = reinterpret_cast<float*>(sm + L.stg) + (warp - 2) * 32 * ST_LD;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int d = it & 1;
+      mbar_wait(bar(ZB_DFULL + d), (it >> 1) & 1);
+      tc_fence_after();
+      float* wrow = W + ((size_t)t * 128 + 32 * q) * ldz;
+      for (int c0 = 0; c0 < ldz; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + d * 128 + lane_base + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= ldz) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(ZB_DEMPTY + d));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int lpr = min(32, ldz - c0) >> 2;            // float4 lanes per row of this chunk
+        for (int idx = lane; idx < 32 * lpr; idx += 32) {
+          const int row = idx / lpr, c4 = idx - row * lpr;
+          *reinterpret_cast<float4*>(wrow + (size_t)row * ldz + c0 + 4 * c4) =
+              *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// z synthesis: out[row][z] = sum_c V[row][c] . Bs[z][c]  (+ addends)
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue: two groups of four on alternate tiles
+// ------------------------------------------------------------------------------------------------
+constexpr int ZS_EPI = 8;
+constexpr int ZS_THREADS = 32 * (2 + ZS_EPI);
+struct ZSSmem { uint32_t ring, bimg, stg, bars, tmem_slot, total; int nring; };
+__host__ __device__ inline ZSSmem zs_smem(int zN, int NKBK, int nring) {
+  ZSSmem s; uint32_t o = 0;
+  s.nring = nring;
+  s.ring = o; o += (uint32_t)nring * KBYTES;
+  s.bimg = o; o += (uint32_t)NKBK * zN * 128;
+  s.stg = o; o += ZS_EPI * 32 * ST_LD * 4;
+  s.bars = o; o += 256;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+
+template <int NADD>
+__global__ void __launch_bounds__(ZS_THREADS, 1)
+gen_z_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_v, float* __restrict__ out, const float* __restrict__ add0,
+                       const float* __restrict__ add1, const float* __restrict__ Bimg, int ntiles, int zN, int NKBK,
+                       int ksteps, int nring, int tmem_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const ZSSmem L = zs_smem(zN, NKBK, nring);
+  auto bar = [&](int i) { return base + L.bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const float4* s1 = reinterpret_cast<const float4*>(Bimg);
+    float4* d1 = reinterpret_cast<float4*>(sm + L.bimg);
+    for (int i = threadIdx.x; i < NKBK * zN * 128 / 16; i += ZS_THREADS) d1[i] = __ldg(s1 + i);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_RING; ++i) { mbar_init(bar(ZB_FULL + i), 1); mbar_init(bar(ZB_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(ZB_DFULL + i), 1); mbar_init(bar(ZB_DEMPTY + i), ZS_EPI / 2); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, (uint32_t)tmem_cols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 1;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+        for (int kb = 0; kb < NKBK; ++kb) {
+          mbar_wait(bar(ZB_EMPTY + s), ph);
+          mbar_arrive_expect_tx(bar(ZB_FULL + s), KBYTES);
+          tma_load_2d(base + L.ring + s * KBYTES, &tmap_v, bar(ZB_FULL + s), kb * 32, t * 128);
+          if (++s == nring) { s = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t id = idesc(128, zN, 0, 0);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int d = it & 1;
+        mbar_wait(bar(ZB_DEMPTY + d), ((it >> 1) & 1) ^ 1);
+        for (int kb = 0; kb < NKBK; ++kb) {
+          mbar_wait(bar(ZB_FULL + s), ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (kb * 4 + k < ksteps)
+              mma_ss(tmem + d * zN, umma_desc(base + L.ring + s * KBYTES + k * 32, 1024),
+                     umma_desc(base + L.bimg + kb * zN * 128 + k * 32, 1024), id, (kb | k) ? 1u : 0u);
+          mma_commit(bar(ZB_EMPTY + s));
+          if (++s == nring) { s = 0; ph ^= 1; }
+        }
+        mma_commit(bar(ZB_DFULL + d));
+      }
+    }
+  } else {
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* st = reinterpret_cast<float*>(sm + L.stg) + (warp - 2) * 32 * ST_LD;
+    const int rsub = lane >> 3, c4 = lane & 7;
+    const int n_my = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int nrounds = zN >> 5;
+    for (int it = grp; it < n_my; it += 2) {
+      const int t = blockIdx.x + it * gridDim.x;
+      mbar_wait(bar(ZB_DFULL + grp), (it >> 1) & 1);
+      tc_fence_after();
+      for (int r = 0; r < nrounds; ++r) {
+        const size_t gbase = ((size_t)t * 128 + 32 * q + rsub) * zN + r * 32 + 4 * c4;
+        float4 a0v[NADD >= 1 ? 8 : 1], a1v[NADD == 2 ? 8 : 1];
+        if (NADD >= 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a0v[j] = __ldcs(reinterpret_cast<const float4*>(add0 + gbase + (size_t)(4 * j) * zN));
+        }
+        if (NADD == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a1v[j] = __ldcs(reinterpret_cast<const float4*>(add1 + gbase + (size_t)(4 * j) * zN));
+        }
+        float v[32];
+        tmem_ld32(tmem + grp * zN + lane_base + r * 32, v);
+        tmem_ld_wait();
+        if (r == nrounds - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(ZB_DEMPTY + grp));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = *reinterpret_cast<const float4*>(st + (4 * j + rsub) * ST_LD + 4 * c4);
+          if (NADD >= 1) { o.x += a0v[j].x; o.y += a0v[j].y; o.z += a0v[j].z; o.w += a0v[j].w; }
+          if (NADD == 2) { o.x += a1v[j].x; o.y += a1v[j].y; o.z += a1v[j].z; o.w += a1v[j].w; }
+          __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)(4 * j) * zN), o);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// axis analysis (contracted index = row): out[b][k][j] = sum_n e^{-i theta(k,n)} in[b][n][j]
+//   warp 0 TMA, warp 1 MMA, warps 2..5 epilogue.  A = [cos k (rows 0..63) | sin k (rows 64..127)] x N lives in TMEM.
+// ------------------------------------------------------------------------------------------------
+constexpr int AA_THREADS = 192;
+constexpr int AA_MAXST = 4;
+constexpr int AA_ELD = 66;
+constexpr int NT = 64;          // floats per column tile (32 complex)
+struct AASmem { uint32_t stage, e, bars, tmem_slot, total; int nst; };
+__host__ __device__ inline AASmem aa_smem(int N, int nst) {
+  AASmem s; uint32_t o = 0;
+  s.nst = nst;
+  s.stage = o; o += (uint32_t)nst * 2 * N * 128;
+  s.e = o; o += 128 * AA_ELD * 4;
+  s.bars = o; o += 256;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+enum { AB_FULL = 0, AB_EMPTY = AA_MAXST, AB_DFULL = 2 * AA_MAXST, AB_DEMPTY = 2 * AA_MAXST + 2 };
+
+__global__ void __launch_bounds__(AA_THREADS, 1)
+gen_axis_analysis_kernel(const __grid_constant__ CUtensorMap tmap_in, float2* __restrict__ out, const float* __restrict__ Aplain,
+                         int N, int m, int Pout, int ntn, long long ntiles, int nst) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const AASmem L = aa_smem(N, nst);
+  auto bar = [&](int i) { return base + L.bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t box = (uint32_t)N * 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AA_MAXST; ++i) { mbar_init(bar(AB_FULL + i), 1); mbar_init(bar(AB_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(AB_DFULL + i), 1); mbar_init(bar(AB_DEMPTY + i), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const uint32_t tmem_a = tmem, tmem_d = tmem + 384;     // A: N <= 256 columns, D: 2 x 64 columns
+  if (warp >= 2) {
+    const int q = warp & 3;
+    const float* row = Aplain + (size_t)(32 * q + lane) * N;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float r[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(row + c0) + j);
+        r[4 * j] = t.x; r[4 * j + 1] = t.y; r[4 * j + 2] = t.z; r[4 * j + 3] = t.w;
+      }
+      tmem_st32(tmem_a + ((uint32_t)(q * 32) << 16) + c0, r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 1;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(bar(AB_EMPTY + s), ph);
+        mbar_arrive_expect_tx(bar(AB_FULL + s), 2 * box);
+        const long long b = t / ntn;
+        const int n0 = (int)(t - b * ntn) * NT;
+        tma_load_2d(base + L.stage + s * 2 * box, &tmap_in, bar(AB_FULL + s), n0, (int)(b * N));
+        tma_load_2d(base + L.stage + s * 2 * box + box, &tmap_in, bar(AB_FULL + s), n0 + 32, (int)(b * N));
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t id = idesc(128, NT, 0, 1);
+      int s = 0; uint32_t ph = 0;
+      long long it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int d = (int)(it & 1);
+        mbar_wait(bar(AB_FULL + s), ph);
+        mbar_wait(bar(AB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        for (int k = 0; k < N / 8; ++k)
+          mma_ts(tmem_d + d * NT, tmem_a + 8 * k, desc_mn(base + L.stage + s * 2 * box + k * 1024, box), id, k ? 1u : 0u);
+        mma_commit(bar(AB_EMPTY + s));
+        mma_commit(bar(AB_DFULL + d));
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int et = (warp - 2) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* E = reinterpret_cast<float*>(sm + L.e);
+    const int niter = (m * 32 + 127) / 128;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int d = (int)(it & 1);
+      mbar_wait(bar(AB_DFULL + d), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      float v[64];
+      tmem_ld32(tmem_d + d * NT + lane_base, v);
+      tmem_ld32(tmem_d + d * NT + lane_base + 32, v + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(AB_DEMPTY + d));
+      epi_bar_sync();                                  // previous tile's readers of E are done
+      {
+        float* er = E + (32 * q + lane) * AA_ELD;
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) *reinterpret_cast<float2*>(er + c) = make_float2(v[c], v[c + 1]);
+      }
+      epi_bar_sync();
+      const long long b = t / ntn;
+      const int p0 = (int)(t - b * ntn) * (NT / 2);
+      float2* outp = out + (size_t)b * m * Pout;
+      for (int i = 0; i < niter; ++i) {
+        const int idx = et + 128 * i, k = idx >> 5, j = idx & 31;
+        if (k < m && p0 + j < Pout) {
+          const float2 c = *reinterpret_cast<const float2*>(E + k * AA_ELD + 2 * j);
+          const float2 s = *reinterpret_cast<const float2*>(E + (64 + k) * AA_ELD + 2 * j);
+          outp[(size_t)k * Pout + p0 + j] = make_float2(c.x + s.y, c.y - s.x);   // (C - iS)(re + i im)
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// axis synthesis (contracted index = row): out[b][n][j] = sum_k e^{+i theta(k,n)} in[b][k][j]
+//   warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (column half = (warp-2)/4)
+// ------------------------------------------------------------------------------------------------
+constexpr int AS_EPI = 8;
+constexpr int AS_THREADS = 32 * (2 + AS_EPI);
+constexpr int AS_MAXST = 4;
+struct ASSmem { uint32_t stage, ac, as, stg, bars, tmem_slot, total; int nst; };
+__host__ __device__ inline ASSmem as_smem(int N, int mk, int nst) {
+  ASSmem s; uint32_t o = 0;
+  s.nst = nst;
+  s.stage = o; o += (uint32_t)nst * 2 * mk * 128;
+  o = (o + 1023u) & ~1023u;
+  s.ac = o; o += (uint32_t)N * mk * 4;
+  s.as = o; o += (uint32_t)N * mk * 4;
+  s.stg = o; o += AS_EPI * 32 * ST_LD * 4;
+  s.bars = o; o += 256;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+
+__global__ void __launch_bounds__(AS_THREADS, 1)
+gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __restrict__ U, const float* __restrict__ Acimg,
+                          const float* __restrict__ Asimg, int N, int m, int mk, int ld_out, int ntn, int nmt,
+                          long long ntiles, int nst) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const ASSmem L = as_smem(N, mk, nst);
+  auto bar = [&](int i) { return base + L.bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t box = (uint32_t)mk * 128;
+  {
+    const float4* s1 = reinterpret_cast<const float4*>(Acimg);
+    const float4* s2 = reinterpret_cast<const float4*>(Asimg);
+    float4* d1 = reinterpret_cast<float4*>(sm + L.ac);
+    float4* d2 = reinterpret_cast<float4*>(sm + L.as);
+    for (int i = threadIdx.x; i < N * mk / 4; i += AS_THREADS) { d1[i] = __ldg(s1 + i); d2[i] = __ldg(s2 + i); }
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AS_MAXST; ++i) { mbar_init(bar(AB_FULL + i), 1); mbar_init(bar(AB_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(AB_DFULL + i), 1); mbar_init(bar(AB_DEMPTY + i), AS_EPI); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const long long per_mt = ntiles / nmt;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 1;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(bar(AB_EMPTY + s), ph);
+        mbar_arrive_expect_tx(bar(AB_FULL + s), 2 * box);
+        const long long r = t % per_mt, b = r / ntn;
+        const int n0 = (int)(r - b * ntn) * NT;
+        tma_load_2d(base + L.stage + s * 2 * box, &tmap_in, bar(AB_FULL + s), n0, (int)(b * m));
+        tma_load_2d(base + L.stage + s * 2 * box + box, &tmap_in, bar(AB_FULL + s), n0 + 32, (int)(b * m));
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t id = idesc(128, NT, 0, 1);
+      int s = 0; uint32_t ph = 0;
+      long long it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int d = (int)(it & 1);
+        const int mt = (int)(t / per_mt);
+        mbar_wait(bar(AB_FULL + s), ph);
+        mbar_wait(bar(AB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        for (int ks = 0; ks < mk / 8; ++ks) {
+          const uint32_t aoff = (uint32_t)(ks >> 2) * (uint32_t)N * 128 + (uint32_t)mt * 16384 + (uint32_t)(ks & 3) * 32;
+          const uint64_t bd = desc_mn(base + L.stage + s * 2 * box + ks * 1024, box);
+          mma_ss(tmem + d * 128, umma_desc(base + L.ac + aoff, 1024), bd, id, ks ? 1u : 0u);
+          mma_ss(tmem + d * 128 + NT, umma_desc(base + L.as + aoff, 1024), bd, id, ks ? 1u : 0u);
+        }
+        mma_commit(bar(AB_EMPTY + s));
+        mma_commit(bar(AB_DFULL + d));
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* st = reinterpret_cast<float*>(sm + L.stg) + (warp - 2) * 32 * ST_LD;
+    const int rsub = lane >> 3, c4 = lane & 7;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int d = (int)(it & 1);
+      mbar_wait(bar(AB_DFULL + d), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      float c[32], s[32];
+      tmem_ld32(tmem + d * 128 + lane_base + half * 32, c);
+      tmem_ld32(tmem + d * 128 + NT + lane_base + half * 32, s);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(AB_DEMPTY + d));
+      // (cos + i sin)(re + i im): re' = C re - S im, im' = C im + S re   (columns 2j = re, 2j+1 = im)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o;
+        o.x = c[4 * j] - s[4 * j + 1];
+        o.y = c[4 * j + 1] + s[4 * j];
+        o.z = c[4 * j + 2] - s[4 * j + 3];
+        o.w = c[4 * j + 3] + s[4 * j + 2];
+        *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) = o;
+      }
+      __syncwarp();
+      const int mt = (int)(t / per_mt);
+      const long long r = t % per_mt, b = r / ntn;
+      const int n0 = (int)(r - b * ntn) * NT + half * 32;
+      float* ub = U + ((size_t)b * N + (size_t)mt * 128 + 32 * q) * ld_out + n0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int row = 4 * g + rsub;
+        if (n0 + 4 * c4 < ld_out)
+          *reinterpret_cast<float4*>(ub + (size_t)row * ld_out + 4 * c4) = *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// Zp[bc][kx][ky][0..ldz/2) = Z[bc][kx][ky][kz] * mode_scale[k] * row_scale[bc]   (zero in the padding columns)
+__global__ void gen_pad_scale_kernel(const float2* __restrict__ Z, float2* __restrict__ Zp, const float* __restrict__ mode_scale,
+                                     const float* __restrict__ row_scale, long long rs_stride, int zm, int ldh, long long Mrows,
+                                     long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long row = i / ldh;            // (bc, kx, ky)
+  const int kz = (int)(i - row * ldh);
+  float2 v = make_float2(0.f, 0.f);
+  if (kz < zm) {
+    const long long bc = row / Mrows, kr = row - bc * Mrows;
+    float s = mode_scale ? __ldg(mode_scale + kr * zm + kz) : 1.f;
+    if (row_scale) s *= __ldg(row_scale + bc * rs_stride);
+    const float2 z = __ldg(Z + row * zm + kz);
+    v = make_float2(z.x * s, z.y * s);
+  }
+  Zp[i] = v;
+}
+
+}  // namespace gen
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder(const void* device_ptr);
+
+static int pow2_at_least(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+
+static int gen_make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, int box_rows, bool mn_major) {
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  if (rows > 0x7fffffffLL) return fail(PDEPHI_ERR_UNSUPPORTED, "general transform route: too many rows for one tensor map");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (cols & 3))
+    return fail(PDEPHI_ERR_INVALID, "general transform route: buffer must be 16-byte aligned with a row length multiple of 4");
+  CUresult r = tensor_map_encoder(ptr)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PDEPHI_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return PDEPHI_OK;
+}
+
+bool gen_supported(const Plan* p) { return p->gen_ok != 0; }
+
+static size_t smem_budget(const Plan* p) { return p->smem_optin - 1024; }
+
+int gen_plan_init(Plan* p) {
+  p->gen_ok = 0;
+  p->gen_arena = nullptr;
+  const bool two_d = (p->Nz == 1 && p->mzh == 1);
+  GenPlan& g = p->g;
+  g.has_mid = two_d ? 0 : 1;
+  g.zN = two_d ? p->Ny : p->Nz;
+  g.zm = two_d ? p->my : p->mzh;
+  g.ym = two_d ? 1 : p->my;
+  g.ldz = (2 * g.zm + 3) / 4 * 4;
+  g.nbm = (g.ldz + 15) / 16 * 16;
+  g.mky = p->my <= 32 ? 32 : 64;
+  g.mkx = p->mx <= 32 ? 32 : 64;
+  auto axis_ok = [](int N, int m) { return N % 128 == 0 && N <= 256 && m <= 64; };
+  bool ok = g.zN % 32 == 0 && g.zN >= 32 && g.zN <= 256 && g.nbm <= 128 && axis_ok(p->Nx, p->mx);
+  if (!two_d) ok = ok && axis_ok(p->Ny, p->my) && (p->my * p->mzh) % 2 == 0;
+  if (!ok || !tensor_map_encoder(nullptr)) return PDEPHI_OK;
+  // shared-memory plans of the four kernels
+  const int NKB = g.zN / 32, NKBK = (g.ldz + 31) / 32;
+  {
+    const size_t fixed = gen::za_smem(NKB, g.nbm, 0).total;
+    const int nr = (int)((smem_budget(p) - fixed) / gen::KBYTES);
+    if (smem_budget(p) < fixed || nr < 2) return PDEPHI_OK;
+    g.za_ring = nr > gen::MAX_RING ? gen::MAX_RING : nr;
+  }
+  {
+    const size_t fixed = gen::zs_smem(g.zN, NKBK, 0).total;
+    const int nr = (int)((smem_budget(p) - fixed) / gen::KBYTES);
+    if (smem_budget(p) < fixed || nr < 2) return PDEPHI_OK;
+    g.zs_ring = nr > gen::MAX_RING ? gen::MAX_RING : nr;
+  }
+  auto aa_stages = [&](int N) {
+    const size_t fixed = gen::aa_smem(N, 0).total;
+    if (smem_budget(p) < fixed) return 0;
+    const int ns = (int)((smem_budget(p) - fixed) / (2 * (size_t)N * 128));
+    return ns > gen::AA_MAXST ? gen::AA_MAXST : ns;
+  };
+  auto as_stages = [&](int N, int mk) {
+    const size_t fixed = gen::as_smem(N, mk, 0).total + 1024;
+    if (smem_budget(p) < fixed) return 0;
+    const int ns = (int)((smem_budget(p) - fixed) / (2 * (size_t)mk * 128));
+    return ns > gen::AS_MAXST ? gen::AS_MAXST : ns;
+  };
+  g.xa_st = aa_stages(p->Nx);
+  g.xs_st = as_stages(p->Nx, g.mkx);
+  g.ya_st = two_d ? 2 : aa_stages(p->Ny);
+  g.ys_st = two_d ? 2 : as_stages(p->Ny, g.mky);
+  if (g.xa_st < 2 || g.xs_st < 2 || g.ya_st < 2 || g.ys_st < 2) return PDEPHI_OK;
+
+  const size_t n_za = (size_t)g.nbm * g.zN, n_zs = (size_t)g.zN * NKBK * 32;
+  const size_t n_ya = two_d ? 0 : (size_t)128 * p->Ny, n_ys = two_d ? 0 : (size_t)p->Ny * g.mky;
+  const size_t n_xa = (size_t)128 * p->Nx, n_xs = (size_t)p->Nx * g.mkx;
+  const size_t total = (2 * n_za + 2 * n_zs + n_ya + 2 * n_ys + n_xa + 2 * n_xs) * sizeof(float);
+  PDEPHI_CUDA(cudaMalloc(&p->gen_arena, total));
+  PDEPHI_CUDA(cudaMemset(p->gen_arena, 0, total));
+  float* f = (float*)p->gen_arena;
+  g.za[0] = f; f += n_za; g.za[1] = f; f += n_za;
+  g.zs[0] = f; f += n_zs; g.zs[1] = f; f += n_zs;
+  g.ya = f; f += n_ya; g.ysc = f; f += n_ys; g.yss = f; f += n_ys;
+  g.xa = f; f += n_xa; g.xsc = f; f += n_xs; g.xss = f; f += n_xs;
+  const double inv_total = 1.0 / ((double)p->Nx_total * p->Ny * p->Nz);
+  const int nyq = (!two_d && p->Nz % 2 == 0 && p->mzh - 1 == p->Nz / 2) ? p->Nz / 2 : -1;
+  const double comp = 1.0 + 1.0 / 2048.0;     // the tensor core truncates the raw fp32 data operand (see transforms_tc.cu)
+  const int wnorm = two_d ? 2 : 1;
+  auto genimg = [&](float* img, int kind, int R, int K, int Nt, int off, int m, int wmode) {
+    const int n = R * K;
+    gen::gen_image_kernel<<<(n + 255) / 256, 256>>>(img, kind, R, K, Nt, off, m, wmode, nyq, inv_total, comp);
+  };
+  genimg(g.za[0], 0, g.nbm, g.zN, g.zN, 0, g.zm, 0);          // analysis FORWARD: plain e^{-i}
+  genimg(g.za[1], 0, g.nbm, g.zN, g.zN, 0, g.zm, wnorm);      // analysis ADJOINT: c_k / total
+  genimg(g.zs[0], 1, g.zN, NKBK * 32, g.zN, 0, g.zm, wnorm);  // synthesis FORWARD: c_k / total
+  genimg(g.zs[1], 1, g.zN, NKBK * 32, g.zN, 0, g.zm, 0);      // synthesis ADJOINT: plain
+  if (!two_d) {
+    genimg(g.ya, 2, 128, p->Ny, p->Ny, 0, p->my, 0);
+    genimg(g.ysc, 3, p->Ny, g.mky, p->Ny, 0, p->my, 0);
+    genimg(g.yss, 4, p->Ny, g.mky, p->Ny, 0, p->my, 0);
+  }
+  genimg(g.xa, 2, 128, p->Nx, p->Nx_total, p->x_offset, p->mx, 0);
+  genimg(g.xsc, 3, p->Nx, g.mkx, p->Nx_total, p->x_offset, p->mx, 0);
+  genimg(g.xss, 4, p->Nx, g.mkx, p->Nx_total, p->x_offset, p->mx, 0);
+  PDEPHI_LAUNCH_CHECK("gen_image_kernel");
+  p->gen_ok = 1;
+  return PDEPHI_OK;
+}
+
+void gen_plan_destroy(Plan* p) {
+  if (p->gen_arena) cudaFree(p->gen_arena);
+  p->gen_arena = nullptr;
+}
+
+// workspace layout of the general route: [W1 | W2 | Zp]
+struct GenWs { size_t w1, w2, zp, total; };
+static GenWs gen_ws(const Plan* p, long long BC) {
+  const GenPlan& g = p->g;
+  const size_t rows = (size_t)BC * p->Nx * (g.has_mid ? p->Ny : 1);
+  GenWs w;
+  w.w1 = 0;
+  size_t o = align_up(rows * g.ldz * sizeof(float), 1024);
+  w.w2 = o;
+  o += align_up((size_t)BC * p->Nx * g.ym * g.ldz * sizeof(float), 1024);
+  w.zp = o;
+  o += align_up((size_t)BC * p->mx * g.ym * g.ldz * sizeof(float), 1024);
+  w.total = o;
+  return w;
+}
+size_t gen_workspace_bytes(const Plan* p, long long BC) { return gen_ws(p, BC).total; }
+
+static int launch_axis_analysis(const Plan* p, const float* in, long long nb, int N, int m, int ld_in, int Pout, float2* out,
+                                const float* Aplain, int nst, int kid, cudaStream_t st) {
+  CUtensorMap map;
+  int rc = gen_make_map(&map, in, nb * N, ld_in, N, true);
+  if (rc) return rc;
+  const int ntn = (ld_in + gen::NT - 1) / gen::NT;
+  const long long ntiles = nb * ntn;
+  const size_t smem = gen::aa_smem(N, nst).total + 1024;
+  const int grid = (int)(ntiles < p->num_sms ? ntiles : p->num_sms);
+  auto k = gen::gen_axis_analysis_kernel;
+  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope ps(kid, st);
+    k<<<grid, gen::AA_THREADS, smem, st>>>(map, out, Aplain, N, m, Pout, ntn, ntiles, nst);
+  }
+  PDEPHI_LAUNCH_CHECK("gen_axis_analysis_kernel");
+  return PDEPHI_OK;
+}
+
+static int launch_axis_synthesis(const Plan* p, const float* in, long long nb, int N, int m, int mk, int ld, float* out,
+                                 const float* Ac, const float* As, int nst, int kid, cudaStream_t st) {
+  CUtensorMap map;
+  int rc = gen_make_map(&map, in, nb * m, ld, mk, true);
+  if (rc) return rc;
+  const int ntn = (ld + gen::NT - 1) / gen::NT;
+  const int nmt = N / 128;
+  const long long ntiles = nb * ntn * nmt;
+  const size_t smem = gen::as_smem(N, mk, nst).total + 1024;
+  const int grid = (int)(ntiles < p->num_sms ? ntiles : p->num_sms);
+  auto k = gen::gen_axis_synthesis_kernel;
+  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope ps(kid, st);
+    k<<<grid, gen::AS_THREADS, smem, st>>>(map, out, Ac, As, N, m, mk, ld, ntn, nmt, ntiles, nst);
+  }
+  PDEPHI_LAUNCH_CHECK("gen_axis_synthesis_kernel");
+  return PDEPHI_OK;
+}
+
+int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int direction, void* ws, cudaStream_t st) {
+  const GenPlan& g = p->g;
+  const GenWs w = gen_ws(p, BC);
+  char* wb = (char*)ws;
+  float* W1 = (float*)(wb + w.w1);
+  float* W2 = (float*)(wb + w.w2);
+  const long long rows = BC * p->Nx * (g.has_mid ? p->Ny : 1);
+  {
+    CUtensorMap map;
+    int rc = gen_make_map(&map, x, rows, g.zN, 128, false);
+    if (rc) return rc;
+    const int NKB = g.zN / 32;
+    const int ntiles = (int)(rows / 128);
+    const size_t smem = gen::za_smem(NKB, g.nbm, g.za_ring).total + 1024;
+    const int grid = ntiles < p->num_sms ? ntiles : p->num_sms;
+    auto k = gen::gen_z_analysis_kernel;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      ProfScope ps(K_GEN_Z_ANALYSIS, st);
+      k<<<grid, gen::ZA_THREADS, smem, st>>>(map, W1, g.za[direction], ntiles, NKB, g.nbm, g.ldz, g.za_ring);
+    }
+    PDEPHI_LAUNCH_CHECK("gen_z_analysis_kernel");
+  }
+  if (g.has_mid) {
+    int rc = launch_axis_analysis(p, W1, BC * p->Nx, p->Ny, p->my, g.ldz, p->mzh, (float2*)W2, g.ya, g.ya_st, K_GEN_AXIS_ANALYSIS, st);
+    if (rc) return rc;
+    return launch_axis_analysis(p, W2, BC, p->Nx, p->mx, 2 * p->my * p->mzh, p->my * p->mzh, X, g.xa, g.xa_st,
+                                K_GEN_AXIS_ANALYSIS, st);
+  }
+  return launch_axis_analysis(p, W1, BC, p->Nx, p->mx, g.ldz, g.zm, X, g.xa, g.xa_st, K_GEN_AXIS_ANALYSIS, st);
+}
+
+int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1, const float* mode_scale,
+                  const float* row_scale, long long rs_stride, long long BC, int direction, void* ws, cudaStream_t st) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(out) || !al16(add0) || !al16(add1)) return fail(PDEPHI_ERR_INVALID, "synthesis: buffers must be 16-byte aligned");
+  const GenPlan& g = p->g;
+  const GenWs w = gen_ws(p, BC);
+  char* wb = (char*)ws;
+  float* W1 = (float*)(wb + w.w1);
+  float* W2 = (float*)(wb + w.w2);
+  float* Zp = (float*)(wb + w.zp);
+  const float* src = (const float*)Z;
+  const int ldh = g.ldz / 2;
+  if (mode_scale || row_scale || g.ldz != 2 * g.zm) {
+    const long long Mrows = (long long)p->mx * g.ym;
+    const long long total = BC * Mrows * ldh;
+    {
+      ProfScope ps(K_SCALE_MODES, st);
+      gen::gen_pad_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, (float2*)Zp, mode_scale, row_scale, rs_stride,
+                                                                               g.zm, ldh, Mrows, total);
+    }
+    PDEPHI_LAUNCH_CHECK("gen_pad_scale_kernel");
+    src = Zp;
+  }
+  const long long rows = BC * p->Nx * (g.has_mid ? p->Ny : 1);
+  const float* zin;
+  if (g.has_mid) {
+    int rc = launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, g.ym * g.ldz, W2, g.xsc, g.xss, g.xs_st, K_GEN_AXIS_SYNTHESIS, st);
+    if (rc) return rc;
+    rc = launch_axis_synthesis(p, W2, BC * p->Nx, p->Ny, p->my, g.mky, g.ldz, W1, g.ysc, g.yss, g.ys_st, K_GEN_AXIS_SYNTHESIS, st);
+    if (rc) return rc;
+    zin = W1;
+  } else {
+    int rc = launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, g.ldz, W1, g.xsc, g.xss, g.xs_st, K_GEN_AXIS_SYNTHESIS, st);
+    if (rc) return rc;
+    zin = W1;
+  }
+  CUtensorMap map;
+  int rc = gen_make_map(&map, zin, rows, g.ldz, 128, false);
+  if (rc) return rc;
+  const int NKBK = (g.ldz + 31) / 32, ksteps = (g.ldz + 7) / 8;
+  const int ntiles = (int)(rows / 128);
+  const size_t smem = gen::zs_smem(g.zN, NKBK, g.zs_ring).total + 1024;
+  const int grid = ntiles < p->num_sms ? ntiles : p->num_sms;
+  const int tmem_cols = pow2_at_least(2 * g.zN);
+  if (add1 && !add0) { add0 = add1; add1 = nullptr; }
+  const int nadd = (add0 ? 1 : 0) + (add1 ? 1 : 0);
+#define PDEPHI_GZS_LAUNCH(NA)                                                                                            \
+  {                                                                                                                      \
+    auto k = gen::gen_z_synthesis_kernel<NA>;                                                                            \
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+    ProfScope ps(K_GEN_Z_SYNTHESIS, st);                                                                                 \
+    k<<<grid, gen::ZS_THREADS, smem, st>>>(map, out, add0, add1, g.zs[direction], ntiles, g.zN, NKBK, ksteps, g.zs_ring, \
+                                           tmem_cols);                                                                   \
+  }
+  if (nadd == 0) PDEPHI_GZS_LAUNCH(0) else if (nadd == 1) PDEPHI_GZS_LAUNCH(1) else PDEPHI_GZS_LAUNCH(2)
+#undef PDEPHI_GZS_LAUNCH
+  PDEPHI_LAUNCH_CHECK("gen_z_synthesis_kernel");
+  return PDEPHI_OK;
+}
+
+}  // namespace pdephi

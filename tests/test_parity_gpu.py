@@ -140,7 +140,11 @@ SHAPES = [((16, 16, 16), (8, 8, 8)), ((16, 12, 20), (6, 4, 8)), ((9, 7, 11), (5,
           # tensor-core shapes (Ny = 128, Nz in {64, 128}); the last one runs more planes than SMs
           ((2, 128, 128), (2, 32, 32)), ((4, 128, 64), (4, 16, 24)), ((5, 128, 128), (3, 20, 38)), ((80, 128, 128), (8, 32, 32)),
           # tensor-core x stage as well (Nx % 32 == 0 for analysis, Nx == 128 for synthesis, even my*mzh)
-          ((128, 128, 128), (32, 32, 32)), ((64, 128, 64), (16, 16, 24)), ((32, 128, 128), (5, 7, 9)), ((128, 128, 64), (9, 6, 10))]
+          ((128, 128, 128), (32, 32, 32)), ((64, 128, 64), (16, 16, 24)), ((32, 128, 128), (5, 7, 9)), ((128, 128, 64), (9, 6, 10)),
+          # per-axis tensor-core route (transforms_gen.cu): up to 64 modes per axis, axes up to 256, 2-D grids, odd mzh
+          # (padded intermediate rows), retained Nyquist, mx > 32 with my <= 32
+          ((128, 128, 32), (5, 8, 9)), ((128, 128, 128), (64, 64, 64)), ((128, 256, 64), (10, 40, 30)),
+          ((128, 128, 1), (32, 16, 1)), ((256, 256, 1), (64, 64, 1)), ((256, 128, 96), (33, 20, 40)), ((128, 128, 64), (16, 16, 64))]
 
 
 @pytest.mark.parametrize("grid,modes", SHAPES)
@@ -279,18 +283,20 @@ def test_fused_block_matches_unfused_and_is_deterministic():
     assert torch.equal(again, fused) and torch.equal(x.grad, gx) and torch.equal(layer.P_coeffs.grad, gP)
 
 
-@pytest.mark.parametrize("precision", ["tf32", "tf32x3", "fp32"])
-def test_tensor_core_layer_gates(precision):
+@pytest.mark.parametrize("precision,modes", [("tf32", (32, 32, 32)), ("tf32x3", (32, 32, 32)), ("fp32", (32, 32, 32)),
+                                             ("tf32", (48, 40, 64))])
+def test_tensor_core_layer_gates(precision, modes):
     """The headline layer shape family against the oracle on outputs and grads: <= 2e-3 on the single-pass TF32
-    route, <= 1e-5 on the split-TF32 route (and on the FFMA route beside it)."""
-    C, modes, grid = 8, (32, 32, 32), (128, 128, 128)
+    route, <= 1e-5 on the split-TF32 route (and on the FFMA route beside it).  Modes (48, 40, 64) take the per-axis
+    tensor-core route of transforms_gen.cu (cfg 4's small-scale operator and cfg 5 have 64 modes per axis)."""
+    C, grid = 8, (128, 128, 128)
     if precision != "fp32" and not tc_ok(grid, modes, _cabi.PRECISIONS[precision]):
         pytest.skip("tcgen05 path not available for this shape")
     torch.manual_seed(21)
     layer = pb.RationalFourierLayer(C, C, modes)
     with torch.no_grad():                       # conditioned weights: isolates transform error (SURVEY 8c (ii))
         q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
-        layer.Q_coeffs.mul_(1e-4)
+        layer.Q_coeffs.mul_(1e-4 if max(modes) <= 32 else 1e-6)     # k^3 reaches 2.6e5 at 64 modes
         layer.Q_coeffs[..., 0, 0, 0] = q0
     x = torch.randn(1, C, *grid)
     g = torch.randn(1, C, *grid)
