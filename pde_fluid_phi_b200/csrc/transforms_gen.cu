@@ -97,7 +97,7 @@ enum { ZB_FULL = 0, ZB_EMPTY = MAX_RING, ZB_DFULL = 2 * MAX_RING, ZB_DEMPTY = 2 
 
 __global__ void __launch_bounds__(ZA_THREADS, 1)
 gen_z_analysis_kernel(const __grid_constant__ CUtensorMap tmap_x, float* __restrict__ W, const float* __restrict__ Bimg,
-                      int ntiles, int NKB, int NBm, int ldz, int nring) {
+                      long long rows, int ntiles, int NKB, int NBm, int ldz, int nring) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -164,6 +164,7 @@ gen_z_analysis_kernel(const __grid_constant__ CUtensorMap tmap_x, float* __restr
       mbar_wait(bar(ZB_DFULL + d), (it >> 1) & 1);
       tc_fence_after();
       float* wrow = W + ((size_t)t * 128 + 32 * q) * ldz;
+      const int nvalid = (int)min(32LL, rows - ((long long)t * 128 + 32 * q));   // the last tile may be partial
       for (int c0 = 0; c0 < ldz; c0 += 32) {
         float v[32];
         tmem_ld32(tmem + d * 128 + lane_base + c0, v);
@@ -180,8 +181,9 @@ gen_z_analysis_kernel(const __grid_constant__ CUtensorMap tmap_x, float* __restr
         const int lpr = min(32, ldz - c0) >> 2;            // float4 lanes per row of this chunk
         for (int idx = lane; idx < 32 * lpr; idx += 32) {
           const int row = idx / lpr, c4 = idx - row * lpr;
-          *reinterpret_cast<float4*>(wrow + (size_t)row * ldz + c0 + 4 * c4) =
-              *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
+          if (row < nvalid)
+            *reinterpret_cast<float4*>(wrow + (size_t)row * ldz + c0 + 4 * c4) =
+                *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
         }
         __syncwarp();
       }
@@ -214,8 +216,8 @@ __host__ __device__ inline ZSSmem zs_smem(int zN, int NKBK, int nring) {
 template <int NADD>
 __global__ void __launch_bounds__(ZS_THREADS, 1)
 gen_z_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_v, float* __restrict__ out, const float* __restrict__ add0,
-                       const float* __restrict__ add1, const float* __restrict__ Bimg, int ntiles, int zN, int NKBK,
-                       int ksteps, int nring, int tmem_cols) {
+                       const float* __restrict__ add1, const float* __restrict__ Bimg, long long rows, int ntiles, int zN,
+                       int NKBK, int ksteps, int nring, int tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -284,16 +286,19 @@ gen_z_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_v, float* __rest
       const int t = blockIdx.x + it * gridDim.x;
       mbar_wait(bar(ZB_DFULL + grp), (it >> 1) & 1);
       tc_fence_after();
+      const int nvalid = (int)min(32LL, rows - ((long long)t * 128 + 32 * q)) - rsub;   // rows 4j + rsub < valid count
       for (int r = 0; r < nrounds; ++r) {
         const size_t gbase = ((size_t)t * 128 + 32 * q + rsub) * zN + r * 32 + 4 * c4;
         float4 a0v[NADD >= 1 ? 8 : 1], a1v[NADD == 2 ? 8 : 1];
         if (NADD >= 1) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a0v[j] = __ldcs(reinterpret_cast<const float4*>(add0 + gbase + (size_t)(4 * j) * zN));
+          for (int j = 0; j < 8; ++j)
+            if (4 * j < nvalid) a0v[j] = __ldcs(reinterpret_cast<const float4*>(add0 + gbase + (size_t)(4 * j) * zN));
         }
         if (NADD == 2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a1v[j] = __ldcs(reinterpret_cast<const float4*>(add1 + gbase + (size_t)(4 * j) * zN));
+          for (int j = 0; j < 8; ++j)
+            if (4 * j < nvalid) a1v[j] = __ldcs(reinterpret_cast<const float4*>(add1 + gbase + (size_t)(4 * j) * zN));
         }
         float v[32];
         tmem_ld32(tmem + grp * zN + lane_base + r * 32, v);
@@ -313,7 +318,7 @@ gen_z_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_v, float* __rest
           float4 o = *reinterpret_cast<const float4*>(st + (4 * j + rsub) * ST_LD + 4 * c4);
           if (NADD >= 1) { o.x += a0v[j].x; o.y += a0v[j].y; o.z += a0v[j].z; o.w += a0v[j].w; }
           if (NADD == 2) { o.x += a1v[j].x; o.y += a1v[j].y; o.z += a1v[j].z; o.w += a1v[j].w; }
-          __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)(4 * j) * zN), o);
+          if (4 * j < nvalid) __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)(4 * j) * zN), o);
         }
       }
     }
@@ -472,7 +477,7 @@ __host__ __device__ inline ASSmem as_smem(int N, int mk, int nst) {
   s.nst = nst;
   s.stage = o; o += (uint32_t)nst * 2 * mk * 128;
   o = (o + 1023u) & ~1023u;
-  s.ac = o; o += (uint32_t)N * mk * 4;
+  s.ac = o; o += (uint32_t)N * mk * 4;       // N here = output rows padded to a multiple of 128
   s.as = o; o += (uint32_t)N * mk * 4;
   s.stg = o; o += AS_EPI * 32 * ST_LD * 4;
   s.bars = o; o += 256;
@@ -483,13 +488,13 @@ __host__ __device__ inline ASSmem as_smem(int N, int mk, int nst) {
 
 __global__ void __launch_bounds__(AS_THREADS, 1)
 gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __restrict__ U, const float* __restrict__ Acimg,
-                          const float* __restrict__ Asimg, int N, int m, int mk, int ld_out, int ntn, int nmt,
+                          const float* __restrict__ Asimg, int N, int Npad, int m, int mk, int ld_out, int ntn, int nmt,
                           long long ntiles, int nst) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const ASSmem L = as_smem(N, mk, nst);
+  const ASSmem L = as_smem(Npad, mk, nst);
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t box = (uint32_t)mk * 128;
@@ -498,7 +503,7 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
     const float4* s2 = reinterpret_cast<const float4*>(Asimg);
     float4* d1 = reinterpret_cast<float4*>(sm + L.ac);
     float4* d2 = reinterpret_cast<float4*>(sm + L.as);
-    for (int i = threadIdx.x; i < N * mk / 4; i += AS_THREADS) { d1[i] = __ldg(s1 + i); d2[i] = __ldg(s2 + i); }
+    for (int i = threadIdx.x; i < Npad * mk / 4; i += AS_THREADS) { d1[i] = __ldg(s1 + i); d2[i] = __ldg(s2 + i); }
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < AS_MAXST; ++i) { mbar_init(bar(AB_FULL + i), 1); mbar_init(bar(AB_EMPTY + i), 1); }
@@ -538,7 +543,7 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
         mbar_wait(bar(AB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
         for (int ks = 0; ks < mk / 8; ++ks) {
-          const uint32_t aoff = (uint32_t)(ks >> 2) * (uint32_t)N * 128 + (uint32_t)mt * 16384 + (uint32_t)(ks & 3) * 32;
+          const uint32_t aoff = (uint32_t)(ks >> 2) * (uint32_t)Npad * 128 + (uint32_t)mt * 16384 + (uint32_t)(ks & 3) * 32;
           const uint64_t bd = desc_mn(base + L.stage + s * 2 * box + ks * 1024, box);
           mma_ss(tmem + d * 128, umma_desc(base + L.ac + aoff, 1024), bd, id, ks ? 1u : 0u);
           mma_ss(tmem + d * 128 + NT, umma_desc(base + L.as + aoff, 1024), bd, id, ks ? 1u : 0u);
@@ -583,7 +588,7 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const int row = 4 * g + rsub;
-        if (n0 + 4 * c4 < ld_out)
+        if (n0 + 4 * c4 < ld_out && mt * 128 + 32 * q + row < N)
           *reinterpret_cast<float4*>(ub + (size_t)row * ld_out + 4 * c4) = *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
       }
       __syncwarp();
@@ -658,7 +663,7 @@ int gen_plan_init(Plan* p) {
   g.nbm = (g.ldz + 15) / 16 * 16;
   g.mky = p->my <= 32 ? 32 : 64;
   g.mkx = p->mx <= 32 ? 32 : 64;
-  auto axis_ok = [](int N, int m) { return N % 128 == 0 && N <= 256 && m <= 64; };
+  auto axis_ok = [](int N, int m) { return N % 32 == 0 && N <= 256 && m <= 64; };
   bool ok = g.zN % 32 == 0 && g.zN >= 32 && g.zN <= 256 && g.nbm <= 128 && axis_ok(p->Nx, p->mx);
   if (!two_d) ok = ok && axis_ok(p->Ny, p->my) && (p->my * p->mzh) % 2 == 0;
   if (!ok || !tensor_map_encoder(nullptr)) return PDEPHI_OK;
@@ -682,8 +687,9 @@ int gen_plan_init(Plan* p) {
     const int ns = (int)((smem_budget(p) - fixed) / (2 * (size_t)N * 128));
     return ns > gen::AA_MAXST ? gen::AA_MAXST : ns;
   };
+  auto pad128 = [](int N) { return (N + 127) / 128 * 128; };
   auto as_stages = [&](int N, int mk) {
-    const size_t fixed = gen::as_smem(N, mk, 0).total + 1024;
+    const size_t fixed = gen::as_smem(pad128(N), mk, 0).total + 1024;
     if (smem_budget(p) < fixed) return 0;
     const int ns = (int)((smem_budget(p) - fixed) / (2 * (size_t)mk * 128));
     return ns > gen::AS_MAXST ? gen::AS_MAXST : ns;
@@ -695,8 +701,8 @@ int gen_plan_init(Plan* p) {
   if (g.xa_st < 2 || g.xs_st < 2 || g.ya_st < 2 || g.ys_st < 2) return PDEPHI_OK;
 
   const size_t n_za = (size_t)g.nbm * g.zN, n_zs = (size_t)g.zN * NKBK * 32;
-  const size_t n_ya = two_d ? 0 : (size_t)128 * p->Ny, n_ys = two_d ? 0 : (size_t)p->Ny * g.mky;
-  const size_t n_xa = (size_t)128 * p->Nx, n_xs = (size_t)p->Nx * g.mkx;
+  const size_t n_ya = two_d ? 0 : (size_t)128 * p->Ny, n_ys = two_d ? 0 : (size_t)pad128(p->Ny) * g.mky;
+  const size_t n_xa = (size_t)128 * p->Nx, n_xs = (size_t)pad128(p->Nx) * g.mkx;
   const size_t total = (2 * n_za + 2 * n_zs + n_ya + 2 * n_ys + n_xa + 2 * n_xs) * sizeof(float);
   PDEPHI_CUDA(cudaMalloc(&p->gen_arena, total));
   PDEPHI_CUDA(cudaMemset(p->gen_arena, 0, total));
@@ -719,12 +725,12 @@ int gen_plan_init(Plan* p) {
   genimg(g.zs[1], 1, g.zN, NKBK * 32, g.zN, 0, g.zm, 0);      // synthesis ADJOINT: plain
   if (!two_d) {
     genimg(g.ya, 2, 128, p->Ny, p->Ny, 0, p->my, 0);
-    genimg(g.ysc, 3, p->Ny, g.mky, p->Ny, 0, p->my, 0);
-    genimg(g.yss, 4, p->Ny, g.mky, p->Ny, 0, p->my, 0);
+    genimg(g.ysc, 3, pad128(p->Ny), g.mky, p->Ny, 0, p->my, 0);
+    genimg(g.yss, 4, pad128(p->Ny), g.mky, p->Ny, 0, p->my, 0);
   }
   genimg(g.xa, 2, 128, p->Nx, p->Nx_total, p->x_offset, p->mx, 0);
-  genimg(g.xsc, 3, p->Nx, g.mkx, p->Nx_total, p->x_offset, p->mx, 0);
-  genimg(g.xss, 4, p->Nx, g.mkx, p->Nx_total, p->x_offset, p->mx, 0);
+  genimg(g.xsc, 3, pad128(p->Nx), g.mkx, p->Nx_total, p->x_offset, p->mx, 0);
+  genimg(g.xss, 4, pad128(p->Nx), g.mkx, p->Nx_total, p->x_offset, p->mx, 0);
   PDEPHI_LAUNCH_CHECK("gen_image_kernel");
   p->gen_ok = 1;
   return PDEPHI_OK;
@@ -777,15 +783,16 @@ static int launch_axis_synthesis(const Plan* p, const float* in, long long nb, i
   int rc = gen_make_map(&map, in, nb * m, ld, mk, true);
   if (rc) return rc;
   const int ntn = (ld + gen::NT - 1) / gen::NT;
-  const int nmt = N / 128;
+  const int Npad = (N + 127) / 128 * 128;
+  const int nmt = Npad / 128;
   const long long ntiles = nb * ntn * nmt;
-  const size_t smem = gen::as_smem(N, mk, nst).total + 1024;
+  const size_t smem = gen::as_smem(Npad, mk, nst).total + 1024;
   const int grid = (int)(ntiles < p->num_sms ? ntiles : p->num_sms);
   auto k = gen::gen_axis_synthesis_kernel;
   PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope ps(kid, st);
-    k<<<grid, gen::AS_THREADS, smem, st>>>(map, out, Ac, As, N, m, mk, ld, ntn, nmt, ntiles, nst);
+    k<<<grid, gen::AS_THREADS, smem, st>>>(map, out, Ac, As, N, Npad, m, mk, ld, ntn, nmt, ntiles, nst);
   }
   PDEPHI_LAUNCH_CHECK("gen_axis_synthesis_kernel");
   return PDEPHI_OK;
@@ -803,14 +810,14 @@ int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int dir
     int rc = gen_make_map(&map, x, rows, g.zN, 128, false);
     if (rc) return rc;
     const int NKB = g.zN / 32;
-    const int ntiles = (int)(rows / 128);
+    const int ntiles = (int)((rows + 127) / 128);
     const size_t smem = gen::za_smem(NKB, g.nbm, g.za_ring).total + 1024;
     const int grid = ntiles < p->num_sms ? ntiles : p->num_sms;
     auto k = gen::gen_z_analysis_kernel;
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       ProfScope ps(K_GEN_Z_ANALYSIS, st);
-      k<<<grid, gen::ZA_THREADS, smem, st>>>(map, W1, g.za[direction], ntiles, NKB, g.nbm, g.ldz, g.za_ring);
+      k<<<grid, gen::ZA_THREADS, smem, st>>>(map, W1, g.za[direction], rows, ntiles, NKB, g.nbm, g.ldz, g.za_ring);
     }
     PDEPHI_LAUNCH_CHECK("gen_z_analysis_kernel");
   }
@@ -863,7 +870,7 @@ int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0,
   int rc = gen_make_map(&map, zin, rows, g.ldz, 128, false);
   if (rc) return rc;
   const int NKBK = (g.ldz + 31) / 32, ksteps = (g.ldz + 7) / 8;
-  const int ntiles = (int)(rows / 128);
+  const int ntiles = (int)((rows + 127) / 128);
   const size_t smem = gen::zs_smem(g.zN, NKBK, g.zs_ring).total + 1024;
   const int grid = ntiles < p->num_sms ? ntiles : p->num_sms;
   const int tmem_cols = pow2_at_least(2 * g.zN);
@@ -874,8 +881,8 @@ int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0,
     auto k = gen::gen_z_synthesis_kernel<NA>;                                                                            \
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
     ProfScope ps(K_GEN_Z_SYNTHESIS, st);                                                                                 \
-    k<<<grid, gen::ZS_THREADS, smem, st>>>(map, out, add0, add1, g.zs[direction], ntiles, g.zN, NKBK, ksteps, g.zs_ring, \
-                                           tmem_cols);                                                                   \
+    k<<<grid, gen::ZS_THREADS, smem, st>>>(map, out, add0, add1, g.zs[direction], rows, ntiles, g.zN, NKBK, ksteps,     \
+                                           g.zs_ring, tmem_cols);                                                        \
   }
   if (nadd == 0) PDEPHI_GZS_LAUNCH(0) else if (nadd == 1) PDEPHI_GZS_LAUNCH(1) else PDEPHI_GZS_LAUNCH(2)
 #undef PDEPHI_GZS_LAUNCH

@@ -144,7 +144,9 @@ SHAPES = [((16, 16, 16), (8, 8, 8)), ((16, 12, 20), (6, 4, 8)), ((9, 7, 11), (5,
           # per-axis tensor-core route (transforms_gen.cu): up to 64 modes per axis, axes up to 256, 2-D grids, odd mzh
           # (padded intermediate rows), retained Nyquist, mx > 32 with my <= 32
           ((128, 128, 32), (5, 8, 9)), ((128, 128, 128), (64, 64, 64)), ((128, 256, 64), (10, 40, 30)),
-          ((128, 128, 1), (32, 16, 1)), ((256, 256, 1), (64, 64, 1)), ((256, 128, 96), (33, 20, 40)), ((128, 128, 64), (16, 16, 64))]
+          ((128, 128, 1), (32, 16, 1)), ((256, 256, 1), (64, 64, 1)), ((256, 128, 96), (33, 20, 40)), ((128, 128, 64), (16, 16, 64)),
+          # ... axes shorter than one 128-row tile, partial last row tile of the z stages
+          ((64, 128, 32), (8, 8, 9)), ((32, 64, 32), (8, 16, 16)), ((96, 32, 1), (20, 8, 1))]
 
 
 @pytest.mark.parametrize("grid,modes", SHAPES)
@@ -350,7 +352,9 @@ def test_pointwise_linear_vs_torch(B, Cin, Cout, grid):
 
 @pytest.mark.parametrize("grid,modes,nslab,precision", [((16, 12, 20), (6, 4, 8), 2, "fp32"), ((32, 32, 32), (8, 8, 8), 4, "fp32"),
                                                         ((8, 128, 128), (8, 16, 16), 2, "tf32"), ((8, 128, 128), (8, 16, 16), 2, "tf32x3"),
-                                                        ((256, 128, 64), (12, 16, 24), 2, "tf32x3")])
+                                                        ((256, 128, 64), (12, 16, 24), 2, "tf32x3"),
+                                                        # per-axis route: 64 modes on 256 x planes in 2 and 8 slabs (cfg 5's shape family)
+                                                        ((256, 128, 128), (64, 64, 64), 2, "tf32"), ((256, 128, 32), (40, 64, 16), 8, "tf32")])
 def test_slab_plans_on_one_gpu(grid, modes, nslab, precision):
     """The slab-decomposed transform, ranks emulated sequentially on one GPU: partial spectra of the x slabs sum
     to the transform of the whole volume, and each slab's synthesis equals its rows of the whole synthesis."""
