@@ -444,6 +444,29 @@ def layer_times(dev, precision):
     x1 = torch.randn(4, 32, 32, 32, 32, device=dev, requires_grad=True)
     out["SpectralConv3D [4,32,32^3] modes 8^3 (fp32, cfg 1)"] = run(pb.SpectralConv3D(32, 32, (8, 8, 8)).to(dev), x1)
     out["RationalFourierLayer [4,32,32^3] modes 8^3 (fp32, cfg-1 shape)"] = run(pb.RationalFourierLayer(32, 32, (8, 8, 8)).to(dev), x1)
+    del x1
+    if precision == "tf32":
+        # shapes of configs 3-5: the per-axis tensor-core route (transforms_gen.cu)
+        def conditioned(layer):           # k^3 reaches 2.6e5 at 64 modes: keep Q(k) away from its poles (timing is value-independent)
+            with torch.no_grad():
+                q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+                layer.Q_coeffs.mul_(1e-6)
+                layer.Q_coeffs[..., 0, 0, 0] = q0
+            layer.precision = precision
+            return layer
+        x3 = torch.randn(64, 64, 256, 256, 1, device=dev, requires_grad=True)
+        sc3 = pb.SpectralConv3D(64, 64, (64, 64, 1)).to(dev)
+        sc3.precision = precision
+        out["SpectralConv3D [64,64,256,256,1] modes (64,64,1) (tf32, cfg 3)"] = run(sc3, x3)
+        del x3, sc3
+        x4 = torch.randn(1, 64, 128, 128, 128, device=dev, requires_grad=True)
+        out["RationalFourierLayer [1,64,128^3] modes 64^3 (tf32, cfg 4 small-scale operator)"] = run(
+            conditioned(pb.RationalFourierLayer(64, 64, (64, 64, 64)).to(dev)), x4)
+        del x4
+        x5 = torch.randn(1, 64, 256, 256, 256, device=dev, requires_grad=True)
+        out["RationalFourierLayer [1,64,256^3] modes 64^3 (tf32, cfg 5)"] = run(
+            conditioned(pb.RationalFourierLayer(64, 64, (64, 64, 64)).to(dev)), x5)
+        del x5
     return out
 
 

@@ -55,6 +55,11 @@ enum pdephi_precision {
  *  synthesis: FORWARD = zero-padded irfftn (1/N, C2R)     ADJOINT = backward of analysis(FORWARD) */
 enum pdephi_direction { PDEPHI_FORWARD = 0, PDEPHI_ADJOINT = 1 };
 
+/* Which stages of a transform one call runs.  The (z,y) stages act on every x plane independently and the x stage on
+ * every (ky,kz) column independently: the seam of the slab-decomposed transform, where an all-to-all re-partitions the
+ * small intermediate T [BC, Nx, my, mzh] complex between "x slab, all ky" and "all x, ky subset" (SURVEY.md section 8e). */
+enum pdephi_stages { PDEPHI_STAGES_ZY = 1, PDEPHI_STAGES_X = 2, PDEPHI_STAGES_ALL = 3 };
+
 int pdephi_version(void);
 const char* pdephi_last_error(void);
 
@@ -67,8 +72,9 @@ int pdephi_plan_create(pdephi_plan_t* plan, int device, int Nx, int Ny, int Nz, 
 int pdephi_plan_create_slab(pdephi_plan_t* plan, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh,
                             int Nx_total, int x_offset);
 int pdephi_plan_destroy(pdephi_plan_t plan);
-/* 1 if the plan's (grid, modes) shape is covered by the kernels of `precision` (FP32 covers every shape; the
- * tensor-core routes need Ny = 128, Nz in {64,128}, my <= 32, mzh <= 20), else 0 */
+/* 1 if the plan's (grid, modes) shape is covered by the kernels of `precision` (FP32 covers every shape; TF32X3 and the fused
+ * TF32 kernels need Ny = 128, Nz in {64,128}, my <= 32, mzh <= 20; TF32 additionally covers, through the per-axis
+ * kernels, axes that are multiples of 32 up to 256 with up to 64 retained modes each and 2-D grids [Nx,Ny,1]), else 0 */
 int pdephi_plan_supports(pdephi_plan_t plan, int precision);
 /* bytes of scratch the two transforms need for `BC` (= batch*channels) volumes */
 size_t pdephi_plan_workspace_bytes(pdephi_plan_t plan, long long BC);
@@ -80,6 +86,12 @@ size_t pdephi_plan_workspace_bytes(pdephi_plan_t plan, long long BC);
  * ADJOINT additionally multiplies by c_kz/(Nx*Ny*Nz): the backward of K3(FORWARD). */
 int pdephi_analysis_r2c(pdephi_plan_t plan, const float* x, float* X, long long BC, int direction,
                         int precision, void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
+/* K1 by stages.  ZY: in = x [BC,Nx,Ny,Nz] float -> out = T [BC,Nx,my,mzh] complex (ADJOINT carries the c_kz/N weights);
+ * X: in = T [BC,Nx,my,mzh] complex -> out = X [BC,mx,my,mzh] complex (the plan's Nx planes and my*mzh columns: a plan
+ * built for the whole x extent and this rank's ky subset);  ALL = pdephi_analysis_r2c.  2-D grids: ALL only. */
+int pdephi_analysis_stages(pdephi_plan_t plan, const float* in, float* out, long long BC, int direction, int precision,
+                           int stages, void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
 
 /* ---- K3: pruned complex-to-real synthesis transform, fused scaling and skip adds ------------
  * replaces zeros_like/zeros + slice-assign + torch.fft.irfftn(out_ft, s=x.shape[-3:])
@@ -95,6 +107,13 @@ int pdephi_synthesis_c2r(pdephi_plan_t plan, const float* Z, float* out, const f
                          const float* addend1, const float* mode_scale, const float* row_scale,
                          long long row_scale_stride, long long BC, int direction, int precision,
                          void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
+/* K3 by stages.  X: in = Z [BC,mx,my,mzh] -> out = T [BC,Nx,my,mzh] complex, scales applied, addends must be NULL;
+ * ZY: in = T -> out [BC,Nx,Ny,Nz] float + addends, scales must be NULL (FORWARD carries c_kz/N);  ALL = pdephi_synthesis_c2r. */
+int pdephi_synthesis_stages(pdephi_plan_t plan, const float* in, float* out, const float* addend0, const float* addend1,
+                            const float* mode_scale, const float* row_scale, long long row_scale_stride, long long BC,
+                            int direction, int precision, int stages, void* workspace, size_t workspace_bytes,
+                            pdephi_stream_t stream);
 
 /* ---- K2: rational channel mix + StabilityProjection statistics ------------------------------
  * replaces RationalFourierLayer.rational_multiply (rational_fourier.py:73-119) and the two
@@ -115,6 +134,13 @@ int pdephi_rational_mix_fwd(const float* X, const float* P, const float* Q, cons
 /* Backward of Z = mask*s*Y (stability.py:59-103) :  dZ [B*O, M] complex -> dY [B*O, M] complex */
 int pdephi_projection_bwd(const float* dZ, const float* Y, const float* mask, const float* stats,
                           float* dY, long long rows, long long M, pdephi_stream_t stream);
+
+/* The same backward when the M modes of a row are sharded over several GPUs (slab-decomposed transform, all-to-all
+ * route): phase 1 writes this shard's partial G[row] = sum_k Re(conj(dZ) mask Y) (dY untouched); the caller sums G over
+ * the shards (NCCL all-reduce of `rows` floats); phase 2 applies dY = m s dZ + G s (1/a - m^2/b) Y with the summed G.
+ * `stats` holds the GLOBAL a, b, s of each row. */
+int pdephi_projection_bwd_sharded(const float* dZ, const float* Y, const float* mask, const float* stats, float* G,
+                                  float* dY, long long rows, long long M, int phase, pdephi_stream_t stream);
 
 /* Backward of the rational mix from the materialised R, Qe of the forward: dX [B,I,M] complex,
  * dP [O,I,op^3], dQ [O,I,oq^3] (entries with a+b+c >= order are written as zeros, as autograd does).

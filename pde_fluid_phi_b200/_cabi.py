@@ -18,6 +18,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = range(5)
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 PREC_AUTO = -1    # host-side only: TF32X3 where the plan supports it, FP32 (FFMA) elsewhere -- both meet the 1e-5 gate
 FORWARD, ADJOINT = 0, 1
+STAGES_ZY, STAGES_X, STAGES_ALL = 1, 2, 3
 PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
 
 # name -> (restype, argtypes); mirrors include/pdephi_b200.h one to one
@@ -30,6 +31,11 @@ SIGNATURES = {
     "pdephi_plan_workspace_bytes": (c_size_t, [c_void_p, c_longlong]),
     "pdephi_plan_supports": (c_int, [c_void_p, c_int]),
     "pdephi_analysis_r2c": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pdephi_analysis_stages": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pdephi_synthesis_stages": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                        c_longlong, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pdephi_projection_bwd_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong,
+                                              c_int, c_void_p]),
     "pdephi_synthesis_c2r": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                      c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pdephi_rational_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,

@@ -115,6 +115,10 @@ struct ProfScope {
   ~ProfScope() { prof_end(id, st); }
 };
 
+// which stages of a transform a call runs (include/pdephi_b200.h: pdephi_stages): the (z,y) stages act on x planes
+// independently, the x stage on (ky,kz) columns independently -- the seam of the slab-decomposed transform
+enum { ST_ZY = 1, ST_X = 2, ST_ALL = 3 };
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {

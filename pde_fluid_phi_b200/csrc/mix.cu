@@ -181,21 +181,30 @@ projection_stats_kernel(const float2* __restrict__ Y, const float* __restrict__ 
 // backward of Z = mask*s*Y:  dY = m s dZ + G s (1/a - m^2/b) Y,  G = sum_k Re(conj(dZ) m Y)
 __global__ void __launch_bounds__(ROW_THREADS)
 projection_bwd_kernel(const float2* __restrict__ dZ, const float2* __restrict__ Y, const float* __restrict__ mask,
-                      const float* __restrict__ stats, float2* __restrict__ dY, long long M) {
+                      const float* __restrict__ stats, float2* __restrict__ dY, long long M, float* __restrict__ Gext, int phase) {
+  // phase 0: whole row on this GPU;  1: partial G of this mode shard -> Gext[row], nothing else;  2: G = Gext[row] (summed)
   __shared__ double red[ROW_THREADS / 32];
   const size_t row = blockIdx.x;
   const float2* y = Y + row * (size_t)M;
   const float2* dz = dZ + row * (size_t)M;
-  float g = 0.f;
   double Gd = 0.0;
-  int n = 0;
-  for (long long k = threadIdx.x; k < M; k += ROW_THREADS) {
-    const float2 v = __ldg(y + k), d = __ldg(dz + k);
-    g = fmaf(__ldg(mask + k), fmaf(d.x, v.x, d.y * v.y), g);
-    if (++n == 64) { Gd += g; g = 0.f; n = 0; }
+  if (phase != 2) {
+    float g = 0.f;
+    int n = 0;
+    for (long long k = threadIdx.x; k < M; k += ROW_THREADS) {
+      const float2 v = __ldg(y + k), d = __ldg(dz + k);
+      g = fmaf(__ldg(mask + k), fmaf(d.x, v.x, d.y * v.y), g);
+      if (++n == 64) { Gd += g; g = 0.f; n = 0; }
+    }
+    Gd += g;
+    Gd = block_sum<ROW_THREADS>(Gd, red);
+    if (phase == 1) {
+      if (threadIdx.x == 0) Gext[row] = (float)Gd;
+      return;
+    }
+  } else {
+    Gd = (double)Gext[row];
   }
-  Gd += g;
-  Gd = block_sum<ROW_THREADS>(Gd, red);
   const float a = stats[row * 4 + 0], b = stats[row * 4 + 1], s = stats[row * 4 + 2];
   const float Gs = (float)Gd * s;
   const float ia = 1.f / a, ib = 1.f / b;
@@ -646,7 +655,21 @@ extern "C" int pdephi_projection_bwd(const float* dZ, const float* Y, const floa
   {
     ProfScope ps(K_PROJ_BWD, (cudaStream_t)stream);
     projection_bwd_kernel<<<(unsigned)rows, ROW_THREADS, 0, (cudaStream_t)stream>>>((const float2*)dZ, (const float2*)Y,
-                                                                                     mask, stats, (float2*)dY, M);
+                                                                                     mask, stats, (float2*)dY, M, nullptr, 0);
+  }
+  PDEPHI_LAUNCH_CHECK("projection_bwd_kernel");
+  return PDEPHI_OK;
+}
+
+extern "C" int pdephi_projection_bwd_sharded(const float* dZ, const float* Y, const float* mask, const float* stats, float* G,
+                                             float* dY, long long rows, long long M, int phase, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(dZ && Y && mask && stats && G, "projection_bwd_sharded: null pointer");
+  PDEPHI_REQUIRE(phase == 1 || (phase == 2 && dY), "projection_bwd_sharded: phase must be 1 or 2 (2 needs dY)");
+  PDEPHI_REQUIRE(rows > 0 && M > 0 && rows <= 0x7fffffffLL, "projection_bwd_sharded: bad size");
+  {
+    ProfScope ps(K_PROJ_BWD, (cudaStream_t)stream);
+    projection_bwd_kernel<<<(unsigned)rows, ROW_THREADS, 0, (cudaStream_t)stream>>>((const float2*)dZ, (const float2*)Y,
+                                                                                     mask, stats, (float2*)dY, M, G, phase);
   }
   PDEPHI_LAUNCH_CHECK("projection_bwd_kernel");
   return PDEPHI_OK;

@@ -798,14 +798,19 @@ static int launch_axis_synthesis(const Plan* p, const float* in, long long nb, i
   return PDEPHI_OK;
 }
 
-int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int direction, void* ws, cudaStream_t st) {
+int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int direction, void* ws, cudaStream_t st, int stages,
+                 float2* T) {
   const GenPlan& g = p->g;
   const GenWs w = gen_ws(p, BC);
   char* wb = (char*)ws;
   float* W1 = (float*)(wb + w.w1);
   float* W2 = (float*)(wb + w.w2);
+  if (stages != ST_ALL) {
+    if (!g.has_mid) return fail(PDEPHI_ERR_UNSUPPORTED, "stage-split transforms are not available for 2-D grids");
+    W2 = (float*)T;        // the exchange tensor [BC, Nx, my, mzh] takes the place of the (y -> x) intermediate
+  }
   const long long rows = BC * p->Nx * (g.has_mid ? p->Ny : 1);
-  {
+  if (stages & ST_ZY) {
     CUtensorMap map;
     int rc = gen_make_map(&map, x, rows, g.zN, 128, false);
     if (rc) return rc;
@@ -820,18 +825,32 @@ int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int dir
       k<<<grid, gen::ZA_THREADS, smem, st>>>(map, W1, g.za[direction], rows, ntiles, NKB, g.nbm, g.ldz, g.za_ring);
     }
     PDEPHI_LAUNCH_CHECK("gen_z_analysis_kernel");
+    if (g.has_mid) {
+      rc = launch_axis_analysis(p, W1, BC * p->Nx, p->Ny, p->my, g.ldz, p->mzh, (float2*)W2, g.ya, g.ya_st, K_GEN_AXIS_ANALYSIS, st);
+      if (rc) return rc;
+    }
   }
-  if (g.has_mid) {
-    int rc = launch_axis_analysis(p, W1, BC * p->Nx, p->Ny, p->my, g.ldz, p->mzh, (float2*)W2, g.ya, g.ya_st, K_GEN_AXIS_ANALYSIS, st);
-    if (rc) return rc;
+  if (!(stages & ST_X)) return PDEPHI_OK;
+  if (g.has_mid)
     return launch_axis_analysis(p, W2, BC, p->Nx, p->mx, 2 * p->my * p->mzh, p->my * p->mzh, X, g.xa, g.xa_st,
                                 K_GEN_AXIS_ANALYSIS, st);
-  }
   return launch_axis_analysis(p, W1, BC, p->Nx, p->mx, g.ldz, g.zm, X, g.xa, g.xa_st, K_GEN_AXIS_ANALYSIS, st);
 }
 
+static int launch_pad_scale(const float2* Z, float2* Zp, const float* mode_scale, const float* row_scale, long long rs_stride,
+                            int zm, int ldh, long long Mrows, long long total, cudaStream_t st) {
+  {
+    ProfScope ps(K_SCALE_MODES, st);
+    gen::gen_pad_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, Zp, mode_scale, row_scale, rs_stride, zm, ldh,
+                                                                             Mrows, total);
+  }
+  PDEPHI_LAUNCH_CHECK("gen_pad_scale_kernel");
+  return PDEPHI_OK;
+}
+
 int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1, const float* mode_scale,
-                  const float* row_scale, long long rs_stride, long long BC, int direction, void* ws, cudaStream_t st) {
+                  const float* row_scale, long long rs_stride, long long BC, int direction, void* ws, cudaStream_t st, int stages,
+                  float2* T) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(out) || !al16(add0) || !al16(add1)) return fail(PDEPHI_ERR_INVALID, "synthesis: buffers must be 16-byte aligned");
   const GenPlan& g = p->g;
@@ -840,30 +859,49 @@ int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0,
   float* W1 = (float*)(wb + w.w1);
   float* W2 = (float*)(wb + w.w2);
   float* Zp = (float*)(wb + w.zp);
-  const float* src = (const float*)Z;
   const int ldh = g.ldz / 2;
-  if (mode_scale || row_scale || g.ldz != 2 * g.zm) {
-    const long long Mrows = (long long)p->mx * g.ym;
-    const long long total = BC * Mrows * ldh;
-    {
-      ProfScope ps(K_SCALE_MODES, st);
-      gen::gen_pad_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, (float2*)Zp, mode_scale, row_scale, rs_stride,
-                                                                               g.zm, ldh, Mrows, total);
-    }
-    PDEPHI_LAUNCH_CHECK("gen_pad_scale_kernel");
-    src = Zp;
-  }
+  const long long Mrows = (long long)p->mx * g.ym;
   const long long rows = BC * p->Nx * (g.has_mid ? p->Ny : 1);
+  if (stages != ST_ALL && !g.has_mid) return fail(PDEPHI_ERR_UNSUPPORTED, "stage-split transforms are not available for 2-D grids");
+  if (stages == ST_X) {
+    // x stage alone: scaled modes -> unpadded exchange tensor T [BC, Nx, my, mzh]
+    const float* src = (const float*)Z;
+    if (mode_scale || row_scale) {
+      int rc = launch_pad_scale(Z, (float2*)Zp, mode_scale, row_scale, rs_stride, g.zm, g.zm, Mrows, BC * Mrows * g.zm, st);
+      if (rc) return rc;
+      src = Zp;
+    }
+    return launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, 2 * p->my * p->mzh, (float*)T, g.xsc, g.xss, g.xs_st,
+                                 K_GEN_AXIS_SYNTHESIS, st);
+  }
   const float* zin;
-  if (g.has_mid) {
-    int rc = launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, g.ym * g.ldz, W2, g.xsc, g.xss, g.xs_st, K_GEN_AXIS_SYNTHESIS, st);
-    if (rc) return rc;
-    rc = launch_axis_synthesis(p, W2, BC * p->Nx, p->Ny, p->my, g.mky, g.ldz, W1, g.ysc, g.yss, g.ys_st, K_GEN_AXIS_SYNTHESIS, st);
+  if (stages == ST_ZY) {
+    // (y,z) stages alone from the unpadded exchange tensor: re-pad its rows when 2*mzh is not a multiple of 4
+    const float* src = (const float*)T;
+    if (g.ldz != 2 * g.zm) {
+      int rc = launch_pad_scale(T, (float2*)W2, nullptr, nullptr, 0, g.zm, ldh, 1, BC * p->Nx * (long long)p->my * ldh, st);
+      if (rc) return rc;
+      src = W2;
+    }
+    int rc = launch_axis_synthesis(p, src, BC * p->Nx, p->Ny, p->my, g.mky, g.ldz, W1, g.ysc, g.yss, g.ys_st, K_GEN_AXIS_SYNTHESIS, st);
     if (rc) return rc;
     zin = W1;
   } else {
-    int rc = launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, g.ldz, W1, g.xsc, g.xss, g.xs_st, K_GEN_AXIS_SYNTHESIS, st);
-    if (rc) return rc;
+    const float* src = (const float*)Z;
+    if (mode_scale || row_scale || g.ldz != 2 * g.zm) {
+      int rc = launch_pad_scale(Z, (float2*)Zp, mode_scale, row_scale, rs_stride, g.zm, ldh, Mrows, BC * Mrows * ldh, st);
+      if (rc) return rc;
+      src = Zp;
+    }
+    if (g.has_mid) {
+      int rc = launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, g.ym * g.ldz, W2, g.xsc, g.xss, g.xs_st, K_GEN_AXIS_SYNTHESIS, st);
+      if (rc) return rc;
+      rc = launch_axis_synthesis(p, W2, BC * p->Nx, p->Ny, p->my, g.mky, g.ldz, W1, g.ysc, g.yss, g.ys_st, K_GEN_AXIS_SYNTHESIS, st);
+      if (rc) return rc;
+    } else {
+      int rc = launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, g.ldz, W1, g.xsc, g.xss, g.xs_st, K_GEN_AXIS_SYNTHESIS, st);
+      if (rc) return rc;
+    }
     zin = W1;
   }
   CUtensorMap map;

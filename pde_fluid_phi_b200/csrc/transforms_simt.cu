@@ -330,7 +330,9 @@ int xstage_synthesis(const Plan* p, const float2* Z, float2* ws, const float* mo
 }
 
 int analysis_simt(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws,
-                  cudaStream_t st) {
+                  cudaStream_t st, int stages, float2* T) {
+  if (stages != ST_ALL) ws = T;                 // the exchange tensor takes the place of the intermediate
+  if (!(stages & ST_ZY)) return xstage_analysis(p, ws, X, BC, st);
   const int Ny = p->Ny, Nz = p->Nz, my = p->my, mzh = p->mzh;
   const bool vec4 = (Nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const int ldx = vec4 ? Nz + 4 : Nz + 1;
@@ -365,17 +367,20 @@ int analysis_simt(const Plan* p, const float* x, float2* X, long long BC, int di
   }
 #undef LAUNCH_A
   PDEPHI_LAUNCH_CHECK("analysis_zy_kernel");
+  if (!(stages & ST_X)) return PDEPHI_OK;
   return xstage_analysis(p, ws, X, BC, st);
 }
 
 int synthesis_simt(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1,
                    const float* mode_scale, const float* row_scale, long long rs_stride, long long BC,
-                   int direction, float2* ws, cudaStream_t st) {
+                   int direction, float2* ws, cudaStream_t st, int stages, float2* T) {
   const int Ny = p->Ny, Nz = p->Nz, my = p->my, mzh = p->mzh;
-  {
+  if (stages != ST_ALL) ws = T;
+  if (stages & ST_X) {
     int rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
     if (rc) return rc;
   }
+  if (!(stages & ST_ZY)) return PDEPHI_OK;
   size_t smem = ((size_t)my * mzh + (size_t)Ny * mzh) * sizeof(float2);
   if (smem > p->smem_optin)
     return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis: %d y rows x %d kz modes do not fit shared memory", Ny, mzh);

@@ -541,7 +541,10 @@ int xstage_analysis_tc(const Plan* p, const float2* ws, float2* X, long long BC,
 int xstage_synthesis_tc(const Plan* p, const float2* Z, float2* ws, float2* scratch, const float* mode_scale,
                         const float* row_scale, long long rs_stride, long long BC, cudaStream_t st);
 
-int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws, cudaStream_t st) {
+int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws, cudaStream_t st,
+                int stages, float2* T) {
+  if (stages != ST_ALL) ws = T;
+  if (!(stages & ST_ZY)) return xstage_analysis_tc_ok(p) ? xstage_analysis_tc(p, ws, X, BC, st) : xstage_analysis(p, ws, X, BC, st);
   const size_t planes = (size_t)BC * p->Nx;
   if (planes * 128 > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "analysis_tc: too many rows for the tensor map");
   if (reinterpret_cast<uintptr_t>(x) & 15) return fail(PDEPHI_ERR_INVALID, "analysis_tc: x must be 16-byte aligned");
@@ -565,24 +568,26 @@ int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int dire
     k<<<grid, tc::A_THREADS, smem, st>>>(tmap, ws, p->tc_b1[direction], p->tc_a2, (int)planes, NKB, p->my, p->mzh);
   }
   PDEPHI_LAUNCH_CHECK("analysis_zy_tc_kernel");
+  if (!(stages & ST_X)) return PDEPHI_OK;
   if (xstage_analysis_tc_ok(p)) return xstage_analysis_tc(p, ws, X, BC, st);
   return xstage_analysis(p, ws, X, BC, st);
 }
 
 int synthesis_tc(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1,
                  const float* mode_scale, const float* row_scale, long long rs_stride, long long BC, int direction,
-                 float2* ws, cudaStream_t st) {
+                 float2* ws, cudaStream_t st, int stages, float2* T) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(out) || !al16(add0) || !al16(add1)) return fail(PDEPHI_ERR_INVALID, "synthesis_tc: buffers must be 16-byte aligned");
-  int rc;
-  if (xstage_synthesis_tc_ok(p)) {
-    float2* scratch = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) +
-                                                align_up((size_t)BC * p->Nx * p->my * p->mzh * sizeof(float2), 1024));
-    rc = xstage_synthesis_tc(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st);
-  } else {
-    rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
+  float2* scratch = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) +
+                                              align_up((size_t)BC * p->Nx * p->my * p->mzh * sizeof(float2), 1024));
+  if (stages != ST_ALL) ws = T;
+  if (stages & ST_X) {
+    int rc;
+    if (xstage_synthesis_tc_ok(p)) rc = xstage_synthesis_tc(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st);
+    else rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
+    if (rc) return rc;
   }
-  if (rc) return rc;
+  if (!(stages & ST_ZY)) return PDEPHI_OK;
   const size_t planes = (size_t)BC * p->Nx;
   if (planes > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis_tc: too many planes");
   const tc::SSmem L = tc::synthesis_smem(p->Nz);

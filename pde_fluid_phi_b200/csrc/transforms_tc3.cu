@@ -649,7 +649,10 @@ void tc3_plan_destroy(Plan* p) {
   p->tc3_arena = nullptr;
 }
 
-int analysis_tc3(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws, cudaStream_t st) {
+int analysis_tc3(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws, cudaStream_t st,
+                 int stages, float2* T) {
+  if (stages != ST_ALL) ws = T;
+  if (!(stages & ST_ZY)) return xstage_analysis_tc3_ok(p) ? xstage_analysis_tc3(p, ws, X, BC, st) : xstage_analysis(p, ws, X, BC, st);
   const size_t planes = (size_t)BC * p->Nx;
   if (planes * 128 > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "analysis_tc3: too many rows for the tensor map");
   if (reinterpret_cast<uintptr_t>(x) & 15) return fail(PDEPHI_ERR_INVALID, "analysis_tc3: x must be 16-byte aligned");
@@ -672,24 +675,26 @@ int analysis_tc3(const Plan* p, const float* x, float2* X, long long BC, int dir
     k<<<grid, tc3::A3_THREADS, smem, st>>>(tmap, ws, p->tc3_b1[direction], p->tc3_a2, (int)planes, NKB, p->my, p->mzh);
   }
   PDEPHI_LAUNCH_CHECK("analysis_zy_tc3_kernel");
+  if (!(stages & ST_X)) return PDEPHI_OK;
   if (xstage_analysis_tc3_ok(p)) return xstage_analysis_tc3(p, ws, X, BC, st);
   return xstage_analysis(p, ws, X, BC, st);
 }
 
 int synthesis_tc3(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1,
                   const float* mode_scale, const float* row_scale, long long rs_stride, long long BC, int direction,
-                  float2* ws, cudaStream_t st) {
+                  float2* ws, cudaStream_t st, int stages, float2* T) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(out) || !al16(add0) || !al16(add1)) return fail(PDEPHI_ERR_INVALID, "synthesis_tc3: buffers must be 16-byte aligned");
-  int rc;
-  if (xstage_synthesis_tc3_ok(p)) {
-    float2* scratch = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) +
-                                                align_up((size_t)BC * p->Nx * p->my * p->mzh * sizeof(float2), 1024));
-    rc = xstage_synthesis_tc3(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st);
-  } else {
-    rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
+  float2* scratch = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) +
+                                              align_up((size_t)BC * p->Nx * p->my * p->mzh * sizeof(float2), 1024));
+  if (stages != ST_ALL) ws = T;
+  if (stages & ST_X) {
+    int rc;
+    if (xstage_synthesis_tc3_ok(p)) rc = xstage_synthesis_tc3(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st);
+    else rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
+    if (rc) return rc;
   }
-  if (rc) return rc;
+  if (!(stages & ST_ZY)) return PDEPHI_OK;
   const size_t planes = (size_t)BC * p->Nx;
   if (planes > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "synthesis_tc3: too many planes");
   const size_t smem = tc3::s3_smem(p->Nz).total + 1024;

@@ -52,8 +52,15 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
         dist.broadcast(_real_view(t.data), src=src, group=group)
 
 
-def enable_slab_parallel(model: torch.nn.Module, nx_total: int, group=None) -> torch.nn.Module:
+def enable_slab_parallel(model: torch.nn.Module, nx_total: int, group=None, exchange: str = "allreduce") -> torch.nn.Module:
     """Slab-decomposed transform for grids too large for one GPU (256^3 and above).
+
+    exchange="allreduce" (described below) replicates the retained modes; exchange="alltoall" is the transpose
+    formulation: the (z,y) stages run on the local x slab, an NCCL all-to-all re-partitions the small intermediate
+    [B,C,Nx,my,mzh] from x slabs to ky subsets (69 MB per rank and direction at 256^3 / modes 64^3 / 2 ranks, 30 MB at
+    8 ranks), the x stage, the channel mix and the projection run on this rank's ky subset only (the projection
+    energies and its backward's inner product take one tiny all-reduce each), and the inverse mirrors it.  It shards the
+    channel mix -- the dominant cost at 64^3 modes -- as well as the transforms; modes[1] must divide by the group size.
 
     Every rank of `group` holds the x slab [rank*Nx/P, (rank+1)*Nx/P) of each activation.  Inside a spectral
     layer the fused (z,y) stage and the x stage run on the local slab and produce a *partial* pruned spectrum;
@@ -63,10 +70,13 @@ def enable_slab_parallel(model: torch.nn.Module, nx_total: int, group=None) -> t
     the local rows, so the inverse needs no communication at all.  All other layers of the operator models
     are pointwise in space and stay local.  After backward, call
     ``allreduce_gradients(model.parameters(), group=group, average=False)``: pointwise-layer gradients are
-    slab-local partial sums, spectral-coefficient gradients are pre-divided by the group size.
+    slab-local partial sums, spectral-coefficient gradients are pre-divided by the group size ("allreduce") or are
+    per-ky-subset partial sums ("alltoall").
     """
+    if exchange not in ("allreduce", "alltoall"):
+        raise ValueError(f"unknown slab exchange {exchange!r} (expected 'allreduce' or 'alltoall')")
     from .operators import RationalFourierLayer, SpectralConv3D
     for m in model.modules():
         if isinstance(m, (RationalFourierLayer, SpectralConv3D)):
-            m.slab = (group, int(nx_total))
+            m.slab = (group, int(nx_total), exchange)
     return model

@@ -236,21 +236,189 @@ def block_tail_supported(h: torch.Tensor, precision: int) -> bool:
 
 
 # ------------------------------------------------------------------------------------------------
+# stage-split transforms and the all-to-all exchange of the slab-decomposed route
+# ------------------------------------------------------------------------------------------------
+def _run_stages(kind, plan, src, dst, BC, direction, precision, stages, a0=None, a1=None, mode_scale=None, row_scale=None,
+                rs_stride=0):
+    lib = _cabi.load()
+    precision = _cabi.resolve_precision(plan, precision)
+    nbytes = lib.pdephi_plan_workspace_bytes(plan, BC)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
+    if kind == "analysis":
+        _cabi.check(lib.pdephi_analysis_stages(plan, _p(src), _p(dst), BC, direction, precision, stages, _p(ws), nbytes,
+                                               _stream()), "analysis_stages")
+    else:
+        _cabi.check(lib.pdephi_synthesis_stages(plan, _p(src), _p(dst), _p(a0), _p(a1), _p(mode_scale), _p(row_scale), rs_stride,
+                                                BC, direction, precision, stages, _p(ws), nbytes, _stream()), "synthesis_stages")
+
+
+def analysis_zy(x: torch.Tensor, modes_h, direction: int, precision: int, nx_total: int) -> torch.Tensor:
+    """(z,y) stages of K1 on an x slab: x [B,C,Nxl,Ny,Nz] float32 -> T [B,C,Nxl,my,mzh] complex64 (all retained ky)."""
+    _require_cuda_f32(x, "x")
+    x = x.contiguous()
+    B, C = x.shape[:2]
+    with torch.cuda.device(x.device):
+        plan = _cabi.get_plan(x.device.index, tuple(x.shape[2:]), modes_h, (nx_total, 0))
+        T = torch.empty((B, C, x.shape[2], modes_h[1], modes_h[2]), dtype=torch.complex64, device=x.device)
+        _run_stages("analysis", plan, x, T, B * C, direction, precision, _cabi.STAGES_ZY)
+    return T
+
+
+def analysis_x(T: torch.Tensor, mx: int, grid, precision: int) -> torch.Tensor:
+    """x stage of K1 on a ky subset: T [B,C,Nx,myl,mzh] complex64 (all x planes) -> X [B,C,mx,myl,mzh]."""
+    T = T.contiguous()
+    B, C, Nx, myl, mzh = T.shape
+    with torch.cuda.device(T.device):
+        plan = _cabi.get_plan(T.device.index, (Nx, grid[1], grid[2]), (mx, myl, mzh))
+        X = torch.empty((B, C, mx, myl, mzh), dtype=torch.complex64, device=T.device)
+        _run_stages("analysis", plan, T, X, B * C, _cabi.FORWARD, precision, _cabi.STAGES_X)
+    return X
+
+
+def synthesis_x(Z: torch.Tensor, grid, mode_scale, row_scale, precision: int) -> torch.Tensor:
+    """x stage of K3 on a ky subset: Z [B,C,mx,myl,mzh] -> T [B,C,Nx,myl,mzh] (all x planes), scales applied."""
+    Z = Z.contiguous()
+    B, C, mx, myl, mzh = Z.shape
+    rs_stride = row_scale.stride(0) if row_scale is not None else 0
+    with torch.cuda.device(Z.device):
+        plan = _cabi.get_plan(Z.device.index, tuple(grid), (mx, myl, mzh))
+        T = torch.empty((B, C, grid[0], myl, mzh), dtype=torch.complex64, device=Z.device)
+        _run_stages("synthesis", plan, Z, T, B * C, _cabi.FORWARD, precision, _cabi.STAGES_X, None, None, mode_scale, row_scale,
+                    rs_stride)
+    return T
+
+
+def synthesis_zy(T: torch.Tensor, mx: int, grid_local, addend0, addend1, direction: int, precision: int, nx_total: int):
+    """(y,z) stages of K3 on an x slab: T [B,C,Nxl,my,mzh] complex64 -> out [B,C,Nxl,Ny,Nz] float32 (+ addends)."""
+    T = T.contiguous()
+    B, C, Nxl, my, mzh = T.shape
+    a0 = addend0.contiguous() if addend0 is not None else None
+    a1 = addend1.contiguous() if addend1 is not None else None
+    with torch.cuda.device(T.device):
+        plan = _cabi.get_plan(T.device.index, tuple(grid_local), (mx, my, mzh), (nx_total, 0))
+        out = torch.empty((B, C, *grid_local), dtype=torch.float32, device=T.device)
+        _run_stages("synthesis", plan, T, out, B * C, direction, precision, _cabi.STAGES_ZY, a0, a1)
+    return out
+
+
+def exchange_x_to_ky(T: torch.Tensor, group, world: int) -> torch.Tensor:
+    """All-to-all transpose "x slab, all ky" -> "all x, ky subset": [B,C,Nxl,my,mzh] -> [B,C,world*Nxl,my/world,mzh].
+    Works on any backend torch.distributed offers (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    B, C, Nxl, my, mzh = T.shape
+    myl = my // world
+    send = T.reshape(B, C, Nxl, world, myl, mzh).permute(3, 0, 1, 2, 4, 5).contiguous()      # [dest rank, B, C, Nxl, myl, mzh]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=group)  # recv[j]: rank j's x slab
+    return recv.permute(1, 2, 0, 3, 4, 5).reshape(B, C, world * Nxl, myl, mzh)
+
+
+def exchange_ky_to_x(U: torch.Tensor, group, world: int) -> torch.Tensor:
+    """The inverse transpose: [B,C,Nx,myl,mzh] -> [B,C,Nx/world,world*myl,mzh]."""
+    import torch.distributed as dist
+    B, C, Nx, myl, mzh = U.shape
+    nxl = Nx // world
+    send = U.reshape(B, C, world, nxl, myl, mzh).permute(2, 0, 1, 3, 4, 5).contiguous()       # [dest rank = x slab, ...]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=group)  # recv[j]: rank j's ky chunk
+    return recv.permute(1, 2, 3, 0, 4, 5).reshape(B, C, nxl, world * myl, mzh)
+
+
+class _Slab:
+    """How one spectral layer call is distributed: not at all, "allreduce" (partial spectra of the x slabs summed, modes
+    replicated) or "alltoall" (transpose between x slabs and ky subsets, modes and the channel mix sharded)."""
+
+    def __init__(self, slab, x):
+        self.active = slab is not None
+        self.mode, self.group, self.world, self.rank, self.nx_total, self.plan = "none", None, 1, 0, None, None
+        if not self.active:
+            return
+        import torch.distributed as dist
+        group, nx_total = slab[0], int(slab[1])
+        self.mode = slab[2] if len(slab) > 2 else "allreduce"
+        if self.mode not in ("allreduce", "alltoall"):
+            raise ValueError(f"unknown slab exchange {self.mode!r} (expected 'allreduce' or 'alltoall')")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        nx = x.shape[2]
+        if nx * self.world != nx_total:
+            raise ValueError(f"slab decomposition needs Nx_total == world * local Nx, got {nx_total} vs {self.world} * {nx}")
+        self.nx_total = nx_total
+        self.plan = (nx_total, self.rank * nx)
+
+    @property
+    def sharded(self) -> bool:
+        return self.mode == "alltoall"
+
+    def local_modes(self, t: torch.Tensor, modes_h, lead: int = 0) -> torch.Tensor:
+        """This rank's ky chunk of a per-mode table [..lead dims.., mx*my*mzh] (flattened modes) as a contiguous copy."""
+        mx, my, mzh = modes_h
+        if my % self.world:
+            raise ValueError(f"the all-to-all slab route needs modes[1] = {my} divisible by the group size {self.world}")
+        myl = my // self.world
+        v = t.reshape(*t.shape[:lead], mx, my, mzh)[..., self.rank * myl:(self.rank + 1) * myl, :]
+        return v.reshape(*t.shape[:lead], -1).contiguous()
+
+    def analysis(self, x, modes_h, direction, precision):
+        """K1 under this distribution; returns the modes this rank works on ([.., my/world, mzh] when sharded)."""
+        if not self.sharded:
+            X = analysis(x, modes_h, direction, precision, self.plan)
+            if self.active:
+                _allreduce_modes(X, self.group)     # partial sums over the x slabs -> every rank holds the full modes
+            return X
+        T = analysis_zy(x, modes_h, direction, precision, self.nx_total)
+        T = exchange_x_to_ky(T, self.group, self.world)
+        return analysis_x(T, modes_h[0], (self.nx_total, x.shape[3], x.shape[4]), precision)
+
+    def synthesis(self, Z, grid, mode_scale, row_scale, add0, add1, direction, precision):
+        if not self.sharded:
+            return synthesis(Z, grid, mode_scale, row_scale, add0, add1, direction, precision, self.plan)
+        U = synthesis_x(Z, (self.nx_total, grid[1], grid[2]), mode_scale, row_scale, precision)
+        U = exchange_ky_to_x(U, self.group, self.world)
+        return synthesis_zy(U, Z.shape[2], grid, add0, add1, direction, precision, self.nx_total)
+
+    def complete_stats(self, stats, eps: float):
+        """Sharded modes: each rank's {a, b} are sums over its ky chunk (+eps); sum them over the group, redo s."""
+        if not self.sharded:
+            return stats
+        import torch.distributed as dist
+        ab = stats[:, :2] - eps
+        dist.all_reduce(ab, op=dist.ReduceOp.SUM, group=self.group)
+        ab += eps
+        out = torch.zeros_like(stats)
+        out[:, :2] = ab
+        out[:, 2] = torch.sqrt(ab[:, 0] / ab[:, 1])
+        return out
+
+    def projection_bwd(self, dZ, Y, mask, stats):
+        if not self.sharded:
+            return projection_bwd(dZ, Y, mask, stats)
+        import torch.distributed as dist
+        rows = Y.shape[0] * Y.shape[1]
+        M = Y[0, 0].numel()
+        lib = _cabi.load()
+        with torch.cuda.device(Y.device):
+            G = torch.empty(rows, dtype=torch.float32, device=Y.device)
+            dY = torch.empty_like(Y)
+            _cabi.check(lib.pdephi_projection_bwd_sharded(_p(dZ), _p(Y), _p(mask), _p(stats), _p(G), _p(None), rows, M, 1,
+                                                          _stream()), "projection_bwd_sharded(1)")
+            dist.all_reduce(G, op=dist.ReduceOp.SUM, group=self.group)
+            _cabi.check(lib.pdephi_projection_bwd_sharded(_p(dZ), _p(Y), _p(mask), _p(stats), _p(G), _p(dY), rows, M, 2,
+                                                          _stream()), "projection_bwd_sharded(2)")
+        return dY
+
+    def finish_coeff_grads(self, *grads):
+        """Replicated modes: every rank computed the complete coefficient gradient -- pre-divide so the SUM all-reduce that
+        completes the slab-local gradients of the pointwise layers leaves it unchanged.  Sharded modes: each rank's
+        gradient is its ky chunk's partial sum, which that same SUM all-reduce completes."""
+        if self.world > 1 and not self.sharded:
+            for g in grads:
+                g.div_(self.world)
+
+
+# ------------------------------------------------------------------------------------------------
 # autograd Functions
 # ------------------------------------------------------------------------------------------------
-def _slab_args(slab, x):
-    """slab = None | (process_group, Nx_total): this rank holds x planes [rank*Nx, (rank+1)*Nx) of the grid."""
-    if slab is None:
-        return False, None, 1
-    import torch.distributed as dist
-    group, nx_total = slab
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    nx = x.shape[2]
-    if nx * world != nx_total:
-        raise ValueError(f"slab decomposition needs Nx_total == world * local Nx, got {nx_total} vs {world} * {nx}")
-    return (group if group is not None else dist.group.WORLD), (nx_total, rank * nx), world
-
-
 def _allreduce_modes(X, group):
     """Sum the slabs' partial spectra: the one collective of the slab-decomposed transform (NCCL over NVLink)."""
     import torch.distributed as dist
@@ -319,19 +487,19 @@ class RationalSpectralFn(torch.autograd.Function):
         mx, my, mz = modes
         modes_h = (mx, my, mz // 2 + 1)
         grid = tuple(x.shape[2:])
-        group, slab_plan, world = _slab_args(slab, x)
+        sl = _Slab(slab, x)
         P = P.contiguous()
         Q = Q.contiguous()
-        X = analysis(x, modes_h, _cabi.FORWARD, precision, slab_plan)
-        if group:
-            _allreduce_modes(X, group)          # partial sums over the x slabs -> every rank holds the full modes
+        if sl.sharded:      # this rank mixes its ky chunk of the modes only
+            mask, monoP, monoQ = sl.local_modes(mask, modes_h), sl.local_modes(monoP, modes_h, 1), sl.local_modes(monoQ, modes_h, 1)
+        X = sl.analysis(x, modes_h, _cabi.FORWARD, precision)
         need_grad = any(ctx.needs_input_grad[:3])
         Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
-        out = synthesis(Y, grid, mask, stats[:, 2], skip0, x if residual else None, _cabi.FORWARD, precision, slab_plan)
+        stats = sl.complete_stats(stats, eps)
+        out = sl.synthesis(Y, grid, mask, stats[:, 2], skip0, x if residual else None, _cabi.FORWARD, precision)
         if need_grad:
             ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ)
-        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, skip0 is not None, bool(residual),
-                    group, slab_plan, world)
+        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, skip0 is not None, bool(residual), sl)
         return out
 
     @staticmethod
@@ -339,25 +507,38 @@ class RationalSpectralFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         X, Y, stats, R, Qe, mask, monoP, monoQ = ctx.saved_tensors
-        modes_h, grid, coeff_shapes, precision, has0, residual, group, slab_plan, world = ctx.meta
+        modes_h, grid, coeff_shapes, precision, has0, residual, sl = ctx.meta
         g = g.contiguous()
         need_x, need_P, need_Q = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dx = dP = dQ = None
         if need_x or need_P or need_Q:
-            dZ = analysis(g, modes_h, _cabi.ADJOINT, precision, slab_plan)
-            if group:
-                _allreduce_modes(dZ, group)
-            dY = projection_bwd(dZ, Y, mask, stats)
+            dZ = sl.analysis(g, modes_h, _cabi.ADJOINT, precision)
+            dY = sl.projection_bwd(dZ, Y, mask, stats)
             dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
-            if world > 1:
-                # every rank computed the complete coefficient gradient from the replicated modes; pre-divide so the
-                # SUM all-reduce that completes the slab-local gradients of the pointwise layers leaves it unchanged
-                dP.div_(world)
-                dQ.div_(world)
+            sl.finish_coeff_grads(dP, dQ)
             if need_x:   # the residual branch's gradient (g itself) rides in the synthesis epilogue
-                dx = synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision, slab_plan)
+                dx = sl.synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision)
         return (dx, dP if need_P else None, dQ if need_Q else None, None, None, None, None, None, None,
                 g if has0 else None, None, None)
+
+
+def _local_weights(W, sl, my):
+    """This rank's ky chunk of a SpectralConv3D weight [O,I,mx,my,mz] (all of it unless the modes are sharded)."""
+    if not sl.sharded:
+        return W.contiguous()
+    if my % sl.world:
+        raise ValueError(f"the all-to-all slab route needs modes[1] = {my} divisible by the group size {sl.world}")
+    myl = my // sl.world
+    return W[:, :, :, sl.rank * myl:(sl.rank + 1) * myl, :].contiguous()
+
+
+def _scatter_weight_grad(dWl, W, sl, my):
+    if not sl.sharded:
+        return dWl
+    myl = my // sl.world
+    dW = torch.zeros_like(W)
+    dW[:, :, :, sl.rank * myl:(sl.rank + 1) * myl, :] = dWl
+    return dW
 
 
 class ComplexSpectralFn(torch.autograd.Function):
@@ -371,34 +552,30 @@ class ComplexSpectralFn(torch.autograd.Function):
         mx, my, mz = modes
         modes_h = (mx, my, mz // 2 + 1)
         grid = tuple(x.shape[2:])
-        group, slab_plan, world = _slab_args(slab, x)
-        W = W.contiguous()
-        X = analysis(x, modes_h, _cabi.FORWARD, precision, slab_plan)
-        if group:
-            _allreduce_modes(X, group)
-        Y = complex_mix_fwd(X, W, modes_h[2])
-        out = synthesis(Y, grid, None, None, skip0, x if residual else None, _cabi.FORWARD, precision, slab_plan)
-        ctx.save_for_backward(X, W)
-        ctx.meta = (modes_h, grid, precision, skip0 is not None, bool(residual), group, slab_plan, world)
+        sl = _Slab(slab, x)
+        Wl = _local_weights(W, sl, my)
+        X = sl.analysis(x, modes_h, _cabi.FORWARD, precision)
+        Y = complex_mix_fwd(X, Wl, modes_h[2])
+        out = sl.synthesis(Y, grid, None, None, skip0, x if residual else None, _cabi.FORWARD, precision)
+        ctx.save_for_backward(X, Wl, W)
+        ctx.meta = (modes_h, grid, precision, skip0 is not None, bool(residual), sl)
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     @once_differentiable
     def backward(ctx, g):
-        X, W = ctx.saved_tensors
-        modes_h, grid, precision, has0, residual, group, slab_plan, world = ctx.meta
+        X, Wl, W = ctx.saved_tensors
+        modes_h, grid, precision, has0, residual, sl = ctx.meta
         g = g.contiguous()
         dx = dW = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            dY = analysis(g, modes_h, _cabi.ADJOINT, precision, slab_plan)
-            if group:
-                _allreduce_modes(dY, group)
-            dX, dW = complex_mix_bwd(X, W, dY, modes_h[2])
-            if world > 1:
-                dW.div_(world)
+            dY = sl.analysis(g, modes_h, _cabi.ADJOINT, precision)
+            dX, dW = complex_mix_bwd(X, Wl, dY, modes_h[2])
+            sl.finish_coeff_grads(dW)
+            dW = _scatter_weight_grad(dW, W, sl, modes_h[1])
             if ctx.needs_input_grad[0]:
-                dx = synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision, slab_plan)
+                dx = sl.synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision)
         return dx, dW if ctx.needs_input_grad[1] else None, None, None, g if has0 else None, None, None
 
 
@@ -472,18 +649,19 @@ class RationalBlockFn(torch.autograd.Function):
         mx, my, mz = modes
         modes_h = (mx, my, mz // 2 + 1)
         grid = tuple(h.shape[2:])
-        group, slab_plan, world = _slab_args(slab, h)
+        sl = _Slab(slab, h)
         P, Q, Wc = P.contiguous(), Q.contiguous(), Wc.contiguous()
-        X = analysis(h, modes_h, _cabi.FORWARD, precision, slab_plan)
-        if group:
-            _allreduce_modes(X, group)
+        if sl.sharded:
+            mask, monoP, monoQ = sl.local_modes(mask, modes_h), sl.local_modes(monoP, modes_h, 1), sl.local_modes(monoQ, modes_h, 1)
+        X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
         need_grad = any(ctx.needs_input_grad)
         Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
-        spec = synthesis(Y, grid, mask, stats[:, 2], None, None, _cabi.FORWARD, precision, slab_plan)
+        stats = sl.complete_stats(stats, eps)
+        spec = sl.synthesis(Y, grid, mask, stats[:, 2], None, None, _cabi.FORWARD, precision)
         u, hout = block_tail_fwd(h, spec, Wc, bc)
         if need_grad:
             ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc)
-        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, bc is not None, group, slab_plan, world)
+        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, bc is not None, sl)
         return hout
 
     @staticmethod
@@ -491,17 +669,13 @@ class RationalBlockFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc = ctx.saved_tensors
-        modes_h, grid, coeff_shapes, precision, has_bias, group, slab_plan, world = ctx.meta
+        modes_h, grid, coeff_shapes, precision, has_bias, sl = ctx.meta
         gu, t, dWc, dbc = block_tail_bwd(g.contiguous(), u, h, Wc, has_bias)
-        dZ = analysis(gu, modes_h, _cabi.ADJOINT, precision, slab_plan)
-        if group:
-            _allreduce_modes(dZ, group)
-        dY = projection_bwd(dZ, Y, mask, stats)
+        dZ = sl.analysis(gu, modes_h, _cabi.ADJOINT, precision)
+        dY = sl.projection_bwd(dZ, Y, mask, stats)
         dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
-        if world > 1:
-            dP.div_(world)
-            dQ.div_(world)
-        dh = synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision, slab_plan)
+        sl.finish_coeff_grads(dP, dQ)
+        dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
         return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None)
 
 
@@ -517,30 +691,26 @@ class ComplexBlockFn(torch.autograd.Function):
         mx, my, mz = modes
         modes_h = (mx, my, mz // 2 + 1)
         grid = tuple(h.shape[2:])
-        group, slab_plan, world = _slab_args(slab, h)
-        W, Wc = W.contiguous(), Wc.contiguous()
-        X = analysis(h, modes_h, _cabi.FORWARD, precision, slab_plan)
-        if group:
-            _allreduce_modes(X, group)
-        Y = complex_mix_fwd(X, W, modes_h[2])
-        spec = synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, precision, slab_plan)
+        sl = _Slab(slab, h)
+        Wl, Wc = _local_weights(W, sl, my), Wc.contiguous()
+        X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
+        Y = complex_mix_fwd(X, Wl, modes_h[2])
+        spec = sl.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, precision)
         u, hout = block_tail_fwd(h, spec, Wc, bc)
-        ctx.save_for_backward(X, W, u, h, Wc)
-        ctx.meta = (modes_h, grid, precision, bc is not None, group, slab_plan, world)
+        ctx.save_for_backward(X, Wl, W, u, h, Wc)
+        ctx.meta = (modes_h, grid, precision, bc is not None, sl)
         return hout
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     @once_differentiable
     def backward(ctx, g):
-        X, W, u, h, Wc = ctx.saved_tensors
-        modes_h, grid, precision, has_bias, group, slab_plan, world = ctx.meta
+        X, Wl, W, u, h, Wc = ctx.saved_tensors
+        modes_h, grid, precision, has_bias, sl = ctx.meta
         gu, t, dWc, dbc = block_tail_bwd(g.contiguous(), u, h, Wc, has_bias)
-        dY = analysis(gu, modes_h, _cabi.ADJOINT, precision, slab_plan)
-        if group:
-            _allreduce_modes(dY, group)
-        dX, dW = complex_mix_bwd(X, W, dY, modes_h[2])
-        if world > 1:
-            dW.div_(world)
-        dh = synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision, slab_plan)
+        dY = sl.analysis(gu, modes_h, _cabi.ADJOINT, precision)
+        dX, dW = complex_mix_bwd(X, Wl, dY, modes_h[2])
+        sl.finish_coeff_grads(dW)
+        dW = _scatter_weight_grad(dW, W, sl, modes_h[1])
+        dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
         return dh, dW, None, None, dWc.view_as(Wc), dbc, None

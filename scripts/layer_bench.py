@@ -40,5 +40,22 @@ if __name__ == "__main__":
     res["SpectralConv3D cfg1 [4,32,32^3] modes 8^3 (fp32 path)"] = time_layer(sc1, x1, iters)
     rf1 = pb.RationalFourierLayer(32, 32, (8, 8, 8)).to(dev)
     res["RationalFourierLayer cfg1-shape [4,32,32^3] modes 8^3 (fp32 path)"] = time_layer(rf1, x1, iters)
+    if prec == "tf32" and "--gen" in sys.argv:
+        def conditioned(layer):
+            with torch.no_grad():
+                q0 = layer.Q_coeffs[..., 0, 0, 0].clone(); layer.Q_coeffs.mul_(1e-6); layer.Q_coeffs[..., 0, 0, 0] = q0
+            layer.precision = prec
+            return layer
+        res = {}
+        del x1
+        x3 = torch.randn(64, 64, 256, 256, 1, device=dev, requires_grad=True)
+        sc3 = pb.SpectralConv3D(64, 64, (64, 64, 1)).to(dev); sc3.precision = prec
+        res["SpectralConv3D cfg3 [64,64,256,256,1] modes (64,64,1)"] = time_layer(sc3, x3, iters)
+        del x3
+        x4 = torch.randn(1, 64, 128, 128, 128, device=dev, requires_grad=True)
+        res["RationalFourierLayer cfg4-small [1,64,128^3] modes 64^3"] = time_layer(conditioned(pb.RationalFourierLayer(64, 64, (64, 64, 64)).to(dev)), x4, iters)
+        del x4
+        x5 = torch.randn(1, 64, 256, 256, 256, device=dev, requires_grad=True)
+        res["RationalFourierLayer cfg5 [1,64,256^3] modes 64^3"] = time_layer(conditioned(pb.RationalFourierLayer(64, 64, (64, 64, 64)).to(dev)), x5, iters)
     for k, (us, kern) in res.items():
         print(f"{k}: {us:.1f} us fwd+bwd   per-kernel us: {kern}")

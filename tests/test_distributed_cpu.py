@@ -77,3 +77,40 @@ def test_slab_partial_spectra_allreduce_two_ranks():
     for r in range(world):
         got, want = out[r]
         assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-12
+
+
+def _alltoall_worker(rank, world, port, out):
+    """Slab-decomposed transform, all-to-all route: (z,y) stages on the x slab, transpose to ky subsets, x stage;
+    then the inverse transpose brings a ky-subset tensor back to x slabs.  numpy FFTs stand in for the kernels."""
+    import numpy as np
+    from pde_fluid_phi_b200.functional import exchange_x_to_ky, exchange_ky_to_x
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((2, 3, 8, 6, 10))
+    mx, my, mzh = 4, 4, 5
+    nxl, myl = x.shape[2] // world, my // world
+    T = np.fft.rfft2(x[:, :, rank * nxl:(rank + 1) * nxl], axes=(-2, -1))[..., :my, :mzh]     # [B,C,Nxl,my,mzh]
+    T2 = exchange_x_to_ky(torch.from_numpy(np.ascontiguousarray(T)).to(torch.complex64), None, world)
+    assert tuple(T2.shape) == (2, 3, 8, myl, mzh)
+    X = np.fft.fft(T2.numpy().astype(np.complex128), axis=2)[:, :, :mx]                         # x stage on the ky subset
+    back = exchange_ky_to_x(T2, None, world)                                                  # inverse transpose
+    out[rank] = (X, back.numpy(), T.astype(np.complex64))
+    dist.destroy_process_group()
+
+
+def test_slab_alltoall_transposes_two_ranks():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_alltoall_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    import numpy as np
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((2, 3, 8, 6, 10))
+    want = np.fft.rfftn(x, axes=(-3, -2, -1))[:, :, :4, :4, :5]
+    for r in range(world):
+        X, back, T = out[r]
+        ref = want[:, :, :, r * 2:(r + 1) * 2, :]
+        assert np.linalg.norm(X - ref) / np.linalg.norm(ref) < 1e-6        # complex64 exchange buffers
+        assert np.array_equal(back, T)                                      # the two transposes are exact inverses

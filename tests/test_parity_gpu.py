@@ -379,7 +379,75 @@ def test_slab_plans_on_one_gpu(grid, modes, nslab, precision):
     assert rel(acc, want) < TOL[precision]
 
 
-def _slab_rank(rank, world, port, out):
+@pytest.mark.parametrize("grid,modes,nslab,precision", [((16, 12, 20), (6, 4, 8), 2, "fp32"), ((32, 32, 32), (8, 8, 8), 4, "fp32"),
+                                                        ((8, 128, 128), (8, 16, 16), 2, "tf32"), ((8, 128, 128), (8, 16, 16), 2, "tf32x3"),
+                                                        ((256, 128, 128), (64, 64, 64), 2, "tf32"), ((256, 128, 32), (40, 64, 16), 8, "tf32")])
+def test_stage_split_transforms_on_one_gpu(grid, modes, nslab, precision):
+    """The all-to-all route's building blocks, ranks emulated on one GPU: (z,y) stages per x slab, re-partition to ky
+    subsets (here a concatenate + slice in place of the all-to-all), x stage per ky subset == the whole transform; and
+    the inverse.  Covers the FFMA, fused tcgen05, split-TF32 and per-axis tcgen05 routes through pdephi_*_stages."""
+    if precision != "fp32" and not tc_ok(grid, modes, _cabi.PRECISIONS[precision]):
+        pytest.skip("shape not covered by the tcgen05 path")
+    prec = _cabi.PRECISIONS[precision]
+    torch.manual_seed(13)
+    mh = (modes[0], modes[1], modes[2] // 2 + 1)
+    x = torch.randn(2, 3, *grid, device=DEV)
+    Z = torch.randn(2, 3, *mh, device=DEV, dtype=torch.complex64)
+    add = torch.randn(2, 3, *grid, device=DEV)
+    ms = torch.rand(mh, device=DEV) + 0.5
+    rs = torch.rand(6, 4, device=DEV) + 0.5
+    nxl, myl = grid[0] // nslab, mh[1] // nslab
+    for direction in (_cabi.FORWARD, _cabi.ADJOINT):
+        want_a = pf.analysis(x, mh, direction, _cabi.PREC_FP32)
+        T = torch.cat([pf.analysis_zy(x[:, :, r * nxl:(r + 1) * nxl].contiguous(), mh, direction, prec, grid[0])
+                       for r in range(nslab)], dim=2)                                      # [B,C,Nx,my,mzh]
+        got_a = torch.cat([pf.analysis_x(T[:, :, :, r * myl:(r + 1) * myl].contiguous(), mh[0], grid, prec)
+                           for r in range(nslab)], dim=3)
+        assert rel(got_a, want_a) < TOL[precision]
+        want_s = pf.synthesis(Z, grid, ms.reshape(-1), rs[:, 2], add, None, direction, _cabi.PREC_FP32)
+        U = torch.cat([pf.synthesis_x(Z[:, :, :, r * myl:(r + 1) * myl].contiguous(), grid,
+                                      ms[:, r * myl:(r + 1) * myl].reshape(-1).contiguous(), rs[:, 2], prec)
+                       for r in range(nslab)], dim=3)                                      # [B,C,Nx,my,mzh]
+        got_s = torch.cat([pf.synthesis_zy(U[:, :, r * nxl:(r + 1) * nxl].contiguous(), mh[0], (nxl, grid[1], grid[2]),
+                                           add[:, :, r * nxl:(r + 1) * nxl].contiguous(), None, direction, prec, grid[0])
+                           for r in range(nslab)], dim=2)
+        assert rel(got_s - add, want_s - add) < TOL[precision]
+
+
+def test_sharded_projection_backward_matches_whole_rows():
+    """pdephi_projection_bwd_sharded: partial G per mode shard, summed (the all-reduce), applied == the unsharded kernel."""
+    torch.manual_seed(5)
+    rows, mh = 6, (8, 8, 5)
+    M = mh[0] * mh[1] * mh[2]
+    Y = torch.randn(2, 3, *mh, device=DEV, dtype=torch.complex64)
+    dZ = torch.randn(2, 3, *mh, device=DEV, dtype=torch.complex64)
+    mask = torch.rand(M, device=DEV) + 0.1
+    a = (Y.abs() ** 2).reshape(rows, M).sum(1) + 1e-6
+    b = ((Y.abs() ** 2).reshape(rows, M) * mask ** 2).sum(1) + 1e-6
+    stats = torch.stack([a, b, torch.sqrt(a / b), torch.zeros_like(a)], dim=1).contiguous()
+    want = pf.projection_bwd(dZ, Y, mask, stats)
+    lib = pb.load_library()
+    halves = [(slice(0, 4),), (slice(4, 8),)]
+    Gs, parts = [], []
+    for (sl,) in halves:
+        Yl, dZl = Y[:, :, :, sl].contiguous(), dZ[:, :, :, sl].contiguous()
+        ml = mask.reshape(mh)[:, sl].reshape(-1).contiguous()
+        G = torch.empty(rows, device=DEV)
+        _cabi.check(lib.pdephi_projection_bwd_sharded(pf._p(dZl), pf._p(Yl), pf._p(ml), pf._p(stats), pf._p(G), pf._p(None), rows,
+                                                      Yl[0, 0].numel(), 1, pf._stream()))
+        Gs.append(G)
+        parts.append((Yl, dZl, ml))
+    Gsum = Gs[0] + Gs[1]
+    outs = []
+    for Yl, dZl, ml in parts:
+        dY = torch.empty_like(Yl)
+        _cabi.check(lib.pdephi_projection_bwd_sharded(pf._p(dZl), pf._p(Yl), pf._p(ml), pf._p(stats), pf._p(Gsum), pf._p(dY), rows,
+                                                      Yl[0, 0].numel(), 2, pf._stream()))
+        outs.append(dY)
+    assert rel(torch.cat(outs, dim=3), want) < 1e-6
+
+
+def _slab_rank(rank, world, port, out, exchange="allreduce"):
     import os
     import torch.distributed as dist
     from pde_fluid_phi_b200.distributed import allreduce_gradients, enable_slab_parallel
@@ -398,7 +466,7 @@ def _slab_rank(rank, world, port, out):
     ref_out = model(x).detach()
     model.zero_grad()
     # slab-parallel: this rank owns x planes [rank*nxl, (rank+1)*nxl)
-    enable_slab_parallel(model, grid[0])
+    enable_slab_parallel(model, grid[0], exchange=exchange)
     nxl = grid[0] // world
     xs, ys = x[:, :, rank * nxl:(rank + 1) * nxl].contiguous(), y[:, :, rank * nxl:(rank + 1) * nxl].contiguous()
     out_s = model(xs)
@@ -410,8 +478,9 @@ def _slab_rank(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_slab_parallel_two_gpus():
-    """Real 2-rank NCCL run of the slab-decomposed operator (skipped on a single-GPU box)."""
+@pytest.mark.parametrize("exchange", ["allreduce", "alltoall"])
+def test_slab_parallel_two_gpus(exchange):
+    """Real 2-rank NCCL run of the slab-decomposed operator, both exchanges (skipped on a single-GPU box)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import socket
@@ -421,7 +490,7 @@ def test_slab_parallel_two_gpus():
         port = s.getsockname()[1]
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_slab_rank, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_slab_rank, args=(2, port, out, exchange), nprocs=2, join=True)
     for r in range(2):
         e_out, e_grad = out[r]
         assert e_out < 1e-5 and e_grad < 5e-5, (r, e_out, e_grad)
