@@ -26,6 +26,11 @@ namespace gen {
 using namespace tcptx;
 
 constexpr int KBYTES = 16384;   // one [128 rows][32 floats] k-block
+// The tensor core truncates the raw fp32 data operand of every stage to TF32 (a mean relative bias of -2^-11).  Each
+// stage undoes it on its fp32 accumulator in the epilogue.  Folding the factor into the constant operand (as
+// transforms_tc.cu does) is only right on average: twiddles that are exactly 1.0 -- the whole DC mode, i.e. every mean
+// and every bias gradient -- round 1 + 2^-11 up to 1 + 2^-10 in TF32 and over-compensate by 4.9e-4 per stage.
+#define PDEPHI_GEN_COMP 1.00048828125f
 constexpr int ST_LD = 36;       // padded staging row (32 floats + 4)
 
 __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo) {   // MN-major TF32 operand, 128B swizzle / 32B atoms
@@ -176,7 +181,9 @@ gen_z_analysis_kernel(const __grid_constant__ CUtensorMap tmap_x, float* __restr
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) =
+              make_float4(v[4 * j] * PDEPHI_GEN_COMP, v[4 * j + 1] * PDEPHI_GEN_COMP, v[4 * j + 2] * PDEPHI_GEN_COMP,
+                          v[4 * j + 3] * PDEPHI_GEN_COMP);
         __syncwarp();
         const int lpr = min(32, ldz - c0) >> 2;            // float4 lanes per row of this chunk
         for (int idx = lane; idx < 32 * lpr; idx += 32) {
@@ -316,7 +323,12 @@ gen_z_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_v, float* __rest
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o = *reinterpret_cast<const float4*>(st + (4 * j + rsub) * ST_LD + 4 * c4);
-          if (NADD >= 1) { o.x += a0v[j].x; o.y += a0v[j].y; o.z += a0v[j].z; o.w += a0v[j].w; }
+          if (NADD >= 1) {
+            o.x = fmaf(o.x, PDEPHI_GEN_COMP, a0v[j].x); o.y = fmaf(o.y, PDEPHI_GEN_COMP, a0v[j].y);
+            o.z = fmaf(o.z, PDEPHI_GEN_COMP, a0v[j].z); o.w = fmaf(o.w, PDEPHI_GEN_COMP, a0v[j].w);
+          } else {
+            o.x *= PDEPHI_GEN_COMP; o.y *= PDEPHI_GEN_COMP; o.z *= PDEPHI_GEN_COMP; o.w *= PDEPHI_GEN_COMP;
+          }
           if (NADD == 2) { o.x += a1v[j].x; o.y += a1v[j].y; o.z += a1v[j].z; o.w += a1v[j].w; }
           if (4 * j < nvalid) __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)(4 * j) * zN), o);
         }
@@ -454,7 +466,7 @@ gen_axis_analysis_kernel(const __grid_constant__ CUtensorMap tmap_in, float2* __
         if (k < m && p0 + j < Pout) {
           const float2 c = *reinterpret_cast<const float2*>(E + k * AA_ELD + 2 * j);
           const float2 s = *reinterpret_cast<const float2*>(E + (64 + k) * AA_ELD + 2 * j);
-          outp[(size_t)k * Pout + p0 + j] = make_float2(c.x + s.y, c.y - s.x);   // (C - iS)(re + i im)
+          outp[(size_t)k * Pout + p0 + j] = make_float2((c.x + s.y) * PDEPHI_GEN_COMP, (c.y - s.x) * PDEPHI_GEN_COMP);   // (C - iS)(re + i im)
         }
       }
     }
@@ -516,7 +528,8 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
-  const long long per_mt = ntiles / nmt;
+  // a tile is (batch item, 64-column block): its operand is staged once and contracted against every 128-row block of
+  // the output (nmt of them), so the input crosses HBM exactly once
 
   if (warp == 0) {
     if (elect_one()) {
@@ -524,8 +537,8 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         mbar_wait(bar(AB_EMPTY + s), ph);
         mbar_arrive_expect_tx(bar(AB_FULL + s), 2 * box);
-        const long long r = t % per_mt, b = r / ntn;
-        const int n0 = (int)(r - b * ntn) * NT;
+        const long long b = t / ntn;
+        const int n0 = (int)(t - b * ntn) * NT;
         tma_load_2d(base + L.stage + s * 2 * box, &tmap_in, bar(AB_FULL + s), n0, (int)(b * m));
         tma_load_2d(base + L.stage + s * 2 * box + box, &tmap_in, bar(AB_FULL + s), n0 + 32, (int)(b * m));
         if (++s == nst) { s = 0; ph ^= 1; }
@@ -536,20 +549,21 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
       constexpr uint32_t id = idesc(128, NT, 0, 1);
       int s = 0; uint32_t ph = 0;
       long long it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int d = (int)(it & 1);
-        const int mt = (int)(t / per_mt);
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         mbar_wait(bar(AB_FULL + s), ph);
-        mbar_wait(bar(AB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
-        tc_fence_after();
-        for (int ks = 0; ks < mk / 8; ++ks) {
-          const uint32_t aoff = (uint32_t)(ks >> 2) * (uint32_t)Npad * 128 + (uint32_t)mt * 16384 + (uint32_t)(ks & 3) * 32;
-          const uint64_t bd = desc_mn(base + L.stage + s * 2 * box + ks * 1024, box);
-          mma_ss(tmem + d * 128, umma_desc(base + L.ac + aoff, 1024), bd, id, ks ? 1u : 0u);
-          mma_ss(tmem + d * 128 + NT, umma_desc(base + L.as + aoff, 1024), bd, id, ks ? 1u : 0u);
+        for (int mt = 0; mt < nmt; ++mt, ++it) {
+          const int d = (int)(it & 1);
+          mbar_wait(bar(AB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
+          tc_fence_after();
+          for (int ks = 0; ks < mk / 8; ++ks) {
+            const uint32_t aoff = (uint32_t)(ks >> 2) * (uint32_t)Npad * 128 + (uint32_t)mt * 16384 + (uint32_t)(ks & 3) * 32;
+            const uint64_t bd = desc_mn(base + L.stage + s * 2 * box + ks * 1024, box);
+            mma_ss(tmem + d * 128, umma_desc(base + L.ac + aoff, 1024), bd, id, ks ? 1u : 0u);
+            mma_ss(tmem + d * 128 + NT, umma_desc(base + L.as + aoff, 1024), bd, id, ks ? 1u : 0u);
+          }
+          mma_commit(bar(AB_DFULL + d));
         }
         mma_commit(bar(AB_EMPTY + s));
-        mma_commit(bar(AB_DFULL + d));
         if (++s == nst) { s = 0; ph ^= 1; }
       }
     }
@@ -559,7 +573,8 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
     float* st = reinterpret_cast<float*>(sm + L.stg) + (warp - 2) * 32 * ST_LD;
     const int rsub = lane >> 3, c4 = lane & 7;
     long long it = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
+     for (int mt = 0; mt < nmt; ++mt, ++it) {
       const int d = (int)(it & 1);
       mbar_wait(bar(AB_DFULL + d), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
@@ -574,16 +589,15 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 o;
-        o.x = c[4 * j] - s[4 * j + 1];
-        o.y = c[4 * j + 1] + s[4 * j];
-        o.z = c[4 * j + 2] - s[4 * j + 3];
-        o.w = c[4 * j + 3] + s[4 * j + 2];
+        o.x = (c[4 * j] - s[4 * j + 1]) * PDEPHI_GEN_COMP;
+        o.y = (c[4 * j + 1] + s[4 * j]) * PDEPHI_GEN_COMP;
+        o.z = (c[4 * j + 2] - s[4 * j + 3]) * PDEPHI_GEN_COMP;
+        o.w = (c[4 * j + 3] + s[4 * j + 2]) * PDEPHI_GEN_COMP;
         *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) = o;
       }
       __syncwarp();
-      const int mt = (int)(t / per_mt);
-      const long long r = t % per_mt, b = r / ntn;
-      const int n0 = (int)(r - b * ntn) * NT + half * 32;
+      const long long b = t / ntn;
+      const int n0 = (int)(t - b * ntn) * NT + half * 32;
       float* ub = U + ((size_t)b * N + (size_t)mt * 128 + 32 * q) * ld_out + n0;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -713,7 +727,7 @@ int gen_plan_init(Plan* p) {
   g.xa = f; f += n_xa; g.xsc = f; f += n_xs; g.xss = f; f += n_xs;
   const double inv_total = 1.0 / ((double)p->Nx_total * p->Ny * p->Nz);
   const int nyq = (!two_d && p->Nz % 2 == 0 && p->mzh - 1 == p->Nz / 2) ? p->Nz / 2 : -1;
-  const double comp = 1.0 + 1.0 / 2048.0;     // the tensor core truncates the raw fp32 data operand (see transforms_tc.cu)
+  const double comp = 1.0;                    // truncation bias of the data operands: undone in the epilogues (PDEPHI_GEN_COMP)
   const int wnorm = two_d ? 2 : 1;
   auto genimg = [&](float* img, int kind, int R, int K, int Nt, int off, int m, int wmode) {
     const int n = R * K;
@@ -785,7 +799,7 @@ static int launch_axis_synthesis(const Plan* p, const float* in, long long nb, i
   const int ntn = (ld + gen::NT - 1) / gen::NT;
   const int Npad = (N + 127) / 128 * 128;
   const int nmt = Npad / 128;
-  const long long ntiles = nb * ntn * nmt;
+  const long long ntiles = nb * ntn;
   const size_t smem = gen::as_smem(Npad, mk, nst).total + 1024;
   const int grid = (int)(ntiles < p->num_sms ? ntiles : p->num_sms);
   auto k = gen::gen_axis_synthesis_kernel;

@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests/test_parity_gpu.py -x -q -k "stage_split or sharded_projection or slab_plans or vs_oracle" 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_configs_gpu.py -x -q -k cfg5 2>&1 | grep -E "Error|rel\(|passed|failed|^E" | head -20
+timeout 300 python scripts/gen_debug.py small 2>&1 | tail -24

@@ -36,8 +36,10 @@ def taylor_green(n: int, amplitudes):
     return torch.stack([a * u for a in amplitudes])
 
 
-def compare_model(model, oracle_fn, x, y, out_tol=1e-5, grad_tol=5e-5):
+def compare_model(model, oracle_fn, x, y, out_tol=1e-5, grad_tol=5e-5, precision=None, spectral_grad_tol=None):
     """fwd + MSE + bwd on the GPU model and on the CPU oracle with the same state_dict."""
+    if precision is not None:
+        model.set_precision(precision)
     sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point or v.is_complex()) for k, v in model.state_dict().items()}
     out_o = oracle_fn(x, sd)
     loss_o = F.mse_loss(out_o, y)
@@ -51,14 +53,16 @@ def compare_model(model, oracle_fn, x, y, out_tol=1e-5, grad_tol=5e-5):
         return out, loss
     out, loss = strict_fp32(run)
     assert rel(out, out_o) < out_tol
-    assert abs(float(loss) - float(loss_o)) <= 1e-5 * abs(float(loss_o))
+    assert abs(float(loss) - float(loss_o)) <= max(1e-5, 2 * out_tol) * abs(float(loss_o))
     for n, p in model.named_parameters():
         assert p.grad is not None, n
         g_o = sd[n].grad
         if float(g_o.abs().max()) == 0.0:
             assert float(p.grad.abs().max()) == 0.0, n
         else:
-            assert rel(p.grad, g_o) < grad_tol, (n, rel(p.grad, g_o))
+            spectral = any(k in n for k in ("P_coeffs", "Q_coeffs", "weights"))
+            tol = spectral_grad_tol if (spectral and spectral_grad_tol is not None) else grad_tol
+            assert rel(p.grad, g_o) < tol, (n, rel(p.grad, g_o))
     return float(loss)
 
 
@@ -114,3 +118,29 @@ def test_cfg4_multiscale_operators_on_128_cubed(modes, order):
     # reductions on both sides, different summation orders): 2e-4 on gradients here, 1e-5 on the outputs
     loss = compare_model(model, lambda xx, sd: so.rfno3d_forward(xx, sd, modes, 1), x, y, grad_tol=2e-4)
     assert math.isfinite(weight * loss)
+
+
+@pytest.mark.parametrize("precision,out_tol,grad_tol", [("fp32", 1e-5, 5e-5), ("tf32", 2e-3, 4e-3)])
+def test_cfg5_operator_on_256_cubed(precision, out_tol, grad_tol):
+    """configs[4]: RationalFourierOperator3D modes (64,64,64) on a 256^3 grid, batch 1 -- against the oracle at width 4 /
+    one layer (the CPU side stays in seconds), on the FFMA route and on the per-axis tcgen05 route (transforms_gen.cu)
+    that this shape takes at TF32; the multi-GPU slab decomposition of the same shape is covered in test_parity_gpu.py.
+    Conditioned weights as in cfg 4.  TF32 gradient gate: 2e-3 per transform, two transforms in series.  The gradients of
+    the pointwise layers (torch's own conv / linear backward on both sides) are fp32 sums of 1.7e7 sign-alternating terms
+    in different orders on CPU and GPU (6e-4 measured on the conv bias): they get 2e-3, the spectral coefficients the gate."""
+    torch.manual_seed(1234)
+    w, modes = 4, (64, 64, 64)
+    model = pb.RationalFourierOperator3D(modes=modes, width=w, n_layers=1, in_channels=w, out_channels=w)
+    with torch.no_grad():
+        layer = model.rational_layers[0]
+        q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+        layer.Q_coeffs.mul_(1e-6)
+        layer.Q_coeffs[..., 0, 0, 0] = q0
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, w, 256, 256, 256, generator=g)
+    y = torch.randn(1, w, 256, 256, 256, generator=g)
+    compare_model(model, lambda xx, sd: so.rfno3d_forward(xx, sd, modes, 1), x, y, out_tol=out_tol, grad_tol=max(grad_tol, 2e-3),
+                  precision=precision, spectral_grad_tol=grad_tol)
+    if precision == "tf32":
+        assert _cabi.load().pdephi_plan_supports(_cabi.get_plan(torch.cuda.current_device(), (256, 256, 256), (64, 64, 33)),
+                                                 _cabi.PREC_TF32) == 1
