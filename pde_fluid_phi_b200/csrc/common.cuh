@@ -63,6 +63,7 @@ struct Plan {
   size_t smem_optin;
   // tcgen05 path: twiddle operands as swizzled K-major shared-memory images (transforms_tc.cu)
   int tc_ok;
+  float tc_comp;    // epilogue factor undoing the TF32 truncation bias of raw data operands (1 + 2^-11)
   void* tc_arena;
   float* tc_b1[2];  // analysis z  [48][Nz]
   float* tc_a2;     // analysis y  [64][Ny]

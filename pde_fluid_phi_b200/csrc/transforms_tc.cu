@@ -88,7 +88,7 @@ enum { AB_FULL0 = 0, AB_FULL1, AB_EMPTY0, AB_EMPTY1, AB_D1FULL0, AB_D1FULL1, AB_
 
 __global__ void __launch_bounds__(A_THREADS, 1)
 analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __restrict__ T2, const float* __restrict__ B1img,
-                      const float* __restrict__ A2img, int planes, int NKB, int my, int mzh) {
+                      const float* __restrict__ A2img, int planes, int NKB, int my, int mzh, float comp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -200,7 +200,7 @@ analysis_zy_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, float2* __rest
         for (int c = 0; c < 40; ++c) {
           if (c < ncol) {
             const uint32_t off = (uint32_t)((c >> 3) * 1024 + (c & 7) * 128 + ((((lane >> 2) ^ (c & 7)) & 7) << 4)) + kin;
-            *reinterpret_cast<float*>(b2 + off) = to_tf32(v[c]);
+            *reinterpret_cast<float*>(b2 + off) = to_tf32(v[c] * comp);     // undo the truncation bias of the raw plane operand
           }
         }
       }
@@ -285,7 +285,7 @@ template <int NZ, int NADD>   // NADD: number of fused addends (0, 1: add0 only,
 __global__ void __launch_bounds__(S_THREADS, 1)
 synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, const float* __restrict__ add0,
                        const float* __restrict__ add1, const float* __restrict__ Ayimg, const float* __restrict__ Bzimg,
-                       int planes, int my, int mzh) {
+                       int planes, int my, int mzh, float comp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -443,7 +443,13 @@ synthesis_zy_tc_kernel(const float2* __restrict__ U, float* __restrict__ out, co
           for (int j = 0; j < G; ++j) {
             const int row = (g0 + j) * RPI + rsub;
             float4 o = *reinterpret_cast<const float4*>(st + row * LD + 4 * c4);
-            if (NADD >= 1) { o.x += a0v[set][j].x; o.y += a0v[set][j].y; o.z += a0v[set][j].z; o.w += a0v[set][j].w; }
+            // comp undoes the truncation bias of the TMEM-resident V operand of GEMM-Z, on the fp32 result
+            if (NADD >= 1) {
+              o.x = fmaf(o.x, comp, a0v[set][j].x); o.y = fmaf(o.y, comp, a0v[set][j].y);
+              o.z = fmaf(o.z, comp, a0v[set][j].z); o.w = fmaf(o.w, comp, a0v[set][j].w);
+            } else {
+              o.x *= comp; o.y *= comp; o.z *= comp; o.w *= comp;
+            }
             if (NADD == 2) { o.x += a1v[j].x; o.y += a1v[j].y; o.z += a1v[j].z; o.w += a1v[j].w; }
             __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)((g0 + j) * RPI) * NZ), o);
           }
@@ -490,6 +496,7 @@ bool tc_supported(const Plan* p) {
 // called from pdephi_plan_create (device already selected)
 int tc_plan_init(Plan* p) {
   p->tc_ok = 0;
+  p->tc_comp = 1.0f;
   const bool shape_ok = p->Ny == 128 && (p->Nz == 64 || p->Nz == 128) && p->my <= 32 && 2 * p->mzh <= tc::N2;
   if (!shape_ok) return PDEPHI_OK;
   const int NKB = p->Nz / 32;
@@ -507,10 +514,14 @@ int tc_plan_init(Plan* p) {
   const double inv_total = 1.0 / ((double)p->Nx_total * p->Ny * p->Nz);
   const int nyq = (p->Nz % 2 == 0 && p->mzh - 1 == p->Nz / 2) ? p->Nz / 2 : -1;
   // The tensor core drops the low 13 mantissa bits of an fp32 operand it reads itself (the TMA-staged
-  // plane, the TMEM-resident V): a mean relative bias of -2^-11.  It is folded into the constant operand
-  // of the same contraction so the data path keeps round-to-nearest statistics.  PDEPHI_TF32_COMP=0 disables.
+  // plane, the TMEM-resident V): a mean relative bias of -2^-11.  The kernels undo it on the fp32 accumulator in
+  // their epilogues (p->tc_comp).  Folding the factor into the constant operand instead is only right on average:
+  // twiddles that are exactly 1.0 -- the whole DC mode, i.e. every mean -- round 1 + 2^-11 up to 1 + 2^-10 in TF32
+  // and over-compensate by 4.9e-4 per stage, and every other entry picks up extra rounding noise (measured per
+  // transform: 4.5e-4 -> see DESIGN.md).  PDEPHI_TF32_COMP=0 disables.
   const char* env = getenv("PDEPHI_TF32_COMP");
-  const double comp = (env && env[0] == '0') ? 1.0 : 1.0 + 1.0 / 2048.0;
+  p->tc_comp = (env && env[0] == '0') ? 1.0f : 1.0f + 1.0f / 2048.0f;
+  const double comp = 1.0;
   auto gen = [&](float* img, int kind, int R, int K, int N, int m, int wm, double c) {
     const int n = R * K;
     tc::tc_image_kernel<<<(n + 255) / 256, 256>>>(img, kind, R, K, N, m, wm, nyq, inv_total, c);
@@ -565,7 +576,7 @@ int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int dire
   const int grid = (int)(planes < (size_t)p->num_sms ? planes : (size_t)p->num_sms);
   {
     ProfScope ps(K_ANALYSIS_ZY_TC, st);
-    k<<<grid, tc::A_THREADS, smem, st>>>(tmap, ws, p->tc_b1[direction], p->tc_a2, (int)planes, NKB, p->my, p->mzh);
+    k<<<grid, tc::A_THREADS, smem, st>>>(tmap, ws, p->tc_b1[direction], p->tc_a2, (int)planes, NKB, p->my, p->mzh, p->tc_comp);
   }
   PDEPHI_LAUNCH_CHECK("analysis_zy_tc_kernel");
   if (!(stages & ST_X)) return PDEPHI_OK;
@@ -600,7 +611,8 @@ int synthesis_tc(const Plan* p, const float2* Z, float* out, const float* add0, 
     auto k = tc::synthesis_zy_tc_kernel<NZV, NA>;                                                                           \
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                           \
     ProfScope ps(K_SYNTHESIS_ZY_TC, st);                                                                                    \
-    k<<<grid, tc::S_THREADS, smem, st>>>(ws, out, add0, add1, p->tc_ay, p->tc_bz[direction], (int)planes, p->my, p->mzh); \
+    k<<<grid, tc::S_THREADS, smem, st>>>(ws, out, add0, add1, p->tc_ay, p->tc_bz[direction], (int)planes, p->my, p->mzh, \
+                                         p->tc_comp);                                                                     \
   }
   if (p->Nz == 128) {
     if (nadd == 0) PDEPHI_SYN_LAUNCH(128, 0) else if (nadd == 1) PDEPHI_SYN_LAUNCH(128, 1) else PDEPHI_SYN_LAUNCH(128, 2)

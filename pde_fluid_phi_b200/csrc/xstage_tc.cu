@@ -114,7 +114,7 @@ enum { AXB_FULL = 0, AXB_EMPTY = AX_STAGES, AXB_DFULL = 2 * AX_STAGES, AXB_DEMPT
 template <bool X3>
 __global__ void __launch_bounds__(AX_THREADS + (X3 ? X3_SPLIT_THREADS : 0), 1)
 analysis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_t2, float2* __restrict__ X, const float* __restrict__ Aimg,
-                     const float* __restrict__ Aloimg, int Nx, int mx, int P, int ntn, long long ntiles) {
+                     const float* __restrict__ Aloimg, int Nx, int mx, int P, int ntn, long long ntiles, float comp) {
   constexpr int NTHR = AX_THREADS + (X3 ? X3_SPLIT_THREADS : 0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -254,7 +254,7 @@ analysis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_t2, float2* __rest
         if (kx < mx && p0 + j < P) {
           const float2 c = *reinterpret_cast<const float2*>(E + kx * E_LD + 2 * j);
           const float2 s = *reinterpret_cast<const float2*>(E + (SIN0 + kx) * E_LD + 2 * j);
-          outp[(size_t)kx * P + p0 + j] = make_float2(c.x + s.y, c.y - s.x);
+          outp[(size_t)kx * P + p0 + j] = make_float2((c.x + s.y) * comp, (c.y - s.x) * comp);   // comp = 1 on the split route
         }
       }
     }
@@ -305,7 +305,7 @@ template <bool X3>
 __global__ void __launch_bounds__(SX_THREADS + (X3 ? X3_SPLIT_THREADS : 0), 1)
 synthesis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, float* __restrict__ U, const float* __restrict__ Acimg,
                       const float* __restrict__ Asimg, const float* __restrict__ Acloimg, const float* __restrict__ Asloimg,
-                      int Nx, int mx, int P, int ntn, int nmt, long long ntiles) {
+                      int Nx, int mx, int P, int ntn, int nmt, long long ntiles, float comp) {
   constexpr int NTHR = SX_THREADS + (X3 ? X3_SPLIT_THREADS : 0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -446,10 +446,10 @@ synthesis_x_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, float* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 o;
-        o.x = c[4 * j] - s[4 * j + 1];
-        o.y = c[4 * j + 1] + s[4 * j];
-        o.z = c[4 * j + 2] - s[4 * j + 3];
-        o.w = c[4 * j + 3] + s[4 * j + 2];
+        o.x = (c[4 * j] - s[4 * j + 1]) * comp;
+        o.y = (c[4 * j + 1] + s[4 * j]) * comp;
+        o.z = (c[4 * j + 2] - s[4 * j + 3]) * comp;
+        o.w = (c[4 * j + 3] + s[4 * j + 2]) * comp;
         *reinterpret_cast<float4*>(st + lane * SX_LD + 4 * j) = o;
       }
       __syncwarp();
@@ -493,7 +493,7 @@ int xtc_plan_init(Plan* p) {
   p->xtc_ax = f; f += nA;
   p->xtc_sc = f; f += nS;
   p->xtc_ss = f;
-  const double comp = 1.0 + 1.0 / 2048.0;   // the data operand is truncated to TF32 by the tensor core
+  const double comp = 1.0;   // the truncation bias of the raw data operand is undone in the epilogues (Plan::tc_comp)
   auto gen = [&](float* img, int kind, int R, int K) {
     const int n = R * K;
     xtc::ximage_kernel<<<(n + 255) / 256, 256>>>(img, kind, R, K, p->Nx_total, p->x_offset, p->mx, comp);
@@ -570,12 +570,12 @@ static int xstage_analysis_launch(const Plan* p, const float2* ws, float2* X, lo
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_ANALYSIS_X_TC3, st);
     k<<<grid, xtc::AX_THREADS + xtc::X3_SPLIT_THREADS, smem, st>>>(map, X, p->xtc3_ax[0], p->xtc3_ax[1], p->Nx, p->mx, P, ntn,
-                                                                  ntiles);
+                                                                  ntiles, 1.0f);
   } else {
     auto k = xtc::analysis_x_tc_kernel<false>;
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_ANALYSIS_X_TC, st);
-    k<<<grid, xtc::AX_THREADS, smem, st>>>(map, X, p->xtc_ax, nullptr, p->Nx, p->mx, P, ntn, ntiles);
+    k<<<grid, xtc::AX_THREADS, smem, st>>>(map, X, p->xtc_ax, nullptr, p->Nx, p->mx, P, ntn, ntiles, p->tc_comp);
   }
   PDEPHI_LAUNCH_CHECK("analysis_x_tc_kernel");
   return PDEPHI_OK;
@@ -617,13 +617,13 @@ static int xstage_synthesis_launch(const Plan* p, const float2* Z, float2* ws, f
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_SYNTHESIS_X_TC3, st);
     k<<<grid, xtc::SX_THREADS + xtc::X3_SPLIT_THREADS, smem, st>>>(map, (float*)ws, p->xtc3_sc[0], p->xtc3_ss[0], p->xtc3_sc[1],
-                                                                  p->xtc3_ss[1], p->Nx, p->mx, P, ntn, nmt, ntiles);
+                                                                  p->xtc3_ss[1], p->Nx, p->mx, P, ntn, nmt, ntiles, 1.0f);
   } else {
     auto k = xtc::synthesis_x_tc_kernel<false>;
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_SYNTHESIS_X_TC, st);
     k<<<grid, xtc::SX_THREADS, smem, st>>>(map, (float*)ws, p->xtc_sc, p->xtc_ss, nullptr, nullptr, p->Nx, p->mx, P, ntn, nmt,
-                                           ntiles);
+                                           ntiles, p->tc_comp);
   }
   PDEPHI_LAUNCH_CHECK("synthesis_x_tc_kernel");
   return PDEPHI_OK;
