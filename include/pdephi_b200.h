@@ -182,6 +182,19 @@ int pdephi_block_tail_bwd(const float* g, const float* u, const float* h, const 
                           float* dWc, float* dbc, int B, int C, long long S, void* workspace,
                           size_t workspace_bytes, pdephi_stream_t stream);
 
+/* ---- whole spectral branch + block tail, forward, with the spectral output never materialised ---------------
+ * u = S(Y * mode_scale * row_scale) + (Wc h + bc) + h,  hout = gelu(u)       (rational_fourier.py:265-271)
+ * Y [B*64, mx, my, mzh] complex: the mixed, un-projected modes (output of pdephi_rational_mix_fwd / complex_mix_fwd).
+ * The x and y stages of the synthesis run as per-axis tensor-core contractions and leave V [B,Nx,Ny,64,ldz] (28 % of an
+ * activation at mzh = 17); the z stage is two more MMA groups inside the block-tail kernel, accumulated into the same
+ * TMEM tile as the 1x1x1 convolution -- the 4.3 GB write and read-back of `spec` per layer disappear.
+ * Needs width 64, Nz = 128 and a (grid, modes) shape of the per-axis route (pdephi_block_spectral_supported). */
+int pdephi_block_spectral_supported(pdephi_plan_t plan, int C);
+size_t pdephi_block_spectral_fwd_workspace_bytes(pdephi_plan_t plan, int B, int C);
+int pdephi_block_spectral_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                              long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u,
+                              float* hout, int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
 /* ---- per-kernel launch counters and CUDA-event timing (measurement support for bench.py) ------
  * Launches are always counted.  With timing enabled every kernel launch is bracketed by a pair of
  * cudaEvents on the launching stream; pdephi_profile_query synchronises on them and returns the

@@ -84,11 +84,12 @@ __device__ __forceinline__ float gelu_grad_f(float u) {
   return fmaf(u * 0.3989422804014327f, e, cdf);
 }
 // W image: K-major [64 rows][K = 64], element (r, k) = TRANSPOSE ? W[k][r] : W[r][k], RN-rounded to TF32
-__device__ __forceinline__ void build_w_image(uint8_t* dst, const float* __restrict__ W, bool transpose, int tid, int nthr) {
+constexpr float TF32_COMP = 1.00048828125f;   // 1 + 2^-11: undoes the mean bias of the tensor core's operand truncation
+__device__ __forceinline__ void build_w_image(uint8_t* dst, const float* __restrict__ W, bool transpose, int tid, int nthr,
+                                              float comp) {
   for (int i = tid; i < C * C; i += nthr) {
     const int r = i >> 6, k = i & 63;
-    // (1 + 2^-11): the data operand of this GEMM is truncated to TF32 by the tensor core (mean bias -2^-11)
-    const float v = (transpose ? __ldg(W + k * C + r) : __ldg(W + i)) * 1.00048828125f;
+    const float v = (transpose ? __ldg(W + k * C + r) : __ldg(W + i)) * comp;
     *reinterpret_cast<float*>(dst + swz_off(C, r, k)) = to_tf32(v);
   }
 }
@@ -131,11 +132,16 @@ __device__ __forceinline__ void stage_rows(uint32_t dst, const float* __restrict
 //   warp 0: MMA issuer + TMEM owner, warps 1..4: loaders, warps 5..20: epilogue
 // ------------------------------------------------------------------------------------------------
 constexpr int F_STAGES = 3;
-struct FSmem { uint32_t stage[F_STAGES], w, bias, bars, tmem_slot, total; };
-__host__ __device__ inline FSmem fwd_smem() {
+// FUSED: the spectral branch is never materialised.  Instead of a staged `spec` tile the stage holds the tile's rows of
+// V = (x,y)-synthesised modes, [64 channel rows][ldz <= 64 floats] (columns 2k = re, 2k+1 = im of kz = k), and the z stage
+// of the synthesis runs as extra MMAs into the same accumulator:  D[128 z x 64 ch] += Bz[128 z x K] . Vtile[64 ch x K]^T.
+// A tile is then one z line of the grid (Nz = 128), and V is laid out [tile][channel][ldz] so its rows are contiguous.
+struct FSmem { uint32_t stage[F_STAGES], w, bz, bias, bars, tmem_slot, total; };
+__host__ __device__ inline FSmem fwd_smem(bool fused) {
   FSmem s; uint32_t o = 0;
-  for (int i = 0; i < F_STAGES; ++i) { s.stage[i] = o; o += 2 * TILE; }
+  for (int i = 0; i < F_STAGES; ++i) { s.stage[i] = o; o += fused ? TILE + 2 * BOX : 2 * TILE; }
   s.w = o; o += 2 * BOX;
+  s.bz = o; o += fused ? 2 * TS * 128 : 0;
   s.bias = o; o += 256;
   s.bars = o; o += 128;
   s.tmem_slot = o; o += 64;
@@ -144,19 +150,32 @@ __host__ __device__ inline FSmem fwd_smem() {
 }
 enum { FB_FULL = 0, FB_EMPTY = F_STAGES, FB_DFULL = 2 * F_STAGES, FB_DEMPTY = 2 * F_STAGES + 2 };
 
+template <bool FUSED>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ spec_in, const float* __restrict__ Wc,
                       const float* __restrict__ bc, float* __restrict__ u_out, float* __restrict__ h_out,
-                      long long tiles_per_batch, long long ntiles, long long S) {
+                      long long tiles_per_batch, long long ntiles, long long S, const float* __restrict__ bzimg, int ldz,
+                      int contiguous) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const FSmem L = fwd_smem();
+  const FSmem L = fwd_smem(FUSED);
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  build_w_image(sm + L.w, Wc, false, threadIdx.x, THREADS);
+  // the truncation bias of the data operands (h; V) is undone on the accumulator in the epilogue, not in the weights
+  build_w_image(sm + L.w, Wc, false, threadIdx.x, THREADS, 1.0f);
+  if (FUSED) {
+    const float4* s1 = reinterpret_cast<const float4*>(bzimg);
+    float4* d1 = reinterpret_cast<float4*>(sm + L.bz);
+    const int nkb = (ldz + 31) / 32;
+    for (int i = threadIdx.x; i < nkb * TS * 128 / 16; i += THREADS) d1[i] = __ldg(s1 + i);
+    for (int st = 0; st < F_STAGES; ++st) {        // the chunks of a V stage beyond ldz are never written: zero them once
+      float4* z = reinterpret_cast<float4*>(sm + L.stage[st] + TILE);
+      for (int i = threadIdx.x; i < 2 * BOX / 16; i += THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   if (threadIdx.x < C) reinterpret_cast<float*>(sm + L.bias)[threadIdx.x] = bc ? __ldg(bc + threadIdx.x) : 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < F_STAGES; ++i) { mbar_init(bar(FB_FULL + i), LD_THREADS); mbar_init(bar(FB_EMPTY + i), 1 + EPI_WARPS); }
@@ -169,30 +188,55 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
-  const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // every CTA walks a CONTIGUOUS range of tiles (PDEPHI_TILE_ORDER=0: round-robin): consecutive tiles extend the same 64
+  // channel rows, so the 512-byte pieces a tile writes to each row meet their neighbours in L2 within one tile time
+  const long long tq = ntiles / gridDim.x, tr = ntiles % gridDim.x;
+  const long long my_tiles = contiguous ? tq + (blockIdx.x < tr ? 1 : 0)
+                                        : (blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  const long long tile0 = contiguous ? blockIdx.x * tq + (blockIdx.x < tr ? blockIdx.x : tr) : blockIdx.x;
+  const long long tstep = contiguous ? 1 : gridDim.x;
 
   if (warp >= 1 && warp < EPI0) {
-    // ===== loaders: h and spec tiles; F_STAGES - 1 tiles stay in flight behind the one being issued =====
+    // ===== loaders: h and spec (or V) tiles, up to F_STAGES - 1 tiles in flight =====
+    // Order matters: a landed tile is published (FULL) BEFORE the loader blocks on the stage the next tile needs.  The
+    // first version waited for that stage first, so FULL(k) could not be signalled until the stage of tile k-1 had been
+    // released by its epilogue -- MMA(k) never overlapped epilogue(k-1).
     const int lw = warp - 1;
-    for (long long it = 0; it < my_tiles + (F_STAGES - 1); ++it) {
-      if (it < my_tiles) {
-        const long long t = blockIdx.x + it * gridDim.x;
-        const int s = (int)(it % F_STAGES);
-        mbar_wait(bar(FB_EMPTY + s), (uint32_t)(((it / F_STAGES) & 1) ^ 1));
-        const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
-        stage_rows<false>(base + L.stage[s], h_in, b, s0, S, lw, lane);
+    const int cpr = ldz >> 2, nchunk = C * cpr;        // FUSED: 16-byte chunks per V row / per V tile
+    auto issue = [&](long long it) {
+      const long long t = tile0 + it * tstep;
+      const int s = (int)(it % F_STAGES);
+      mbar_wait(bar(FB_EMPTY + s), (uint32_t)(((it / F_STAGES) & 1) ^ 1));
+      const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
+      stage_rows<false>(base + L.stage[s], h_in, b, s0, S, lw, lane);
+      if (FUSED) {
+        // V rows of tile t are contiguous: chunk q = (channel c, chunk j of its row) -> K-major 128B-swizzled B operand
+        const float* vsrc = spec_in + (size_t)t * C * ldz;
+        const uint32_t vdst = base + L.stage[s] + TILE;
+        for (int q = lw * 32 + lane; q < nchunk; q += LD_THREADS) {
+          const int c = q / cpr, j = q - c * cpr;
+          cp_async16(vdst + (uint32_t)((j >> 3) * BOX + c * 128 + ((((j & 7) ^ (c & 7)) & 7) << 4)), vsrc + (size_t)q * 4);
+        }
+      } else {
         stage_rows<false>(base + L.stage[s] + TILE, spec_in, b, s0, S, lw, lane);
       }
-      cp_async_commit();                         // (empty groups in the drain iterations keep the group count uniform)
-      if (it >= F_STAGES - 1) {
-        cp_async_wait<F_STAGES - 1>();           // the group committed F_STAGES - 1 iterations ago has landed
-        fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(bar(FB_FULL + (int)((it - (F_STAGES - 1)) % F_STAGES)));
-      }
+    };
+    for (int pre = 0; pre < F_STAGES - 1; ++pre) {
+      if (pre < my_tiles) issue(pre);
+      cp_async_commit();
+    }
+    for (long long it = 0; it < my_tiles; ++it) {
+      cp_async_wait<F_STAGES - 2>();             // every group but the newest F_STAGES - 2: tile `it` has landed
+      fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(bar(FB_FULL + (int)(it % F_STAGES)));
+      if (it + F_STAGES - 1 < my_tiles) issue(it + F_STAGES - 1);
+      cp_async_commit();                         // (possibly empty: keeps the group count uniform)
     }
   } else if (warp == 0) {
     if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA back to back
       constexpr uint32_t id = idesc_tf32(TS, C, 1, 0);
+      constexpr uint32_t idz = idesc_tf32(TS, C, 0, 0);
+      const int ksteps = (ldz + 7) / 8;
       for (long long it = 0; it < my_tiles; ++it) {
         const int s = (int)(it % F_STAGES), d = (int)(it & 1);
         mbar_wait(bar(FB_FULL + s), (uint32_t)((it / F_STAGES) & 1));
@@ -202,6 +246,11 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
         for (int k = 0; k < C / 8; ++k)
           mma_ss(tmem + d * C, umma_desc_mn(base + L.stage[s] + k * 1024, BOX),
                  umma_desc(base + L.w + (k >> 2) * BOX + (k & 3) * 32, 1024), id, k ? 1u : 0u);
+        if (FUSED) {
+          for (int k = 0; k < ksteps; ++k)         // z stage of the synthesis: += Bz[z][k] . V[ch][k]
+            mma_ss(tmem + d * C, umma_desc(base + L.bz + (k >> 2) * (TS * 128) + (k & 3) * 32, 1024),
+                   umma_desc(base + L.stage[s] + TILE + (k >> 2) * BOX + (k & 3) * 32, 1024), idz, 1u);
+        }
         mma_commit(bar(FB_EMPTY + s));
         mma_commit(bar(FB_DFULL + d));
       }
@@ -217,7 +266,7 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
 #pragma unroll
     for (int r = 0; r < 4; ++r) xc[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 3) ^ r) & 3) << 5) + (lane & 7) * 4);
     for (long long it = 0; it < my_tiles; ++it) {
-      const long long t = blockIdx.x + it * gridDim.x;
+      const long long t = tile0 + it * tstep;
       const int s = (int)(it % F_STAGES), d = (int)(it & 1);
       mbar_wait(bar(FB_DFULL + d), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
@@ -230,22 +279,30 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       const uint8_t* th = sm + L.stage[s];
       const uint8_t* tsp = th + TILE;
+      // The residual (and spec) operands leave the stage first and the stage is released BEFORE the GELU and the
+      // stores: its lifetime is then load latency + MMA instead of load latency + MMA + the whole epilogue, which is
+      // what the three-deep ring has to cover (measured: the kernel took 2.0 ms with an empty epilogue and 3.2 ms with
+      // the real one at any byte count -- it was bound by this chain, not by HBM).
+      float pre[CPW];
+#pragma unroll
+      for (int j = 0; j < CPW; ++j) {
+        const uint32_t off = xc[j & 3] + j * 128;
+        pre[j] = *reinterpret_cast<const float*>(th + off);
+        if (!FUSED) pre[j] += *reinterpret_cast<const float*>(tsp + off);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(FB_EMPTY + s));
       const size_t g0 = ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
       float* up = u_out + g0;
       float* hp = h_out + g0;
 #pragma unroll
       for (int j = 0; j < CPW; ++j) {
-        const uint32_t off = xc[j & 3] + j * 128;
-        const float hv = *reinterpret_cast<const float*>(th + off);
-        const float sv = *reinterpret_cast<const float*>(tsp + off);
-        const float u = (sv + (v[j] + bsr[j])) + hv;
+        const float u = fmaf(v[j], TF32_COMP, bsr[j]) + pre[j];
         __stcs(up, u);
         *hp = gelu_f(u);
         up += S;
         hp += S;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(FB_EMPTY + s));
     }
   }
   tc_fence_before();
@@ -277,7 +334,7 @@ enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
                       const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
-                      float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S) {
+                      float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S, int contiguous) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -286,7 +343,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  build_w_image(sm + L.wt, Wc, true, threadIdx.x, THREADS);      // rows c, K = o : (Wc^T)
+  build_w_image(sm + L.wt, Wc, true, threadIdx.x, THREADS, TF32_COMP);      // rows c, K = o : (Wc^T)
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), LD_THREADS); mbar_init(bar(BB_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
@@ -304,27 +361,37 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
   const uint32_t tmem_t[2] = {tmem, tmem + C}, tmem_dw = tmem + 2 * C;
-  const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // every CTA walks a CONTIGUOUS range of tiles (PDEPHI_TILE_ORDER=0: round-robin): consecutive tiles extend the same 64
+  // channel rows, so the 512-byte pieces a tile writes to each row meet their neighbours in L2 within one tile time
+  const long long tq = ntiles / gridDim.x, tr = ntiles % gridDim.x;
+  const long long my_tiles = contiguous ? tq + (blockIdx.x < tr ? 1 : 0)
+                                        : (blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  const long long tile0 = contiguous ? blockIdx.x * tq + (blockIdx.x < tr ? blockIdx.x : tr) : blockIdx.x;
+  const long long tstep = contiguous ? 1 : gridDim.x;
 
   if (warp >= 1 && warp < EPI0) {
-    // ===== loaders: g' (MN layout), h (K layout), u (K layout) =====
+    // ===== loaders: g' (MN layout), h (K layout), u (K layout); a landed tile is published before the loader blocks on
+    //       the stage of the next one (see the forward kernel) =====
     const int lw = warp - 1;
-    for (long long it = 0; it < my_tiles + (B_STAGES - 1); ++it) {
-      if (it < my_tiles) {
-        const long long t = blockIdx.x + it * gridDim.x;
-        const int s = (int)(it % B_STAGES);
-        mbar_wait(bar(BB_EMPTY + s), (uint32_t)(((it / B_STAGES) & 1) ^ 1));
-        const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
-        stage_rows<false>(base + L.stage[s], g_in, b, s0, S, lw, lane);
-        stage_rows<true>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
-        stage_rows<true>(base + L.stage[s] + 2 * TILE, u_in, b, s0, S, lw, lane);
-      }
+    auto issue = [&](long long it) {
+      const long long t = tile0 + it * tstep;
+      const int s = (int)(it % B_STAGES);
+      mbar_wait(bar(BB_EMPTY + s), (uint32_t)(((it / B_STAGES) & 1) ^ 1));
+      const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
+      stage_rows<false>(base + L.stage[s], g_in, b, s0, S, lw, lane);
+      stage_rows<true>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
+      stage_rows<true>(base + L.stage[s] + 2 * TILE, u_in, b, s0, S, lw, lane);
+    };
+    for (int pre = 0; pre < B_STAGES - 1; ++pre) {
+      if (pre < my_tiles) issue(pre);
       cp_async_commit();
-      if (it >= B_STAGES - 1) {
-        cp_async_wait<B_STAGES - 1>();
-        fence_proxy_async();
-        mbar_arrive(bar(BB_FULL + (int)((it - (B_STAGES - 1)) % B_STAGES)));
-      }
+    }
+    for (long long it = 0; it < my_tiles; ++it) {
+      cp_async_wait<B_STAGES - 2>();
+      fence_proxy_async();
+      mbar_arrive(bar(BB_FULL + (int)(it % B_STAGES)));
+      if (it + B_STAGES - 1 < my_tiles) issue(it + B_STAGES - 1);
+      cp_async_commit();
     }
   } else if (warp == 0) {
     if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows one lane is active and issues UTCHMMA back to back
@@ -365,7 +432,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
 #pragma unroll
     for (int r = 0; r < 8; ++r) xk[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 2) ^ r) & 7) << 4) + (lane & 3) * 4);
     for (long long it = 0; it < my_tiles; ++it) {
-      const long long t = blockIdx.x + it * gridDim.x;
+      const long long t = tile0 + it * tstep;
       const int s = (int)(it % B_STAGES), d = (int)(it & 1);
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       uint8_t* tg = sm + L.stage[s];
@@ -465,6 +532,12 @@ static int check_shape(int B, int Cc, long long S, const char* who) {
   return PDEPHI_OK;
 }
 
+static int tile_order() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PDEPHI_TILE_ORDER"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+
 static int num_sms() {
   int dev = 0, n = 148;
   cudaGetDevice(&dev);
@@ -484,19 +557,44 @@ extern "C" int pdephi_block_tail_fwd(const float* h, const float* spec, const fl
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(h) || !al16(spec)) return fail(PDEPHI_ERR_INVALID, "block_tail_fwd: h and spec must be 16-byte aligned");
   const long long tpb = S / blk::TS, ntiles = tpb * B;
-  const size_t smem = blk::fwd_smem().total + 1024;
-  auto k = blk::block_tail_fwd_kernel;
+  const size_t smem = blk::fwd_smem(false).total + 1024;
+  auto k = blk::block_tail_fwd_kernel<false>;
   PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = num_sms();
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope ps(K_BLOCK_TAIL_FWD, st);
-    k<<<grid, blk::THREADS, smem, st>>>(h, spec, Wc, bc, u, hout, tpb, ntiles, S);
+    k<<<grid, blk::THREADS, smem, st>>>(h, spec, Wc, bc, u, hout, tpb, ntiles, S, nullptr, 0, tile_order());
   }
   PDEPHI_LAUNCH_CHECK("block_tail_fwd_kernel");
   return PDEPHI_OK;
 }
+
+namespace pdephi {
+// Block tail with the z stage of the synthesis fused in (transforms_gen.cu: pdephi_block_spectral_fwd).
+// V [B*S/128 tiles][64][ldz] float, bzimg = the plan's z-synthesis operand image for Nz = 128.
+int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const float* bzimg, const float* Wc, const float* bc,
+                                float* u, float* hout, int B, long long S, cudaStream_t st) {
+  int rc = check_shape(B, blk::C, S, "block_spectral_fwd");
+  if (rc) return rc;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(h) || !al16(V)) return fail(PDEPHI_ERR_INVALID, "block_spectral_fwd: h and the workspace must be 16-byte aligned");
+  if (ldz % 4 != 0 || ldz > 64) return fail(PDEPHI_ERR_UNSUPPORTED, "block_spectral_fwd: ldz %d", ldz);
+  const long long tpb = S / blk::TS, ntiles = tpb * B;
+  const size_t smem = blk::fwd_smem(true).total + 1024;
+  auto k = blk::block_tail_fwd_kernel<true>;
+  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sms = num_sms();
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  {
+    ProfScope ps(K_BLOCK_SPECTRAL_FWD, st);
+    k<<<grid, blk::THREADS, smem, st>>>(h, V, Wc, bc, u, hout, tpb, ntiles, S, bzimg, ldz, tile_order());
+  }
+  PDEPHI_LAUNCH_CHECK("block_tail_fwd_kernel<fused>");
+  return PDEPHI_OK;
+}
+}  // namespace pdephi
 
 extern "C" size_t pdephi_block_tail_bwd_workspace_bytes(int Cc) {
   if (Cc != blk::C) return 0;
@@ -523,7 +621,7 @@ extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope ps(K_BLOCK_TAIL_BWD, st);
-    k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S);
+    k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order());
   }
   PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
   {

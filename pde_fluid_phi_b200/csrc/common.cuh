@@ -106,7 +106,7 @@ enum KernelId {
   K_RATIONAL_MIX, K_RATIONAL_MIX_T, K_PROJ_STATS, K_PROJ_BWD, K_RATIONAL_DPQ, K_DPQ_REDUCE,
   K_COMPLEX_MIX, K_COMPLEX_MIX_T, K_COMPLEX_DW, K_POINTWISE_LINEAR, K_POINTWISE_WGRAD, K_BLOCK_TAIL_FWD, K_BLOCK_TAIL_BWD, K_ANALYSIS_X_TC, K_SYNTHESIS_X_TC, K_SCALE_MODES, K_RATIONAL_G,
   K_ANALYSIS_ZY_TC3, K_SYNTHESIS_ZY_TC3, K_ANALYSIS_X_TC3, K_SYNTHESIS_X_TC3,
-  K_GEN_Z_ANALYSIS, K_GEN_Z_SYNTHESIS, K_GEN_AXIS_ANALYSIS, K_GEN_AXIS_SYNTHESIS, K_COUNT
+  K_GEN_Z_ANALYSIS, K_GEN_Z_SYNTHESIS, K_GEN_AXIS_ANALYSIS, K_GEN_AXIS_SYNTHESIS, K_BLOCK_SPECTRAL_FWD, K_COUNT
 };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);

@@ -28,7 +28,7 @@ static const char* const kKernelNames[K_COUNT] = {
     "pointwise_wgrad_kernel", "block_tail_fwd_kernel", "block_tail_bwd_kernel", "analysis_x_tc_kernel",
     "synthesis_x_tc_kernel", "scale_modes_kernel", "rational_g_kernel", "analysis_zy_tc3_kernel",
     "synthesis_zy_tc3_kernel", "analysis_x_tc3_kernel", "synthesis_x_tc3_kernel", "gen_z_analysis_kernel",
-    "gen_z_synthesis_kernel", "gen_axis_analysis_kernel", "gen_axis_synthesis_kernel"};
+    "gen_z_synthesis_kernel", "gen_axis_analysis_kernel", "gen_axis_synthesis_kernel", "block_spectral_fwd_kernel"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 static std::atomic<long long> g_launches[K_COUNT];
 static std::atomic<bool> g_prof_on{false};

@@ -632,6 +632,30 @@ __global__ void gen_pad_scale_kernel(const float2* __restrict__ Z, float2* __res
   Zp[i] = v;
 }
 
+// The same with the channel index moved inside: Zc[b][kx][ky][c][0..ldh) = Z[b*C + c][kx][ky][kz] * scales.  With the
+// channels innermost the x and y synthesis stages treat (c, kz) as columns, and the rows of V = [b, x, y][c][ldz] that one
+// block-tail tile reads (block_tc.cu, fused forward) are 64*ldz contiguous floats.
+__global__ void gen_pad_scale_cinner_kernel(const float2* __restrict__ Z, float2* __restrict__ Zc, const float* __restrict__ mode_scale,
+                                            const float* __restrict__ row_scale, long long rs_stride, int zm, int ldh, int C,
+                                            long long Mrows, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kz = (int)(i % ldh);
+  long long r = i / ldh;
+  const int c = (int)(r % C);
+  r /= C;
+  const long long kr = r % Mrows, b = r / Mrows;      // kr = kx*my + ky
+  float2 v = make_float2(0.f, 0.f);
+  if (kz < zm) {
+    const long long bc = b * C + c;
+    float s = mode_scale ? __ldg(mode_scale + kr * zm + kz) : 1.f;
+    if (row_scale) s *= __ldg(row_scale + bc * rs_stride);
+    const float2 z = __ldg(Z + (bc * Mrows + kr) * zm + kz);
+    v = make_float2(z.x * s, z.y * s);
+  }
+  Zc[i] = v;
+}
+
 }  // namespace gen
 
 // ------------------------------------------------------------------------------------------------
@@ -942,4 +966,66 @@ int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0,
   return PDEPHI_OK;
 }
 
+int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const float* bzimg, const float* Wc, const float* bc,
+                                float* u, float* hout, int B, long long S, cudaStream_t st);
+
+// The fused block forward is available when the per-axis kernels cover the shape and a 128-point tile of the block
+// tail is exactly one z line.
+bool block_spectral_ok(const Plan* p, int C) {
+  return p->gen_ok && p->g.has_mid && p->Nz == 128 && C == 64 && p->g.ldz <= 64 && p->Nx == p->Nx_total;
+}
+
 }  // namespace pdephi
+
+using namespace pdephi;
+
+extern "C" int pdephi_block_spectral_supported(pdephi_plan_t plan, int C) {
+  const Plan* p = (const Plan*)plan;
+  return (p && block_spectral_ok(p, C)) ? 1 : 0;
+}
+
+extern "C" size_t pdephi_block_spectral_fwd_workspace_bytes(pdephi_plan_t plan, int B, int C) {
+  const Plan* p = (const Plan*)plan;
+  if (!p || !block_spectral_ok(p, C) || B <= 0) return 0;
+  return gen_workspace_bytes(p, (long long)B * C);
+}
+
+extern "C" int pdephi_block_spectral_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                                         long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u,
+                                         float* hout, int B, int C, void* workspace, size_t workspace_bytes,
+                                         pdephi_stream_t stream) {
+  const Plan* p = (const Plan*)plan;
+  PDEPHI_REQUIRE(p && Y && h && Wc && u && hout, "block_spectral_fwd: null pointer");
+  if (!block_spectral_ok(p, C))
+    return fail(PDEPHI_ERR_UNSUPPORTED, "block_spectral_fwd: needs width 64, Nz = 128 and a shape of the per-axis tensor-core route");
+  const long long BC = (long long)B * C;
+  const size_t need = gen_workspace_bytes(p, BC);
+  if (!workspace || workspace_bytes < need)
+    return fail(PDEPHI_ERR_WORKSPACE, "block_spectral_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const GenPlan& g = p->g;
+  const GenWs w = gen_ws(p, BC);
+  char* wb = (char*)workspace;
+  float* V = (float*)(wb + w.w1);      // [B, Nx, Ny, C, ldz]
+  float* W2 = (float*)(wb + w.w2);     // [BC, Nx, my, ldz]
+  float* Zp = (float*)(wb + w.zp);     // [BC, mx, my, ldz]
+  // modes -> channel-innermost padded layout [B, mx, my, C, ldz] (always: it is also the transposition)
+  {
+    const long long Mrows = (long long)p->mx * p->my;
+    const long long total = (long long)B * Mrows * C * (g.ldz / 2);
+    {
+      ProfScope ps(K_SCALE_MODES, st);
+      gen::gen_pad_scale_cinner_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float2*)Y, (float2*)Zp, mode_scale,
+                                                                                      row_scale, row_scale_stride, g.zm, g.ldz / 2,
+                                                                                      C, Mrows, total);
+    }
+    PDEPHI_LAUNCH_CHECK("gen_pad_scale_cinner_kernel");
+  }
+  // x stage: batch = volume b, columns = (ky, c, kz);  y stage: batch = (b, x), columns = (c, kz) -> V [b, x, y][c][ldz]
+  int rc = launch_axis_synthesis(p, Zp, B, p->Nx, p->mx, g.mkx, p->my * C * g.ldz, W2, g.xsc, g.xss, g.xs_st, K_GEN_AXIS_SYNTHESIS, st);
+  if (rc) return rc;
+  rc = launch_axis_synthesis(p, W2, (long long)B * p->Nx, p->Ny, p->my, g.mky, C * g.ldz, V, g.ysc, g.yss, g.ys_st,
+                             K_GEN_AXIS_SYNTHESIS, st);
+  if (rc) return rc;
+  return block_tail_fwd_fused_launch(h, V, g.ldz, g.zs[PDEPHI_FORWARD], Wc, bc, u, hout, B, (long long)p->Nx * p->Ny * p->Nz, st);
+}

@@ -206,6 +206,33 @@ def block_tail_fwd(h, spec, Wc, bc):
     return u, hout
 
 
+def block_spectral_supported(h: torch.Tensor, modes_h, precision: int) -> bool:
+    """Whole spectral-synthesis + block-tail forward in one chain with `spec` never materialised (pdephi_block_spectral_fwd):
+    single-pass TF32 route, width 64, Nz = 128, shapes of the per-axis tensor-core kernels."""
+    if precision != _cabi.PREC_TF32 or h.shape[1] != 64:
+        return False
+    with torch.cuda.device(h.device):
+        plan = _cabi.get_plan(h.device.index, tuple(h.shape[2:]), modes_h)
+        return bool(_cabi.load().pdephi_block_spectral_supported(plan, 64))
+
+
+def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc):
+    """u = S(Y * mode_scale * row_scale) + (Wc h + bc) + h, hout = gelu(u): x / y stages of the synthesis as per-axis
+    tensor-core contractions, z stage inside the block-tail kernel."""
+    B, C = h.shape[:2]
+    lib = _cabi.load()
+    rs_stride = row_scale.stride(0) if row_scale is not None else 0
+    with torch.cuda.device(h.device):
+        plan = _cabi.get_plan(h.device.index, tuple(h.shape[2:]), tuple(Y.shape[2:]))
+        u = torch.empty_like(h)
+        hout = torch.empty_like(h)
+        nbytes = lib.pdephi_block_spectral_fwd_workspace_bytes(plan, B, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+        _cabi.check(lib.pdephi_block_spectral_fwd(plan, _p(Y), _p(mode_scale), _p(row_scale), rs_stride, _p(h), _p(Wc), _p(bc),
+                                                  _p(u), _p(hout), B, C, _p(ws), nbytes, _stream()), "block_spectral_fwd")
+    return u, hout
+
+
 def block_tail_bwd(g, u, h, Wc, want_bias: bool):
     """gu = g gelu'(u), t = gu + Wc^T gu, dWc = sum gu (x) h, dbc = sum gu."""
     B, C = h.shape[:2]
@@ -657,8 +684,11 @@ class RationalBlockFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
         stats = sl.complete_stats(stats, eps)
-        spec = sl.synthesis(Y, grid, mask, stats[:, 2], None, None, _cabi.FORWARD, precision)
-        u, hout = block_tail_fwd(h, spec, Wc, bc)
+        if not sl.active and block_spectral_supported(h, modes_h, precision):
+            u, hout = block_spectral_fwd(Y, mask, stats[:, 2], h, Wc, bc)      # `spec` never touches HBM
+        else:
+            spec = sl.synthesis(Y, grid, mask, stats[:, 2], None, None, _cabi.FORWARD, precision)
+            u, hout = block_tail_fwd(h, spec, Wc, bc)
         if need_grad:
             ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc)
         ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, bc is not None, sl)
@@ -695,8 +725,11 @@ class ComplexBlockFn(torch.autograd.Function):
         Wl, Wc = _local_weights(W, sl, my), Wc.contiguous()
         X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
         Y = complex_mix_fwd(X, Wl, modes_h[2])
-        spec = sl.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, precision)
-        u, hout = block_tail_fwd(h, spec, Wc, bc)
+        if not sl.active and block_spectral_supported(h, modes_h, precision):
+            u, hout = block_spectral_fwd(Y, None, None, h, Wc, bc)
+        else:
+            spec = sl.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, precision)
+            u, hout = block_tail_fwd(h, spec, Wc, bc)
         ctx.save_for_backward(X, Wl, W, u, h, Wc)
         ctx.meta = (modes_h, grid, precision, bc is not None, sl)
         return hout

@@ -65,6 +65,35 @@ __global__ void __launch_bounds__(256, 1) write_plane_kernel(float* __restrict__
     for (int g = 0; g < 16; ++g) __stcs(reinterpret_cast<float4*>(base + (size_t)(2 * g) * 128), v);
   }
 }
+// write-only, the block tail's tile pattern (64 channel rows 8 MB apart x 128 points, two output tensors):
+//   SEG = 128: a warp instruction stores 128 B of one row (lane = point, 4 B each) -- the epilogue's TMEM-lane mapping
+//   SEG = 512: a warp instruction stores 512 B of one row (lane = 4 consecutive points)
+template <int SEG>
+__global__ void __launch_bounds__(512, 1) tile_write_kernel(float* __restrict__ c, float* __restrict__ d, long long S, long long ntiles,
+                                                            long long tiles_per_batch, int contiguous) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tq = ntiles / gridDim.x;
+  for (long long it = 0; it < tq; ++it) {
+    const long long t = contiguous ? blockIdx.x * tq + it : blockIdx.x + it * gridDim.x;
+    const long long bb = t / tiles_per_batch, s0 = (t - bb * tiles_per_batch) * 128;
+    if (SEG == 128) {
+      const int q = warp & 3, part = warp >> 2;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const size_t o = (size_t)(bb * 64 + part * 16 + j) * S + s0 + 32 * q + lane;
+        __stcs(c + o, 1.f);
+        d[o] = 2.f;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const size_t o = (size_t)(bb * 64 + warp * 4 + r) * S + s0 + lane * 4;
+        __stcs(reinterpret_cast<float4*>(c + o), make_float4(1.f, 2.f, 3.f, 4.f));
+        *reinterpret_cast<float4*>(d + o) = make_float4(1.f, 2.f, 3.f, 4.f);
+      }
+    }
+  }
+}
 template <int NR, int NW>
 __global__ void flat_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ c, float4* __restrict__ d, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -107,6 +136,15 @@ int main() {
   { const long long planes = (long long)(n / (128 * 128)); for (int g : {148, 296}) {
       float ms = time_ms([&] { write_plane_kernel<<<g, 256>>>(c, planes); });
       printf("write-only planes grid=%4d: %.3f ms  %.0f GB/s\n", g, ms, gb / ms * 1e3); } }
+  { long long tpb = S / 128, nt = tpb * B;
+    for (int cont : {0, 1}) {
+      float ms = time_ms([&] { tile_write_kernel<128><<<148, 512>>>(c, d, S, nt, tpb, cont); });
+      printf("tile write-only SEG=128 contiguous=%d: %.3f ms  %.0f GB/s\n", cont, ms, 2 * gb / ms * 1e3);
+      ms = time_ms([&] { tile_write_kernel<512><<<148, 512>>>(c, d, S, nt, tpb, cont); });
+      printf("tile write-only SEG=512 contiguous=%d: %.3f ms  %.0f GB/s\n", cont, ms, 2 * gb / ms * 1e3);
+      ms = time_ms([&] { tile_write_kernel<512><<<296, 512>>>(c, d, S, nt, tpb, cont); });
+      printf("tile write-only SEG=512 grid 296 contiguous=%d: %.3f ms  %.0f GB/s\n", cont, ms, 2 * gb / ms * 1e3);
+    } }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status %s\n", cudaGetErrorString(e));
   return 0;

@@ -522,6 +522,75 @@ def test_fused_block_tail_vs_torch():
     assert rel(db, conv.bias.grad) < TOL["tf32"]
 
 
+@pytest.mark.parametrize("B,grid,modes", [(1, (32, 128, 128), (8, 16, 16)), (2, (128, 128, 128), (32, 32, 32)), (1, (64, 128, 128), (5, 12, 38))])
+def test_fused_spectral_block_forward(B, grid, modes):
+    """pdephi_block_spectral_fwd (x / y synthesis stages channel-innermost, z stage inside the block-tail kernel, `spec`
+    never materialised) against the fp32 synthesis + plain torch ops, with the spectral branch dominating u."""
+    mh = (modes[0], modes[1], modes[2] // 2 + 1)
+    torch.manual_seed(41)
+    C = 64
+    h = torch.randn(B, C, *grid, device=DEV)
+    if not pf.block_spectral_supported(h, mh, _cabi.PREC_TF32):
+        pytest.skip("fused spectral block forward not available for this shape")
+    n = float(np.prod(grid))
+    Y = torch.randn(B, C, *mh, device=DEV, dtype=torch.complex64) * (n / np.sqrt(np.prod(mh))) * 3.0     # spec ~ 3x the rest
+    Wc = torch.randn(C, C, device=DEV) * 0.1
+    bc = torch.randn(C, device=DEV)
+    mask = (torch.rand(mh, device=DEV) + 0.5).reshape(-1).contiguous()
+    rs = torch.rand(B * C, 4, device=DEV) + 0.5
+    spec = pf.synthesis(Y, grid, mask, rs[:, 2], None, None, _cabi.FORWARD, _cabi.PREC_FP32).double()
+    rest = torch.einsum("oc,bcxyz->boxyz", Wc.double(), h.double()) + bc.double().view(1, C, 1, 1, 1) + h.double()
+    u, hout = pf.block_spectral_fwd(Y, mask, rs[:, 2], h, Wc, bc)
+    assert float(spec.norm()) > float(rest.norm())
+    assert rel(u, spec + rest) < TOL["tf32"]
+    assert rel(u.double() - rest, spec) < TOL["tf32"]                        # the spectral branch on its own
+    assert rel(hout, torch.nn.functional.gelu(spec + rest)) < TOL["tf32"]
+    u2, _ = pf.block_spectral_fwd(Y, None, None, h, Wc, None)                   # no scaling, no bias (FNO3D's block)
+    spec2 = pf.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, _cabi.PREC_FP32).double()
+    assert rel(u2, spec2 + rest - bc.double().view(1, C, 1, 1, 1)) < TOL["tf32"]
+
+
+def test_whole_block_model_on_the_fused_spectral_route():
+    """RationalFourierOperator3D at width 64 on a [*,128,128]-plane grid in TF32 mode runs every block through
+    pdephi_block_spectral_fwd; compare with the unfused route on outputs and every parameter gradient."""
+    torch.manual_seed(35)
+    modes, grid = (8, 16, 16), (32, 128, 128)
+    model = pb.RationalFourierOperator3D(modes=modes, width=64, n_layers=2).to(DEV).set_precision("tf32")
+    with torch.no_grad():
+        for layer in model.rational_layers:
+            q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+            layer.Q_coeffs.mul_(1e-4)
+            layer.Q_coeffs[..., 0, 0, 0] = q0
+            layer.P_coeffs.mul_(1e-2)
+    x = torch.randn(1, 3, *grid, device=DEV)
+    y = torch.randn(1, 3, *grid, device=DEV)
+    hh = torch.empty(1, 64, *grid, device=DEV)
+    assert model.rational_layers[0].block_supported(hh, model.local_convs[0])
+    assert pf.block_spectral_supported(hh, (8, 16, 9), _cabi.PREC_TF32)
+    _cabi.profile(True, True)
+    loss = torch.nn.functional.mse_loss(model(x), y)
+    loss.backward()
+    torch.cuda.synchronize()
+    rep = _cabi.profile_report(timed=False)
+    _cabi.profile(False, True)
+    assert rep.get("block_spectral_fwd_kernel", (0, 0))[0] == 2 and "block_tail_fwd_kernel" not in rep
+    fused = {n: p.grad.clone() for n, p in model.named_parameters()}
+    out_fused = model(x).detach()
+    model.zero_grad()
+    model.activation = lambda t: torch.nn.functional.gelu(t)        # not F.gelu itself -> unfused route
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        loss2 = torch.nn.functional.mse_loss(model(x), y)
+        loss2.backward()
+        out_ref = model(x).detach()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel(out_fused, out_ref) < 3e-3
+    for n, p in model.named_parameters():
+        assert rel(fused[n], p.grad) < 6e-3, (n, rel(fused[n], p.grad))
+
+
 def test_whole_block_model_tf32_vs_unfused():
     """RationalFourierOperator3D at width 64 takes the fused-block route in TF32 mode; compare with the unfused route
     (same kernels for the spectral part, torch for conv / GELU) on outputs and every parameter gradient."""
