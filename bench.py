@@ -356,10 +356,13 @@ def run_native(args):
             "analysis_zy_tc_kernel": act + mid, "analysis_zy_kernel": act + mid, "analysis_zy_tc3_kernel": act + mid,
             "synthesis_zy_tc3_kernel": act + mid + 1.5 * act,   # unfused block route: forward fuses both skip addends, adjoint one
             "analysis_x_tc3_kernel": mid + modes_b, "synthesis_x_tc3_kernel": mid + modes_b,
-            # per step: 4 forward launches without addends + 4 adjoint launches with one addend -> mean
-            "synthesis_zy_tc_kernel": act + mid + 0.5 * act,
+            # fused block route: the forward synthesis lives in block_spectral_fwd_kernel, so every launch of this kernel is
+            # an adjoint one with one addend (the unfused forward launches, if any, carry none: counted from the launches)
+            "synthesis_zy_tc_kernel": act + mid + act,
             "synthesis_zy_kernel": act + mid + 1.5 * act,   # fp32 route: forward fuses both skip addends, adjoint one
             "block_tail_fwd_kernel": 4 * act,            # read h, spec; write u, h'
+            # fused forward: read h and V [B,Nx,Ny,64,ldz] (ldz = 2*mzh rounded up to 4 floats); write u, h'
+            "block_spectral_fwd_kernel": 3 * act + 4.0 * B * C * n * n * ((2 * mzh + 3) // 4 * 4),
             "block_tail_bwd_kernel": 5 * act,            # read g', u, h; write gu, t
             "analysis_x_tc_kernel": mid + modes_b, "synthesis_x_tc_kernel": mid + modes_b,
         }
@@ -371,6 +374,8 @@ def run_native(args):
                 avg_ms = v[1] / v[0]
                 if k.startswith("block_tail_bwd"):
                     avg_ms = v[1] / (v[0] / 2)           # the tiny partial-sum reduce kernel shares the counter
+                if k == "synthesis_zy_tc_kernel" and "block_spectral_fwd_kernel" not in prof:
+                    alg[k] = act + mid + 0.5 * act       # unfused forward: half the launches carry no addend
                 ach = alg[k] / (avg_ms * 1e-3) / 1e9
                 rooflines[k] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                                 "frac": round(ach / peak, 4), "algorithmic_bytes_per_launch": alg[k],
@@ -379,7 +384,7 @@ def run_native(args):
         dom = max(rooflines, key=lambda k: prof[k][1]) if rooflines else None
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
         ncu_traffic = {"analysis_zy_tc_kernel": 4.580e9, "synthesis_zy_tc_kernel": None, "block_tail_fwd_kernel": 17.187e9,
-                       "block_tail_bwd_kernel": 21.489e9}
+                       "block_tail_bwd_kernel": 21.489e9, "block_spectral_fwd_kernel": 14.093e9}
         for k in rooflines:
             rooflines[k]["traffic"] = ncu_traffic.get(k)
         roof = None
