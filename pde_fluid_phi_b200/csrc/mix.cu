@@ -47,6 +47,36 @@ __device__ __forceinline__ float eval_R(const float* cp, const float* cq, const 
   return __fdiv_rn(p, qe);
 }
 
+// Two transfer functions at once (output channels u and u+1, same mode k) on Blackwell's packed fp32 pipe.  The
+// reference's rounding sequence needs a separately rounded product and a separately rounded add per monomial, and
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (also under -fmad=false; it even folds fma(a, 1, b) back
+// to an add first).  So both steps are written as FMAs whose constant operands are RUNTIME values the compiler cannot
+// see through:  term = fma(c, m, -0) rounds c*m once (and keeps the sign of a zero product), acc = fma(acc, 1, term)
+// rounds acc + term once -- bit for bit __fmul_rn / __fadd_rn, at half the instruction count.
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// cp2 / cq2: coefficient pairs (c_u[t], c_{u+1}[t]); one2 = (1, 1), nz2 = (-0, -0) from kernel arguments
+template <int TPN, int TQN>
+__device__ __forceinline__ void eval_R2(const uint64_t* cp2, const uint64_t* cq2, const float* mp, const float* mq, float eps,
+                                        uint64_t one2, uint64_t nz2, float* R, float* qe) {
+  uint64_t p = pk2(0.f, 0.f), q = pk2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < TPN; ++t) p = fma2(p, one2, fma2(cp2[t], pk2(mp[t], mp[t]), nz2));
+#pragma unroll
+  for (int t = 0; t < TQN; ++t) q = fma2(q, one2, fma2(cq2[t], pk2(mq[t], mq[t]), nz2));
+  q = fma2(q, one2, pk2(eps, eps));
+  float p0, p1;
+  upk2(p, p0, p1);
+  upk2(q, qe[0], qe[1]);
+  R[0] = __fdiv_rn(p0, qe[0]);
+  R[1] = __fdiv_rn(p1, qe[1]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // out[b][u][k] = sum_v R(u,v)[k] * in[b][v][k]     (TR=false: (o,i)=(u,v);  TR=true: (o,i)=(v,u))
 // thread = one mode k (coalesced along k), UT output channels x BT batch entries per thread.
@@ -60,12 +90,13 @@ __global__ void __launch_bounds__(MIX_THREADS)
 rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float* __restrict__ P,
                     const float* __restrict__ Q, const float* __restrict__ monoP, const float* __restrict__ monoQ,
                     float eps, float* __restrict__ Rout, float* __restrict__ Qeout, int B, int U, int V, long long M,
-                    MonoOffsets offs) {
+                    MonoOffsets offs, float one, float negzero) {
   constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
   constexpr int TP4 = Tri<OP>::TP4, TQ4 = Tri<OQ>::TP4;
   extern __shared__ __align__(16) float smem[];
-  float* cPs = smem;                            // [UT][V][TP4]
-  float* cQs = smem + (size_t)UT * V * TP4;     // [UT][V][TQ4]
+  float* cPs = smem;                            // [UT/2][V][TP4][2]: coefficient pairs of output channels (2p, 2p+1)
+  float* cQs = smem + (size_t)UT * V * TP4;     // [UT/2][V][TQ4][2]
+  const uint64_t one2 = pk2(one, one), nz2 = pk2(negzero, negzero);
   const int u0 = blockIdx.y * UT;
   const int O = TR ? V : U, I = TR ? U : V;
   (void)O;
@@ -73,13 +104,15 @@ rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, con
     const int t = idx % TP4, uv = idx / TP4, v = uv % V, ul = uv / V;
     const int u = min(u0 + ul, U - 1);
     const int o = TR ? v : u, i = TR ? u : v;
-    cPs[idx] = (t < TPN) ? __ldg(P + ((size_t)o * I + i) * (OP * OP * OP) + offs.p[t]) : 0.f;
+    cPs[((((size_t)(ul >> 1) * V + v) * TP4 + t) << 1) + (ul & 1)] =
+        (t < TPN) ? __ldg(P + ((size_t)o * I + i) * (OP * OP * OP) + offs.p[t]) : 0.f;
   }
   for (int idx = threadIdx.x; idx < UT * V * TQ4; idx += MIX_THREADS) {
     const int t = idx % TQ4, uv = idx / TQ4, v = uv % V, ul = uv / V;
     const int u = min(u0 + ul, U - 1);
     const int o = TR ? v : u, i = TR ? u : v;
-    cQs[idx] = (t < TQN) ? __ldg(Q + ((size_t)o * I + i) * (OQ * OQ * OQ) + offs.q[t]) : 0.f;
+    cQs[((((size_t)(ul >> 1) * V + v) * TQ4 + t) << 1) + (ul & 1)] =
+        (t < TQN) ? __ldg(Q + ((size_t)o * I + i) * (OQ * OQ * OQ) + offs.q[t]) : 0.f;
   }
   __syncthreads();
 
@@ -106,31 +139,35 @@ rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, con
       for (int j = 0; j < BT; ++j)
         xin[j] = (b0 + j < B) ? __ldg(in + ((size_t)(b0 + j) * V + v) * M + kc) : make_float2(0.f, 0.f);
 #pragma unroll
-      for (int ul = 0; ul < UT; ++ul) {
-        float cp[TP4], cq[TQ4];
-        const float4* p4 = reinterpret_cast<const float4*>(cPs + ((size_t)ul * V + v) * TP4);
-        const float4* q4 = reinterpret_cast<const float4*>(cQs + ((size_t)ul * V + v) * TQ4);
+      for (int up = 0; up < UT / 2; ++up) {
+        uint64_t cp2[TP4], cq2[TQ4];
+        const float4* p4 = reinterpret_cast<const float4*>(cPs + (((size_t)up * V + v) * TP4) * 2);
+        const float4* q4 = reinterpret_cast<const float4*>(cQs + (((size_t)up * V + v) * TQ4) * 2);
 #pragma unroll
-        for (int t = 0; t < TP4 / 4; ++t) {
+        for (int t = 0; t < TP4 / 2; ++t) {
           const float4 c = p4[t];
-          cp[4 * t] = c.x; cp[4 * t + 1] = c.y; cp[4 * t + 2] = c.z; cp[4 * t + 3] = c.w;
+          cp2[2 * t] = pk2(c.x, c.y); cp2[2 * t + 1] = pk2(c.z, c.w);
         }
 #pragma unroll
-        for (int t = 0; t < TQ4 / 4; ++t) {
+        for (int t = 0; t < TQ4 / 2; ++t) {
           const float4 c = q4[t];
-          cq[4 * t] = c.x; cq[4 * t + 1] = c.y; cq[4 * t + 2] = c.z; cq[4 * t + 3] = c.w;
+          cq2[2 * t] = pk2(c.x, c.y); cq2[2 * t + 1] = pk2(c.z, c.w);
         }
-        float qe;
-        const float R = eval_R<TPN, TQN>(cp, cq, mp, mq, eps, &qe);
-        if (!TR && Rout && b0 == 0 && k < M && u0 + ul < U) {   // materialise R and Q+eps once for the backward
-          const size_t ri = ((size_t)(u0 + ul) * V + v) * M + k;
-          Rout[ri] = R;
-          Qeout[ri] = qe;
-        }
+        float R2[2], qe2[2];
+        eval_R2<TPN, TQN>(cp2, cq2, mp, mq, eps, one2, nz2, R2, qe2);
 #pragma unroll
-        for (int j = 0; j < BT; ++j) {
-          acc[ul][j].x = fmaf(R, xin[j].x, acc[ul][j].x);
-          acc[ul][j].y = fmaf(R, xin[j].y, acc[ul][j].y);
+        for (int h = 0; h < 2; ++h) {
+          const int ul = 2 * up + h;
+          if (!TR && Rout && b0 == 0 && k < M && u0 + ul < U) {   // materialise R and Q+eps once for the backward
+            const size_t ri = ((size_t)(u0 + ul) * V + v) * M + k;
+            Rout[ri] = R2[h];
+            Qeout[ri] = qe2[h];
+          }
+#pragma unroll
+          for (int j = 0; j < BT; ++j) {
+            acc[ul][j].x = fmaf(R2[h], xin[j].x, acc[ul][j].x);
+            acc[ul][j].y = fmaf(R2[h], xin[j].y, acc[ul][j].y);
+          }
         }
       }
     }
@@ -555,7 +592,8 @@ static int launch_mix(const float2* in, float2* out, const float* P, const float
   dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (U + UT - 1) / UT);
   {
     ProfScope ps(K_RATIONAL_MIX, st);
-    k<<<grid, MIX_THREADS, smem, st>>>(in, out, P, Q, monoP, monoQ, eps, Rout, Qeout, B, U, V, M, offs);
+    // 1 and -0 travel as kernel arguments: the packed evaluation needs them opaque to the compiler (see eval_R2)
+    k<<<grid, MIX_THREADS, smem, st>>>(in, out, P, Q, monoP, monoQ, eps, Rout, Qeout, B, U, V, M, offs, 1.0f, -0.0f);
   }
   PDEPHI_LAUNCH_CHECK("rational_mix_kernel");
   return PDEPHI_OK;

@@ -1,1 +1,2 @@
-for d in 0 1 2 3; do echo "== dbg $d"; PDEPHI_BLOCK_DBG=$d timeout 300 python scripts/block_time.py 2>&1 | tail -1; done
+timeout 900 python -m pytest tests/test_parity_gpu.py -x -q -k "transfer_function or rational_layer or golden" 2>&1 | tail -4
+timeout 300 python scripts/layer_bench.py tf32 10 --gen 2>&1 | tail -3 | cut -c1-420
