@@ -75,7 +75,7 @@ pointwise_linear_kernel(const float* __restrict__ x, const float* __restrict__ W
 // sum_big[big_ch], sum_small[small_ch].  Stage 1: per-CTA partials (fixed order), stage 2: fixed-order sum.
 constexpr int PG_BT = 8;       // big channels per CTA
 template <int CS>              // channels on the small side, compile time so no predicated-off FMAs are issued
-__global__ void __launch_bounds__(PW_THREADS)
+__global__ void __launch_bounds__(PW_THREADS, 2)   // 160 registers unbounded = one 8-warp CTA per SM: latency-bound at 3.5 TB/s
 pointwise_wgrad_kernel(const float* __restrict__ big, const float* __restrict__ small, float* __restrict__ partial,
                        int Cbig, long long S4, int B, long long chunk4) {
   constexpr int Csmall = CS;
