@@ -129,11 +129,48 @@ def get_plan(device_index: int, grid, modes_h, slab=None):
     return h
 
 
+_auto_route = {}
+_ws_bytes = {}
+
+
 def resolve_precision(plan, precision: int) -> int:
-    """PREC_AUTO -> the fastest route that meets the fp32 parity gate for this plan's shape."""
+    """PREC_AUTO -> the fastest route that meets the fp32 parity gate for this plan's shape (cached per plan: at the
+    small shapes of cfg 1 a layer is launch-latency-bound and every ctypes round trip counts)."""
     if precision != PREC_AUTO:
         return precision
-    return PREC_TF32X3 if load().pdephi_plan_supports(plan, PREC_TF32X3) else PREC_FP32
+    r = _auto_route.get(plan.value)
+    if r is None:
+        r = PREC_TF32X3 if load().pdephi_plan_supports(plan, PREC_TF32X3) else PREC_FP32
+        _auto_route[plan.value] = r
+    return r
+
+
+def workspace_bytes(plan, BC: int) -> int:
+    """pdephi_plan_workspace_bytes(plan, BC), cached."""
+    key = (plan.value, int(BC))
+    n = _ws_bytes.get(key)
+    if n is None:
+        n = load().pdephi_plan_workspace_bytes(plan, BC)
+        _ws_bytes[key] = n
+    return n
+
+
+class _NoDeviceSwitch:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_no_switch = _NoDeviceSwitch()
+
+
+def on_device(device):
+    """Context manager that makes `device` current -- a no-op object when it already is (torch.cuda.device costs a few
+    microseconds per use, which adds up over the ~10 library calls of one small layer)."""
+    import torch
+    return _no_switch if torch.cuda.current_device() == device.index else torch.cuda.device(device)
 
 
 def profile(enable: bool = True, reset: bool = True):

@@ -19,6 +19,21 @@ from torch.autograd.function import once_differentiable
 from . import _cabi
 
 
+def _opaque(fn):
+    """torch.compile must treat a call into the library as one opaque eager op: dynamo cannot trace ctypes, and there is
+    nothing for it to fuse below this seam.  The reference wraps its models in torch.compile(mode='max-autotune')
+    (optimization/performance_optimization.py:466-486); with this the wrapper graph-breaks around the spectral layers
+    and runs the same kernels."""
+    disable = getattr(getattr(torch, "compiler", None), "disable", None)
+    return disable(fn, recursive=True) if disable is not None else fn
+
+
+@_opaque
+def library_call(fn_cls, *args):
+    """fn_cls.apply(*args) for one of the autograd Functions below, outside of any dynamo trace."""
+    return fn_cls.apply(*args)
+
+
 def _p(t: Optional[torch.Tensor]):
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
 
@@ -68,11 +83,11 @@ def analysis(x: torch.Tensor, modes_h: Tuple[int, int, int], direction: int = _c
     B, C = x.shape[:2]
     grid = tuple(x.shape[2:])
     lib = _cabi.load()
-    with torch.cuda.device(x.device):
+    with _cabi.on_device(x.device):
         plan = _cabi.get_plan(x.device.index, grid, modes_h, slab)
         precision = _cabi.resolve_precision(plan, precision)
         X = torch.empty((B, C, *modes_h), dtype=torch.complex64, device=x.device)
-        nbytes = lib.pdephi_plan_workspace_bytes(plan, B * C)
+        nbytes = _cabi.workspace_bytes(plan, B * C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         _cabi.check(lib.pdephi_analysis_r2c(plan, _p(x), _p(X), B * C, direction, precision, _p(ws), nbytes, _stream()),
                     "analysis_r2c")
@@ -106,11 +121,11 @@ def synthesis(Z: torch.Tensor, grid: Tuple[int, int, int], mode_scale: Optional[
     a0 = addend0.contiguous() if addend0 is not None else None
     a1 = addend1.contiguous() if addend1 is not None else None
     lib = _cabi.load()
-    with torch.cuda.device(Z.device):
+    with _cabi.on_device(Z.device):
         plan = _cabi.get_plan(Z.device.index, grid, modes_h, slab)
         precision = _cabi.resolve_precision(plan, precision)
         out = torch.empty((B, C, *grid), dtype=torch.float32, device=Z.device)
-        nbytes = lib.pdephi_plan_workspace_bytes(plan, B * C)
+        nbytes = _cabi.workspace_bytes(plan, B * C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=Z.device)
         _cabi.check(lib.pdephi_synthesis_c2r(plan, _p(Z), _p(out), _p(a0), _p(a1), _p(mode_scale), _p(row_scale),
                                              rs_stride, B * C, direction, precision, _p(ws), nbytes, _stream()),
@@ -125,7 +140,7 @@ def rational_mix_fwd(X, P, Q, monoP, monoQ, eps: float, mask, proj_eps: float, k
     O = P.shape[0]
     M = X[0, 0].numel()
     lib = _cabi.load()
-    with torch.cuda.device(X.device):
+    with _cabi.on_device(X.device):
         Y = torch.empty((B, O, *X.shape[2:]), dtype=torch.complex64, device=X.device)
         stats = torch.empty((B * O, 4), dtype=torch.float32, device=X.device)
         R = Qe = None
@@ -142,7 +157,7 @@ def projection_bwd(dZ, Y, mask, stats):
     rows = Y.shape[0] * Y.shape[1]
     M = Y[0, 0].numel()
     lib = _cabi.load()
-    with torch.cuda.device(Y.device):
+    with _cabi.on_device(Y.device):
         dY = torch.empty_like(Y)
         _cabi.check(lib.pdephi_projection_bwd(_p(dZ), _p(Y), _p(mask), _p(stats), _p(dY), rows, M, _stream()),
                     "projection_bwd")
@@ -156,7 +171,7 @@ def rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes):
     M = X[0, 0].numel()
     p_shape, q_shape = coeff_shapes
     lib = _cabi.load()
-    with torch.cuda.device(X.device):
+    with _cabi.on_device(X.device):
         dX = torch.empty_like(X)
         dP = torch.empty(p_shape, dtype=torch.float32, device=X.device)
         dQ = torch.empty(q_shape, dtype=torch.float32, device=X.device)
@@ -173,7 +188,7 @@ def complex_mix_fwd(X, W, mzh: int):
     O = W.shape[0]
     mx, my, mz = W.shape[2:]
     lib = _cabi.load()
-    with torch.cuda.device(X.device):
+    with _cabi.on_device(X.device):
         Y = torch.empty((B, O, mx, my, mzh), dtype=torch.complex64, device=X.device)
         _cabi.check(lib.pdephi_complex_mix_fwd(_p(X), _p(W), _p(Y), B, I, O, mx * my, mzh, mz, _stream()),
                     "complex_mix_fwd")
@@ -185,7 +200,7 @@ def complex_mix_bwd(X, W, dY, mzh: int):
     O = W.shape[0]
     mx, my, mz = W.shape[2:]
     lib = _cabi.load()
-    with torch.cuda.device(X.device):
+    with _cabi.on_device(X.device):
         dX = torch.empty_like(X)
         dW = torch.empty_like(W)
         _cabi.check(lib.pdephi_complex_mix_bwd(_p(X), _p(W), _p(dY), _p(dX), _p(dW), B, I, O, mx * my, mzh, mz,
@@ -198,7 +213,7 @@ def block_tail_fwd(h, spec, Wc, bc):
     B, C = h.shape[:2]
     S = h[0, 0].numel()
     lib = _cabi.load()
-    with torch.cuda.device(h.device):
+    with _cabi.on_device(h.device):
         u = torch.empty_like(h)
         hout = torch.empty_like(h)
         _cabi.check(lib.pdephi_block_tail_fwd(_p(h), _p(spec), _p(Wc), _p(bc), _p(u), _p(hout), B, C, S, _stream()),
@@ -211,7 +226,7 @@ def block_spectral_supported(h: torch.Tensor, modes_h, precision: int) -> bool:
     single-pass TF32 route, width 64, Nz = 128, shapes of the per-axis tensor-core kernels."""
     if precision != _cabi.PREC_TF32 or h.shape[1] != 64:
         return False
-    with torch.cuda.device(h.device):
+    with _cabi.on_device(h.device):
         plan = _cabi.get_plan(h.device.index, tuple(h.shape[2:]), modes_h)
         return bool(_cabi.load().pdephi_block_spectral_supported(plan, 64))
 
@@ -222,7 +237,7 @@ def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc):
     B, C = h.shape[:2]
     lib = _cabi.load()
     rs_stride = row_scale.stride(0) if row_scale is not None else 0
-    with torch.cuda.device(h.device):
+    with _cabi.on_device(h.device):
         plan = _cabi.get_plan(h.device.index, tuple(h.shape[2:]), tuple(Y.shape[2:]))
         u = torch.empty_like(h)
         hout = torch.empty_like(h)
@@ -238,7 +253,7 @@ def block_tail_bwd(g, u, h, Wc, want_bias: bool):
     B, C = h.shape[:2]
     S = h[0, 0].numel()
     lib = _cabi.load()
-    with torch.cuda.device(h.device):
+    with _cabi.on_device(h.device):
         gu = torch.empty_like(h)
         t = torch.empty_like(h)
         dW = torch.empty((C, C), dtype=torch.float32, device=h.device)
@@ -269,7 +284,7 @@ def _run_stages(kind, plan, src, dst, BC, direction, precision, stages, a0=None,
                 rs_stride=0):
     lib = _cabi.load()
     precision = _cabi.resolve_precision(plan, precision)
-    nbytes = lib.pdephi_plan_workspace_bytes(plan, BC)
+    nbytes = _cabi.workspace_bytes(plan, BC)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
     if kind == "analysis":
         _cabi.check(lib.pdephi_analysis_stages(plan, _p(src), _p(dst), BC, direction, precision, stages, _p(ws), nbytes,
@@ -284,7 +299,7 @@ def analysis_zy(x: torch.Tensor, modes_h, direction: int, precision: int, nx_tot
     _require_cuda_f32(x, "x")
     x = x.contiguous()
     B, C = x.shape[:2]
-    with torch.cuda.device(x.device):
+    with _cabi.on_device(x.device):
         plan = _cabi.get_plan(x.device.index, tuple(x.shape[2:]), modes_h, (nx_total, 0))
         T = torch.empty((B, C, x.shape[2], modes_h[1], modes_h[2]), dtype=torch.complex64, device=x.device)
         _run_stages("analysis", plan, x, T, B * C, direction, precision, _cabi.STAGES_ZY)
@@ -295,7 +310,7 @@ def analysis_x(T: torch.Tensor, mx: int, grid, precision: int) -> torch.Tensor:
     """x stage of K1 on a ky subset: T [B,C,Nx,myl,mzh] complex64 (all x planes) -> X [B,C,mx,myl,mzh]."""
     T = T.contiguous()
     B, C, Nx, myl, mzh = T.shape
-    with torch.cuda.device(T.device):
+    with _cabi.on_device(T.device):
         plan = _cabi.get_plan(T.device.index, (Nx, grid[1], grid[2]), (mx, myl, mzh))
         X = torch.empty((B, C, mx, myl, mzh), dtype=torch.complex64, device=T.device)
         _run_stages("analysis", plan, T, X, B * C, _cabi.FORWARD, precision, _cabi.STAGES_X)
@@ -307,7 +322,7 @@ def synthesis_x(Z: torch.Tensor, grid, mode_scale, row_scale, precision: int) ->
     Z = Z.contiguous()
     B, C, mx, myl, mzh = Z.shape
     rs_stride = row_scale.stride(0) if row_scale is not None else 0
-    with torch.cuda.device(Z.device):
+    with _cabi.on_device(Z.device):
         plan = _cabi.get_plan(Z.device.index, tuple(grid), (mx, myl, mzh))
         T = torch.empty((B, C, grid[0], myl, mzh), dtype=torch.complex64, device=Z.device)
         _run_stages("synthesis", plan, Z, T, B * C, _cabi.FORWARD, precision, _cabi.STAGES_X, None, None, mode_scale, row_scale,
@@ -321,7 +336,7 @@ def synthesis_zy(T: torch.Tensor, mx: int, grid_local, addend0, addend1, directi
     B, C, Nxl, my, mzh = T.shape
     a0 = addend0.contiguous() if addend0 is not None else None
     a1 = addend1.contiguous() if addend1 is not None else None
-    with torch.cuda.device(T.device):
+    with _cabi.on_device(T.device):
         plan = _cabi.get_plan(T.device.index, tuple(grid_local), (mx, my, mzh), (nx_total, 0))
         out = torch.empty((B, C, *grid_local), dtype=torch.float32, device=T.device)
         _run_stages("synthesis", plan, T, out, B * C, direction, precision, _cabi.STAGES_ZY, a0, a1)
@@ -424,7 +439,7 @@ class _Slab:
         rows = Y.shape[0] * Y.shape[1]
         M = Y[0, 0].numel()
         lib = _cabi.load()
-        with torch.cuda.device(Y.device):
+        with _cabi.on_device(Y.device):
             G = torch.empty(rows, dtype=torch.float32, device=Y.device)
             dY = torch.empty_like(Y)
             _cabi.check(lib.pdephi_projection_bwd_sharded(_p(dZ), _p(Y), _p(mask), _p(stats), _p(G), _p(None), rows, M, 1,
@@ -495,7 +510,7 @@ def spectral_resample(x: torch.Tensor, modes_h: Tuple[int, int, int], grid: Tupl
     coarse half-spectrum), up-sampling (rfno.py:132-149: modes = the whole input half-spectrum) and the 2/3-rule
     de-aliasing of the rollout loop (rational_fourier.py:392-412: same grid, modes = the retained box), without
     materialising a full spectrum."""
-    return PrunedSynthesisFn.apply(PrunedAnalysisFn.apply(x, tuple(modes_h), precision), tuple(grid), precision)
+    return library_call(PrunedSynthesisFn, library_call(PrunedAnalysisFn, x, tuple(modes_h), precision), tuple(grid), precision)
 
 
 class RationalSpectralFn(torch.autograd.Function):
@@ -623,7 +638,7 @@ class PointwiseLinearFn(torch.autograd.Function):
         Cout = weight.shape[0]
         S = x[0, 0].numel()
         lib = _cabi.load()
-        with torch.cuda.device(x.device):
+        with _cabi.on_device(x.device):
             out = torch.empty((B, Cout, *x.shape[2:]), dtype=torch.float32, device=x.device)
             _cabi.check(lib.pdephi_pointwise_linear(_p(x), _p(weight), _p(bias), _p(out), B, Cin, Cout, S, 0, _stream()),
                         "pointwise_linear")
@@ -642,7 +657,7 @@ class PointwiseLinearFn(torch.autograd.Function):
         S = x[0, 0].numel()
         lib = _cabi.load()
         dx = dW = db = None
-        with torch.cuda.device(x.device):
+        with _cabi.on_device(x.device):
             if ctx.needs_input_grad[0]:
                 dx = torch.empty_like(x)
                 _cabi.check(lib.pdephi_pointwise_linear(_p(g), _p(weight), _p(None), _p(dx), B, Cout, Cin, S, 1, _stream()),

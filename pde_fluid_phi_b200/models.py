@@ -18,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _cabi
-from .functional import PointwiseLinearFn, pointwise_linear_supported, spectral_resample
+from .functional import PointwiseLinearFn, library_call, pointwise_linear_supported, spectral_resample
 from .operators import RationalFourierLayer, SpectralConv3D
 
 
@@ -66,7 +66,7 @@ def _lift(x: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
     if x.shape[1] != linear.in_features:
         raise RuntimeError(f"input has {x.shape[1]} channels, the model was built for {linear.in_features}")
     if pointwise_linear_supported(x, linear.weight):
-        return PointwiseLinearFn.apply(x, linear.weight, linear.bias)
+        return library_call(PointwiseLinearFn, x, linear.weight, linear.bias)
     return linear(x.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
 
 

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .functional import (ComplexBlockFn, ComplexSpectralFn, RationalBlockFn, RationalSpectralFn, block_tail_supported,
+from .functional import (ComplexBlockFn, ComplexSpectralFn, RationalBlockFn, RationalSpectralFn, block_tail_supported, library_call,
                          monomial_exponents, monomial_table)
 
 _default_precision = "auto"
@@ -158,7 +158,7 @@ class RationalFourierLayer(nn.Module):
         _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
         if self.in_channels != self.out_channels:
             raise RuntimeError("RationalFourierLayer needs in_channels == out_channels (as the reference does)")
-        return RationalSpectralFn.apply(x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
+        return library_call(RationalSpectralFn, x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
                                         self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
                                         self._precision_code(), skip0, residual, self.slab)
 
@@ -180,7 +180,7 @@ class RationalFourierLayer(nn.Module):
         (TF32 path, width 64): spectral layer, then the 1x1x1 convolution as a tcgen05 channel GEMM whose
         epilogue applies bias, both residual adds and the exact GELU."""
         _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
-        return RationalBlockFn.apply(x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
+        return library_call(RationalBlockFn, x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
                                      self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
                                      self._precision_code(), conv.weight, conv.bias, self.slab)
 
@@ -209,7 +209,7 @@ class SpectralConv3D(nn.Module):
         _check_input(x, self.in_channels, self.modes, "SpectralConv3D", self.slab)
         if residual and self.in_channels != self.out_channels:
             raise RuntimeError("fused residual needs in_channels == out_channels")
-        return ComplexSpectralFn.apply(x, self.weights, tuple(self.modes), self._precision_code(), skip0, residual,
+        return library_call(ComplexSpectralFn, x, self.weights, tuple(self.modes), self._precision_code(), skip0, residual,
                                        self.slab)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -227,5 +227,5 @@ class SpectralConv3D(nn.Module):
     def forward_block(self, x: torch.Tensor, conv: nn.Conv3d) -> torch.Tensor:
         """gelu(spectral_conv(x) + conv(x) + x): the whole block of models/fno3d.py:91-97 in the library."""
         _check_input(x, self.in_channels, self.modes, "SpectralConv3D", self.slab)
-        return ComplexBlockFn.apply(x, self.weights, tuple(self.modes), self._precision_code(), conv.weight, conv.bias,
+        return library_call(ComplexBlockFn, x, self.weights, tuple(self.modes), self._precision_code(), conv.weight, conv.bias,
                                     self.slab)

@@ -10,6 +10,8 @@ import pytest
 import torch
 
 import pde_fluid_phi_b200 as pb
+from pde_fluid_phi_b200 import _cabi
+from oracle import spectral_oracle as so
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -258,3 +260,55 @@ def test_rollout_vs_reference_golden():
     _strict_fp32(run)
     m = model.get_stability_monitor()
     assert set(m) == {"spectral_radius", "energy_drift", "realizability_violations", "passivity_violations"}
+
+
+# ------------------------------------------------------------------------------------------------
+# wrappers the reference puts around the operator: activation checkpointing
+# (optimization/memory_optimization.py:263-350) and torch.compile (optimization/performance_optimization.py:466-486)
+# ------------------------------------------------------------------------------------------------
+def _small_model():
+    torch.manual_seed(3)
+    m = pb.RationalFourierOperator3D(modes=(4, 4, 4), width=8, n_layers=2).to(DEV)
+    with torch.no_grad():
+        for layer in m.rational_layers:
+            q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+            layer.Q_coeffs.mul_(1e-3)
+            layer.Q_coeffs[..., 0, 0, 0] = q0
+    return m
+
+
+def test_activation_checkpointing_reexecutes_the_layers_identically():
+    from torch.utils.checkpoint import checkpoint
+    m = _small_model()
+    x = torch.randn(2, 3, 16, 16, 16, device=DEV, requires_grad=True)
+    out = m(x)
+    out.square().mean().backward()
+    ref = [p.grad.clone() for p in m.parameters()] + [x.grad.clone()]
+    m.zero_grad()
+    x.grad = None
+    out_c = checkpoint(m, x, use_reentrant=False)      # forward runs twice: must be deterministic and side-effect free
+    out_c.square().mean().backward()
+    got = [p.grad for p in m.parameters()] + [x.grad]
+    assert torch.equal(out_c, out)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+
+
+def test_torch_compile_wrapper_runs_the_library_path():
+    m = _small_model()
+    x = torch.randn(2, 3, 16, 16, 16, device=DEV)
+    want = m(x)
+    want.square().mean().backward()
+    ref = [p.grad.clone() for p in m.parameters()]
+    m.zero_grad()
+    cm = torch.compile(m)                               # the spectral layers are opaque to dynamo: graph breaks, same kernels
+    _cabi.profile(True, True)
+    got = cm(x)
+    got.square().mean().backward()
+    torch.cuda.synchronize()
+    launched = _cabi.profile_report(timed=False)
+    _cabi.profile(False, True)
+    assert launched, "compiled model did not call the library"
+    assert so.rel_l2(got.detach().cpu(), want.detach().cpu()) < 1e-6
+    for p, g in zip(m.parameters(), ref):
+        assert so.rel_l2(p.grad.cpu(), g.cpu()) < 1e-5
