@@ -436,6 +436,35 @@ def layer_times(dev, precision):
         torch.cuda.synchronize()
         return round(e0.elapsed_time(e1) / 10 * 1e3, 1)
 
+    def run_graph(layer, x):
+        """The same fwd+bwd captured once into a CUDA graph and replayed: what a launch-latency-bound shape costs without
+        the Python / ctypes host path (the library never synchronises or allocates outside torch's allocator)."""
+        g = torch.randn_like(x)
+
+        def step():
+            x.grad = None
+            layer.zero_grad(set_to_none=True)
+            layer(x).backward(g)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return round(e0.elapsed_time(e1) / 50 * 1e3, 1)
+
     out = {}
     torch.manual_seed(0)
     x2 = torch.randn(8, 64, 128, 128, 128, device=dev, requires_grad=True)
@@ -449,6 +478,9 @@ def layer_times(dev, precision):
     x1 = torch.randn(4, 32, 32, 32, 32, device=dev, requires_grad=True)
     out["SpectralConv3D [4,32,32^3] modes 8^3 (fp32, cfg 1)"] = run(pb.SpectralConv3D(32, 32, (8, 8, 8)).to(dev), x1)
     out["RationalFourierLayer [4,32,32^3] modes 8^3 (fp32, cfg-1 shape)"] = run(pb.RationalFourierLayer(32, 32, (8, 8, 8)).to(dev), x1)
+    out["SpectralConv3D [4,32,32^3] modes 8^3 (fp32, cfg 1, CUDA graph replay)"] = run_graph(pb.SpectralConv3D(32, 32, (8, 8, 8)).to(dev), x1)
+    out["RationalFourierLayer [4,32,32^3] modes 8^3 (fp32, cfg-1 shape, CUDA graph replay)"] = run_graph(
+        pb.RationalFourierLayer(32, 32, (8, 8, 8)).to(dev), x1)
     del x1
     if precision == "tf32":
         # shapes of configs 3-5: the per-axis tensor-core route (transforms_gen.cu)

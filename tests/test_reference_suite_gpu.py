@@ -312,3 +312,38 @@ def test_torch_compile_wrapper_runs_the_library_path():
     assert so.rel_l2(got.detach().cpu(), want.detach().cpu()) < 1e-6
     for p, g in zip(m.parameters(), ref):
         assert so.rel_l2(p.grad.cpu(), g.cpu()) < 1e-5
+
+
+def test_layer_forward_backward_is_cuda_graph_capturable():
+    """No host synchronisation, no allocation outside torch's allocator, tensor maps passed by value: a whole layer
+    forward + backward captures into one CUDA graph and replays to the same bits (the launch-latency-bound small shapes,
+    cfg 1, are where this matters; SURVEY.md section 8f N3 asks for a graph-capturable path)."""
+    torch.manual_seed(5)
+    layer = pb.SpectralConv3D(32, 32, (8, 8, 8)).to(DEV)
+    x = torch.randn(4, 32, 32, 32, 32, device=DEV, requires_grad=True)
+    g = torch.randn_like(x)
+
+    def step():
+        x.grad = None
+        layer.weights.grad = None
+        out = layer(x)
+        out.backward(g)
+        return out
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):                      # plans, kernels attributes and the allocator pool are warm before capture
+            want = step().detach().clone()
+            gx, gw = x.grad.clone(), layer.weights.grad.clone()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    x.grad = None
+    layer.weights.grad = None
+    with torch.cuda.graph(graph):
+        out = step()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    assert torch.equal(x.grad, gx) and torch.equal(layer.weights.grad, gw)
