@@ -235,9 +235,12 @@ def run_native(args):
     state = {"n": 0}
     params = [p for p in model.parameters()]
 
-    def step(xd, yd):
+    def step(xd, yd, before_loss=None):
         opt.zero_grad(set_to_none=True)
-        loss = torch.nn.functional.mse_loss(model(xd), yd)
+        pred = model(xd)
+        if before_loss is not None:
+            before_loss()                                    # e2e leg: the target's copy has to have landed by now
+        loss = torch.nn.functional.mse_loss(pred, yd)
         loss.backward()
         if world > 1:
             allreduce_gradients(params, world)
@@ -250,11 +253,12 @@ def run_native(args):
 
     # End-to-end leg: every step copies its own inputs from pinned host memory (2 x 201 MB) and reads the loss back.
     # The copies run on a side stream into the buffer pair the *next* step will use, as a prefetching data loader
-    # does, so they overlap the current step's kernels; the first step's copy is not overlapped and is inside the
-    # timed region like all the others.
+    # does, so they overlap the current step's kernels; the first step's input copy is not overlapped (its target
+    # copy runs behind the forward pass, which only needs the inputs) and is inside the timed region like all the others.
     copy_stream = torch.cuda.Stream(device=dev)
     dbuf = [(torch.empty_like(x), torch.empty_like(y)) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]           # inputs of the slot have landed
+    ready_y = [torch.cuda.Event() for _ in range(2)]         # ... and its targets (needed only at the loss)
     consumed = [torch.cuda.Event() for _ in range(2)]
     e2e_state = {"i": 0, "primed": False}
 
@@ -262,8 +266,9 @@ def run_native(args):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])           # the step that last read this pair has finished with it
             dbuf[slot][0].copy_(hx, non_blocking=True)
-            dbuf[slot][1].copy_(hy, non_blocking=True)
             ready[slot].record(copy_stream)
+            dbuf[slot][1].copy_(hy, non_blocking=True)       # overlaps the forward pass even when nothing was prefetched
+            ready_y[slot].record(copy_stream)
 
     def step_e2e():
         i = e2e_state["i"]
@@ -272,7 +277,8 @@ def run_native(args):
             e2e_state["primed"] = True
         _prefetch((i + 1) & 1)                               # next step's inputs, overlapped with this step
         torch.cuda.current_stream().wait_event(ready[i & 1])
-        loss = step(dbuf[i & 1][0], dbuf[i & 1][1])
+        loss = step(dbuf[i & 1][0], dbuf[i & 1][1],
+                    before_loss=lambda: torch.cuda.current_stream().wait_event(ready_y[i & 1]))
         consumed[i & 1].record(torch.cuda.current_stream())
         h_loss.copy_(loss.detach(), non_blocking=True)
         e2e_state["i"] = i + 1
