@@ -179,6 +179,40 @@ def test_transforms_vs_fp64_spec(grid, modes, precision):
     assert rel(got.double(), want) < tol
 
 
+def test_per_axis_route_random_shapes():
+    """Seeded sweep of the per-axis tensor-core route (transforms_gen.cu) over grids / modes / batch sizes it accepts --
+    partial row tiles, padded rows, 2-D grids, axes below one tile -- against the FFMA route: 2e-3 on every transform."""
+    import random
+    rnd = random.Random(7)
+    lib = pb.load_library()
+    axes = [32, 64, 96, 128, 160, 192, 256]
+    done = 0
+    while done < 16:
+        two_d = rnd.random() < 0.25
+        Nx, Ny = rnd.choice(axes), rnd.choice(axes)
+        Nz = 1 if two_d else rnd.choice([32, 64, 96, 128, 256])
+        if Nx * Ny * Nz > 192 * 192 * 128:
+            continue
+        mh = (rnd.randint(1, min(64, Nx)), rnd.randint(1, min(64, Ny)), 1 if two_d else rnd.randint(1, min(40, Nz // 2 + 1)))
+        grid = (Nx, Ny, Nz)
+        plan = _cabi.get_plan(torch.cuda.current_device(), grid, mh)
+        if not lib.pdephi_plan_supports(plan, _cabi.PREC_TF32):
+            continue
+        B, C = rnd.randint(1, 2), rnd.randint(1, 3)
+        torch.manual_seed(rnd.randint(0, 1 << 30))
+        x = torch.randn(B, C, *grid, device=DEV)
+        Z = torch.randn(B, C, *mh, device=DEV, dtype=torch.complex64)
+        a0 = torch.randn(B, C, *grid, device=DEV)
+        ms = torch.rand(mh, device=DEV).reshape(-1) + 0.5
+        rs = torch.rand(B * C, 4, device=DEV) + 0.5
+        for d in (_cabi.FORWARD, _cabi.ADJOINT):
+            assert rel(pf.analysis(x, mh, d, _cabi.PREC_TF32), pf.analysis(x, mh, d, _cabi.PREC_FP32)) < TOL["tf32"], (grid, mh, d)
+            want = pf.synthesis(Z, grid, ms, rs[:, 2], a0, None, d, _cabi.PREC_FP32) - a0
+            got = pf.synthesis(Z, grid, ms, rs[:, 2], a0, None, d, _cabi.PREC_TF32) - a0
+            assert rel(got, want) < TOL["tf32"], (grid, mh, d)
+        done += 1
+
+
 def test_adjointness_at_cfg2_plane_shape():
     """<A x, Z> == <x, A^H Z> on a 128^3 grid with 32^3 modes (size-independent property, full plane size)."""
     torch.manual_seed(0)
