@@ -195,6 +195,24 @@ int pdephi_block_spectral_fwd(pdephi_plan_t plan, const float* Y, const float* m
                               long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u,
                               float* hout, int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
 
+/* ---- the LAST block of a model together with the output projection (nn.Linear 64 -> n_out <= 4) --------------
+ * replaces rational_fourier.py:274-276 / fno3d.py:100-102 on top of the block above.
+ *   forward : additionally out[b,n,s] = bp[n] + sum_c Wp[n,c] hout[b,c,s], computed in the block-tail epilogue (the separate
+ *             projection pass and its read of hout disappear; hout is still written for the projection's weight gradient)
+ *   backward: the block's incoming gradient g' = Wp^T gout is generated inside pdephi_block_tail_proj_bwd from
+ *             gout [B,n_out,S] instead of being written by one kernel and read by the next.
+ * Wp [n_out,64] row-major, bp [n_out] or NULL. */
+int pdephi_block_tail_proj_fwd(const float* h, const float* spec, const float* Wc, const float* bc, float* u, float* hout,
+                               const float* Wp, const float* bp, int n_out, float* out, int B, int C, long long S,
+                               pdephi_stream_t stream);
+int pdephi_block_spectral_proj_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                                   long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u,
+                                   float* hout, const float* Wp, const float* bp, int n_out, float* out, int B, int C,
+                                   void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+int pdephi_block_tail_proj_bwd(const float* gout, const float* Wp, int n_out, const float* u, const float* h, const float* Wc,
+                               float* gu, float* t, float* dWc, float* dbc, int B, int C, long long S, void* workspace,
+                               size_t workspace_bytes, pdephi_stream_t stream);
+
 /* ---- per-kernel launch counters and CUDA-event timing (measurement support for bench.py) ------
  * Launches are always counted.  With timing enabled every kernel launch is bracketed by a pair of
  * cudaEvents on the launching stream; pdephi_profile_query synchronises on them and returns the

@@ -62,6 +62,13 @@ SIGNATURES = {
     "pdephi_block_spectral_fwd_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "pdephi_block_spectral_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pdephi_block_tail_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                           c_void_p, c_int, c_int, c_longlong, c_void_p]),
+    "pdephi_block_spectral_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
+                                               c_size_t, c_void_p]),
+    "pdephi_block_tail_proj_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_int, c_int, c_longlong, c_void_p, c_size_t, c_void_p]),
     "pdephi_profile_enable": (c_int, [c_int]),
     "pdephi_profile_reset": (c_int, []),
     "pdephi_profile_num_kernels": (c_int, []),

@@ -136,13 +136,19 @@ constexpr int F_STAGES = 3;
 // V = (x,y)-synthesised modes, [64 channel rows][ldz <= 64 floats] (columns 2k = re, 2k+1 = im of kz = k), and the z stage
 // of the synthesis runs as extra MMAs into the same accumulator:  D[128 z x 64 ch] += Bz[128 z x K] . Vtile[64 ch x K]^T.
 // A tile is then one z line of the grid (Nz = 128), and V is laid out [tile][channel][ldz] so its rows are contiguous.
-struct FSmem { uint32_t stage[F_STAGES], w, bz, bias, bars, tmem_slot, total; };
-__host__ __device__ inline FSmem fwd_smem(bool fused) {
+// PROJ: the model's output projection (nn.Linear 64 -> n_out <= 4, rational_fourier.py:274-276) of the LAST block rides in
+// the epilogue: every thread reduces its 16 channels, the four channel groups meet through shared memory.  The separate
+// projection kernel and its 4.3 GB read of h' disappear (h' is still written: the projection's weight gradient reads it).
+constexpr int MAXP = 4;
+struct FSmem { uint32_t stage[F_STAGES], w, bz, bias, wp, red, bars, tmem_slot, total; };
+__host__ __device__ inline FSmem fwd_smem(bool fused, bool proj = false) {
   FSmem s; uint32_t o = 0;
   for (int i = 0; i < F_STAGES; ++i) { s.stage[i] = o; o += fused ? TILE + 2 * BOX : 2 * TILE; }
   s.w = o; o += 2 * BOX;
   s.bz = o; o += fused ? 2 * TS * 128 : 0;
   s.bias = o; o += 256;
+  s.wp = o; o += proj ? C * 16 + 16 : 0;                   // [64] float4 (w_0..w_3 of channel c) + bias float4
+  s.red = o; o += proj ? 2 * 4 * MAXP * TS * 4 : 0;        // [tile parity][channel group][output][point]
   s.bars = o; o += 128;
   s.tmem_slot = o; o += 64;
   s.total = o;
@@ -150,22 +156,30 @@ __host__ __device__ inline FSmem fwd_smem(bool fused) {
 }
 enum { FB_FULL = 0, FB_EMPTY = F_STAGES, FB_DFULL = 2 * F_STAGES, FB_DEMPTY = 2 * F_STAGES + 2 };
 
-template <bool FUSED>
+template <bool FUSED, bool PROJ>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ spec_in, const float* __restrict__ Wc,
                       const float* __restrict__ bc, float* __restrict__ u_out, float* __restrict__ h_out,
                       long long tiles_per_batch, long long ntiles, long long S, const float* __restrict__ bzimg, int ldz,
-                      int contiguous) {
+                      int contiguous, const float* __restrict__ Wp, const float* __restrict__ bp, float* __restrict__ proj_out,
+                      int NP) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const FSmem L = fwd_smem(FUSED);
+  const FSmem L = fwd_smem(FUSED, PROJ);
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // the truncation bias of the data operands (h; V) is undone on the accumulator in the epilogue, not in the weights
   build_w_image(sm + L.w, Wc, false, threadIdx.x, THREADS, 1.0f);
+  if (PROJ) {
+    float* wp = reinterpret_cast<float*>(sm + L.wp);
+    for (int i = threadIdx.x; i < C * MAXP + MAXP; i += THREADS) {
+      const int c = i >> 2, n = i & 3;
+      wp[i] = (n < NP) ? (c < C ? __ldg(Wp + n * C + c) : (bp ? __ldg(bp + n) : 0.f)) : 0.f;
+    }
+  }
   if (FUSED) {
     const float4* s1 = reinterpret_cast<const float4*>(bzimg);
     float4* d1 = reinterpret_cast<float4*>(sm + L.bz);
@@ -295,13 +309,38 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
       const size_t g0 = ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
       float* up = u_out + g0;
       float* hp = h_out + g0;
+      float pj[MAXP] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < CPW; ++j) {
         const float u = fmaf(v[j], TF32_COMP, bsr[j]) + pre[j];
         __stcs(up, u);
-        *hp = gelu_f(u);
+        const float hv = gelu_f(u);
+        *hp = hv;
+        if (PROJ) {
+          const float4 w = reinterpret_cast<const float4*>(sm + L.wp)[part * CPW + j];
+          pj[0] = fmaf(w.x, hv, pj[0]); pj[1] = fmaf(w.y, hv, pj[1]);
+          pj[2] = fmaf(w.z, hv, pj[2]); pj[3] = fmaf(w.w, hv, pj[3]);
+        }
         up += S;
         hp += S;
+      }
+      if (PROJ) {
+        // two buffers by tile parity and one barrier per tile: a buffer is rewritten two tiles later, after every warp has
+        // passed the next tile's barrier, i.e. after its readers are done
+        float* red = reinterpret_cast<float*>(sm + L.red) + (it & 1) * (4 * MAXP * TS);
+        const int pt = 32 * q + lane;
+#pragma unroll
+        for (int n = 0; n < MAXP; ++n) red[(part * MAXP + n) * TS + pt] = pj[n];
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        if (part == 0) {
+          const float4 bias4 = reinterpret_cast<const float4*>(sm + L.wp)[C];
+          const float bb[MAXP] = {bias4.x, bias4.y, bias4.z, bias4.w};
+#pragma unroll
+          for (int n = 0; n < MAXP; ++n)
+            if (n < NP)
+              proj_out[((size_t)b * NP + n) * S + s0 + pt] =
+                  bb[n] + ((red[n * TS + pt] + red[(MAXP + n) * TS + pt]) + (red[(2 * MAXP + n) * TS + pt] + red[(3 * MAXP + n) * TS + pt]));
+        }
       }
     }
   }
@@ -315,12 +354,13 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
 //   warp 0: MMA issuer + TMEM owner, warps 1..4: loaders, warps 5..20: compute / epilogue
 // ------------------------------------------------------------------------------------------------
 constexpr int B_STAGES = 2;
-struct BSmem { uint32_t stage[B_STAGES], wt, red, bars, tmem_slot, total; };
+struct BSmem { uint32_t stage[B_STAGES], wt, red, wp, bars, tmem_slot, total; };
 __host__ __device__ inline BSmem bwd_smem() {
   BSmem s; uint32_t o = 0;
   for (int i = 0; i < B_STAGES; ++i) { s.stage[i] = o; o += 3 * TILE; }   // g' (-> gu, MN layout), h (K layout), u (-> gu, K layout)
   s.wt = o; o += 2 * BOX;
   s.red = o; o += 4 * C * 4;
+  s.wp = o; o += C * 16;                                                   // GENG: [64] float4 columns of the projection weight
   s.bars = o; o += 128;
   s.tmem_slot = o; o += 64;
   s.total = o;
@@ -331,10 +371,14 @@ __host__ __device__ inline BSmem bwd_smem() {
 enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2 * B_STAGES + 2, BB_TEMPTY = 2 * B_STAGES + 4,
        BB_DWDONE = 2 * B_STAGES + 6 };
 
+// GENG: the incoming gradient g' = Wp^T gout of the LAST block (the output projection's input gradient) is generated by the
+// loader warps from gout [B, n_out <= 4, S] instead of being read: the 4.3 GB g' is neither written nor read.
+template <bool GENG>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
                       const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
-                      float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S, int contiguous) {
+                      float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S, int contiguous,
+                      const float* __restrict__ Wp, int NP) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -344,6 +388,10 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   build_w_image(sm + L.wt, Wc, true, threadIdx.x, THREADS, TF32_COMP);      // rows c, K = o : (Wc^T)
+  if (GENG) {
+    float* wp = reinterpret_cast<float*>(sm + L.wp);
+    for (int i = threadIdx.x; i < C * MAXP; i += THREADS) wp[i] = ((i & 3) < NP) ? __ldg(Wp + (i & 3) * C + (i >> 2)) : 0.f;
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), LD_THREADS); mbar_init(bar(BB_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
@@ -378,9 +426,31 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       const int s = (int)(it % B_STAGES);
       mbar_wait(bar(BB_EMPTY + s), (uint32_t)(((it / B_STAGES) & 1) ^ 1));
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
-      stage_rows<false>(base + L.stage[s], g_in, b, s0, S, lw, lane);
+      float4 gv[MAXP];
+      if (GENG) {        // g_in = gout: this lane's four points of every output channel, issued ahead of the bulk copies
+#pragma unroll
+        for (int n = 0; n < MAXP; ++n)
+          gv[n] = (n < NP) ? __ldg(reinterpret_cast<const float4*>(g_in + ((size_t)b * NP + n) * S + s0) + lane)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        stage_rows<false>(base + L.stage[s], g_in, b, s0, S, lw, lane);
+      }
       stage_rows<true>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
       stage_rows<true>(base + L.stage[s] + 2 * TILE, u_in, b, s0, S, lw, lane);
+      if (GENG) {
+        uint8_t* dst = sm + L.stage[s];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int r = lw * 16 + i;
+          const float4 w = reinterpret_cast<const float4*>(sm + L.wp)[r];
+          float4 o;
+          o.x = fmaf(w.w, gv[3].x, fmaf(w.z, gv[2].x, fmaf(w.y, gv[1].x, w.x * gv[0].x)));
+          o.y = fmaf(w.w, gv[3].y, fmaf(w.z, gv[2].y, fmaf(w.y, gv[1].y, w.x * gv[0].y)));
+          o.z = fmaf(w.w, gv[3].z, fmaf(w.z, gv[2].z, fmaf(w.y, gv[1].z, w.x * gv[0].z)));
+          o.w = fmaf(w.w, gv[3].w, fmaf(w.z, gv[2].w, fmaf(w.y, gv[1].w, w.x * gv[0].w)));
+          *reinterpret_cast<float4*>(dst + chunk_off_mn(r, lane)) = o;
+        }
+      }
     };
     for (int pre = 0; pre < B_STAGES - 1; ++pre) {
       if (pre < my_tiles) issue(pre);
@@ -549,49 +619,107 @@ static int num_sms() {
 
 using namespace pdephi;
 
-extern "C" int pdephi_block_tail_fwd(const float* h, const float* spec, const float* Wc, const float* bc, float* u,
-                                     float* hout, int B, int Cc, long long S, pdephi_stream_t stream) {
-  PDEPHI_REQUIRE(h && spec && Wc && u && hout, "block_tail_fwd: null pointer");
-  int rc = check_shape(B, Cc, S, "block_tail_fwd");
-  if (rc) return rc;
+namespace pdephi {
+struct ProjArgs { const float* Wp; const float* bp; float* out; int n; };   // output projection fused into the last block
+
+static int check_proj(const ProjArgs& pr, const char* who) {
+  if (!pr.Wp) return PDEPHI_OK;
+  PDEPHI_REQUIRE(pr.out != nullptr, "%s: projection output is null", who);
+  if (pr.n < 1 || pr.n > blk::MAXP) return fail(PDEPHI_ERR_UNSUPPORTED, "%s: the fused projection takes 1..%d outputs, got %d", who, blk::MAXP, pr.n);
+  return PDEPHI_OK;
+}
+
+static int block_tail_fwd_launch(const float* h, const float* spec, const float* Wc, const float* bc, float* u, float* hout,
+                                 int B, long long S, const ProjArgs& pr, cudaStream_t st) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(h) || !al16(spec)) return fail(PDEPHI_ERR_INVALID, "block_tail_fwd: h and spec must be 16-byte aligned");
+  int rc = check_proj(pr, "block_tail_fwd");
+  if (rc) return rc;
   const long long tpb = S / blk::TS, ntiles = tpb * B;
-  const size_t smem = blk::fwd_smem(false).total + 1024;
-  auto k = blk::block_tail_fwd_kernel<false>;
-  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool proj = pr.Wp != nullptr;
+  const size_t smem = blk::fwd_smem(false, proj).total + 1024;
   const int sms = num_sms();
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  cudaStream_t st = (cudaStream_t)stream;
-  {
-    ProfScope ps(K_BLOCK_TAIL_FWD, st);
-    k<<<grid, blk::THREADS, smem, st>>>(h, spec, Wc, bc, u, hout, tpb, ntiles, S, nullptr, 0, tile_order());
+  ProfScope ps(K_BLOCK_TAIL_FWD, st);
+  if (proj) {
+    auto k = blk::block_tail_fwd_kernel<false, true>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, blk::THREADS, smem, st>>>(h, spec, Wc, bc, u, hout, tpb, ntiles, S, nullptr, 0, tile_order(), pr.Wp, pr.bp, pr.out, pr.n);
+  } else {
+    auto k = blk::block_tail_fwd_kernel<false, false>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, blk::THREADS, smem, st>>>(h, spec, Wc, bc, u, hout, tpb, ntiles, S, nullptr, 0, tile_order(), nullptr, nullptr, nullptr, 0);
   }
   PDEPHI_LAUNCH_CHECK("block_tail_fwd_kernel");
   return PDEPHI_OK;
 }
 
-namespace pdephi {
 // Block tail with the z stage of the synthesis fused in (transforms_gen.cu: pdephi_block_spectral_fwd).
 // V [B*S/128 tiles][64][ldz] float, bzimg = the plan's z-synthesis operand image for Nz = 128.
 int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const float* bzimg, const float* Wc, const float* bc,
-                                float* u, float* hout, int B, long long S, cudaStream_t st) {
+                                float* u, float* hout, int B, long long S, const float* Wp, const float* bp, float* proj_out,
+                                int n_out, cudaStream_t st) {
   int rc = check_shape(B, blk::C, S, "block_spectral_fwd");
   if (rc) return rc;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(h) || !al16(V)) return fail(PDEPHI_ERR_INVALID, "block_spectral_fwd: h and the workspace must be 16-byte aligned");
   if (ldz % 4 != 0 || ldz > 64) return fail(PDEPHI_ERR_UNSUPPORTED, "block_spectral_fwd: ldz %d", ldz);
+  const ProjArgs pr{Wp, bp, proj_out, n_out};
+  rc = check_proj(pr, "block_spectral_fwd");
+  if (rc) return rc;
   const long long tpb = S / blk::TS, ntiles = tpb * B;
-  const size_t smem = blk::fwd_smem(true).total + 1024;
-  auto k = blk::block_tail_fwd_kernel<true>;
-  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool proj = Wp != nullptr;
+  const size_t smem = blk::fwd_smem(true, proj).total + 1024;
   const int sms = num_sms();
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  {
-    ProfScope ps(K_BLOCK_SPECTRAL_FWD, st);
-    k<<<grid, blk::THREADS, smem, st>>>(h, V, Wc, bc, u, hout, tpb, ntiles, S, bzimg, ldz, tile_order());
+  ProfScope ps(K_BLOCK_SPECTRAL_FWD, st);
+  if (proj) {
+    auto k = blk::block_tail_fwd_kernel<true, true>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, blk::THREADS, smem, st>>>(h, V, Wc, bc, u, hout, tpb, ntiles, S, bzimg, ldz, tile_order(), Wp, bp, proj_out, n_out);
+  } else {
+    auto k = blk::block_tail_fwd_kernel<true, false>;
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, blk::THREADS, smem, st>>>(h, V, Wc, bc, u, hout, tpb, ntiles, S, bzimg, ldz, tile_order(), nullptr, nullptr, nullptr, 0);
   }
   PDEPHI_LAUNCH_CHECK("block_tail_fwd_kernel<fused>");
+  return PDEPHI_OK;
+}
+
+static int block_tail_bwd_launch(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t, float* dWc,
+                                 float* dbc, int B, int Cc, long long S, void* workspace, size_t workspace_bytes,
+                                 const float* Wp, int n_out, cudaStream_t st) {
+  int rc = check_shape(B, Cc, S, "block_tail_bwd");
+  if (rc) return rc;
+  const size_t need = pdephi_block_tail_bwd_workspace_bytes(Cc);
+  if (!workspace || workspace_bytes < need) return fail(PDEPHI_ERR_WORKSPACE, "block_tail_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(g) || !al16(h) || !al16(u)) return fail(PDEPHI_ERR_INVALID, "block_tail_bwd: g, h and u must be 16-byte aligned");
+  if (Wp && (n_out < 1 || n_out > blk::MAXP))
+    return fail(PDEPHI_ERR_UNSUPPORTED, "block_tail_bwd: the fused projection takes 1..%d outputs, got %d", blk::MAXP, n_out);
+  const long long tpb = S / blk::TS, ntiles = tpb * B;
+  const size_t smem = blk::bwd_smem().total + 1024;
+  int sms = num_sms();
+  if (sms > 1024) sms = 1024;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  {
+    ProfScope ps(K_BLOCK_TAIL_BWD, st);
+    if (Wp) {
+      auto k = blk::block_tail_bwd_kernel<true>;
+      PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out);
+    } else {
+      auto k = blk::block_tail_bwd_kernel<false>;
+      PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), nullptr, 0);
+    }
+  }
+  PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
+  {
+    ProfScope ps(K_BLOCK_TAIL_BWD, st);
+    blk::block_tail_reduce_kernel<<<(blk::C * blk::C + blk::C + 127) / 128, 128, 0, st>>>((const float*)workspace, dWc, dbc, grid);
+  }
+  PDEPHI_LAUNCH_CHECK("block_tail_reduce_kernel");
   return PDEPHI_OK;
 }
 }  // namespace pdephi
@@ -601,33 +729,33 @@ extern "C" size_t pdephi_block_tail_bwd_workspace_bytes(int Cc) {
   return align_up((size_t)1024 * (blk::C * blk::C + blk::C) * sizeof(float), 256);   // up to 1024 CTAs of partials
 }
 
+extern "C" int pdephi_block_tail_fwd(const float* h, const float* spec, const float* Wc, const float* bc, float* u,
+                                     float* hout, int B, int Cc, long long S, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(h && spec && Wc && u && hout, "block_tail_fwd: null pointer");
+  int rc = check_shape(B, Cc, S, "block_tail_fwd");
+  if (rc) return rc;
+  return block_tail_fwd_launch(h, spec, Wc, bc, u, hout, B, S, ProjArgs{nullptr, nullptr, nullptr, 0}, (cudaStream_t)stream);
+}
+
+extern "C" int pdephi_block_tail_proj_fwd(const float* h, const float* spec, const float* Wc, const float* bc, float* u,
+                                          float* hout, const float* Wp, const float* bp, int n_out, float* out, int B, int Cc,
+                                          long long S, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(h && spec && Wc && u && hout && Wp && out, "block_tail_proj_fwd: null pointer");
+  int rc = check_shape(B, Cc, S, "block_tail_proj_fwd");
+  if (rc) return rc;
+  return block_tail_fwd_launch(h, spec, Wc, bc, u, hout, B, S, ProjArgs{Wp, bp, out, n_out}, (cudaStream_t)stream);
+}
+
 extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t,
                                      float* dWc, float* dbc, int B, int Cc, long long S, void* workspace,
                                      size_t workspace_bytes, pdephi_stream_t stream) {
   PDEPHI_REQUIRE(g && u && h && Wc && gu && t && dWc, "block_tail_bwd: null pointer");
-  int rc = check_shape(B, Cc, S, "block_tail_bwd");
-  if (rc) return rc;
-  const size_t need = pdephi_block_tail_bwd_workspace_bytes(Cc);
-  if (!workspace || workspace_bytes < need) return fail(PDEPHI_ERR_WORKSPACE, "block_tail_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (!al16(g) || !al16(h) || !al16(u)) return fail(PDEPHI_ERR_INVALID, "block_tail_bwd: g, h and u must be 16-byte aligned");
-  const long long tpb = S / blk::TS, ntiles = tpb * B;
-  const size_t smem = blk::bwd_smem().total + 1024;
-  auto k = blk::block_tail_bwd_kernel;
-  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int sms = num_sms();
-  if (sms > 1024) sms = 1024;
-  const int grid = (int)(ntiles < sms ? ntiles : sms);
-  cudaStream_t st = (cudaStream_t)stream;
-  {
-    ProfScope ps(K_BLOCK_TAIL_BWD, st);
-    k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order());
-  }
-  PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
-  {
-    ProfScope ps(K_BLOCK_TAIL_BWD, st);
-    blk::block_tail_reduce_kernel<<<(blk::C * blk::C + blk::C + 127) / 128, 128, 0, st>>>((const float*)workspace, dWc, dbc, grid);
-  }
-  PDEPHI_LAUNCH_CHECK("block_tail_reduce_kernel");
-  return PDEPHI_OK;
+  return block_tail_bwd_launch(g, u, h, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int pdephi_block_tail_proj_bwd(const float* gout, const float* Wp, int n_out, const float* u, const float* h,
+                                          const float* Wc, float* gu, float* t, float* dWc, float* dbc, int B, int Cc, long long S,
+                                          void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(gout && Wp && u && h && Wc && gu && t && dWc, "block_tail_proj_bwd: null pointer");
+  return block_tail_bwd_launch(gout, u, h, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, Wp, n_out, (cudaStream_t)stream);
 }

@@ -967,7 +967,8 @@ int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0,
 }
 
 int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const float* bzimg, const float* Wc, const float* bc,
-                                float* u, float* hout, int B, long long S, cudaStream_t st);
+                                float* u, float* hout, int B, long long S, const float* Wp, const float* bp, float* proj_out,
+                                int n_out, cudaStream_t st);
 
 // The fused block forward is available when the per-axis kernels cover the shape and a 128-point tile of the block
 // tail is exactly one z line.
@@ -990,10 +991,32 @@ extern "C" size_t pdephi_block_spectral_fwd_workspace_bytes(pdephi_plan_t plan, 
   return gen_workspace_bytes(p, (long long)B * C);
 }
 
+static int block_spectral_run(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                              long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u, float* hout,
+                              const float* Wp, const float* bp, int n_out, float* proj_out, int B, int C, void* workspace,
+                              size_t workspace_bytes, pdephi_stream_t stream);
+
 extern "C" int pdephi_block_spectral_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
                                          long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u,
                                          float* hout, int B, int C, void* workspace, size_t workspace_bytes,
                                          pdephi_stream_t stream) {
+  return block_spectral_run(plan, Y, mode_scale, row_scale, row_scale_stride, h, Wc, bc, u, hout, nullptr, nullptr, 0, nullptr, B, C,
+                            workspace, workspace_bytes, stream);
+}
+
+extern "C" int pdephi_block_spectral_proj_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                                              long long row_scale_stride, const float* h, const float* Wc, const float* bc,
+                                              float* u, float* hout, const float* Wp, const float* bp, int n_out, float* out,
+                                              int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(Wp && out, "block_spectral_proj_fwd: null pointer");
+  return block_spectral_run(plan, Y, mode_scale, row_scale, row_scale_stride, h, Wc, bc, u, hout, Wp, bp, n_out, out, B, C,
+                            workspace, workspace_bytes, stream);
+}
+
+static int block_spectral_run(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                              long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u, float* hout,
+                              const float* Wp, const float* bp, int n_out, float* proj_out, int B, int C, void* workspace,
+                              size_t workspace_bytes, pdephi_stream_t stream) {
   const Plan* p = (const Plan*)plan;
   PDEPHI_REQUIRE(p && Y && h && Wc && u && hout, "block_spectral_fwd: null pointer");
   if (!block_spectral_ok(p, C))
@@ -1027,5 +1050,6 @@ extern "C" int pdephi_block_spectral_fwd(pdephi_plan_t plan, const float* Y, con
   rc = launch_axis_synthesis(p, W2, (long long)B * p->Nx, p->Ny, p->my, g.mky, C * g.ldz, V, g.ysc, g.yss, g.ys_st,
                              K_GEN_AXIS_SYNTHESIS, st);
   if (rc) return rc;
-  return block_tail_fwd_fused_launch(h, V, g.ldz, g.zs[PDEPHI_FORWARD], Wc, bc, u, hout, B, (long long)p->Nx * p->Ny * p->Nz, st);
+  return block_tail_fwd_fused_launch(h, V, g.ldz, g.zs[PDEPHI_FORWARD], Wc, bc, u, hout, B, (long long)p->Nx * p->Ny * p->Nz, Wp, bp,
+                                     proj_out, n_out, st);
 }

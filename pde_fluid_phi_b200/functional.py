@@ -208,17 +208,30 @@ def complex_mix_bwd(X, W, dY, mzh: int):
     return dX, dW
 
 
-def block_tail_fwd(h, spec, Wc, bc):
-    """u = spec + (Wc h + bc) + h, hout = gelu(u) on [B,64,...] tensors (tcgen05 TF32 channel GEMM, fused epilogue)."""
+def head_supported(linear) -> bool:
+    """The output projection the last block can carry in its epilogue: nn.Linear(64 -> at most 4 outputs), fp32 on CUDA."""
+    return (isinstance(linear, torch.nn.Linear) and linear.in_features == 64 and 1 <= linear.out_features <= 4
+            and linear.weight.is_cuda and linear.weight.dtype == torch.float32)
+
+
+def block_tail_fwd(h, spec, Wc, bc, head=None):
+    """u = spec + (Wc h + bc) + h, hout = gelu(u) on [B,64,...] tensors (tcgen05 TF32 channel GEMM, fused epilogue).
+    head = (Wp [n,64], bp [n] | None): additionally returns out = Wp hout + bp, computed in the same epilogue."""
     B, C = h.shape[:2]
     S = h[0, 0].numel()
     lib = _cabi.load()
     with _cabi.on_device(h.device):
         u = torch.empty_like(h)
         hout = torch.empty_like(h)
-        _cabi.check(lib.pdephi_block_tail_fwd(_p(h), _p(spec), _p(Wc), _p(bc), _p(u), _p(hout), B, C, S, _stream()),
-                    "block_tail_fwd")
-    return u, hout
+        if head is None:
+            _cabi.check(lib.pdephi_block_tail_fwd(_p(h), _p(spec), _p(Wc), _p(bc), _p(u), _p(hout), B, C, S, _stream()),
+                        "block_tail_fwd")
+            return u, hout
+        Wp, bp = head
+        out = torch.empty((B, Wp.shape[0], *h.shape[2:]), dtype=torch.float32, device=h.device)
+        _cabi.check(lib.pdephi_block_tail_proj_fwd(_p(h), _p(spec), _p(Wc), _p(bc), _p(u), _p(hout), _p(Wp), _p(bp), Wp.shape[0],
+                                                   _p(out), B, C, S, _stream()), "block_tail_proj_fwd")
+    return u, hout, out
 
 
 def block_spectral_supported(h: torch.Tensor, modes_h, precision: int) -> bool:
@@ -231,9 +244,9 @@ def block_spectral_supported(h: torch.Tensor, modes_h, precision: int) -> bool:
         return bool(_cabi.load().pdephi_block_spectral_supported(plan, 64))
 
 
-def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc):
+def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None):
     """u = S(Y * mode_scale * row_scale) + (Wc h + bc) + h, hout = gelu(u): x / y stages of the synthesis as per-axis
-    tensor-core contractions, z stage inside the block-tail kernel."""
+    tensor-core contractions, z stage inside the block-tail kernel.  head: see block_tail_fwd."""
     B, C = h.shape[:2]
     lib = _cabi.load()
     rs_stride = row_scale.stride(0) if row_scale is not None else 0
@@ -243,13 +256,22 @@ def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc):
         hout = torch.empty_like(h)
         nbytes = lib.pdephi_block_spectral_fwd_workspace_bytes(plan, B, C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
-        _cabi.check(lib.pdephi_block_spectral_fwd(plan, _p(Y), _p(mode_scale), _p(row_scale), rs_stride, _p(h), _p(Wc), _p(bc),
-                                                  _p(u), _p(hout), B, C, _p(ws), nbytes, _stream()), "block_spectral_fwd")
-    return u, hout
+        if head is None:
+            _cabi.check(lib.pdephi_block_spectral_fwd(plan, _p(Y), _p(mode_scale), _p(row_scale), rs_stride, _p(h), _p(Wc), _p(bc),
+                                                      _p(u), _p(hout), B, C, _p(ws), nbytes, _stream()), "block_spectral_fwd")
+            return u, hout
+        Wp, bp = head
+        out = torch.empty((B, Wp.shape[0], *h.shape[2:]), dtype=torch.float32, device=h.device)
+        _cabi.check(lib.pdephi_block_spectral_proj_fwd(plan, _p(Y), _p(mode_scale), _p(row_scale), rs_stride, _p(h), _p(Wc), _p(bc),
+                                                       _p(u), _p(hout), _p(Wp), _p(bp), Wp.shape[0], _p(out), B, C, _p(ws),
+                                                       nbytes, _stream()), "block_spectral_proj_fwd")
+    return u, hout, out
 
 
-def block_tail_bwd(g, u, h, Wc, want_bias: bool):
-    """gu = g gelu'(u), t = gu + Wc^T gu, dWc = sum gu (x) h, dbc = sum gu."""
+def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None):
+    """gu = g gelu'(u), t = gu + Wc^T gu, dWc = sum gu (x) h, dbc = sum gu.
+    head_w = Wp [n,64]: `g` is the gradient of the fused output projection's result, [B,n,...]; the block's incoming
+    gradient Wp^T g is generated inside the kernel."""
     B, C = h.shape[:2]
     S = h[0, 0].numel()
     lib = _cabi.load()
@@ -260,8 +282,12 @@ def block_tail_bwd(g, u, h, Wc, want_bias: bool):
         db = torch.empty(C, dtype=torch.float32, device=h.device) if want_bias else None
         nbytes = lib.pdephi_block_tail_bwd_workspace_bytes(C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
-        _cabi.check(lib.pdephi_block_tail_bwd(_p(g), _p(u), _p(h), _p(Wc), _p(gu), _p(t), _p(dW), _p(db), B, C, S, _p(ws),
-                                              nbytes, _stream()), "block_tail_bwd")
+        if head_w is None:
+            _cabi.check(lib.pdephi_block_tail_bwd(_p(g), _p(u), _p(h), _p(Wc), _p(gu), _p(t), _p(dW), _p(db), B, C, S, _p(ws),
+                                                  nbytes, _stream()), "block_tail_bwd")
+        else:
+            _cabi.check(lib.pdephi_block_tail_proj_bwd(_p(g), _p(head_w), head_w.shape[0], _p(u), _p(h), _p(Wc), _p(gu), _p(t),
+                                                       _p(dW), _p(db), B, C, S, _p(ws), nbytes, _stream()), "block_tail_proj_bwd")
     return gu, t, dW, db
 
 
@@ -677,6 +703,26 @@ def pointwise_linear_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
             and min(weight.shape[0], weight.shape[1]) <= 8)
 
 
+def _head_tuple(Wp, bp):
+    return None if Wp is None else (Wp.contiguous(), bp.contiguous() if bp is not None else None)
+
+
+def _head_param_grads(hout, gout, Wp, has_bias):
+    """dWp = sum gout (x) hout, dbp = sum gout: the weight gradient of the fused output projection (pointwise.cu)."""
+    B, C = hout.shape[:2]
+    n = Wp.shape[0]
+    S = hout[0, 0].numel()
+    lib = _cabi.load()
+    with _cabi.on_device(hout.device):
+        dWp = torch.empty_like(Wp)
+        dbp = torch.empty(n, dtype=torch.float32, device=hout.device) if has_bias else None
+        nbytes = lib.pdephi_pointwise_wgrad_workspace_bytes(C, n, S)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=hout.device)
+        _cabi.check(lib.pdephi_pointwise_wgrad(_p(hout), _p(gout), _p(dWp), _p(dbp), B, C, n, S, _p(ws), nbytes, _stream()),
+                    "pointwise_wgrad(head)")
+    return dWp, dbp
+
+
 class RationalBlockFn(torch.autograd.Function):
     """One whole block of RationalFourierOperator3D: h' = gelu(RationalFourierLayer(h) + Conv1x1(h) + h)
     (rational_fourier.py:263-271) as K1 -> K2 -> K3 -> fused block tail, with a hand-written backward that
@@ -684,7 +730,8 @@ class RationalBlockFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, h, P, Q, mask, monoP, monoQ, modes, eps, precision, Wc, bc, slab=None):
+    def forward(ctx, h, P, Q, mask, monoP, monoQ, modes, eps, precision, Wc, bc, slab=None, Wp=None, bp=None):
+        # Wp / bp: the model's output projection, fused into this (the last) block: the result is then Wp h' + bp
         for t, n in ((h, "x"), (P, "P_coeffs"), (Q, "Q_coeffs"), (Wc, "conv weight")):
             _require_cuda_f32(t, n)
         h = h.contiguous()
@@ -699,29 +746,39 @@ class RationalBlockFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
         stats = sl.complete_stats(stats, eps)
+        head = _head_tuple(Wp, bp)
         if not sl.active and block_spectral_supported(h, modes_h, precision):
-            u, hout = block_spectral_fwd(Y, mask, stats[:, 2], h, Wc, bc)      # `spec` never touches HBM
+            res = block_spectral_fwd(Y, mask, stats[:, 2], h, Wc, bc, head)    # `spec` never touches HBM
         else:
             spec = sl.synthesis(Y, grid, mask, stats[:, 2], None, None, _cabi.FORWARD, precision)
-            u, hout = block_tail_fwd(h, spec, Wc, bc)
+            res = block_tail_fwd(h, spec, Wc, bc, head)
+        u, hout = res[0], res[1]
         if need_grad:
-            ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc)
-        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, bc is not None, sl)
-        return hout
+            ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc, *((hout, head[0]) if head else ()))
+        ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, bc is not None, sl, head is not None,
+                    bp is not None)
+        return res[2] if head else hout
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     @once_differentiable
     def backward(ctx, g):
-        X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc = ctx.saved_tensors
-        modes_h, grid, coeff_shapes, precision, has_bias, sl = ctx.meta
-        gu, t, dWc, dbc = block_tail_bwd(g.contiguous(), u, h, Wc, has_bias)
+        X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc = ctx.saved_tensors[:11]
+        modes_h, grid, coeff_shapes, precision, has_bias, sl, has_head, head_bias = ctx.meta
+        g = g.contiguous()
+        dWp = dbp = None
+        if has_head:      # g is the gradient of the projected output: Wp^T g is formed inside the block-tail kernel
+            hout, Wp = ctx.saved_tensors[11:13]
+            dWp, dbp = _head_param_grads(hout, g, Wp, head_bias)
+            gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp)
+        else:
+            gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias)
         dZ = sl.analysis(gu, modes_h, _cabi.ADJOINT, precision)
         dY = sl.projection_bwd(dZ, Y, mask, stats)
         dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
         sl.finish_coeff_grads(dP, dQ)
         dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
-        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None)
+        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp)
 
 
 class ComplexBlockFn(torch.autograd.Function):
@@ -729,7 +786,7 @@ class ComplexBlockFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, h, W, modes, precision, Wc, bc, slab=None):
+    def forward(ctx, h, W, modes, precision, Wc, bc, slab=None, Wp=None, bp=None):
         _require_cuda_f32(h, "x")
         _require_cuda_f32(W, "weights", complex_ok=True)
         h = h.contiguous()
@@ -740,25 +797,34 @@ class ComplexBlockFn(torch.autograd.Function):
         Wl, Wc = _local_weights(W, sl, my), Wc.contiguous()
         X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
         Y = complex_mix_fwd(X, Wl, modes_h[2])
+        head = _head_tuple(Wp, bp)
         if not sl.active and block_spectral_supported(h, modes_h, precision):
-            u, hout = block_spectral_fwd(Y, None, None, h, Wc, bc)
+            res = block_spectral_fwd(Y, None, None, h, Wc, bc, head)
         else:
             spec = sl.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, precision)
-            u, hout = block_tail_fwd(h, spec, Wc, bc)
-        ctx.save_for_backward(X, Wl, W, u, h, Wc)
-        ctx.meta = (modes_h, grid, precision, bc is not None, sl)
-        return hout
+            res = block_tail_fwd(h, spec, Wc, bc, head)
+        u, hout = res[0], res[1]
+        ctx.save_for_backward(X, Wl, W, u, h, Wc, *((hout, head[0]) if head else ()))
+        ctx.meta = (modes_h, grid, precision, bc is not None, sl, head is not None, bp is not None)
+        return res[2] if head else hout
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     @once_differentiable
     def backward(ctx, g):
-        X, Wl, W, u, h, Wc = ctx.saved_tensors
-        modes_h, grid, precision, has_bias, sl = ctx.meta
-        gu, t, dWc, dbc = block_tail_bwd(g.contiguous(), u, h, Wc, has_bias)
+        X, Wl, W, u, h, Wc = ctx.saved_tensors[:6]
+        modes_h, grid, precision, has_bias, sl, has_head, head_bias = ctx.meta
+        g = g.contiguous()
+        dWp = dbp = None
+        if has_head:
+            hout, Wp = ctx.saved_tensors[6:8]
+            dWp, dbp = _head_param_grads(hout, g, Wp, head_bias)
+            gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp)
+        else:
+            gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias)
         dY = sl.analysis(gu, modes_h, _cabi.ADJOINT, precision)
         dX, dW = complex_mix_bwd(X, Wl, dY, modes_h[2])
         sl.finish_coeff_grads(dW)
         dW = _scatter_weight_grad(dW, W, sl, modes_h[1])
         dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
-        return dh, dW, None, None, dWc.view_as(Wc), dbc, None
+        return dh, dW, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp

@@ -18,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _cabi
-from .functional import PointwiseLinearFn, library_call, pointwise_linear_supported, spectral_resample
+from .functional import PointwiseLinearFn, head_supported, library_call, pointwise_linear_supported, spectral_resample
 from .operators import RationalFourierLayer, SpectralConv3D
 
 
@@ -106,6 +106,7 @@ class RationalFourierOperator3D(nn.Module):
         self.final_activation = getattr(F, final_activation) if final_activation else None
         self.stability_constraints = stability_constraints or StabilityConstraints()
         _reset_pointwise(self)
+        self.fuse_head = True      # last block + output projection in one kernel chain where the shapes allow (not a parameter)
 
     def set_precision(self, precision: Optional[str]):
         """'auto' | 'fp32' | 'tf32x3' | 'tf32' | None (module default) for every spectral layer of this model."""
@@ -116,12 +117,18 @@ class RationalFourierOperator3D(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         h = _lift(x, self.input_proj)
         gelu = self.activation is F.gelu
-        for spectral, local in zip(self.rational_layers, self.local_convs):
+        last = len(self.rational_layers) - 1
+        out = None
+        for i, (spectral, local) in enumerate(zip(self.rational_layers, self.local_convs)):
             if gelu and spectral.block_supported(h, local):
-                h = spectral.forward_block(h, local)          # whole block in the library (TF32 path, width 64)
+                if i == last and self.fuse_head and head_supported(self.output_proj):
+                    out = spectral.forward_block(h, local, self.output_proj)   # ... and the output projection with it
+                else:
+                    h = spectral.forward_block(h, local)      # whole block in the library (TF32 path, width 64)
             else:   # spectral(h) + local(h) + h in one pass: both adds ride in the synthesis kernel's epilogue
                 h = self.activation(spectral.forward_fused(h, local(h)))
-        out = _lift(h, self.output_proj)
+        if out is None:
+            out = _lift(h, self.output_proj)
         return self.final_activation(out) if self.final_activation is not None else out
 
     # ---- inference-time rollout (rational_fourier.py:284-412) ---------------------
@@ -222,6 +229,7 @@ class FNO3D(nn.Module):
         self.activation = getattr(F, activation)
         self.final_activation = getattr(F, final_activation) if final_activation else None
         _reset_pointwise(self)
+        self.fuse_head = True      # last block + output projection in one kernel chain where the shapes allow (not a parameter)
 
     def set_precision(self, precision: Optional[str]):
         for layer in self.spectral_layers:
@@ -231,12 +239,18 @@ class FNO3D(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         h = _lift(x, self.input_proj)
         gelu = self.activation is F.gelu
-        for spectral, local in zip(self.spectral_layers, self.local_layers):
+        last = len(self.spectral_layers) - 1
+        out = None
+        for i, (spectral, local) in enumerate(zip(self.spectral_layers, self.local_layers)):
             if gelu and spectral.block_supported(h, local):
-                h = spectral.forward_block(h, local)
+                if i == last and self.fuse_head and head_supported(self.output_proj):
+                    out = spectral.forward_block(h, local, self.output_proj)
+                else:
+                    h = spectral.forward_block(h, local)
             else:
                 h = self.activation(spectral.forward_fused(h, local(h)))
-        out = _lift(h, self.output_proj)
+        if out is None:
+            out = _lift(h, self.output_proj)
         return self.final_activation(out) if self.final_activation is not None else out
 
     def rollout(self, initial_condition: torch.Tensor, steps: int, return_trajectory: bool = False) -> torch.Tensor:

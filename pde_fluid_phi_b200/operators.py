@@ -175,14 +175,16 @@ class RationalFourierLayer(nn.Module):
                 and conv.in_channels == conv.out_channels == self.in_channels == self.out_channels
                 and block_tail_supported(x, self._precision_code()))
 
-    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d) -> torch.Tensor:
+    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d, head: Optional[nn.Linear] = None) -> torch.Tensor:
         """gelu(layer(x) + conv(x) + x): the whole block of rational_fourier.py:263-271 in the library
         (TF32 path, width 64): spectral layer, then the 1x1x1 convolution as a tcgen05 channel GEMM whose
-        epilogue applies bias, both residual adds and the exact GELU."""
+        epilogue applies bias, both residual adds and the exact GELU.  `head`: the model's output projection, applied
+        to the result inside the same kernel (the last block of the model): returns head(gelu(...)) channels-first."""
         _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
         return library_call(RationalBlockFn, x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
-                                     self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
-                                     self._precision_code(), conv.weight, conv.bias, self.slab)
+                            self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
+                            self._precision_code(), conv.weight, conv.bias, self.slab,
+                            head.weight if head is not None else None, head.bias if head is not None else None)
 
 
 class SpectralConv3D(nn.Module):
@@ -224,8 +226,9 @@ class SpectralConv3D(nn.Module):
                 and conv.in_channels == conv.out_channels == self.in_channels == self.out_channels
                 and block_tail_supported(x, self._precision_code()))
 
-    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d) -> torch.Tensor:
-        """gelu(spectral_conv(x) + conv(x) + x): the whole block of models/fno3d.py:91-97 in the library."""
+    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d, head: Optional[nn.Linear] = None) -> torch.Tensor:
+        """gelu(spectral_conv(x) + conv(x) + x): the whole block of models/fno3d.py:91-97 in the library; `head` as in
+        RationalFourierLayer.forward_block."""
         _check_input(x, self.in_channels, self.modes, "SpectralConv3D", self.slab)
         return library_call(ComplexBlockFn, x, self.weights, tuple(self.modes), self._precision_code(), conv.weight, conv.bias,
-                                    self.slab)
+                            self.slab, head.weight if head is not None else None, head.bias if head is not None else None)

@@ -659,3 +659,43 @@ def test_whole_block_model_tf32_vs_unfused():
     assert rel(out_fused, out_ref) < 3e-3
     for n, p in model.named_parameters():
         assert rel(fused[n], p.grad) < 5e-3, n
+
+
+@pytest.mark.parametrize("cls,grid", [("rfno", (32, 128, 128)), ("rfno", (8, 16, 16)), ("fno", (32, 128, 128))])
+def test_last_block_with_fused_output_projection(cls, grid):
+    """The last block carries the output projection (forward: in the block-tail epilogue; backward: the block's incoming
+    gradient Wp^T gout is generated inside the kernel): same outputs and gradients as with the projection as its own op."""
+    torch.manual_seed(37)
+    modes = (8, 16, 16) if grid[1] == 128 else (4, 4, 4)
+    prec = "tf32" if grid[1] == 128 else "auto"      # small grid: FFMA transforms + the unfused block tail, also with a head
+    if cls == "rfno":
+        model = pb.RationalFourierOperator3D(modes=modes, width=64, n_layers=2).to(DEV).set_precision(prec)
+        with torch.no_grad():
+            for layer in model.rational_layers:
+                q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+                layer.Q_coeffs.mul_(1e-4)
+                layer.Q_coeffs[..., 0, 0, 0] = q0
+                layer.P_coeffs.mul_(1e-2)
+    else:
+        model = pb.FNO3D(modes=modes, width=64, n_layers=2, in_channels=2, out_channels=2).to(DEV).set_precision(prec)
+    cin = 3 if cls == "rfno" else 2
+    x = torch.randn(2, cin, *grid, device=DEV)
+    y = torch.randn(2, cin, *grid, device=DEV)
+    res = {}
+    for fuse in (True, False):
+        model.fuse_head = fuse
+        model.zero_grad(set_to_none=True)
+        _cabi.profile(True, True)
+        out = model(x)
+        torch.nn.functional.mse_loss(out, y).backward()
+        torch.cuda.synchronize()
+        rep = _cabi.profile_report(timed=False)
+        _cabi.profile(False, True)
+        res[fuse] = (out.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters()}, rep)
+    # the fused run launches one projection pass fewer in each direction
+    assert res[True][2].get("pointwise_linear_kernel", (0, 0))[0] == res[False][2]["pointwise_linear_kernel"][0] - 2
+    assert rel(res[True][0], res[False][0]) < 1e-6
+    # the generated g' differs from the materialised one in the last fp32 bit here and there, which the TF32 truncation of
+    # the next GEMM operand turns into 2^-11 flips: TF32-level agreement on the gradients (a wrong mapping would be O(1))
+    for n in res[True][1]:
+        assert rel(res[True][1][n], res[False][1][n]) < 5e-4, (n, rel(res[True][1][n], res[False][1][n]))
