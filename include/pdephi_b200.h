@@ -173,7 +173,7 @@ int pdephi_pointwise_wgrad(const float* x, const float* g, float* dW, float* dbi
 /* ---- fused block tail of a width-64 operator model (tcgen05 TF32 channel GEMM + epilogue) -----
  * replaces Conv3d 1x1x1 + the two residual adds + exact GELU of rational_fourier.py:268-271 / fno3d.py:93-97
  *   fwd:  u = spec + (Wc h + bc) + h,  hout = gelu(u)            h, spec, u, hout [B,64,S];  Wc [64,64]
- *   bwd:  gu = g * gelu'(u),  t = gu + Wc^T gu,  dWc = sum_{b,s} gu (x) h,  dbc = sum_{b,s} gu
+ *   bwd:  gu = g * gelu'(u),  t = gu + Wc^T gu,  dWc = sum_{b,s} gu (x) h,  dbc = sum_{b,s} gu   (t may be NULL: not stored)
  * Needs 64 channels and S % 128 == 0 (PDEPHI_ERR_UNSUPPORTED otherwise). */
 int pdephi_block_tail_fwd(const float* h, const float* spec, const float* Wc, const float* bc, float* u,
                           float* hout, int B, int C, long long S, pdephi_stream_t stream);

@@ -373,7 +373,9 @@ enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2
 
 // GENG: the incoming gradient g' = Wp^T gout of the LAST block (the output projection's input gradient) is generated by the
 // loader warps from gout [B, n_out <= 4, S] instead of being read: the 4.3 GB g' is neither written nor read.
-template <bool GENG>
+// WT = false: t is not needed (first block of a model whose input needs no gradient: the lift's weight gradient is formed
+// from gu and the retained modes instead, functional.py::_lift_backward) and is not stored.
+template <bool GENG, bool WT>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
                       const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
@@ -538,11 +540,13 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BB_TEMPTY + d));
-      float* tp = t_out + g0;
+      if (WT) {
+        float* tp = t_out + g0;
 #pragma unroll
-      for (int j = 0; j < CPW; ++j) {
-        __stcs(tp, v[j] + r[j]);
-        tp += S;
+        for (int j = 0; j < CPW; ++j) {
+          __stcs(tp, v[j] + r[j]);
+          tp += S;
+        }
       }
     }
     // ---- per-CTA partials: dbias (registers -> warp shuffle -> 4 quarter-warps summed in order) and dW (TMEM) ----
@@ -704,15 +708,15 @@ static int block_tail_bwd_launch(const float* g, const float* u, const float* h,
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   {
     ProfScope ps(K_BLOCK_TAIL_BWD, st);
-    if (Wp) {
-      auto k = blk::block_tail_bwd_kernel<true>;
-      PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out);
-    } else {
-      auto k = blk::block_tail_bwd_kernel<false>;
-      PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), nullptr, 0);
+#define PDEPHI_BWD_LAUNCH(GG, WW)                                                                                          \
+    {                                                                                                                      \
+      auto k = blk::block_tail_bwd_kernel<GG, WW>;                                                                         \
+      PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
+      k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out); \
     }
+    if (Wp) { if (t) PDEPHI_BWD_LAUNCH(true, true) else PDEPHI_BWD_LAUNCH(true, false) }
+    else { if (t) PDEPHI_BWD_LAUNCH(false, true) else PDEPHI_BWD_LAUNCH(false, false) }
+#undef PDEPHI_BWD_LAUNCH
   }
   PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
   {
@@ -749,13 +753,13 @@ extern "C" int pdephi_block_tail_proj_fwd(const float* h, const float* spec, con
 extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t,
                                      float* dWc, float* dbc, int B, int Cc, long long S, void* workspace,
                                      size_t workspace_bytes, pdephi_stream_t stream) {
-  PDEPHI_REQUIRE(g && u && h && Wc && gu && t && dWc, "block_tail_bwd: null pointer");
+  PDEPHI_REQUIRE(g && u && h && Wc && gu && dWc, "block_tail_bwd: null pointer");     /* t may be NULL: not stored */
   return block_tail_bwd_launch(g, u, h, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int pdephi_block_tail_proj_bwd(const float* gout, const float* Wp, int n_out, const float* u, const float* h,
                                           const float* Wc, float* gu, float* t, float* dWc, float* dbc, int B, int Cc, long long S,
                                           void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
-  PDEPHI_REQUIRE(gout && Wp && u && h && Wc && gu && t && dWc, "block_tail_proj_bwd: null pointer");
+  PDEPHI_REQUIRE(gout && Wp && u && h && Wc && gu && dWc, "block_tail_proj_bwd: null pointer");   /* t may be NULL */
   return block_tail_bwd_launch(gout, u, h, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, Wp, n_out, (cudaStream_t)stream);
 }

@@ -268,7 +268,7 @@ def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None):
     return u, hout, out
 
 
-def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None):
+def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None, write_t: bool = True):
     """gu = g gelu'(u), t = gu + Wc^T gu, dWc = sum gu (x) h, dbc = sum gu.
     head_w = Wp [n,64]: `g` is the gradient of the fused output projection's result, [B,n,...]; the block's incoming
     gradient Wp^T g is generated inside the kernel."""
@@ -277,7 +277,7 @@ def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None):
     lib = _cabi.load()
     with _cabi.on_device(h.device):
         gu = torch.empty_like(h)
-        t = torch.empty_like(h)
+        t = torch.empty_like(h) if write_t else None
         dW = torch.empty((C, C), dtype=torch.float32, device=h.device)
         db = torch.empty(C, dtype=torch.float32, device=h.device) if want_bias else None
         nbytes = lib.pdephi_block_tail_bwd_workspace_bytes(C)
@@ -296,7 +296,11 @@ def block_tail_supported(h: torch.Tensor, precision: int) -> bool:
     arithmetic torch's own cuDNN convolution uses while ``torch.backends.cudnn.allow_tf32`` is True (the PyTorch
     default, so also what the reference's Conv3d does on this GPU): the 'tf32' route always takes it, the
     fp32-grade tensor-core routes take it exactly when torch would run the conv in TF32 too, 'fp32' never does."""
-    if not (h.is_cuda and h.dtype == torch.float32 and h.dim() == 5 and h.shape[1] == 64 and h[0, 0].numel() % 128 == 0):
+    return (h.dim() == 5 and block_tail_supported_shape(h.is_cuda, h.dtype, h.shape[1], h[0, 0].numel(), precision))
+
+
+def block_tail_supported_shape(is_cuda: bool, dtype, C: int, S: int, precision: int) -> bool:
+    if not (is_cuda and dtype == torch.float32 and C == 64 and S % 128 == 0):
         return False
     if precision == _cabi.PREC_TF32:
         return True
@@ -677,30 +681,79 @@ class PointwiseLinearFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        g = g.contiguous()
-        B, Cin = x.shape[:2]
-        Cout = weight.shape[0]
-        S = x[0, 0].numel()
-        lib = _cabi.load()
-        dx = dW = db = None
-        with _cabi.on_device(x.device):
-            if ctx.needs_input_grad[0]:
-                dx = torch.empty_like(x)
-                _cabi.check(lib.pdephi_pointwise_linear(_p(g), _p(weight), _p(None), _p(dx), B, Cout, Cin, S, 1, _stream()),
-                            "pointwise_linear(dx)")
-            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-                dW = torch.empty_like(weight)
-                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
-                nbytes = lib.pdephi_pointwise_wgrad_workspace_bytes(Cin, Cout, S)
-                ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-                _cabi.check(lib.pdephi_pointwise_wgrad(_p(x), _p(g), _p(dW), _p(db), B, Cin, Cout, S, _p(ws), nbytes,
-                                                       _stream()), "pointwise_wgrad")
-        return dx, dW, db
+        return _pointwise_linear_backward(x, weight, g.contiguous(), ctx.needs_input_grad[0],
+                                          ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]), ctx.has_bias)
+
+
+def _pointwise_linear_backward(x, weight, g, need_dx: bool, need_dw: bool, has_bias: bool):
+    """(dx, dW, db) of y = W x + b on the channels-first layout."""
+    B, Cin = x.shape[:2]
+    Cout = weight.shape[0]
+    S = x[0, 0].numel()
+    lib = _cabi.load()
+    dx = dW = db = None
+    with _cabi.on_device(x.device):
+        if need_dx:
+            dx = torch.empty_like(x)
+            _cabi.check(lib.pdephi_pointwise_linear(_p(g), _p(weight), _p(None), _p(dx), B, Cout, Cin, S, 1, _stream()),
+                        "pointwise_linear(dx)")
+        if need_dw:
+            dW = torch.empty_like(weight)
+            db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
+            nbytes = lib.pdephi_pointwise_wgrad_workspace_bytes(Cin, Cout, S)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _cabi.check(lib.pdephi_pointwise_wgrad(_p(x), _p(g), _p(dW), _p(db), B, Cin, Cout, S, _p(ws), nbytes,
+                                                   _stream()), "pointwise_wgrad")
+    return dx, dW, db
 
 
 def pointwise_linear_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x[0, 0].numel() % 4 == 0
             and min(weight.shape[0], weight.shape[1]) <= 8)
+
+
+# ---- the input lift (nn.Linear in_channels -> width) taken into the FIRST block ------------------------------------------
+# With h0 = W_in x + b_in (rational_fourier.py:258-260) everything the block needs from h0 in mode space is linear in the
+# modes of the 3-channel input:  A(h0)[c] = sum_j W_in[c,j] A(x)[j] + b_in[c] N delta_k0  -- so the forward analysis reads
+# 0.2 GB instead of 4.3 GB -- and, when x needs no gradient, the lift's parameter gradients follow from
+#   gh0 = S_adj(dX) + t,  t = gu + Wc^T gu,   <x_j, S_adj(dX_c)> = Re sum_k conj(A(x_j)_k) dX_c,k   (adjointness)
+#   dW_in[c,j] = Re sum_{b,k} conj(A(x)[b,j,k]) dX[b,c,k] + ((I + Wc^T) G)[c,j],   G[o,j] = sum_{b,s} gu[b,o,s] x[b,j,s]
+#   db_in[c]   = N sum_b Re dX[b,c,0] + ((I + Wc^T) sum_{b,s} gu)[c]
+# without the adjoint synthesis (8.9 GB), without storing t (4.3 GB) and without gh0 ever existing.
+def _lift_forward(x, Win, bin_, modes_h, precision):
+    x = x.contiguous()
+    Win = Win.contiguous()
+    B, Cin = x.shape[:2]
+    Cout = Win.shape[0]
+    S = x[0, 0].numel()
+    lib = _cabi.load()
+    with _cabi.on_device(x.device):
+        h = torch.empty((B, Cout, *x.shape[2:]), dtype=torch.float32, device=x.device)
+        _cabi.check(lib.pdephi_pointwise_linear(_p(x), _p(Win), _p(bin_), _p(h), B, Cin, Cout, S, 0, _stream()), "pointwise_linear")
+    Ax = analysis(x, modes_h, _cabi.FORWARD, precision)                          # [B, Cin, mx, my, mzh]
+    X = torch.einsum("cj,bjxyz->bcxyz", Win.to(torch.complex64), Ax).contiguous()    # a few MB: glue, not a pass over a volume
+    if bin_ is not None:
+        X[:, :, 0, 0, 0] += bin_ * float(S)
+    return x, h, Ax, X
+
+
+def _lift_backward(x, Ax, gu, dX, Wc, has_bias):
+    """(dW_in, db_in) from the first block's gu and dX (see above); Wc [64,64] is the block's 1x1x1 conv weight."""
+    B, Cin = x.shape[:2]
+    Cout = gu.shape[1]
+    S = x[0, 0].numel()
+    lib = _cabi.load()
+    with _cabi.on_device(x.device):
+        G = torch.empty((Cout, Cin), dtype=torch.float32, device=x.device)
+        gsum = torch.empty(Cout, dtype=torch.float32, device=x.device)
+        nbytes = lib.pdephi_pointwise_wgrad_workspace_bytes(Cin, Cout, S)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _cabi.check(lib.pdephi_pointwise_wgrad(_p(x), _p(gu), _p(G), _p(gsum), B, Cin, Cout, S, _p(ws), nbytes, _stream()),
+                    "pointwise_wgrad(lift)")
+    A = Wc.reshape(Cout, Cout).t() + torch.eye(Cout, dtype=torch.float32, device=x.device)      # I + Wc^T
+    dWin = A @ G + torch.einsum("bjxyz,bcxyz->cj", Ax.conj(), dX).real
+    dbin = (A @ gsum + float(S) * dX[:, :, 0, 0, 0].real.sum(0)) if has_bias else None
+    return dWin, dbin
 
 
 def _head_tuple(Wp, bp):
@@ -730,8 +783,10 @@ class RationalBlockFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, h, P, Q, mask, monoP, monoQ, modes, eps, precision, Wc, bc, slab=None, Wp=None, bp=None):
+    def forward(ctx, h, P, Q, mask, monoP, monoQ, modes, eps, precision, Wc, bc, slab=None, Wp=None, bp=None, Win=None,
+                bin_=None):
         # Wp / bp: the model's output projection, fused into this (the last) block: the result is then Wp h' + bp
+        # Win / bin_: the model's input lift, taken into this (the first) block: `h` is then the model input x
         for t, n in ((h, "x"), (P, "P_coeffs"), (Q, "Q_coeffs"), (Wc, "conv weight")):
             _require_cuda_f32(t, n)
         h = h.contiguous()
@@ -742,7 +797,12 @@ class RationalBlockFn(torch.autograd.Function):
         P, Q, Wc = P.contiguous(), Q.contiguous(), Wc.contiguous()
         if sl.sharded:
             mask, monoP, monoQ = sl.local_modes(mask, modes_h), sl.local_modes(monoP, modes_h, 1), sl.local_modes(monoQ, modes_h, 1)
-        X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
+        lifted = Win is not None
+        x_in = Ax = None
+        if lifted:
+            x_in, h, Ax, X = _lift_forward(h, Win, bin_, modes_h, precision)
+        else:
+            X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
         need_grad = any(ctx.needs_input_grad)
         Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
         stats = sl.complete_stats(stats, eps)
@@ -754,9 +814,10 @@ class RationalBlockFn(torch.autograd.Function):
             res = block_tail_fwd(h, spec, Wc, bc, head)
         u, hout = res[0], res[1]
         if need_grad:
-            ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc, *((hout, head[0]) if head else ()))
+            ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc, *((hout, head[0]) if head else ()),
+                                  *((x_in, Ax, Win) if lifted else ()))
         ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, bc is not None, sl, head is not None,
-                    bp is not None)
+                    bp is not None, lifted, bin_ is not None)
         return res[2] if head else hout
 
     @staticmethod
@@ -764,21 +825,33 @@ class RationalBlockFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc = ctx.saved_tensors[:11]
-        modes_h, grid, coeff_shapes, precision, has_bias, sl, has_head, head_bias = ctx.meta
+        modes_h, grid, coeff_shapes, precision, has_bias, sl, has_head, head_bias, lifted, lift_bias = ctx.meta
         g = g.contiguous()
-        dWp = dbp = None
+        nsaved = 11
+        dWp = dbp = dWin = dbin = None
+        # first block of a model whose input needs no gradient: t and the adjoint synthesis are not needed (_lift_backward)
+        skip_dh = lifted and not ctx.needs_input_grad[0]
+        Wp = None
         if has_head:      # g is the gradient of the projected output: Wp^T g is formed inside the block-tail kernel
-            hout, Wp = ctx.saved_tensors[11:13]
+            hout, Wp = ctx.saved_tensors[nsaved:nsaved + 2]
+            nsaved += 2
             dWp, dbp = _head_param_grads(hout, g, Wp, head_bias)
-            gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp)
-        else:
-            gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias)
+        gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh)
         dZ = sl.analysis(gu, modes_h, _cabi.ADJOINT, precision)
         dY = sl.projection_bwd(dZ, Y, mask, stats)
         dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
         sl.finish_coeff_grads(dP, dQ)
-        dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
-        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp)
+        dh = None
+        if lifted:
+            x_in, Ax, Win = ctx.saved_tensors[nsaved:nsaved + 3]
+            if skip_dh:
+                dWin, dbin = _lift_backward(x_in, Ax, gu, dX, Wc, lift_bias)
+            else:         # the input wants its gradient: materialise gh0 and run the lift's own backward on it
+                gh0 = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
+                dh, dWin, dbin = _pointwise_linear_backward(x_in, Win, gh0, True, True, lift_bias)
+        else:
+            dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
+        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin)
 
 
 class ComplexBlockFn(torch.autograd.Function):
@@ -786,7 +859,7 @@ class ComplexBlockFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, h, W, modes, precision, Wc, bc, slab=None, Wp=None, bp=None):
+    def forward(ctx, h, W, modes, precision, Wc, bc, slab=None, Wp=None, bp=None, Win=None, bin_=None):
         _require_cuda_f32(h, "x")
         _require_cuda_f32(W, "weights", complex_ok=True)
         h = h.contiguous()
@@ -795,7 +868,12 @@ class ComplexBlockFn(torch.autograd.Function):
         grid = tuple(h.shape[2:])
         sl = _Slab(slab, h)
         Wl, Wc = _local_weights(W, sl, my), Wc.contiguous()
-        X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
+        lifted = Win is not None
+        x_in = Ax = None
+        if lifted:
+            x_in, h, Ax, X = _lift_forward(h, Win, bin_, modes_h, precision)
+        else:
+            X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
         Y = complex_mix_fwd(X, Wl, modes_h[2])
         head = _head_tuple(Wp, bp)
         if not sl.active and block_spectral_supported(h, modes_h, precision):
@@ -804,8 +882,8 @@ class ComplexBlockFn(torch.autograd.Function):
             spec = sl.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, precision)
             res = block_tail_fwd(h, spec, Wc, bc, head)
         u, hout = res[0], res[1]
-        ctx.save_for_backward(X, Wl, W, u, h, Wc, *((hout, head[0]) if head else ()))
-        ctx.meta = (modes_h, grid, precision, bc is not None, sl, head is not None, bp is not None)
+        ctx.save_for_backward(X, Wl, W, u, h, Wc, *((hout, head[0]) if head else ()), *((x_in, Ax, Win) if lifted else ()))
+        ctx.meta = (modes_h, grid, precision, bc is not None, sl, head is not None, bp is not None, lifted, bin_ is not None)
         return res[2] if head else hout
 
     @staticmethod
@@ -813,18 +891,29 @@ class ComplexBlockFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         X, Wl, W, u, h, Wc = ctx.saved_tensors[:6]
-        modes_h, grid, precision, has_bias, sl, has_head, head_bias = ctx.meta
+        modes_h, grid, precision, has_bias, sl, has_head, head_bias, lifted, lift_bias = ctx.meta
         g = g.contiguous()
-        dWp = dbp = None
+        nsaved = 6
+        dWp = dbp = dWin = dbin = None
+        skip_dh = lifted and not ctx.needs_input_grad[0]
+        Wp = None
         if has_head:
-            hout, Wp = ctx.saved_tensors[6:8]
+            hout, Wp = ctx.saved_tensors[nsaved:nsaved + 2]
+            nsaved += 2
             dWp, dbp = _head_param_grads(hout, g, Wp, head_bias)
-            gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp)
-        else:
-            gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias)
+        gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh)
         dY = sl.analysis(gu, modes_h, _cabi.ADJOINT, precision)
         dX, dW = complex_mix_bwd(X, Wl, dY, modes_h[2])
         sl.finish_coeff_grads(dW)
         dW = _scatter_weight_grad(dW, W, sl, modes_h[1])
-        dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
-        return dh, dW, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp
+        dh = None
+        if lifted:
+            x_in, Ax, Win = ctx.saved_tensors[nsaved:nsaved + 3]
+            if skip_dh:
+                dWin, dbin = _lift_backward(x_in, Ax, gu, dX, Wc, lift_bias)
+            else:
+                gh0 = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
+                dh, dWin, dbin = _pointwise_linear_backward(x_in, Win, gh0, True, True, lift_bias)
+        else:
+            dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
+        return dh, dW, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin

@@ -107,6 +107,7 @@ class RationalFourierOperator3D(nn.Module):
         self.stability_constraints = stability_constraints or StabilityConstraints()
         _reset_pointwise(self)
         self.fuse_head = True      # last block + output projection in one kernel chain where the shapes allow (not a parameter)
+        self.fuse_lift = True      # first block + input lift: mode-space analysis / lift backward (functional._lift_forward)
 
     def set_precision(self, precision: Optional[str]):
         """'auto' | 'fp32' | 'tf32x3' | 'tf32' | None (module default) for every spectral layer of this model."""
@@ -115,11 +116,20 @@ class RationalFourierOperator3D(nn.Module):
         return self
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        h = _lift(x, self.input_proj)
         gelu = self.activation is F.gelu
         last = len(self.rational_layers) - 1
         out = None
+        first = 0
+        if (gelu and self.fuse_lift and last > 0 and x.dim() == 5 and x.shape[1] == self.input_proj.in_features
+                and self.rational_layers[0].lifted_block_supported(x, self.local_convs[0], self.input_proj)):
+            # the lift rides in the first block: its analysis and (x needs no gradient) its backward run in mode space
+            h = self.rational_layers[0].forward_block(x, self.local_convs[0], None, self.input_proj)
+            first = 1
+        else:
+            h = _lift(x, self.input_proj)
         for i, (spectral, local) in enumerate(zip(self.rational_layers, self.local_convs)):
+            if i < first:
+                continue
             if gelu and spectral.block_supported(h, local):
                 if i == last and self.fuse_head and head_supported(self.output_proj):
                     out = spectral.forward_block(h, local, self.output_proj)   # ... and the output projection with it
@@ -230,6 +240,7 @@ class FNO3D(nn.Module):
         self.final_activation = getattr(F, final_activation) if final_activation else None
         _reset_pointwise(self)
         self.fuse_head = True      # last block + output projection in one kernel chain where the shapes allow (not a parameter)
+        self.fuse_lift = True      # first block + input lift: mode-space analysis / lift backward (functional._lift_forward)
 
     def set_precision(self, precision: Optional[str]):
         for layer in self.spectral_layers:
@@ -237,11 +248,19 @@ class FNO3D(nn.Module):
         return self
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        h = _lift(x, self.input_proj)
         gelu = self.activation is F.gelu
         last = len(self.spectral_layers) - 1
         out = None
+        first = 0
+        if (gelu and self.fuse_lift and last > 0 and x.dim() == 5 and x.shape[1] == self.input_proj.in_features
+                and self.spectral_layers[0].lifted_block_supported(x, self.local_layers[0], self.input_proj)):
+            h = self.spectral_layers[0].forward_block(x, self.local_layers[0], None, self.input_proj)
+            first = 1
+        else:
+            h = _lift(x, self.input_proj)
         for i, (spectral, local) in enumerate(zip(self.spectral_layers, self.local_layers)):
+            if i < first:
+                continue
             if gelu and spectral.block_supported(h, local):
                 if i == last and self.fuse_head and head_supported(self.output_proj):
                     out = spectral.forward_block(h, local, self.output_proj)

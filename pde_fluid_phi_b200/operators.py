@@ -50,6 +50,17 @@ def get_grid(modes: Tuple[int, int, int], device: Union[str, torch.device] = "cp
     return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=0)
 
 
+def _lifted_ok(layer, x: torch.Tensor, conv: nn.Module, lift: nn.Module) -> bool:
+    from .functional import block_tail_supported_shape, pointwise_linear_supported
+    return (layer.slab is None and isinstance(lift, nn.Linear) and isinstance(x, torch.Tensor) and x.dim() == 5
+            and x.shape[1] == lift.in_features and lift.out_features == layer.in_channels
+            and pointwise_linear_supported(x, lift.weight)
+            and isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.groups == 1
+            and conv.in_channels == conv.out_channels == layer.in_channels == layer.out_channels
+            and block_tail_supported_shape(x.is_cuda, x.dtype, lift.out_features, x[0, 0].numel(), layer._precision_code())
+            and all(m <= n for m, n in zip(layer.modes[:2], x.shape[2:4])) and layer.modes[2] // 2 + 1 <= x.shape[4] // 2 + 1)
+
+
 def _check_input(x: torch.Tensor, channels: int, modes, who: str, slab=None):
     if not isinstance(x, torch.Tensor) or x.dim() != 5:
         raise ValueError(f"{who}: expected a [batch, channels, Nx, Ny, Nz] tensor, got "
@@ -175,16 +186,25 @@ class RationalFourierLayer(nn.Module):
                 and conv.in_channels == conv.out_channels == self.in_channels == self.out_channels
                 and block_tail_supported(x, self._precision_code()))
 
-    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d, head: Optional[nn.Linear] = None) -> torch.Tensor:
+    def lifted_block_supported(self, x: torch.Tensor, conv: nn.Module, lift: nn.Module) -> bool:
+        """Can the first block take the model input `x` and the lift with it? (the block route must apply to lift(x))"""
+        return _lifted_ok(self, x, conv, lift)
+
+    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d, head: Optional[nn.Linear] = None,
+                      lift: Optional[nn.Linear] = None) -> torch.Tensor:
         """gelu(layer(x) + conv(x) + x): the whole block of rational_fourier.py:263-271 in the library
         (TF32 path, width 64): spectral layer, then the 1x1x1 convolution as a tcgen05 channel GEMM whose
         epilogue applies bias, both residual adds and the exact GELU.  `head`: the model's output projection, applied
-        to the result inside the same kernel (the last block of the model): returns head(gelu(...)) channels-first."""
-        _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
+        to the result inside the same kernel (the last block of the model): returns head(gelu(...)) channels-first.
+        `lift`: the model's input lift; `x` is then the model input and the block starts from lift(x) (the first block:
+        its analysis and, when x needs no gradient, the lift's backward run in mode space -- functional._lift_forward)."""
+        if lift is None:
+            _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
         return library_call(RationalBlockFn, x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
                             self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
                             self._precision_code(), conv.weight, conv.bias, self.slab,
-                            head.weight if head is not None else None, head.bias if head is not None else None)
+                            head.weight if head is not None else None, head.bias if head is not None else None,
+                            lift.weight if lift is not None else None, lift.bias if lift is not None else None)
 
 
 class SpectralConv3D(nn.Module):
@@ -226,9 +246,15 @@ class SpectralConv3D(nn.Module):
                 and conv.in_channels == conv.out_channels == self.in_channels == self.out_channels
                 and block_tail_supported(x, self._precision_code()))
 
-    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d, head: Optional[nn.Linear] = None) -> torch.Tensor:
-        """gelu(spectral_conv(x) + conv(x) + x): the whole block of models/fno3d.py:91-97 in the library; `head` as in
-        RationalFourierLayer.forward_block."""
-        _check_input(x, self.in_channels, self.modes, "SpectralConv3D", self.slab)
+    def lifted_block_supported(self, x: torch.Tensor, conv: nn.Module, lift: nn.Module) -> bool:
+        return _lifted_ok(self, x, conv, lift)
+
+    def forward_block(self, x: torch.Tensor, conv: nn.Conv3d, head: Optional[nn.Linear] = None,
+                      lift: Optional[nn.Linear] = None) -> torch.Tensor:
+        """gelu(spectral_conv(x) + conv(x) + x): the whole block of models/fno3d.py:91-97 in the library; `head`, `lift` as
+        in RationalFourierLayer.forward_block."""
+        if lift is None:
+            _check_input(x, self.in_channels, self.modes, "SpectralConv3D", self.slab)
         return library_call(ComplexBlockFn, x, self.weights, tuple(self.modes), self._precision_code(), conv.weight, conv.bias,
-                            self.slab, head.weight if head is not None else None, head.bias if head is not None else None)
+                            self.slab, head.weight if head is not None else None, head.bias if head is not None else None,
+                            lift.weight if lift is not None else None, lift.bias if lift is not None else None)

@@ -699,3 +699,53 @@ def test_last_block_with_fused_output_projection(cls, grid):
     # the next GEMM operand turns into 2^-11 flips: TF32-level agreement on the gradients (a wrong mapping would be O(1))
     for n in res[True][1]:
         assert rel(res[True][1][n], res[False][1][n]) < 5e-4, (n, rel(res[True][1][n], res[False][1][n]))
+
+
+@pytest.mark.parametrize("cls,grid,x_grad", [("rfno", (32, 128, 128), False), ("rfno", (32, 128, 128), True), ("rfno", (8, 16, 16), False),
+                                             ("fno", (32, 128, 128), False)])
+def test_first_block_with_lift_in_mode_space(cls, grid, x_grad):
+    """The first block takes the input lift: A(h0) = W_in A(x) + b_in N delta_k0 in the forward, and -- when x needs no
+    gradient -- dW_in, db_in from gu and dX through the adjointness of the transform pair, with neither t nor the adjoint
+    synthesis.  Same outputs and gradients as lift -> block as separate ops (TF32-level agreement on that route)."""
+    torch.manual_seed(39)
+    modes = (8, 16, 16) if grid[1] == 128 else (4, 4, 4)
+    prec = "tf32" if grid[1] == 128 else "auto"
+    if cls == "rfno":
+        model = pb.RationalFourierOperator3D(modes=modes, width=64, n_layers=2).to(DEV).set_precision(prec)
+        with torch.no_grad():
+            for layer in model.rational_layers:
+                q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+                layer.Q_coeffs.mul_(1e-4)
+                layer.Q_coeffs[..., 0, 0, 0] = q0
+                layer.P_coeffs.mul_(1e-2)
+            model.input_proj.bias.normal_()                      # the DC term of the mode-space lift
+    else:
+        model = pb.FNO3D(modes=modes, width=64, n_layers=2, in_channels=2, out_channels=2).to(DEV).set_precision(prec)
+        with torch.no_grad():
+            model.input_proj.bias.normal_()
+    cin = 3 if cls == "rfno" else 2
+    x = torch.randn(2, cin, *grid, device=DEV, requires_grad=x_grad)
+    y = torch.randn(2, cin, *grid, device=DEV)
+    res = {}
+    for fuse in (True, False):
+        model.fuse_lift = fuse
+        model.zero_grad(set_to_none=True)
+        x.grad = None
+        _cabi.profile(True, True)
+        out = model(x)
+        torch.nn.functional.mse_loss(out, y).backward()
+        torch.cuda.synchronize()
+        rep = _cabi.profile_report(timed=False)
+        _cabi.profile(False, True)
+        grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+        if x_grad:
+            grads["x"] = x.grad.clone()
+        res[fuse] = (out.detach().clone(), grads, rep)
+    # "auto" here = fp32 transforms but the block tail's 1x1x1 conv in TF32 (cudnn.allow_tf32): the separate-ops run forms
+    # Wc^T gu on the tensor core, the mode-space lift backward applies (I + Wc^T) in fp32 -- agreement at the conv's level
+    tol_out, tol_g = (2e-3, 4e-3) if prec == "tf32" else (1e-5, 1e-3)
+    assert rel(res[True][0], res[False][0]) < tol_out
+    for n in res[True][1]:
+        assert rel(res[True][1][n], res[False][1][n]) < tol_g, (n, rel(res[True][1][n], res[False][1][n]))
+    if not x_grad and prec == "tf32":     # one adjoint synthesis fewer
+        assert res[True][2]["synthesis_zy_tc_kernel"][0] == res[False][2]["synthesis_zy_tc_kernel"][0] - 1
