@@ -213,6 +213,20 @@ int pdephi_block_tail_proj_bwd(const float* gout, const float* Wp, int n_out, co
                                float* gu, float* t, float* dWc, float* dbc, int B, int C, long long S, void* workspace,
                                size_t workspace_bytes, pdephi_stream_t stream);
 
+/* ---- the FIRST block of a model together with the input lift (nn.Linear n_in <= 4 -> 64) -------------------
+ * replaces rational_fourier.py:258-260 / fno3d.py:86-88 under the block above: the block's input h = Win x + bin is
+ * generated tile by tile inside the block-tail kernels from x [B,n_in,S] -- h is never written to or read from HBM.
+ * Win [64,n_in] row-major, bin [64] or NULL.  (The block's modes follow from the modes of x: A(h) = Win A(x) + bin N delta_k0.) */
+int pdephi_block_tail_lift_fwd(const float* x, const float* Win, const float* bin, int n_in, const float* spec, const float* Wc,
+                               const float* bc, float* u, float* hout, int B, int C, long long S, pdephi_stream_t stream);
+int pdephi_block_spectral_lift_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                                   long long row_scale_stride, const float* x, const float* Win, const float* bin, int n_in,
+                                   const float* Wc, const float* bc, float* u, float* hout, int B, int C, void* workspace,
+                                   size_t workspace_bytes, pdephi_stream_t stream);
+int pdephi_block_tail_lift_bwd(const float* g, const float* u, const float* x, const float* Win, const float* bin, int n_in,
+                               const float* Wc, float* gu, float* t, float* dWc, float* dbc, int B, int C, long long S,
+                               void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
 /* ---- per-kernel launch counters and CUDA-event timing (measurement support for bench.py) ------
  * Launches are always counted.  With timing enabled every kernel launch is bracketed by a pair of
  * cudaEvents on the launching stream; pdephi_profile_query synchronises on them and returns the

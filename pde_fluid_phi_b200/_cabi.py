@@ -69,6 +69,13 @@ SIGNATURES = {
                                                c_size_t, c_void_p]),
     "pdephi_block_tail_proj_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_int, c_int, c_longlong, c_void_p, c_size_t, c_void_p]),
+    "pdephi_block_tail_lift_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int, c_int, c_longlong, c_void_p]),
+    "pdephi_block_spectral_lift_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
+                                               c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
+                                               c_void_p]),
+    "pdephi_block_tail_lift_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_size_t, c_void_p]),
     "pdephi_profile_enable": (c_int, [c_int]),
     "pdephi_profile_reset": (c_int, []),
     "pdephi_profile_num_kernels": (c_int, []),

@@ -31,6 +31,7 @@ constexpr int LD_WARPS = 4;      // cp.async loader warps: warp w stages channel
 constexpr int LD_THREADS = 32 * LD_WARPS;
 constexpr int EPI0 = 1 + LD_WARPS;         // first epilogue warp (warp 0 issues the MMAs)
 constexpr int THREADS = 32 * (EPI0 + EPI_WARPS);
+constexpr int MAXP_IN = 4;       // most input channels the fused lift takes
 
 // MN-major TF32 operand (M or N contiguous).  32-bit MN-major operands exist only in the "128B swizzle with
 // 32-byte atoms" layout (UMMA LayoutType 1 = SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
@@ -127,6 +128,40 @@ __device__ __forceinline__ void stage_rows(uint32_t dst, const float* __restrict
   }
 }
 
+// GENH: the block's input h = W_in x + b_in (the model's lift, rational_fourier.py:258-260) is generated by the loader warps
+// from the n_in <= 4 channels of the model input instead of being staged from HBM: h0 is never materialised.  wtab: [64]
+// float4 (W_in[c][0..3]) followed by [64] bias floats in shared memory.  Same arithmetic in the forward and the backward.
+// this lane's four points of every input channel of tile (b, s0)
+__device__ __forceinline__ void load_x(float4* xv, const float* __restrict__ xin, int n_in, long long b, long long s0, long long S,
+                                       int lane) {
+#pragma unroll
+  for (int n = 0; n < MAXP_IN; ++n)
+    xv[n] = (n < n_in) ? __ldg(reinterpret_cast<const float4*>(xin + ((size_t)b * n_in + n) * S + s0) + lane)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <bool KMAJOR>
+__device__ __forceinline__ void generate_rows(uint8_t* dst, const float4* xv, const uint8_t* wtab, int lw, int lane) {
+  const float* bias = reinterpret_cast<const float*>(wtab + C * 16);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = lw * 16 + i;
+    const float4 w = reinterpret_cast<const float4*>(wtab)[r];
+    const float bb = bias[r];
+    float4 o;
+    o.x = fmaf(w.w, xv[3].x, fmaf(w.z, xv[2].x, fmaf(w.y, xv[1].x, fmaf(w.x, xv[0].x, bb))));
+    o.y = fmaf(w.w, xv[3].y, fmaf(w.z, xv[2].y, fmaf(w.y, xv[1].y, fmaf(w.x, xv[0].y, bb))));
+    o.z = fmaf(w.w, xv[3].z, fmaf(w.z, xv[2].z, fmaf(w.y, xv[1].z, fmaf(w.x, xv[0].z, bb))));
+    o.w = fmaf(w.w, xv[3].w, fmaf(w.z, xv[2].w, fmaf(w.y, xv[1].w, fmaf(w.x, xv[0].w, bb))));
+    *reinterpret_cast<float4*>(dst + (KMAJOR ? chunk_off_k(r, lane) : chunk_off_mn(r, lane))) = o;
+  }
+}
+__device__ __forceinline__ void build_lift_table(uint8_t* wtab, const float* __restrict__ Win, const float* __restrict__ bin, int n_in,
+                                                 int tid, int nthr) {
+  float* w = reinterpret_cast<float*>(wtab);
+  for (int i = tid; i < C * 4; i += nthr) w[i] = ((i & 3) < n_in) ? __ldg(Win + (i >> 2) * n_in + (i & 3)) : 0.f;
+  for (int i = tid; i < C; i += nthr) w[C * 4 + i] = bin ? __ldg(bin + i) : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 //   warp 0: MMA issuer + TMEM owner, warps 1..4: loaders, warps 5..20: epilogue
@@ -140,8 +175,8 @@ constexpr int F_STAGES = 3;
 // the epilogue: every thread reduces its 16 channels, the four channel groups meet through shared memory.  The separate
 // projection kernel and its 4.3 GB read of h' disappear (h' is still written: the projection's weight gradient reads it).
 constexpr int MAXP = 4;
-struct FSmem { uint32_t stage[F_STAGES], w, bz, bias, wp, red, bars, tmem_slot, total; };
-__host__ __device__ inline FSmem fwd_smem(bool fused, bool proj = false) {
+struct FSmem { uint32_t stage[F_STAGES], w, bz, bias, wp, red, lift, bars, tmem_slot, total; };
+__host__ __device__ inline FSmem fwd_smem(bool fused, bool proj = false, bool genh = false) {
   FSmem s; uint32_t o = 0;
   for (int i = 0; i < F_STAGES; ++i) { s.stage[i] = o; o += fused ? TILE + 2 * BOX : 2 * TILE; }
   s.w = o; o += 2 * BOX;
@@ -149,6 +184,7 @@ __host__ __device__ inline FSmem fwd_smem(bool fused, bool proj = false) {
   s.bias = o; o += 256;
   s.wp = o; o += proj ? C * 16 + 16 : 0;                   // [64] float4 (w_0..w_3 of channel c) + bias float4
   s.red = o; o += proj ? 2 * 4 * MAXP * TS * 4 : 0;        // [tile parity][channel group][output][point]
+  s.lift = o; o += genh ? C * 16 + C * 4 : 0;              // GENH: [64] float4 lift weights + [64] bias
   s.bars = o; o += 128;
   s.tmem_slot = o; o += 64;
   s.total = o;
@@ -156,23 +192,24 @@ __host__ __device__ inline FSmem fwd_smem(bool fused, bool proj = false) {
 }
 enum { FB_FULL = 0, FB_EMPTY = F_STAGES, FB_DFULL = 2 * F_STAGES, FB_DEMPTY = 2 * F_STAGES + 2 };
 
-template <bool FUSED, bool PROJ>
+template <bool FUSED, bool PROJ, bool GENH>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ spec_in, const float* __restrict__ Wc,
                       const float* __restrict__ bc, float* __restrict__ u_out, float* __restrict__ h_out,
                       long long tiles_per_batch, long long ntiles, long long S, const float* __restrict__ bzimg, int ldz,
                       int contiguous, const float* __restrict__ Wp, const float* __restrict__ bp, float* __restrict__ proj_out,
-                      int NP) {
+                      int NP, const float* __restrict__ Win, const float* __restrict__ bin, int n_in) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const FSmem L = fwd_smem(FUSED, PROJ);
+  const FSmem L = fwd_smem(FUSED, PROJ, GENH);
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // the truncation bias of the data operands (h; V) is undone on the accumulator in the epilogue, not in the weights
   build_w_image(sm + L.w, Wc, false, threadIdx.x, THREADS, 1.0f);
+  if (GENH) build_lift_table(sm + L.lift, Win, bin, n_in, threadIdx.x, THREADS);
   if (PROJ) {
     float* wp = reinterpret_cast<float*>(sm + L.wp);
     for (int i = threadIdx.x; i < C * MAXP + MAXP; i += THREADS) {
@@ -217,12 +254,28 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
     // released by its epilogue -- MMA(k) never overlapped epilogue(k-1).
     const int lw = warp - 1;
     const int cpr = ldz >> 2, nchunk = C * cpr;        // FUSED: 16-byte chunks per V row / per V tile
+    // GENH: the x values of the NEXT tile are fetched while this one is generated (with the loads issued where they are
+    // consumed the loader, not HBM, set the pace of the first block: 2.5 -> 3.25 ms)
+    float4 xnext[MAXP_IN];
+    auto fetch_x = [&](long long it) {
+      const long long t = tile0 + it * tstep;
+      const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
+      load_x(xnext, h_in, n_in, b, s0, S, lane);
+    };
+    if (GENH && my_tiles > 0) fetch_x(0);
     auto issue = [&](long long it) {
       const long long t = tile0 + it * tstep;
       const int s = (int)(it % F_STAGES);
+      float4 xv[MAXP_IN];
+      if (GENH) {
+#pragma unroll
+        for (int n = 0; n < MAXP_IN; ++n) xv[n] = xnext[n];
+        if (it + 1 < my_tiles) fetch_x(it + 1);
+      }
       mbar_wait(bar(FB_EMPTY + s), (uint32_t)(((it / F_STAGES) & 1) ^ 1));
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
-      stage_rows<false>(base + L.stage[s], h_in, b, s0, S, lw, lane);
+      if (GENH) generate_rows<false>(sm + L.stage[s], xv, sm + L.lift, lw, lane);   // h_in = model input x
+      else stage_rows<false>(base + L.stage[s], h_in, b, s0, S, lw, lane);
       if (FUSED) {
         // V rows of tile t are contiguous: chunk q = (channel c, chunk j of its row) -> K-major 128B-swizzled B operand
         const float* vsrc = spec_in + (size_t)t * C * ldz;
@@ -354,13 +407,14 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
 //   warp 0: MMA issuer + TMEM owner, warps 1..4: loaders, warps 5..20: compute / epilogue
 // ------------------------------------------------------------------------------------------------
 constexpr int B_STAGES = 2;
-struct BSmem { uint32_t stage[B_STAGES], wt, red, wp, bars, tmem_slot, total; };
+struct BSmem { uint32_t stage[B_STAGES], wt, red, wp, lift, bars, tmem_slot, total; };
 __host__ __device__ inline BSmem bwd_smem() {
   BSmem s; uint32_t o = 0;
   for (int i = 0; i < B_STAGES; ++i) { s.stage[i] = o; o += 3 * TILE; }   // g' (-> gu, MN layout), h (K layout), u (-> gu, K layout)
   s.wt = o; o += 2 * BOX;
   s.red = o; o += 4 * C * 4;
   s.wp = o; o += C * 16;                                                   // GENG: [64] float4 columns of the projection weight
+  s.lift = o; o += C * 16 + C * 4;                                         // GENH: lift weights + bias
   s.bars = o; o += 128;
   s.tmem_slot = o; o += 64;
   s.total = o;
@@ -375,12 +429,12 @@ enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2
 // loader warps from gout [B, n_out <= 4, S] instead of being read: the 4.3 GB g' is neither written nor read.
 // WT = false: t is not needed (first block of a model whose input needs no gradient: the lift's weight gradient is formed
 // from gu and the retained modes instead, functional.py::_lift_backward) and is not stored.
-template <bool GENG, bool WT>
+template <bool GENG, bool WT, bool GENH>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
                       const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
                       float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S, int contiguous,
-                      const float* __restrict__ Wp, int NP) {
+                      const float* __restrict__ Wp, int NP, const float* __restrict__ Win, const float* __restrict__ bin, int n_in) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -394,6 +448,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
     float* wp = reinterpret_cast<float*>(sm + L.wp);
     for (int i = threadIdx.x; i < C * MAXP; i += THREADS) wp[i] = ((i & 3) < NP) ? __ldg(Wp + (i & 3) * C + (i >> 2)) : 0.f;
   }
+  if (GENH) build_lift_table(sm + L.lift, Win, bin, n_in, threadIdx.x, THREADS);
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), LD_THREADS); mbar_init(bar(BB_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
@@ -437,7 +492,13 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       } else {
         stage_rows<false>(base + L.stage[s], g_in, b, s0, S, lw, lane);
       }
-      stage_rows<true>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
+      if (GENH) {                                                                  // h_in = model input x
+        float4 xv[MAXP_IN];
+        load_x(xv, h_in, n_in, b, s0, S, lane);
+        generate_rows<true>(sm + L.stage[s] + TILE, xv, sm + L.lift, lw, lane);
+      } else {
+        stage_rows<true>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
+      }
       stage_rows<true>(base + L.stage[s] + 2 * TILE, u_in, b, s0, S, lw, lane);
       if (GENG) {
         uint8_t* dst = sm + L.stage[s];
@@ -625,6 +686,14 @@ using namespace pdephi;
 
 namespace pdephi {
 struct ProjArgs { const float* Wp; const float* bp; float* out; int n; };   // output projection fused into the last block
+struct LiftArgs { const float* Win; const float* bin; int n; };              // input lift fused into the first block (h = x then)
+
+static int check_lift(const LiftArgs& lf, const ProjArgs* pr, const char* who) {
+  if (!lf.Win) return PDEPHI_OK;
+  if (lf.n < 1 || lf.n > blk::MAXP_IN) return fail(PDEPHI_ERR_UNSUPPORTED, "%s: the fused lift takes 1..%d input channels, got %d", who, blk::MAXP_IN, lf.n);
+  if (pr && pr->Wp) return fail(PDEPHI_ERR_UNSUPPORTED, "%s: lift and projection in the same block are not combined", who);
+  return PDEPHI_OK;
+}
 
 static int check_proj(const ProjArgs& pr, const char* who) {
   if (!pr.Wp) return PDEPHI_OK;
@@ -633,27 +702,31 @@ static int check_proj(const ProjArgs& pr, const char* who) {
   return PDEPHI_OK;
 }
 
+#define PDEPHI_FWD_LAUNCH(FF, PP, HH, SPEC, BZ, LDZ)                                                                        \
+  {                                                                                                                        \
+    auto k = blk::block_tail_fwd_kernel<FF, PP, HH>;                                                                       \
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
+    k<<<grid, blk::THREADS, smem, st>>>(h, SPEC, Wc, bc, u, hout, tpb, ntiles, S, BZ, LDZ, tile_order(), pr.Wp, pr.bp, pr.out, \
+                                        pr.n, lf.Win, lf.bin, lf.n);                                                       \
+  }
+
 static int block_tail_fwd_launch(const float* h, const float* spec, const float* Wc, const float* bc, float* u, float* hout,
-                                 int B, long long S, const ProjArgs& pr, cudaStream_t st) {
+                                 int B, long long S, const ProjArgs& pr, const LiftArgs& lf, cudaStream_t st) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(h) || !al16(spec)) return fail(PDEPHI_ERR_INVALID, "block_tail_fwd: h and spec must be 16-byte aligned");
   int rc = check_proj(pr, "block_tail_fwd");
   if (rc) return rc;
+  rc = check_lift(lf, &pr, "block_tail_fwd");
+  if (rc) return rc;
   const long long tpb = S / blk::TS, ntiles = tpb * B;
-  const bool proj = pr.Wp != nullptr;
-  const size_t smem = blk::fwd_smem(false, proj).total + 1024;
+  const bool proj = pr.Wp != nullptr, genh = lf.Win != nullptr;
+  const size_t smem = blk::fwd_smem(false, proj, genh).total + 1024;
   const int sms = num_sms();
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   ProfScope ps(K_BLOCK_TAIL_FWD, st);
-  if (proj) {
-    auto k = blk::block_tail_fwd_kernel<false, true>;
-    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, blk::THREADS, smem, st>>>(h, spec, Wc, bc, u, hout, tpb, ntiles, S, nullptr, 0, tile_order(), pr.Wp, pr.bp, pr.out, pr.n);
-  } else {
-    auto k = blk::block_tail_fwd_kernel<false, false>;
-    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, blk::THREADS, smem, st>>>(h, spec, Wc, bc, u, hout, tpb, ntiles, S, nullptr, 0, tile_order(), nullptr, nullptr, nullptr, 0);
-  }
+  if (genh) PDEPHI_FWD_LAUNCH(false, false, true, spec, nullptr, 0)
+  else if (proj) PDEPHI_FWD_LAUNCH(false, true, false, spec, nullptr, 0)
+  else PDEPHI_FWD_LAUNCH(false, false, false, spec, nullptr, 0)
   PDEPHI_LAUNCH_CHECK("block_tail_fwd_kernel");
   return PDEPHI_OK;
 }
@@ -662,37 +735,34 @@ static int block_tail_fwd_launch(const float* h, const float* spec, const float*
 // V [B*S/128 tiles][64][ldz] float, bzimg = the plan's z-synthesis operand image for Nz = 128.
 int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const float* bzimg, const float* Wc, const float* bc,
                                 float* u, float* hout, int B, long long S, const float* Wp, const float* bp, float* proj_out,
-                                int n_out, cudaStream_t st) {
+                                int n_out, const float* Win, const float* bin, int n_in, cudaStream_t st) {
   int rc = check_shape(B, blk::C, S, "block_spectral_fwd");
   if (rc) return rc;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(h) || !al16(V)) return fail(PDEPHI_ERR_INVALID, "block_spectral_fwd: h and the workspace must be 16-byte aligned");
   if (ldz % 4 != 0 || ldz > 64) return fail(PDEPHI_ERR_UNSUPPORTED, "block_spectral_fwd: ldz %d", ldz);
   const ProjArgs pr{Wp, bp, proj_out, n_out};
+  const LiftArgs lf{Win, bin, n_in};
   rc = check_proj(pr, "block_spectral_fwd");
   if (rc) return rc;
+  rc = check_lift(lf, &pr, "block_spectral_fwd");
+  if (rc) return rc;
   const long long tpb = S / blk::TS, ntiles = tpb * B;
-  const bool proj = Wp != nullptr;
-  const size_t smem = blk::fwd_smem(true, proj).total + 1024;
+  const bool proj = Wp != nullptr, genh = Win != nullptr;
+  const size_t smem = blk::fwd_smem(true, proj, genh).total + 1024;
   const int sms = num_sms();
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   ProfScope ps(K_BLOCK_SPECTRAL_FWD, st);
-  if (proj) {
-    auto k = blk::block_tail_fwd_kernel<true, true>;
-    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, blk::THREADS, smem, st>>>(h, V, Wc, bc, u, hout, tpb, ntiles, S, bzimg, ldz, tile_order(), Wp, bp, proj_out, n_out);
-  } else {
-    auto k = blk::block_tail_fwd_kernel<true, false>;
-    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, blk::THREADS, smem, st>>>(h, V, Wc, bc, u, hout, tpb, ntiles, S, bzimg, ldz, tile_order(), nullptr, nullptr, nullptr, 0);
-  }
+  if (genh) PDEPHI_FWD_LAUNCH(true, false, true, V, bzimg, ldz)
+  else if (proj) PDEPHI_FWD_LAUNCH(true, true, false, V, bzimg, ldz)
+  else PDEPHI_FWD_LAUNCH(true, false, false, V, bzimg, ldz)
   PDEPHI_LAUNCH_CHECK("block_tail_fwd_kernel<fused>");
   return PDEPHI_OK;
 }
 
 static int block_tail_bwd_launch(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t, float* dWc,
                                  float* dbc, int B, int Cc, long long S, void* workspace, size_t workspace_bytes,
-                                 const float* Wp, int n_out, cudaStream_t st) {
+                                 const float* Wp, int n_out, const LiftArgs& lf, cudaStream_t st) {
   int rc = check_shape(B, Cc, S, "block_tail_bwd");
   if (rc) return rc;
   const size_t need = pdephi_block_tail_bwd_workspace_bytes(Cc);
@@ -701,6 +771,11 @@ static int block_tail_bwd_launch(const float* g, const float* u, const float* h,
   if (!al16(g) || !al16(h) || !al16(u)) return fail(PDEPHI_ERR_INVALID, "block_tail_bwd: g, h and u must be 16-byte aligned");
   if (Wp && (n_out < 1 || n_out > blk::MAXP))
     return fail(PDEPHI_ERR_UNSUPPORTED, "block_tail_bwd: the fused projection takes 1..%d outputs, got %d", blk::MAXP, n_out);
+  {
+    const ProjArgs pr{Wp, nullptr, nullptr, n_out};
+    rc = check_lift(lf, &pr, "block_tail_bwd");
+    if (rc) return rc;
+  }
   const long long tpb = S / blk::TS, ntiles = tpb * B;
   const size_t smem = blk::bwd_smem().total + 1024;
   int sms = num_sms();
@@ -708,14 +783,16 @@ static int block_tail_bwd_launch(const float* g, const float* u, const float* h,
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   {
     ProfScope ps(K_BLOCK_TAIL_BWD, st);
-#define PDEPHI_BWD_LAUNCH(GG, WW)                                                                                          \
+#define PDEPHI_BWD_LAUNCH(GG, WW, HH)                                                                                      \
     {                                                                                                                      \
-      auto k = blk::block_tail_bwd_kernel<GG, WW>;                                                                         \
+      auto k = blk::block_tail_bwd_kernel<GG, WW, HH>;                                                                     \
       PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
-      k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out); \
+      k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out,  \
+                                          lf.Win, lf.bin, lf.n);                                                           \
     }
-    if (Wp) { if (t) PDEPHI_BWD_LAUNCH(true, true) else PDEPHI_BWD_LAUNCH(true, false) }
-    else { if (t) PDEPHI_BWD_LAUNCH(false, true) else PDEPHI_BWD_LAUNCH(false, false) }
+    if (lf.Win) { if (t) PDEPHI_BWD_LAUNCH(false, true, true) else PDEPHI_BWD_LAUNCH(false, false, true) }
+    else if (Wp) { if (t) PDEPHI_BWD_LAUNCH(true, true, false) else PDEPHI_BWD_LAUNCH(true, false, false) }
+    else { if (t) PDEPHI_BWD_LAUNCH(false, true, false) else PDEPHI_BWD_LAUNCH(false, false, false) }
 #undef PDEPHI_BWD_LAUNCH
   }
   PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
@@ -738,7 +815,18 @@ extern "C" int pdephi_block_tail_fwd(const float* h, const float* spec, const fl
   PDEPHI_REQUIRE(h && spec && Wc && u && hout, "block_tail_fwd: null pointer");
   int rc = check_shape(B, Cc, S, "block_tail_fwd");
   if (rc) return rc;
-  return block_tail_fwd_launch(h, spec, Wc, bc, u, hout, B, S, ProjArgs{nullptr, nullptr, nullptr, 0}, (cudaStream_t)stream);
+  return block_tail_fwd_launch(h, spec, Wc, bc, u, hout, B, S, ProjArgs{nullptr, nullptr, nullptr, 0}, LiftArgs{nullptr, nullptr, 0},
+                               (cudaStream_t)stream);
+}
+
+extern "C" int pdephi_block_tail_lift_fwd(const float* x, const float* Win, const float* bin, int n_in, const float* spec,
+                                          const float* Wc, const float* bc, float* u, float* hout, int B, int Cc, long long S,
+                                          pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(x && Win && spec && Wc && u && hout, "block_tail_lift_fwd: null pointer");
+  int rc = check_shape(B, Cc, S, "block_tail_lift_fwd");
+  if (rc) return rc;
+  return block_tail_fwd_launch(x, spec, Wc, bc, u, hout, B, S, ProjArgs{nullptr, nullptr, nullptr, 0}, LiftArgs{Win, bin, n_in},
+                               (cudaStream_t)stream);
 }
 
 extern "C" int pdephi_block_tail_proj_fwd(const float* h, const float* spec, const float* Wc, const float* bc, float* u,
@@ -747,19 +835,30 @@ extern "C" int pdephi_block_tail_proj_fwd(const float* h, const float* spec, con
   PDEPHI_REQUIRE(h && spec && Wc && u && hout && Wp && out, "block_tail_proj_fwd: null pointer");
   int rc = check_shape(B, Cc, S, "block_tail_proj_fwd");
   if (rc) return rc;
-  return block_tail_fwd_launch(h, spec, Wc, bc, u, hout, B, S, ProjArgs{Wp, bp, out, n_out}, (cudaStream_t)stream);
+  return block_tail_fwd_launch(h, spec, Wc, bc, u, hout, B, S, ProjArgs{Wp, bp, out, n_out}, LiftArgs{nullptr, nullptr, 0},
+                               (cudaStream_t)stream);
 }
 
 extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t,
                                      float* dWc, float* dbc, int B, int Cc, long long S, void* workspace,
                                      size_t workspace_bytes, pdephi_stream_t stream) {
   PDEPHI_REQUIRE(g && u && h && Wc && gu && dWc, "block_tail_bwd: null pointer");     /* t may be NULL: not stored */
-  return block_tail_bwd_launch(g, u, h, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, nullptr, 0, (cudaStream_t)stream);
+  return block_tail_bwd_launch(g, u, h, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, nullptr, 0,
+                               LiftArgs{nullptr, nullptr, 0}, (cudaStream_t)stream);
+}
+
+extern "C" int pdephi_block_tail_lift_bwd(const float* g, const float* u, const float* x, const float* Win, const float* bin,
+                                          int n_in, const float* Wc, float* gu, float* t, float* dWc, float* dbc, int B, int Cc,
+                                          long long S, void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(g && u && x && Win && Wc && gu && dWc, "block_tail_lift_bwd: null pointer");     /* t may be NULL */
+  return block_tail_bwd_launch(g, u, x, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, nullptr, 0,
+                               LiftArgs{Win, bin, n_in}, (cudaStream_t)stream);
 }
 
 extern "C" int pdephi_block_tail_proj_bwd(const float* gout, const float* Wp, int n_out, const float* u, const float* h,
                                           const float* Wc, float* gu, float* t, float* dWc, float* dbc, int B, int Cc, long long S,
                                           void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
   PDEPHI_REQUIRE(gout && Wp && u && h && Wc && gu && dWc, "block_tail_proj_bwd: null pointer");   /* t may be NULL */
-  return block_tail_bwd_launch(gout, u, h, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, Wp, n_out, (cudaStream_t)stream);
+  return block_tail_bwd_launch(gout, u, h, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, Wp, n_out,
+                               LiftArgs{nullptr, nullptr, 0}, (cudaStream_t)stream);
 }

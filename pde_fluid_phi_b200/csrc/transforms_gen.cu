@@ -968,7 +968,7 @@ int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0,
 
 int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const float* bzimg, const float* Wc, const float* bc,
                                 float* u, float* hout, int B, long long S, const float* Wp, const float* bp, float* proj_out,
-                                int n_out, cudaStream_t st);
+                                int n_out, const float* Win, const float* bin, int n_in, cudaStream_t st);
 
 // The fused block forward is available when the per-axis kernels cover the shape and a 128-point tile of the block
 // tail is exactly one z line.
@@ -993,15 +993,24 @@ extern "C" size_t pdephi_block_spectral_fwd_workspace_bytes(pdephi_plan_t plan, 
 
 static int block_spectral_run(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
                               long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u, float* hout,
-                              const float* Wp, const float* bp, int n_out, float* proj_out, int B, int C, void* workspace,
-                              size_t workspace_bytes, pdephi_stream_t stream);
+                              const float* Wp, const float* bp, int n_out, float* proj_out, const float* Win, const float* bin,
+                              int n_in, int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
 
 extern "C" int pdephi_block_spectral_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
                                          long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u,
                                          float* hout, int B, int C, void* workspace, size_t workspace_bytes,
                                          pdephi_stream_t stream) {
-  return block_spectral_run(plan, Y, mode_scale, row_scale, row_scale_stride, h, Wc, bc, u, hout, nullptr, nullptr, 0, nullptr, B, C,
-                            workspace, workspace_bytes, stream);
+  return block_spectral_run(plan, Y, mode_scale, row_scale, row_scale_stride, h, Wc, bc, u, hout, nullptr, nullptr, 0, nullptr,
+                            nullptr, nullptr, 0, B, C, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pdephi_block_spectral_lift_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                                              long long row_scale_stride, const float* x, const float* Win, const float* bin,
+                                              int n_in, const float* Wc, const float* bc, float* u, float* hout, int B, int C,
+                                              void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(x && Win, "block_spectral_lift_fwd: null pointer");
+  return block_spectral_run(plan, Y, mode_scale, row_scale, row_scale_stride, x, Wc, bc, u, hout, nullptr, nullptr, 0, nullptr, Win,
+                            bin, n_in, B, C, workspace, workspace_bytes, stream);
 }
 
 extern "C" int pdephi_block_spectral_proj_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
@@ -1009,14 +1018,14 @@ extern "C" int pdephi_block_spectral_proj_fwd(pdephi_plan_t plan, const float* Y
                                               float* u, float* hout, const float* Wp, const float* bp, int n_out, float* out,
                                               int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
   PDEPHI_REQUIRE(Wp && out, "block_spectral_proj_fwd: null pointer");
-  return block_spectral_run(plan, Y, mode_scale, row_scale, row_scale_stride, h, Wc, bc, u, hout, Wp, bp, n_out, out, B, C,
-                            workspace, workspace_bytes, stream);
+  return block_spectral_run(plan, Y, mode_scale, row_scale, row_scale_stride, h, Wc, bc, u, hout, Wp, bp, n_out, out, nullptr,
+                            nullptr, 0, B, C, workspace, workspace_bytes, stream);
 }
 
 static int block_spectral_run(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
                               long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u, float* hout,
-                              const float* Wp, const float* bp, int n_out, float* proj_out, int B, int C, void* workspace,
-                              size_t workspace_bytes, pdephi_stream_t stream) {
+                              const float* Wp, const float* bp, int n_out, float* proj_out, const float* Win, const float* bin,
+                              int n_in, int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
   const Plan* p = (const Plan*)plan;
   PDEPHI_REQUIRE(p && Y && h && Wc && u && hout, "block_spectral_fwd: null pointer");
   if (!block_spectral_ok(p, C))
@@ -1051,5 +1060,5 @@ static int block_spectral_run(pdephi_plan_t plan, const float* Y, const float* m
                              K_GEN_AXIS_SYNTHESIS, st);
   if (rc) return rc;
   return block_tail_fwd_fused_launch(h, V, g.ldz, g.zs[PDEPHI_FORWARD], Wc, bc, u, hout, B, (long long)p->Nx * p->Ny * p->Nz, Wp, bp,
-                                     proj_out, n_out, st);
+                                     proj_out, n_out, Win, bin, n_in, st);
 }

@@ -214,15 +214,23 @@ def head_supported(linear) -> bool:
             and linear.weight.is_cuda and linear.weight.dtype == torch.float32)
 
 
-def block_tail_fwd(h, spec, Wc, bc, head=None):
+def block_tail_fwd(h, spec, Wc, bc, head=None, lift=None):
     """u = spec + (Wc h + bc) + h, hout = gelu(u) on [B,64,...] tensors (tcgen05 TF32 channel GEMM, fused epilogue).
-    head = (Wp [n,64], bp [n] | None): additionally returns out = Wp hout + bp, computed in the same epilogue."""
-    B, C = h.shape[:2]
+    head = (Wp [n,64], bp [n] | None): additionally returns out = Wp hout + bp, computed in the same epilogue.
+    lift = (Win [64,n_in], bin | None): `h` is the model input x [B,n_in,...] and the block's input Win x + bin is generated
+    inside the kernel (never materialised)."""
+    B = h.shape[0]
+    C = spec.shape[1]
     S = h[0, 0].numel()
     lib = _cabi.load()
     with _cabi.on_device(h.device):
-        u = torch.empty_like(h)
-        hout = torch.empty_like(h)
+        u = torch.empty_like(spec)
+        hout = torch.empty_like(spec)
+        if lift is not None:
+            Win, bin_ = lift
+            _cabi.check(lib.pdephi_block_tail_lift_fwd(_p(h), _p(Win), _p(bin_), Win.shape[1], _p(spec), _p(Wc), _p(bc), _p(u),
+                                                       _p(hout), B, C, S, _stream()), "block_tail_lift_fwd")
+            return u, hout
         if head is None:
             _cabi.check(lib.pdephi_block_tail_fwd(_p(h), _p(spec), _p(Wc), _p(bc), _p(u), _p(hout), B, C, S, _stream()),
                         "block_tail_fwd")
@@ -234,28 +242,34 @@ def block_tail_fwd(h, spec, Wc, bc, head=None):
     return u, hout, out
 
 
-def block_spectral_supported(h: torch.Tensor, modes_h, precision: int) -> bool:
+def block_spectral_supported(h: torch.Tensor, modes_h, precision: int, width: int = None) -> bool:
     """Whole spectral-synthesis + block-tail forward in one chain with `spec` never materialised (pdephi_block_spectral_fwd):
     single-pass TF32 route, width 64, Nz = 128, shapes of the per-axis tensor-core kernels."""
-    if precision != _cabi.PREC_TF32 or h.shape[1] != 64:
+    if precision != _cabi.PREC_TF32 or (width if width is not None else h.shape[1]) != 64:
         return False
     with _cabi.on_device(h.device):
         plan = _cabi.get_plan(h.device.index, tuple(h.shape[2:]), modes_h)
         return bool(_cabi.load().pdephi_block_spectral_supported(plan, 64))
 
 
-def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None):
+def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None, lift=None):
     """u = S(Y * mode_scale * row_scale) + (Wc h + bc) + h, hout = gelu(u): x / y stages of the synthesis as per-axis
     tensor-core contractions, z stage inside the block-tail kernel.  head: see block_tail_fwd."""
-    B, C = h.shape[:2]
+    B, C = Y.shape[:2]
     lib = _cabi.load()
     rs_stride = row_scale.stride(0) if row_scale is not None else 0
     with _cabi.on_device(h.device):
         plan = _cabi.get_plan(h.device.index, tuple(h.shape[2:]), tuple(Y.shape[2:]))
-        u = torch.empty_like(h)
-        hout = torch.empty_like(h)
+        u = torch.empty((B, C, *h.shape[2:]), dtype=torch.float32, device=h.device)
+        hout = torch.empty_like(u)
         nbytes = lib.pdephi_block_spectral_fwd_workspace_bytes(plan, B, C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+        if lift is not None:            # h is the model input x; the block's input Win x + bin is generated in the kernel
+            Win, bin_ = lift
+            _cabi.check(lib.pdephi_block_spectral_lift_fwd(plan, _p(Y), _p(mode_scale), _p(row_scale), rs_stride, _p(h), _p(Win),
+                                                           _p(bin_), Win.shape[1], _p(Wc), _p(bc), _p(u), _p(hout), B, C, _p(ws),
+                                                           nbytes, _stream()), "block_spectral_lift_fwd")
+            return u, hout
         if head is None:
             _cabi.check(lib.pdephi_block_spectral_fwd(plan, _p(Y), _p(mode_scale), _p(row_scale), rs_stride, _p(h), _p(Wc), _p(bc),
                                                       _p(u), _p(hout), B, C, _p(ws), nbytes, _stream()), "block_spectral_fwd")
@@ -268,21 +282,25 @@ def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None):
     return u, hout, out
 
 
-def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None, write_t: bool = True):
+def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None, write_t: bool = True, lift=None):
     """gu = g gelu'(u), t = gu + Wc^T gu, dWc = sum gu (x) h, dbc = sum gu.
     head_w = Wp [n,64]: `g` is the gradient of the fused output projection's result, [B,n,...]; the block's incoming
     gradient Wp^T g is generated inside the kernel."""
-    B, C = h.shape[:2]
-    S = h[0, 0].numel()
+    B, C = u.shape[:2]
+    S = u[0, 0].numel()
     lib = _cabi.load()
     with _cabi.on_device(h.device):
-        gu = torch.empty_like(h)
-        t = torch.empty_like(h) if write_t else None
+        gu = torch.empty_like(u)
+        t = torch.empty_like(u) if write_t else None
         dW = torch.empty((C, C), dtype=torch.float32, device=h.device)
         db = torch.empty(C, dtype=torch.float32, device=h.device) if want_bias else None
         nbytes = lib.pdephi_block_tail_bwd_workspace_bytes(C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
-        if head_w is None:
+        if lift is not None:            # h is the model input x: the block's input is regenerated inside the kernel
+            Win, bin_ = lift
+            _cabi.check(lib.pdephi_block_tail_lift_bwd(_p(g), _p(u), _p(h), _p(Win), _p(bin_), Win.shape[1], _p(Wc), _p(gu), _p(t),
+                                                       _p(dW), _p(db), B, C, S, _p(ws), nbytes, _stream()), "block_tail_lift_bwd")
+        elif head_w is None:
             _cabi.check(lib.pdephi_block_tail_bwd(_p(g), _p(u), _p(h), _p(Wc), _p(gu), _p(t), _p(dW), _p(db), B, C, S, _p(ws),
                                                   nbytes, _stream()), "block_tail_bwd")
         else:
@@ -723,18 +741,12 @@ def pointwise_linear_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
 def _lift_forward(x, Win, bin_, modes_h, precision):
     x = x.contiguous()
     Win = Win.contiguous()
-    B, Cin = x.shape[:2]
-    Cout = Win.shape[0]
     S = x[0, 0].numel()
-    lib = _cabi.load()
-    with _cabi.on_device(x.device):
-        h = torch.empty((B, Cout, *x.shape[2:]), dtype=torch.float32, device=x.device)
-        _cabi.check(lib.pdephi_pointwise_linear(_p(x), _p(Win), _p(bin_), _p(h), B, Cin, Cout, S, 0, _stream()), "pointwise_linear")
     Ax = analysis(x, modes_h, _cabi.FORWARD, precision)                          # [B, Cin, mx, my, mzh]
     X = torch.einsum("cj,bjxyz->bcxyz", Win.to(torch.complex64), Ax).contiguous()    # a few MB: glue, not a pass over a volume
     if bin_ is not None:
         X[:, :, 0, 0, 0] += bin_ * float(S)
-    return x, h, Ax, X
+    return x, Win, Ax, X       # h0 = Win x + bin itself is generated tile by tile inside the block-tail kernels
 
 
 def _lift_backward(x, Ax, gu, dX, Wc, has_bias):
@@ -799,23 +811,26 @@ class RationalBlockFn(torch.autograd.Function):
             mask, monoP, monoQ = sl.local_modes(mask, modes_h), sl.local_modes(monoP, modes_h, 1), sl.local_modes(monoQ, modes_h, 1)
         lifted = Win is not None
         x_in = Ax = None
+        lift = None
         if lifted:
-            x_in, h, Ax, X = _lift_forward(h, Win, bin_, modes_h, precision)
+            x_in, Win, Ax, X = _lift_forward(h, Win, bin_, modes_h, precision)
+            h = x_in
+            lift = (Win, bin_.contiguous() if bin_ is not None else None)
         else:
             X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
         need_grad = any(ctx.needs_input_grad)
         Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
         stats = sl.complete_stats(stats, eps)
         head = _head_tuple(Wp, bp)
-        if not sl.active and block_spectral_supported(h, modes_h, precision):
-            res = block_spectral_fwd(Y, mask, stats[:, 2], h, Wc, bc, head)    # `spec` never touches HBM
+        if not sl.active and block_spectral_supported(h, modes_h, precision, Y.shape[1]):
+            res = block_spectral_fwd(Y, mask, stats[:, 2], h, Wc, bc, head, lift)    # `spec` never touches HBM
         else:
             spec = sl.synthesis(Y, grid, mask, stats[:, 2], None, None, _cabi.FORWARD, precision)
-            res = block_tail_fwd(h, spec, Wc, bc, head)
+            res = block_tail_fwd(h, spec, Wc, bc, head, lift)
         u, hout = res[0], res[1]
         if need_grad:
             ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc, *((hout, head[0]) if head else ()),
-                                  *((x_in, Ax, Win) if lifted else ()))
+                                  *((Ax, Win, *((lift[1],) if lift[1] is not None else ())) if lifted else ()))
         ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, bc is not None, sl, head is not None,
                     bp is not None, lifted, bin_ is not None)
         return res[2] if head else hout
@@ -836,14 +851,18 @@ class RationalBlockFn(torch.autograd.Function):
             hout, Wp = ctx.saved_tensors[nsaved:nsaved + 2]
             nsaved += 2
             dWp, dbp = _head_param_grads(hout, g, Wp, head_bias)
-        gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh)
+        lift = None
+        if lifted:        # h is the model input x here
+            Ax, Win = ctx.saved_tensors[nsaved:nsaved + 2]
+            lift = (Win, ctx.saved_tensors[nsaved + 2] if lift_bias else None)
+            x_in = h
+        gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
         dZ = sl.analysis(gu, modes_h, _cabi.ADJOINT, precision)
         dY = sl.projection_bwd(dZ, Y, mask, stats)
         dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
         sl.finish_coeff_grads(dP, dQ)
         dh = None
         if lifted:
-            x_in, Ax, Win = ctx.saved_tensors[nsaved:nsaved + 3]
             if skip_dh:
                 dWin, dbin = _lift_backward(x_in, Ax, gu, dX, Wc, lift_bias)
             else:         # the input wants its gradient: materialise gh0 and run the lift's own backward on it
@@ -870,19 +889,23 @@ class ComplexBlockFn(torch.autograd.Function):
         Wl, Wc = _local_weights(W, sl, my), Wc.contiguous()
         lifted = Win is not None
         x_in = Ax = None
+        lift = None
         if lifted:
-            x_in, h, Ax, X = _lift_forward(h, Win, bin_, modes_h, precision)
+            x_in, Win, Ax, X = _lift_forward(h, Win, bin_, modes_h, precision)
+            h = x_in
+            lift = (Win, bin_.contiguous() if bin_ is not None else None)
         else:
             X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
         Y = complex_mix_fwd(X, Wl, modes_h[2])
         head = _head_tuple(Wp, bp)
-        if not sl.active and block_spectral_supported(h, modes_h, precision):
-            res = block_spectral_fwd(Y, None, None, h, Wc, bc, head)
+        if not sl.active and block_spectral_supported(h, modes_h, precision, Y.shape[1]):
+            res = block_spectral_fwd(Y, None, None, h, Wc, bc, head, lift)
         else:
             spec = sl.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, precision)
-            res = block_tail_fwd(h, spec, Wc, bc, head)
+            res = block_tail_fwd(h, spec, Wc, bc, head, lift)
         u, hout = res[0], res[1]
-        ctx.save_for_backward(X, Wl, W, u, h, Wc, *((hout, head[0]) if head else ()), *((x_in, Ax, Win) if lifted else ()))
+        ctx.save_for_backward(X, Wl, W, u, h, Wc, *((hout, head[0]) if head else ()),
+                              *((Ax, Win, *((lift[1],) if lift[1] is not None else ())) if lifted else ()))
         ctx.meta = (modes_h, grid, precision, bc is not None, sl, head is not None, bp is not None, lifted, bin_ is not None)
         return res[2] if head else hout
 
@@ -901,14 +924,18 @@ class ComplexBlockFn(torch.autograd.Function):
             hout, Wp = ctx.saved_tensors[nsaved:nsaved + 2]
             nsaved += 2
             dWp, dbp = _head_param_grads(hout, g, Wp, head_bias)
-        gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh)
+        lift = None
+        if lifted:
+            Ax, Win = ctx.saved_tensors[nsaved:nsaved + 2]
+            lift = (Win, ctx.saved_tensors[nsaved + 2] if lift_bias else None)
+            x_in = h
+        gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
         dY = sl.analysis(gu, modes_h, _cabi.ADJOINT, precision)
         dX, dW = complex_mix_bwd(X, Wl, dY, modes_h[2])
         sl.finish_coeff_grads(dW)
         dW = _scatter_weight_grad(dW, W, sl, modes_h[1])
         dh = None
         if lifted:
-            x_in, Ax, Win = ctx.saved_tensors[nsaved:nsaved + 3]
             if skip_dh:
                 dWin, dbin = _lift_backward(x_in, Ax, gu, dX, Wc, lift_bias)
             else:
