@@ -358,8 +358,15 @@ def run_native(args):
         act = 4.0 * B * C * n ** 3                       # one full-size fp32 activation
         mid = 8.0 * B * C * n * my * mzh                 # [BC,Nx,my,mzh] complex intermediate
         modes_b = 8.0 * B * C * mx * my * mzh            # retained modes
+        # The first block takes the input lift (its forward analysis reads the 3-channel input, its block tail generates
+        # h0 and, in the backward, stores no t) and the last block the output projection (its backward generates g'):
+        # per-launch algorithmic bytes of those kernels are averages over the L layers' launches of one step.
+        L = CFG["n_layers"]
+        fused_ends = bool(getattr(model, "fuse_lift", False) and getattr(model, "fuse_head", False)) and args.precision == "tf32"
+        cin = 3
+        a_launch = ((2 * L - 1) + cin / C) / (2 * L) if fused_ends else 1.0          # analysis: 2L launches, one on cin channels
         alg = {
-            "analysis_zy_tc_kernel": act + mid, "analysis_zy_kernel": act + mid, "analysis_zy_tc3_kernel": act + mid,
+            "analysis_zy_tc_kernel": (act + mid) * a_launch, "analysis_zy_kernel": act + mid, "analysis_zy_tc3_kernel": act + mid,
             "synthesis_zy_tc3_kernel": act + mid + 1.5 * act,   # unfused block route: forward fuses both skip addends, adjoint one
             "analysis_x_tc3_kernel": mid + modes_b, "synthesis_x_tc3_kernel": mid + modes_b,
             # fused block route: the forward synthesis lives in block_spectral_fwd_kernel, so every launch of this kernel is
@@ -368,8 +375,11 @@ def run_native(args):
             "synthesis_zy_kernel": act + mid + 1.5 * act,   # fp32 route: forward fuses both skip addends, adjoint one
             "block_tail_fwd_kernel": 4 * act,            # read h, spec; write u, h'
             # fused forward: read h and V [B,Nx,Ny,64,ldz] (ldz = 2*mzh rounded up to 4 floats); write u, h'
-            "block_spectral_fwd_kernel": 3 * act + 4.0 * B * C * n * n * ((2 * mzh + 3) // 4 * 4),
-            "block_tail_bwd_kernel": 5 * act,            # read g', u, h; write gu, t
+            # (first block: h generated from the input, one activation less)
+            "block_spectral_fwd_kernel": (3 * act * (L - 1) + 2 * act) / L + 4.0 * B * C * n * n * ((2 * mzh + 3) // 4 * 4)
+            if fused_ends else 3 * act + 4.0 * B * C * n * n * ((2 * mzh + 3) // 4 * 4),
+            # read g', u, h; write gu, t -- first block: no h read, no t write (3 activations); last block: g' generated (4)
+            "block_tail_bwd_kernel": (5 * act * (L - 2) + 3 * act + 4 * act) / L if fused_ends else 5 * act,
             "analysis_x_tc_kernel": mid + modes_b, "synthesis_x_tc_kernel": mid + modes_b,
         }
         per_kernel = {k: {"launches": v[0], "ms_total": round(v[1], 3), "share_of_step": round(v[1] / total_ms, 4)}
@@ -389,10 +399,14 @@ def run_native(args):
         hot = [k for k in ("analysis_zy_tc_kernel", "analysis_zy_tc3_kernel", "analysis_zy_kernel") if k in rooflines]
         dom = max(rooflines, key=lambda k: prof[k][1]) if rooflines else None
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
-        ncu_traffic = {"analysis_zy_tc_kernel": 4.580e9, "synthesis_zy_tc_kernel": None, "block_tail_fwd_kernel": 17.187e9,
+        # (captures of the middle blocks' launches: the full-size variants of each kernel)
+        ncu_traffic = {"analysis_zy_tc_kernel": 4.580e9, "synthesis_zy_tc_kernel": 8.822e9, "block_tail_fwd_kernel": 17.187e9,
                        "block_tail_bwd_kernel": 21.489e9, "block_spectral_fwd_kernel": 14.093e9}
         for k in rooflines:
             rooflines[k]["traffic"] = ncu_traffic.get(k)
+            if fused_ends and k in ("block_tail_bwd_kernel", "block_spectral_fwd_kernel"):
+                rooflines[k]["traffic_note"] = ("ncu dram bytes of a middle block's launch; algorithmic_bytes_per_launch is the mean "
+                                                "over the step's launches (the first / last block's launches move fewer activations)")
         roof = None
         if dom:
             roof = dict(rooflines[dom], kernel=dom, peak_source=which,
