@@ -564,19 +564,17 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
     for (int r = 0; r < 4; ++r) xc[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 3) ^ r) & 3) << 5) + (lane & 7) * 4);
 #pragma unroll
     for (int r = 0; r < 8; ++r) xk[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 2) ^ r) & 7) << 4) + (lane & 3) * 4);
-    for (long long it = 0; it < my_tiles; ++it) {
+    // ---- step 1: gu = g' * gelu'(u) (this warp: channels [16*part, +16), points [32q, +32)).  gu replaces g' in place
+    //      (MN layout, operand of the Wc^T gu GEMM) and u in place (K layout, operand of the dWc GEMM), goes to HBM, and
+    //      stays in registers (r) for the epilogue ----
+    auto step1 = [&](long long it, float* r) {
       const long long t = tile0 + it * tstep;
       const int s = (int)(it % B_STAGES), d = (int)(it & 1);
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       uint8_t* tg = sm + L.stage[s];
       uint8_t* tgk = tg + 2 * TILE;
-      const size_t g0 = ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
-      // ---- step 1: gu = g' * gelu'(u) (this warp: channels [16*part, +16), points [32q, +32)).  gu replaces g' in place
-      //      (MN layout, operand of the Wc^T gu GEMM) and u in place (K layout, operand of the dWc GEMM), goes to HBM, and
-      //      stays in registers for the epilogue ----
       mbar_wait(bar(BB_FULL + s), (uint32_t)((it / B_STAGES) & 1));
-      float r[CPW];
-      float* gp = gu_out + g0;
+      float* gp = gu_out + ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
 #pragma unroll
       for (int j = 0; j < CPW; ++j) {
         const uint32_t off = xc[j & 3] + j * 128, offk = xk[j & 7] + j * 128;
@@ -592,22 +590,41 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BB_GUREADY + d));
-      // ---- epilogue: t[c][s] = (Wc^T gu)[c][s] + gu[c][s] ----
+    };
+    // ---- epilogue: t[c][s] = (Wc^T gu)[c][s] + gu[c][s] ----
+    auto epilogue = [&](long long it, const float* r) {
+      const long long t = tile0 + it * tstep;
+      const int d = (int)(it & 1);
+      const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       mbar_wait(bar(BB_TFULL + d), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       float v[CPW];
-      tmem_ld16(tmem_t[d] + lane_base + part * CPW, v);
-      tmem_ld_wait();
+      if (WT) {
+        tmem_ld16(tmem_t[d] + lane_base + part * CPW, v);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BB_TEMPTY + d));
       if (WT) {
-        float* tp = t_out + g0;
+        float* tp = t_out + ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
 #pragma unroll
         for (int j = 0; j < CPW; ++j) {
           __stcs(tp, v[j] + r[j]);
           tp += S;
         }
+      }
+    };
+    // Step 1 of tile i+1 runs BEFORE the epilogue of tile i: the Wc^T gu GEMM of tile i (and its commit / barrier round
+    // trip, ~1000 clocks) is then hidden behind useful work instead of being waited for by all sixteen warps.
+    float ra[CPW], rb[CPW];
+    if (my_tiles > 0) step1(0, ra);
+    for (long long it = 0; it < my_tiles; it += 2) {
+      if (it + 1 < my_tiles) step1(it + 1, rb);
+      epilogue(it, ra);
+      if (it + 1 < my_tiles) {
+        if (it + 2 < my_tiles) step1(it + 2, ra);
+        epilogue(it + 1, rb);
       }
     }
     // ---- per-CTA partials: dbias (registers -> warp shuffle -> 4 quarter-warps summed in order) and dW (TMEM) ----
