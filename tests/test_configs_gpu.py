@@ -144,3 +144,23 @@ def test_cfg5_operator_on_256_cubed(precision, out_tol, grad_tol):
     if precision == "tf32":
         assert _cabi.load().pdephi_plan_supports(_cabi.get_plan(torch.cuda.current_device(), (256, 256, 256), (64, 64, 33)),
                                                  _cabi.PREC_TF32) == 1
+
+
+def test_cfg5_full_size_adjointness_on_the_tensor_core_route():
+    """configs[4] at its full layer size [1, 64, 256^3], modes 64^3, on the per-axis tcgen05 route: <A x, Z> == <x, A^H Z>
+    (size-independent property; the transform pair is what the layer's forward and backward are built from), and the
+    normalised pair inverts itself on Hermitian-consistent modes."""
+    torch.manual_seed(2)
+    grid, mh = (256, 256, 256), (64, 64, 33)
+    x = torch.randn(1, 64, *grid, device=DEV)
+    Z = torch.randn(1, 64, *mh, device=DEV, dtype=torch.complex64)
+    Ax = pf.analysis(x, mh, precision=_cabi.PREC_TF32)
+    AhZ = pf.synthesis(Z, grid, direction=_cabi.ADJOINT, precision=_cabi.PREC_TF32)
+    lhs = (Ax.conj().to(torch.complex128) * Z.to(torch.complex128)).sum().real
+    rhs = (x.double() * AhZ.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-3 * abs(float(lhs))
+    del x, AhZ, Ax
+    Zc = Z.clone()
+    Zc[..., 0] = 0                     # kz = 0 plane is not Hermitian in general: irfftn drops its imaginary part
+    back = pf.analysis(pf.synthesis(Zc, grid, precision=_cabi.PREC_TF32), mh, precision=_cabi.PREC_TF32)
+    assert rel(back[..., 1:], Zc[..., 1:]) < 2e-3
