@@ -67,6 +67,11 @@ def _lift(x: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
         raise RuntimeError(f"input has {x.shape[1]} channels, the model was built for {linear.in_features}")
     if pointwise_linear_supported(x, linear.weight):
         return library_call(PointwiseLinearFn, x, linear.weight, linear.bias)
+    if x.is_cuda and x.dtype == torch.float32:
+        # wide -> wide (MultiScaleFNO's inner operators, in = out = width): a plain library GEMM on the channels-first
+        # layout (cuDNN 1x1x1 convolution, fp32 like the reference's Linear) instead of two permuted copies around one
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return F.conv3d(x, linear.weight.view(linear.out_features, linear.in_features, 1, 1, 1), linear.bias)
     return linear(x.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
 
 

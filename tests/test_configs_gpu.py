@@ -164,3 +164,20 @@ def test_cfg5_full_size_adjointness_on_the_tensor_core_route():
     Zc[..., 0] = 0                     # kz = 0 plane is not Hermitian in general: irfftn drops its imaginary part
     back = pf.analysis(pf.synthesis(Zc, grid, precision=_cabi.PREC_TF32), mh, precision=_cabi.PREC_TF32)
     assert rel(back[..., 1:], Zc[..., 1:]) < 2e-3
+
+
+def test_cfg4_operator_with_wide_input_and_output():
+    """MultiScaleFNO's inner operators have in_channels = out_channels = width (multiscale_fno.py:100-127): the lift and
+    the projection are then wide channel GEMMs, run channels-first without the reference's permuted copies."""
+    torch.manual_seed(1234)
+    w, modes = 16, (8, 8, 8)
+    model = pb.RationalFourierOperator3D(modes=modes, width=w, n_layers=1, in_channels=w, out_channels=w, rational_order=(2, 2))
+    with torch.no_grad():
+        layer = model.rational_layers[0]
+        q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+        layer.Q_coeffs.mul_(1e-3)
+        layer.Q_coeffs[..., 0, 0, 0] = q0
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(2, w, 16, 16, 16, generator=g)
+    y = torch.randn(2, w, 16, 16, 16, generator=g)
+    compare_model(model, lambda xx, sd: so.rfno3d_forward(xx, sd, modes, 1), x, y)
