@@ -259,31 +259,34 @@ projection_bwd_kernel(const float2* __restrict__ dZ, const float2* __restrict__ 
 // exactly once (thread = mode k, IT input channels x BT batch entries per thread).
 // ---------------------------------------------------------------------------------------------
 constexpr int IT = 4;
+// BTV: batch entries per thread (8 for training batches; 1 / 2 / 4 for the small batches of the 256^3 configurations,
+// where a fixed 8 spent 7/8 of the FMAs and registers on zeros)
+template <int BTV>
 __global__ void __launch_bounds__(MIX_THREADS, 4)
 mix_from_R_kernel(const float2* __restrict__ dY, float2* __restrict__ dX, const float* __restrict__ R, int B, int I,
                   int O, long long M) {
   const long long k = (long long)blockIdx.x * MIX_THREADS + threadIdx.x;
   const long long kc = k < M ? k : M - 1;
   const int i0 = blockIdx.y * IT;
-  for (int b0 = 0; b0 < B; b0 += BT) {
-    float2 acc[IT][BT];
+  for (int b0 = 0; b0 < B; b0 += BTV) {
+    float2 acc[IT][BTV];
 #pragma unroll
     for (int a = 0; a < IT; ++a)
 #pragma unroll
-      for (int j = 0; j < BT; ++j) acc[a][j] = make_float2(0.f, 0.f);
-#pragma unroll 2
+      for (int j = 0; j < BTV; ++j) acc[a][j] = make_float2(0.f, 0.f);
+#pragma unroll(BTV >= 8 ? 2 : 8)      // few batch entries: more o steps in flight instead
     for (int o = 0; o < O; ++o) {
       float r[IT];
 #pragma unroll
       for (int a = 0; a < IT; ++a) r[a] = __ldg(R + ((size_t)o * I + min(i0 + a, I - 1)) * M + kc);
-      float2 g[BT];
+      float2 g[BTV];
 #pragma unroll
-      for (int j = 0; j < BT; ++j)
+      for (int j = 0; j < BTV; ++j)
         g[j] = (b0 + j < B) ? __ldg(dY + ((size_t)(b0 + j) * O + o) * M + kc) : make_float2(0.f, 0.f);
 #pragma unroll
       for (int a = 0; a < IT; ++a)
 #pragma unroll
-        for (int j = 0; j < BT; ++j) {
+        for (int j = 0; j < BTV; ++j) {
           acc[a][j].x = fmaf(r[a], g[j].x, acc[a][j].x);
           acc[a][j].y = fmaf(r[a], g[j].y, acc[a][j].y);
         }
@@ -292,7 +295,7 @@ mix_from_R_kernel(const float2* __restrict__ dY, float2* __restrict__ dX, const 
 #pragma unroll
       for (int a = 0; a < IT; ++a)
 #pragma unroll
-        for (int j = 0; j < BT; ++j)
+        for (int j = 0; j < BTV; ++j)
           if (i0 + a < I && b0 + j < B) dX[((size_t)(b0 + j) * I + i0 + a) * M + k] = acc[a][j];
     }
   }
@@ -307,19 +310,21 @@ mix_from_R_kernel(const float2* __restrict__ dY, float2* __restrict__ dX, const 
 // ---------------------------------------------------------------------------------------------
 constexpr int GO = 4;   // output channels per CTA of phase A
 constexpr int GI = 2;   // input channels per inner step
-template <bool SINGLE>  // SINGLE: B <= BT, the dY values of the CTA's output channels stay in registers
+// SINGLE: B <= BTV, the dY values of the CTA's output channels stay in registers; BTV: batch entries per inner step
+// (8 for training batches, fewer for the small batches of the 256^3 configurations)
+template <bool SINGLE, int BTV = BT>
 __global__ void __launch_bounds__(MIX_THREADS, 4)
 rational_g_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, const float* __restrict__ Qe,
                   float* __restrict__ G, int B, int I, int O, long long M) {
   const long long k = (long long)blockIdx.x * MIX_THREADS + threadIdx.x;
   const long long kc = k < M ? k : M - 1;
   const int o0 = blockIdx.y * GO;
-  float2 y[GO][BT];
+  float2 y[GO][BTV];
   if (SINGLE) {
 #pragma unroll
     for (int a = 0; a < GO; ++a)
 #pragma unroll
-      for (int j = 0; j < BT; ++j)
+      for (int j = 0; j < BTV; ++j)
         y[a][j] = (j < B) ? __ldg(dY + ((size_t)j * O + min(o0 + a, O - 1)) * M + kc) : make_float2(0.f, 0.f);
   }
   const size_t iM = (size_t)I * M;
@@ -339,20 +344,20 @@ rational_g_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, c
         dR[a][c] = 0.f;
         qe[a][c] = __ldg(Qe + qrow + (size_t)min(a, O - 1 - o0) * iM + (size_t)min(i0 + c, I - 1) * M);
       }
-    for (int b0 = 0; b0 < B; b0 += BT) {
+    for (int b0 = 0; b0 < B; b0 += BTV) {
       if (!SINGLE) {
 #pragma unroll
         for (int a = 0; a < GO; ++a)
 #pragma unroll
-          for (int j = 0; j < BT; ++j)
+          for (int j = 0; j < BTV; ++j)
             y[a][j] = (b0 + j < B) ? __ldg(dY + ((size_t)(b0 + j) * O + min(o0 + a, O - 1)) * M + kc) : make_float2(0.f, 0.f);
       }
-      float2 xv[GI][BT];
+      float2 xv[GI][BTV];
 #pragma unroll
       for (int c = 0; c < GI; ++c) {
         const float2* xi = xk + (size_t)min(i0 + c, I - 1) * M + (size_t)b0 * iM;
 #pragma unroll
-        for (int j = 0; j < BT; ++j)   // entries beyond B multiply a zero dY: clamp the address, skip the predicate
+        for (int j = 0; j < BTV; ++j)   // entries beyond B multiply a zero dY: clamp the address, skip the predicate
           xv[c][j] = __ldg(xi + (size_t)min(j, B - 1 - b0) * iM);
       }
 #pragma unroll
@@ -360,7 +365,7 @@ rational_g_kernel(const float2* __restrict__ X, const float2* __restrict__ dY, c
 #pragma unroll
         for (int c = 0; c < GI; ++c)
 #pragma unroll
-          for (int j = 0; j < BT; ++j) {
+          for (int j = 0; j < BTV; ++j) {
             dR[a][c] = fmaf(xv[c][j].x, y[a][j].x, dR[a][c]);
             dR[a][c] = fmaf(xv[c][j].y, y[a][j].y, dR[a][c]);
           }
@@ -631,7 +636,10 @@ static int launch_dpq(const float2* X, const float2* dY, const float* R, const f
   {
     dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (O + GO - 1) / GO);
     ProfScope ps(K_RATIONAL_G, st);
-    if (B <= BT) rational_g_kernel<true><<<grid, MIX_THREADS, 0, st>>>(X, dY, Qe, G, B, I, O, M);
+    if (B == 1) rational_g_kernel<true, 1><<<grid, MIX_THREADS, 0, st>>>(X, dY, Qe, G, B, I, O, M);
+    else if (B == 2) rational_g_kernel<true, 2><<<grid, MIX_THREADS, 0, st>>>(X, dY, Qe, G, B, I, O, M);
+    else if (B <= 4) rational_g_kernel<true, 4><<<grid, MIX_THREADS, 0, st>>>(X, dY, Qe, G, B, I, O, M);
+    else if (B <= BT) rational_g_kernel<true><<<grid, MIX_THREADS, 0, st>>>(X, dY, Qe, G, B, I, O, M);
     else rational_g_kernel<false><<<grid, MIX_THREADS, 0, st>>>(X, dY, Qe, G, B, I, O, M);
   }
   PDEPHI_LAUNCH_CHECK("rational_g_kernel");
@@ -732,7 +740,10 @@ extern "C" int pdephi_rational_mix_bwd(const float* X, const float* dY, const fl
   {
     dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (I + IT - 1) / IT);
     ProfScope ps(K_RATIONAL_MIX_T, st);
-    mix_from_R_kernel<<<grid, MIX_THREADS, 0, st>>>((const float2*)dY, (float2*)dX, R, B, I, O, M);
+    if (B >= 5) mix_from_R_kernel<8><<<grid, MIX_THREADS, 0, st>>>((const float2*)dY, (float2*)dX, R, B, I, O, M);
+    else if (B >= 3) mix_from_R_kernel<4><<<grid, MIX_THREADS, 0, st>>>((const float2*)dY, (float2*)dX, R, B, I, O, M);
+    else if (B == 2) mix_from_R_kernel<2><<<grid, MIX_THREADS, 0, st>>>((const float2*)dY, (float2*)dX, R, B, I, O, M);
+    else mix_from_R_kernel<1><<<grid, MIX_THREADS, 0, st>>>((const float2*)dY, (float2*)dX, R, B, I, O, M);
   }
   PDEPHI_LAUNCH_CHECK("mix_from_R_kernel");
   MonoOffsets offs;
