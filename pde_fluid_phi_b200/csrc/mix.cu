@@ -85,7 +85,7 @@ constexpr int MIX_THREADS = 128;
 constexpr int UT = 4;
 constexpr int BT = 8;
 
-template <int OP, int OQ, bool TR>
+template <int OP, int OQ, bool TR, int BTV = BT>   // BTV: batch entries per thread (fewer for small batches)
 __global__ void __launch_bounds__(MIX_THREADS)
 rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float* __restrict__ P,
                     const float* __restrict__ Q, const float* __restrict__ monoP, const float* __restrict__ monoQ,
@@ -127,16 +127,16 @@ rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, con
   }
   const float* mq = (OP == OQ) ? mp : mqs;
 
-  for (int b0 = 0; b0 < B; b0 += BT) {
-    float2 acc[UT][BT];
+  for (int b0 = 0; b0 < B; b0 += BTV) {
+    float2 acc[UT][BTV];
 #pragma unroll
     for (int ul = 0; ul < UT; ++ul)
 #pragma unroll
-      for (int j = 0; j < BT; ++j) acc[ul][j] = make_float2(0.f, 0.f);
+      for (int j = 0; j < BTV; ++j) acc[ul][j] = make_float2(0.f, 0.f);
     for (int v = 0; v < V; ++v) {
-      float2 xin[BT];
+      float2 xin[BTV];
 #pragma unroll
-      for (int j = 0; j < BT; ++j)
+      for (int j = 0; j < BTV; ++j)
         xin[j] = (b0 + j < B) ? __ldg(in + ((size_t)(b0 + j) * V + v) * M + kc) : make_float2(0.f, 0.f);
 #pragma unroll
       for (int up = 0; up < UT / 2; ++up) {
@@ -164,7 +164,7 @@ rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, con
             Qeout[ri] = qe2[h];
           }
 #pragma unroll
-          for (int j = 0; j < BT; ++j) {
+          for (int j = 0; j < BTV; ++j) {
             acc[ul][j].x = fmaf(R2[h], xin[j].x, acc[ul][j].x);
             acc[ul][j].y = fmaf(R2[h], xin[j].y, acc[ul][j].y);
           }
@@ -175,7 +175,7 @@ rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, con
 #pragma unroll
       for (int ul = 0; ul < UT; ++ul)
 #pragma unroll
-        for (int j = 0; j < BT; ++j)
+        for (int j = 0; j < BTV; ++j)
           if (u0 + ul < U && b0 + j < B) out[((size_t)(b0 + j) * U + u0 + ul) * M + k] = acc[ul][j];
     }
   }
@@ -591,7 +591,9 @@ static int launch_mix(const float2* in, float2* out, const float* P, const float
                       const float* monoQ, float eps, float* Rout, float* Qeout, int B, int U, int V, long long M,
                       const MonoOffsets& offs, cudaStream_t st) {
   const size_t smem = (size_t)UT * V * (Tri<OP>::TP4 + Tri<OQ>::TP4) * sizeof(float);
-  auto k = rational_mix_kernel<OP, OQ, false>;
+  auto k = B >= 5 ? rational_mix_kernel<OP, OQ, false, 8>
+                  : (B >= 3 ? rational_mix_kernel<OP, OQ, false, 4> : (B == 2 ? rational_mix_kernel<OP, OQ, false, 2>
+                                                                              : rational_mix_kernel<OP, OQ, false, 1>));
   if (smem > 200 * 1024) return fail(PDEPHI_ERR_UNSUPPORTED, "rational_mix_fwd: %d input channels exceed shared memory", V);
   if (smem > 48 * 1024) PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (U + UT - 1) / UT);
