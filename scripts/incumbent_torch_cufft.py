@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""The incumbent on the same B200: the reference's op sequence in stock PyTorch eager (torch.fft -> cuFFT, einsum,
+elementwise ops), timed beside the library at the cfg-2 workload ("also time the reference on
+the same B200 (cuFFT path) -- that, not the CPU, is the incumbent the kernels must beat").
+
+    python scripts/incumbent_torch_cufft.py [--steps 5] [--warmup 3] [--batch 8] [--out gpurun_out/incumbent.json]
+
+The reference package cannot travel to the GPU box, so the module below restates it with plain torch ops in the
+reference's own op order (operators/rational_fourier.py:73-172,185-276, operators/stability.py:59-103); it shares no code
+with the product or with oracle/.  It measures
+  (1) one RationalFourierLayer fwd+bwd at [B,64,128^3], modes 32^3 (CUDA events, median),
+  (2) the bench.py training step (fwd + MSE + bwd + clip_grad_norm + AdamW) in samples/s,
+  (3) outputs and parameter gradients of the two whole models on the same batch and weights (relative L2),
+each for the stock incumbent and for pde_fluid_phi_b200.  A measurement script: nothing in the product imports it.
+"""
+from __future__ import annotations
+
+import argparse
+import itertools
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+from bench import CFG, turbulence_batch  # noqa: E402
+
+
+class EagerRationalLayer(nn.Module):
+    """rfftn -> slice -> P(k)/Q(k) real mix -> zero-padded spectrum -> decay mask + energy rescale on a clone -> irfftn."""
+
+    def __init__(self, width, modes, order=(4, 4), eps=1e-6):
+        super().__init__()
+        self.modes, self.eps = modes, eps
+        p, q = order
+        self.P_coeffs = nn.Parameter(torch.randn(width, width, p, p, p) * 0.02)
+        self.Q_coeffs = nn.Parameter(torch.randn(width, width, q, q, q) * 0.02)
+        with torch.no_grad():
+            self.Q_coeffs[..., 0, 0, 0] = self.Q_coeffs[..., 0, 0, 0].abs() + 1.0
+        mx, my, mz = modes
+        axes = [torch.arange(n, dtype=torch.float32) for n in (mx, my, mz // 2 + 1)]
+        k = torch.stack(torch.meshgrid(*axes, indexing="ij"))
+        self.register_buffer("k_grid", k)
+        self.register_buffer("decay_mask", (1 + torch.sqrt(k[0] ** 2 + k[1] ** 2 + k[2] ** 2) ** 2) ** (-2.0 / 2))
+
+    def poly(self, coeffs):
+        kx, ky, kz = self.k_grid
+        n = coeffs.shape[-1]
+        acc = torch.zeros(coeffs.shape[:2] + kx.shape, device=coeffs.device, dtype=coeffs.dtype)
+        for a, b, c in itertools.product(range(n), repeat=3):
+            if a + b + c < n:
+                acc = acc + coeffs[:, :, a, b, c].unsqueeze(-1).unsqueeze(-1).unsqueeze(-1) * ((kx ** a) * (ky ** b) * (kz ** c))
+        return acc
+
+    def forward(self, x):
+        mx, my, mz = self.modes
+        mzh = mz // 2 + 1
+        x_ft = torch.fft.rfftn(x, dim=[-3, -2, -1])
+        R = self.poly(self.P_coeffs) / (self.poly(self.Q_coeffs) + self.eps)
+        kept = x_ft[:, :, :mx, :my, :mzh]
+        out_ft = torch.zeros_like(x_ft)
+        out_ft[:, :, :mx, :my, :mzh] = torch.einsum("bixyz,oixyz->boxyz", kept, R.to(kept.dtype))
+        box = out_ft[:, :, :mx, :my, :mzh]
+        damped = box * self.decay_mask
+        e0 = torch.sum(torch.abs(box) ** 2, dim=(-3, -2, -1), keepdim=True)
+        e1 = torch.sum(torch.abs(damped) ** 2, dim=(-3, -2, -1), keepdim=True)
+        damped = damped * torch.sqrt((e0 + self.eps) / (e1 + self.eps))
+        proj = out_ft.clone()
+        proj[:, :, :mx, :my, :mzh] = damped
+        return torch.fft.irfftn(proj, s=x.shape[-3:], dim=[-3, -2, -1])
+
+
+class EagerOperator(nn.Module):
+    """rearrange -> Linear -> rearrange, n x gelu(spectral + conv1x1 + x), rearrange -> Linear -> rearrange."""
+
+    def __init__(self, modes, width, n_layers, order, cin=3, cout=3):
+        super().__init__()
+        self.input_proj = nn.Linear(cin, width)
+        self.output_proj = nn.Linear(width, cout)
+        self.rational_layers = nn.ModuleList([EagerRationalLayer(width, modes, order) for _ in range(n_layers)])
+        self.local_convs = nn.ModuleList([nn.Conv3d(width, width, kernel_size=1) for _ in range(n_layers)])
+
+    def forward(self, x):
+        h = self.input_proj(x.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
+        for spectral, local in zip(self.rational_layers, self.local_convs):
+            h = F.gelu(spectral(h) + local(h) + h)
+        return self.output_proj(h.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
+
+
+def condition(layers):
+    """bench.py's weight set: non-constant Q and all P coefficients x1e-4 (the default init overflows)."""
+    with torch.no_grad():
+        for layer in layers:
+            q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+            layer.Q_coeffs.mul_(1e-4)
+            layer.Q_coeffs[..., 0, 0, 0] = q0
+            layer.P_coeffs.mul_(1e-4)
+
+
+def event_times(fn, warmup, reps):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    out = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        out.append(a.elapsed_time(b))
+    return out
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-300))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=CFG["batch_per_gpu"])
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "incumbent.json"))
+    args = ap.parse_args()
+    import pde_fluid_phi_b200 as pb
+    pb.load_library()
+    dev = torch.device("cuda", 0)
+    n, B, W = CFG["grid"], args.batch, CFG["width"]
+    res = {"device": torch.cuda.get_device_name(0), "torch": torch.__version__, "batch": B,
+           "cudnn_allow_tf32": torch.backends.cudnn.allow_tf32, "matmul_allow_tf32": torch.backends.cuda.matmul.allow_tf32}
+
+    def flush():
+        with open(args.out, "w") as f:
+            json.dump(res, f, indent=1)
+
+    x = turbulence_batch(B, n, 42, dev)
+    y = turbulence_batch(B, n, 1042, dev)
+
+    # ---- (1) one layer, fwd+bwd ----------------------------------------------------------------------------------
+    torch.manual_seed(1234)
+    theirs = EagerRationalLayer(W, CFG["modes"], CFG["rational_order"]).to(dev)
+    ours = pb.RationalFourierLayer(W, W, CFG["modes"], rational_order=CFG["rational_order"]).to(dev)
+    with torch.no_grad():
+        ours.P_coeffs.copy_(theirs.P_coeffs)
+        ours.Q_coeffs.copy_(theirs.Q_coeffs)
+    condition([theirs, ours])
+    h = torch.randn(B, W, n, n, n, device=dev, requires_grad=True)
+    g = torch.randn(B, W, n, n, n, device=dev)
+
+    def layer_step(layer):
+        def run():
+            layer(h).backward(g)
+            h.grad = layer.P_coeffs.grad = layer.Q_coeffs.grad = None
+        return run
+
+    res["layer_fwd_bwd_ms"] = {"incumbent_torch_cufft": statistics.median(event_times(layer_step(theirs), 3, 10))}
+    for prec in ("tf32", "auto"):
+        ours.precision = prec
+        res["layer_fwd_bwd_ms"][f"pde_fluid_phi_b200[{prec}]"] = statistics.median(event_times(layer_step(ours), 5, 20))
+    res["layer_peak_mem_gb_incumbent"] = None
+    torch.cuda.reset_peak_memory_stats()
+    layer_step(theirs)()
+    res["layer_peak_mem_gb_incumbent"] = torch.cuda.max_memory_allocated() / 1e9
+    torch.cuda.reset_peak_memory_stats()
+    layer_step(ours)()
+    res["layer_peak_mem_gb_ours"] = torch.cuda.max_memory_allocated() / 1e9
+    flush()
+    del theirs, ours, h, g
+    torch.cuda.empty_cache()
+
+    # ---- (2), (3) whole model: parity on one batch, then the training step --------------------------------------------
+    torch.manual_seed(1234)
+    ref = EagerOperator(CFG["modes"], W, CFG["n_layers"], CFG["rational_order"]).to(dev)
+    new = pb.RationalFourierOperator3D(modes=CFG["modes"], width=W, n_layers=CFG["n_layers"],
+                                       rational_order=CFG["rational_order"]).to(dev)
+    new.load_state_dict({k: v for k, v in ref.state_dict().items() if k in new.state_dict()}, strict=False)
+    with torch.no_grad():
+        for a, b in zip(ref.rational_layers, new.rational_layers):
+            b.P_coeffs.copy_(a.P_coeffs)
+            b.Q_coeffs.copy_(a.Q_coeffs)
+    condition(ref.rational_layers)
+    condition(new.rational_layers)
+    for a, b in zip(ref.parameters(), new.parameters()):
+        assert a.shape == b.shape and torch.equal(a, b), "weight copy failed"
+
+    def grads(model):
+        model.zero_grad(set_to_none=True)
+        out = model(x)
+        F.mse_loss(out, y).backward()
+        return out.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+    try:
+        # the incumbent's own convolution runs in TF32 under the stock cudnn.allow_tf32 = True: strict fp32 for the comparison
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            o_ref, g_ref = grads(ref)
+        ref.zero_grad(set_to_none=True)
+        parity = {}
+        for prec in ("auto", "tf32"):
+            new.set_precision(prec)
+            o_new, g_new = grads(new)
+            parity[prec] = {"output": rel(o_new, o_ref),
+                            "grad_max_over_params": max(rel(g_new[k], g_ref[k]) for k in g_ref),
+                            "grad_P_coeffs_layer0": rel(g_new["rational_layers.0.P_coeffs"], g_ref["rational_layers.0.P_coeffs"]),
+                            "grad_Q_coeffs_layer0": rel(g_new["rational_layers.0.Q_coeffs"], g_ref["rational_layers.0.Q_coeffs"])}
+        new.zero_grad(set_to_none=True)
+        res["whole_model_parity_vs_incumbent_fp32"] = parity
+        del o_ref, g_ref, o_new, g_new
+    except torch.OutOfMemoryError as e:          # the incumbent keeps ~15 GB per layer at B = 8
+        res["whole_model_parity_vs_incumbent_fp32"] = f"out of memory: {str(e)[:120]}"
+    torch.cuda.empty_cache()
+    flush()
+
+    def train_step(model):
+        params = list(model.parameters())
+        opt = torch.optim.AdamW(params, lr=1e-8, weight_decay=1e-4)     # bench.py's first warm-up value
+
+        def run():
+            opt.zero_grad(set_to_none=True)
+            loss = F.mse_loss(model(x), y)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+        return run
+
+    step = {}
+    try:
+        torch.cuda.reset_peak_memory_stats()
+        ms = statistics.median(event_times(train_step(ref), args.warmup, args.steps))
+        step["incumbent_torch_cufft"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3,
+                                         "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+    except torch.OutOfMemoryError as e:
+        step["incumbent_torch_cufft"] = f"out of memory: {str(e)[:120]}"
+    del ref
+    torch.cuda.empty_cache()
+    for prec in ("tf32", "auto"):
+        new.set_precision(prec)
+        torch.cuda.reset_peak_memory_stats()
+        ms = statistics.median(event_times(train_step(new), args.warmup, args.steps))
+        step[f"pde_fluid_phi_b200[{prec}]"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3,
+                                                "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+    res["train_step"] = step
+    flush()
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
