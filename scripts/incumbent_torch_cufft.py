@@ -127,6 +127,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=CFG["batch_per_gpu"])
+    ap.add_argument("--fp64", action="store_true", help="also run the incumbent in float64 (noise floors)")
+    ap.add_argument("--parity-only", action="store_true")
+    ap.add_argument("--diagnose", action="store_true", help="where the incumbent's fp32 run leaves its fp64 run, module by module")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "incumbent.json"))
     args = ap.parse_args()
     import pde_fluid_phi_b200 as pb
@@ -143,6 +146,53 @@ def main():
     x = turbulence_batch(B, n, 42, dev)
     y = turbulence_batch(B, n, 1042, dev)
 
+    if args.diagnose:
+        diagnose(res, x[:1], W, dev, pb)
+        flush()
+        print(json.dumps(res))
+        return
+    if not args.parity_only:
+        layer_times(res, B, W, n, dev, pb)
+        flush()
+    whole_model(res, args, x, y, B, W, dev, pb, flush)
+    print(json.dumps(res))
+
+
+def diagnose(res, x1, W, dev, pb):
+    """One sample through the incumbent in fp32 (strict) and fp64 and through the library ('auto'), module outputs compared."""
+    torch.manual_seed(1234)
+    ref = EagerOperator(CFG["modes"], W, CFG["n_layers"], CFG["rational_order"]).to(dev)
+    condition(ref.rational_layers)
+    new = pb.RationalFourierOperator3D(modes=CFG["modes"], width=W, n_layers=CFG["n_layers"],
+                                       rational_order=CFG["rational_order"]).to(dev)
+    new.load_state_dict({k: v for k, v in ref.state_dict().items() if k in new.state_dict()}, strict=False)
+    new.set_precision("auto")
+
+    def trace(model, x):
+        seen = {}
+        hooks = [m.register_forward_hook(lambda mod, i, o, name=name: seen.__setitem__(name, o.detach()))
+                 for name, m in model.named_modules() if name and "." in name or name in ("input_proj", "output_proj")]
+        with torch.no_grad():
+            seen["out"] = model(x)
+        for h in hooks:
+            h.remove()
+        return seen
+
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        t32 = trace(ref, x1)
+        tnew = trace(new, x1)
+    t64 = trace(ref.double(), x1.double())
+    rows = {}
+    for k, v in t64.items():
+        if k in t32:
+            rows[k] = {"rms_fp64": float(v.pow(2).mean().sqrt()), "incumbent_fp32_vs_fp64": rel(t32[k], v),
+                       "mean_offset_over_rms": float((t32[k].double() - v).mean() / v.pow(2).mean().sqrt())}
+            if k in tnew and tnew[k].shape == v.shape:
+                rows[k]["library_auto_vs_fp64"] = rel(tnew[k], v)
+    res["diagnose"] = rows
+
+
+def layer_times(res, B, W, n, dev, pb):
     # ---- (1) one layer, fwd+bwd ----------------------------------------------------------------------------------
     torch.manual_seed(1234)
     theirs = EagerRationalLayer(W, CFG["modes"], CFG["rational_order"]).to(dev)
@@ -171,10 +221,11 @@ def main():
     torch.cuda.reset_peak_memory_stats()
     layer_step(ours)()
     res["layer_peak_mem_gb_ours"] = torch.cuda.max_memory_allocated() / 1e9
-    flush()
     del theirs, ours, h, g
     torch.cuda.empty_cache()
 
+
+def whole_model(res, args, x, y, B, W, dev, pb, flush):
     # ---- (2), (3) whole model: parity on one batch, then the training step --------------------------------------------
     torch.manual_seed(1234)
     ref = EagerOperator(CFG["modes"], W, CFG["n_layers"], CFG["rational_order"]).to(dev)
@@ -197,25 +248,53 @@ def main():
         return out.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
 
     try:
-        # the incumbent's own convolution runs in TF32 under the stock cudnn.allow_tf32 = True: strict fp32 for the comparison
+        # Four runs of the incumbent and two of the library on the same batch and weights.  The incumbent's own 1x1x1
+        # convolution runs in TF32 under the stock cudnn.allow_tf32 = True, so its strict-fp32 run is the comparison
+        # target, its stock run gives the TF32 noise floor of the incumbent itself, and its fp64 run (half the batch at a
+        # time) the fp32 noise floor (new-vs-ref32, ref32-vs-ref64, new-vs-ref64).
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             o_ref, g_ref = grads(ref)
+        o_stock, g_stock = grads(ref)
         ref.zero_grad(set_to_none=True)
-        parity = {}
+
+        def versus(o, g, o0, g0):
+            return {"output": rel(o, o0), "grad_max_over_params": max(rel(g[k], g0[k]) for k in g0),
+                    "grad_P_coeffs_layer0": rel(g["rational_layers.0.P_coeffs"], g0["rational_layers.0.P_coeffs"]),
+                    "grad_Q_coeffs_layer0": rel(g["rational_layers.0.Q_coeffs"], g0["rational_layers.0.Q_coeffs"])}
+
+        parity = {"incumbent_stock_tf32_conv_vs_incumbent_strict_fp32": versus(o_stock, g_stock, o_ref, g_ref)}
+        del o_stock, g_stock
+        outs = {}
         for prec in ("auto", "tf32"):
             new.set_precision(prec)
-            o_new, g_new = grads(new)
-            parity[prec] = {"output": rel(o_new, o_ref),
-                            "grad_max_over_params": max(rel(g_new[k], g_ref[k]) for k in g_ref),
-                            "grad_P_coeffs_layer0": rel(g_new["rational_layers.0.P_coeffs"], g_ref["rational_layers.0.P_coeffs"]),
-                            "grad_Q_coeffs_layer0": rel(g_new["rational_layers.0.Q_coeffs"], g_ref["rational_layers.0.Q_coeffs"])}
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=(prec == "tf32")):   # 'auto' is the fp32-grade route
+                outs[prec] = grads(new)
+            parity[f"{prec}_vs_incumbent_strict_fp32"] = versus(*outs[prec], o_ref, g_ref)
         new.zero_grad(set_to_none=True)
-        res["whole_model_parity_vs_incumbent_fp32"] = parity
-        del o_ref, g_ref, o_new, g_new
+        if args.fp64:
+            ref64 = EagerOperator(CFG["modes"], W, CFG["n_layers"], CFG["rational_order"]).to(dev)
+            ref64.load_state_dict(ref.state_dict())
+            ref64 = ref64.double()
+            ref64.zero_grad(set_to_none=True)
+            o64 = []
+            for i in range(B):                                   # one sample at a time: the loss is a mean over the batch
+                out = ref64(x[i:i + 1].double())
+                (F.mse_loss(out, y[i:i + 1].double()) / B).backward()
+                o64.append(out.detach())
+            o64 = torch.cat(o64)
+            g64 = {k: p.grad.detach() for k, p in ref64.named_parameters()}
+            parity["incumbent_strict_fp32_vs_incumbent_fp64"] = versus(o_ref, g_ref, o64, g64)
+            for prec in outs:
+                parity[f"{prec}_vs_incumbent_fp64"] = versus(*outs[prec], o64, g64)
+            del ref64, o64, g64
+        res["whole_model_parity"] = parity
+        del o_ref, g_ref, outs
     except torch.OutOfMemoryError as e:          # the incumbent keeps ~15 GB per layer at B = 8
-        res["whole_model_parity_vs_incumbent_fp32"] = f"out of memory: {str(e)[:120]}"
+        res["whole_model_parity"] = f"out of memory: {str(e)[:120]}"
     torch.cuda.empty_cache()
     flush()
+    if args.parity_only:
+        return
 
     def train_step(model):
         params = list(model.parameters())
@@ -247,7 +326,6 @@ def main():
                                                 "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
     res["train_step"] = step
     flush()
-    print(json.dumps(res))
 
 
 if __name__ == "__main__":
