@@ -76,6 +76,25 @@ class EagerRationalLayer(nn.Module):
         return torch.fft.irfftn(proj, s=x.shape[-3:], dim=[-3, -2, -1])
 
 
+class EagerSpectralConv(nn.Module):
+    """operators/spectral_layers.py:46-78 with the weight contracted on [..., :mz//2+1] (the unmodified forward raises
+    for mz > 2; SURVEY.md section 8c convention 2)."""
+
+    def __init__(self, cin, cout, modes):
+        super().__init__()
+        self.modes, self.cout = modes, cout
+        self.weights = nn.Parameter(torch.randn(cout, cin, *modes, dtype=torch.cfloat) * 0.02)
+
+    def forward(self, x):
+        mx, my, mz = self.modes
+        mzh = mz // 2 + 1
+        x_ft = torch.fft.rfftn(x, dim=[-3, -2, -1])
+        out_modes = torch.einsum("bixyz,oixyz->boxyz", x_ft[:, :, :mx, :my, :mzh], self.weights[..., :mzh])
+        out_ft = torch.zeros(x.shape[0], self.cout, *x_ft.shape[-3:], dtype=torch.cfloat, device=x.device)
+        out_ft[:, :, :mx, :my, :mzh] = out_modes
+        return torch.fft.irfftn(out_ft, s=x.shape[-3:], dim=[-3, -2, -1])
+
+
 class EagerOperator(nn.Module):
     """rearrange -> Linear -> rearrange, n x gelu(spectral + conv1x1 + x), rearrange -> Linear -> rearrange."""
 
@@ -129,6 +148,7 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["batch_per_gpu"])
     ap.add_argument("--fp64", action="store_true", help="also run the incumbent in float64 (noise floors)")
     ap.add_argument("--parity-only", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="fwd+bwd microseconds of single layers at the BASELINE shapes")
     ap.add_argument("--diagnose", action="store_true", help="where the incumbent's fp32 run leaves its fp64 run, module by module")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "incumbent.json"))
     args = ap.parse_args()
@@ -143,9 +163,13 @@ def main():
         with open(args.out, "w") as f:
             json.dump(res, f, indent=1)
 
+    if args.layers:
+        single_layers(res, dev, pb)
+        flush()
+        print(json.dumps(res))
+        return
     x = turbulence_batch(B, n, 42, dev)
     y = turbulence_batch(B, n, 1042, dev)
-
     if args.diagnose:
         diagnose(res, x[:1], W, dev, pb)
         flush()
@@ -156,6 +180,47 @@ def main():
         flush()
     whole_model(res, args, x, y, B, W, dev, pb, flush)
     print(json.dumps(res))
+
+
+def single_layers(res, dev, pb):
+    """The 'SpectralConv3d fwd+bwd us' half of the BASELINE metric: incumbent vs library, median over CUDA-event-timed calls."""
+    def conditioned(layer):
+        condition([layer])
+        return layer
+
+    cases = [
+        ("SpectralConv3D [4,32,32^3] modes 8^3 (cfg 1)", (4, 32, 32, 32, 32), lambda: EagerSpectralConv(32, 32, (8, 8, 8)),
+         lambda: pb.SpectralConv3D(32, 32, (8, 8, 8)), "auto", 20, 100),
+        ("RationalFourierLayer [4,32,32^3] modes 8^3 (cfg-1 shape)", (4, 32, 32, 32, 32),
+         lambda: conditioned(EagerRationalLayer(32, (8, 8, 8))), lambda: conditioned(pb.RationalFourierLayer(32, 32, (8, 8, 8))), "auto", 20, 100),
+        ("SpectralConv3D [8,64,128^3] modes 32^3 (cfg-2 shape)", (8, 64, 128, 128, 128), lambda: EagerSpectralConv(64, 64, (32, 32, 32)),
+         lambda: pb.SpectralConv3D(64, 64, (32, 32, 32)), "tf32", 3, 10),
+        ("SpectralConv3D [64,64,256,256,1] modes (64,64,1) (cfg 3)", (64, 64, 256, 256, 1), lambda: EagerSpectralConv(64, 64, (64, 64, 1)),
+         lambda: pb.SpectralConv3D(64, 64, (64, 64, 1)), "tf32", 5, 20),
+    ]
+    rows = {}
+    for name, shape, make_ref, make_new, prec, warm, reps in cases:
+        torch.manual_seed(7)
+        x = torch.randn(*shape, device=dev, requires_grad=True)
+        g = torch.randn(*shape, device=dev)
+        row = {}
+        for who, make in (("incumbent_torch_cufft_us", make_ref), (f"pde_fluid_phi_b200[{prec}]_us", make_new)):
+            layer = make().to(dev)
+            if hasattr(layer, "precision"):
+                layer.precision = prec
+
+            def run():
+                layer(x).backward(g)
+                x.grad = None
+                for p in layer.parameters():
+                    p.grad = None
+            row[who] = 1e3 * statistics.median(event_times(run, warm, reps))
+            del layer
+        row["speedup"] = row["incumbent_torch_cufft_us"] / row[f"pde_fluid_phi_b200[{prec}]_us"]
+        rows[name] = row
+        del x, g
+        torch.cuda.empty_cache()
+    res["layer_fwd_bwd_us"] = rows
 
 
 def diagnose(res, x1, W, dev, pb):

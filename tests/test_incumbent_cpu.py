@@ -31,3 +31,19 @@ def test_incumbent_restatement_reproduces_the_reference_fixture():
     fresh = inc.EagerOperator((4, 4, 4), 8, 2, order)   # ... and the buffers it builds itself are the same
     assert torch.equal(fresh.rational_layers[0].decay_mask, sd["rational_layers.0.decay_mask"])
     assert torch.equal(fresh.rational_layers[0].k_grid, sd["rational_layers.0.k_grid"])
+
+
+def test_incumbent_spectral_conv_reproduces_the_reference_fixtures():
+    inc = _load_script()
+    for name in ("sc3d_c4_m4_n8_sliced", "sc3d_c3_m881_n16x16x1_unmodified", "sc3d_c2_m462_n8x12x6_unmodified"):
+        d = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        W = torch.from_numpy(d["sd:weights"])
+        layer = inc.EagerSpectralConv(W.shape[1], W.shape[0], tuple(int(v) for v in d["meta:modes"]))
+        with torch.no_grad():
+            layer.weights.copy_(W)
+        x = torch.from_numpy(d["x"]).requires_grad_(True)
+        out = layer(x)
+        out.backward(torch.from_numpy(d["g"]))
+        assert torch.equal(out.detach(), torch.from_numpy(d["out"])), name
+        assert torch.equal(x.grad, torch.from_numpy(d["dx"])), name
+        assert torch.equal(layer.weights.grad, torch.from_numpy(d["grad:weights"])), name
