@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--fp64", action="store_true", help="also run the incumbent in float64 (noise floors)")
     ap.add_argument("--parity-only", action="store_true")
     ap.add_argument("--layers", action="store_true", help="fwd+bwd microseconds of single layers at the BASELINE shapes")
+    ap.add_argument("--big", action="store_true", help="with --layers: the 64^3-mode layers of configs 4 and 5 instead")
     ap.add_argument("--diagnose", action="store_true", help="where the incumbent's fp32 run leaves its fp64 run, module by module")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "incumbent.json"))
     args = ap.parse_args()
@@ -164,7 +165,7 @@ def main():
             json.dump(res, f, indent=1)
 
     if args.layers:
-        single_layers(res, dev, pb)
+        single_layers(res, dev, pb, args.big)
         flush()
         print(json.dumps(res))
         return
@@ -182,7 +183,7 @@ def main():
     print(json.dumps(res))
 
 
-def single_layers(res, dev, pb):
+def single_layers(res, dev, pb, big=False):
     """The 'SpectralConv3d fwd+bwd us' half of the BASELINE metric: incumbent vs library, median over CUDA-event-timed calls."""
     def conditioned(layer):
         condition([layer])
@@ -198,6 +199,13 @@ def single_layers(res, dev, pb):
         ("SpectralConv3D [64,64,256,256,1] modes (64,64,1) (cfg 3)", (64, 64, 256, 256, 1), lambda: EagerSpectralConv(64, 64, (64, 64, 1)),
          lambda: pb.SpectralConv3D(64, 64, (64, 64, 1)), "tf32", 5, 20),
     ]
+    if big:     # the 64^3-mode operator of configs 4 and 5 (R(k) alone is 2.2 GB per polynomial term on the incumbent)
+        cases = [
+            ("RationalFourierLayer [1,64,128^3] modes 64^3 (cfg 4 small-scale operator)", (1, 64, 128, 128, 128),
+             lambda: conditioned(EagerRationalLayer(64, (64, 64, 64))), lambda: conditioned(pb.RationalFourierLayer(64, 64, (64, 64, 64))), "tf32", 2, 5),
+            ("RationalFourierLayer [1,64,256^3] modes 64^3 (cfg 5)", (1, 64, 256, 256, 256),
+             lambda: conditioned(EagerRationalLayer(64, (64, 64, 64))), lambda: conditioned(pb.RationalFourierLayer(64, 64, (64, 64, 64))), "tf32", 2, 5),
+        ]
     rows = {}
     for name, shape, make_ref, make_new, prec, warm, reps in cases:
         torch.manual_seed(7)
