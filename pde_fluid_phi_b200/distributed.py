@@ -8,6 +8,7 @@ latency-bound collective per step.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Iterable, List
 
 import torch
@@ -44,6 +45,85 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], world_size: int = 
             n = g.numel()
             g.copy_(flat[off:off + n].view_as(g))
             off += n
+
+
+class OverlappedGradientAllReduce:
+    """Gradient averaging that overlaps the backward pass (cfg 3: four complex64 `weights` gradients
+    of 134 MB each -- too much to leave behind the last backward kernel in one flat bucket).
+
+    A post-accumulate-grad hook on every parameter fires as soon as autograd has finished that parameter's gradient:
+    a gradient of at least `bucket_bytes` is all-reduced IN PLACE, asynchronously, while the backward of the layers
+    below it is still running (no staging copy at all); smaller ones collect in a flat bucket that is sent when it
+    reaches `bucket_bytes`.  `finish()` -- call it after `backward()`, before the optimizer -- sends the last partial
+    bucket, waits for every collective and applies the 1/world_size.  The hooks fire in autograd's order, which is the
+    same on every rank for replicas of one model, so the collectives pair up without any negotiation; the result equals
+    `allreduce_gradients` (the same sums, element by element).  For gradient accumulation wrap the non-final backward
+    passes in `no_sync()`, as with DistributedDataParallel.
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int = None, group=None, average: bool = True,
+                 bucket_bytes: int = 32 << 20):
+        self.world_size = dist.get_world_size(group) if world_size is None else world_size
+        self.group, self.average, self.bucket_bytes = group, average, int(bucket_bytes)
+        self.enabled = True
+        self._pending = []            # (work, [gradient views], flat bucket or None)
+        self._small, self._small_bytes = [], 0
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params if p.requires_grad]
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if not self.enabled or self.world_size == 1 or p.grad is None:
+            return
+        g = _real_view(p.grad)
+        nbytes = g.numel() * g.element_size()
+        if nbytes >= self.bucket_bytes and g.is_contiguous():
+            self._pending.append((dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True), [g], None))
+            return
+        self._small.append(g)
+        self._small_bytes += nbytes
+        if self._small_bytes >= self.bucket_bytes:
+            self._flush_small()
+
+    def _flush_small(self) -> None:
+        by_dtype = {}
+        for g in self._small:
+            by_dtype.setdefault(g.dtype, []).append(g)
+        for same in by_dtype.values():
+            flat = torch.cat([g.reshape(-1) for g in same])
+            self._pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), same, flat))
+        self._small, self._small_bytes = [], 0
+
+    def finish(self) -> None:
+        """Complete every outstanding collective; afterwards each .grad holds the mean (or the sum) over the ranks."""
+        if self._small:
+            self._flush_small()
+        for work, grads, flat in self._pending:
+            work.wait()
+            if flat is None:
+                if self.average:
+                    grads[0].div_(self.world_size)
+                continue
+            if self.average:
+                flat.div_(self.world_size)
+            off = 0
+            for g in grads:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n
+        self._pending = []
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Backward passes inside this context only accumulate locally (no collective is issued)."""
+        was, self.enabled = self.enabled, False
+        try:
+            yield
+        finally:
+            self.enabled = was
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:

@@ -97,6 +97,43 @@ def test_cfg3_2d_kolmogorov_scaled_and_full_size():
     assert abs(float(lhs - rhs)) <= 1e-5 * abs(float(lhs))
 
 
+def test_cfg3_full_width_model_block_route_vs_fp32_route():
+    """configs[2] at its full width (64) and grid, 4 layers, batch 2: on a 2-D grid the width-64 model takes the block
+    route (lift in the first block, 1x1x1 convolution + residual + GELU on the tensor cores, projection in the last
+    block; per-axis transforms).  Outputs and every parameter gradient against the fp32 route of the same model, whose
+    layers the width-16 case above pins to the oracle."""
+    torch.manual_seed(1234)
+    n = 256
+    model = pb.FNO3D(modes=(64, 64, 1), width=64, n_layers=4, in_channels=2, out_channels=2).to(DEV)
+    g = torch.Generator().manual_seed(42)
+    yy = torch.linspace(0, 2 * math.pi, n)
+    base = torch.sin(4 * yy)[None, :, None].expand(n, n, 1)
+    x = torch.stack([torch.stack([base + 0.1 * torch.randn(n, n, 1, generator=g), 0.1 * torch.randn(n, n, 1, generator=g)])
+                     for _ in range(2)]).to(DEV)
+    y = torch.roll(x, 3, dims=2)
+
+    def run(precision):
+        model.set_precision(precision)
+        model.zero_grad(set_to_none=True)
+        out = model(x)
+        torch.nn.functional.mse_loss(out, y).backward()
+        return out.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters()}
+
+    assert model.spectral_layers[0].block_supported(torch.empty(2, 64, n, n, 1, device=DEV), model.local_layers[0])
+    out_tc, g_tc = run("tf32")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        out_ref, g_ref = run("fp32")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert torch.isfinite(out_tc).all()
+    assert rel(out_tc, out_ref) < 3e-3
+    for k in g_ref:
+        assert rel(g_tc[k], g_ref[k]) < 5e-3, k
+        assert g_tc[k].dtype == g_ref[k].dtype and g_tc[k].shape == g_ref[k].shape
+
+
 @pytest.mark.parametrize("modes,order", [((16, 16, 16), (2, 2)), ((32, 32, 32), (3, 3)), ((64, 64, 64), (4, 4))])
 def test_cfg4_multiscale_operators_on_128_cubed(modes, order):
     """configs[3] (oracle convention 3): the large / medium / small RationalFourierOperator3D(in = out = width) of

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pde_fluid_phi_b200.distributed import allreduce_gradients, broadcast_parameters
+from pde_fluid_phi_b200.distributed import OverlappedGradientAllReduce, allreduce_gradients, broadcast_parameters
 
 
 def _free_port():
@@ -48,6 +48,61 @@ def test_gradient_allreduce_two_ranks():
         assert torch.equal(g0, g1)                      # same averaged gradient on both ranks
         assert torch.allclose(g0, (l0 + l1) / 2, rtol=1e-6, atol=1e-7)
         assert g0.dtype == l0.dtype                     # complex64 stays complex64
+
+
+def _overlap_worker(rank, world, port, out):
+    """The hook-driven reducer (large gradients in place, small ones bucketed) against the flat all-reduce."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(3)                                 # replicas: same weights on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.GELU(), torch.nn.Linear(16, 16), torch.nn.GELU(), torch.nn.Linear(16, 4))
+    w = torch.nn.Parameter(torch.randn(4, 4, 5, dtype=torch.cfloat))       # a "large" complex gradient: 640 bytes
+    params = list(net.parameters()) + [w]
+    torch.manual_seed(50 + rank)                         # different data per rank
+    x = torch.randn(8, 6)
+    z = torch.randn(4, 4, 5, dtype=torch.cfloat)
+
+    def loss_fn():
+        return (net(x) ** 2).mean() + (w * z).abs().pow(2).sum() * net[4].bias.sum().abs()
+
+    loss_fn().backward()
+    allreduce_gradients(params, world)
+    want = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    red = OverlappedGradientAllReduce(params, world, bucket_bytes=512)     # w and net[2].weight (1 KB) go in place
+    loss_fn().backward()
+    assert red._pending, "no collective was issued during backward"
+    red.finish()
+    got = [p.grad.clone() for p in params]
+    # accumulation: first pass local only, second pass reduces the accumulated sum -> mean of the per-rank sums
+    for p in params:
+        p.grad = None
+    with red.no_sync():
+        loss_fn().backward()
+    assert not red._pending and not red._small
+    local2 = [2 * p.grad.clone() for p in params]
+    loss_fn().backward()
+    red.finish()
+    acc = [p.grad.clone() for p in params]
+    red.remove()
+    out[rank] = dict(want=want, got=got, acc=acc, local2=local2)
+    dist.destroy_process_group()
+
+
+def test_overlapped_gradient_allreduce_two_ranks():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_overlap_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    for w0, g0, g1 in zip(r0["want"], r0["got"], r1["got"]):
+        assert g0.dtype == w0.dtype and torch.equal(g0, g1)
+        assert torch.equal(g0, w0)                       # the same sums as the flat all-reduce, element by element
+    for a0, a1, l0, l1 in zip(r0["acc"], r1["acc"], r0["local2"], r1["local2"]):
+        assert torch.equal(a0, a1)
+        assert torch.allclose(a0, (l0 + l1) / 2, rtol=1e-5, atol=1e-7)
 
 
 def _slab_worker(rank, world, port, out):
