@@ -112,6 +112,23 @@ class EagerOperator(nn.Module):
         return self.output_proj(h.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
 
 
+class EagerFNO(nn.Module):
+    """models/fno3d.py:75-108: the same loop around SpectralConv3D (names as in the reference: spectral_layers, local_layers)."""
+
+    def __init__(self, modes, width, n_layers, cin=3, cout=3):
+        super().__init__()
+        self.input_proj = nn.Linear(cin, width)
+        self.output_proj = nn.Linear(width, cout)
+        self.spectral_layers = nn.ModuleList([EagerSpectralConv(width, width, modes) for _ in range(n_layers)])
+        self.local_layers = nn.ModuleList([nn.Conv3d(width, width, kernel_size=1) for _ in range(n_layers)])
+
+    def forward(self, x):
+        h = self.input_proj(x.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
+        for spectral, local in zip(self.spectral_layers, self.local_layers):
+            h = F.gelu(spectral(h) + local(h) + h)
+        return self.output_proj(h.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
+
+
 def condition(layers):
     """bench.py's weight set: non-constant Q and all P coefficients x1e-4 (the default init overflows)."""
     with torch.no_grad():
@@ -150,6 +167,7 @@ def main():
     ap.add_argument("--parity-only", action="store_true")
     ap.add_argument("--layers", action="store_true", help="fwd+bwd microseconds of single layers at the BASELINE shapes")
     ap.add_argument("--big", action="store_true", help="with --layers: the 64^3-mode layers of configs 4 and 5 instead")
+    ap.add_argument("--cfg3", action="store_true", help="training step of the 2-D Kolmogorov FNO (configs[2]) instead")
     ap.add_argument("--diagnose", action="store_true", help="where the incumbent's fp32 run leaves its fp64 run, module by module")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "incumbent.json"))
     args = ap.parse_args()
@@ -164,6 +182,11 @@ def main():
         with open(args.out, "w") as f:
             json.dump(res, f, indent=1)
 
+    if args.cfg3:
+        cfg3_step(res, dev, pb, args)
+        flush()
+        print(json.dumps(res))
+        return
     if args.layers:
         single_layers(res, dev, pb, args.big)
         flush()
@@ -181,6 +204,31 @@ def main():
         flush()
     whole_model(res, args, x, y, B, W, dev, pb, flush)
     print(json.dumps(res))
+
+
+def cfg3_step(res, dev, pb, args):
+    """configs[2]: FNO modes (64,64,1), width 64, 4 layers, 256 x 256 x 1 grid, batch 64: fwd + MSE + bwd + AdamW."""
+    B, n = 64, 256
+    torch.manual_seed(1234)
+    x = torch.randn(B, 2, n, n, 1, device=dev)
+    y = torch.roll(x, 3, dims=3)
+    step = {}
+    for who, make in (("incumbent_torch_cufft", lambda: EagerFNO((64, 64, 1), 64, 4, 2, 2)),
+                      ("pde_fluid_phi_b200[tf32]", lambda: pb.FNO3D(modes=(64, 64, 1), width=64, n_layers=4, in_channels=2,
+                                                                     out_channels=2).set_precision("tf32"))):
+        model = make().to(dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-5, weight_decay=1e-4)
+
+        def run():
+            opt.zero_grad(set_to_none=True)
+            F.mse_loss(model(x), y).backward()
+            opt.step()
+        torch.cuda.reset_peak_memory_stats()
+        ms = statistics.median(event_times(run, args.warmup, args.steps))
+        step[who] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+        del model, opt
+        torch.cuda.empty_cache()
+    res["cfg3_train_step"] = step
 
 
 def single_layers(res, dev, pb, big=False):

@@ -47,3 +47,16 @@ def test_incumbent_spectral_conv_reproduces_the_reference_fixtures():
         assert torch.equal(out.detach(), torch.from_numpy(d["out"])), name
         assert torch.equal(x.grad, torch.from_numpy(d["dx"])), name
         assert torch.equal(layer.weights.grad, torch.from_numpy(d["grad:weights"])), name
+
+
+def test_incumbent_fno_reproduces_the_reference_fixture():
+    inc = _load_script()
+    d = np.load(os.path.join(ROOT, "tests", "golden", "fno3d_w8_m4_l2_n8_sliced.npz"))
+    sd = {k[3:]: torch.from_numpy(d[k]) for k in d.keys() if k.startswith("sd:")}
+    model = inc.EagerFNO((4, 4, 4), 8, 2)
+    model.load_state_dict(sd, strict=True)
+    x = torch.from_numpy(d["x"]).requires_grad_(True)
+    out = model(x)
+    out.backward(torch.from_numpy(d["g"]))
+    assert torch.equal(out.detach(), torch.from_numpy(d["out"]))
+    assert torch.equal(x.grad, torch.from_numpy(d["dx"]))
