@@ -15,9 +15,24 @@ PATTERNS = [("UTC*MMA", r"\bUTC[A-Z]*MMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bST
             ("FFMA", r"\bFFMA\b"), ("FFMA2", r"\bFFMA2"), ("SYNCS", r"\bSYNCS")]
 
 
+def ptxas_resources():
+    """{mangled name: (registers, spill store bytes, spill load bytes)} from the build's ptxas -v logs."""
+    res, build = {}, os.path.join(ROOT, "pde_fluid_phi_b200", "build")
+    for fn in sorted(os.listdir(build)) if os.path.isdir(build) else []:
+        if not fn.endswith(".ptxas.log"):
+            continue
+        text = open(os.path.join(build, fn)).read()
+        for m in re.finditer(r"Function properties for (\S+)\s+\d+ bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\s+"
+                             r"ptxas info\s+: Used (\d+) registers", text):
+            res[m.group(1)] = (int(m.group(4)), int(m.group(2)), int(m.group(3)))
+    return res
+
+
 def main(out):
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
-    names = subprocess.run(["cu++filt"], input="\n".join(re.findall(r"Function : (\S+)", sass)), capture_output=True, text=True).stdout.split("\n")
+    mangled = re.findall(r"Function : (\S+)", sass)
+    names = subprocess.run(["cu++filt"], input="\n".join(mangled), capture_output=True, text=True).stdout.split("\n")
+    resources, raw_of = ptxas_resources(), {}
     counts, order, cur, total = {}, [], None, collections.Counter()
     it = iter(names)
     for line in sass.splitlines():
@@ -31,6 +46,7 @@ def main(out):
             while cur in counts:
                 cur = f"{base} #{k}"; k += 1
             counts[cur] = collections.Counter()
+            raw_of[cur] = m.group(1)
             order.append(cur)
             continue
         if cur and "/*" in line:
@@ -40,9 +56,9 @@ def main(out):
                     counts[cur][key] += 1
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow(["kernel", "instructions"] + [k for k, _ in PATTERNS])
+        w.writerow(["kernel", "registers", "spill store bytes", "spill load bytes", "instructions"] + [k for k, _ in PATTERNS])
         for k in sorted(order):
-            w.writerow([k, counts[k]["instructions"]] + [counts[k][p] for p, _ in PATTERNS])
+            w.writerow([k, *resources.get(raw_of[k], ("", "", "")), counts[k]["instructions"]] + [counts[k][p] for p, _ in PATTERNS])
             total.update(counts[k])
     print(f"{len(order)} kernels; totals:", {p: total[p] for p, _ in PATTERNS})
 
