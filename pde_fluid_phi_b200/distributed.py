@@ -63,11 +63,12 @@ class OverlappedGradientAllReduce:
 
     def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int = None, group=None, average: bool = True,
                  bucket_bytes: int = 32 << 20):
-        self.world_size = dist.get_world_size(group) if world_size is None else world_size
+        initialized = dist.is_available() and dist.is_initialized()       # a single process without a group: a no-op
+        self.world_size = world_size if world_size is not None else (dist.get_world_size(group) if initialized else 1)
         self.group, self.average, self.bucket_bytes = group, average, int(bucket_bytes)
         self.enabled = True
         # NCCL averages inside the collective (ReduceOp.AVG): no separate pass over a 134 MB gradient for the 1/world_size
-        self._fused_avg = bool(average) and dist.get_backend(group) == "nccl"
+        self._fused_avg = bool(average) and initialized and dist.get_backend(group) == "nccl"
         self._op = dist.ReduceOp.AVG if self._fused_avg else dist.ReduceOp.SUM
         self._pending = []            # (work, [gradient views], flat bucket or None)
         self._small, self._small_bytes = [], 0

@@ -105,6 +105,17 @@ def test_overlapped_gradient_allreduce_two_ranks():
         assert torch.allclose(a0, (l0 + l1) / 2, rtol=1e-5, atol=1e-7)
 
 
+def test_overlapped_reducer_is_a_no_op_in_a_single_process():
+    lin = torch.nn.Linear(3, 2)
+    red = OverlappedGradientAllReduce(lin.parameters())          # no process group: world size 1
+    lin(torch.randn(4, 3)).sum().backward()
+    want = [p.grad.clone() for p in lin.parameters()]
+    assert not red._pending and not red._small
+    red.finish()
+    assert all(torch.equal(p.grad, w) for p, w in zip(lin.parameters(), want))
+    red.remove()
+
+
 def _slab_worker(rank, world, port, out):
     """Slab-decomposed analysis: local partial spectrum (oracle arithmetic) + one all-reduce == full transform."""
     import numpy as np
