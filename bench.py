@@ -186,6 +186,268 @@ def workload_config(n_gpus: int, precision: str) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
+# measured DRAM traffic per launch, read from the ncu summaries committed under profiles/ (never a literal)
+# ------------------------------------------------------------------------------------------------
+# bench kernel name -> prefix of the kernel name in the profiles/*ncu_full*.csv summaries (scripts/ncu_summary.py)
+NCU_NAME = {"analysis_zy_tc_kernel": "tc::analysis_zy_tc_kernel", "synthesis_zy_tc_kernel": "tc::synthesis_zy_tc_kernel",
+            "analysis_x_tc_kernel": "xtc::analysis_x_tc_kernel", "synthesis_x_tc_kernel": "xtc::synthesis_x_tc_kernel",
+            "block_tail_fwd_kernel": "blk::block_tail_fwd_kernel<0", "block_spectral_fwd_kernel": "blk::block_tail_fwd_kernel<1",
+            "block_tail_bwd_kernel": "blk::block_tail_bwd_kernel", "rational_mix_kernel": "rational_mix_kernel",
+            "mix_from_R_kernel": "mix_from_R_kernel", "rational_g_kernel": "rational_g_kernel",
+            "rational_dpq_kernel": "rational_dpq_kernel", "projection_stats_kernel": "projection_stats_kernel",
+            "projection_bwd_kernel": "projection_bwd_kernel", "gen_axis_synthesis_kernel": "gen::gen_axis_synthesis_kernel",
+            "analysis_zy_tc3_kernel": "tc3::analysis_zy_tc3_kernel", "synthesis_zy_tc3_kernel": "tc3::synthesis_zy_tc3_kernel",
+            "pointwise_wgrad_kernel": "pointwise_wgrad_kernel"}
+
+
+def ncu_traffic_from_profiles():
+    """{bench kernel name: (bytes per launch, source file)}: dram__bytes_read.sum + dram__bytes_write.sum of the launch
+    with the most traffic of each kernel (the full-size variant) in the newest profiles/*ncu_full*.csv that has it."""
+    import csv
+    import glob
+    out = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full*.csv"))):      # later rounds override earlier ones
+        try:
+            rows = list(csv.reader(open(path)))
+        except OSError:
+            continue
+        if not rows:
+            continue
+        hdr = rows[0]
+        try:
+            ir = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum"))
+            iw = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum"))
+        except StopIteration:
+            continue
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        ur = scale.get(hdr[ir].split("[")[-1].rstrip("]"), 1e9)
+        uw = scale.get(hdr[iw].split("[")[-1].rstrip("]"), 1e9)
+        best = {}
+        for r in rows[1:]:
+            if len(r) <= max(ir, iw):
+                continue
+            name = r[0].replace("pdephi::", "")
+            for bench_name, prefix in NCU_NAME.items():
+                if name.startswith(prefix) or name.startswith(prefix.split("::")[-1]):
+                    try:
+                        b = float(r[ir]) * ur + float(r[iw]) * uw
+                    except ValueError:
+                        continue
+                    if b > best.get(bench_name, 0.0):
+                        best[bench_name] = b
+        for k, b in best.items():
+            out[k] = (b, os.path.relpath(path, ROOT))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the incumbent on the same GPU: the reference's op sequence in stock PyTorch (cuFFT, cuBLAS, eager elementwise ops)
+# ------------------------------------------------------------------------------------------------
+def gpu_incumbent(dev, x, y, steps: int = 3):
+    """Training step of scripts/incumbent_torch_cufft.py's EagerOperator (the reference restated with plain torch ops in the
+    reference's op order; bit-identical to the reference's fixture on the CPU, tests/test_incumbent_cpu.py) on the same
+    batch: SURVEY.md section 8d's "number to beat".  One warm-up + `steps` timed steps, CUDA events."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    try:
+        import incumbent_torch_cufft as inc
+    except Exception as e:       # the script is measurement support, not product: report instead of failing the bench
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    try:
+        torch.manual_seed(1234)
+        ref = inc.EagerOperator(CFG["modes"], CFG["width"], CFG["n_layers"], CFG["rational_order"]).to(dev)
+        inc.condition(ref.rational_layers)
+        params = list(ref.parameters())
+        opt = torch.optim.AdamW(params, lr=1e-8, weight_decay=1e-4)
+
+        def run():
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.mse_loss(ref(x), y)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+        torch.cuda.reset_peak_memory_stats()
+        ms = inc.event_times(run, 1, steps)
+        med = statistics.median(ms)
+        out = {"ms_per_step": round(med, 2), "samples_s": round(x.shape[0] / med * 1e3, 3), "steps": steps,
+               "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
+               "what": "stock PyTorch eager restatement of the reference operator (torch.fft -> cuFFT, einsum, cuDNN 1x1x1 conv, "
+                       "eager elementwise), same batch / weights / optimizer step, same GPU (scripts/incumbent_torch_cufft.py)"}
+    except torch.OutOfMemoryError as e:
+        out = {"unavailable": f"out of memory: {str(e)[:120]}"}
+    finally:
+        ref = opt = params = None
+        torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# N > 1 only: the two multi-GPU parts of the north star that the weak-scaling line does not exercise
+# ------------------------------------------------------------------------------------------------
+def slab_block(dev, rank: int, world: int, precision: str, steps: int = 5):
+    """cfg 5: one RationalFourierLayer [1,64,256^3], modes 64^3, fwd+bwd on x slabs with the NCCL all-to-all transpose
+    (strong scaling: one 256^3 sample over all ranks).  Device time, max over ranks; parity of the slab result against the
+    single-GPU layer on rank 0's slab (outputs, input gradient) and on the summed coefficient gradients -- asserted."""
+    import torch.distributed as dist
+    import pde_fluid_phi_b200 as pb
+    grid, modes, C = (256, 256, 256), (64, 64, 64), 64
+    torch.manual_seed(3)
+    layer = pb.RationalFourierLayer(C, C, modes).to(dev)
+    with torch.no_grad():
+        q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+        layer.Q_coeffs.mul_(1e-6)
+        layer.Q_coeffs[..., 0, 0, 0] = q0
+    layer.precision = precision
+    nxl = grid[0] // world
+    g = torch.Generator(device=dev).manual_seed(100)
+    xfull = torch.randn(1, C, *grid, device=dev, generator=g)
+    gfull = torch.randn(1, C, *grid, device=dev, generator=g)
+    x = xfull[:, :, rank * nxl:(rank + 1) * nxl].contiguous().requires_grad_(True)
+    go = gfull[:, :, rank * nxl:(rank + 1) * nxl].contiguous()
+
+    def timed(fn, n):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    res = {"workload": "RationalFourierLayer [1,64,256^3] modes 64^3 fwd+bwd, x slabs of 256/N planes, strong scaling",
+           "transform_precision": precision, "steps": steps}
+    outs = {}
+    for exchange in ("alltoall", "allreduce"):
+        layer.slab = (None, grid[0], exchange)
+
+        def step():
+            x.grad = None
+            layer.zero_grad(set_to_none=True)
+            out = layer(x)
+            out.backward(go)
+            return out
+        for _ in range(2):
+            out = step()
+        gP, gQ = layer.P_coeffs.grad.clone(), layer.Q_coeffs.grad.clone()
+        dist.all_reduce(gP)     # "alltoall": per-ky-subset partial sums; "allreduce": complete but pre-divided by world
+        dist.all_reduce(gQ)
+        outs[exchange] = (out.detach().clone(), x.grad.clone(), gP, gQ)
+        res["ms" if exchange == "alltoall" else "ms_allreduce_exchange"] = round(timed(step, steps), 3)
+    # the single-GPU layer on the whole volume: every rank runs it (same device time), rank 0's number is reported
+    layer.slab = None
+    xf = xfull.requires_grad_(True)
+
+    def step1():
+        xf.grad = None
+        layer.zero_grad(set_to_none=True)
+        out = layer(xf)
+        out.backward(gfull)
+        return out
+    for _ in range(2):
+        of = step1()
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    sl = slice(rank * nxl, (rank + 1) * nxl)
+    a2a = outs["alltoall"]
+    errs = torch.tensor([rel(a2a[0], of.detach()[:, :, sl]), rel(a2a[1], xf.grad[:, :, sl]),
+                         rel(a2a[2], layer.P_coeffs.grad), rel(a2a[3], layer.Q_coeffs.grad),
+                         rel(outs["allreduce"][0], of.detach()[:, :, sl])], device=dev, dtype=torch.float64)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    res["ms_1gpu"] = round(timed(step1, steps), 3)
+    res["speedup"] = round(res["ms_1gpu"] / res["ms"], 3)
+    res["efficiency"] = round(res["ms_1gpu"] / res["ms"] / world, 4)
+    res["relL2_vs_single_gpu_out"], res["relL2_dx"], res["relL2_dP"], res["relL2_dQ"], res["relL2_allreduce_exchange_out"] = (
+        float(f"{v:.3e}") for v in errs.tolist())
+    res["relL2_grads"] = max(res["relL2_dx"], res["relL2_dP"], res["relL2_dQ"])
+    # slab and single-GPU runs use the same kernels on differently shaped x stages: fp32-grade agreement on outputs; the
+    # TF32 rounding of differently grouped partial sums on the gradients of the coefficient sums
+    gate_out, gate_grad = (2e-3, 2e-3) if precision == "tf32" else (1e-5, 5e-5)
+    res["gate"] = {"out": gate_out, "grads": gate_grad}
+    ok = res["relL2_vs_single_gpu_out"] <= gate_out and res["relL2_grads"] <= gate_grad and res["relL2_allreduce_exchange_out"] <= gate_out
+    del xfull, gfull, x, go, xf, outs, layer
+    torch.cuda.empty_cache()
+    if not ok:
+        raise SystemExit(f"slab-decomposed layer disagrees with the single-GPU layer: {res}")
+    return res
+
+
+def cfg3_dp_block(dev, rank: int, world: int, steps: int = 8):
+    """cfg 3: 2-D Kolmogorov FNO (modes (64,64,1), width 64, 4 layers, 256^2, batch 64 per GPU): the data-parallel case with
+    real gradient volume (537 MB of complex64 weight gradients per step) through distributed.OverlappedGradientAllReduce.
+    Training step with AdamW, device time, max over ranks; efficiency against the same step without any reduction."""
+    import math
+    import torch.distributed as dist
+    import pde_fluid_phi_b200 as pb
+    from pde_fluid_phi_b200.distributed import OverlappedGradientAllReduce, allreduce_gradients, broadcast_parameters
+    n, B = 256, 64
+    torch.manual_seed(1234)
+    model = pb.FNO3D(modes=(64, 64, 1), width=64, n_layers=4, in_channels=2, out_channels=2).to(dev).set_precision("tf32")
+    broadcast_parameters(model)
+    params = list(model.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    yy = torch.linspace(0, 2 * math.pi, n, device=dev)
+    base = torch.sin(4 * yy)[None, None, None, :, None].expand(B, 1, n, n, 1)
+    x = torch.cat([base + 0.1 * torch.randn(B, 1, n, n, 1, device=dev, generator=g),
+                   0.1 * torch.randn(B, 1, n, n, 1, device=dev, generator=g)], 1)
+    y = torch.roll(x, 3, dims=3)
+    reducer = OverlappedGradientAllReduce(params, world)
+
+    def step(mode):
+        opt.zero_grad(set_to_none=True)
+        reducer.enabled = mode == "overlapped"
+        loss = torch.nn.functional.mse_loss(model(x), y)
+        loss.backward()
+        if mode == "flat":
+            allreduce_gradients(params, world)
+        elif mode == "overlapped":
+            reducer.finish()
+        opt.step()
+        return loss
+
+    res = {"workload": "FNO3D modes (64,64,1) width 64, 4 layers, [64,2,256,256,1] per GPU, fwd+MSE+bwd+AdamW, tf32 route",
+           "grad_bytes": sum(p.numel() * p.element_size() for p in params), "steps": steps}
+    for mode in ("none", "flat", "overlapped"):
+        for _ in range(3):
+            step(mode)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step(mode)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[f"ms_per_step_{mode}"] = round(float(t), 3)
+    # both reductions give the same gradients from the same weights (element for element)
+    grads = {}
+    for mode in ("flat", "overlapped"):
+        opt.zero_grad(set_to_none=True)
+        reducer.enabled = mode == "overlapped"
+        torch.nn.functional.mse_loss(model(x), y).backward()
+        allreduce_gradients(params, world) if mode == "flat" else reducer.finish()
+        grads[mode] = [p.grad.clone() for p in params]
+    same = all(torch.equal(a, b) for a, b in zip(grads["flat"], grads["overlapped"]))
+    res["overlapped_equals_flat"] = bool(same)
+    res["samples_s"] = round(B * world / res["ms_per_step_overlapped"] * 1e3, 1)
+    res["samples_s_flat"] = round(B * world / res["ms_per_step_flat"] * 1e3, 1)
+    res["efficiency"] = round(res["ms_per_step_none"] / res["ms_per_step_overlapped"], 4)
+    res["loss_finite"] = bool(torch.isfinite(loss))
+    reducer.remove()
+    del model, opt, x, y, grads
+    torch.cuda.empty_cache()
+    if not (same and res["loss_finite"]):
+        raise SystemExit(f"cfg-3 data-parallel step failed its checks: {res}")
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
 def run_native(args):
@@ -333,22 +595,42 @@ def run_native(args):
     e2e_ms = timed(step_e2e, args.steps)
     final_loss = float(h_loss)
 
-    # the other precision route, same step, for the record (2 timed steps)
+    # the other precision route, same step, same number of timed steps, with its own per-kernel profile
     other = None
+    other_prof = None
     if world == 1 and not args.no_other_precision:
         alt = "auto" if args.precision == "tf32" else "tf32"    # "auto" = the modules' default: fp32-grade (split-TF32 tcgen05)
         model.set_precision(alt)
-        for _ in range(2):
+        for _ in range(3):
             step(x, y)
-        alt_ms = timed(lambda: step(x, y), 2) / 2
+        _cabi.profile(enable=True, reset=True)
+        alt_total = timed(lambda: step(x, y), args.steps)
+        other_prof = _cabi.profile_report(timed=True)
+        _cabi.profile(enable=False, reset=True)
+        alt_ms = alt_total / args.steps
         model.set_precision(args.precision)
         other = {"transform_precision": alt, "value": round(B / (alt_ms * 1e-3), 3), "unit": "samples/s",
-                 "ms_per_step": round(alt_ms, 3)}
-    layer_us = None
-    if rank == 0 and world == 1 and not args.no_layer_times:
-        del x, y
+                 "ms_per_step": round(alt_ms, 3), "steps": args.steps, "total_ms": alt_total}
+    fused_ends = bool(getattr(model, "fuse_lift", False) and getattr(model, "fuse_head", False))
+    # N > 1: the slab-decomposed cfg-5 layer (all-to-all transpose) and cfg 3's data-parallel step with real gradient volume
+    slab = cfg3 = None
+    if world > 1 and not args.no_multi_gpu_blocks:
+        del x, y, opt, model
         torch.cuda.empty_cache()
-        layer_us = layer_times(dev, args.precision)
+        slab = slab_block(dev, rank, world, args.precision if args.precision in ("tf32", "fp32") else "tf32")
+        cfg3 = cfg3_dp_block(dev, rank, world)
+        x = y = None
+    layer_us = None
+    incumbent = None
+    if rank == 0 and world == 1:
+        if not args.no_incumbent:
+            del opt, model
+            torch.cuda.empty_cache()
+            incumbent = gpu_incumbent(dev, x, y)
+        if not args.no_layer_times:
+            x = y = None
+            torch.cuda.empty_cache()
+            layer_us = layer_times(dev, args.precision)
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = B * world / (ms_per_step * 1e-3)
@@ -360,67 +642,19 @@ def run_native(args):
         except OSError:
             pass
         peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        # Algorithmic bytes per launch, one launch = all B*C*Nx planes / all B*S/128 tiles.
-        C, (mx, my, mz) = CFG["width"], CFG["modes"]
-        mzh = mz // 2 + 1
-        act = 4.0 * B * C * n ** 3                       # one full-size fp32 activation
-        mid = 8.0 * B * C * n * my * mzh                 # [BC,Nx,my,mzh] complex intermediate
-        modes_b = 8.0 * B * C * mx * my * mzh            # retained modes
-        # The first block takes the input lift (its forward analysis reads the 3-channel input, its block tail generates
-        # h0 and, in the backward, stores no t) and the last block the output projection (its backward generates g'):
-        # per-launch algorithmic bytes of those kernels are averages over the L layers' launches of one step.
-        L = CFG["n_layers"]
-        fused_ends = bool(getattr(model, "fuse_lift", False) and getattr(model, "fuse_head", False)) and args.precision == "tf32"
-        cin = 3
-        a_launch = ((2 * L - 1) + cin / C) / (2 * L) if fused_ends else 1.0          # analysis: 2L launches, one on cin channels
-        alg = {
-            "analysis_zy_tc_kernel": (act + mid) * a_launch, "analysis_zy_kernel": act + mid, "analysis_zy_tc3_kernel": act + mid,
-            "synthesis_zy_tc3_kernel": act + mid + 1.5 * act,   # unfused block route: forward fuses both skip addends, adjoint one
-            "analysis_x_tc3_kernel": mid + modes_b, "synthesis_x_tc3_kernel": mid + modes_b,
-            # fused block route: the forward synthesis lives in block_spectral_fwd_kernel, so every launch of this kernel is
-            # an adjoint one with one addend (the unfused forward launches, if any, carry none: counted from the launches)
-            "synthesis_zy_tc_kernel": act + mid + act,
-            "synthesis_zy_kernel": act + mid + 1.5 * act,   # fp32 route: forward fuses both skip addends, adjoint one
-            "block_tail_fwd_kernel": 4 * act,            # read h, spec; write u, h'
-            # fused forward: read h and V [B,Nx,Ny,64,ldz] (ldz = 2*mzh rounded up to 4 floats); write u, h'
-            # (first block: h generated from the input, one activation less)
-            "block_spectral_fwd_kernel": (3 * act * (L - 1) + 2 * act) / L + 4.0 * B * C * n * n * ((2 * mzh + 3) // 4 * 4)
-            if fused_ends else 3 * act + 4.0 * B * C * n * n * ((2 * mzh + 3) // 4 * 4),
-            # read g', u, h; write gu, t -- first block: no h read, no t write (3 activations); last block: g' generated (4)
-            "block_tail_bwd_kernel": (5 * act * (L - 2) + 3 * act + 4 * act) / L if fused_ends else 5 * act,
-            "analysis_x_tc_kernel": mid + modes_b, "synthesis_x_tc_kernel": mid + modes_b,
-        }
-        per_kernel = {k: {"launches": v[0], "ms_total": round(v[1], 3), "share_of_step": round(v[1] / total_ms, 4)}
-                      for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-        rooflines = {}
-        for k, v in prof.items():
-            if k in alg and v[1] > 0:
-                avg_ms = v[1] / v[0]
-                if k.startswith("block_tail_bwd"):
-                    avg_ms = v[1] / (v[0] / 2)           # the tiny partial-sum reduce kernel shares the counter
-                if k == "synthesis_zy_tc_kernel" and "block_spectral_fwd_kernel" not in prof:
-                    alg[k] = act + mid + 0.5 * act       # unfused forward: half the launches carry no addend
-                ach = alg[k] / (avg_ms * 1e-3) / 1e9
-                rooflines[k] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                                "frac": round(ach / peak, 4), "algorithmic_bytes_per_launch": alg[k],
-                                "avg_launch_ms": round(avg_ms, 4)}
-        hot = [k for k in ("analysis_zy_tc_kernel", "analysis_zy_tc3_kernel", "analysis_zy_kernel") if k in rooflines]
-        dom = max(rooflines, key=lambda k: prof[k][1]) if rooflines else None
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
-        # (captures of the middle blocks' launches: the full-size variants of each kernel)
-        ncu_traffic = {"analysis_zy_tc_kernel": 4.580e9, "synthesis_zy_tc_kernel": 8.822e9, "block_tail_fwd_kernel": 17.187e9,
-                       "block_tail_bwd_kernel": 21.489e9, "block_spectral_fwd_kernel": 14.093e9}
-        for k in rooflines:
-            rooflines[k]["traffic"] = ncu_traffic.get(k)
-            if fused_ends and k in ("block_tail_bwd_kernel", "block_spectral_fwd_kernel"):
-                rooflines[k]["traffic_note"] = ("ncu dram bytes of a middle block's launch; algorithmic_bytes_per_launch is the mean "
-                                                "over the step's launches (the first / last block's launches move fewer activations)")
+        traffic = ncu_traffic_from_profiles()
+        per_kernel, rooflines, dom = kernel_rooflines(prof, total_ms, B, n, args.precision, fused_ends, peak, traffic)
         roof = None
         if dom:
             roof = dict(rooflines[dom], kernel=dom, peak_source=which,
-                        note="largest share of the step; 'rooflines' lists every HBM-bound kernel of the path")
-        if hot:
-            rooflines[hot[0]]["note"] = "K1 fused (z,y) stage: ncu dram bytes 4.58 GB/launch = algorithmic (profiles/)"
+                        note="largest share of the step; 'rooflines' lists every kernel of the path")
+        if other is not None:
+            o_kernels, o_roofs, o_dom = kernel_rooflines(other_prof, other.pop("total_ms"), B, n, other["transform_precision"],
+                                                        fused_ends, peak, traffic)
+            other["roofline"] = dict(o_roofs[o_dom], kernel=o_dom) if o_dom else None
+            other["kernels"] = o_kernels
+        if incumbent is not None and "ms_per_step" in incumbent:
+            incumbent["speedup_of_this_library"] = round(incumbent["ms_per_step"] / ms_per_step, 2)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             t = cpu_layer_slice_seconds(reps=2, warmup=1)
@@ -429,6 +663,9 @@ def run_native(args):
                    "sample": f"{CPU_OUT_SLICE}/64 output channels of one RationalFourierLayer fwd+bwd on one "
                              f"[1,64,128,128,128] sample ({per:.2f} s), scaled x{CFG['width'] // CPU_OUT_SLICE} x{CFG['n_layers']} "
                              "layers; pointwise ops excluded"}
+        k2 = sum(v["ms_total"] for k, v in per_kernel.items()
+                 if k in ("rational_mix_kernel", "mix_from_R_kernel", "rational_g_kernel", "rational_dpq_kernel", "dpq_reduce_kernel",
+                          "projection_stats_kernel", "projection_bwd_kernel", "rational_transfer_kernel"))
         line = {"metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": {"tf32": "tf32", "fp32": "f32"}.get(args.precision, "tf32x3 (fp32-grade)"),
@@ -436,10 +673,116 @@ def run_native(args):
                 "e2e": {"value": round(e2e_value, 3), "unit": "samples/s",
                         "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": rooflines,
-                "cpu_baseline": cpu, "layer_fwd_bwd_us": layer_us, "other_precision": other, "kernels": per_kernel, "first_loss": first_loss, "final_loss": final_loss}
+                "cpu_baseline": cpu, "gpu_incumbent": incumbent, "layer_fwd_bwd_us": layer_us, "other_precision": other,
+                "k2_share_of_step": round(k2 / total_ms, 4), "kernels": per_kernel, "first_loss": first_loss,
+                "final_loss": final_loss}
+        if slab is not None:
+            line["slab"] = slab
+        if cfg3 is not None:
+            line["cfg3_dp"] = cfg3
         print(json.dumps(line), flush=True)
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if world > 1 and os.path.isdir(out_dir):       # kept beside the run for profiles/ (the JSON line carries them too)
+            try:
+                if slab is not None:
+                    json.dump(slab, open(os.path.join(out_dir, f"slab_n{world}.json"), "w"), indent=1)
+                if cfg3 is not None:
+                    json.dump(cfg3, open(os.path.join(out_dir, f"dp_cfg3_n{world}.json"), "w"), indent=1)
+            except OSError:
+                pass
     if world > 1:
         dist.destroy_process_group()
+
+
+def kernel_rooflines(prof, total_ms, B, n, precision, fused_ends, peak, traffic):
+    """({kernel: launches / ms / share}, {kernel: roofline dict}, dominant kernel) from the library's per-launch CUDA events.
+
+    Algorithmic bytes per launch follow DESIGN.md section 5 (one launch = all B*C*Nx planes / all B*S/128 tiles / all modes);
+    `traffic` = measured dram bytes per launch from the ncu summaries under profiles/ (None where no capture exists)."""
+    C, (mx, my, mz), L = CFG["width"], CFG["modes"], CFG["n_layers"]
+    mzh = mz // 2 + 1
+    M = mx * my * mzh
+    act = 4.0 * B * C * n ** 3                       # one full-size fp32 activation
+    mid = 8.0 * B * C * n * my * mzh                 # [BC,Nx,my,mzh] complex intermediate
+    modes_b = 8.0 * B * C * M                        # retained modes of one tensor [B,C,M] complex64
+    tf = 4.0 * C * C * M                             # one materialised transfer-function tensor [O,I,M] fp32 (R, Qe or G)
+    order_p, order_q = CFG["rational_order"]
+    tri = lambda o: o * (o + 1) * (o + 2) // 6
+    fused_ends = fused_ends and precision == "tf32"
+    cin = 3
+    # The first block takes the input lift (its forward analysis reads the 3-channel input, its block tail generates
+    # h0 and, in the backward, stores no t) and the last block the output projection (its backward generates g'):
+    # per-launch algorithmic bytes of those kernels are averages over the L layers' launches of one step.
+    a_launch = ((2 * L - 1) + cin / C) / (2 * L) if fused_ends else 1.0          # analysis: 2L launches, one on cin channels
+    vbytes = 4.0 * B * C * n * n * ((2 * mzh + 3) // 4 * 4)                      # V [B,Nx,Ny,64,ldz]
+    alg = {
+        "analysis_zy_tc_kernel": (act + mid) * a_launch, "analysis_zy_kernel": act + mid, "analysis_zy_tc3_kernel": act + mid,
+        "synthesis_zy_tc3_kernel": act + mid + 1.5 * act,   # unfused block route: forward fuses both skip addends, adjoint one
+        "analysis_x_tc3_kernel": mid + modes_b, "synthesis_x_tc3_kernel": mid + modes_b,
+        # fused block route: the forward synthesis lives in block_spectral_fwd_kernel, so every launch of this kernel is
+        # an adjoint one with one addend (the unfused forward launches, if any, carry none: counted from the launches)
+        "synthesis_zy_tc_kernel": act + mid + act,
+        "synthesis_zy_kernel": act + mid + 1.5 * act,   # fp32 route: forward fuses both skip addends, adjoint one
+        "block_tail_fwd_kernel": 4 * act,            # read h, spec; write u, h'
+        # fused forward: read h and V; write u, h' (first block: h generated from the input, one activation less)
+        "block_spectral_fwd_kernel": (3 * act * (L - 1) + 2 * act) / L + vbytes if fused_ends else 3 * act + vbytes,
+        # read g', u, h; write gu, t -- first block: no h read, no t write (3 activations); last block: g' generated (4)
+        "block_tail_bwd_kernel": (5 * act * (L - 2) + 3 * act + 4 * act) / L if fused_ends else 5 * act,
+        "analysis_x_tc_kernel": mid + modes_b, "synthesis_x_tc_kernel": mid + modes_b,
+        # K2 (DESIGN.md section 5.3).  SURVEY.md section 8d counts 0.145 GB forward / 0.29 GB backward for an evaluation that
+        # never materialises R; this design writes R and Q+eps once per forward (2 x tf) and streams them in the backward.
+        "rational_mix_kernel": 2 * modes_b + 2 * tf + 4.0 * C * C * (order_p ** 3 + order_q ** 3),
+        "rational_transfer_kernel": 2 * tf + 4.0 * C * C * (order_p ** 3 + order_q ** 3),
+        "mix_apply_kernel": 2 * modes_b + tf,
+        "mix_from_R_kernel": 2 * modes_b + tf,       # dY in, dX out, R in
+        "rational_g_kernel": 2 * modes_b + 2 * tf,   # X, dY, Qe in; G out
+        "rational_dpq_kernel": 2 * tf,               # G, R in (the monomial tables stay in L2)
+        "projection_stats_kernel": modes_b, "projection_bwd_kernel": 3 * modes_b,
+        "pointwise_wgrad_kernel": act + 4.0 * B * cin * n ** 3,
+        "gen_axis_synthesis_kernel": None,           # x and y stages of the fused forward share the counter: see below
+    }
+    survey = {"rational_mix_kernel": 2 * modes_b + 4.0 * C * C * (order_p ** 3 + order_q ** 3)}
+    # fp32 instruction floor of the bit-exact P/Q evaluation: one rounded product + one rounded add per monomial and
+    # polynomial (packed two channels per FFMA2), +eps, an IEEE division (~8 issue slots), 2B FMAs of the mix per (o,i,k)
+    lane_ops = C * C * M * ((tri(order_p) + tri(order_q)) + 0.5 + 8 + 2 * B)
+    alu_peak = 148 * 128 * 1.965e9                   # fp32 lanes x SMs x max SM clock: lane-instructions per second
+    per_kernel = {k: {"launches": v[0], "ms_total": round(v[1], 3), "share_of_step": round(v[1] / total_ms, 4)}
+                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    rooflines = {}
+    for k, v in prof.items():
+        if alg.get(k) is None or v[1] <= 0:
+            continue
+        avg_ms = v[1] / v[0]
+        if k.startswith("block_tail_bwd"):
+            avg_ms = v[1] / (v[0] / 2)           # the tiny partial-sum reduce kernel shares the counter
+        if k == "pointwise_wgrad_kernel":
+            avg_ms = v[1] / (v[0] / 2)           # ... and so does this one's
+        a = alg[k]
+        if k == "synthesis_zy_tc_kernel" and "block_spectral_fwd_kernel" not in prof:
+            a = act + mid + 0.5 * act            # unfused forward: half the launches carry no addend
+        ach = a / (avg_ms * 1e-3) / 1e9
+        r = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+             "algorithmic_bytes_per_launch": a, "avg_launch_ms": round(avg_ms, 4)}
+        t = traffic.get(k)
+        r["traffic"] = t[0] if t else None
+        if t:
+            r["traffic_source"] = t[1]
+        if k in survey:
+            r["survey_8d_bytes_per_launch"] = survey[k]
+            r["frac_of_survey_8d_bytes"] = round(survey[k] / (avg_ms * 1e-3) / 1e9 / peak, 4)
+        if k in ("rational_mix_kernel", "rational_transfer_kernel"):
+            ops = lane_ops if k == "rational_mix_kernel" else lane_ops - C * C * M * 2 * B
+            r["alu"] = {"bound": "alu", "achieved": round(ops / (avg_ms * 1e-3) / 1e12, 2), "peak": round(alu_peak / 1e12, 2),
+                        "unit": "T fp32 lane-instructions/s", "frac": round(ops / (avg_ms * 1e-3) / alu_peak, 4),
+                        "note": "instruction-bound by the bit-exact P(k)/Q(k) evaluation (one separately rounded product and add "
+                                "per monomial, packed FFMA2), not by HBM"}
+        if fused_ends and k in ("block_tail_bwd_kernel", "block_spectral_fwd_kernel"):
+            r["traffic_note"] = ("ncu dram bytes of a middle block's launch; algorithmic_bytes_per_launch is the mean "
+                                 "over the step's launches (the first / last block's launches move fewer activations)")
+        rooflines[k] = r
+    big = [k for k in rooflines if rooflines[k]["algorithmic_bytes_per_launch"] >= act]
+    dom = max(big, key=lambda k: prof[k][1]) if big else None
+    return per_kernel, rooflines, dom
 
 
 def layer_times(dev, precision):
@@ -548,6 +891,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layer-times", action="store_true")
     ap.add_argument("--no-other-precision", action="store_true")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the stock-PyTorch (cuFFT) training step on the same GPU")
+    ap.add_argument("--no-multi-gpu-blocks", action="store_true", help="N > 1: skip the cfg-5 slab layer and the cfg-3 DP step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -36,7 +36,7 @@ typedef void* pdephi_stream_t; /* cudaStream_t */
 enum pdephi_status {
   PDEPHI_OK = 0,
   PDEPHI_ERR_INVALID = 1,     /* bad argument (null pointer, size mismatch, modes > grid ...) */
-  PDEPHI_ERR_UNSUPPORTED = 2, /* valid but not implemented (e.g. rational order outside 2..4) */
+  PDEPHI_ERR_UNSUPPORTED = 2, /* valid but not implemented (e.g. a rational order that is not instantiated) */
   PDEPHI_ERR_CUDA = 3,        /* a CUDA runtime call or launch failed */
   PDEPHI_ERR_WORKSPACE = 4    /* workspace too small */
 };

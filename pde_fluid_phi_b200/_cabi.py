@@ -21,6 +21,15 @@ FORWARD, ADJOINT = 0, 1
 STAGES_ZY, STAGES_X, STAGES_ALL = 1, 2, 3
 PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
 
+def rational_order_supported(order) -> bool:
+    """(p, q) pairs the K2 kernels are instantiated for (ORDER_CASES in csrc/mix.cu)."""
+    try:
+        p, q = (int(v) for v in order)
+    except (TypeError, ValueError):
+        return False
+    return (2 <= p <= 4 and 2 <= q <= 4) or (p == q and p in (1, 5, 6))
+
+
 # name -> (restype, argtypes); mirrors include/pdephi_b200.h one to one
 SIGNATURES = {
     "pdephi_version": (c_int, []),

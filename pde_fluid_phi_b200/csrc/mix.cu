@@ -14,7 +14,7 @@
 
 namespace pdephi {
 
-constexpr int MAX_T = 20;  // monomials of order 4
+constexpr int MAX_T = 56;  // monomials of order 6
 struct MonoOffsets {
   int p[MAX_T];
   int q[MAX_T];
@@ -665,7 +665,10 @@ static int launch_dpq(const float2* X, const float2* dY, const float* R, const f
 
 using namespace pdephi;
 
-#define ORDER_CASES CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 2) CASE(3, 3) CASE(3, 4) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+// every (p, q) in 2..4 -- the orders the reference's models construct (rational_fourier.py:33, rfno.py:66,
+// multiscale_fno.py:100-127) -- plus the symmetric orders 1, 5 and 6 (quantum_rational_fourier.py:392 asks for (6,6))
+#define ORDER_CASES CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 2) CASE(3, 3) CASE(3, 4) CASE(4, 2) CASE(4, 3) CASE(4, 4) \
+  CASE(1, 1) CASE(5, 5) CASE(6, 6)
 
 extern "C" int pdephi_rational_mix_fwd(const float* X, const float* P, const float* Q, const float* monoP,
                                        const float* monoQ, int order_p, int order_q, float eps, const float* mask,
@@ -686,7 +689,7 @@ extern "C" int pdephi_rational_mix_fwd(const float* X, const float* P, const flo
     rc = launch_mix<a, b>((const float2*)X, (float2*)Y, P, Q, monoP, monoQ, eps, R_out, Qe_out, B, O, I, M, offs, st);
   ORDER_CASES
 #undef CASE
-  if (rc == -1) return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) outside the supported range 2..4", order_p, order_q);
+  if (rc == -1) return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) is not instantiated (supported: every (p,q) in 2..4, and (1,1), (5,5), (6,6))", order_p, order_q);
   if (rc) return rc;
   {
     ProfScope ps(K_PROJ_STATS, st);
@@ -759,7 +762,7 @@ extern "C" int pdephi_rational_mix_bwd(const float* X, const float* dY, const fl
                             (float*)workspace, Gbuf, offs, st);
   ORDER_CASES
 #undef CASE
-  return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) outside the supported range 2..4", order_p, order_q);
+  return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) is not instantiated (supported: every (p,q) in 2..4, and (1,1), (5,5), (6,6))", order_p, order_q);
 }
 
 extern "C" int pdephi_complex_mix_fwd(const float* X, const float* W, float* Y, int B, int I, int O, long long mxy,

@@ -90,6 +90,8 @@ using namespace pdephi;
 extern "C" int pdephi_version(void) { return PDEPHI_VERSION; }
 extern "C" const char* pdephi_last_error(void) { return err_buf(); }
 
+static int plan_build(Plan* p, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh, int Nx_total, int x_offset);
+
 extern "C" int pdephi_plan_create(pdephi_plan_t* out, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh) {
   return pdephi_plan_create_slab(out, device, Nx, Ny, Nz, mx, my, mzh, Nx, 0);
 }
@@ -108,6 +110,17 @@ extern "C" int pdephi_plan_create_slab(pdephi_plan_t* out, int device, int Nx, i
   PDEPHI_CUDA(cudaSetDevice(device));
   Plan* p = new Plan();
   memset(p, 0, sizeof(Plan));
+  // every failure below unwinds through here: the partially built plan and its device arenas are released and the
+  // caller's current device is restored (an out-of-memory error on one GPU must not leave the thread on another)
+  const int rc = plan_build(p, device, Nx, Ny, Nz, mx, my, mzh, Nx_total, x_offset);
+  if (rc != PDEPHI_OK) pdephi_plan_destroy((pdephi_plan_t)p);
+  cudaSetDevice(cur);
+  if (rc != PDEPHI_OK) return rc;
+  *out = (pdephi_plan_t)p;
+  return PDEPHI_OK;
+}
+
+static int plan_build(Plan* p, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh, int Nx_total, int x_offset) {
   p->device = device;
   p->Nx = Nx; p->Ny = Ny; p->Nz = Nz; p->mx = mx; p->my = my; p->mzh = mzh;
   p->Nx_total = Nx_total; p->x_offset = x_offset;
@@ -158,8 +171,6 @@ extern "C" int pdephi_plan_create_slab(pdephi_plan_t* out, int device, int Nx, i
     if (rc) return rc;
   }
   PDEPHI_CUDA(cudaDeviceSynchronize());  // plan creation is the one synchronous call
-  PDEPHI_CUDA(cudaSetDevice(cur));
-  *out = (pdephi_plan_t)p;
   return PDEPHI_OK;
 }
 

@@ -214,6 +214,13 @@ def head_supported(linear) -> bool:
             and linear.weight.is_cuda and linear.weight.dtype == torch.float32)
 
 
+def lift_supported(linear) -> bool:
+    """The input lift the first block can generate in its loader warps: nn.Linear(at most 4 inputs -> 64), fp32 on CUDA
+    (MAXP_IN of block_tc.cu; wider inputs take the separate pointwise-linear pass)."""
+    return (isinstance(linear, torch.nn.Linear) and linear.out_features == 64 and 1 <= linear.in_features <= 4
+            and linear.weight.is_cuda and linear.weight.dtype == torch.float32)
+
+
 def block_tail_fwd(h, spec, Wc, bc, head=None, lift=None):
     """u = spec + (Wc h + bc) + h, hout = gelu(u) on [B,64,...] tensors (tcgen05 TF32 channel GEMM, fused epilogue).
     head = (Wp [n,64], bp [n] | None): additionally returns out = Wp hout + bp, computed in the same epilogue.
@@ -517,6 +524,17 @@ def _allreduce_modes(X, group):
 
 
 
+def _unit_stats(stats: torch.Tensor) -> torch.Tensor:
+    """StabilityProjection(energy_conserving=False) (stability.py:81-83): the decay mask alone.  Row statistics
+    {a, b, s} = {inf, inf, 1} make every consumer exact for that case: K3 multiplies by s = 1, and the projection backward
+    dY = m s dZ + G s (1/a - m^2/b) Y loses its second term (1/inf = 0)."""
+    out = torch.empty_like(stats)
+    out[:, :2] = float("inf")
+    out[:, 2] = 1.0
+    out[:, 3] = 0.0
+    return out
+
+
 class PrunedAnalysisFn(torch.autograd.Function):
     """K1 alone with autograd: X = rfftn(x)[..., :mx, :my, :mzh].  Backward is the ADJOINT synthesis."""
 
@@ -571,7 +589,8 @@ class RationalSpectralFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, P, Q, mask, monoP, monoQ, modes, eps, precision, skip0, residual, slab=None):
+    def forward(ctx, x, P, Q, mask, monoP, monoQ, modes, eps, precision, skip0, residual, slab=None, proj=None):
+        # proj = (eps, energy_conserving) of the layer's StabilityProjection (stability.py:27-38); None: (eps, True)
         for t, n in ((x, "x"), (P, "P_coeffs"), (Q, "Q_coeffs")):
             _require_cuda_f32(t, n)
         mx, my, mz = modes
@@ -580,12 +599,13 @@ class RationalSpectralFn(torch.autograd.Function):
         sl = _Slab(slab, x)
         P = P.contiguous()
         Q = Q.contiguous()
+        proj_eps, energy = (float(eps), True) if proj is None else (float(proj[0]), bool(proj[1]))
         if sl.sharded:      # this rank mixes its ky chunk of the modes only
             mask, monoP, monoQ = sl.local_modes(mask, modes_h), sl.local_modes(monoP, modes_h, 1), sl.local_modes(monoQ, modes_h, 1)
         X = sl.analysis(x, modes_h, _cabi.FORWARD, precision)
         need_grad = any(ctx.needs_input_grad[:3])
-        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
-        stats = sl.complete_stats(stats, eps)
+        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, proj_eps, keep_transfer=need_grad)
+        stats = sl.complete_stats(stats, proj_eps) if energy else _unit_stats(stats)
         out = sl.synthesis(Y, grid, mask, stats[:, 2], skip0, x if residual else None, _cabi.FORWARD, precision)
         if need_grad:
             ctx.save_for_backward(X, Y, stats, R, Qe, mask, monoP, monoQ)
@@ -596,12 +616,12 @@ class RationalSpectralFn(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     @once_differentiable
     def backward(ctx, g):
-        X, Y, stats, R, Qe, mask, monoP, monoQ = ctx.saved_tensors
         modes_h, grid, coeff_shapes, precision, has0, residual, sl = ctx.meta
         g = g.contiguous()
         need_x, need_P, need_Q = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dx = dP = dQ = None
-        if need_x or need_P or need_Q:
+        if need_x or need_P or need_Q:      # otherwise only skip0 wants a gradient (g itself) and nothing was saved
+            X, Y, stats, R, Qe, mask, monoP, monoQ = ctx.saved_tensors
             dZ = sl.analysis(g, modes_h, _cabi.ADJOINT, precision)
             dY = sl.projection_bwd(dZ, Y, mask, stats)
             dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
@@ -609,7 +629,7 @@ class RationalSpectralFn(torch.autograd.Function):
             if need_x:   # the residual branch's gradient (g itself) rides in the synthesis epilogue
                 dx = sl.synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT, precision)
         return (dx, dP if need_P else None, dQ if need_Q else None, None, None, None, None, None, None,
-                g if has0 else None, None, None)
+                g if has0 else None, None, None, None)
 
 
 def _local_weights(W, sl, my):
@@ -796,7 +816,7 @@ class RationalBlockFn(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, h, P, Q, mask, monoP, monoQ, modes, eps, precision, Wc, bc, slab=None, Wp=None, bp=None, Win=None,
-                bin_=None):
+                bin_=None, proj=None):
         # Wp / bp: the model's output projection, fused into this (the last) block: the result is then Wp h' + bp
         # Win / bin_: the model's input lift, taken into this (the first) block: `h` is then the model input x
         for t, n in ((h, "x"), (P, "P_coeffs"), (Q, "Q_coeffs"), (Wc, "conv weight")):
@@ -819,8 +839,9 @@ class RationalBlockFn(torch.autograd.Function):
         else:
             X = sl.analysis(h, modes_h, _cabi.FORWARD, precision)
         need_grad = any(ctx.needs_input_grad)
-        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, eps, keep_transfer=need_grad)
-        stats = sl.complete_stats(stats, eps)
+        proj_eps, energy = (float(eps), True) if proj is None else (float(proj[0]), bool(proj[1]))
+        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, proj_eps, keep_transfer=need_grad)
+        stats = sl.complete_stats(stats, proj_eps) if energy else _unit_stats(stats)
         head = _head_tuple(Wp, bp)
         if not sl.active and block_spectral_supported(h, modes_h, precision, Y.shape[1]):
             res = block_spectral_fwd(Y, mask, stats[:, 2], h, Wc, bc, head, lift)    # `spec` never touches HBM
@@ -870,7 +891,7 @@ class RationalBlockFn(torch.autograd.Function):
                 dh, dWin, dbin = _pointwise_linear_backward(x_in, Win, gh0, True, True, lift_bias)
         else:
             dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, precision)
-        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin)
+        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin, None)
 
 
 class ComplexBlockFn(torch.autograd.Function):

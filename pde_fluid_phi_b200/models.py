@@ -5,9 +5,11 @@
 
 Constructor signatures, sub-module / parameter names and the order in which the global RNG is
 consumed match the reference, so ``torch.manual_seed(s); Model(...)`` gives the same weights and
-checkpoints load either way.  Per block the spectral layer, the two skip adds and (inside the
-layer) the projection run in libpdephi_b200.so, as do the lift / project Linears (SURVEY.md section 8f
-row N2); the 1x1x1 convolution and GELU stay with torch (row N1).
+checkpoints load either way.  At width 64 (and 32) with the GELU activation a whole block -- spectral
+layer, 1x1x1 convolution, both residual adds, exact GELU -- runs in libpdephi_b200.so, with the input
+lift folded into the first block and the output projection into the last (SURVEY.md section 8f rows N1,
+N2); other widths / activations keep torch's Conv3d and activation around the library's spectral
+layer, whose synthesis epilogue still carries both skip adds.
 """
 from __future__ import annotations
 

@@ -51,10 +51,10 @@ def get_grid(modes: Tuple[int, int, int], device: Union[str, torch.device] = "cp
 
 
 def _lifted_ok(layer, x: torch.Tensor, conv: nn.Module, lift: nn.Module) -> bool:
-    from .functional import block_tail_supported_shape, pointwise_linear_supported
+    from .functional import block_tail_supported_shape, lift_supported, pointwise_linear_supported
     return (layer.slab is None and isinstance(lift, nn.Linear) and isinstance(x, torch.Tensor) and x.dim() == 5
             and x.shape[1] == lift.in_features and lift.out_features == layer.in_channels
-            and pointwise_linear_supported(x, lift.weight)
+            and pointwise_linear_supported(x, lift.weight) and lift_supported(lift)
             and isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.groups == 1
             and conv.in_channels == conv.out_channels == layer.in_channels == layer.out_channels
             and block_tail_supported_shape(x.is_cuda, x.dtype, lift.out_features, x[0, 0].numel(), layer._precision_code())
@@ -125,6 +125,9 @@ class RationalFourierLayer(nn.Module):
         self.out_channels = out_channels
         self.modes = modes
         self.rational_order = rational_order
+        if not _cabi.rational_order_supported(tuple(rational_order)):
+            raise NotImplementedError(f"rational_order {tuple(rational_order)}: the kernels are instantiated for every (p, q) "
+                                      "with p, q in 2..4 and for (1, 1), (5, 5), (6, 6)")
         self.stability_eps = stability_eps
         self.precision: Optional[str] = None     # None -> module-level default
         self.slab = None                         # (process_group, Nx_total) for the slab-decomposed transform
@@ -165,13 +168,24 @@ class RationalFourierLayer(nn.Module):
     def _precision_code(self) -> int:
         return _cabi.PRECISIONS[self.precision or _default_precision]
 
+    def _projection(self):
+        """(eps, energy_conserving) of the stability_projection submodule, which the fused kernels implement
+        (the reference calls the submodule, rational_fourier.py:167, so its attributes are honoured here)."""
+        proj = self.stability_projection
+        if type(proj) is not StabilityProjection:
+            raise NotImplementedError(
+                f"RationalFourierLayer.forward fuses the stock StabilityProjection into its kernels; the layer's "
+                f"stability_projection is a {type(proj).__name__}.  Call rational_multiply / stability_projection (torch ops on "
+                "full spectra) directly for a custom projection.")
+        return (float(proj.eps), bool(proj.energy_conserving))
+
     def _run(self, x, skip0, residual):
         _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
         if self.in_channels != self.out_channels:
             raise RuntimeError("RationalFourierLayer needs in_channels == out_channels (as the reference does)")
         return library_call(RationalSpectralFn, x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
                                         self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
-                                        self._precision_code(), skip0, residual, self.slab)
+                                        self._precision_code(), skip0, residual, self.slab, self._projection())
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._run(x, None, False)
@@ -204,7 +218,8 @@ class RationalFourierLayer(nn.Module):
                             self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
                             self._precision_code(), conv.weight, conv.bias, self.slab,
                             head.weight if head is not None else None, head.bias if head is not None else None,
-                            lift.weight if lift is not None else None, lift.bias if lift is not None else None)
+                            lift.weight if lift is not None else None, lift.bias if lift is not None else None,
+                            self._projection())
 
 
 class SpectralConv3D(nn.Module):

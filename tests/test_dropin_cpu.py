@@ -126,3 +126,33 @@ def test_rollout_fixture_is_self_consistent():
     assert np.array_equal(z["traj_adaptive"][:, 0], z["x"]) and np.array_equal(z["traj_fixed"][:, 0], z["x"])
     want = d64.synthesis(d64.analysis(z["x"].astype(np.float64), (8, 8, 4)), (12, 12, 12))
     assert so.rel_l2(torch.from_numpy(z["dealias"]).double(), torch.from_numpy(np.asarray(want))) < 1e-6
+
+
+def test_rational_orders_the_kernels_cover():
+    """Every (p, q) in 2..4 and the symmetric orders 1, 5, 6 construct (same parameter shapes as the reference for any
+    order, rational_fourier.py:59-71); anything else is refused at construction, not at the first forward."""
+    for order in [(2, 2), (4, 3), (3, 4), (1, 1), (5, 5), (6, 6)]:
+        layer = pb.RationalFourierLayer(2, 2, (4, 4, 4), rational_order=order)
+        assert layer.P_coeffs.shape == (2, 2, order[0], order[0], order[0])
+        assert layer.Q_coeffs.shape == (2, 2, order[1], order[1], order[1])
+        assert layer._mono_p.shape[0] == order[0] * (order[0] + 1) * (order[0] + 2) // 6
+    for order in [(1, 3), (5, 4), (7, 7), (0, 2)]:
+        with pytest.raises(NotImplementedError, match="rational_order"):
+            pb.RationalFourierLayer(2, 2, (4, 4, 4), rational_order=order)
+
+
+def test_fused_route_guards_are_host_side():
+    """The lift the first block can absorb is capped at 4 input channels (MAXP_IN of block_tc.cu) and the projection at 4
+    outputs: checked on the host so a 5..8-channel input takes the separate lift pass instead of a kernel error."""
+    from pde_fluid_phi_b200.functional import head_supported, lift_supported
+    assert lift_supported(torch.nn.Linear(3, 64)) is False      # CPU weights: never (the GPU cases are in test_parity_gpu.py)
+    assert head_supported(torch.nn.Linear(64, 3)) is False
+    layer = pb.RationalFourierLayer(4, 4, (4, 4, 4))
+
+    class Custom(pb.StabilityProjection):
+        pass
+    layer.stability_projection = Custom((4, 4, 4))
+    with pytest.raises(NotImplementedError, match="stability_projection"):
+        layer._projection()
+    layer.stability_projection = pb.StabilityProjection((4, 4, 4), eps=1e-3, energy_conserving=False)
+    assert layer._projection() == (1e-3, False)
