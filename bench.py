@@ -717,7 +717,8 @@ def kernel_rooflines(prof, total_ms, B, n, precision, fused_ends, peak, traffic)
     vbytes = 4.0 * B * C * n * n * ((2 * mzh + 3) // 4 * 4)                      # V [B,Nx,Ny,64,ldz]
     alg = {
         "analysis_zy_tc_kernel": (act + mid) * a_launch, "analysis_zy_kernel": act + mid, "analysis_zy_tc3_kernel": act + mid,
-        "synthesis_zy_tc3_kernel": act + mid + 1.5 * act,   # unfused block route: forward fuses both skip addends, adjoint one
+        # fp32-grade route, unfused block: forward fuses both skip addends, adjoint one; tf32 route: adjoint launches only
+        "synthesis_zy_tc3_kernel": act + mid + (act if precision == "tf32" else 1.5 * act),
         "analysis_x_tc3_kernel": mid + modes_b, "synthesis_x_tc3_kernel": mid + modes_b,
         # fused block route: the forward synthesis lives in block_spectral_fwd_kernel, so every launch of this kernel is
         # an adjoint one with one addend (the unfused forward launches, if any, carry none: counted from the launches)

@@ -72,10 +72,20 @@ int pdephi_plan_create(pdephi_plan_t* plan, int device, int Nx, int Ny, int Nz, 
 int pdephi_plan_create_slab(pdephi_plan_t* plan, int device, int Nx, int Ny, int Nz, int mx, int my, int mzh,
                             int Nx_total, int x_offset);
 int pdephi_plan_destroy(pdephi_plan_t plan);
-/* 1 if the plan's (grid, modes) shape is covered by the kernels of `precision` (FP32 covers every shape; TF32X3 and the fused
- * TF32 kernels need Ny = 128, Nz in {64,128}, my <= 32, mzh <= 20; TF32 additionally covers, through the per-axis
+/* 1 if the plan's (grid, modes) shape is covered by the kernels of `precision` (FP32 covers every shape; the fused TF32 /
+ * TF32X3 kernels need Ny = 128, Nz in {64,128}, my <= 32, mzh <= 20; both additionally cover, through the per-axis
  * kernels, axes that are multiples of 32 up to 256 with up to 64 retained modes each and 2-D grids [Nx,Ny,1]), else 0 */
 int pdephi_plan_supports(pdephi_plan_t plan, int precision);
+/* Which kernel family a transform of `precision` takes on this plan's shape.  The host side uses it to choose between the
+ * fp32-grade routes ('auto'): the fused kernels win at every size they cover, the per-axis split kernels (three launches
+ * per axis stage) only once the volume is large enough to hide their launch count. */
+enum pdephi_route {
+  PDEPHI_ROUTE_NONE = 0,     /* precision not available for this shape */
+  PDEPHI_ROUTE_FFMA = 1,     /* transforms_simt.cu */
+  PDEPHI_ROUTE_FUSED_TC = 2, /* fused (z,y) + x stage tcgen05 kernels (transforms_tc.cu / transforms_tc3.cu / xstage_tc.cu) */
+  PDEPHI_ROUTE_PER_AXIS_TC = 3 /* one tcgen05 contraction per axis (transforms_gen.cu) */
+};
+int pdephi_plan_route(pdephi_plan_t plan, int precision);
 /* bytes of scratch the two transforms need for `BC` (= batch*channels) volumes */
 size_t pdephi_plan_workspace_bytes(pdephi_plan_t plan, long long BC);
 
@@ -226,6 +236,13 @@ int pdephi_block_spectral_lift_fwd(pdephi_plan_t plan, const float* Y, const flo
 int pdephi_block_tail_lift_bwd(const float* g, const float* u, const float* x, const float* Win, const float* bin, int n_in,
                                const float* Wc, float* gu, float* t, float* dWc, float* dbc, int B, int C, long long S,
                                void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
+/* ---- run-time options ------------------------------------------------------------------------------
+ * PDEPHI_OPT_TF32_XSTAGE_SPLIT (default 1): on the single-pass TF32 route the x stage -- which works on the pruned
+ * intermediate, 6.6 % of an activation -- runs split (fp32-grade), removing one of the transform's three TF32 roundings. */
+enum pdephi_option { PDEPHI_OPT_TF32_XSTAGE_SPLIT = 0 };
+int pdephi_set_option(int key, int value);
+int pdephi_get_option(int key);
 
 /* ---- per-kernel launch counters and CUDA-event timing (measurement support for bench.py) ------
  * Launches are always counted.  With timing enabled every kernel launch is bracketed by a pair of

@@ -19,6 +19,9 @@ PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 PREC_AUTO = -1    # host-side only: TF32X3 where the plan supports it, FP32 (FFMA) elsewhere -- both meet the 1e-5 gate
 FORWARD, ADJOINT = 0, 1
 STAGES_ZY, STAGES_X, STAGES_ALL = 1, 2, 3
+OPT_TF32_XSTAGE_SPLIT = 0
+ROUTE_NONE, ROUTE_FFMA, ROUTE_FUSED_TC, ROUTE_PER_AXIS_TC = 0, 1, 2, 3
+PER_AXIS_SPLIT_MIN_POINTS = 1 << 25      # 'auto': below this many points per call the FFMA kernels beat the per-axis split route
 PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
 
 def rational_order_supported(order) -> bool:
@@ -39,6 +42,7 @@ SIGNATURES = {
     "pdephi_plan_destroy": (c_int, [c_void_p]),
     "pdephi_plan_workspace_bytes": (c_size_t, [c_void_p, c_longlong]),
     "pdephi_plan_supports": (c_int, [c_void_p, c_int]),
+    "pdephi_plan_route": (c_int, [c_void_p, c_int]),
     "pdephi_analysis_r2c": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pdephi_analysis_stages": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pdephi_synthesis_stages": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
@@ -85,6 +89,8 @@ SIGNATURES = {
                                                c_void_p]),
     "pdephi_block_tail_lift_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_size_t, c_void_p]),
+    "pdephi_set_option": (c_int, [c_int, c_int]),
+    "pdephi_get_option": (c_int, [c_int]),
     "pdephi_profile_enable": (c_int, [c_int]),
     "pdephi_profile_reset": (c_int, []),
     "pdephi_profile_num_kernels": (c_int, []),
@@ -156,16 +162,28 @@ _auto_route = {}
 _ws_bytes = {}
 
 
-def resolve_precision(plan, precision: int) -> int:
-    """PREC_AUTO -> the fastest route that meets the fp32 parity gate for this plan's shape (cached per plan: at the
-    small shapes of cfg 1 a layer is launch-latency-bound and every ctypes round trip counts)."""
+def plan_route(plan, precision: int) -> int:
+    """pdephi_plan_route(plan, precision), cached (at the small shapes of cfg 1 a layer is launch-latency-bound and every
+    ctypes round trip counts)."""
+    key = (plan.value, precision)
+    r = _auto_route.get(key)
+    if r is None:
+        r = load().pdephi_plan_route(plan, precision)
+        _auto_route[key] = r
+    return r
+
+
+def resolve_precision(plan, precision: int, points: int = 0) -> int:
+    """PREC_AUTO -> the fastest route that meets the fp32 parity gate for this plan's shape and `points` (= volumes x grid
+    points of the call; 0 = unknown / large).  The fused split-TF32 kernels win wherever they apply; the per-axis split
+    kernels run every axis stage as three launches and beat the FFMA kernels only once the call is large enough to hide
+    them (measured on the B200: [4,32,32^3] FFMA 0.39 ms vs 0.96 ms per layer, [1,64,128^3] modes 64^3 the other way)."""
     if precision != PREC_AUTO:
         return precision
-    r = _auto_route.get(plan.value)
-    if r is None:
-        r = PREC_TF32X3 if load().pdephi_plan_supports(plan, PREC_TF32X3) else PREC_FP32
-        _auto_route[plan.value] = r
-    return r
+    route = plan_route(plan, PREC_TF32X3)
+    if route == ROUTE_FUSED_TC or (route == ROUTE_PER_AXIS_TC and (points == 0 or points >= PER_AXIS_SPLIT_MIN_POINTS)):
+        return PREC_TF32X3
+    return PREC_FP32
 
 
 def workspace_bytes(plan, BC: int) -> int:

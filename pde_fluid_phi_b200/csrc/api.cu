@@ -18,9 +18,12 @@ int synthesis_tc3(const Plan* p, const float2* Z, float* out, const float* add0,
                   const float* mode_scale, const float* row_scale, long long rs_stride, long long BC, int direction,
                   float2* ws, cudaStream_t st, int stages, float2* T);
 bool gen_supported(const Plan* p);
-int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int direction, void* ws, cudaStream_t st, int stages, float2* T);
+bool gen_x3_supported(const Plan* p);
+int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int direction, void* ws, cudaStream_t st, int stages, float2* T,
+                 bool x3);
 int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1, const float* mode_scale,
-                  const float* row_scale, long long rs_stride, long long BC, int direction, void* ws, cudaStream_t st, int stages, float2* T);
+                  const float* row_scale, long long rs_stride, long long BC, int direction, void* ws, cudaStream_t st, int stages, float2* T,
+                  bool x3);
 }  // namespace pdephi
 
 using namespace pdephi;
@@ -30,8 +33,19 @@ extern "C" int pdephi_plan_supports(pdephi_plan_t plan, int precision) {
   if (!p) return 0;
   if (precision == PDEPHI_PREC_FP32) return 1;
   if (precision == PDEPHI_PREC_TF32) return (tc_supported(p) || gen_supported(p)) ? 1 : 0;
-  if (precision == PDEPHI_PREC_TF32X3) return tc3_supported(p) ? 1 : 0;
+  if (precision == PDEPHI_PREC_TF32X3) return (tc3_supported(p) || gen_x3_supported(p)) ? 1 : 0;
   return 0;
+}
+
+extern "C" int pdephi_plan_route(pdephi_plan_t plan, int precision) {
+  const Plan* p = (const Plan*)plan;
+  if (!p) return PDEPHI_ROUTE_NONE;
+  if (precision == PDEPHI_PREC_FP32) return PDEPHI_ROUTE_FFMA;
+  if (precision == PDEPHI_PREC_TF32)
+    return tc_supported(p) ? PDEPHI_ROUTE_FUSED_TC : (gen_supported(p) ? PDEPHI_ROUTE_PER_AXIS_TC : PDEPHI_ROUTE_NONE);
+  if (precision == PDEPHI_PREC_TF32X3)
+    return tc3_supported(p) ? PDEPHI_ROUTE_FUSED_TC : (gen_x3_supported(p) ? PDEPHI_ROUTE_PER_AXIS_TC : PDEPHI_ROUTE_NONE);
+  return PDEPHI_ROUTE_NONE;
 }
 
 static int check_common(const Plan* p, long long BC, int direction, int precision, int stages, void* ws, size_t ws_bytes,
@@ -51,7 +65,7 @@ static int check_common(const Plan* p, long long BC, int direction, int precisio
   if (precision == PDEPHI_PREC_TF32 && !tc_supported(p) && !gen_supported(p))
     return fail(PDEPHI_ERR_UNSUPPORTED, "%s: TF32 tensor-core path does not support grid (%d,%d,%d) modes (%d,%d,%d)", who, p->Nx,
                 p->Ny, p->Nz, p->mx, p->my, p->mzh);
-  if (precision == PDEPHI_PREC_TF32X3 && !tc3_supported(p))
+  if (precision == PDEPHI_PREC_TF32X3 && !tc3_supported(p) && !gen_x3_supported(p))
     return fail(PDEPHI_ERR_UNSUPPORTED, "%s: split-TF32 tensor-core path does not support grid (%d,%d,%d) modes (%d,%d,%d)", who,
                 p->Nx, p->Ny, p->Nz, p->mx, p->my, p->mzh);
   return PDEPHI_OK;
@@ -65,9 +79,12 @@ static int run_analysis(const Plan* p, const float* in, float* out, long long BC
   float2* T = stages == ST_ZY ? (float2*)out : (stages == ST_X ? (float2*)const_cast<float*>(in) : nullptr);
   if (precision == PDEPHI_PREC_TF32) {
     if (tc_supported(p)) return analysis_tc(p, x, X, BC, direction, (float2*)workspace, st, stages, T);
-    return analysis_gen(p, x, X, BC, direction, workspace, st, stages, T);
+    return analysis_gen(p, x, X, BC, direction, workspace, st, stages, T, false);
   }
-  if (precision == PDEPHI_PREC_TF32X3) return analysis_tc3(p, x, X, BC, direction, (float2*)workspace, st, stages, T);
+  if (precision == PDEPHI_PREC_TF32X3) {
+    if (tc3_supported(p)) return analysis_tc3(p, x, X, BC, direction, (float2*)workspace, st, stages, T);
+    return analysis_gen(p, x, X, BC, direction, workspace, st, stages, T, true);
+  }
   return analysis_simt(p, x, X, BC, direction, (float2*)workspace, st, stages, T);
 }
 
@@ -81,10 +98,13 @@ static int run_synthesis(const Plan* p, const float* in, float* out, const float
   if (precision == PDEPHI_PREC_TF32) {
     if (tc_supported(p))
       return synthesis_tc(p, Z, o, a0, a1, mode_scale, row_scale, rs_stride, BC, direction, (float2*)workspace, st, stages, T);
-    return synthesis_gen(p, Z, o, a0, a1, mode_scale, row_scale, rs_stride, BC, direction, workspace, st, stages, T);
+    return synthesis_gen(p, Z, o, a0, a1, mode_scale, row_scale, rs_stride, BC, direction, workspace, st, stages, T, false);
   }
-  if (precision == PDEPHI_PREC_TF32X3)
-    return synthesis_tc3(p, Z, o, a0, a1, mode_scale, row_scale, rs_stride, BC, direction, (float2*)workspace, st, stages, T);
+  if (precision == PDEPHI_PREC_TF32X3) {
+    if (tc3_supported(p))
+      return synthesis_tc3(p, Z, o, a0, a1, mode_scale, row_scale, rs_stride, BC, direction, (float2*)workspace, st, stages, T);
+    return synthesis_gen(p, Z, o, a0, a1, mode_scale, row_scale, rs_stride, BC, direction, workspace, st, stages, T, true);
+  }
   return synthesis_simt(p, Z, o, a0, a1, mode_scale, row_scale, rs_stride, BC, direction, (float2*)workspace, st, stages, T);
 }
 

@@ -45,6 +45,14 @@ struct GenPlan {
   float* zs[2];             // z synthesis B images [direction]
   float* ya; float* ysc; float* yss;   // y axis: analysis A (plain [128][Ny]), synthesis cos / sin images
   float* xa; float* xsc; float* xss;   // x axis
+  // split-TF32 (fp32-grade) variant of the route: lo parts of the axis images, stacked [hi | lo] z images per column block
+  int x3_ok;
+  float* ya_lo; float* ysc_lo; float* yss_lo;
+  float* xa_lo; float* xsc_lo; float* xss_lo;
+  int za3_np, za3_nc, za3_ring, za3_lo;          // z analysis: np launches over ranges of k-blocks, nc = nbm output columns
+  float* za3[2];                                 // [direction] stacked (hi rows | lo rows) image
+  int zs3_np, zs3_c0[8], zs3_nc[8], zs3_ring[8]; // z synthesis: blocks of output positions
+  float* zs3[2][8];
 };
 
 struct Plan {
@@ -89,6 +97,7 @@ struct Plan {
   float* xtc3_ss[2];
   int gen_ok;
   void* gen_arena;
+  void* gen_arena3;   // operand images of the split-TF32 variant
   GenPlan g;
 };
 int tc_plan_init(Plan* p);
@@ -108,6 +117,9 @@ enum KernelId {
   K_ANALYSIS_ZY_TC3, K_SYNTHESIS_ZY_TC3, K_ANALYSIS_X_TC3, K_SYNTHESIS_X_TC3,
   K_GEN_Z_ANALYSIS, K_GEN_Z_SYNTHESIS, K_GEN_AXIS_ANALYSIS, K_GEN_AXIS_SYNTHESIS, K_BLOCK_SPECTRAL_FWD, K_COUNT
 };
+// run-time options (pdephi_set_option)
+enum { OPT_TF32_XSTAGE_SPLIT = 0, OPT_COUNT };
+int option_get(int key);
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 struct ProfScope {

@@ -30,6 +30,8 @@ static const char* const kKernelNames[K_COUNT] = {
     "synthesis_zy_tc3_kernel", "analysis_x_tc3_kernel", "synthesis_x_tc3_kernel", "gen_z_analysis_kernel",
     "gen_z_synthesis_kernel", "gen_axis_analysis_kernel", "gen_axis_synthesis_kernel", "block_spectral_fwd_kernel"};
 struct ProfRec { int id; cudaEvent_t a, b; };
+// option defaults: the x stage of the single-pass TF32 route runs split (fp32-grade) -- see pdephi_set_option
+static std::atomic<int> g_options[OPT_COUNT] = {{1}};
 static std::atomic<long long> g_launches[K_COUNT];
 static std::atomic<bool> g_prof_on{false};
 static std::mutex g_prof_mu;
@@ -43,6 +45,8 @@ static cudaEvent_t get_event() {
   cudaEventCreate(&e);
   return e;
 }
+int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key].load() : 0; }
+
 void prof_begin(int id, cudaStream_t st) {
   g_launches[id].fetch_add(1, std::memory_order_relaxed);
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
@@ -197,6 +201,13 @@ extern "C" size_t pdephi_plan_workspace_bytes(pdephi_plan_t h, long long BC) {
   const size_t general = (p->gen_ok && !p->tc_ok) ? gen_workspace_bytes(p, BC) : 0;
   return fused > general ? fused : general;
 }
+
+extern "C" int pdephi_set_option(int key, int value) {
+  PDEPHI_REQUIRE(key >= 0 && key < OPT_COUNT, "set_option: unknown option %d", key);
+  g_options[key].store(value);
+  return PDEPHI_OK;
+}
+extern "C" int pdephi_get_option(int key) { return option_get(key); }
 
 extern "C" int pdephi_profile_enable(int on) {
   g_prof_on.store(on != 0);

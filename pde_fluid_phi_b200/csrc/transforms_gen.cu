@@ -56,17 +56,23 @@ __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
 // wmode 0: w = 1, 1: w = c_k / total (c_k = 1 for k = 0 and Nyquist, else 2), 2: w = 1 / total
 // ------------------------------------------------------------------------------------------------
 __global__ void gen_image_kernel(float* __restrict__ img, int kind, int R, int K, int Nt, int off, int m, int wmode, int nyq,
-                                 double inv_total, double comp) {
+                                 double inv_total, double comp, int part, int c0, int nc) {
+  // part 0: the TF32 (round-to-nearest) value of the entry; 1: its lo part, rna_tf32(v - hi).
+  // nc > 0 (kinds 0 and 1): the STACKED image of a column block of the split-TF32 z kernels -- rows [0, nc) hold the hi
+  // parts of columns c0 .. c0+nc-1 (kind 0: output columns; kind 1: output positions), rows [nc, 2 nc) their lo parts.
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * K) return;
-  const int r = idx / K, k = idx % K;
+  int r = idx / K;
+  const int k = idx % K;
+  const int rimg = r;
+  if (nc > 0) { part = r >= nc ? 1 : 0; r = c0 + (r >= nc ? r - nc : r); }
   int mode = -1, pos = 0, sine = 0;
   if (kind == 0) { mode = r >> 1; sine = r & 1; pos = k; }
   if (kind == 1) { mode = k >> 1; sine = k & 1; pos = r; }
   if (kind == 2) { mode = r & 63; sine = r >> 6; pos = k + off; }
   if (kind == 3 || kind == 4) { mode = k; sine = (kind == 4); pos = r + off; }
   double v = 0.0;
-  if (mode < m) {
+  if (mode < m && (kind != 1 || nc == 0 || r < Nt)) {
     double s, c;
     sincospi(2.0 * (double)(((long long)mode * pos) % Nt) / (double)Nt, &s, &c);
     double w = 1.0;
@@ -75,9 +81,10 @@ __global__ void gen_image_kernel(float* __restrict__ img, int kind, int R, int K
     v = (kind <= 1) ? (sine ? -w * s : w * c) : (sine ? s : c);
     v *= comp;
   }
-  const float f = to_tf32((float)v);
-  if (kind == 2) img[(size_t)r * K + k] = f;
-  else img[swz_off(R, r, k) / 4] = f;
+  float f = to_tf32((float)v);
+  if (part == 1) f = to_tf32((float)(v - (double)f));
+  if (kind == 2) img[(size_t)rimg * K + k] = f;
+  else img[swz_off(R, rimg, k) / 4] = f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,6 +348,336 @@ gen_z_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_v, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// split-TF32 (fp32-grade) z stages.  A.B ~ Ahi.Bhi + (Ahi.Blo + Alo.Bhi): the raw fp32 data operand IS its hi part (the
+// tensor core drops the low 13 mantissa bits), lo = rna_tf32(v - hi).  The constant operand comes as a STACKED image --
+// hi rows then lo rows of one column block -- so one MMA of twice the width yields data_hi.Bhi and data_hi.Blo side by
+// side in TMEM; a second MMA adds data_lo.Bhi to the small half.  Large and small partial products keep separate
+// accumulators and meet in fp32 in the epilogue (the tensor core truncates after every accumulation step: one shared
+// accumulator leaves a systematic 2e-6 shrink, transforms_tc3.cu).  Where the stacked image does not fit beside the data
+// ring (256-point axes, 64 retained modes) the z analysis splits the CONTRACTED index over launches -- launch j reads only
+// its k-blocks of x, so the activation still crosses HBM once, and accumulates into the small W -- and the z synthesis
+// splits the output positions (each launch re-reads the small V).
+//
+// z analysis: W[row][0 .. nc) (+)= sum_{z in this launch's k-blocks} x[row][z] . Bz[c][z];  Wlo = lo part of the final W
+// (data operand of the next stage)
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue, warps 6..9 splitter (landed k-block -> lo k-block)
+// ------------------------------------------------------------------------------------------------
+constexpr int ZA3_THREADS = 320;
+constexpr int ZA3_MAXLO = 4;
+struct ZA3Smem { uint32_t ring, lo, bimg, stg, bars, tmem_slot, total; };
+__host__ __device__ inline ZA3Smem za3_smem(int NKB, int nc, int nring, int nlo) {
+  ZA3Smem s; uint32_t o = 0;
+  s.ring = o; o += (uint32_t)nring * KBYTES;
+  s.lo = o; o += (uint32_t)nlo * KBYTES;
+  s.bimg = o; o += (uint32_t)NKB * 2 * nc * 128;
+  s.stg = o; o += 4 * 32 * ST_LD * 4;
+  s.bars = o; o += 512;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+enum { Z3_FULL = 0, Z3_EMPTY = MAX_RING, Z3_LFULL = 2 * MAX_RING, Z3_LEMPTY = 2 * MAX_RING + ZA3_MAXLO,
+       Z3_DFULL = 2 * MAX_RING + 2 * ZA3_MAXLO, Z3_DEMPTY = 2 * MAX_RING + 2 * ZA3_MAXLO + 2 };
+
+__device__ __forceinline__ float split_lo(float v) { return to_tf32(v - tf32_trunc(v)); }
+
+__global__ void __launch_bounds__(ZA3_THREADS, 1)
+gen_z_analysis_x3_kernel(const __grid_constant__ CUtensorMap tmap_x, float* __restrict__ W, float* __restrict__ Wlo,
+                         const float* __restrict__ Bimg, long long rows, int ntiles, int NKB, int nc, int ldz, int kb0, int accumulate,
+                         int nring, int nlo, int tmem_cols) {
+  // NKB k-blocks starting at kb0 (Bimg points at their slice of the stacked image); accumulate: W += (an earlier launch
+  // covered other k-blocks); Wlo non-null on the last launch only
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const ZA3Smem L = za3_smem(NKB, nc, nring, nlo);
+  auto bar = [&](int i) { return base + L.bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const float4* s1 = reinterpret_cast<const float4*>(Bimg);
+    float4* d1 = reinterpret_cast<float4*>(sm + L.bimg);
+    for (int i = threadIdx.x; i < NKB * 2 * nc * 128 / 16; i += ZA3_THREADS) d1[i] = __ldg(s1 + i);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_RING; ++i) { mbar_init(bar(Z3_FULL + i), 1); mbar_init(bar(Z3_EMPTY + i), 1); }
+    for (int i = 0; i < ZA3_MAXLO; ++i) { mbar_init(bar(Z3_LFULL + i), 4); mbar_init(bar(Z3_LEMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(Z3_DFULL + i), 1); mbar_init(bar(Z3_DEMPTY + i), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, (uint32_t)tmem_cols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const int DW = 2 * nc;                       // TMEM columns of one accumulator pair: [large | small]
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 1;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait(bar(Z3_EMPTY + s), ph);
+          mbar_arrive_expect_tx(bar(Z3_FULL + s), KBYTES);
+          tma_load_2d(base + L.ring + s * KBYTES, &tmap_x, bar(Z3_FULL + s), (kb0 + kb) * 32, t * 128);
+          if (++s == nring) { s = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t id2 = idesc(128, 2 * nc, 0, 0), id1 = idesc(128, nc, 0, 0);
+      int s = 0, l = 0; uint32_t ph = 0, lph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int d = it & 1;
+        mbar_wait(bar(Z3_DEMPTY + d), ((it >> 1) & 1) ^ 1);
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait(bar(Z3_FULL + s), ph);
+          mbar_wait(bar(Z3_LFULL + l), lph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = umma_desc(base + L.bimg + kb * 2 * nc * 128 + k * 32, 1024);
+            mma_ss(tmem + d * DW, umma_desc(base + L.ring + s * KBYTES + k * 32, 1024), bd, id2, (kb | k) ? 1u : 0u);
+            mma_ss(tmem + d * DW + nc, umma_desc(base + L.lo + l * KBYTES + k * 32, 1024), bd, id1, 1u);
+          }
+          mma_commit(bar(Z3_EMPTY + s));
+          mma_commit(bar(Z3_LEMPTY + l));
+          if (++s == nring) { s = 0; ph ^= 1; }
+          if (++l == nlo) { l = 0; lph ^= 1; }
+        }
+        mma_commit(bar(Z3_DFULL + d));
+      }
+    }
+  } else if (warp >= 6) {
+    // splitter: the landed k-block (raw fp32 = hi + lo) -> its lo part at the same (swizzled) offsets of a lo slot
+    const int tid = threadIdx.x - 6 * 32;
+    int s = 0, l = 0; uint32_t ph = 0, lph = 1;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+      for (int kb = 0; kb < NKB; ++kb) {
+        mbar_wait(bar(Z3_FULL + s), ph);
+        mbar_wait(bar(Z3_LEMPTY + l), lph);
+        const float4* src = reinterpret_cast<const float4*>(sm + L.ring + s * KBYTES);
+        float4* dst = reinterpret_cast<float4*>(sm + L.lo + l * KBYTES);
+#pragma unroll
+        for (int j = 0; j < KBYTES / 16 / 128; ++j) {
+          float4 v = src[tid + 128 * j];
+          v.x = split_lo(v.x); v.y = split_lo(v.y); v.z = split_lo(v.z); v.w = split_lo(v.w);
+          dst[tid + 128 * j] = v;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(Z3_LFULL + l));
+        if (++s == nring) { s = 0; ph ^= 1; }
+        if (++l == nlo) { l = 0; lph ^= 1; }
+      }
+  } else {
+    const int q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* st = reinterpret_cast<float*>(sm + L.stg) + (warp - 2) * 32 * ST_LD;
+    const int ncv = min(nc, ldz);              // columns that exist in W
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int d = it & 1;
+      const size_t rbase = ((size_t)t * 128 + 32 * q) * ldz;
+      const int nvalid = (int)min(32LL, rows - ((long long)t * 128 + 32 * q));   // the last tile may be partial
+      for (int cc = 0; cc < nc; cc += 32) {
+        const int lpr = max(0, min(32, ncv - cc)) >> 2;            // float4 lanes per row of this chunk
+        float4 prev[8];          // accumulating launch: the earlier partial sums, fetched before the TMEM read
+        if (accumulate) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = lane + 32 * i, row = idx / max(lpr, 1), c4 = idx - row * lpr;
+            prev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < lpr && row < nvalid) prev[i] = __ldcs(reinterpret_cast<const float4*>(W + rbase + (size_t)row * ldz + cc + 4 * c4));
+          }
+        }
+        if (cc == 0) {
+          mbar_wait(bar(Z3_DFULL + d), (it >> 1) & 1);
+          tc_fence_after();
+        }
+        float v[32], w[32];
+        if (cc + 32 <= nc) {
+          tmem_ld32(tmem + d * DW + lane_base + cc, v);
+          tmem_ld32(tmem + d * DW + nc + lane_base + cc, w);
+        } else {                                 // nc is a multiple of 16: a 16-column tail
+          tmem_ld16(tmem + d * DW + lane_base + cc, v);
+          tmem_ld16(tmem + d * DW + nc + lane_base + cc, w);
+#pragma unroll
+          for (int j = 16; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
+        }
+        tmem_ld_wait();
+        if (cc + 32 >= nc) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(Z3_DEMPTY + d));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) =
+              make_float4(v[4 * j] + w[4 * j], v[4 * j + 1] + w[4 * j + 1], v[4 * j + 2] + w[4 * j + 2], v[4 * j + 3] + w[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = lane + 32 * i, row = idx / max(lpr, 1), c4 = idx - row * lpr;
+          if (i < lpr && row < nvalid) {
+            float4 o = *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
+            if (accumulate) { o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w; }
+            *reinterpret_cast<float4*>(W + rbase + (size_t)row * ldz + cc + 4 * c4) = o;
+            if (Wlo)
+              *reinterpret_cast<float4*>(Wlo + rbase + (size_t)row * ldz + cc + 4 * c4) =
+                  make_float4(split_lo(o.x), split_lo(o.y), split_lo(o.z), split_lo(o.w));
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-TF32 z synthesis: out[row][c0 .. c0+nc) = sum_c V[row][c] . Bs[z][c]  (+ addends), V = Vhi (raw) + Vlo (its own array,
+// written by the producing stage): two TMA streams, no splitter.  warps as in gen_z_synthesis_kernel.
+// ------------------------------------------------------------------------------------------------
+struct ZS3Smem { uint32_t ring, bimg, stg, bars, tmem_slot, total; };
+__host__ __device__ inline ZS3Smem zs3_smem(int nc, int NKBK, int nring) {
+  ZS3Smem s; uint32_t o = 0;
+  s.ring = o; o += (uint32_t)nring * 2 * KBYTES;           // a slot = the k-block of V and the same k-block of Vlo
+  s.bimg = o; o += (uint32_t)NKBK * 2 * nc * 128;
+  s.stg = o; o += ZS_EPI * 32 * ST_LD * 4;
+  s.bars = o; o += 256;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+
+template <int NADD>
+__global__ void __launch_bounds__(ZS_THREADS, 1)
+gen_z_synthesis_x3_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_vlo,
+                          float* __restrict__ out, const float* __restrict__ add0, const float* __restrict__ add1,
+                          const float* __restrict__ Bimg, long long rows, int ntiles, int zN, int c0, int nc, int NKBK, int ksteps,
+                          int nring, int tmem_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const ZS3Smem L = zs3_smem(nc, NKBK, nring);
+  auto bar = [&](int i) { return base + L.bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const float4* s1 = reinterpret_cast<const float4*>(Bimg);
+    float4* d1 = reinterpret_cast<float4*>(sm + L.bimg);
+    for (int i = threadIdx.x; i < NKBK * 2 * nc * 128 / 16; i += ZS_THREADS) d1[i] = __ldg(s1 + i);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_RING; ++i) { mbar_init(bar(ZB_FULL + i), 1); mbar_init(bar(ZB_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(ZB_DFULL + i), 1); mbar_init(bar(ZB_DEMPTY + i), ZS_EPI / 2); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(base + L.tmem_slot, (uint32_t)tmem_cols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const int DW = 2 * nc;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 1;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+        for (int kb = 0; kb < NKBK; ++kb) {
+          mbar_wait(bar(ZB_EMPTY + s), ph);
+          mbar_arrive_expect_tx(bar(ZB_FULL + s), 2 * KBYTES);
+          tma_load_2d(base + L.ring + s * 2 * KBYTES, &tmap_v, bar(ZB_FULL + s), kb * 32, t * 128);
+          tma_load_2d(base + L.ring + s * 2 * KBYTES + KBYTES, &tmap_vlo, bar(ZB_FULL + s), kb * 32, t * 128);
+          if (++s == nring) { s = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t id2 = idesc(128, 2 * nc, 0, 0), id1 = idesc(128, nc, 0, 0);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int d = it & 1;
+        mbar_wait(bar(ZB_DEMPTY + d), ((it >> 1) & 1) ^ 1);
+        for (int kb = 0; kb < NKBK; ++kb) {
+          mbar_wait(bar(ZB_FULL + s), ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (kb * 4 + k < ksteps) {
+              const uint64_t bd = umma_desc(base + L.bimg + kb * 2 * nc * 128 + k * 32, 1024);
+              mma_ss(tmem + d * DW, umma_desc(base + L.ring + s * 2 * KBYTES + k * 32, 1024), bd, id2, (kb | k) ? 1u : 0u);
+              mma_ss(tmem + d * DW + nc, umma_desc(base + L.ring + s * 2 * KBYTES + KBYTES + k * 32, 1024), bd, id1, 1u);
+            }
+          mma_commit(bar(ZB_EMPTY + s));
+          if (++s == nring) { s = 0; ph ^= 1; }
+        }
+        mma_commit(bar(ZB_DFULL + d));
+      }
+    }
+  } else {
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* st = reinterpret_cast<float*>(sm + L.stg) + (warp - 2) * 32 * ST_LD;
+    const int rsub = lane >> 3, c4 = lane & 7;
+    const int n_my = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int nrounds = nc >> 5;               // nc is a multiple of 32 here
+    for (int it = grp; it < n_my; it += 2) {
+      const int t = blockIdx.x + it * gridDim.x;
+      mbar_wait(bar(ZB_DFULL + grp), (it >> 1) & 1);
+      tc_fence_after();
+      const int nvalid = (int)min(32LL, rows - ((long long)t * 128 + 32 * q)) - rsub;   // rows 4j + rsub < valid count
+      for (int r = 0; r < nrounds; ++r) {
+        const size_t gbase = ((size_t)t * 128 + 32 * q + rsub) * zN + c0 + r * 32 + 4 * c4;
+        float4 a0v[NADD >= 1 ? 8 : 1], a1v[NADD == 2 ? 8 : 1];
+        if (NADD >= 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (4 * j < nvalid) a0v[j] = __ldcs(reinterpret_cast<const float4*>(add0 + gbase + (size_t)(4 * j) * zN));
+        }
+        if (NADD == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (4 * j < nvalid) a1v[j] = __ldcs(reinterpret_cast<const float4*>(add1 + gbase + (size_t)(4 * j) * zN));
+        }
+        float v[32], w[32];
+        tmem_ld32(tmem + grp * DW + lane_base + r * 32, v);
+        tmem_ld32(tmem + grp * DW + nc + lane_base + r * 32, w);
+        tmem_ld_wait();
+        if (r == nrounds - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(ZB_DEMPTY + grp));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) =
+              make_float4(v[4 * j] + w[4 * j], v[4 * j + 1] + w[4 * j + 1], v[4 * j + 2] + w[4 * j + 2], v[4 * j + 3] + w[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = *reinterpret_cast<const float4*>(st + (4 * j + rsub) * ST_LD + 4 * c4);
+          if (NADD >= 1) { o.x += a0v[j].x; o.y += a0v[j].y; o.z += a0v[j].z; o.w += a0v[j].w; }
+          if (NADD == 2) { o.x += a1v[j].x; o.y += a1v[j].y; o.z += a1v[j].z; o.w += a1v[j].w; }
+          if (4 * j < nvalid) __stcs(reinterpret_cast<float4*>(out + gbase + (size_t)(4 * j) * zN), o);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // axis analysis (contracted index = row): out[b][k][j] = sum_n e^{-i theta(k,n)} in[b][n][j]
 //   warp 0 TMA, warp 1 MMA, warps 2..5 epilogue.  A = [cos k (rows 0..63) | sin k (rows 64..127)] x N lives in TMEM.
 // ------------------------------------------------------------------------------------------------
@@ -363,7 +700,11 @@ enum { AB_FULL = 0, AB_EMPTY = AA_MAXST, AB_DFULL = 2 * AA_MAXST, AB_DEMPTY = 2 
 
 __global__ void __launch_bounds__(AA_THREADS, 1)
 gen_axis_analysis_kernel(const __grid_constant__ CUtensorMap tmap_in, float2* __restrict__ out, const float* __restrict__ Aplain,
-                         int N, int m, int Pout, int ntn, long long ntiles, int nst) {
+                         int N, int m, int Pout, int ntn, long long ntiles, int nst, float comp, int accumulate,
+                         float2* __restrict__ out_lo) {
+  // comp: epilogue factor (PDEPHI_GEN_COMP on the single-pass route, 1 on the split route).  accumulate: out += result -- the
+  // split route runs a stage as three launches (data.Ahi, data_lo.Ahi, data.Alo) that meet in fp32 here.  out_lo: also
+  // store the lo part of the final value (the data_lo operand of the next stage).
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -442,6 +783,19 @@ gen_axis_analysis_kernel(const __grid_constant__ CUtensorMap tmap_in, float2* __
     long long it = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int d = (int)(it & 1);
+      const long long b = t / ntn;
+      const int p0 = (int)(t - b * ntn) * (NT / 2);
+      // accumulating launch: the previous partial result comes from an earlier launch, so fetch it before waiting for this
+      // tile's MMAs (a load -> add -> store chain per element inside the store loop made these launches latency-bound)
+      float2 prev[16];
+      if (accumulate) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int idx = et + 128 * i, k = idx >> 5, j = idx & 31;
+          prev[i] = make_float2(0.f, 0.f);
+          if (i < niter && k < m && p0 + j < Pout) prev[i] = __ldcs(out + (size_t)b * m * Pout + (size_t)k * Pout + p0 + j);
+        }
+      }
       mbar_wait(bar(AB_DFULL + d), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       float v[64];
@@ -458,15 +812,17 @@ gen_axis_analysis_kernel(const __grid_constant__ CUtensorMap tmap_in, float2* __
         for (int c = 0; c < 64; c += 2) *reinterpret_cast<float2*>(er + c) = make_float2(v[c], v[c + 1]);
       }
       epi_bar_sync();
-      const long long b = t / ntn;
-      const int p0 = (int)(t - b * ntn) * (NT / 2);
-      float2* outp = out + (size_t)b * m * Pout;
-      for (int i = 0; i < niter; ++i) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
         const int idx = et + 128 * i, k = idx >> 5, j = idx & 31;
-        if (k < m && p0 + j < Pout) {
+        if (i < niter && k < m && p0 + j < Pout) {
           const float2 c = *reinterpret_cast<const float2*>(E + k * AA_ELD + 2 * j);
           const float2 s = *reinterpret_cast<const float2*>(E + (64 + k) * AA_ELD + 2 * j);
-          outp[(size_t)k * Pout + p0 + j] = make_float2((c.x + s.y) * PDEPHI_GEN_COMP, (c.y - s.x) * PDEPHI_GEN_COMP);   // (C - iS)(re + i im)
+          float2 o = make_float2((c.x + s.y) * comp, (c.y - s.x) * comp);   // (C - iS)(re + i im)
+          const size_t oi = (size_t)b * m * Pout + (size_t)k * Pout + p0 + j;
+          if (accumulate) { o.x += prev[i].x; o.y += prev[i].y; }
+          out[oi] = o;
+          if (out_lo) out_lo[oi] = make_float2(split_lo(o.x), split_lo(o.y));
         }
       }
     }
@@ -501,7 +857,8 @@ __host__ __device__ inline ASSmem as_smem(int N, int mk, int nst) {
 __global__ void __launch_bounds__(AS_THREADS, 1)
 gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __restrict__ U, const float* __restrict__ Acimg,
                           const float* __restrict__ Asimg, int N, int Npad, int m, int mk, int ld_out, int ntn, int nmt,
-                          long long ntiles, int nst) {
+                          long long ntiles, int nst, float comp, int accumulate, float* __restrict__ U_lo) {
+  // comp / accumulate / U_lo: as in gen_axis_analysis_kernel
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -576,6 +933,19 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
      for (int mt = 0; mt < nmt; ++mt, ++it) {
       const int d = (int)(it & 1);
+      const long long b = t / ntn;
+      const int n0 = (int)(t - b * ntn) * NT + half * 32;
+      float* ub = U + ((size_t)b * N + (size_t)mt * 128 + 32 * q) * ld_out + n0;
+      float4 prev[8];            // accumulating launch: fetch the earlier partial result before waiting for the MMAs
+      if (accumulate) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int row = 4 * g + rsub;
+          prev[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n0 + 4 * c4 < ld_out && mt * 128 + 32 * q + row < N)
+            prev[g] = __ldcs(reinterpret_cast<const float4*>(ub + (size_t)row * ld_out + 4 * c4));
+        }
+      }
       mbar_wait(bar(AB_DFULL + d), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       float c[32], s[32];
@@ -589,21 +959,25 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 o;
-        o.x = (c[4 * j] - s[4 * j + 1]) * PDEPHI_GEN_COMP;
-        o.y = (c[4 * j + 1] + s[4 * j]) * PDEPHI_GEN_COMP;
-        o.z = (c[4 * j + 2] - s[4 * j + 3]) * PDEPHI_GEN_COMP;
-        o.w = (c[4 * j + 3] + s[4 * j + 2]) * PDEPHI_GEN_COMP;
+        o.x = (c[4 * j] - s[4 * j + 1]) * comp;
+        o.y = (c[4 * j + 1] + s[4 * j]) * comp;
+        o.z = (c[4 * j + 2] - s[4 * j + 3]) * comp;
+        o.w = (c[4 * j + 3] + s[4 * j + 2]) * comp;
         *reinterpret_cast<float4*>(st + lane * ST_LD + 4 * j) = o;
       }
       __syncwarp();
-      const long long b = t / ntn;
-      const int n0 = (int)(t - b * ntn) * NT + half * 32;
-      float* ub = U + ((size_t)b * N + (size_t)mt * 128 + 32 * q) * ld_out + n0;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const int row = 4 * g + rsub;
-        if (n0 + 4 * c4 < ld_out && mt * 128 + 32 * q + row < N)
-          *reinterpret_cast<float4*>(ub + (size_t)row * ld_out + 4 * c4) = *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
+        if (n0 + 4 * c4 < ld_out && mt * 128 + 32 * q + row < N) {
+          float4 o = *reinterpret_cast<const float4*>(st + row * ST_LD + 4 * c4);
+          float4* dst = reinterpret_cast<float4*>(ub + (size_t)row * ld_out + 4 * c4);
+          if (accumulate) { o.x += prev[g].x; o.y += prev[g].y; o.z += prev[g].z; o.w += prev[g].w; }
+          *dst = o;
+          if (U_lo)
+            *reinterpret_cast<float4*>(U_lo + (ub - U) + (size_t)row * ld_out + 4 * c4) =
+                make_float4(split_lo(o.x), split_lo(o.y), split_lo(o.z), split_lo(o.w));
+        }
       }
       __syncwarp();
     }
@@ -616,7 +990,7 @@ gen_axis_synthesis_kernel(const __grid_constant__ CUtensorMap tmap_in, float* __
 // Zp[bc][kx][ky][0..ldz/2) = Z[bc][kx][ky][kz] * mode_scale[k] * row_scale[bc]   (zero in the padding columns)
 __global__ void gen_pad_scale_kernel(const float2* __restrict__ Z, float2* __restrict__ Zp, const float* __restrict__ mode_scale,
                                      const float* __restrict__ row_scale, long long rs_stride, int zm, int ldh, long long Mrows,
-                                     long long total) {
+                                     long long total, float2* __restrict__ Zp_lo) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long row = i / ldh;            // (bc, kx, ky)
@@ -630,6 +1004,16 @@ __global__ void gen_pad_scale_kernel(const float2* __restrict__ Z, float2* __res
     v = make_float2(z.x * s, z.y * s);
   }
   Zp[i] = v;
+  if (Zp_lo) Zp_lo[i] = make_float2(split_lo(v.x), split_lo(v.y));
+}
+
+// lo[i] = lo part of src[i]: the data_lo operand of a split stage whose input arrives from outside (the exchange tensor of
+// the slab-decomposed transform)
+__global__ void gen_split_lo_kernel(const float4* __restrict__ src, float4* __restrict__ lo, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(src + i);
+  lo[i] = make_float4(split_lo(v.x), split_lo(v.y), split_lo(v.z), split_lo(v.w));
 }
 
 // The same with the channel index moved inside: Zc[b][kx][ky][c][0..ldh) = Z[b*C + c][kx][ky][kz] * scales.  With the
@@ -685,12 +1069,15 @@ static int gen_make_map(CUtensorMap* m, const void* ptr, long long rows, long lo
 }
 
 bool gen_supported(const Plan* p) { return p->gen_ok != 0; }
+bool gen_x3_supported(const Plan* p) { return p->gen_ok != 0 && p->g.x3_ok != 0; }
 
 static size_t smem_budget(const Plan* p) { return p->smem_optin - 1024; }
 
 int gen_plan_init(Plan* p) {
   p->gen_ok = 0;
   p->gen_arena = nullptr;
+  p->gen_arena3 = nullptr;
+  p->g.x3_ok = 0;
   const bool two_d = (p->Nz == 1 && p->mzh == 1);
   GenPlan& g = p->g;
   g.has_mid = two_d ? 0 : 1;
@@ -753,9 +1140,9 @@ int gen_plan_init(Plan* p) {
   const int nyq = (!two_d && p->Nz % 2 == 0 && p->mzh - 1 == p->Nz / 2) ? p->Nz / 2 : -1;
   const double comp = 1.0;                    // truncation bias of the data operands: undone in the epilogues (PDEPHI_GEN_COMP)
   const int wnorm = two_d ? 2 : 1;
-  auto genimg = [&](float* img, int kind, int R, int K, int Nt, int off, int m, int wmode) {
+  auto genimg = [&](float* img, int kind, int R, int K, int Nt, int off, int m, int wmode, int part = 0, int c0 = 0, int nc = 0) {
     const int n = R * K;
-    gen::gen_image_kernel<<<(n + 255) / 256, 256>>>(img, kind, R, K, Nt, off, m, wmode, nyq, inv_total, comp);
+    gen::gen_image_kernel<<<(n + 255) / 256, 256>>>(img, kind, R, K, Nt, off, m, wmode, nyq, inv_total, comp, part, c0, nc);
   };
   genimg(g.za[0], 0, g.nbm, g.zN, g.zN, 0, g.zm, 0);          // analysis FORWARD: plain e^{-i}
   genimg(g.za[1], 0, g.nbm, g.zN, g.zN, 0, g.zm, wnorm);      // analysis ADJOINT: c_k / total
@@ -771,33 +1158,94 @@ int gen_plan_init(Plan* p) {
   genimg(g.xss, 4, pad128(p->Nx), g.mkx, p->Nx_total, p->x_offset, p->mx, 0);
   PDEPHI_LAUNCH_CHECK("gen_image_kernel");
   p->gen_ok = 1;
+
+  // ---- split-TF32 variant: geometry of the column blocks, then the lo / stacked images --------------------------
+  g.x3_ok = 0;
+  {
+    // z analysis: the stacked image of all nbm output columns takes zN * nbm * 8 bytes; the contracted index is split over
+    // np launches (np divides the number of k-blocks) until a launch's slice leaves room for 4 data + 2 lo slots
+    const int nc = g.nbm;
+    int np = 1;
+    while (np <= NKB && (NKB % np != 0 || gen::za3_smem(NKB / np, nc, 6, 0).total > smem_budget(p))) ++np;
+    if (np > NKB || np > 8) return PDEPHI_OK;
+    const size_t fixed = gen::za3_smem(NKB / np, nc, 0, 0).total;
+    const int slots = (int)((smem_budget(p) - fixed) / gen::KBYTES);
+    g.za3_np = np; g.za3_nc = nc; g.za3_lo = 2;
+    g.za3_ring = slots - 2 > gen::MAX_RING ? gen::MAX_RING : slots - 2;
+    // z synthesis: blocks of at most 128 output positions (TMEM: two accumulator pairs of 2 * nc columns)
+    int nblk = 0, c0 = 0;
+    int cap = 128;
+    while (cap >= 32 && gen::zs3_smem(cap, NKBK, 2).total > smem_budget(p)) cap -= 32;
+    if (cap < 32) return PDEPHI_OK;
+    while (c0 < g.zN) {
+      if (nblk == 8) return PDEPHI_OK;
+      const int nb = g.zN - c0 < cap ? g.zN - c0 : cap;
+      const size_t fx = gen::zs3_smem(nb, NKBK, 0).total;
+      int nr = (int)((smem_budget(p) - fx) / (2 * gen::KBYTES));
+      g.zs3_c0[nblk] = c0; g.zs3_nc[nblk] = nb; g.zs3_ring[nblk] = nr > gen::MAX_RING ? gen::MAX_RING : nr;
+      c0 += nb; ++nblk;
+    }
+    g.zs3_np = nblk;
+  }
+  {
+    size_t n3 = n_ya + 2 * n_ys + n_xa + 2 * n_xs;                          // lo parts of the six axis images
+    n3 += 2 * (size_t)2 * g.za3_nc * g.zN;                                     // [direction] stacked z analysis image
+    for (int j = 0; j < g.zs3_np; ++j) n3 += 2 * (size_t)2 * g.zs3_nc[j] * NKBK * 32;
+    float* f3 = nullptr;
+    PDEPHI_CUDA(cudaMalloc(&f3, n3 * sizeof(float)));
+    p->gen_arena3 = f3;
+    PDEPHI_CUDA(cudaMemset(f3, 0, n3 * sizeof(float)));
+    g.ya_lo = f3; f3 += n_ya; g.ysc_lo = f3; f3 += n_ys; g.yss_lo = f3; f3 += n_ys;
+    g.xa_lo = f3; f3 += n_xa; g.xsc_lo = f3; f3 += n_xs; g.xss_lo = f3; f3 += n_xs;
+    for (int d = 0; d < 2; ++d) {
+      g.za3[d] = f3; f3 += (size_t)2 * g.za3_nc * g.zN;
+      genimg(g.za3[d], 0, 2 * g.za3_nc, g.zN, g.zN, 0, g.zm, d == 0 ? 0 : wnorm, 0, 0, g.za3_nc);
+      for (int j = 0; j < g.zs3_np; ++j) {
+        g.zs3[d][j] = f3; f3 += (size_t)2 * g.zs3_nc[j] * NKBK * 32;
+        genimg(g.zs3[d][j], 1, 2 * g.zs3_nc[j], NKBK * 32, g.zN, 0, g.zm, d == 0 ? wnorm : 0, 0, g.zs3_c0[j], g.zs3_nc[j]);
+      }
+    }
+    if (!two_d) {
+      genimg(g.ya_lo, 2, 128, p->Ny, p->Ny, 0, p->my, 0, 1);
+      genimg(g.ysc_lo, 3, pad128(p->Ny), g.mky, p->Ny, 0, p->my, 0, 1);
+      genimg(g.yss_lo, 4, pad128(p->Ny), g.mky, p->Ny, 0, p->my, 0, 1);
+    }
+    genimg(g.xa_lo, 2, 128, p->Nx, p->Nx_total, p->x_offset, p->mx, 0, 1);
+    genimg(g.xsc_lo, 3, pad128(p->Nx), g.mkx, p->Nx_total, p->x_offset, p->mx, 0, 1);
+    genimg(g.xss_lo, 4, pad128(p->Nx), g.mkx, p->Nx_total, p->x_offset, p->mx, 0, 1);
+    PDEPHI_LAUNCH_CHECK("gen_image_kernel(lo)");
+    g.x3_ok = 1;
+  }
   return PDEPHI_OK;
 }
 
 void gen_plan_destroy(Plan* p) {
   if (p->gen_arena) cudaFree(p->gen_arena);
-  p->gen_arena = nullptr;
+  if (p->gen_arena3) cudaFree(p->gen_arena3);
+  p->gen_arena = p->gen_arena3 = nullptr;
 }
 
-// workspace layout of the general route: [W1 | W2 | Zp]
-struct GenWs { size_t w1, w2, zp, total; };
+// workspace layout of the general route: [W1 | W2 | Zp | W1lo | W2lo | Zplo]  (the lo arrays: split-TF32 variant only)
+struct GenWs { size_t w1, w2, zp, w1lo, w2lo, zplo, total; };
 static GenWs gen_ws(const Plan* p, long long BC) {
   const GenPlan& g = p->g;
   const size_t rows = (size_t)BC * p->Nx * (g.has_mid ? p->Ny : 1);
+  const size_t b1 = align_up(rows * g.ldz * sizeof(float), 1024);
+  const size_t b2 = align_up((size_t)BC * p->Nx * g.ym * g.ldz * sizeof(float), 1024);
+  const size_t b3 = align_up((size_t)BC * p->mx * g.ym * g.ldz * sizeof(float), 1024);
   GenWs w;
-  w.w1 = 0;
-  size_t o = align_up(rows * g.ldz * sizeof(float), 1024);
-  w.w2 = o;
-  o += align_up((size_t)BC * p->Nx * g.ym * g.ldz * sizeof(float), 1024);
-  w.zp = o;
-  o += align_up((size_t)BC * p->mx * g.ym * g.ldz * sizeof(float), 1024);
+  w.w1 = 0; w.w2 = b1; w.zp = b1 + b2;
+  size_t o = b1 + b2 + b3;
+  w.w1lo = w.w2lo = w.zplo = o;
+  if (g.x3_ok) { w.w1lo = o; w.w2lo = o + b1; w.zplo = o + b1 + b2; o += b1 + b2 + b3; }
   w.total = o;
   return w;
 }
 size_t gen_workspace_bytes(const Plan* p, long long BC) { return gen_ws(p, BC).total; }
 
 static int launch_axis_analysis(const Plan* p, const float* in, long long nb, int N, int m, int ld_in, int Pout, float2* out,
-                                const float* Aplain, int nst, int kid, cudaStream_t st) {
+                                const float* Aplain, int nst, int kid, cudaStream_t st, float comp = PDEPHI_GEN_COMP,
+                                int accumulate = 0, float2* out_lo = nullptr) {
   CUtensorMap map;
   int rc = gen_make_map(&map, in, nb * N, ld_in, N, true);
   if (rc) return rc;
@@ -809,14 +1257,15 @@ static int launch_axis_analysis(const Plan* p, const float* in, long long nb, in
   PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope ps(kid, st);
-    k<<<grid, gen::AA_THREADS, smem, st>>>(map, out, Aplain, N, m, Pout, ntn, ntiles, nst);
+    k<<<grid, gen::AA_THREADS, smem, st>>>(map, out, Aplain, N, m, Pout, ntn, ntiles, nst, comp, accumulate, out_lo);
   }
   PDEPHI_LAUNCH_CHECK("gen_axis_analysis_kernel");
   return PDEPHI_OK;
 }
 
 static int launch_axis_synthesis(const Plan* p, const float* in, long long nb, int N, int m, int mk, int ld, float* out,
-                                 const float* Ac, const float* As, int nst, int kid, cudaStream_t st) {
+                                 const float* Ac, const float* As, int nst, int kid, cudaStream_t st,
+                                 float comp = PDEPHI_GEN_COMP, int accumulate = 0, float* out_lo = nullptr) {
   CUtensorMap map;
   int rc = gen_make_map(&map, in, nb * m, ld, mk, true);
   if (rc) return rc;
@@ -830,19 +1279,58 @@ static int launch_axis_synthesis(const Plan* p, const float* in, long long nb, i
   PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope ps(kid, st);
-    k<<<grid, gen::AS_THREADS, smem, st>>>(map, out, Ac, As, N, Npad, m, mk, ld, ntn, nmt, ntiles, nst);
+    k<<<grid, gen::AS_THREADS, smem, st>>>(map, out, Ac, As, N, Npad, m, mk, ld, ntn, nmt, ntiles, nst, comp, accumulate, out_lo);
   }
   PDEPHI_LAUNCH_CHECK("gen_axis_synthesis_kernel");
   return PDEPHI_OK;
 }
 
+// One axis stage on either route.  Split route: data.A ~ data.Ahi + data_lo.Ahi + data.Alo as three launches that meet in
+// fp32 in the epilogue (the tensor core reads `data` as its hi part); the last one can emit the lo part of the result.
+static int axis_analysis_stage(const Plan* p, bool x3, const float* in, const float* in_lo, long long nb, int N, int m, int ld_in,
+                               int Pout, float2* out, float2* out_lo, const float* Ahi, const float* Alo, int nst,
+                               cudaStream_t st) {
+  if (!x3) return launch_axis_analysis(p, in, nb, N, m, ld_in, Pout, out, Ahi, nst, K_GEN_AXIS_ANALYSIS, st);
+  int rc = launch_axis_analysis(p, in, nb, N, m, ld_in, Pout, out, Ahi, nst, K_GEN_AXIS_ANALYSIS, st, 1.0f, 0, nullptr);
+  if (rc) return rc;
+  rc = launch_axis_analysis(p, in_lo, nb, N, m, ld_in, Pout, out, Ahi, nst, K_GEN_AXIS_ANALYSIS, st, 1.0f, 1, nullptr);
+  if (rc) return rc;
+  return launch_axis_analysis(p, in, nb, N, m, ld_in, Pout, out, Alo, nst, K_GEN_AXIS_ANALYSIS, st, 1.0f, 1, out_lo);
+}
+
+static int axis_synthesis_stage(const Plan* p, bool x3, const float* in, const float* in_lo, long long nb, int N, int m, int mk,
+                                int ld, float* out, float* out_lo, const float* Ac, const float* As, const float* Ac_lo,
+                                const float* As_lo, int nst, cudaStream_t st) {
+  if (!x3) return launch_axis_synthesis(p, in, nb, N, m, mk, ld, out, Ac, As, nst, K_GEN_AXIS_SYNTHESIS, st);
+  int rc = launch_axis_synthesis(p, in, nb, N, m, mk, ld, out, Ac, As, nst, K_GEN_AXIS_SYNTHESIS, st, 1.0f, 0, nullptr);
+  if (rc) return rc;
+  rc = launch_axis_synthesis(p, in_lo, nb, N, m, mk, ld, out, Ac, As, nst, K_GEN_AXIS_SYNTHESIS, st, 1.0f, 1, nullptr);
+  if (rc) return rc;
+  return launch_axis_synthesis(p, in, nb, N, m, mk, ld, out, Ac_lo, As_lo, nst, K_GEN_AXIS_SYNTHESIS, st, 1.0f, 1, out_lo);
+}
+
+static int launch_split_lo(const float* src, float* lo, size_t nfloats, cudaStream_t st) {
+  if ((nfloats & 3) || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(lo) & 15))
+    return fail(PDEPHI_ERR_INVALID, "general transform route: exchange tensor must be 16-byte aligned with a multiple of 4 floats");
+  const long long n4 = (long long)(nfloats / 4);
+  {
+    ProfScope ps(K_SCALE_MODES, st);
+    gen::gen_split_lo_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float4*)src, (float4*)lo, n4);
+  }
+  PDEPHI_LAUNCH_CHECK("gen_split_lo_kernel");
+  return PDEPHI_OK;
+}
+
 int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int direction, void* ws, cudaStream_t st, int stages,
-                 float2* T) {
+                 float2* T, bool x3) {
   const GenPlan& g = p->g;
+  if (x3 && !g.x3_ok) return fail(PDEPHI_ERR_UNSUPPORTED, "split-TF32 per-axis route is not available for this shape");
   const GenWs w = gen_ws(p, BC);
   char* wb = (char*)ws;
   float* W1 = (float*)(wb + w.w1);
   float* W2 = (float*)(wb + w.w2);
+  float* W1lo = (float*)(wb + w.w1lo);
+  float* W2lo = (float*)(wb + w.w2lo);
   if (stages != ST_ALL) {
     if (!g.has_mid) return fail(PDEPHI_ERR_UNSUPPORTED, "stage-split transforms are not available for 2-D grids");
     W2 = (float*)T;        // the exchange tensor [BC, Nx, my, mzh] takes the place of the (y -> x) intermediate
@@ -854,33 +1342,54 @@ int analysis_gen(const Plan* p, const float* x, float2* X, long long BC, int dir
     if (rc) return rc;
     const int NKB = g.zN / 32;
     const int ntiles = (int)((rows + 127) / 128);
-    const size_t smem = gen::za_smem(NKB, g.nbm, g.za_ring).total + 1024;
     const int grid = ntiles < p->num_sms ? ntiles : p->num_sms;
-    auto k = gen::gen_z_analysis_kernel;
-    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-      ProfScope ps(K_GEN_Z_ANALYSIS, st);
-      k<<<grid, gen::ZA_THREADS, smem, st>>>(map, W1, g.za[direction], rows, ntiles, NKB, g.nbm, g.ldz, g.za_ring);
+    if (!x3) {
+      const size_t smem = gen::za_smem(NKB, g.nbm, g.za_ring).total + 1024;
+      auto k = gen::gen_z_analysis_kernel;
+      PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      {
+        ProfScope ps(K_GEN_Z_ANALYSIS, st);
+        k<<<grid, gen::ZA_THREADS, smem, st>>>(map, W1, g.za[direction], rows, ntiles, NKB, g.nbm, g.ldz, g.za_ring);
+      }
+      PDEPHI_LAUNCH_CHECK("gen_z_analysis_kernel");
+    } else {
+      const int nc = g.za3_nc, np = g.za3_np, nkb = NKB / np;
+      const size_t smem = gen::za3_smem(nkb, nc, g.za3_ring, g.za3_lo).total + 1024;
+      const int tmem_cols = pow2_at_least(4 * nc + ((nc & 31) ? 32 : 0));
+      auto k = gen::gen_z_analysis_x3_kernel;
+      PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      for (int j = 0; j < np; ++j) {             // one launch per range of k-blocks (the contracted index)
+        ProfScope ps(K_GEN_Z_ANALYSIS, st);
+        k<<<grid, gen::ZA3_THREADS, smem, st>>>(map, W1, j == np - 1 ? W1lo : nullptr,
+                                               g.za3[direction] + (size_t)j * nkb * 2 * nc * 32, rows, ntiles, nkb, nc, g.ldz,
+                                               j * nkb, j > 0 ? 1 : 0, g.za3_ring, g.za3_lo, tmem_cols);
+      }
+      PDEPHI_LAUNCH_CHECK("gen_z_analysis_x3_kernel");
     }
-    PDEPHI_LAUNCH_CHECK("gen_z_analysis_kernel");
     if (g.has_mid) {
-      rc = launch_axis_analysis(p, W1, BC * p->Nx, p->Ny, p->my, g.ldz, p->mzh, (float2*)W2, g.ya, g.ya_st, K_GEN_AXIS_ANALYSIS, st);
+      rc = axis_analysis_stage(p, x3, W1, W1lo, BC * p->Nx, p->Ny, p->my, g.ldz, p->mzh, (float2*)W2,
+                               (stages & ST_X) ? (float2*)W2lo : nullptr, g.ya, g.ya_lo, g.ya_st, st);
       if (rc) return rc;
     }
   }
   if (!(stages & ST_X)) return PDEPHI_OK;
-  if (g.has_mid)
-    return launch_axis_analysis(p, W2, BC, p->Nx, p->mx, 2 * p->my * p->mzh, p->my * p->mzh, X, g.xa, g.xa_st,
-                                K_GEN_AXIS_ANALYSIS, st);
-  return launch_axis_analysis(p, W1, BC, p->Nx, p->mx, g.ldz, g.zm, X, g.xa, g.xa_st, K_GEN_AXIS_ANALYSIS, st);
+  if (g.has_mid) {
+    if (x3 && stages == ST_X) {       // the exchange tensor arrives from outside: form its lo part here
+      int rc = launch_split_lo(W2, W2lo, (size_t)BC * p->Nx * 2 * p->my * p->mzh, st);
+      if (rc) return rc;
+    }
+    return axis_analysis_stage(p, x3, W2, W2lo, BC, p->Nx, p->mx, 2 * p->my * p->mzh, p->my * p->mzh, X, nullptr, g.xa, g.xa_lo,
+                               g.xa_st, st);
+  }
+  return axis_analysis_stage(p, x3, W1, W1lo, BC, p->Nx, p->mx, g.ldz, g.zm, X, nullptr, g.xa, g.xa_lo, g.xa_st, st);
 }
 
 static int launch_pad_scale(const float2* Z, float2* Zp, const float* mode_scale, const float* row_scale, long long rs_stride,
-                            int zm, int ldh, long long Mrows, long long total, cudaStream_t st) {
+                            int zm, int ldh, long long Mrows, long long total, cudaStream_t st, float2* Zp_lo = nullptr) {
   {
     ProfScope ps(K_SCALE_MODES, st);
     gen::gen_pad_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, Zp, mode_scale, row_scale, rs_stride, zm, ldh,
-                                                                             Mrows, total);
+                                                                             Mrows, total, Zp_lo);
   }
   PDEPHI_LAUNCH_CHECK("gen_pad_scale_kernel");
   return PDEPHI_OK;
@@ -888,15 +1397,19 @@ static int launch_pad_scale(const float2* Z, float2* Zp, const float* mode_scale
 
 int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1, const float* mode_scale,
                   const float* row_scale, long long rs_stride, long long BC, int direction, void* ws, cudaStream_t st, int stages,
-                  float2* T) {
+                  float2* T, bool x3) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(out) || !al16(add0) || !al16(add1)) return fail(PDEPHI_ERR_INVALID, "synthesis: buffers must be 16-byte aligned");
   const GenPlan& g = p->g;
+  if (x3 && !g.x3_ok) return fail(PDEPHI_ERR_UNSUPPORTED, "split-TF32 per-axis route is not available for this shape");
   const GenWs w = gen_ws(p, BC);
   char* wb = (char*)ws;
   float* W1 = (float*)(wb + w.w1);
   float* W2 = (float*)(wb + w.w2);
   float* Zp = (float*)(wb + w.zp);
+  float* W1lo = (float*)(wb + w.w1lo);
+  float* W2lo = (float*)(wb + w.w2lo);
+  float* Zplo = (float*)(wb + w.zplo);
   const int ldh = g.ldz / 2;
   const long long Mrows = (long long)p->mx * g.ym;
   const long long rows = BC * p->Nx * (g.has_mid ? p->Ny : 1);
@@ -904,40 +1417,50 @@ int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0,
   if (stages == ST_X) {
     // x stage alone: scaled modes -> unpadded exchange tensor T [BC, Nx, my, mzh]
     const float* src = (const float*)Z;
-    if (mode_scale || row_scale) {
-      int rc = launch_pad_scale(Z, (float2*)Zp, mode_scale, row_scale, rs_stride, g.zm, g.zm, Mrows, BC * Mrows * g.zm, st);
+    if (mode_scale || row_scale || x3) {
+      int rc = launch_pad_scale(Z, (float2*)Zp, mode_scale, row_scale, rs_stride, g.zm, g.zm, Mrows, BC * Mrows * g.zm, st,
+                                x3 ? (float2*)Zplo : nullptr);
       if (rc) return rc;
       src = Zp;
     }
-    return launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, 2 * p->my * p->mzh, (float*)T, g.xsc, g.xss, g.xs_st,
-                                 K_GEN_AXIS_SYNTHESIS, st);
+    return axis_synthesis_stage(p, x3, src, Zplo, BC, p->Nx, p->mx, g.mkx, 2 * p->my * p->mzh, (float*)T, nullptr, g.xsc, g.xss,
+                                g.xsc_lo, g.xss_lo, g.xs_st, st);
   }
   const float* zin;
   if (stages == ST_ZY) {
     // (y,z) stages alone from the unpadded exchange tensor: re-pad its rows when 2*mzh is not a multiple of 4
     const float* src = (const float*)T;
     if (g.ldz != 2 * g.zm) {
-      int rc = launch_pad_scale(T, (float2*)W2, nullptr, nullptr, 0, g.zm, ldh, 1, BC * p->Nx * (long long)p->my * ldh, st);
+      int rc = launch_pad_scale(T, (float2*)W2, nullptr, nullptr, 0, g.zm, ldh, 1, BC * p->Nx * (long long)p->my * ldh, st,
+                                x3 ? (float2*)W2lo : nullptr);
       if (rc) return rc;
       src = W2;
+    } else if (x3) {
+      int rc = launch_split_lo(src, W2lo, (size_t)BC * p->Nx * p->my * g.ldz, st);
+      if (rc) return rc;
     }
-    int rc = launch_axis_synthesis(p, src, BC * p->Nx, p->Ny, p->my, g.mky, g.ldz, W1, g.ysc, g.yss, g.ys_st, K_GEN_AXIS_SYNTHESIS, st);
+    int rc = axis_synthesis_stage(p, x3, src, W2lo, BC * p->Nx, p->Ny, p->my, g.mky, g.ldz, W1, W1lo, g.ysc, g.yss, g.ysc_lo,
+                                  g.yss_lo, g.ys_st, st);
     if (rc) return rc;
     zin = W1;
   } else {
     const float* src = (const float*)Z;
-    if (mode_scale || row_scale || g.ldz != 2 * g.zm) {
-      int rc = launch_pad_scale(Z, (float2*)Zp, mode_scale, row_scale, rs_stride, g.zm, ldh, Mrows, BC * Mrows * ldh, st);
+    if (mode_scale || row_scale || g.ldz != 2 * g.zm || x3) {
+      int rc = launch_pad_scale(Z, (float2*)Zp, mode_scale, row_scale, rs_stride, g.zm, ldh, Mrows, BC * Mrows * ldh, st,
+                                x3 ? (float2*)Zplo : nullptr);
       if (rc) return rc;
       src = Zp;
     }
     if (g.has_mid) {
-      int rc = launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, g.ym * g.ldz, W2, g.xsc, g.xss, g.xs_st, K_GEN_AXIS_SYNTHESIS, st);
+      int rc = axis_synthesis_stage(p, x3, src, Zplo, BC, p->Nx, p->mx, g.mkx, g.ym * g.ldz, W2, W2lo, g.xsc, g.xss, g.xsc_lo,
+                                    g.xss_lo, g.xs_st, st);
       if (rc) return rc;
-      rc = launch_axis_synthesis(p, W2, BC * p->Nx, p->Ny, p->my, g.mky, g.ldz, W1, g.ysc, g.yss, g.ys_st, K_GEN_AXIS_SYNTHESIS, st);
+      rc = axis_synthesis_stage(p, x3, W2, W2lo, BC * p->Nx, p->Ny, p->my, g.mky, g.ldz, W1, W1lo, g.ysc, g.yss, g.ysc_lo,
+                                g.yss_lo, g.ys_st, st);
       if (rc) return rc;
     } else {
-      int rc = launch_axis_synthesis(p, src, BC, p->Nx, p->mx, g.mkx, g.ldz, W1, g.xsc, g.xss, g.xs_st, K_GEN_AXIS_SYNTHESIS, st);
+      int rc = axis_synthesis_stage(p, x3, src, Zplo, BC, p->Nx, p->mx, g.mkx, g.ldz, W1, W1lo, g.xsc, g.xss, g.xsc_lo, g.xss_lo,
+                                    g.xs_st, st);
       if (rc) return rc;
     }
     zin = W1;
@@ -947,11 +1470,33 @@ int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0,
   if (rc) return rc;
   const int NKBK = (g.ldz + 31) / 32, ksteps = (g.ldz + 7) / 8;
   const int ntiles = (int)((rows + 127) / 128);
-  const size_t smem = gen::zs_smem(g.zN, NKBK, g.zs_ring).total + 1024;
   const int grid = ntiles < p->num_sms ? ntiles : p->num_sms;
-  const int tmem_cols = pow2_at_least(2 * g.zN);
   if (add1 && !add0) { add0 = add1; add1 = nullptr; }
   const int nadd = (add0 ? 1 : 0) + (add1 ? 1 : 0);
+  if (x3) {
+    CUtensorMap maplo;
+    rc = gen_make_map(&maplo, W1lo, rows, g.ldz, 128, false);
+    if (rc) return rc;
+    for (int j = 0; j < g.zs3_np; ++j) {         // one launch per block of output positions
+      const int nc = g.zs3_nc[j], c0 = g.zs3_c0[j];
+      const size_t smem = gen::zs3_smem(nc, NKBK, g.zs3_ring[j]).total + 1024;
+      const int tmem_cols = pow2_at_least(4 * nc);
+#define PDEPHI_GZS3_LAUNCH(NA)                                                                                           \
+  {                                                                                                                      \
+    auto k = gen::gen_z_synthesis_x3_kernel<NA>;                                                                         \
+    PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+    ProfScope ps(K_GEN_Z_SYNTHESIS, st);                                                                                 \
+    k<<<grid, gen::ZS_THREADS, smem, st>>>(map, maplo, out, add0, add1, g.zs3[direction][j], rows, ntiles, g.zN, c0, nc, \
+                                           NKBK, ksteps, g.zs3_ring[j], tmem_cols);                                      \
+  }
+      if (nadd == 0) PDEPHI_GZS3_LAUNCH(0) else if (nadd == 1) PDEPHI_GZS3_LAUNCH(1) else PDEPHI_GZS3_LAUNCH(2)
+#undef PDEPHI_GZS3_LAUNCH
+    }
+    PDEPHI_LAUNCH_CHECK("gen_z_synthesis_x3_kernel");
+    return PDEPHI_OK;
+  }
+  const size_t smem = gen::zs_smem(g.zN, NKBK, g.zs_ring).total + 1024;
+  const int tmem_cols = pow2_at_least(2 * g.zN);
 #define PDEPHI_GZS_LAUNCH(NA)                                                                                            \
   {                                                                                                                      \
     auto k = gen::gen_z_synthesis_kernel<NA>;                                                                            \

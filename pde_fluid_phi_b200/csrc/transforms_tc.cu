@@ -548,14 +548,27 @@ int xstage_synthesis(const Plan* p, const float2* Z, float2* ws, const float* mo
                      long long rs_stride, long long BC, cudaStream_t st);
 bool xstage_analysis_tc_ok(const Plan* p);
 bool xstage_synthesis_tc_ok(const Plan* p);
+bool xstage_analysis_tc3_ok(const Plan* p);
+bool xstage_synthesis_tc3_ok(const Plan* p);
+int xstage_analysis_tc3(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st);
+int xstage_synthesis_tc3(const Plan* p, const float2* Z, float2* ws, float2* scratch, const float* mode_scale,
+                         const float* row_scale, long long rs_stride, long long BC, cudaStream_t st);
 int xstage_analysis_tc(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st);
 int xstage_synthesis_tc(const Plan* p, const float2* Z, float2* ws, float2* scratch, const float* mode_scale,
                         const float* row_scale, long long rs_stride, long long BC, cudaStream_t st);
 
+// The x stage works on the pruned intermediate (6.6 % of an activation): running it split (three MMAs per product, the
+// kernels of the fp32-grade route) costs ~20 us per call and removes one of the three TF32 roundings of the transform
+// (5.8e-4 -> 4.7e-4 per transform).  OPT_TF32_XSTAGE_SPLIT (default on) selects it.
+static int xstage_analysis_for_tf32(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st) {
+  if (option_get(OPT_TF32_XSTAGE_SPLIT) && xstage_analysis_tc3_ok(p)) return xstage_analysis_tc3(p, ws, X, BC, st);
+  return xstage_analysis_tc_ok(p) ? xstage_analysis_tc(p, ws, X, BC, st) : xstage_analysis(p, ws, X, BC, st);
+}
+
 int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int direction, float2* ws, cudaStream_t st,
                 int stages, float2* T) {
   if (stages != ST_ALL) ws = T;
-  if (!(stages & ST_ZY)) return xstage_analysis_tc_ok(p) ? xstage_analysis_tc(p, ws, X, BC, st) : xstage_analysis(p, ws, X, BC, st);
+  if (!(stages & ST_ZY)) return xstage_analysis_for_tf32(p, ws, X, BC, st);
   const size_t planes = (size_t)BC * p->Nx;
   if (planes * 128 > 0x7fffffffULL) return fail(PDEPHI_ERR_UNSUPPORTED, "analysis_tc: too many rows for the tensor map");
   if (reinterpret_cast<uintptr_t>(x) & 15) return fail(PDEPHI_ERR_INVALID, "analysis_tc: x must be 16-byte aligned");
@@ -580,8 +593,7 @@ int analysis_tc(const Plan* p, const float* x, float2* X, long long BC, int dire
   }
   PDEPHI_LAUNCH_CHECK("analysis_zy_tc_kernel");
   if (!(stages & ST_X)) return PDEPHI_OK;
-  if (xstage_analysis_tc_ok(p)) return xstage_analysis_tc(p, ws, X, BC, st);
-  return xstage_analysis(p, ws, X, BC, st);
+  return xstage_analysis_for_tf32(p, ws, X, BC, st);
 }
 
 int synthesis_tc(const Plan* p, const float2* Z, float* out, const float* add0, const float* add1,
@@ -594,7 +606,9 @@ int synthesis_tc(const Plan* p, const float2* Z, float* out, const float* add0, 
   if (stages != ST_ALL) ws = T;
   if (stages & ST_X) {
     int rc;
-    if (xstage_synthesis_tc_ok(p)) rc = xstage_synthesis_tc(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st);
+    if (option_get(OPT_TF32_XSTAGE_SPLIT) && xstage_synthesis_tc3_ok(p))
+      rc = xstage_synthesis_tc3(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st);
+    else if (xstage_synthesis_tc_ok(p)) rc = xstage_synthesis_tc(p, Z, ws, scratch, mode_scale, row_scale, rs_stride, BC, st);
     else rc = xstage_synthesis(p, Z, ws, mode_scale, row_scale, rs_stride, BC, st);
     if (rc) return rc;
   }

@@ -29,24 +29,24 @@ if __name__ == "__main__":
     dev = "cuda"
     torch.manual_seed(0)
     res = {}
-    rfl = pb.RationalFourierLayer(64, 64, (32, 32, 32)).to(dev); rfl.precision = prec
-    x = torch.randn(8, 64, 128, 128, 128, device=dev, requires_grad=True)
-    res["RationalFourierLayer cfg2 [8,64,128^3] modes 32^3"] = time_layer(rfl, x, iters)
-    sc = pb.SpectralConv3D(64, 64, (32, 32, 32)).to(dev); sc.precision = prec
-    res["SpectralConv3D cfg2-shape [8,64,128^3] modes 32^3"] = time_layer(sc, x, iters)
-    del x
-    sc1 = pb.SpectralConv3D(32, 32, (8, 8, 8)).to(dev)
+    if "--gen-only" not in sys.argv:
+        rfl = pb.RationalFourierLayer(64, 64, (32, 32, 32)).to(dev); rfl.precision = prec
+        x = torch.randn(8, 64, 128, 128, 128, device=dev, requires_grad=True)
+        res["RationalFourierLayer cfg2 [8,64,128^3] modes 32^3"] = time_layer(rfl, x, iters)
+        sc = pb.SpectralConv3D(64, 64, (32, 32, 32)).to(dev); sc.precision = prec
+        res["SpectralConv3D cfg2-shape [8,64,128^3] modes 32^3"] = time_layer(sc, x, iters)
+        del x
+    sc1 = pb.SpectralConv3D(32, 32, (8, 8, 8)).to(dev); sc1.precision = prec
     x1 = torch.randn(4, 32, 32, 32, 32, device=dev, requires_grad=True)
-    res["SpectralConv3D cfg1 [4,32,32^3] modes 8^3 (fp32 path)"] = time_layer(sc1, x1, iters)
-    rf1 = pb.RationalFourierLayer(32, 32, (8, 8, 8)).to(dev)
-    res["RationalFourierLayer cfg1-shape [4,32,32^3] modes 8^3 (fp32 path)"] = time_layer(rf1, x1, iters)
-    if prec == "tf32" and "--gen" in sys.argv:
+    res[f"SpectralConv3D cfg1 [4,32,32^3] modes 8^3 ({prec})"] = time_layer(sc1, x1, iters)
+    rf1 = pb.RationalFourierLayer(32, 32, (8, 8, 8)).to(dev); rf1.precision = prec
+    res[f"RationalFourierLayer cfg1-shape [4,32,32^3] modes 8^3 ({prec})"] = time_layer(rf1, x1, iters)
+    if "--gen" in sys.argv:
         def conditioned(layer):
             with torch.no_grad():
                 q0 = layer.Q_coeffs[..., 0, 0, 0].clone(); layer.Q_coeffs.mul_(1e-6); layer.Q_coeffs[..., 0, 0, 0] = q0
             layer.precision = prec
             return layer
-        res = {}
         del x1
         x3 = torch.randn(64, 64, 256, 256, 1, device=dev, requires_grad=True)
         sc3 = pb.SpectralConv3D(64, 64, (64, 64, 1)).to(dev); sc3.precision = prec

@@ -754,8 +754,9 @@ def test_first_block_with_lift_in_mode_space(cls, grid, x_grad):
     assert rel(res[True][0], res[False][0]) < tol_out
     for n in res[True][1]:
         assert rel(res[True][1][n], res[False][1][n]) < tol_g, (n, rel(res[True][1][n], res[False][1][n]))
-    if not x_grad and prec == "tf32":     # one adjoint synthesis fewer
-        assert res[True][2]["synthesis_zy_tc_kernel"][0] == res[False][2]["synthesis_zy_tc_kernel"][0] - 1
+    if not x_grad and prec == "tf32":     # one adjoint synthesis fewer (the tf32 route runs it on the split kernels)
+        count = lambda rep: rep.get("synthesis_zy_tc_kernel", (0,))[0] + rep.get("synthesis_zy_tc3_kernel", (0,))[0]
+        assert count(res[True][2]) == count(res[False][2]) - 1
 
 
 # ------------------------------------------------------------------------------------------------
@@ -836,9 +837,9 @@ def test_stability_projection_attributes_are_honoured(energy, proj_eps):
     ref.backward(g)
     for a, b, name in zip(got, (ref, x.grad, layer.P_coeffs.grad, layer.Q_coeffs.grad), ("out", "dx", "dP", "dQ")):
         assert rel(a, b) < 2e-5, (name, rel(a, b))
-    # and the attribute really matters (the default-attribute layer gives something else)
-    layer.stability_projection.energy_conserving, layer.stability_projection.eps = True, 1e-6
-    assert rel(layer(x), got[0]) > 1e-4
+    if not energy:      # ... and the attribute really matters: the energy-conserving default gives something else
+        layer.stability_projection.energy_conserving = True
+        assert rel(layer(x), got[0]) > 1e-4
 
 
 def test_replaced_projection_module_raises():
