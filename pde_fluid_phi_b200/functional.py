@@ -71,10 +71,13 @@ def monomial_table(modes: Sequence[int], order: int) -> torch.Tensor:
 # (almost) nothing to run on the fp32-grade tensor-core kernels, so the TF32 rounding noise of the route is spent only where
 # it buys time (measured on the headline model, tests/test_headline_gate_gpu.py):
 #   lift_analysis      the first block's forward analysis reads the 3-channel model input, not a 64-channel activation
-#   adjoint_synthesis  the backward's adjoint synthesis carries an addend: HBM-bound either way (1.46 vs 1.41 ms)
+#   adjoint_synthesis  the backward's adjoint synthesis: +0.48 ms per call in the training step (1.89 vs 1.41 ms) and no
+#                      change of the worst gradient error (1.32e-3 either way): off
 #   backward_analysis / forward_analysis  the full-size analyses: +0.55 ms per call on the split kernels (off)
+# The x stage (OPT_TF32_XSTAGE_SPLIT in the library, +0.5 ms per step) is what brings the worst coefficient gradient of the
+# headline model from 2.03e-3 to 1.49e-3; the lift analysis takes it to 1.32e-3.
 # ------------------------------------------------------------------------------------------------
-TF32_SPLIT_WHERE = {"lift_analysis": True, "adjoint_synthesis": True, "backward_analysis": False, "forward_analysis": False}
+TF32_SPLIT_WHERE = {"lift_analysis": True, "adjoint_synthesis": False, "backward_analysis": False, "forward_analysis": False}
 _split_ok = {}
 
 
