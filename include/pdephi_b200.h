@@ -224,8 +224,9 @@ int pdephi_block_tail_proj_bwd(const float* gout, const float* Wp, int n_out, co
                                size_t workspace_bytes, pdephi_stream_t stream);
 
 /* ---- the FIRST block of a model together with the input lift (nn.Linear n_in <= 4 -> 64) -------------------
- * replaces rational_fourier.py:258-260 / fno3d.py:86-88 under the block above: the block's input h = Win x + bin is
- * generated tile by tile inside the block-tail kernels from x [B,n_in,S] -- h is never written to or read from HBM.
+ * replaces rational_fourier.py:258-260 / fno3d.py:86-88 under the block above: the block's input h = Win x + bin is never
+ * written to or read from HBM.  The fused forward folds it into the epilogue (u = spec + (Wc + I) Win x + (Wc + I) bin + bc,
+ * n_in FMAs per element, no 64-channel operand tile); the unfused forward and the backward with t generate it tile by tile.
  * Win [64,n_in] row-major, bin [64] or NULL.  (The block's modes follow from the modes of x: A(h) = Win A(x) + bin N delta_k0.) */
 int pdephi_block_tail_lift_fwd(const float* x, const float* Win, const float* bin, int n_in, const float* spec, const float* Wc,
                                const float* bc, float* u, float* hout, int B, int C, long long S, pdephi_stream_t stream);
@@ -233,9 +234,35 @@ int pdephi_block_spectral_lift_fwd(pdephi_plan_t plan, const float* Y, const flo
                                    long long row_scale_stride, const float* x, const float* Win, const float* bin, int n_in,
                                    const float* Wc, const float* bc, float* u, float* hout, int B, int C, void* workspace,
                                    size_t workspace_bytes, pdephi_stream_t stream);
+/* Backward.  t == NULL (the model input needs no gradient): the block needs neither t nor an h0 tile -- dWc = G Win^T +
+ * dbc (x) bin with G [64,n_in] = sum_s gu (x) x accumulated on the tensor cores against the staged x rows; G (may be NULL) is
+ * also returned: it is what the lift's own weight gradient needs (dWin = (I + Wc^T) G + the mode-space term). */
 int pdephi_block_tail_lift_bwd(const float* g, const float* u, const float* x, const float* Win, const float* bin, int n_in,
-                               const float* Wc, float* gu, float* t, float* dWc, float* dbc, int B, int C, long long S,
+                               const float* Wc, float* gu, float* t, float* dWc, float* dbc, float* G, int B, int C, long long S,
                                void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
+/* ---- pointwise maps with up to 64 channels on BOTH sides, fp32 FFMA, any spatial size (pointwise_wide.cu) --------------
+ * wide_linear: out[b,o,s] = bias[o] + sum_i W(o,i) x[b,i,s] (+ add0 + add1, each [B,Cout,S] or NULL);
+ * W(o,i) = transpose_w ? W[i*Cout + o] : W[o*Cin + i].  Replaces rearrange -> nn.Linear -> rearrange for the lift / projection
+ * of operators built with in_channels = out_channels = width (models/multiscale_fno.py:100-127), and its backward
+ * (dx: the same call with transpose_w = 1; dW, db: pdephi_wide_wgrad). */
+int pdephi_wide_linear(const float* x, const float* W, const float* bias, const float* add0, const float* add1, float* out, int B,
+                       int Cin, int Cout, long long S, int transpose_w, pdephi_stream_t stream);
+size_t pdephi_wide_wgrad_workspace_bytes(int B, long long S);
+int pdephi_wide_wgrad(const float* x, const float* g, float* dW, float* dbias, int B, int Cin, int Cout, long long S, void* workspace,
+                      size_t workspace_bytes, pdephi_stream_t stream);
+/* The block tail (see pdephi_block_tail_fwd / _bwd) for ANY width C <= 64, any spatial size and the activations the models are
+ * usually built with (fno3d.py:57 `getattr(F, activation)`), fp32: u = spec + (Wc h + bc) + h, hout = act(u);
+ * gu = g act'(u), t = gu + Wc^T gu, dWc = sum gu (x) h, dbc = sum gu.  workspace: pdephi_wide_wgrad_workspace_bytes(B, S). */
+enum pdephi_activation {
+  PDEPHI_ACT_IDENTITY = 0, PDEPHI_ACT_GELU = 1 /* exact (erf) */, PDEPHI_ACT_RELU = 2, PDEPHI_ACT_TANH = 3, PDEPHI_ACT_SILU = 4,
+  PDEPHI_ACT_SIGMOID = 5, PDEPHI_ACT_LEAKY_RELU = 6 /* slope 0.01 */, PDEPHI_ACT_ELU = 7 /* alpha 1 */
+};
+int pdephi_wide_block_tail_fwd(const float* h, const float* spec, const float* Wc, const float* bc, float* u, float* hout, int B,
+                               int C, long long S, int activation, pdephi_stream_t stream);
+int pdephi_wide_block_tail_bwd(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t, float* dWc,
+                               float* dbc, int B, int C, long long S, int activation, void* workspace, size_t workspace_bytes,
+                               pdephi_stream_t stream);
 
 /* ---- run-time options ------------------------------------------------------------------------------
  * PDEPHI_OPT_TF32_XSTAGE_SPLIT (default 1): on the single-pass TF32 route the x stage -- which works on the pruned

@@ -10,7 +10,8 @@ import os
 import threading
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpdephi_b200.so")
+# PDEPHI_LIB: an alternate build of the same library (kernel experiments: `python -m pde_fluid_phi_b200.build --variant NAME -D...`)
+_LIB_PATH = os.environ.get("PDEPHI_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpdephi_b200.so")
 _lib = None
 _lock = threading.RLock()
 
@@ -20,6 +21,7 @@ PREC_AUTO = -1    # host-side only: TF32X3 where the plan supports it, FP32 (FFM
 FORWARD, ADJOINT = 0, 1
 STAGES_ZY, STAGES_X, STAGES_ALL = 1, 2, 3
 OPT_TF32_XSTAGE_SPLIT = 0
+ACTIVATIONS = {"identity": 0, "gelu": 1, "relu": 2, "tanh": 3, "silu": 4, "sigmoid": 5, "leaky_relu": 6, "elu": 7}
 ROUTE_NONE, ROUTE_FFMA, ROUTE_FUSED_TC, ROUTE_PER_AXIS_TC = 0, 1, 2, 3
 PER_AXIS_SPLIT_MIN_POINTS = 1 << 25      # 'auto': below this many points per call the FFMA kernels beat the per-axis split route
 PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
@@ -88,7 +90,15 @@ SIGNATURES = {
                                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
                                                c_void_p]),
     "pdephi_block_tail_lift_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                           c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_size_t, c_void_p]),
+                                           c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_size_t, c_void_p]),
+    "pdephi_wide_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int,
+                                   c_void_p]),
+    "pdephi_wide_wgrad_workspace_bytes": (c_size_t, [c_int, c_longlong]),
+    "pdephi_wide_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_size_t, c_void_p]),
+    "pdephi_wide_block_tail_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int,
+                                           c_void_p]),
+    "pdephi_wide_block_tail_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                           c_longlong, c_int, c_void_p, c_size_t, c_void_p]),
     "pdephi_set_option": (c_int, [c_int, c_int]),
     "pdephi_get_option": (c_int, [c_int]),
     "pdephi_profile_enable": (c_int, [c_int]),

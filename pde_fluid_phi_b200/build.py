@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libpdephi_b200.so")
-SOURCES = ["plan.cu", "api.cu", "transforms_simt.cu", "transforms_tc.cu", "transforms_tc3.cu", "mix.cu", "pointwise.cu", "block_tc.cu", "xstage_tc.cu", "transforms_gen.cu"]
+SOURCES = ["plan.cu", "api.cu", "transforms_simt.cu", "transforms_tc.cu", "transforms_tc3.cu", "mix.cu", "pointwise.cu", "pointwise_wide.cu", "block_tc.cu", "xstage_tc.cu", "transforms_gen.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -31,16 +31,19 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """variant / defines: an experiment build, lib/libpdephi_b200.<variant>.so compiled with the extra -D flags (loaded with
+    PDEPHI_LIB=<path>); the product is the plain build."""
+    lib = LIB if not variant else os.path.join(LIBDIR, f"libpdephi_b200.{variant}.so")
+    if not variant and not force and not _stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build" if not variant else f"build_{variant}")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
@@ -52,12 +55,14 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [NVCC, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=variant,
+                        defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -27,7 +27,11 @@ constexpr int BOX = C * 128;     // bytes of one [64 rows][32 floats] box
 constexpr int TILE = 4 * BOX;    // 32 KB
 constexpr int EPI_WARPS = 16;    // 4 TMEM quarters x 4 channel groups: enough warps to hide LDS / MUFU latency
 constexpr int CPW = C / (EPI_WARPS / 4);   // channels per epilogue warp (16)
-constexpr int LD_WARPS = 4;      // cp.async loader warps: warp w stages channel rows [16w, 16w+16) of every tile
+#ifndef PDEPHI_LD_WARPS
+#define PDEPHI_LD_WARPS 4
+#endif
+constexpr int LD_WARPS = PDEPHI_LD_WARPS;   // cp.async loader warps: warp w stages channel rows w, w + LD_WARPS, ... of every tile
+constexpr int LD_ROWS = (64 + LD_WARPS - 1) / LD_WARPS;
 constexpr int LD_THREADS = 32 * LD_WARPS;
 constexpr int EPI0 = 1 + LD_WARPS;         // first epilogue warp (warp 0 issues the MMAs)
 constexpr int THREADS = 32 * (EPI0 + EPI_WARPS);
@@ -120,11 +124,12 @@ __device__ __forceinline__ uint32_t chunk_off_k(int r, int lane) {
 template <bool KMAJOR>
 __device__ __forceinline__ void stage_rows(uint32_t dst, const float* __restrict__ t, long long b, long long s0, long long S,
                                            int lw, int lane) {
-  const float* src = t + ((size_t)b * C + lw * 16) * S + s0 + lane * 4;
+  const float* src = t + ((size_t)b * C + lw) * S + s0 + lane * 4;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int r = lw * 16 + i;
-    cp_async16(dst + (KMAJOR ? chunk_off_k(r, lane) : chunk_off_mn(r, lane)), src + (size_t)i * S);
+  for (int i = 0; i < LD_ROWS; ++i) {
+    const int r = lw + LD_WARPS * i;
+    if (C % LD_WARPS == 0 || r < C)
+      cp_async16(dst + (KMAJOR ? chunk_off_k(r, lane) : chunk_off_mn(r, lane)), src + (size_t)i * LD_WARPS * S);
   }
 }
 
@@ -143,8 +148,9 @@ template <bool KMAJOR>
 __device__ __forceinline__ void generate_rows(uint8_t* dst, const float4* xv, const uint8_t* wtab, int lw, int lane) {
   const float* bias = reinterpret_cast<const float*>(wtab + C * 16);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int r = lw * 16 + i;
+  for (int i = 0; i < LD_ROWS; ++i) {
+    const int r = lw + LD_WARPS * i;
+    if (C % LD_WARPS != 0 && r >= C) break;
     const float4 w = reinterpret_cast<const float4*>(wtab)[r];
     const float bb = bias[r];
     float4 o;
@@ -160,6 +166,38 @@ __device__ __forceinline__ void build_lift_table(uint8_t* wtab, const float* __r
   float* w = reinterpret_cast<float*>(wtab);
   for (int i = tid; i < C * 4; i += nthr) w[i] = ((i & 3) < n_in) ? __ldg(Win + (i >> 2) * n_in + (i & 3)) : 0.f;
   for (int i = tid; i < C; i += nthr) w[C * 4 + i] = bin ? __ldg(bin + i) : 0.f;
+}
+// The first block needs no h0 tile at all:  u = spec + Wc h0 + bc + h0  with  h0 = W_in x + b_in  is
+//   u = spec + W_eff x + b_eff,   W_eff = (Wc + I) W_in  [64 x n_in],   b_eff = (Wc + I) b_in + bc,
+// three FMAs per element in the epilogue instead of a generated 64-channel operand tile and a 64 x 64 contraction (the
+// generating loader warps, not HBM, set the pace of that launch: 3.7 TB/s).  Same table layout as build_lift_table; fp32.
+__device__ __forceinline__ void build_lift_eff_table(uint8_t* wtab, const float* __restrict__ Win, const float* __restrict__ bin,
+                                                     int n_in, const float* __restrict__ Wc, const float* __restrict__ bc, int tid,
+                                                     int nthr) {
+  float* w = reinterpret_cast<float*>(wtab);
+  for (int i = tid; i < C * 4 + C; i += nthr) {
+    const int c = i < C * 4 ? i >> 2 : i - C * 4, n = i & 3;
+    float acc = 0.f;
+    if (i < C * 4) {
+      if (n < n_in) {
+        acc = __ldg(Win + c * n_in + n);
+        for (int k = 0; k < C; ++k) acc = fmaf(__ldg(Wc + c * C + k), __ldg(Win + k * n_in + n), acc);
+      }
+    } else {
+      acc = bc ? __ldg(bc + c) : 0.f;
+      if (bin) {
+        acc += __ldg(bin + c);
+        for (int k = 0; k < C; ++k) acc = fmaf(__ldg(Wc + c * C + k), __ldg(bin + k), acc);
+      }
+    }
+    w[i] = acc;
+  }
+}
+// one row of a small side tensor ([B, n, S], n <= 4: the model input x / the output gradient gout) staged plain:
+// lane = 16-byte chunk of the 128-point row
+__device__ __forceinline__ void stage_small_rows(uint32_t dst, const float* __restrict__ t, int n, long long b, long long s0,
+                                                 long long S, int lane) {
+  for (int r = 0; r < n; ++r) cp_async16(dst + r * 512 + lane * 16, t + ((size_t)b * n + r) * S + s0 + lane * 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -209,7 +247,9 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
 
   // the truncation bias of the data operands (h; V) is undone on the accumulator in the epilogue, not in the weights
   build_w_image(sm + L.w, Wc, false, threadIdx.x, THREADS, 1.0f);
-  if (GENH) build_lift_table(sm + L.lift, Win, bin, n_in, threadIdx.x, THREADS);
+  constexpr bool LIFT_EFF = GENH && FUSED;     // first block, fused forward: no h0 tile (build_lift_eff_table)
+  if (LIFT_EFF) build_lift_eff_table(sm + L.lift, Win, bin, n_in, Wc, bc, threadIdx.x, THREADS);
+  else if (GENH) build_lift_table(sm + L.lift, Win, bin, n_in, threadIdx.x, THREADS);
   if (PROJ) {
     float* wp = reinterpret_cast<float*>(sm + L.wp);
     for (int i = threadIdx.x; i < C * MAXP + MAXP; i += THREADS) {
@@ -262,19 +302,20 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       load_x(xnext, h_in, n_in, b, s0, S, lane);
     };
-    if (GENH && my_tiles > 0) fetch_x(0);
+    if (GENH && !LIFT_EFF && my_tiles > 0) fetch_x(0);
     auto issue = [&](long long it) {
       const long long t = tile0 + it * tstep;
       const int s = (int)(it % F_STAGES);
       float4 xv[MAXP_IN];
-      if (GENH) {
+      if (GENH && !LIFT_EFF) {
 #pragma unroll
         for (int n = 0; n < MAXP_IN; ++n) xv[n] = xnext[n];
         if (it + 1 < my_tiles) fetch_x(it + 1);
       }
       mbar_wait(bar(FB_EMPTY + s), (uint32_t)(((it / F_STAGES) & 1) ^ 1));
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
-      if (GENH) generate_rows<false>(sm + L.stage[s], xv, sm + L.lift, lw, lane);   // h_in = model input x
+      if (LIFT_EFF) { if (lw == 0) stage_small_rows(base + L.stage[s], h_in, n_in, b, s0, S, lane); }   // x rows, plain
+      else if (GENH) generate_rows<false>(sm + L.stage[s], xv, sm + L.lift, lw, lane);   // h_in = model input x
       else stage_rows<false>(base + L.stage[s], h_in, b, s0, S, lw, lane);
       if (FUSED) {
         // V rows of tile t are contiguous: chunk q = (channel c, chunk j of its row) -> K-major 128B-swizzled B operand
@@ -309,14 +350,16 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
         mbar_wait(bar(FB_FULL + s), (uint32_t)((it / F_STAGES) & 1));
         mbar_wait(bar(FB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
+        if (!LIFT_EFF) {
 #pragma unroll
-        for (int k = 0; k < C / 8; ++k)
-          mma_ss(tmem + d * C, umma_desc_mn(base + L.stage[s] + k * 1024, BOX),
-                 umma_desc(base + L.w + (k >> 2) * BOX + (k & 3) * 32, 1024), id, k ? 1u : 0u);
+          for (int k = 0; k < C / 8; ++k)
+            mma_ss(tmem + d * C, umma_desc_mn(base + L.stage[s] + k * 1024, BOX),
+                   umma_desc(base + L.w + (k >> 2) * BOX + (k & 3) * 32, 1024), id, k ? 1u : 0u);
+        }
         if (FUSED) {
           for (int k = 0; k < ksteps; ++k)         // z stage of the synthesis: += Bz[z][k] . V[ch][k]
             mma_ss(tmem + d * C, umma_desc(base + L.bz + (k >> 2) * (TS * 128) + (k & 3) * 32, 1024),
-                   umma_desc(base + L.stage[s] + TILE + (k >> 2) * BOX + (k & 3) * 32, 1024), idz, 1u);
+                   umma_desc(base + L.stage[s] + TILE + (k >> 2) * BOX + (k & 3) * 32, 1024), idz, (LIFT_EFF && k == 0) ? 0u : 1u);
         }
         mma_commit(bar(FB_EMPTY + s));
         mma_commit(bar(FB_DFULL + d));
@@ -327,7 +370,9 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float bsr[CPW];
 #pragma unroll
-    for (int j = 0; j < CPW; ++j) bsr[j] = reinterpret_cast<const float*>(sm + L.bias)[part * CPW + j];
+    for (int j = 0; j < CPW; ++j)
+      bsr[j] = LIFT_EFF ? reinterpret_cast<const float*>(sm + L.lift)[C * 4 + part * CPW + j]      // b_eff
+                        : reinterpret_cast<const float*>(sm + L.bias)[part * CPW + j];
     // element (channel row o = part*CPW + j, point 32q + lane): the swizzle term depends on o & 3 = j & 3 only
     uint32_t xc[4];
 #pragma unroll
@@ -351,11 +396,21 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
       // what the three-deep ring has to cover (measured: the kernel took 2.0 ms with an empty epilogue and 3.2 ms with
       // the real one at any byte count -- it was bound by this chain, not by HBM).
       float pre[CPW];
+      if (LIFT_EFF) {      // this thread's point of the n_in <= 4 input channels (rows beyond n_in are never written: weight 0)
+        const float* xs = reinterpret_cast<const float*>(th) + 32 * q + lane;
+        const float x0 = xs[0], x1 = n_in > 1 ? xs[128] : 0.f, x2 = n_in > 2 ? xs[256] : 0.f, x3 = n_in > 3 ? xs[384] : 0.f;
 #pragma unroll
-      for (int j = 0; j < CPW; ++j) {
-        const uint32_t off = xc[j & 3] + j * 128;
-        pre[j] = *reinterpret_cast<const float*>(th + off);
-        if (!FUSED) pre[j] += *reinterpret_cast<const float*>(tsp + off);
+        for (int j = 0; j < CPW; ++j) {
+          const float4 w = reinterpret_cast<const float4*>(sm + L.lift)[part * CPW + j];
+          pre[j] = fmaf(w.w, x3, fmaf(w.z, x2, fmaf(w.y, x1, w.x * x0)));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) {
+          const uint32_t off = xc[j & 3] + j * 128;
+          pre[j] = *reinterpret_cast<const float*>(th + off);
+          if (!FUSED) pre[j] += *reinterpret_cast<const float*>(tsp + off);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(FB_EMPTY + s));
@@ -407,10 +462,12 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
 //   warp 0: MMA issuer + TMEM owner, warps 1..4: loaders, warps 5..20: compute / epilogue
 // ------------------------------------------------------------------------------------------------
 constexpr int B_STAGES = 2;
-struct BSmem { uint32_t stage[B_STAGES], wt, red, wp, lift, bars, tmem_slot, total; };
+constexpr int AUX = 4096;        // per stage: the x rows as a K-major [8 rows][128 points] operand (LIFT_G)
+struct BSmem { uint32_t stage[B_STAGES], aux[B_STAGES], wt, red, wp, lift, bars, tmem_slot, total; };
 __host__ __device__ inline BSmem bwd_smem() {
   BSmem s; uint32_t o = 0;
   for (int i = 0; i < B_STAGES; ++i) { s.stage[i] = o; o += 3 * TILE; }   // g' (-> gu, MN layout), h (K layout), u (-> gu, K layout)
+  for (int i = 0; i < B_STAGES; ++i) { s.aux[i] = o; o += AUX; }
   s.wt = o; o += 2 * BOX;
   s.red = o; o += 4 * C * 4;
   s.wp = o; o += C * 16;                                                   // GENG: [64] float4 columns of the projection weight
@@ -426,9 +483,14 @@ enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2
        BB_DWDONE = 2 * B_STAGES + 6 };
 
 // GENG: the incoming gradient g' = Wp^T gout of the LAST block (the output projection's input gradient) is generated by the
-// loader warps from gout [B, n_out <= 4, S] instead of being read: the 4.3 GB g' is neither written nor read.
+// loader warps from gout [B, n_out <= 4, S] instead of being read: the 4.3 GB g' is neither written nor read.  (Forming it
+// in step 1 from staged gout rows instead was measured slower, 3.62 vs 3.52 ms: the compute warps are this kernel's bound.)
 // WT = false: t is not needed (first block of a model whose input needs no gradient: the lift's weight gradient is formed
 // from gu and the retained modes instead, functional.py::_lift_backward) and is not stored.
+// GENH && !WT ("LIFT_G"): that first block needs no h0 tile either.  dWc = sum gu (x) h0 with h0 = W_in x + b_in is
+//   dWc = G W_in^T + dbc (x) b_in,   G = sum_s gu (x) x  [64 x n_in],
+// so the weight-gradient GEMM runs against the staged x rows (N = 8 instead of 64) and the reduce kernel finishes dWc;
+// G is also what the lift's own weight gradient needs, so the separate pass over gu (pointwise_wgrad, 4.3 GB) goes too.
 template <bool GENG, bool WT, bool GENH>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
@@ -443,12 +505,17 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  constexpr bool LIFT_G = GENH && !WT;
   build_w_image(sm + L.wt, Wc, true, threadIdx.x, THREADS, TF32_COMP);      // rows c, K = o : (Wc^T)
   if (GENG) {
     float* wp = reinterpret_cast<float*>(sm + L.wp);
     for (int i = threadIdx.x; i < C * MAXP; i += THREADS) wp[i] = ((i & 3) < NP) ? __ldg(Wp + (i & 3) * C + (i >> 2)) : 0.f;
   }
-  if (GENH) build_lift_table(sm + L.lift, Win, bin, n_in, threadIdx.x, THREADS);
+  if (GENH && !LIFT_G) build_lift_table(sm + L.lift, Win, bin, n_in, threadIdx.x, THREADS);
+  if (LIFT_G) {              // operand rows beyond n_in are never written: zero once
+    float4* z = reinterpret_cast<float4*>(sm + L.aux[0]);
+    for (int i = threadIdx.x; i < B_STAGES * AUX / 16; i += THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), LD_THREADS); mbar_init(bar(BB_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
@@ -492,7 +559,14 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       } else {
         stage_rows<false>(base + L.stage[s], g_in, b, s0, S, lw, lane);
       }
-      if (GENH) {                                                                  // h_in = model input x
+      if (LIFT_G) {      // h_in = model input x: its n_in rows as a K-major operand [8 rows][128 points], 128-byte swizzle
+        if (lw == 0) {
+          const int j = lane >> 3, cc = lane & 7;
+          for (int r = 0; r < n_in; ++r)
+            cp_async16(base + L.aux[s] + (uint32_t)(j * 1024 + r * 128 + (((cc ^ (r & 7)) & 7) << 4)),
+                       h_in + ((size_t)b * n_in + r) * S + s0 + lane * 4);
+        }
+      } else if (GENH) {                                                           // h_in = model input x
         float4 xv[MAXP_IN];
         load_x(xv, h_in, n_in, b, s0, S, lane);
         generate_rows<true>(sm + L.stage[s] + TILE, xv, sm + L.lift, lw, lane);
@@ -503,8 +577,9 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       if (GENG) {
         uint8_t* dst = sm + L.stage[s];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int r = lw * 16 + i;
+        for (int i = 0; i < LD_ROWS; ++i) {
+          const int r = lw + LD_WARPS * i;
+          if (C % LD_WARPS != 0 && r >= C) break;
           const float4 w = reinterpret_cast<const float4*>(sm + L.wp)[r];
           float4 o;
           o.x = fmaf(w.w, gv[3].x, fmaf(w.z, gv[2].x, fmaf(w.y, gv[1].x, w.x * gv[0].x)));
@@ -538,15 +613,26 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         mbar_wait(bar(BB_TEMPTY + d), ph ^ 1);
         tc_fence_after();
         const uint32_t gu = base + L.stage[s], hh = gu + TILE, guk = gu + 2 * TILE;
+        if (WT) {
 #pragma unroll
-        for (int k = 0; k < C / 8; ++k)
-          mma_ss(tmem_t[d], umma_desc_mn(gu + k * 1024, BOX), umma_desc(base + L.wt + (k >> 2) * BOX + (k & 3) * 32, 1024), id_t,
-                 k ? 1u : 0u);
+          for (int k = 0; k < C / 8; ++k)
+            mma_ss(tmem_t[d], umma_desc_mn(gu + k * 1024, BOX), umma_desc(base + L.wt + (k >> 2) * BOX + (k & 3) * 32, 1024), id_t,
+                   k ? 1u : 0u);
+        }
         mma_commit(bar(BB_TFULL + d));
+        if (LIFT_G) {      // G[64 x 8] += GU (K-major A) . X (K-major B, rows >= n_in are zero)
+          constexpr uint32_t id_g = idesc_tf32(C, 8, 0, 0);
+          const uint32_t xx = base + L.aux[s];
 #pragma unroll
-        for (int k = 0; k < TS / 8; ++k)
-          mma_ss(tmem_dw, umma_desc(guk + (k >> 2) * BOX + (k & 3) * 32, 1024), umma_desc(hh + (k >> 2) * BOX + (k & 3) * 32, 1024),
-                 id_w, (it | k) ? 1u : 0u);
+          for (int k = 0; k < TS / 8; ++k)
+            mma_ss(tmem_dw, umma_desc(guk + (k >> 2) * BOX + (k & 3) * 32, 1024), umma_desc(xx + (k >> 2) * 1024 + (k & 3) * 32, 1024),
+                   id_g, (it | k) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < TS / 8; ++k)
+            mma_ss(tmem_dw, umma_desc(guk + (k >> 2) * BOX + (k & 3) * 32, 1024), umma_desc(hh + (k >> 2) * BOX + (k & 3) * 32, 1024),
+                   id_w, (it | k) ? 1u : 0u);
+        }
         mma_commit(bar(BB_EMPTY + s));
       }
       mma_commit(bar(BB_DWDONE));
@@ -581,7 +667,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         const float gv = *reinterpret_cast<const float*>(tg + off);
         const float uv = *reinterpret_cast<const float*>(tgk + offk);
         r[j] = gv * gelu_grad_f(uv);
-        *reinterpret_cast<float*>(tg + off) = r[j];
+        if (WT) *reinterpret_cast<float*>(tg + off) = r[j];
         *reinterpret_cast<float*>(tgk + offk) = to_tf32(r[j]);
         *gp = r[j];
         gp += S;
@@ -645,14 +731,25 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       mbar_wait(bar(BB_DWDONE), 0);
       tc_fence_after();
       if (part == 0) {                 // M = 64 accumulator: rows 16q..16q+15 live in lanes 0..15 of quarter q
-        float w0[32], w1[32];
-        tmem_ld32(tmem_dw + lane_base, w0);
-        tmem_ld32(tmem_dw + lane_base + 32, w1);
-        tmem_ld_wait();
-        if (lane < 16) {
-          float* row = pout + (size_t)(16 * q + lane) * C;
+        if (LIFT_G) {                  // G: 8 columns
+          float w0[8];
+          tmem_ld8(tmem_dw + lane_base, w0);
+          tmem_ld_wait();
+          if (lane < 16) {
+            float* row = pout + (size_t)(16 * q + lane) * C;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) { row[c] = w0[c]; row[32 + c] = w1[c]; }
+            for (int c = 0; c < 8; ++c) row[c] = w0[c];
+          }
+        } else {
+          float w0[32], w1[32];
+          tmem_ld32(tmem_dw + lane_base, w0);
+          tmem_ld32(tmem_dw + lane_base + 32, w1);
+          tmem_ld_wait();
+          if (lane < 16) {
+            float* row = pout + (size_t)(16 * q + lane) * C;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { row[c] = w0[c]; row[32 + c] = w1[c]; }
+          }
         }
       }
     } else if (part == 0 && lane < 16) {
@@ -673,6 +770,32 @@ __global__ void block_tail_reduce_kernel(const float* __restrict__ partial, floa
   for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * (C * C + C) + idx];
   if (idx < C * C) dW[idx] = (float)(s * 1.00048828125);   // h is truncated to TF32 by the tensor core in the dWc GEMM
   else if (db) db[idx - C * C] = (float)s;
+}
+
+// LIFT_G: G[c][n] = sum of the per-CTA partials (first 8 columns of each 64-wide row), dbc likewise, then
+// dWc[c][k] = sum_n G[c][n] W_in[k][n] + dbc[c] b_in[k]   (one block of 1024 threads)
+__global__ void block_tail_lift_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ Win,
+                                              const float* __restrict__ bin, int n_in, float* __restrict__ dW, float* __restrict__ db,
+                                              float* __restrict__ G, int nparts) {
+  __shared__ float sG[C * 8];
+  __shared__ float sdb[C];
+  const int tid = threadIdx.x;
+  if (tid < C * 8 + C) {
+    const int idx = tid < C * 8 ? (tid >> 3) * C + (tid & 7) : C * C + (tid - C * 8);
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * (C * C + C) + idx];
+    if (tid < C * 8) sG[tid] = (float)(s * 1.00048828125);       // x is truncated to TF32 by the tensor core in the G GEMM
+    else sdb[tid - C * 8] = (float)s;
+  }
+  __syncthreads();
+  if (tid < C) { if (db) db[tid] = sdb[tid]; }
+  if (G && tid < C * n_in) G[tid] = sG[(tid / n_in) * 8 + tid % n_in];
+  for (int i = tid; i < C * C; i += blockDim.x) {
+    const int c = i >> 6, k = i & 63;
+    float acc = bin ? sdb[c] * __ldg(bin + k) : 0.f;
+    for (int n = 0; n < n_in; ++n) acc = fmaf(sG[c * 8 + n], __ldg(Win + k * n_in + n), acc);
+    dW[i] = acc;
+  }
 }
 
 }  // namespace blk
@@ -779,7 +902,7 @@ int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const f
 
 static int block_tail_bwd_launch(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t, float* dWc,
                                  float* dbc, int B, int Cc, long long S, void* workspace, size_t workspace_bytes,
-                                 const float* Wp, int n_out, const LiftArgs& lf, cudaStream_t st) {
+                                 const float* Wp, int n_out, const LiftArgs& lf, cudaStream_t st, float* G = nullptr) {
   int rc = check_shape(B, Cc, S, "block_tail_bwd");
   if (rc) return rc;
   const size_t need = pdephi_block_tail_bwd_workspace_bytes(Cc);
@@ -815,7 +938,10 @@ static int block_tail_bwd_launch(const float* g, const float* u, const float* h,
   PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
   {
     ProfScope ps(K_BLOCK_TAIL_BWD, st);
-    blk::block_tail_reduce_kernel<<<(blk::C * blk::C + blk::C + 127) / 128, 128, 0, st>>>((const float*)workspace, dWc, dbc, grid);
+    if (lf.Win && !t)      // LIFT_G: the partials hold G = sum gu (x) x; dWc = G W_in^T + dbc (x) b_in
+      blk::block_tail_lift_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, lf.Win, lf.bin, lf.n, dWc, dbc, G, grid);
+    else
+      blk::block_tail_reduce_kernel<<<(blk::C * blk::C + blk::C + 127) / 128, 128, 0, st>>>((const float*)workspace, dWc, dbc, grid);
   }
   PDEPHI_LAUNCH_CHECK("block_tail_reduce_kernel");
   return PDEPHI_OK;
@@ -865,11 +991,11 @@ extern "C" int pdephi_block_tail_bwd(const float* g, const float* u, const float
 }
 
 extern "C" int pdephi_block_tail_lift_bwd(const float* g, const float* u, const float* x, const float* Win, const float* bin,
-                                          int n_in, const float* Wc, float* gu, float* t, float* dWc, float* dbc, int B, int Cc,
-                                          long long S, void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
-  PDEPHI_REQUIRE(g && u && x && Win && Wc && gu && dWc, "block_tail_lift_bwd: null pointer");     /* t may be NULL */
+                                          int n_in, const float* Wc, float* gu, float* t, float* dWc, float* dbc, float* G, int B,
+                                          int Cc, long long S, void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(g && u && x && Win && Wc && gu && dWc, "block_tail_lift_bwd: null pointer");     /* t, G may be NULL */
   return block_tail_bwd_launch(g, u, x, Wc, gu, t, dWc, dbc, B, Cc, S, workspace, workspace_bytes, nullptr, 0,
-                               LiftArgs{Win, bin, n_in}, (cudaStream_t)stream);
+                               LiftArgs{Win, bin, n_in}, (cudaStream_t)stream, G);
 }
 
 extern "C" int pdephi_block_tail_proj_bwd(const float* gout, const float* Wp, int n_out, const float* u, const float* h,

@@ -14,6 +14,7 @@ from ctypes import c_void_p
 from typing import Optional, Sequence, Tuple
 
 import torch
+import torch.nn.functional as F
 from torch.autograd.function import once_differentiable
 
 from . import _cabi
@@ -320,7 +321,9 @@ def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None, lift=None
 def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None, write_t: bool = True, lift=None):
     """gu = g gelu'(u), t = gu + Wc^T gu, dWc = sum gu (x) h, dbc = sum gu.
     head_w = Wp [n,64]: `g` is the gradient of the fused output projection's result, [B,n,...]; the block's incoming
-    gradient Wp^T g is generated inside the kernel."""
+    gradient Wp^T g is generated inside the kernel.
+    lift = (Win, bin): `h` is the model input x.  With write_t False the fifth result is G = sum gu (x) x [64, n_in] (and dbc is
+    always formed): what the lift's own parameter gradients need (_lift_backward)."""
     B, C = u.shape[:2]
     S = u[0, 0].numel()
     lib = _cabi.load()
@@ -328,13 +331,17 @@ def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None, write_t: bool = Tr
         gu = torch.empty_like(u)
         t = torch.empty_like(u) if write_t else None
         dW = torch.empty((C, C), dtype=torch.float32, device=h.device)
-        db = torch.empty(C, dtype=torch.float32, device=h.device) if want_bias else None
+        db = torch.empty(C, dtype=torch.float32, device=h.device) if (want_bias or (lift is not None and not write_t)) else None
         nbytes = lib.pdephi_block_tail_bwd_workspace_bytes(C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
-        if lift is not None:            # h is the model input x: the block's input is regenerated inside the kernel
+        if lift is not None:            # h is the model input x: the block's input never exists in HBM
             Win, bin_ = lift
+            G = torch.empty((C, Win.shape[1]), dtype=torch.float32, device=h.device) if not write_t else None
             _cabi.check(lib.pdephi_block_tail_lift_bwd(_p(g), _p(u), _p(h), _p(Win), _p(bin_), Win.shape[1], _p(Wc), _p(gu), _p(t),
-                                                       _p(dW), _p(db), B, C, S, _p(ws), nbytes, _stream()), "block_tail_lift_bwd")
+                                                       _p(dW), _p(db), _p(G), B, C, S, _p(ws), nbytes, _stream()),
+                        "block_tail_lift_bwd")
+            if G is not None:
+                return gu, t, dW, db, G
         elif head_w is None:
             _cabi.check(lib.pdephi_block_tail_bwd(_p(g), _p(u), _p(h), _p(Wc), _p(gu), _p(t), _p(dW), _p(db), B, C, S, _p(ws),
                                                   nbytes, _stream()), "block_tail_bwd")
@@ -738,8 +745,12 @@ class PointwiseLinearFn(torch.autograd.Function):
         lib = _cabi.load()
         with _cabi.on_device(x.device):
             out = torch.empty((B, Cout, *x.shape[2:]), dtype=torch.float32, device=x.device)
-            _cabi.check(lib.pdephi_pointwise_linear(_p(x), _p(weight), _p(bias), _p(out), B, Cin, Cout, S, 0, _stream()),
-                        "pointwise_linear")
+            if _narrow(Cin, Cout, S):
+                _cabi.check(lib.pdephi_pointwise_linear(_p(x), _p(weight), _p(bias), _p(out), B, Cin, Cout, S, 0, _stream()),
+                            "pointwise_linear")
+            else:       # both sides wide (<= 64 channels): pointwise_wide.cu
+                _cabi.check(lib.pdephi_wide_linear(_p(x), _p(weight), _p(bias), None, None, _p(out), B, Cin, Cout, S, 0, _stream()),
+                            "wide_linear")
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         return out
@@ -760,24 +771,102 @@ def _pointwise_linear_backward(x, weight, g, need_dx: bool, need_dw: bool, has_b
     S = x[0, 0].numel()
     lib = _cabi.load()
     dx = dW = db = None
+    narrow = _narrow(Cin, Cout, S)
     with _cabi.on_device(x.device):
         if need_dx:
             dx = torch.empty_like(x)
-            _cabi.check(lib.pdephi_pointwise_linear(_p(g), _p(weight), _p(None), _p(dx), B, Cout, Cin, S, 1, _stream()),
-                        "pointwise_linear(dx)")
+            if narrow:
+                _cabi.check(lib.pdephi_pointwise_linear(_p(g), _p(weight), _p(None), _p(dx), B, Cout, Cin, S, 1, _stream()),
+                            "pointwise_linear(dx)")
+            else:
+                _cabi.check(lib.pdephi_wide_linear(_p(g), _p(weight), None, None, None, _p(dx), B, Cout, Cin, S, 1, _stream()),
+                            "wide_linear(dx)")
         if need_dw:
             dW = torch.empty_like(weight)
             db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
-            nbytes = lib.pdephi_pointwise_wgrad_workspace_bytes(Cin, Cout, S)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-            _cabi.check(lib.pdephi_pointwise_wgrad(_p(x), _p(g), _p(dW), _p(db), B, Cin, Cout, S, _p(ws), nbytes,
-                                                   _stream()), "pointwise_wgrad")
+            if narrow:
+                nbytes = lib.pdephi_pointwise_wgrad_workspace_bytes(Cin, Cout, S)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                _cabi.check(lib.pdephi_pointwise_wgrad(_p(x), _p(g), _p(dW), _p(db), B, Cin, Cout, S, _p(ws), nbytes,
+                                                       _stream()), "pointwise_wgrad")
+            else:
+                nbytes = lib.pdephi_wide_wgrad_workspace_bytes(B, S)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                _cabi.check(lib.pdephi_wide_wgrad(_p(x), _p(g), _p(dW), _p(db), B, Cin, Cout, S, _p(ws), nbytes, _stream()),
+                            "wide_wgrad")
     return dx, dW, db
 
 
+def _narrow(Cin: int, Cout: int, S: int) -> bool:
+    """pointwise.cu (one side <= 8 channels, the other streamed) vs pointwise_wide.cu (both sides <= 64)."""
+    return min(Cin, Cout) <= 8 and S % 4 == 0
+
+
 def pointwise_linear_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
-    return (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x[0, 0].numel() % 4 == 0
-            and min(weight.shape[0], weight.shape[1]) <= 8)
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x.shape[0] <= 65535):
+        return False
+    Cout, Cin = weight.shape
+    return _narrow(Cin, Cout, x[0, 0].numel()) or max(Cin, Cout) <= 64
+
+
+# ---- the block tail at any width <= 64 / the usual activations, fp32 (pointwise_wide.cu) -----------------------------------
+_ACT_CODES = {F.gelu: "gelu", F.relu: "relu", torch.relu: "relu", torch.tanh: "tanh", F.tanh: "tanh", F.silu: "silu",
+              torch.sigmoid: "sigmoid", F.sigmoid: "sigmoid", F.leaky_relu: "leaky_relu", F.elu: "elu"}
+
+
+def wide_activation_code(fn) -> Optional[int]:
+    """pdephi_activation code of a torch activation function called with its default arguments, or None."""
+    name = _ACT_CODES.get(fn)
+    return None if name is None else _cabi.ACTIVATIONS[name]
+
+
+def wide_block_tail_supported(h: torch.Tensor, conv) -> bool:
+    return (h.is_cuda and h.dtype == torch.float32 and h.dim() == 5 and isinstance(conv, torch.nn.Conv3d)
+            and conv.kernel_size == (1, 1, 1) and conv.groups == 1 and conv.in_channels == conv.out_channels == h.shape[1] <= 64
+            and h.shape[0] <= 65535)
+
+
+class WideBlockTailFn(torch.autograd.Function):
+    """act(spec + Conv1x1(h) + h) (rational_fourier.py:268-271, fno3d.py:93-97) for the widths / activations / spatial sizes
+    the tcgen05 block kernels do not take: one fp32 kernel forward, two backward (gu, t = gu + Wc^T gu; dWc, dbc), instead of
+    cuDNN's convolution, the eager activation and their autograd."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, spec, h, Wc, bc, act: int):
+        spec, h, Wc = spec.contiguous(), h.contiguous(), Wc.contiguous()
+        B, C = h.shape[:2]
+        S = h[0, 0].numel()
+        lib = _cabi.load()
+        with _cabi.on_device(h.device):
+            u = torch.empty_like(h)
+            hout = torch.empty_like(h)
+            _cabi.check(lib.pdephi_wide_block_tail_fwd(_p(h), _p(spec), _p(Wc), _p(bc), _p(u), _p(hout), B, C, S, act, _stream()),
+                        "wide_block_tail_fwd")
+        ctx.save_for_backward(u, h, Wc)
+        ctx.meta = (act, bc is not None)
+        return hout
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
+    def backward(ctx, g):
+        u, h, Wc = ctx.saved_tensors
+        act, has_bias = ctx.meta
+        g = g.contiguous()
+        B, C = h.shape[:2]
+        S = h[0, 0].numel()
+        lib = _cabi.load()
+        with _cabi.on_device(h.device):
+            gu = torch.empty_like(u)
+            t = torch.empty_like(u)
+            dW = torch.empty((C, C), dtype=torch.float32, device=h.device)
+            db = torch.empty(C, dtype=torch.float32, device=h.device) if has_bias else None
+            nbytes = lib.pdephi_wide_wgrad_workspace_bytes(B, S)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+            _cabi.check(lib.pdephi_wide_block_tail_bwd(_p(g), _p(u), _p(h), _p(Wc), _p(gu), _p(t), _p(dW), _p(db), B, C, S, act,
+                                                       _p(ws), nbytes, _stream()), "wide_block_tail_bwd")
+        return gu, t, dW.view_as(Wc), db, None
 
 
 # ---- the input lift (nn.Linear in_channels -> width) taken into the FIRST block ------------------------------------------
@@ -799,19 +888,11 @@ def _lift_forward(x, Win, bin_, modes_h, precision):
     return x, Win, Ax, X       # h0 = Win x + bin itself is generated tile by tile inside the block-tail kernels
 
 
-def _lift_backward(x, Ax, gu, dX, Wc, has_bias):
-    """(dW_in, db_in) from the first block's gu and dX (see above); Wc [64,64] is the block's 1x1x1 conv weight."""
-    B, Cin = x.shape[:2]
-    Cout = gu.shape[1]
+def _lift_backward(x, Ax, G, gsum, dX, Wc, has_bias):
+    """(dW_in, db_in) from the first block's G = sum gu (x) x, gsum = sum gu (both from the block-tail backward) and dX (see
+    above); Wc [64,64] is the block's 1x1x1 conv weight.  A few 64 x 64 products: glue, not a pass over a volume."""
+    Cout = G.shape[0]
     S = x[0, 0].numel()
-    lib = _cabi.load()
-    with _cabi.on_device(x.device):
-        G = torch.empty((Cout, Cin), dtype=torch.float32, device=x.device)
-        gsum = torch.empty(Cout, dtype=torch.float32, device=x.device)
-        nbytes = lib.pdephi_pointwise_wgrad_workspace_bytes(Cin, Cout, S)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        _cabi.check(lib.pdephi_pointwise_wgrad(_p(x), _p(gu), _p(G), _p(gsum), B, Cin, Cout, S, _p(ws), nbytes, _stream()),
-                    "pointwise_wgrad(lift)")
     A = Wc.reshape(Cout, Cout).t() + torch.eye(Cout, dtype=torch.float32, device=x.device)      # I + Wc^T
     dWin = A @ G + torch.einsum("bjxyz,bcxyz->cj", Ax.conj(), dX).real
     dbin = (A @ gsum + float(S) * dX[:, :, 0, 0, 0].real.sum(0)) if has_bias else None
@@ -907,7 +988,10 @@ class RationalBlockFn(torch.autograd.Function):
             Ax, Win = ctx.saved_tensors[nsaved:nsaved + 2]
             lift = (Win, ctx.saved_tensors[nsaved + 2] if lift_bias else None)
             x_in = h
-        gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
+        gu, t, dWc, dbc, *rest = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
+        if skip_dh:
+            G_lift, gsum = rest[0], dbc
+            dbc = dbc if has_bias else None
         prec_syn = _tf32_route(precision, "adjoint_synthesis", gu.device, grid, modes_h, sl)
         dZ = sl.analysis(gu, modes_h, _cabi.ADJOINT, _tf32_route(precision, "backward_analysis", gu.device, grid, modes_h, sl))
         dY = sl.projection_bwd(dZ, Y, mask, stats)
@@ -916,7 +1000,7 @@ class RationalBlockFn(torch.autograd.Function):
         dh = None
         if lifted:
             if skip_dh:
-                dWin, dbin = _lift_backward(x_in, Ax, gu, dX, Wc, lift_bias)
+                dWin, dbin = _lift_backward(x_in, Ax, G_lift, gsum, dX, Wc, lift_bias)
             else:         # the input wants its gradient: materialise gh0 and run the lift's own backward on it
                 gh0 = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, prec_syn)
                 dh, dWin, dbin = _pointwise_linear_backward(x_in, Win, gh0, True, True, lift_bias)
@@ -981,7 +1065,10 @@ class ComplexBlockFn(torch.autograd.Function):
             Ax, Win = ctx.saved_tensors[nsaved:nsaved + 2]
             lift = (Win, ctx.saved_tensors[nsaved + 2] if lift_bias else None)
             x_in = h
-        gu, t, dWc, dbc = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
+        gu, t, dWc, dbc, *rest = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
+        if skip_dh:
+            G_lift, gsum = rest[0], dbc
+            dbc = dbc if has_bias else None
         prec_syn = _tf32_route(precision, "adjoint_synthesis", gu.device, grid, modes_h, sl)
         dY = sl.analysis(gu, modes_h, _cabi.ADJOINT, _tf32_route(precision, "backward_analysis", gu.device, grid, modes_h, sl))
         dX, dW = complex_mix_bwd(X, Wl, dY, modes_h[2])
@@ -990,7 +1077,7 @@ class ComplexBlockFn(torch.autograd.Function):
         dh = None
         if lifted:
             if skip_dh:
-                dWin, dbin = _lift_backward(x_in, Ax, gu, dX, Wc, lift_bias)
+                dWin, dbin = _lift_backward(x_in, Ax, G_lift, gsum, dX, Wc, lift_bias)
             else:
                 gh0 = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, prec_syn)
                 dh, dWin, dbin = _pointwise_linear_backward(x_in, Win, gh0, True, True, lift_bias)

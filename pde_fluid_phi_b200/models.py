@@ -5,11 +5,13 @@
 
 Constructor signatures, sub-module / parameter names and the order in which the global RNG is
 consumed match the reference, so ``torch.manual_seed(s); Model(...)`` gives the same weights and
-checkpoints load either way.  At width 64 (and 32) with the GELU activation a whole block -- spectral
-layer, 1x1x1 convolution, both residual adds, exact GELU -- runs in libpdephi_b200.so, with the input
-lift folded into the first block and the output projection into the last (SURVEY.md section 8f rows N1,
-N2); other widths / activations keep torch's Conv3d and activation around the library's spectral
-layer, whose synthesis epilogue still carries both skip adds.
+checkpoints load either way.  The whole block -- spectral layer, 1x1x1 convolution, both residual adds,
+activation -- runs in libpdephi_b200.so: at width 64 with GELU on the tcgen05 kernels of block_tc.cu, with
+the input lift folded into the first block and the output projection into the last (SURVEY.md section 8f
+rows N1, N2); at any other width <= 64, spatial size or usual activation on the fp32 kernels of
+pointwise_wide.cu, which also carry the wide -> wide lift / projection of operators built with
+in_channels = out_channels = width.  Only a width above 64 or an exotic activation keeps torch's Conv3d and
+activation around the library's spectral layer, whose synthesis epilogue then carries both skip adds.
 """
 from __future__ import annotations
 
@@ -20,7 +22,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _cabi
-from .functional import PointwiseLinearFn, head_supported, library_call, pointwise_linear_supported, spectral_resample
+from .functional import (PointwiseLinearFn, WideBlockTailFn, head_supported, library_call, pointwise_linear_supported,
+                         spectral_resample, wide_activation_code, wide_block_tail_supported)
 from .operators import RationalFourierLayer, SpectralConv3D
 
 
@@ -70,11 +73,21 @@ def _lift(x: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
     if pointwise_linear_supported(x, linear.weight):
         return library_call(PointwiseLinearFn, x, linear.weight, linear.bias)
     if x.is_cuda and x.dtype == torch.float32:
-        # wide -> wide (MultiScaleFNO's inner operators, in = out = width): a plain library GEMM on the channels-first
-        # layout (cuDNN 1x1x1 convolution, fp32 like the reference's Linear) instead of two permuted copies around one
+        # more than 64 channels on both sides: a plain library GEMM on the channels-first layout (cuDNN 1x1x1
+        # convolution, fp32 like the reference's Linear) instead of two permuted copies around one
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             return F.conv3d(x, linear.weight.view(linear.out_features, linear.in_features, 1, 1, 1), linear.bias)
     return linear(x.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
+
+
+def _generic_block(activation, spectral: nn.Module, local: nn.Module, h: torch.Tensor) -> torch.Tensor:
+    """activation(spectral(h) + local(h) + h) where the tcgen05 block kernels do not apply: the block tail as one fp32 library
+    kernel (any width <= 64, the usual activations: pointwise_wide.cu); beyond that torch's own convolution and activation
+    around the spectral layer, with both adds in the synthesis kernel's epilogue."""
+    code = wide_activation_code(activation)
+    if code is not None and getattr(spectral, "slab", None) is None and wide_block_tail_supported(h, local):
+        return library_call(WideBlockTailFn, spectral(h), h, local.weight, local.bias, code)
+    return activation(spectral.forward_fused(h, local(h)))
 
 
 def _reset_pointwise(module: nn.Module):
@@ -142,8 +155,8 @@ class RationalFourierOperator3D(nn.Module):
                     out = spectral.forward_block(h, local, self.output_proj)   # ... and the output projection with it
                 else:
                     h = spectral.forward_block(h, local)      # whole block in the library (TF32 path, width 64)
-            else:   # spectral(h) + local(h) + h in one pass: both adds ride in the synthesis kernel's epilogue
-                h = self.activation(spectral.forward_fused(h, local(h)))
+            else:
+                h = _generic_block(self.activation, spectral, local, h)
         if out is None:
             out = _lift(h, self.output_proj)
         return self.final_activation(out) if self.final_activation is not None else out
@@ -274,7 +287,7 @@ class FNO3D(nn.Module):
                 else:
                     h = spectral.forward_block(h, local)
             else:
-                h = self.activation(spectral.forward_fused(h, local(h)))
+                h = _generic_block(self.activation, spectral, local, h)
         if out is None:
             out = _lift(h, self.output_proj)
         return self.final_activation(out) if self.final_activation is not None else out

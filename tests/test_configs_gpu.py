@@ -157,6 +157,93 @@ def test_cfg4_multiscale_operators_on_128_cubed(modes, order):
     assert math.isfinite(weight * loss)
 
 
+CFG4_SCALES = {"large": ((16, 16, 16), 2, (2, 2), 1.0), "medium": ((32, 32, 32), 3, (3, 3), 2.0),
+               "small": ((64, 64, 64), 4, (4, 4), 4.0)}     # modes, n_layers, rational_order, MultiScaleLoss weight
+
+
+def _cfg4_operator(scale: str, width: int = 64):
+    """One of MultiScaleFNO's default scale operators (multiscale_fno.py:93-127: in_channels = out_channels = width) with
+    conditioned weights (Q(k) kept away from its poles, P(k) scaled so the spectral branch is level
+    with the other two) and visible biases."""
+    modes, n_layers, order, _ = CFG4_SCALES[scale]
+    model = pb.RationalFourierOperator3D(modes=modes, width=width, n_layers=n_layers, in_channels=width, out_channels=width,
+                                         rational_order=order)
+    kmax = float(modes[0] - 1)
+    with torch.no_grad():
+        for layer in model.rational_layers:
+            q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+            layer.Q_coeffs.mul_(1e-6)
+            layer.Q_coeffs[..., 0, 0, 0] = q0
+            layer.P_coeffs.mul_(2.0 / (width * 0.02 * max(1.0, kmax ** (order[0] - 1))))
+        for m in list(model.local_convs) + [model.input_proj, model.output_proj]:
+            m.bias.normal_(0.0, 0.1)
+    return model
+
+
+def _band_limited(channels: int, n: int, kmax: float, seed: int) -> torch.Tensor:
+    """[1, channels, n, n, n] random fields with a k^-5/3 energy spectrum over 1 <= |k| <= kmax, unit variance."""
+    g = torch.Generator().manual_seed(seed)
+    k1 = torch.fft.fftfreq(n, 1.0 / n)
+    kx, ky, kz = torch.meshgrid(k1, k1, torch.fft.rfftfreq(n, 1.0 / n), indexing="ij")
+    kmag = torch.sqrt(kx ** 2 + ky ** 2 + kz ** 2)
+    amp = torch.where((kmag >= 1) & (kmag <= kmax), kmag.clamp(min=1.0) ** (-11.0 / 6.0), torch.zeros_like(kmag))
+    out = torch.empty(1, channels, n, n, n)
+    for c in range(channels):
+        noise = torch.randn(2, n, n, n // 2 + 1, generator=g)
+        u = torch.fft.irfftn(torch.complex(noise[0], noise[1]) * amp, s=(n, n, n))
+        out[0, c] = u / u.std()
+    return out
+
+
+def test_cfg4_three_scale_operators_full_width_weighted_step():
+    """configs[3] assembled: the large / medium / small operators of MultiScaleFNO at their full width 64 on one 128^3 sample,
+    the scale-weighted loss (multiscale_fno.py:47-55: 1 / 2 / 4) summed and back-propagated in one step.  Every operator runs
+    lift (64 -> 64, pointwise_wide.cu) -> tcgen05 block route -> projection in the library; the LARGE operator's output and
+    every parameter gradient are checked against the CPU oracle at the full width (2e-3, the TF32 gate: the blocks'
+    1x1x1 convolution runs in TF32 like torch's own with cudnn.allow_tf32)."""
+    torch.manual_seed(4321)
+    ops = {s: _cfg4_operator(s) for s in CFG4_SCALES}
+    # band-limited random fields (k^-5/3 over 1 <= |k| <= 16, the large scale's own band).  With a WHITE-noise target the
+    # loss gradient is white too, 99.8 % of its energy lies outside a 16^3 mode box, and the single-pass TF32 analysis -- whose
+    # rounding error scales with the energy of the whole field -- leaves 1.3e-2 on the last layer's coefficient gradients
+    # (measured); that is the arithmetic of the tf32 route, not a property of this configuration.
+    x, y = _band_limited(64, 128, 16.0, 7), _band_limited(64, 128, 16.0, 1007)
+    # oracle: the large-scale operator, full width
+    modes, n_layers, _, w_large = CFG4_SCALES["large"]
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in ops["large"].state_dict().items()}
+    out_o = so.rfno3d_forward(x, sd, modes, n_layers)
+    (w_large * F.mse_loss(out_o, y)).backward()
+    # library: all three, one weighted loss
+    xd, yd = x.to(DEV), y.to(DEV)
+    _cabi.profile(True, True)
+    total = 0.0
+    outs = {}
+    for s, op in ops.items():
+        op.to(DEV).set_precision("tf32")
+        outs[s] = op(xd)
+        total = total + CFG4_SCALES[s][3] * F.mse_loss(outs[s], yd)
+    total.backward()
+    torch.cuda.synchronize()
+    rep = _cabi.profile_report(timed=False)
+    _cabi.profile(False, True)
+    assert math.isfinite(float(total))
+    n_blocks = sum(v[1] for v in CFG4_SCALES.values())
+    assert rep.get("block_spectral_fwd_kernel", (0,))[0] + rep.get("block_tail_fwd_kernel", (0,))[0] == n_blocks, rep
+    assert rep.get("block_tail_bwd_kernel", (0,))[0] >= n_blocks, rep
+    assert rep.get("pointwise_linear_kernel", (0,))[0] >= 2 * 3, rep         # wide lift and projection of every operator
+    assert not any(k in rep for k in ("analysis_zy_kernel", "synthesis_zy_kernel")), rep        # no FFMA transform
+    errs = {"out": rel(outs["large"], out_o)}
+    for n, p in ops["large"].named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        errs[n] = rel(p.grad, sd[n].grad)
+    print("\ncfg 4, large-scale operator at width 64 vs CPU oracle (rel L2):", {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < 2e-3}
+    assert not bad, bad
+    for s in ("medium", "small"):
+        for n, p in ops[s].named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), (s, n)
+
+
 @pytest.mark.parametrize("precision,out_tol,grad_tol", [("fp32", 1e-5, 5e-5), ("tf32", 2e-3, 4e-3)])
 def test_cfg5_operator_on_256_cubed(precision, out_tol, grad_tol):
     """configs[4]: RationalFourierOperator3D modes (64,64,64) on a 256^3 grid, batch 1 -- against the oracle at width 4 /

@@ -7,6 +7,7 @@ tensor-core path, for outputs and for gradients wrt x, P_coeffs, Q_coeffs / weig
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 import pde_fluid_phi_b200 as pb
 from pde_fluid_phi_b200 import _cabi
@@ -890,3 +891,88 @@ def test_more_rational_orders_vs_oracle(order):
 def test_unsupported_rational_order_is_rejected_at_construction():
     with pytest.raises(NotImplementedError, match="rational_order"):
         pb.RationalFourierLayer(4, 4, (4, 4, 4), rational_order=(1, 3))
+
+
+# ------------------------------------------------------------------------------------------------
+# pointwise maps with up to 64 channels on both sides and the block tail at any width / activation (pointwise_wide.cu)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,Cin,Cout,spatial", [(2, 64, 64, (8, 8, 16)), (1, 32, 48, (5, 7, 3)), (3, 9, 64, (4, 4, 5)),
+                                               (2, 64, 12, (16, 2, 2)), (1, 20, 20, (3, 3, 3))])
+def test_wide_pointwise_linear_vs_torch(B, Cin, Cout, spatial):
+    """lift / project with both sides wide (MultiScaleFNO's inner operators, multiscale_fno.py:100-127): forward and all three
+    gradients against the reference formulation rearrange -> nn.Linear -> rearrange in float64."""
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(Cin, Cout).to(DEV)
+    x = torch.randn(B, Cin, *spatial, device=DEV, requires_grad=True)
+    g = torch.randn(B, Cout, *spatial, device=DEV)
+    assert pf.pointwise_linear_supported(x, lin.weight)
+    _cabi.profile(True, True)
+    out = pf.library_call(pf.PointwiseLinearFn, x, lin.weight, lin.bias)
+    out.backward(g)
+    rep = _cabi.profile_report(timed=False)
+    _cabi.profile(False, True)
+    assert rep.get("pointwise_linear_kernel", (0,))[0] == 2 and rep.get("pointwise_wgrad_kernel", (0,))[0] >= 1, rep
+    got = (out.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    xd = x.detach().double().requires_grad_(True)
+    lind = torch.nn.Linear(Cin, Cout).to(DEV).double()
+    lind.load_state_dict({k: v.double() for k, v in lin.state_dict().items()})
+    ref = lind(xd.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
+    ref.backward(g.double())
+    for a, b, name in zip(got, (ref, xd.grad, lind.weight.grad, lind.bias.grad), ("out", "dx", "dW", "db")):
+        assert rel(a, b) < 2e-6, (name, rel(a, b))
+
+
+@pytest.mark.parametrize("act", ["gelu", "relu", "tanh", "silu", "sigmoid", "leaky_relu", "elu"])
+@pytest.mark.parametrize("B,C,spatial", [(2, 32, (8, 8, 8)), (1, 64, (4, 6, 5)), (2, 5, (3, 3, 7)), (1, 48, (16, 4, 2))])
+def test_wide_block_tail_vs_torch(act, B, C, spatial):
+    """act(spec + Conv1x1(h) + h) and its backward at widths / spatial sizes / activations the tcgen05 block kernels do not
+    take (fno3d.py:93-97 with activation = getattr(F, name)) against torch in float64."""
+    torch.manual_seed(5)
+    fn = getattr(F, act)
+    code = pf.wide_activation_code(fn)
+    assert code is not None
+    conv = torch.nn.Conv3d(C, C, 1).to(DEV)
+    spec = torch.randn(B, C, *spatial, device=DEV, requires_grad=True)
+    h = torch.randn(B, C, *spatial, device=DEV, requires_grad=True)
+    g = torch.randn(B, C, *spatial, device=DEV)
+    assert pf.wide_block_tail_supported(h, conv)
+    out = pf.library_call(pf.WideBlockTailFn, spec, h, conv.weight, conv.bias, code)
+    out.backward(g)
+    got = (out.detach(), spec.grad.clone(), h.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone())
+    convd = torch.nn.Conv3d(C, C, 1).to(DEV).double()
+    convd.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
+    sd, hd = spec.detach().double().requires_grad_(True), h.detach().double().requires_grad_(True)
+    ref = fn(sd + convd(hd) + hd)
+    ref.backward(g.double())
+    for a, b, name in zip(got, (ref, sd.grad, hd.grad, convd.weight.grad, convd.bias.grad), ("out", "dspec", "dh", "dWc", "dbc")):
+        assert rel(a, b) < 3e-6, (name, rel(a, b))
+
+
+@pytest.mark.parametrize("activation", ["relu", "tanh"])
+def test_fno3d_other_activation_runs_the_block_in_the_library(activation):
+    """FNO3D(activation=...) (fno3d.py:57): the block tail runs in pointwise_wide.cu, not in cuDNN + eager ops; outputs and
+    gradients against the same model evaluated with torch's own convolution / activation around the spectral layer."""
+    torch.manual_seed(11)
+    model = pb.FNO3D(modes=(4, 4, 4), width=32, n_layers=2, activation=activation).to(DEV)
+    x = torch.randn(2, 3, 16, 16, 16, device=DEV)
+    _cabi.profile(True, True)
+    out = model(x)
+    out.square().mean().backward()
+    rep = _cabi.profile_report(timed=False)
+    _cabi.profile(False, True)
+    assert rep.get("block_tail_fwd_kernel", (0,))[0] == 2 and rep.get("block_tail_bwd_kernel", (0,))[0] == 2, rep
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        h = pb.models._lift(x, model.input_proj)
+        for spectral, local in zip(model.spectral_layers, model.local_layers):
+            h = model.activation(spectral.forward_fused(h, local(h)))
+        ref = pb.models._lift(h, model.output_proj)
+        ref.square().mean().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel(out, ref) < 1e-5
+    for n, p in model.named_parameters():
+        assert rel(grads[n], p.grad) < 5e-5, (n, rel(grads[n], p.grad))
