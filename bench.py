@@ -192,7 +192,8 @@ def workload_config(n_gpus: int, precision: str) -> dict:
 NCU_NAME = {"analysis_zy_tc_kernel": "tc::analysis_zy_tc_kernel", "synthesis_zy_tc_kernel": "tc::synthesis_zy_tc_kernel",
             "analysis_x_tc_kernel": "xtc::analysis_x_tc_kernel", "synthesis_x_tc_kernel": "xtc::synthesis_x_tc_kernel",
             "block_tail_fwd_kernel": "blk::block_tail_fwd_kernel<0", "block_spectral_fwd_kernel": "blk::block_tail_fwd_kernel<1",
-            "block_tail_bwd_kernel": "blk::block_tail_bwd_kernel", "rational_mix_kernel": "rational_mix_kernel",
+            "block_tail_bwd_kernel": "blk::block_tail_bwd_kernel", "block_spectral_bwd_kernel": "blk::block_tail_bwd_kernel",
+            "gen_axis_analysis_kernel": "gen::gen_plane_analysis_kernel", "rational_mix_kernel": "rational_mix_kernel",
             "mix_from_R_kernel": "mix_from_R_kernel", "rational_g_kernel": "rational_g_kernel",
             "rational_dpq_kernel": "rational_dpq_kernel", "projection_stats_kernel": "projection_stats_kernel",
             "projection_bwd_kernel": "projection_bwd_kernel", "gen_axis_synthesis_kernel": "gen::gen_axis_synthesis_kernel",
@@ -228,6 +229,14 @@ def ncu_traffic_from_profiles():
                 continue
             name = r[0].replace("pdephi::", "")
             for bench_name, prefix in NCU_NAME.items():
+                if bench_name.startswith("block_") and "bwd" in bench_name:
+                    # block_tail_bwd_kernel<GENG, WT, GENH, ZA>: the ZA instantiations are the fused backward
+                    # (block_spectral_bwd_kernel in the library's profile), the others (or the 3-parameter name of the
+                    # round-1 captures) the plain block-tail backward
+                    args = name[name.find("<") + 1:name.rfind(">")].replace(" ", "").split(",") if "<" in name else []
+                    za = len(args) == 4 and args[3] in ("1", "true")
+                    if za != (bench_name == "block_spectral_bwd_kernel"):
+                        continue
                 if name.startswith(prefix) or name.startswith(prefix.split("::")[-1]):
                     try:
                         b = float(r[ir]) * ur + float(r[iw]) * uw
@@ -715,8 +724,13 @@ def kernel_rooflines(prof, total_ms, B, n, precision, fused_ends, peak, traffic)
     # per-launch algorithmic bytes of those kernels are averages over the L layers' launches of one step.
     a_launch = ((2 * L - 1) + cin / C) / (2 * L) if fused_ends else 1.0          # analysis: 2L launches, one on cin channels
     vbytes = 4.0 * B * C * n * n * ((2 * mzh + 3) // 4 * 4)                      # V [B,Nx,Ny,64,ldz]
+    fused_bwd = "block_spectral_bwd_kernel" in prof      # backward analysis of gu: z stage inside the block-tail kernel
+    if fused_bwd:
+        a_launch = 1.0                                   # analysis_zy_tc: the L - 1 full-size forward analyses only
     alg = {
-        "analysis_zy_tc_kernel": (act + mid) * a_launch, "analysis_zy_kernel": act + mid, "analysis_zy_tc3_kernel": act + mid,
+        "analysis_zy_tc_kernel": (act + mid) * a_launch, "analysis_zy_kernel": act + mid,
+        # tf32 route with fused ends: the split kernel runs the 3-channel lift analysis only
+        "analysis_zy_tc3_kernel": (act + mid) * (cin / C if fused_ends else 1.0),
         # fp32-grade route, unfused block: forward fuses both skip addends, adjoint one; tf32 route: adjoint launches only
         "synthesis_zy_tc3_kernel": act + mid + (act if precision == "tf32" else 1.5 * act),
         "analysis_x_tc3_kernel": mid + modes_b, "synthesis_x_tc3_kernel": mid + modes_b,
@@ -729,6 +743,10 @@ def kernel_rooflines(prof, total_ms, B, n, precision, fused_ends, peak, traffic)
         "block_spectral_fwd_kernel": (3 * act * (L - 1) + 2 * act) / L + vbytes if fused_ends else 3 * act + vbytes,
         # read g', u, h; write gu, t -- first block: no h read, no t write (3 activations); last block: g' generated (4)
         "block_tail_bwd_kernel": (5 * act * (L - 2) + 3 * act + 4 * act) / L if fused_ends else 5 * act,
+        # fused backward: gu is not stored; the z-analysed gu (Vg, the size of V) is.  Middle: read g', u, h, write t (4);
+        # first block: read g', u (2: no h, no t); last block: read u, h, write t (3: g' generated)
+        "block_spectral_bwd_kernel": ((4 * act * (L - 2) + 2 * act + 3 * act) / L if fused_ends else 4 * act) + vbytes,
+        "gen_axis_analysis_kernel": vbytes + mid,    # y stage of the fused backward: Vg in, [BC,Nx,my,mzh] out
         "analysis_x_tc_kernel": mid + modes_b, "synthesis_x_tc_kernel": mid + modes_b,
         # K2.  SURVEY.md section 8d counts 0.145 GB forward / 0.29 GB backward for an evaluation that
         # never materialises R; this design writes R and Q+eps once per forward (2 x tf) and streams them in the backward.
@@ -754,7 +772,7 @@ def kernel_rooflines(prof, total_ms, B, n, precision, fused_ends, peak, traffic)
         if alg.get(k) is None or v[1] <= 0:
             continue
         avg_ms = v[1] / v[0]
-        if k.startswith("block_tail_bwd"):
+        if k.startswith("block_tail_bwd") or k == "block_spectral_bwd_kernel":
             avg_ms = v[1] / (v[0] / 2)           # the tiny partial-sum reduce kernel shares the counter
         if k == "pointwise_wgrad_kernel":
             avg_ms = v[1] / (v[0] / 2)           # ... and so does this one's
@@ -777,7 +795,7 @@ def kernel_rooflines(prof, total_ms, B, n, precision, fused_ends, peak, traffic)
                         "unit": "T fp32 lane-instructions/s", "frac": round(ops / (avg_ms * 1e-3) / alu_peak, 4),
                         "note": "instruction-bound by the bit-exact P(k)/Q(k) evaluation (one separately rounded product and add "
                                 "per monomial, packed FFMA2), not by HBM"}
-        if fused_ends and k in ("block_tail_bwd_kernel", "block_spectral_fwd_kernel"):
+        if fused_ends and k in ("block_tail_bwd_kernel", "block_spectral_fwd_kernel", "block_spectral_bwd_kernel"):
             r["traffic_note"] = ("ncu dram bytes of a middle block's launch; algorithmic_bytes_per_launch is the mean "
                                  "over the step's launches (the first / last block's launches move fewer activations)")
         rooflines[k] = r

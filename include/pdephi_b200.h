@@ -141,6 +141,24 @@ int pdephi_rational_mix_fwd(const float* X, const float* P, const float* Q, cons
                             float proj_eps, float* Y, float* stats, float* R_out, float* Qe_out, int B, int I,
                             int O, long long M, pdephi_stream_t stream);
 
+/* ---- K2 with a materialised transfer function (the cached forward) ---------------------------------------------
+ * R(k) = P(k)/(Q(k)+eps) depends on the coefficients only (rational_fourier.py:92-104,135-146), not on the input: a forward
+ * pass with unchanged coefficients (inference, the four evaluations of an RK4 rollout step, gradient accumulation) can reuse
+ * the copies pdephi_rational_mix_fwd materialised.
+ *  pdephi_rational_transfer      R_out, Qe_out [O,I,M] alone, bit-identical to what pdephi_rational_mix_fwd writes.  With
+ *                                snapP / snapQ (device copies of P / Q the caller keeps next to R, Qe) and `changed` (one device
+ *                                int) it is a REFRESH: a guard kernel compares the coefficients with the snapshots bit for bit
+ *                                (updating them) and the evaluation runs only if something differs -- two few-microsecond
+ *                                launches when nothing has changed.  (A host-side version counter alone misses writes through
+ *                                `param.data`, e.g. the reference's broadcast_parameters, training/distributed.py:230.)
+ *  pdephi_rational_mix_apply     Y = sum_i R X and the projection statistics from a materialised R: same accumulation order
+ *                                as pdephi_rational_mix_fwd, so Y and stats are bit-identical to the fused evaluation. */
+int pdephi_rational_transfer(const float* P, const float* Q, const float* monoP, const float* monoQ, int order_p, int order_q,
+                             float eps, float* R_out, float* Qe_out, int I, int O, long long M, float* snapP, float* snapQ,
+                             int* changed, pdephi_stream_t stream);
+int pdephi_rational_mix_apply(const float* X, const float* R, const float* mask, float proj_eps, float* Y, float* stats, int B,
+                              int I, int O, long long M, pdephi_stream_t stream);
+
 /* Backward of Z = mask*s*Y (stability.py:59-103) :  dZ [B*O, M] complex -> dY [B*O, M] complex */
 int pdephi_projection_bwd(const float* dZ, const float* Y, const float* mask, const float* stats,
                           float* dY, long long rows, long long M, pdephi_stream_t stream);
@@ -240,6 +258,22 @@ int pdephi_block_spectral_lift_fwd(pdephi_plan_t plan, const float* Y, const flo
 int pdephi_block_tail_lift_bwd(const float* g, const float* u, const float* x, const float* Win, const float* bin, int n_in,
                                const float* Wc, float* gu, float* t, float* dWc, float* dbc, float* G, int B, int C, long long S,
                                void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+
+/* ---- fused block BACKWARD (mirror of pdephi_block_spectral_fwd) ----------------------------------------------------------
+ * The backward of `gelu(spectral + conv1x1 + x)` (rational_fourier.py:263-271) needs gu = g gelu'(u) only as the input of the
+ * ADJOINT analysis that follows it.  Here the z stage of that analysis runs inside the block-tail backward kernel (one more
+ * tcgen05 contraction on the staged gu tile, a tile being one z line), gu is never written to or read from HBM, and the y / x
+ * stages run as per-axis contractions on the pruned channel-innermost intermediate.  Results: t = gu + Wc^T gu (may be NULL:
+ * first block of a model whose input needs no gradient), dWc, dbc (may be NULL), and dZ [B,C,mx,my,mzh] complex64 = the
+ * ADJOINT analysis of gu (what pdephi_analysis_r2c(gu, PDEPHI_ADJOINT) would return).  Optional ends of the model as in
+ * pdephi_block_tail_proj_bwd (Wp, n_out: `g` is then the projected output's gradient) and pdephi_block_tail_lift_bwd (Win, bin,
+ * n_in, G: `h` is then the model input).  Same shapes as pdephi_block_spectral_supported.  tail_workspace:
+ * pdephi_block_tail_bwd_workspace_bytes(C); workspace: pdephi_block_spectral_bwd_workspace_bytes. */
+size_t pdephi_block_spectral_bwd_workspace_bytes(pdephi_plan_t plan, int B, int C);
+int pdephi_block_spectral_bwd(pdephi_plan_t plan, const float* g, const float* u, const float* h, const float* Wc, float* t,
+                              float* dWc, float* dbc, float* dZ, int B, int C, const float* Wp, int n_out, const float* Win,
+                              const float* bin, int n_in, float* G, void* tail_workspace, size_t tail_workspace_bytes,
+                              void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
 
 /* ---- pointwise maps with up to 64 channels on BOTH sides, fp32 FFMA, any spatial size (pointwise_wide.cu) --------------
  * wide_linear: out[b,o,s] = bias[o] + sum_i W(o,i) x[b,i,s] (+ add0 + add1, each [B,Cout,S] or NULL);

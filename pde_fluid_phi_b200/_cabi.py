@@ -56,6 +56,10 @@ SIGNATURES = {
     "pdephi_rational_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
                                         c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong,
                                         c_void_p]),
+    "pdephi_rational_transfer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
+                                         c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pdephi_rational_mix_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_longlong, c_void_p]),
     "pdephi_projection_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p]),
     "pdephi_rational_mix_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_longlong]),
     "pdephi_rational_mix_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -91,6 +95,10 @@ SIGNATURES = {
                                                c_void_p]),
     "pdephi_block_tail_lift_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_size_t, c_void_p]),
+    "pdephi_block_spectral_bwd_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "pdephi_block_spectral_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                                          c_void_p, c_size_t, c_void_p]),
     "pdephi_wide_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int,
                                    c_void_p]),
     "pdephi_wide_wgrad_workspace_bytes": (c_size_t, [c_int, c_longlong]),

@@ -480,7 +480,7 @@ __host__ __device__ inline BSmem bwd_smem() {
 // GUREADY / TFULL / TEMPTY are per parity of the tile index (two each): the compute warps run step 1 of tile i+1
 // before the epilogue of tile i, so two tiles are in flight between them and the MMA warp.
 enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2 * B_STAGES + 2, BB_TEMPTY = 2 * B_STAGES + 4,
-       BB_DWDONE = 2 * B_STAGES + 6 };
+       BB_DWDONE = 2 * B_STAGES + 6, BB_ZAFULL = 2 * B_STAGES + 7, BB_ZAEMPTY = 2 * B_STAGES + 9 };
 
 // GENG: the incoming gradient g' = Wp^T gout of the LAST block (the output projection's input gradient) is generated by the
 // loader warps from gout [B, n_out <= 4, S] instead of being read: the 4.3 GB g' is neither written nor read.  (Forming it
@@ -491,12 +491,18 @@ enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2
 //   dWc = G W_in^T + dbc (x) b_in,   G = sum_s gu (x) x  [64 x n_in],
 // so the weight-gradient GEMM runs against the staged x rows (N = 8 instead of 64) and the reduce kernel finishes dWc;
 // G is also what the lift's own weight gradient needs, so the separate pass over gu (pointwise_wgrad, 4.3 GB) goes too.
-template <bool GENG, bool WT, bool GENH>
+// ZA: the z stage of the ADJOINT analysis of gu (the next kernel of the backward pass, 4.3 GB written here and read straight
+// back there) runs inside this kernel: a tile is one z line (Nz = 128), so  Vg[tile][ch][kz'] = sum_z A[kz'][z] gu[ch][z]  is
+// one more GEMM on the staged K-layout gu tile -- D'[128 x 64 ch] = A (TMEM-resident, rows kz' = 2 kz + (re | im), c_kz / N
+// folded in) . gu^T -- and gu itself is never stored.  Vg has the layout of the per-axis route's z-analysed intermediate
+// ([B*64][Nx][Ny][ldz]), so the y and x stages follow unchanged (transforms_gen.cu: pdephi_block_spectral_bwd).
+template <bool GENG, bool WT, bool GENH, bool ZA>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
                       const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
                       float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S, int contiguous,
-                      const float* __restrict__ Wp, int NP, const float* __restrict__ Win, const float* __restrict__ bin, int n_in) {
+                      const float* __restrict__ Wp, int NP, const float* __restrict__ Win, const float* __restrict__ bin, int n_in,
+                      const float* __restrict__ za_img, float* __restrict__ vg_out, int ldz) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -522,17 +528,40 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       mbar_init(bar(BB_GUREADY + i), EPI_WARPS);
       mbar_init(bar(BB_TFULL + i), 1);
       mbar_init(bar(BB_TEMPTY + i), EPI_WARPS);
+      mbar_init(bar(BB_ZAFULL + i), 1);
+      mbar_init(bar(BB_ZAEMPTY + i), EPI_WARPS);
     }
     mbar_init(bar(BB_DWDONE), 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(base + L.tmem_slot, 256);
+  constexpr uint32_t TMEM_COLS = ZA ? 512 : 256;
+  if (warp == 0) tmem_alloc(base + L.tmem_slot, TMEM_COLS);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
   const uint32_t tmem_t[2] = {tmem, tmem + C}, tmem_dw = tmem + 2 * C;
+  const uint32_t tmem_za[2] = {tmem + 3 * C, tmem + 4 * C}, tmem_a = tmem + 6 * C;   // ZA: accumulators, A image [128 x 128]
+  if (ZA) {
+    if (warp >= EPI0 && warp < EPI0 + 4) {       // four consecutive warps cover the four TMEM lane quarters
+      const int q = warp & 3;
+      const float* row = za_img + (size_t)(32 * q + lane) * TS;
+      for (int c0 = 0; c0 < TS; c0 += 32) {
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(row + c0) + j);
+          r[4 * j] = t4.x; r[4 * j + 1] = t4.y; r[4 * j + 2] = t4.z; r[4 * j + 3] = t4.w;
+        }
+        tmem_st32(tmem_a + ((uint32_t)(q * 32) << 16) + c0, r);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   // every CTA walks a CONTIGUOUS range of tiles (PDEPHI_TILE_ORDER=0: round-robin): consecutive tiles extend the same 64
   // channel rows, so the 512-byte pieces a tile writes to each row meet their neighbours in L2 within one tile time
   const long long tq = ntiles / gridDim.x, tr = ntiles % gridDim.x;
@@ -633,6 +662,15 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
             mma_ss(tmem_dw, umma_desc(guk + (k >> 2) * BOX + (k & 3) * 32, 1024), umma_desc(hh + (k >> 2) * BOX + (k & 3) * 32, 1024),
                    id_w, (it | k) ? 1u : 0u);
         }
+        if (ZA) {          // D'[128 (kz') x 64 ch] = A[128 x 128 z] (TMEM) . gu[64 ch x 128 z]^T (K-major B, the dWc GEMM's A tile)
+          constexpr uint32_t id_z = idesc_tf32(TS, C, 0, 0);
+          mbar_wait(bar(BB_ZAEMPTY + d), ph ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < TS / 8; ++k)
+            mma_ts(tmem_za[d], tmem_a + 8 * k, umma_desc(guk + (k >> 2) * BOX + (k & 3) * 32, 1024), id_z, k ? 1u : 0u);
+          mma_commit(bar(BB_ZAFULL + d));
+        }
         mma_commit(bar(BB_EMPTY + s));
       }
       mma_commit(bar(BB_DWDONE));
@@ -669,8 +707,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         r[j] = gv * gelu_grad_f(uv);
         if (WT) *reinterpret_cast<float*>(tg + off) = r[j];
         *reinterpret_cast<float*>(tgk + offk) = to_tf32(r[j]);
-        *gp = r[j];
-        gp += S;
+        if (!ZA) { *gp = r[j]; gp += S; }
         db[j] += r[j];
       }
       fence_proxy_async();
@@ -698,6 +735,24 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         for (int j = 0; j < CPW; ++j) {
           __stcs(tp, v[j] + r[j]);
           tp += S;
+        }
+      }
+      if (ZA) {            // rows kz' = 32 q + lane of D' exist in quarters 0 and 1 only (ldz <= 64)
+        mbar_wait(bar(BB_ZAFULL + d), (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        if (q < 2) {
+          tmem_ld16(tmem_za[d] + lane_base + part * CPW, v);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BB_ZAEMPTY + d));
+        if (q < 2 && 32 * q + lane < ldz) {       // Vg [B*64 volumes][tiles of a volume = (x, y)][ldz]: the W1 layout of the per-axis route
+          const long long b = t / tiles_per_batch, tib = t - b * tiles_per_batch;
+          float* vp = vg_out + (((size_t)b * C + part * CPW) * tiles_per_batch + tib) * ldz + 32 * q + lane;
+          const size_t cs = (size_t)tiles_per_batch * ldz;
+#pragma unroll
+          for (int j = 0; j < CPW; ++j) vp[(size_t)j * cs] = v[j];
         }
       }
     };
@@ -759,7 +814,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 __global__ void block_tail_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db,
@@ -900,9 +955,11 @@ int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const f
   return PDEPHI_OK;
 }
 
-static int block_tail_bwd_launch(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t, float* dWc,
-                                 float* dbc, int B, int Cc, long long S, void* workspace, size_t workspace_bytes,
-                                 const float* Wp, int n_out, const LiftArgs& lf, cudaStream_t st, float* G = nullptr) {
+// za_img / vg / ldz: the ZA variant (z stage of the adjoint analysis of gu fused in; gu is not stored then and may be NULL)
+int block_tail_bwd_launch(const float* g, const float* u, const float* h, const float* Wc, float* gu, float* t, float* dWc,
+                          float* dbc, int B, int Cc, long long S, void* workspace, size_t workspace_bytes,
+                          const float* Wp, int n_out, const LiftArgs& lf, cudaStream_t st, float* G = nullptr,
+                          const float* za_img = nullptr, float* vg = nullptr, int ldz = 0) {
   int rc = check_shape(B, Cc, S, "block_tail_bwd");
   if (rc) return rc;
   const size_t need = pdephi_block_tail_bwd_workspace_bytes(Cc);
@@ -911,6 +968,9 @@ static int block_tail_bwd_launch(const float* g, const float* u, const float* h,
   if (!al16(g) || !al16(h) || !al16(u)) return fail(PDEPHI_ERR_INVALID, "block_tail_bwd: g, h and u must be 16-byte aligned");
   if (Wp && (n_out < 1 || n_out > blk::MAXP))
     return fail(PDEPHI_ERR_UNSUPPORTED, "block_tail_bwd: the fused projection takes 1..%d outputs, got %d", blk::MAXP, n_out);
+  if (vg && (!za_img || ldz < 4 || ldz > 64 || (reinterpret_cast<uintptr_t>(za_img) & 15)))
+    return fail(PDEPHI_ERR_INVALID, "block_tail_bwd: fused z analysis needs an operand image and 4 <= ldz <= 64");
+  if (!vg && !gu) return fail(PDEPHI_ERR_INVALID, "block_tail_bwd: gu is null");
   {
     const ProjArgs pr{Wp, nullptr, nullptr, n_out};
     rc = check_lift(lf, &pr, "block_tail_bwd");
@@ -921,23 +981,26 @@ static int block_tail_bwd_launch(const float* g, const float* u, const float* h,
   int sms = num_sms();
   if (sms > 1024) sms = 1024;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
+  const int kid = vg ? K_BLOCK_SPECTRAL_BWD : K_BLOCK_TAIL_BWD;
   {
-    ProfScope ps(K_BLOCK_TAIL_BWD, st);
-#define PDEPHI_BWD_LAUNCH(GG, WW, HH)                                                                                      \
+    ProfScope ps(kid, st);
+#define PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, ZZ)                                                                                \
     {                                                                                                                      \
-      auto k = blk::block_tail_bwd_kernel<GG, WW, HH>;                                                                     \
+      auto k = blk::block_tail_bwd_kernel<GG, WW, HH, ZZ>;                                                                 \
       PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
       k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out,  \
-                                          lf.Win, lf.bin, lf.n);                                                           \
+                                          lf.Win, lf.bin, lf.n, za_img, vg, ldz);                                          \
     }
+#define PDEPHI_BWD_LAUNCH(GG, WW, HH) { if (vg) PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, true) else PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, false) }
     if (lf.Win) { if (t) PDEPHI_BWD_LAUNCH(false, true, true) else PDEPHI_BWD_LAUNCH(false, false, true) }
     else if (Wp) { if (t) PDEPHI_BWD_LAUNCH(true, true, false) else PDEPHI_BWD_LAUNCH(true, false, false) }
     else { if (t) PDEPHI_BWD_LAUNCH(false, true, false) else PDEPHI_BWD_LAUNCH(false, false, false) }
 #undef PDEPHI_BWD_LAUNCH
+#undef PDEPHI_BWD_LAUNCH_Z
   }
   PDEPHI_LAUNCH_CHECK("block_tail_bwd_kernel");
   {
-    ProfScope ps(K_BLOCK_TAIL_BWD, st);
+    ProfScope ps(kid, st);
     if (lf.Win && !t)      // LIFT_G: the partials hold G = sum gu (x) x; dWc = G W_in^T + dbc (x) b_in
       blk::block_tail_lift_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, lf.Win, lf.bin, lf.n, dWc, dbc, G, grid);
     else
@@ -945,6 +1008,17 @@ static int block_tail_bwd_launch(const float* g, const float* u, const float* h,
   }
   PDEPHI_LAUNCH_CHECK("block_tail_reduce_kernel");
   return PDEPHI_OK;
+}
+
+// Block-tail backward with the z stage of the adjoint analysis of gu fused in (transforms_gen.cu: pdephi_block_spectral_bwd).
+// vg [B*64][S/128][ldz] float, za_img = the plan's plain [128][128] adjoint z-analysis operand for Nz = 128.
+int block_tail_bwd_za_launch(const float* g, const float* u, const float* h, const float* Wc, float* t, float* dWc, float* dbc,
+                             int B, long long S, void* workspace, size_t workspace_bytes, const float* Wp, int n_out,
+                             const float* Win, const float* bin, int n_in, float* G, const float* za_img, float* vg, int ldz,
+                             cudaStream_t st) {
+  if (!vg) return fail(PDEPHI_ERR_INVALID, "block_spectral_bwd: null workspace");
+  return block_tail_bwd_launch(g, u, h, Wc, nullptr, t, dWc, dbc, B, blk::C, S, workspace, workspace_bytes, Wp, n_out,
+                               LiftArgs{Win, bin, n_in}, st, G, za_img, vg, ldz);
 }
 }  // namespace pdephi
 

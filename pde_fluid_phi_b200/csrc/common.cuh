@@ -43,6 +43,7 @@ struct GenPlan {
   int za_ring, zs_ring, xa_st, xs_st, ya_st, ys_st;   // pipeline depths that fit shared memory
   float* za[2];             // z analysis  B images [direction]
   float* zs[2];             // z synthesis B images [direction]
+  float* za_plain;          // adjoint z analysis as a plain [128][128] TMEM-resident A operand (fused block backward; zN = 128 only)
   float* ya; float* ysc; float* yss;   // y axis: analysis A (plain [128][Ny]), synthesis cos / sin images
   float* xa; float* xsc; float* xss;   // x axis
   // split-TF32 (fp32-grade) variant of the route: lo parts of the axis images, stacked [hi | lo] z images per column block
@@ -115,7 +116,8 @@ enum KernelId {
   K_RATIONAL_MIX, K_RATIONAL_MIX_T, K_PROJ_STATS, K_PROJ_BWD, K_RATIONAL_DPQ, K_DPQ_REDUCE,
   K_COMPLEX_MIX, K_COMPLEX_MIX_T, K_COMPLEX_DW, K_POINTWISE_LINEAR, K_POINTWISE_WGRAD, K_BLOCK_TAIL_FWD, K_BLOCK_TAIL_BWD, K_ANALYSIS_X_TC, K_SYNTHESIS_X_TC, K_SCALE_MODES, K_RATIONAL_G,
   K_ANALYSIS_ZY_TC3, K_SYNTHESIS_ZY_TC3, K_ANALYSIS_X_TC3, K_SYNTHESIS_X_TC3,
-  K_GEN_Z_ANALYSIS, K_GEN_Z_SYNTHESIS, K_GEN_AXIS_ANALYSIS, K_GEN_AXIS_SYNTHESIS, K_BLOCK_SPECTRAL_FWD, K_COUNT
+  K_GEN_Z_ANALYSIS, K_GEN_Z_SYNTHESIS, K_GEN_AXIS_ANALYSIS, K_GEN_AXIS_SYNTHESIS, K_BLOCK_SPECTRAL_FWD, K_BLOCK_SPECTRAL_BWD,
+  K_RATIONAL_TRANSFER, K_RATIONAL_MIX_APPLY, K_COUNT
 };
 // run-time options (pdephi_set_option)
 enum { OPT_TF32_XSTAGE_SPLIT = 0, OPT_COUNT };

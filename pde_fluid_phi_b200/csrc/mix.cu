@@ -182,6 +182,95 @@ rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// R and Q+eps alone (no mix): the transfer function depends on the coefficients only, not on the input, so a forward with
+// unchanged coefficients (inference, the 4 evaluations of an RK4 rollout step, gradient accumulation) reuses the materialised
+// copies (functional.py: TransferCache) and runs the streaming mix below instead of re-evaluating 2 x 20 monomials per
+// (o, i, k).  Same evaluation, bit for bit, as rational_mix_kernel.  `changed`: device flag written by params_changed_kernel;
+// 0 = the cached copies are still valid, nothing to do (the guard costs two few-microsecond launches).
+// ---------------------------------------------------------------------------------------------
+template <int OP, int OQ>
+__global__ void __launch_bounds__(MIX_THREADS)
+rational_transfer_kernel(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ monoP,
+                         const float* __restrict__ monoQ, float eps, float* __restrict__ Rout, float* __restrict__ Qeout, int U,
+                         int V, long long M, MonoOffsets offs, float one, float negzero, const int* __restrict__ changed) {
+  if (changed && *changed == 0) return;
+  constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
+  constexpr int TP4 = Tri<OP>::TP4, TQ4 = Tri<OQ>::TP4;
+  extern __shared__ __align__(16) float smem[];
+  float* cPs = smem;                            // [UT/2][V][TP4][2]
+  float* cQs = smem + (size_t)UT * V * TP4;     // [UT/2][V][TQ4][2]
+  const uint64_t one2 = pk2(one, one), nz2 = pk2(negzero, negzero);
+  const int u0 = blockIdx.y * UT;
+  for (int idx = threadIdx.x; idx < UT * V * TP4; idx += MIX_THREADS) {
+    const int t = idx % TP4, uv = idx / TP4, v = uv % V, ul = uv / V;
+    const int u = min(u0 + ul, U - 1);
+    cPs[((((size_t)(ul >> 1) * V + v) * TP4 + t) << 1) + (ul & 1)] =
+        (t < TPN) ? __ldg(P + ((size_t)u * V + v) * (OP * OP * OP) + offs.p[t]) : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < UT * V * TQ4; idx += MIX_THREADS) {
+    const int t = idx % TQ4, uv = idx / TQ4, v = uv % V, ul = uv / V;
+    const int u = min(u0 + ul, U - 1);
+    cQs[((((size_t)(ul >> 1) * V + v) * TQ4 + t) << 1) + (ul & 1)] =
+        (t < TQN) ? __ldg(Q + ((size_t)u * V + v) * (OQ * OQ * OQ) + offs.q[t]) : 0.f;
+  }
+  __syncthreads();
+  const long long k = (long long)blockIdx.x * MIX_THREADS + threadIdx.x;
+  const long long kc = k < M ? k : M - 1;
+  float mp[TP4], mqs[(OP == OQ) ? 1 : TQ4];
+#pragma unroll
+  for (int t = 0; t < TP4; ++t) mp[t] = (t < TPN) ? __ldg(monoP + (size_t)t * M + kc) : 0.f;
+  if (OP != OQ) {
+#pragma unroll
+    for (int t = 0; t < TQ4; ++t) mqs[t] = (t < TQN) ? __ldg(monoQ + (size_t)t * M + kc) : 0.f;
+  }
+  const float* mq = (OP == OQ) ? mp : mqs;
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int up = 0; up < UT / 2; ++up) {
+      uint64_t cp2[TP4], cq2[TQ4];
+      const float4* p4 = reinterpret_cast<const float4*>(cPs + (((size_t)up * V + v) * TP4) * 2);
+      const float4* q4 = reinterpret_cast<const float4*>(cQs + (((size_t)up * V + v) * TQ4) * 2);
+#pragma unroll
+      for (int t = 0; t < TP4 / 2; ++t) {
+        const float4 c = p4[t];
+        cp2[2 * t] = pk2(c.x, c.y); cp2[2 * t + 1] = pk2(c.z, c.w);
+      }
+#pragma unroll
+      for (int t = 0; t < TQ4 / 2; ++t) {
+        const float4 c = q4[t];
+        cq2[2 * t] = pk2(c.x, c.y); cq2[2 * t + 1] = pk2(c.z, c.w);
+      }
+      float R2[2], qe2[2];
+      eval_R2<TPN, TQN>(cp2, cq2, mp, mq, eps, one2, nz2, R2, qe2);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ul = 2 * up + h;
+        if (k < M && u0 + ul < U) {
+          const size_t ri = ((size_t)(u0 + ul) * V + v) * M + k;
+          Rout[ri] = R2[h];
+          Qeout[ri] = qe2[h];
+        }
+      }
+    }
+  }
+}
+
+// flag |= (cur != snap) bitwise, snap = cur: has a coefficient tensor changed since the transfer function was materialised?
+// (A host-side version counter misses `param.data` writes such as the reference's broadcast_parameters,
+// training/distributed.py:230.)
+__global__ void params_changed_kernel(const uint32_t* __restrict__ curP, uint32_t* __restrict__ snapP, long long nP,
+                                      const uint32_t* __restrict__ curQ, uint32_t* __restrict__ snapQ, long long nQ,
+                                      int* __restrict__ changed) {
+  bool diff = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nP + nQ; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t c = i < nP ? __ldg(curP + i) : __ldg(curQ + (i - nP));
+    uint32_t* s = i < nP ? snapP + i : snapQ + (i - nP);
+    if (*s != c) { diff = true; *s = c; }
+  }
+  if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(changed, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
 // StabilityProjection statistics: one CTA per (b,o) row.  stats = {a, b, s, 0}
 // ---------------------------------------------------------------------------------------------
 constexpr int ROW_THREADS = 256;
@@ -261,7 +350,10 @@ projection_bwd_kernel(const float2* __restrict__ dZ, const float2* __restrict__ 
 constexpr int IT = 4;
 // BTV: batch entries per thread (8 for training batches; 1 / 2 / 4 for the small batches of the 256^3 configurations,
 // where a fixed 8 spent 7/8 of the FMAs and registers on zeros)
-template <int BTV>
+// FWD: the forward mix from a materialised (cached) transfer function, Y[b][o][k] = sum_i R[o][i][k] X[b][i][k] -- the same
+// kernel with the roles of the channel indices exchanged (dY = X, dX = Y, "I" = outputs, "O" = contracted inputs); the
+// accumulation order over the contracted index is that of rational_mix_kernel, so Y is bit-identical to the fused evaluation.
+template <int BTV, bool FWD = false>
 __global__ void __launch_bounds__(MIX_THREADS, 4)
 mix_from_R_kernel(const float2* __restrict__ dY, float2* __restrict__ dX, const float* __restrict__ R, int B, int I,
                   int O, long long M) {
@@ -278,7 +370,8 @@ mix_from_R_kernel(const float2* __restrict__ dY, float2* __restrict__ dX, const 
     for (int o = 0; o < O; ++o) {
       float r[IT];
 #pragma unroll
-      for (int a = 0; a < IT; ++a) r[a] = __ldg(R + ((size_t)o * I + min(i0 + a, I - 1)) * M + kc);
+      for (int a = 0; a < IT; ++a)
+        r[a] = __ldg(R + (FWD ? ((size_t)min(i0 + a, I - 1) * O + o) : ((size_t)o * I + min(i0 + a, I - 1))) * M + kc);
       float2 g[BTV];
 #pragma unroll
       for (int j = 0; j < BTV; ++j)
@@ -691,6 +784,76 @@ extern "C" int pdephi_rational_mix_fwd(const float* X, const float* P, const flo
 #undef CASE
   if (rc == -1) return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) is not instantiated (supported: every (p,q) in 2..4, and (1,1), (5,5), (6,6))", order_p, order_q);
   if (rc) return rc;
+  {
+    ProfScope ps(K_PROJ_STATS, st);
+    projection_stats_kernel<<<(unsigned)(B * O), ROW_THREADS, 0, st>>>((const float2*)Y, mask, proj_eps, stats, M);
+  }
+  PDEPHI_LAUNCH_CHECK("projection_stats_kernel");
+  return PDEPHI_OK;
+}
+
+// ---- transfer function alone / mix from a materialised transfer function (the cached forward) ----
+template <int OP, int OQ>
+static int launch_transfer(const float* P, const float* Q, const float* monoP, const float* monoQ, float eps, float* R, float* Qe,
+                           int U, int V, long long M, const MonoOffsets& offs, const int* changed, cudaStream_t st) {
+  const size_t smem = (size_t)UT * V * (Tri<OP>::TP4 + Tri<OQ>::TP4) * sizeof(float);
+  auto k = rational_transfer_kernel<OP, OQ>;
+  if (smem > 200 * 1024) return fail(PDEPHI_ERR_UNSUPPORTED, "rational_transfer: %d input channels exceed shared memory", V);
+  if (smem > 48 * 1024) PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (U + UT - 1) / UT);
+  {
+    ProfScope ps(K_RATIONAL_TRANSFER, st);
+    k<<<grid, MIX_THREADS, smem, st>>>(P, Q, monoP, monoQ, eps, R, Qe, U, V, M, offs, 1.0f, -0.0f, changed);
+  }
+  PDEPHI_LAUNCH_CHECK("rational_transfer_kernel");
+  return PDEPHI_OK;
+}
+
+extern "C" int pdephi_rational_transfer(const float* P, const float* Q, const float* monoP, const float* monoQ, int order_p,
+                                        int order_q, float eps, float* R_out, float* Qe_out, int I, int O, long long M,
+                                        float* snapP, float* snapQ, int* changed, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(P && Q && monoP && monoQ && R_out && Qe_out, "rational_transfer: null pointer");
+  PDEPHI_REQUIRE(I > 0 && O > 0 && M > 0, "rational_transfer: non-positive size");
+  PDEPHI_REQUIRE((snapP == nullptr) == (snapQ == nullptr) && (snapP == nullptr) == (changed == nullptr),
+                 "rational_transfer: snapP, snapQ and changed must all be given or all be NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (changed) {     // refresh: re-evaluate only if a coefficient differs from its snapshot
+    PDEPHI_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
+    const long long nP = (long long)O * I * order_p * order_p * order_p, nQ = (long long)O * I * order_q * order_q * order_q;
+    {
+      ProfScope ps(K_RATIONAL_TRANSFER, st);
+      params_changed_kernel<<<(unsigned)((nP + nQ + 1023) / 1024 < 296 ? (nP + nQ + 1023) / 1024 : 296), 256, 0, st>>>(
+          (const uint32_t*)P, (uint32_t*)snapP, nP, (const uint32_t*)Q, (uint32_t*)snapQ, nQ, changed);
+    }
+    PDEPHI_LAUNCH_CHECK("params_changed_kernel");
+  }
+  MonoOffsets offs;
+  memset(&offs, 0, sizeof(offs));
+  fill_offsets(order_p, offs.p);
+  fill_offsets(order_q, offs.q);
+#define CASE(a, b) \
+  if (order_p == a && order_q == b) return launch_transfer<a, b>(P, Q, monoP, monoQ, eps, R_out, Qe_out, O, I, M, offs, changed, st);
+  ORDER_CASES
+#undef CASE
+  return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) is not instantiated (supported: every (p,q) in 2..4, and (1,1), (5,5), (6,6))", order_p, order_q);
+}
+
+extern "C" int pdephi_rational_mix_apply(const float* X, const float* R, const float* mask, float proj_eps, float* Y, float* stats,
+                                         int B, int I, int O, long long M, pdephi_stream_t stream) {
+  PDEPHI_REQUIRE(X && R && mask && Y && stats, "rational_mix_apply: null pointer");
+  PDEPHI_REQUIRE(B > 0 && I > 0 && O > 0 && M > 0, "rational_mix_apply: non-positive size");
+  PDEPHI_REQUIRE((long long)B * O <= 0x7fffffffLL, "rational_mix_apply: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    // mix_from_R_kernel<.., FWD>: its "I" = output channels, its "O" = contracted input channels
+    dim3 grid((unsigned)((M + MIX_THREADS - 1) / MIX_THREADS), (O + IT - 1) / IT);
+    ProfScope ps(K_RATIONAL_MIX_APPLY, st);
+    if (B >= 5) mix_from_R_kernel<8, true><<<grid, MIX_THREADS, 0, st>>>((const float2*)X, (float2*)Y, R, B, O, I, M);
+    else if (B >= 3) mix_from_R_kernel<4, true><<<grid, MIX_THREADS, 0, st>>>((const float2*)X, (float2*)Y, R, B, O, I, M);
+    else if (B == 2) mix_from_R_kernel<2, true><<<grid, MIX_THREADS, 0, st>>>((const float2*)X, (float2*)Y, R, B, O, I, M);
+    else mix_from_R_kernel<1, true><<<grid, MIX_THREADS, 0, st>>>((const float2*)X, (float2*)Y, R, B, O, I, M);
+  }
+  PDEPHI_LAUNCH_CHECK("mix_from_R_kernel<fwd>");
   {
     ProfScope ps(K_PROJ_STATS, st);
     projection_stats_kernel<<<(unsigned)(B * O), ROW_THREADS, 0, st>>>((const float2*)Y, mask, proj_eps, stats, M);

@@ -28,7 +28,8 @@ static const char* const kKernelNames[K_COUNT] = {
     "pointwise_wgrad_kernel", "block_tail_fwd_kernel", "block_tail_bwd_kernel", "analysis_x_tc_kernel",
     "synthesis_x_tc_kernel", "scale_modes_kernel", "rational_g_kernel", "analysis_zy_tc3_kernel",
     "synthesis_zy_tc3_kernel", "analysis_x_tc3_kernel", "synthesis_x_tc3_kernel", "gen_z_analysis_kernel",
-    "gen_z_synthesis_kernel", "gen_axis_analysis_kernel", "gen_axis_synthesis_kernel", "block_spectral_fwd_kernel"};
+    "gen_z_synthesis_kernel", "gen_axis_analysis_kernel", "gen_axis_synthesis_kernel", "block_spectral_fwd_kernel",
+    "block_spectral_bwd_kernel", "rational_transfer_kernel", "mix_apply_kernel"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 // option defaults: the x stage of the single-pass TF32 route runs split (fp32-grade) -- see pdephi_set_option
 static std::atomic<int> g_options[OPT_COUNT] = {{1}};

@@ -53,6 +53,7 @@ __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
 //   kind 1  z synthesis B  K-major [R = zN rows][K]        col k: mode k>>1, (k&1 ? -w sin : w cos)(2 pi mode r / N)
 //   kind 2  axis analysis A  plain [128][N]                row r: mode r&63, (r>>6 ? sin : cos)(2 pi mode (k+off) / Nt)
 //   kind 3/4 axis synthesis A K-major [R = N rows][K = mk]  (cos / sin)(2 pi k (r+off) / Nt)
+//   kind 5  z analysis as a plain [R][K = zN] A operand (TMEM-resident, fused block backward): rows as kind 0
 // wmode 0: w = 1, 1: w = c_k / total (c_k = 1 for k = 0 and Nyquist, else 2), 2: w = 1 / total
 // ------------------------------------------------------------------------------------------------
 __global__ void gen_image_kernel(float* __restrict__ img, int kind, int R, int K, int Nt, int off, int m, int wmode, int nyq,
@@ -67,7 +68,7 @@ __global__ void gen_image_kernel(float* __restrict__ img, int kind, int R, int K
   const int rimg = r;
   if (nc > 0) { part = r >= nc ? 1 : 0; r = c0 + (r >= nc ? r - nc : r); }
   int mode = -1, pos = 0, sine = 0;
-  if (kind == 0) { mode = r >> 1; sine = r & 1; pos = k; }
+  if (kind == 0 || kind == 5) { mode = r >> 1; sine = r & 1; pos = k; }
   if (kind == 1) { mode = k >> 1; sine = k & 1; pos = r; }
   if (kind == 2) { mode = r & 63; sine = r >> 6; pos = k + off; }
   if (kind == 3 || kind == 4) { mode = k; sine = (kind == 4); pos = r + off; }
@@ -78,12 +79,12 @@ __global__ void gen_image_kernel(float* __restrict__ img, int kind, int R, int K
     double w = 1.0;
     if (wmode == 1) w = ((mode == 0 || mode == nyq) ? 1.0 : 2.0) * inv_total;
     if (wmode == 2) w = inv_total;
-    v = (kind <= 1) ? (sine ? -w * s : w * c) : (sine ? s : c);
+    v = (kind <= 1 || kind == 5) ? (sine ? -w * s : w * c) : (sine ? s : c);
     v *= comp;
   }
   float f = to_tf32((float)v);
   if (part == 1) f = to_tf32((float)(v - (double)f));
-  if (kind == 2) img[(size_t)rimg * K + k] = f;
+  if (kind == 2 || kind == 5) img[(size_t)rimg * K + k] = f;
   else img[swz_off(R, rimg, k) / 4] = f;
 }
 
@@ -833,6 +834,194 @@ gen_axis_analysis_kernel(const __grid_constant__ CUtensorMap tmap_in, float2* __
 }
 
 // ------------------------------------------------------------------------------------------------
+// y analysis of whole [N rows][ld <= 64 floats] blocks (one batch item = one contiguous block): the stage after the z
+// analysis when a row is short (ld = 36 at 17 retained kz).  gen_axis_analysis_kernel stages such a block as two TMA boxes of
+// N rows -- 128-byte and 16-byte pieces -- and the TMA engine pays per ROW request, not per byte (1.4 us for an 18 KB block:
+// 0.62 ms for the y stage of the fused block backward at the cfg-2 shape, 2.7 TB/s).  Here four loader warps stage the block
+// with cp.async in 16-byte chunks, applying the MN-major swizzle (128-byte rows, 32-byte atoms) in software; the contraction
+// and the epilogue are those of gen_axis_analysis_kernel with the whole row as the one column tile.
+//   warp 0 MMA issuer + TMEM owner, warps 1..4 loaders, warps 5..8 epilogue
+// ------------------------------------------------------------------------------------------------
+constexpr int PA_THREADS = 32 * 9;
+constexpr int PA_MAXST = 6;
+constexpr int PA_BOX = 128 * 128;      // one [128 rows][32 floats] box
+struct PASmem { uint32_t stage, e, bars, tmem_slot, total; int nst; };
+__host__ __device__ inline PASmem pa_smem(int nst) {
+  PASmem s; uint32_t o = 0;
+  s.nst = nst;
+  s.stage = o; o += (uint32_t)nst * 2 * PA_BOX;
+  s.e = o; o += 128 * AA_ELD * 4;
+  s.bars = o; o += 256;
+  s.tmem_slot = o; o += 64;
+  s.total = o;
+  return s;
+}
+enum { PB_FULL = 0, PB_EMPTY = PA_MAXST, PB_DFULL = 2 * PA_MAXST, PB_DEMPTY = 2 * PA_MAXST + 2 };
+__device__ __forceinline__ void pa_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(PA_THREADS, 1)
+gen_plane_analysis_kernel(const float* __restrict__ in, float2* __restrict__ out, const float* __restrict__ Aplain, int m, int ld,
+                          int nbn, int Pout, long long nblocks, int nst, float comp) {
+  constexpr int N = 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const PASmem L = pa_smem(nst);
+  auto bar = [&](int i) { return base + L.bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  {   // columns >= ld of a staged block are never written: zero every stage once
+    float4* z = reinterpret_cast<float4*>(sm + L.stage);
+    for (int i = threadIdx.x; i < nst * 2 * PA_BOX / 16; i += PA_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < PA_MAXST; ++i) { mbar_init(bar(PB_FULL + i), 128); mbar_init(bar(PB_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(PB_DFULL + i), 1); mbar_init(bar(PB_DEMPTY + i), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(base + L.tmem_slot, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const uint32_t tmem_a = tmem, tmem_d = tmem + 128;     // A: 128 columns, D: 2 x 64 columns
+  if (warp >= 5) {
+    const int q = warp & 3;
+    const float* row = Aplain + (size_t)(32 * q + lane) * N;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float r[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(row + c0) + j);
+        r[4 * j] = t.x; r[4 * j + 1] = t.y; r[4 * j + 2] = t.z; r[4 * j + 3] = t.w;
+      }
+      tmem_st32(tmem_a + ((uint32_t)(q * 32) << 16) + c0, r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const long long first = blockIdx.x, step = gridDim.x;
+  const long long mine = first < nblocks ? (nblocks - first + step - 1) / step : 0;
+  if (warp >= 1 && warp < 5) {
+    // ===== loaders: block `it` -> stage it % nst, up to nst - 1 blocks in flight; a landed block is published before the
+    //       loader blocks on the stage of the next one =====
+    const int lt = threadIdx.x - 32;                 // 0..127
+    const int cpr = ld >> 2, nchunk = N * cpr;       // 16-byte chunks per row / per block
+    // this thread's chunks qd = lt + 128 i are the same in every block: their swizzled offsets are formed once (the division
+    // by the chunks-per-row inside the copy loop cost more than the copies)
+    constexpr int PA_MAXCH = 16;                     // ld <= 64 -> at most 128 * 16 / 128 chunks per thread
+    uint32_t doff[PA_MAXCH];
+#pragma unroll
+    for (int i = 0; i < PA_MAXCH; ++i) {
+      const int qd = lt + 128 * i;
+      const int r = qd / cpr, c9 = qd - r * cpr, j = c9 >> 3, cc = c9 & 7;
+      doff[i] = (uint32_t)(j * PA_BOX + r * 128 + ((((cc >> 1) ^ (r & 3)) & 3) << 5) + (cc & 1) * 16);
+    }
+    auto issue = [&](long long it) {
+      const int s = (int)(it % nst);
+      mbar_wait(bar(PB_EMPTY + s), (uint32_t)(((it / nst) & 1) ^ 1));
+      const float* src = in + (size_t)(first + it * step) * N * ld + (size_t)lt * 4;
+      const uint32_t dst = base + L.stage + (uint32_t)s * 2 * PA_BOX;
+#pragma unroll
+      for (int i = 0; i < PA_MAXCH; ++i)
+        if (lt + 128 * i < nchunk) pa_cp_async16(dst + doff[i], src + (size_t)i * 512);
+    };
+    // groups are committed one per block (possibly empty) so that wait_group<K> always means "block it has landed"
+    auto wait_landed = [&](int depth) {              // all but the newest depth - 1 groups complete
+      switch (depth) {
+        case 1: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+      }
+    };
+    const int ahead = nst - 1;
+    for (int pre = 0; pre < ahead; ++pre) {
+      if (pre < mine) issue(pre);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (long long it = 0; it < mine; ++it) {
+      wait_landed(ahead);
+      fence_proxy_async();
+      mbar_arrive(bar(PB_FULL + (int)(it % nst)));
+      if (it + ahead < mine) issue(it + ahead);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  } else if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t id = idesc(128, nbn, 0, 1);
+      for (long long it = 0; it < mine; ++it) {
+        const int s = (int)(it % nst), d = (int)(it & 1);
+        mbar_wait(bar(PB_FULL + s), (uint32_t)((it / nst) & 1));
+        mbar_wait(bar(PB_DEMPTY + d), (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t st = base + L.stage + (uint32_t)s * 2 * PA_BOX;
+#pragma unroll
+        for (int k = 0; k < N / 8; ++k) mma_ts(tmem_d + d * 64, tmem_a + 8 * k, desc_mn(st + k * 1024, PA_BOX), id, k ? 1u : 0u);
+        mma_commit(bar(PB_EMPTY + s));
+        mma_commit(bar(PB_DFULL + d));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int et = (warp - 5) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* E = reinterpret_cast<float*>(sm + L.e);
+    const int nout = m * Pout;
+    // this thread's outputs idx = et + 128 i = (ky k, column j) are the same in every block
+    constexpr int PA_MAXOUT = 16;                    // m <= 64, Pout <= 32 -> at most 2048 / 128 outputs per thread
+    int eoff[PA_MAXOUT];
+#pragma unroll
+    for (int i = 0; i < PA_MAXOUT; ++i) {
+      const int idx = et + 128 * i, k = idx / Pout, j = idx - k * Pout;
+      eoff[i] = k * AA_ELD + 2 * j;
+    }
+    for (long long it = 0; it < mine; ++it) {
+      const int d = (int)(it & 1);
+      const long long b = first + it * step;
+      mbar_wait(bar(PB_DFULL + d), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      float v[64];
+      tmem_ld32(tmem_d + d * 64 + lane_base, v);
+      if (nbn > 32) tmem_ld32(tmem_d + d * 64 + lane_base + 32, v + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PB_DEMPTY + d));
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // previous block's readers of E are done
+      {
+        float* er = E + (32 * q + lane) * AA_ELD;
+#pragma unroll
+        for (int c = 0; c < 64; c += 2)
+          if (c < nbn) *reinterpret_cast<float2*>(er + c) = make_float2(v[c], v[c + 1]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float2* ob = out + (size_t)b * nout + et;
+#pragma unroll
+      for (int i = 0; i < PA_MAXOUT; ++i) {
+        if (et + 128 * i < nout) {
+          const float2 c = *reinterpret_cast<const float2*>(E + eoff[i]);
+          const float2 sn = *reinterpret_cast<const float2*>(E + 64 * AA_ELD + eoff[i]);
+          ob[128 * i] = make_float2((c.x + sn.y) * comp, (c.y - sn.x) * comp);   // (C - iS)(re + i im)
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
 // axis synthesis (contracted index = row): out[b][n][j] = sum_k e^{+i theta(k,n)} in[b][k][j]
 //   warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (column half = (warp-2)/4)
 // ------------------------------------------------------------------------------------------------
@@ -1128,7 +1317,8 @@ int gen_plan_init(Plan* p) {
   const size_t n_za = (size_t)g.nbm * g.zN, n_zs = (size_t)g.zN * NKBK * 32;
   const size_t n_ya = two_d ? 0 : (size_t)128 * p->Ny, n_ys = two_d ? 0 : (size_t)pad128(p->Ny) * g.mky;
   const size_t n_xa = (size_t)128 * p->Nx, n_xs = (size_t)pad128(p->Nx) * g.mkx;
-  const size_t total = (2 * n_za + 2 * n_zs + n_ya + 2 * n_ys + n_xa + 2 * n_xs) * sizeof(float);
+  const size_t n_zap = (!two_d && g.zN == 128) ? (size_t)128 * 128 : 0;
+  const size_t total = (2 * n_za + 2 * n_zs + n_ya + 2 * n_ys + n_xa + 2 * n_xs + n_zap) * sizeof(float);
   PDEPHI_CUDA(cudaMalloc(&p->gen_arena, total));
   PDEPHI_CUDA(cudaMemset(p->gen_arena, 0, total));
   float* f = (float*)p->gen_arena;
@@ -1136,6 +1326,7 @@ int gen_plan_init(Plan* p) {
   g.zs[0] = f; f += n_zs; g.zs[1] = f; f += n_zs;
   g.ya = f; f += n_ya; g.ysc = f; f += n_ys; g.yss = f; f += n_ys;
   g.xa = f; f += n_xa; g.xsc = f; f += n_xs; g.xss = f; f += n_xs;
+  g.za_plain = n_zap ? f : nullptr; f += n_zap;
   const double inv_total = 1.0 / ((double)p->Nx_total * p->Ny * p->Nz);
   const int nyq = (!two_d && p->Nz % 2 == 0 && p->mzh - 1 == p->Nz / 2) ? p->Nz / 2 : -1;
   const double comp = 1.0;                    // truncation bias of the data operands: undone in the epilogues (PDEPHI_GEN_COMP)
@@ -1148,6 +1339,7 @@ int gen_plan_init(Plan* p) {
   genimg(g.za[1], 0, g.nbm, g.zN, g.zN, 0, g.zm, wnorm);      // analysis ADJOINT: c_k / total
   genimg(g.zs[0], 1, g.zN, NKBK * 32, g.zN, 0, g.zm, wnorm);  // synthesis FORWARD: c_k / total
   genimg(g.zs[1], 1, g.zN, NKBK * 32, g.zN, 0, g.zm, 0);      // synthesis ADJOINT: plain
+  if (g.za_plain) genimg(g.za_plain, 5, 128, 128, g.zN, 0, g.zm, wnorm);   // analysis ADJOINT, rows >= 2 zm zero
   if (!two_d) {
     genimg(g.ya, 2, 128, p->Ny, p->Ny, 0, p->my, 0);
     genimg(g.ysc, 3, pad128(p->Ny), g.mky, p->Ny, 0, p->my, 0);
@@ -1260,6 +1452,29 @@ static int launch_axis_analysis(const Plan* p, const float* in, long long nb, in
     k<<<grid, gen::AA_THREADS, smem, st>>>(map, out, Aplain, N, m, Pout, ntn, ntiles, nst, comp, accumulate, out_lo);
   }
   PDEPHI_LAUNCH_CHECK("gen_axis_analysis_kernel");
+  return PDEPHI_OK;
+}
+
+// y analysis of contiguous [128][ld] blocks with cp.async staging (gen_plane_analysis_kernel); same result as
+// launch_axis_analysis(p, in, nb, 128, m, ld, Pout, ...)
+static bool plane_analysis_ok(const Plan* p, int N, int ld, int Pout) {
+  return N == 128 && ld % 4 == 0 && ld >= 4 && ld <= 64 && 2 * Pout <= ld && smem_budget(p) >= gen::pa_smem(2).total;
+}
+static int launch_plane_analysis(const Plan* p, const float* in, long long nb, int m, int ld, int Pout, float2* out,
+                                 const float* Aplain, int kid, cudaStream_t st) {
+  if (reinterpret_cast<uintptr_t>(in) & 15) return fail(PDEPHI_ERR_INVALID, "plane analysis: input must be 16-byte aligned");
+  int nst = (int)((smem_budget(p) - gen::pa_smem(0).total) / (2 * (size_t)gen::PA_BOX));
+  if (nst > gen::PA_MAXST) nst = gen::PA_MAXST;
+  const int nbn = (ld + 15) / 16 * 16;
+  const size_t smem = gen::pa_smem(nst).total + 1024;
+  const int grid = (int)(nb < p->num_sms ? nb : p->num_sms);
+  auto k = gen::gen_plane_analysis_kernel;
+  PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope ps(kid, st);
+    k<<<grid, gen::PA_THREADS, smem, st>>>(in, out, Aplain, m, ld, nbn, Pout, nb, nst, PDEPHI_GEN_COMP);
+  }
+  PDEPHI_LAUNCH_CHECK("gen_plane_analysis_kernel");
   return PDEPHI_OK;
 }
 
@@ -1565,6 +1780,64 @@ extern "C" int pdephi_block_spectral_proj_fwd(pdephi_plan_t plan, const float* Y
   PDEPHI_REQUIRE(Wp && out, "block_spectral_proj_fwd: null pointer");
   return block_spectral_run(plan, Y, mode_scale, row_scale, row_scale_stride, h, Wc, bc, u, hout, Wp, bp, n_out, out, nullptr,
                             nullptr, 0, B, C, workspace, workspace_bytes, stream);
+}
+
+// ---- fused block backward: block-tail backward with the z stage of the ADJOINT analysis of gu inside it (it leaves the
+// per-axis route's z-analysed intermediate), then that route's y stage and the split x stage ----
+namespace pdephi {
+bool xstage_analysis_tc_ok(const Plan* p);
+bool xstage_analysis_tc3_ok(const Plan* p);
+int xstage_analysis_cols(const Plan* p, const float2* in, float2* X, long long nb, int Pcols, bool x3, cudaStream_t st);
+int block_tail_bwd_za_launch(const float* g, const float* u, const float* h, const float* Wc, float* t, float* dWc, float* dbc,
+                             int B, long long S, void* workspace, size_t workspace_bytes, const float* Wp, int n_out,
+                             const float* Win, const float* bin, int n_in, float* G, const float* za_img, float* vg, int ldz,
+                             cudaStream_t st);
+}
+
+extern "C" size_t pdephi_block_spectral_bwd_workspace_bytes(pdephi_plan_t plan, int B, int C) {
+  const Plan* p = (const Plan*)plan;
+  if (!p || !block_spectral_ok(p, C) || !p->g.za_plain || B <= 0) return 0;
+  return gen_workspace_bytes(p, (long long)B * C);
+}
+
+extern "C" int pdephi_block_spectral_bwd(pdephi_plan_t plan, const float* g, const float* u, const float* h, const float* Wc,
+                                         float* t, float* dWc, float* dbc, float* dZ, int B, int C, const float* Wp, int n_out,
+                                         const float* Win, const float* bin, int n_in, float* G, void* tail_workspace,
+                                         size_t tail_workspace_bytes, void* workspace, size_t workspace_bytes,
+                                         pdephi_stream_t stream) {
+  const Plan* p = (const Plan*)plan;
+  PDEPHI_REQUIRE(p && g && u && h && Wc && dWc && dZ, "block_spectral_bwd: null pointer");     /* t, dbc, G may be NULL */
+  if (!block_spectral_ok(p, C) || !p->g.za_plain)
+    return fail(PDEPHI_ERR_UNSUPPORTED, "block_spectral_bwd: needs width 64, Nz = 128 and a shape of the per-axis tensor-core route");
+  const long long BC = (long long)B * C;
+  const size_t need = gen_workspace_bytes(p, BC);
+  if (!workspace || workspace_bytes < need)
+    return fail(PDEPHI_ERR_WORKSPACE, "block_spectral_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const GenPlan& gp = p->g;
+  const GenWs w = gen_ws(p, BC);
+  char* wb = (char*)workspace;
+  float* Vg = (float*)(wb + w.w1);       // [BC, Nx, Ny, ldz]   z-analysed gu (the per-axis route's W1)
+  float* W2 = (float*)(wb + w.w2);       // [BC, Nx, my, mzh]   after the y stage
+  float* W2lo = (float*)(wb + w.w2lo);
+  int rc = block_tail_bwd_za_launch(g, u, h, Wc, t, dWc, dbc, B, (long long)p->Nx * p->Ny * p->Nz, tail_workspace,
+                                    tail_workspace_bytes, Wp, n_out, Win, bin, n_in, G, gp.za_plain, Vg, gp.ldz, st);
+  if (rc) return rc;
+  // y stage: batch = (volume, x), rows = y, columns = kz (one contiguous [Ny][ldz] block per batch item).  The x stage is small
+  // and runs split (fp32-grade): its TF32 noise is what the coefficient gradients of the headline model are most sensitive to
+  // (OPT_TF32_XSTAGE_SPLIT of the unfused route) -- the single-kernel split x stage of xstage_tc.cu where it applies (mx <= 32),
+  // else three accumulating launches of the per-axis kernel.
+  const bool x_fused = xstage_analysis_tc3_ok(p);
+  const bool xsplit = !x_fused && gp.x3_ok != 0;
+  if (!xsplit && plane_analysis_ok(p, p->Ny, gp.ldz, p->mzh))
+    rc = launch_plane_analysis(p, Vg, BC * p->Nx, p->my, gp.ldz, p->mzh, (float2*)W2, gp.ya, K_GEN_AXIS_ANALYSIS, st);
+  else
+    rc = launch_axis_analysis(p, Vg, BC * p->Nx, p->Ny, p->my, gp.ldz, p->mzh, (float2*)W2, gp.ya, gp.ya_st, K_GEN_AXIS_ANALYSIS, st,
+                              PDEPHI_GEN_COMP, 0, xsplit ? (float2*)W2lo : nullptr);
+  if (rc) return rc;
+  if (x_fused) return xstage_analysis_cols(p, (const float2*)W2, (float2*)dZ, BC, p->my * p->mzh, true, st);
+  return axis_analysis_stage(p, xsplit, W2, W2lo, BC, p->Nx, p->mx, 2 * p->my * p->mzh, p->my * p->mzh, (float2*)dZ, nullptr, gp.xa,
+                             gp.xa_lo, gp.xa_st, st);
 }
 
 static int block_spectral_run(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,

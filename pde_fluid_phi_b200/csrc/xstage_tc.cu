@@ -554,8 +554,10 @@ bool xstage_synthesis_tc_ok(const Plan* p) { return p->xtc_s_ok != 0; }
 bool xstage_analysis_tc3_ok(const Plan* p) { return p->xtc3_a_ok != 0; }
 bool xstage_synthesis_tc3_ok(const Plan* p) { return p->xtc3_s_ok != 0; }
 
-static int xstage_analysis_launch(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st, bool x3) {
-  const int P = p->my * p->mzh;
+// Pcols > 0: complex columns per batch item instead of my * mzh (the channel-innermost intermediate of the fused block
+// backward: batch item = volume b, columns = (ky, c, kz))
+static int xstage_analysis_launch(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st, bool x3, int Pcols = 0) {
+  const int P = Pcols > 0 ? Pcols : p->my * p->mzh;
   const long long rows = BC * p->Nx;
   if (rows > 0x7fffffffLL) return fail(PDEPHI_ERR_UNSUPPORTED, "x stage: too many rows");
   CUtensorMap map;
@@ -585,6 +587,10 @@ int xstage_analysis_tc(const Plan* p, const float2* ws, float2* X, long long BC,
 }
 int xstage_analysis_tc3(const Plan* p, const float2* ws, float2* X, long long BC, cudaStream_t st) {
   return xstage_analysis_launch(p, ws, X, BC, st, true);
+}
+int xstage_analysis_cols(const Plan* p, const float2* in, float2* X, long long nb, int Pcols, bool x3, cudaStream_t st) {
+  if (Pcols <= 0 || (Pcols & 1)) return fail(PDEPHI_ERR_INVALID, "x stage: column count %d", Pcols);
+  return xstage_analysis_launch(p, in, X, nb, st, x3, Pcols);
 }
 
 // Z -> (optional scaling into `scratch`) -> U (workspace)

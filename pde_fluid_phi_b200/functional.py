@@ -162,9 +162,71 @@ def synthesis(Z: torch.Tensor, grid: Tuple[int, int, int], mode_scale: Optional[
     return out
 
 
-def rational_mix_fwd(X, P, Q, monoP, monoQ, eps: float, mask, proj_eps: float, keep_transfer: bool = False):
+# ------------------------------------------------------------------------------------------------
+# Transfer-function cache.  R(k) = P(k)/(Q(k)+eps) depends on the coefficients only (rational_fourier.py:92-104, 135-146), yet
+# the reference -- and the fused K2 kernel -- re-evaluate its 2 x 20 monomials per (o, i, k) on every forward.  A layer keeps
+# the R / Q+eps tensors its last forward materialised; the next forward with unchanged coefficients (inference, the four
+# evaluations of an RK4 rollout step, gradient accumulation) runs the streaming mix against them instead.
+#   - "unchanged" is decided on the DEVICE: a guard kernel compares P / Q with snapshots bit for bit and the evaluation kernel
+#     returns at once when nothing differs (pdephi_rational_transfer).  The host-side key (tensor identity and autograd version
+#     counters) only decides between that cheap refresh and a fresh evaluation into new tensors -- which is what keeps the R of
+#     an autograd graph still alive intact when the optimizer has stepped in between.
+#   - set_transfer_cache(False) turns it off (every forward evaluates, as before).
+# ------------------------------------------------------------------------------------------------
+_transfer_cache_enabled = True
+
+
+def set_transfer_cache(enabled: bool) -> None:
+    global _transfer_cache_enabled
+    _transfer_cache_enabled = bool(enabled)
+
+
+class TransferCache:
+    """R, Q+eps of one RationalFourierLayer as of its last forward (see above).  Holds 2 x 4 O I M bytes on the device."""
+
+    def __init__(self):
+        self.key = None
+        self.R = self.Qe = self.snapP = self.snapQ = self.flag = None
+        self.hits = self.misses = 0
+
+    def clear(self):
+        self.__init__()
+
+    @staticmethod
+    def _key(P, Q, monoP, eps, shard):
+        return (P.data_ptr(), Q.data_ptr(), P._version, Q._version, tuple(P.shape), tuple(Q.shape), monoP.shape[-1], float(eps),
+                shard, P.device)
+
+    def lookup(self, P, Q, monoP, monoQ, eps, shard):
+        """(R, Qe) valid for the current coefficients, or None.  On a host-key match the device-side guard re-evaluates in
+        place if a coefficient was changed behind autograd's back (`param.data` writes)."""
+        if not _transfer_cache_enabled or self.key is None or self.key != self._key(P, Q, monoP, eps, shard):
+            self.misses += 1
+            return None
+        O, I = P.shape[:2]
+        lib = _cabi.load()
+        with _cabi.on_device(P.device):
+            _cabi.check(lib.pdephi_rational_transfer(_p(P), _p(Q), _p(monoP), _p(monoQ), P.shape[-1], Q.shape[-1], eps, _p(self.R),
+                                                     _p(self.Qe), I, O, monoP.shape[-1], _p(self.snapP), _p(self.snapQ),
+                                                     _p(self.flag), _stream()), "rational_transfer(refresh)")
+        self.hits += 1
+        return self.R, self.Qe
+
+    def store(self, P, Q, monoP, eps, shard, R, Qe):
+        if not _transfer_cache_enabled:
+            return
+        self.key = self._key(P, Q, monoP, eps, shard)
+        self.R, self.Qe = R, Qe
+        self.snapP, self.snapQ = P.detach().clone(), Q.detach().clone()
+        self.flag = torch.zeros(1, dtype=torch.int32, device=P.device)
+
+
+def rational_mix_fwd(X, P, Q, monoP, monoQ, eps: float, mask, proj_eps: float, keep_transfer: bool = False, cache=None,
+                     shard=None):
     """K2.  Returns Y [B,O,mx,my,mzh] complex64 (unprojected), stats [B*O,4] = {a, b, s, 0} and, when
-    ``keep_transfer``, the materialised R and Q+eps [O,I,mx,my,mzh] the backward streams."""
+    ``keep_transfer``, the materialised R and Q+eps [O,I,mx,my,mzh] the backward streams.
+    cache: the layer's TransferCache -- with it R / Q+eps are always materialised (and returned), and a forward with unchanged
+    coefficients runs the streaming mix against the cached copies; shard: which slice of the modes this call works on."""
     B, I = X.shape[:2]
     O = P.shape[0]
     M = X[0, 0].numel()
@@ -172,13 +234,21 @@ def rational_mix_fwd(X, P, Q, monoP, monoQ, eps: float, mask, proj_eps: float, k
     with _cabi.on_device(X.device):
         Y = torch.empty((B, O, *X.shape[2:]), dtype=torch.complex64, device=X.device)
         stats = torch.empty((B * O, 4), dtype=torch.float32, device=X.device)
+        hit = cache.lookup(P, Q, monoP, monoQ, eps, shard) if cache is not None else None
+        if hit is not None:
+            R, Qe = hit
+            _cabi.check(lib.pdephi_rational_mix_apply(_p(X), _p(R), _p(mask), proj_eps, _p(Y), _p(stats), B, I, O, M, _stream()),
+                        "rational_mix_apply")
+            return Y, stats, R, Qe
         R = Qe = None
-        if keep_transfer:
+        if keep_transfer or (cache is not None and _transfer_cache_enabled):
             R = torch.empty((O, I, *X.shape[2:]), dtype=torch.float32, device=X.device)
             Qe = torch.empty_like(R)
         _cabi.check(lib.pdephi_rational_mix_fwd(_p(X), _p(P), _p(Q), _p(monoP), _p(monoQ), P.shape[-1], Q.shape[-1],
                                                 eps, _p(mask), proj_eps, _p(Y), _p(stats), _p(R), _p(Qe), B, I, O, M,
                                                 _stream()), "rational_mix_fwd")
+        if cache is not None and R is not None:
+            cache.store(P, Q, monoP, eps, shard, R, Qe)
     return Y, stats, R, Qe
 
 
@@ -349,6 +419,45 @@ def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None, write_t: bool = Tr
             _cabi.check(lib.pdephi_block_tail_proj_bwd(_p(g), _p(head_w), head_w.shape[0], _p(u), _p(h), _p(Wc), _p(gu), _p(t),
                                                        _p(dW), _p(db), B, C, S, _p(ws), nbytes, _stream()), "block_tail_proj_bwd")
     return gu, t, dW, db
+
+
+# The backward of a block on the fused route: the z stage of the adjoint analysis of gu runs inside the block-tail backward
+# kernel and gu never touches HBM (pdephi_block_spectral_bwd).  False: the block-tail backward writes gu and the fused (z,y)
+# analysis kernel reads it back (the route before this one; kept for A/B measurements and as the reference of the tests).
+FUSED_BLOCK_BACKWARD = True
+
+
+def block_spectral_bwd(g, u, h, Wc, modes_h, want_bias: bool, head_w=None, write_t: bool = True, lift=None):
+    """Block-tail backward + ADJOINT analysis of gu = g gelu'(u) in one chain: returns (t, dWc, dbc, dZ, G) with
+    dZ [B,64,mx,my,mzh] complex64 = analysis(gu, ADJOINT); t / G as in block_tail_bwd.  gu is never materialised."""
+    B, C = u.shape[:2]
+    lib = _cabi.load()
+    with _cabi.on_device(u.device):
+        plan = _cabi.get_plan(u.device.index, tuple(u.shape[2:]), tuple(modes_h))
+        t = torch.empty_like(u) if write_t else None
+        dW = torch.empty((C, C), dtype=torch.float32, device=u.device)
+        need_db = want_bias or (lift is not None and not write_t)
+        db = torch.empty(C, dtype=torch.float32, device=u.device) if need_db else None
+        dZ = torch.empty((B, C, *modes_h), dtype=torch.complex64, device=u.device)
+        Win = bin_ = G = None
+        n_in = 0
+        if lift is not None:
+            Win, bin_ = lift
+            n_in = Win.shape[1]
+            if not write_t:
+                G = torch.empty((C, n_in), dtype=torch.float32, device=u.device)
+        tail_bytes = lib.pdephi_block_tail_bwd_workspace_bytes(C)
+        tail_ws = torch.empty(tail_bytes, dtype=torch.uint8, device=u.device)
+        nbytes = lib.pdephi_block_spectral_bwd_workspace_bytes(plan, B, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=u.device)
+        _cabi.check(lib.pdephi_block_spectral_bwd(plan, _p(g), _p(u), _p(h), _p(Wc), _p(t), _p(dW), _p(db), _p(dZ), B, C,
+                                                  _p(head_w), head_w.shape[0] if head_w is not None else 0, _p(Win), _p(bin_), n_in,
+                                                  _p(G), _p(tail_ws), tail_bytes, _p(ws), nbytes, _stream()), "block_spectral_bwd")
+    return t, dW, db, dZ, G
+
+
+def block_spectral_bwd_supported(u: torch.Tensor, modes_h, precision: int, sl) -> bool:
+    return FUSED_BLOCK_BACKWARD and not sl.active and block_spectral_supported(u, modes_h, precision, u.shape[1])
 
 
 def block_tail_supported(h: torch.Tensor, precision: int) -> bool:
@@ -624,8 +733,9 @@ class RationalSpectralFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, P, Q, mask, monoP, monoQ, modes, eps, precision, skip0, residual, slab=None, proj=None):
+    def forward(ctx, x, P, Q, mask, monoP, monoQ, modes, eps, precision, skip0, residual, slab=None, proj=None, cache=None):
         # proj = (eps, energy_conserving) of the layer's StabilityProjection (stability.py:27-38); None: (eps, True)
+        # cache: the layer's TransferCache (R / Q+eps reused while the coefficients are unchanged)
         for t, n in ((x, "x"), (P, "P_coeffs"), (Q, "Q_coeffs")):
             _require_cuda_f32(t, n)
         mx, my, mz = modes
@@ -639,7 +749,8 @@ class RationalSpectralFn(torch.autograd.Function):
             mask, monoP, monoQ = sl.local_modes(mask, modes_h), sl.local_modes(monoP, modes_h, 1), sl.local_modes(monoQ, modes_h, 1)
         X = sl.analysis(x, modes_h, _cabi.FORWARD, _tf32_route(precision, "forward_analysis", x.device, grid, modes_h, sl))
         need_grad = any(ctx.needs_input_grad[:3])
-        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, proj_eps, keep_transfer=need_grad)
+        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, proj_eps, keep_transfer=need_grad, cache=cache,
+                                           shard=(sl.rank, sl.world) if sl.sharded else None)
         stats = sl.complete_stats(stats, proj_eps) if energy else _unit_stats(stats)
         out = sl.synthesis(Y, grid, mask, stats[:, 2], skip0, x if residual else None, _cabi.FORWARD, precision)
         if need_grad:
@@ -665,7 +776,7 @@ class RationalSpectralFn(torch.autograd.Function):
                 dx = sl.synthesis(dX, grid, None, None, g if residual else None, None, _cabi.ADJOINT,
                                   _tf32_route(precision, "adjoint_synthesis", g.device, grid, modes_h, sl))
         return (dx, dP if need_P else None, dQ if need_Q else None, None, None, None, None, None, None,
-                g if has0 else None, None, None, None)
+                g if has0 else None, None, None, None, None)
 
 
 def _local_weights(W, sl, my):
@@ -927,7 +1038,7 @@ class RationalBlockFn(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, h, P, Q, mask, monoP, monoQ, modes, eps, precision, Wc, bc, slab=None, Wp=None, bp=None, Win=None,
-                bin_=None, proj=None):
+                bin_=None, proj=None, cache=None):
         # Wp / bp: the model's output projection, fused into this (the last) block: the result is then Wp h' + bp
         # Win / bin_: the model's input lift, taken into this (the first) block: `h` is then the model input x
         for t, n in ((h, "x"), (P, "P_coeffs"), (Q, "Q_coeffs"), (Wc, "conv weight")):
@@ -951,7 +1062,8 @@ class RationalBlockFn(torch.autograd.Function):
             X = sl.analysis(h, modes_h, _cabi.FORWARD, _tf32_route(precision, "forward_analysis", h.device, grid, modes_h, sl))
         need_grad = any(ctx.needs_input_grad)
         proj_eps, energy = (float(eps), True) if proj is None else (float(proj[0]), bool(proj[1]))
-        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, proj_eps, keep_transfer=need_grad)
+        Y, stats, R, Qe = rational_mix_fwd(X, P, Q, monoP, monoQ, eps, mask, proj_eps, keep_transfer=need_grad, cache=cache,
+                                           shard=(sl.rank, sl.world) if sl.sharded else None)
         stats = sl.complete_stats(stats, proj_eps) if energy else _unit_stats(stats)
         head = _head_tuple(Wp, bp)
         if not sl.active and block_spectral_supported(h, modes_h, precision, Y.shape[1]):
@@ -988,12 +1100,16 @@ class RationalBlockFn(torch.autograd.Function):
             Ax, Win = ctx.saved_tensors[nsaved:nsaved + 2]
             lift = (Win, ctx.saved_tensors[nsaved + 2] if lift_bias else None)
             x_in = h
-        gu, t, dWc, dbc, *rest = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
+        if block_spectral_bwd_supported(u, modes_h, precision, sl):     # gu never touches HBM
+            t, dWc, dbc, dZ, G_lift = block_spectral_bwd(g, u, h, Wc, modes_h, has_bias, Wp, write_t=not skip_dh, lift=lift)
+        else:
+            gu, t, dWc, dbc, *rest = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
+            G_lift = rest[0] if skip_dh else None
+            dZ = sl.analysis(gu, modes_h, _cabi.ADJOINT, _tf32_route(precision, "backward_analysis", gu.device, grid, modes_h, sl))
         if skip_dh:
-            G_lift, gsum = rest[0], dbc
+            gsum = dbc
             dbc = dbc if has_bias else None
-        prec_syn = _tf32_route(precision, "adjoint_synthesis", gu.device, grid, modes_h, sl)
-        dZ = sl.analysis(gu, modes_h, _cabi.ADJOINT, _tf32_route(precision, "backward_analysis", gu.device, grid, modes_h, sl))
+        prec_syn = _tf32_route(precision, "adjoint_synthesis", u.device, grid, modes_h, sl)
         dY = sl.projection_bwd(dZ, Y, mask, stats)
         dX, dP, dQ = rational_mix_bwd(X, dY, R, Qe, monoP, monoQ, coeff_shapes)
         sl.finish_coeff_grads(dP, dQ)
@@ -1006,7 +1122,7 @@ class RationalBlockFn(torch.autograd.Function):
                 dh, dWin, dbin = _pointwise_linear_backward(x_in, Win, gh0, True, True, lift_bias)
         else:
             dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, prec_syn)
-        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin, None)
+        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin, None, None)
 
 
 class ComplexBlockFn(torch.autograd.Function):
@@ -1065,12 +1181,16 @@ class ComplexBlockFn(torch.autograd.Function):
             Ax, Win = ctx.saved_tensors[nsaved:nsaved + 2]
             lift = (Win, ctx.saved_tensors[nsaved + 2] if lift_bias else None)
             x_in = h
-        gu, t, dWc, dbc, *rest = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
+        if block_spectral_bwd_supported(u, modes_h, precision, sl):     # gu never touches HBM
+            t, dWc, dbc, dY, G_lift = block_spectral_bwd(g, u, h, Wc, modes_h, has_bias, Wp, write_t=not skip_dh, lift=lift)
+        else:
+            gu, t, dWc, dbc, *rest = block_tail_bwd(g, u, h, Wc, has_bias, Wp, write_t=not skip_dh, lift=lift)
+            G_lift = rest[0] if skip_dh else None
+            dY = sl.analysis(gu, modes_h, _cabi.ADJOINT, _tf32_route(precision, "backward_analysis", gu.device, grid, modes_h, sl))
         if skip_dh:
-            G_lift, gsum = rest[0], dbc
+            gsum = dbc
             dbc = dbc if has_bias else None
-        prec_syn = _tf32_route(precision, "adjoint_synthesis", gu.device, grid, modes_h, sl)
-        dY = sl.analysis(gu, modes_h, _cabi.ADJOINT, _tf32_route(precision, "backward_analysis", gu.device, grid, modes_h, sl))
+        prec_syn = _tf32_route(precision, "adjoint_synthesis", u.device, grid, modes_h, sl)
         dX, dW = complex_mix_bwd(X, Wl, dY, modes_h[2])
         sl.finish_coeff_grads(dW)
         dW = _scatter_weight_grad(dW, W, sl, modes_h[1])

@@ -17,8 +17,8 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .functional import (ComplexBlockFn, ComplexSpectralFn, RationalBlockFn, RationalSpectralFn, block_tail_supported, library_call,
-                         monomial_exponents, monomial_table)
+from .functional import (ComplexBlockFn, ComplexSpectralFn, RationalBlockFn, RationalSpectralFn, TransferCache, block_tail_supported,
+                         library_call, monomial_exponents, monomial_table)
 
 _default_precision = "auto"
 
@@ -131,6 +131,9 @@ class RationalFourierLayer(nn.Module):
         self.stability_eps = stability_eps
         self.precision: Optional[str] = None     # None -> module-level default
         self.slab = None                         # (process_group, Nx_total) for the slab-decomposed transform
+        # R(k), Q(k)+eps of the last forward, reused while the coefficients are unchanged (functional.TransferCache); a plain
+        # attribute: not a parameter, not a buffer, not in the state_dict
+        self._transfer_cache = TransferCache()
         self._init_rational_coefficients(init_scale)
         self.stability_projection = StabilityProjection(modes=modes, decay_rate=2.0, eps=stability_eps)
         self.register_buffer("k_grid", get_grid(modes, device="cpu"))
@@ -185,7 +188,7 @@ class RationalFourierLayer(nn.Module):
             raise RuntimeError("RationalFourierLayer needs in_channels == out_channels (as the reference does)")
         return library_call(RationalSpectralFn, x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
                                         self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
-                                        self._precision_code(), skip0, residual, self.slab, self._projection())
+                                        self._precision_code(), skip0, residual, self.slab, self._projection(), self._transfer_cache)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._run(x, None, False)
@@ -219,7 +222,7 @@ class RationalFourierLayer(nn.Module):
                             self._precision_code(), conv.weight, conv.bias, self.slab,
                             head.weight if head is not None else None, head.bias if head is not None else None,
                             lift.weight if lift is not None else None, lift.bias if lift is not None else None,
-                            self._projection())
+                            self._projection(), self._transfer_cache)
 
 
 class SpectralConv3D(nn.Module):

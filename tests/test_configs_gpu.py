@@ -229,7 +229,7 @@ def test_cfg4_three_scale_operators_full_width_weighted_step():
     assert math.isfinite(float(total))
     n_blocks = sum(v[1] for v in CFG4_SCALES.values())
     assert rep.get("block_spectral_fwd_kernel", (0,))[0] + rep.get("block_tail_fwd_kernel", (0,))[0] == n_blocks, rep
-    assert rep.get("block_tail_bwd_kernel", (0,))[0] >= n_blocks, rep
+    assert rep.get("block_tail_bwd_kernel", (0,))[0] + rep.get("block_spectral_bwd_kernel", (0,))[0] >= n_blocks, rep
     assert rep.get("pointwise_linear_kernel", (0,))[0] >= 2 * 3, rep         # wide lift and projection of every operator
     assert not any(k in rep for k in ("analysis_zy_kernel", "synthesis_zy_kernel")), rep        # no FFMA transform
     errs = {"out": rel(outs["large"], out_o)}

@@ -110,10 +110,13 @@ def test_headline_tf32_fused_block_route_vs_oracle_at_the_gate():
     # lift / projection pass, no materialised spectral output, the tensor-core transforms
     assert rep.get("block_spectral_fwd_kernel", (0,))[0] == LAYERS, rep
     assert "pointwise_linear_kernel" not in rep and "block_tail_fwd_kernel" not in rep, rep
-    # (the tf32 route runs the 3-channel lift analysis and the adjoint syntheses on the split kernels: functional.TF32_SPLIT_WHERE)
+    # (the tf32 route runs the 3-channel lift analysis on the split kernels: functional.TF32_SPLIT_WHERE)
     n_analysis = rep.get("analysis_zy_tc_kernel", (0,))[0] + rep.get("analysis_zy_tc3_kernel", (0,))[0]
-    assert rep.get("block_tail_bwd_kernel", (0,))[0] >= LAYERS and n_analysis >= 2 * LAYERS, rep
-    assert rep.get("analysis_zy_tc_kernel", (0,))[0] >= 2 * LAYERS - 1, rep        # the full-size analyses stay single-pass
+    assert n_analysis >= LAYERS and rep.get("analysis_zy_tc_kernel", (0,))[0] >= LAYERS - 1, rep   # forward analyses, single-pass
+    # backward: every block through block_spectral_bwd -- the z stage of the adjoint analysis of gu inside the block-tail
+    # kernel (gu never stored), then the y stage of the per-axis route; no unfused block-tail backward, no (z,y) analysis of gu
+    assert rep.get("block_spectral_bwd_kernel", (0,))[0] >= LAYERS and "block_tail_bwd_kernel" not in rep, rep
+    assert rep.get("gen_axis_analysis_kernel", (0,))[0] >= LAYERS and n_analysis < 2 * LAYERS, rep
     assert not any(k in rep for k in ("analysis_zy_kernel", "synthesis_zy_kernel")), rep       # no FFMA transform
     assert 0.2 < share < 5.0, f"spectral branch is {share:.3f} of the block input: the gate should see all three branches"
     errs = {"out": rel(out, out_o)}

@@ -976,3 +976,174 @@ def test_fno3d_other_activation_runs_the_block_in_the_library(activation):
     assert rel(out, ref) < 1e-5
     for n, p in model.named_parameters():
         assert rel(grads[n], p.grad) < 5e-5, (n, rel(grads[n], p.grad))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused block backward: block-tail backward + z stage of the adjoint analysis of gu in one kernel (pdephi_block_spectral_bwd)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["middle", "head", "lift", "lift_t"])
+@pytest.mark.parametrize("B,grid,modes_h", [(2, (32, 128, 128), (16, 32, 17)), (1, (64, 128, 128), (5, 12, 20)),
+                                            (1, (128, 128, 128), (32, 32, 17))])
+def test_fused_block_backward_vs_unfused_kernels(variant, B, grid, modes_h):
+    """t, dWc, dbc and G are the SAME arithmetic as the unfused block-tail backward (bit-identical); dZ is the ADJOINT
+    analysis of a gu that never reaches HBM: against the fp32-grade (split-TF32) analysis of the stored gu at the TF32 gate,
+    and no further from it than the unfused single-pass analysis is (x 1.5)."""
+    if variant != "middle" and grid[0] == 128:
+        pytest.skip("end-block variants are covered at the smaller shapes")
+    torch.manual_seed(7)
+    C = 64
+    u = torch.randn(B, C, *grid, device=DEV)
+    Wc = torch.randn(C, C, device=DEV) * 0.1
+    assert pf.block_spectral_supported(u, modes_h, _cabi.PREC_TF32)
+    head_w = lift = None
+    write_t = True
+    g = torch.randn(B, 3 if variant == "head" else C, *grid, device=DEV)
+    h = torch.randn(B, 3 if variant.startswith("lift") else C, *grid, device=DEV)
+    if variant == "head":
+        head_w = torch.randn(3, C, device=DEV) * 0.3
+    if variant.startswith("lift"):
+        lift = (torch.randn(C, 3, device=DEV) * 0.3, torch.randn(C, device=DEV) * 0.1)
+        write_t = variant == "lift_t"
+    gu, t0, dW0, db0, *rest = pf.block_tail_bwd(g, u, h, Wc, True, head_w, write_t=write_t, lift=lift)
+    dZ_ref = pf.analysis(gu, modes_h, _cabi.ADJOINT, _cabi.PREC_TF32X3)
+    dZ_old = pf.analysis(gu, modes_h, _cabi.ADJOINT, _cabi.PREC_TF32)
+    _cabi.profile(True, True)
+    t1, dW1, db1, dZ1, G1 = pf.block_spectral_bwd(g, u, h, Wc, modes_h, True, head_w, write_t=write_t, lift=lift)
+    torch.cuda.synchronize()
+    rep = _cabi.profile_report(timed=False)
+    _cabi.profile(False, True)
+    assert rep.get("block_spectral_bwd_kernel", (0,))[0] == 2 and "block_tail_bwd_kernel" not in rep, rep     # kernel + reduce
+    assert "analysis_zy_tc_kernel" not in rep and rep.get("gen_axis_analysis_kernel", (0,))[0] == 1, rep      # y stage only
+    assert torch.equal(dW1, dW0) and torch.equal(db1, db0)
+    if write_t:
+        assert torch.equal(t1, t0)
+    else:
+        assert t1 is None and torch.equal(G1, rest[0])
+    e_new = rel(torch.view_as_real(dZ1), torch.view_as_real(dZ_ref))
+    e_old = rel(torch.view_as_real(dZ_old), torch.view_as_real(dZ_ref))
+    print(f"\nfused block backward [{variant}] dZ vs fp32-grade analysis of gu: fused {e_new:.2e}, unfused tf32 {e_old:.2e}")
+    assert e_new < TOL["tf32"] and e_new < 1.5 * e_old + 1e-6
+
+
+def test_fused_block_backward_model_vs_unfused_route_and_deterministic():
+    """Whole width-64 model on the tf32 route with the fused backward on and off: every parameter gradient within the TF32
+    gate of the other route, and two runs of the fused route are bit-identical (fixed-order reductions)."""
+    torch.manual_seed(5)
+    modes, grid = (16, 32, 32), (32, 128, 128)
+    model = pb.RationalFourierOperator3D(modes=modes, width=64, n_layers=3).to(DEV).set_precision("tf32")
+    with torch.no_grad():
+        for layer in model.rational_layers:
+            q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+            layer.Q_coeffs.mul_(1e-4)
+            layer.Q_coeffs[..., 0, 0, 0] = q0
+            layer.P_coeffs.mul_(1e-2)
+    x = torch.randn(2, 3, *grid, device=DEV)
+    y = torch.randn(2, 3, *grid, device=DEV)
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        F.mse_loss(model(x), y).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for n, p in model.named_parameters()}
+
+    assert pf.FUSED_BLOCK_BACKWARD
+    a, b = run(), run()
+    assert all(torch.equal(a[n], b[n]) for n in a)
+    pf.FUSED_BLOCK_BACKWARD = False
+    try:
+        c = run()
+    finally:
+        pf.FUSED_BLOCK_BACKWARD = True
+    errs = {n: rel(a[n], c[n]) for n in a}
+    print("\nfused vs unfused block backward (rel L2):", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < SELF_TOL["fused_block"][1], errs
+
+
+# ------------------------------------------------------------------------------------------------
+# transfer-function cache: R(k), Q(k)+eps reused across forwards while the coefficients are unchanged
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order,B", [((4, 4), 8), ((3, 4), 2), ((2, 2), 1)])
+def test_transfer_kernels_are_bit_identical_to_the_fused_mix(order, B):
+    """pdephi_rational_transfer writes the same R / Q+eps as pdephi_rational_mix_fwd, and pdephi_rational_mix_apply the same Y
+    and projection statistics (same evaluation, same accumulation order): torch.equal."""
+    torch.manual_seed(3)
+    C, modes = 16, (8, 6, 8)
+    layer = pb.RationalFourierLayer(C, C, modes, rational_order=order).to(DEV)
+    M = modes[0] * modes[1] * (modes[2] // 2 + 1)
+    X = torch.randn(B, C, modes[0], modes[1], modes[2] // 2 + 1, dtype=torch.complex64, device=DEV)
+    mask = layer.stability_projection.decay_mask.reshape(-1).contiguous()
+    Y0, st0, R0, Qe0 = pf.rational_mix_fwd(X, layer.P_coeffs, layer.Q_coeffs, layer._mono_p, layer._mono_q, 1e-6, mask, 1e-6, True)
+    lib = pb.load_library()
+    R1, Qe1 = torch.empty_like(R0), torch.empty_like(Qe0)
+    _cabi.check(lib.pdephi_rational_transfer(pf._p(layer.P_coeffs), pf._p(layer.Q_coeffs), pf._p(layer._mono_p), pf._p(layer._mono_q),
+                                             order[0], order[1], 1e-6, pf._p(R1), pf._p(Qe1), C, C, M, None, None, None, pf._stream()))
+    Y1, st1 = torch.empty_like(Y0), torch.empty_like(st0)
+    _cabi.check(lib.pdephi_rational_mix_apply(pf._p(X), pf._p(R1), pf._p(mask), 1e-6, pf._p(Y1), pf._p(st1), B, C, C, M, pf._stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(R1, R0) and torch.equal(Qe1, Qe0)
+    assert torch.equal(torch.view_as_real(Y1), torch.view_as_real(Y0)) and torch.equal(st1, st0)
+
+
+def test_transfer_cache_hits_misses_and_data_writes():
+    """Second forward with unchanged coefficients: cache hit, no evaluation kernel, identical output.  An optimizer-style
+    in-place update (version bump): miss, fresh evaluation.  A write through `.data` (invisible to the version counter, e.g.
+    the reference's broadcast_parameters, training/distributed.py:230): caught by the device-side guard, output equals a
+    cache-less evaluation.  Gradients through a cached R equal the uncached ones bit for bit."""
+    torch.manual_seed(9)
+    C, modes, grid = 8, (8, 8, 8), (16, 16, 16)
+    layer = pb.RationalFourierLayer(C, C, modes).to(DEV)
+    x = torch.randn(2, C, *grid, device=DEV)
+    cache = layer._transfer_cache
+
+    def run(grad=False):
+        _cabi.profile(True, True)
+        if grad:
+            layer.zero_grad(set_to_none=True)
+            xx = x.clone().requires_grad_(True)
+            out = layer(xx)
+            out.square().sum().backward()
+            res = (out.detach().clone(), xx.grad.clone(), layer.P_coeffs.grad.clone(), layer.Q_coeffs.grad.clone())
+        else:
+            with torch.no_grad():
+                res = (layer(x).clone(),)
+        torch.cuda.synchronize()
+        rep = _cabi.profile_report(timed=False)
+        _cabi.profile(False, True)
+        return res, rep
+
+    (o0,), rep0 = run()
+    assert "rational_mix_kernel" in rep0 and cache.misses == 1 and cache.hits == 0
+    (o1,), rep1 = run()
+    assert cache.hits == 1 and "rational_mix_kernel" not in rep1 and "mix_apply_kernel" in rep1, rep1
+    assert torch.equal(o1, o0)
+    g_cached, rep2 = run(grad=True)                      # gradients through the cached R
+    assert cache.hits == 2 and "rational_mix_kernel" not in rep2
+    pf.set_transfer_cache(False)
+    try:
+        g_plain, rep3 = run(grad=True)
+        assert "rational_mix_kernel" in rep3
+    finally:
+        pf.set_transfer_cache(True)
+    assert all(torch.equal(a, b) for a, b in zip(g_cached, g_plain))
+    # a write through .data: same version counter, different coefficients
+    v = layer.P_coeffs._version
+    layer.P_coeffs.data.mul_(1.5)
+    assert layer.P_coeffs._version == v
+    hits = cache.hits
+    (o2,), rep4 = run()
+    assert cache.hits == hits + 1                          # host key matched ... the guard re-evaluated on the device
+    pf.set_transfer_cache(False)
+    try:
+        (o2_ref,), _ = run()
+    finally:
+        pf.set_transfer_cache(True)
+    assert torch.equal(o2, o2_ref) and not torch.equal(o2, o0)
+    # an in-place update that bumps the version (what an optimizer does): a miss, evaluated afresh
+    misses = cache.misses
+    with torch.no_grad():
+        layer.Q_coeffs.mul_(0.5)
+        layer.Q_coeffs[..., 0, 0, 0] = 1.0
+    (o3,), rep5 = run()
+    assert cache.misses == misses + 1 and "rational_mix_kernel" in rep5
+    (o4,), _ = run()
+    assert torch.equal(o4, o3)
