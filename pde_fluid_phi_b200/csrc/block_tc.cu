@@ -121,15 +121,15 @@ __device__ __forceinline__ uint32_t chunk_off_k(int r, int lane) {
   return (uint32_t)(j * BOX + r * 128 + (((cc ^ (r & 7)) & 7) << 4));
 }
 // rows [16*lw, 16*lw+16) of the tile of tensor `t` ([B*64 rows][S]) at (batch b, first point s0)
-template <bool KMAJOR>
+template <bool KMAJOR, int NW = LD_WARPS>
 __device__ __forceinline__ void stage_rows(uint32_t dst, const float* __restrict__ t, long long b, long long s0, long long S,
                                            int lw, int lane) {
   const float* src = t + ((size_t)b * C + lw) * S + s0 + lane * 4;
 #pragma unroll
-  for (int i = 0; i < LD_ROWS; ++i) {
-    const int r = lw + LD_WARPS * i;
-    if (C % LD_WARPS == 0 || r < C)
-      cp_async16(dst + (KMAJOR ? chunk_off_k(r, lane) : chunk_off_mn(r, lane)), src + (size_t)i * LD_WARPS * S);
+  for (int i = 0; i < (C + NW - 1) / NW; ++i) {
+    const int r = lw + NW * i;
+    if (C % NW == 0 || r < C)
+      cp_async16(dst + (KMAJOR ? chunk_off_k(r, lane) : chunk_off_mn(r, lane)), src + (size_t)i * NW * S);
   }
 }
 
@@ -144,13 +144,13 @@ __device__ __forceinline__ void load_x(float4* xv, const float* __restrict__ xin
     xv[n] = (n < n_in) ? __ldg(reinterpret_cast<const float4*>(xin + ((size_t)b * n_in + n) * S + s0) + lane)
                        : make_float4(0.f, 0.f, 0.f, 0.f);
 }
-template <bool KMAJOR>
+template <bool KMAJOR, int NW = LD_WARPS>
 __device__ __forceinline__ void generate_rows(uint8_t* dst, const float4* xv, const uint8_t* wtab, int lw, int lane) {
   const float* bias = reinterpret_cast<const float*>(wtab + C * 16);
 #pragma unroll
-  for (int i = 0; i < LD_ROWS; ++i) {
-    const int r = lw + LD_WARPS * i;
-    if (C % LD_WARPS != 0 && r >= C) break;
+  for (int i = 0; i < (C + NW - 1) / NW; ++i) {
+    const int r = lw + NW * i;
+    if (C % NW != 0 && r >= C) break;
     const float4 w = reinterpret_cast<const float4*>(wtab)[r];
     const float bb = bias[r];
     float4 o;
@@ -462,6 +462,12 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
 //   warp 0: MMA issuer + TMEM owner, warps 1..4: loaders, warps 5..20: compute / epilogue
 // ------------------------------------------------------------------------------------------------
 constexpr int B_STAGES = 2;
+// The ZA variants run three loader warps instead of four: 20 warps fit the 96-register allocation, 21 round up to 24 and cap
+// the kernel at 80, where the extra epilogue of the fused z analysis spilled ~300 bytes per thread onto the critical path of
+// the compute warps (3.67 / 4.04 / 3.97 ms for the first / middle / last block at 80 registers, 2.85 / 3.67 / 3.53 ms at 96).
+// The forward kernels and the plain backward keep four loaders (they are loader-bound: 2.49 -> 2.62 ms with three).
+__host__ __device__ constexpr int bwd_ld_warps(bool za) { return za ? 3 : LD_WARPS; }
+__host__ __device__ constexpr int bwd_threads(bool za) { return 32 * (1 + bwd_ld_warps(za) + EPI_WARPS); }
 constexpr int AUX = 4096;        // per stage: the x rows as a K-major [8 rows][128 points] operand (LIFT_G)
 struct BSmem { uint32_t stage[B_STAGES], aux[B_STAGES], wt, red, wp, lift, bars, tmem_slot, total; };
 __host__ __device__ inline BSmem bwd_smem() {
@@ -497,7 +503,7 @@ enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2
 // folded in) . gu^T -- and gu itself is never stored.  Vg has the layout of the per-axis route's z-analysed intermediate
 // ([B*64][Nx][Ny][ldz]), so the y and x stages follow unchanged (transforms_gen.cu: pdephi_block_spectral_bwd).
 template <bool GENG, bool WT, bool GENH, bool ZA>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(bwd_threads(ZA), 1)
 block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
                       const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
                       float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S, int contiguous,
@@ -512,18 +518,31 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   constexpr bool LIFT_G = GENH && !WT;
-  build_w_image(sm + L.wt, Wc, true, threadIdx.x, THREADS, TF32_COMP);      // rows c, K = o : (Wc^T)
+  constexpr int NLW = bwd_ld_warps(ZA), NTHR = bwd_threads(ZA), BEPI0 = 1 + NLW;      // loader warps / threads / first compute warp
+  build_w_image(sm + L.wt, Wc, true, threadIdx.x, NTHR, TF32_COMP);      // rows c, K = o : (Wc^T)
   if (GENG) {
     float* wp = reinterpret_cast<float*>(sm + L.wp);
-    for (int i = threadIdx.x; i < C * MAXP; i += THREADS) wp[i] = ((i & 3) < NP) ? __ldg(Wp + (i & 3) * C + (i >> 2)) : 0.f;
+    for (int i = threadIdx.x; i < C * MAXP; i += NTHR) wp[i] = ((i & 3) < NP) ? __ldg(Wp + (i & 3) * C + (i >> 2)) : 0.f;
   }
-  if (GENH && !LIFT_G) build_lift_table(sm + L.lift, Win, bin, n_in, threadIdx.x, THREADS);
-  if (LIFT_G) {              // operand rows beyond n_in are never written: zero once
-    float4* z = reinterpret_cast<float4*>(sm + L.aux[0]);
-    for (int i = threadIdx.x; i < B_STAGES * AUX / 16; i += THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (GENH && !LIFT_G) build_lift_table(sm + L.lift, Win, bin, n_in, threadIdx.x, NTHR);
+  // The bias gradient dbc = sum_s gu costs sixteen running sums per thread when it is kept in registers -- the registers that
+  // pushed this kernel into spilling.  Where a tensor-core product over the staged gu tile exists anyway it comes out of that
+  // product instead, against a row of ONES in the constant operand:
+  //   LIFT_G  row 7 of both aux blocks (K-major [8 rows][128 points]; rows < n_in receive the x rows of every tile): column 7
+  //           of G = sum gu (x) x accumulates it in TMEM over all tiles of the CTA;
+  //   ZA      row 127 of the z-analysis operand (gen_image_kernel kind 5): row 127 of D' holds the tile's sums, lane 31 of the
+  //           four quarter-3 compute warps adds them into shared memory (DB_ZA);
+  //   else    the running sums in registers (DB_REGS; not on the fused route).
+  // (A separate [64 x 8] product against a ones block was measured too: its 16 MMAs delay the release of the stage, which is
+  // what paces the last block's generating loaders -- 3.6 -> 4.0 ms.)
+  constexpr bool DB_ZA = ZA && !LIFT_G, DB_REGS = !ZA && !LIFT_G;
+  if (LIFT_G) {
+    float* z = reinterpret_cast<float*>(sm + L.aux[0]);
+    for (int i = threadIdx.x; i < B_STAGES * AUX / 4; i += NTHR) z[i] = (((i >> 5) & 7) == 7) ? 1.f : 0.f;
   }
+  if (threadIdx.x < 4 * C) reinterpret_cast<float*>(sm + L.red)[threadIdx.x] = 0.f;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), LD_THREADS); mbar_init(bar(BB_EMPTY + i), 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), 32 * NLW); mbar_init(bar(BB_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(BB_GUREADY + i), EPI_WARPS);
       mbar_init(bar(BB_TFULL + i), 1);
@@ -544,7 +563,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   const uint32_t tmem_t[2] = {tmem, tmem + C}, tmem_dw = tmem + 2 * C;
   const uint32_t tmem_za[2] = {tmem + 3 * C, tmem + 4 * C}, tmem_a = tmem + 6 * C;   // ZA: accumulators, A image [128 x 128]
   if (ZA) {
-    if (warp >= EPI0 && warp < EPI0 + 4) {       // four consecutive warps cover the four TMEM lane quarters
+    if (warp >= BEPI0 && warp < BEPI0 + 4) {       // four consecutive warps cover the four TMEM lane quarters
       const int q = warp & 3;
       const float* row = za_img + (size_t)(32 * q + lane) * TS;
       for (int c0 = 0; c0 < TS; c0 += 32) {
@@ -570,7 +589,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   const long long tile0 = contiguous ? blockIdx.x * tq + (blockIdx.x < tr ? blockIdx.x : tr) : blockIdx.x;
   const long long tstep = contiguous ? 1 : gridDim.x;
 
-  if (warp >= 1 && warp < EPI0) {
+  if (warp >= 1 && warp < BEPI0) {
     // ===== loaders: g' (MN layout), h (K layout), u (K layout); a landed tile is published before the loader blocks on
     //       the stage of the next one (see the forward kernel) =====
     const int lw = warp - 1;
@@ -586,7 +605,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
           gv[n] = (n < NP) ? __ldg(reinterpret_cast<const float4*>(g_in + ((size_t)b * NP + n) * S + s0) + lane)
                            : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
-        stage_rows<false>(base + L.stage[s], g_in, b, s0, S, lw, lane);
+        stage_rows<false, NLW>(base + L.stage[s], g_in, b, s0, S, lw, lane);
       }
       if (LIFT_G) {      // h_in = model input x: its n_in rows as a K-major operand [8 rows][128 points], 128-byte swizzle
         if (lw == 0) {
@@ -598,17 +617,17 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       } else if (GENH) {                                                           // h_in = model input x
         float4 xv[MAXP_IN];
         load_x(xv, h_in, n_in, b, s0, S, lane);
-        generate_rows<true>(sm + L.stage[s] + TILE, xv, sm + L.lift, lw, lane);
+        generate_rows<true, NLW>(sm + L.stage[s] + TILE, xv, sm + L.lift, lw, lane);
       } else {
-        stage_rows<true>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
+        stage_rows<true, NLW>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
       }
-      stage_rows<true>(base + L.stage[s] + 2 * TILE, u_in, b, s0, S, lw, lane);
+      stage_rows<true, NLW>(base + L.stage[s] + 2 * TILE, u_in, b, s0, S, lw, lane);
       if (GENG) {
         uint8_t* dst = sm + L.stage[s];
 #pragma unroll
-        for (int i = 0; i < LD_ROWS; ++i) {
-          const int r = lw + LD_WARPS * i;
-          if (C % LD_WARPS != 0 && r >= C) break;
+        for (int i = 0; i < (C + NLW - 1) / NLW; ++i) {
+          const int r = lw + NLW * i;
+          if (C % NLW != 0 && r >= C) break;
           const float4 w = reinterpret_cast<const float4*>(sm + L.wp)[r];
           float4 o;
           o.x = fmaf(w.w, gv[3].x, fmaf(w.z, gv[2].x, fmaf(w.y, gv[1].x, w.x * gv[0].x)));
@@ -676,11 +695,11 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       mma_commit(bar(BB_DWDONE));
     }
   } else {
-    const int q = warp & 3, part = (warp - EPI0) >> 2;
+    const int q = warp & 3, part = (warp - BEPI0) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float db[CPW];
+    float db[DB_REGS ? CPW : 1];
 #pragma unroll
-    for (int j = 0; j < CPW; ++j) db[j] = 0.f;
+    for (int j = 0; j < (DB_REGS ? CPW : 1); ++j) db[j] = 0.f;
     // static shared-memory offsets of this thread's elements: row o = part*CPW + j, point 32q + lane.  The swizzle term
     // depends on o & 3 (32-byte-atom layout) or o & 7 (16-byte-chunk layout), i.e. on j only (CPW is a multiple of 8).
     uint32_t xc[4], xk[8];
@@ -708,7 +727,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         if (WT) *reinterpret_cast<float*>(tg + off) = r[j];
         *reinterpret_cast<float*>(tgk + offk) = to_tf32(r[j]);
         if (!ZA) { *gp = r[j]; gp += S; }
-        db[j] += r[j];
+        if (DB_REGS) db[j] += r[j];
       }
       fence_proxy_async();
       __syncwarp();
@@ -740,13 +759,18 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       if (ZA) {            // rows kz' = 32 q + lane of D' exist in quarters 0 and 1 only (ldz <= 64)
         mbar_wait(bar(BB_ZAFULL + d), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
-        if (q < 2) {
+        if (q < 2 || (DB_ZA && q == 3)) {
           tmem_ld16(tmem_za[d] + lane_base + part * CPW, v);
           tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BB_ZAEMPTY + d));
+        if (DB_ZA && q == 3 && lane == 31) {     // row 127 of D' = sum over the tile's points of gu (the operand's ones row)
+          float* acc = reinterpret_cast<float*>(sm + L.red) + part * CPW;
+#pragma unroll
+          for (int j = 0; j < CPW; ++j) acc[j] += v[j];
+        }
         if (q < 2 && 32 * q + lane < ldz) {       // Vg [B*64 volumes][tiles of a volume = (x, y)][ldz]: the W1 layout of the per-axis route
           const long long b = t / tiles_per_batch, tib = t - b * tiles_per_batch;
           float* vp = vg_out + (((size_t)b * C + part * CPW) * tiles_per_batch + tib) * ldz + 32 * q + lane;
@@ -768,32 +792,37 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         epilogue(it + 1, rb);
       }
     }
-    // ---- per-CTA partials: dbias (registers -> warp shuffle -> 4 quarter-warps summed in order) and dW (TMEM) ----
-    float* red = reinterpret_cast<float*>(sm + L.red);      // [4 quarters][64]
+    // ---- per-CTA partials: the bias gradient (see DB_ZA / DB_REGS / LIFT_G above) and dW or G (TMEM) ----
+    float* red = reinterpret_cast<float*>(sm + L.red);      // DB_REGS: [4 quarters][64];  DB_ZA: [64]
+    if (DB_REGS) {
 #pragma unroll
-    for (int j = 0; j < CPW; ++j) {
-      float x = db[j];
+      for (int j = 0; j < CPW; ++j) {
+        float x = db[j];
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-      if (lane == 0) red[q * C + part * CPW + j] = x;
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if (lane == 0) red[q * C + part * CPW + j] = x;
+      }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     float* pout = partial + (size_t)blockIdx.x * (C * C + C);
-    if (warp == EPI0 && my_tiles >= 0) {
-      for (int o = lane; o < C; o += 32) pout[C * C + o] = (red[o] + red[C + o]) + (red[2 * C + o] + red[3 * C + o]);
+    if (!LIFT_G && warp == BEPI0) {
+      for (int o = lane; o < C; o += 32)
+        pout[C * C + o] = DB_REGS ? (red[o] + red[C + o]) + (red[2 * C + o] + red[3 * C + o]) : red[o];
     }
     if (my_tiles > 0) {
       mbar_wait(bar(BB_DWDONE), 0);
       tc_fence_after();
       if (part == 0) {                 // M = 64 accumulator: rows 16q..16q+15 live in lanes 0..15 of quarter q
-        if (LIFT_G) {                  // G: 8 columns
+        if (LIFT_G) {                  // G: 8 columns, column 7 = sum gu (the ones row)
           float w0[8];
           tmem_ld8(tmem_dw + lane_base, w0);
           tmem_ld_wait();
           if (lane < 16) {
             float* row = pout + (size_t)(16 * q + lane) * C;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) row[c] = w0[c];
+            for (int c = 0; c < 7; ++c) row[c] = w0[c];
+            row[7] = 0.f;
+            pout[C * C + 16 * q + lane] = w0[7];
           }
         } else {
           float w0[32], w1[32];
@@ -810,6 +839,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
     } else if (part == 0 && lane < 16) {
       float* row = pout + (size_t)(16 * q + lane) * C;
       for (int c = 0; c < C; ++c) row[c] = 0.f;
+      if (LIFT_G) pout[C * C + 16 * q + lane] = 0.f;
     }
   }
   tc_fence_before();
@@ -988,7 +1018,7 @@ int block_tail_bwd_launch(const float* g, const float* u, const float* h, const 
     {                                                                                                                      \
       auto k = blk::block_tail_bwd_kernel<GG, WW, HH, ZZ>;                                                                 \
       PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
-      k<<<grid, blk::THREADS, smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out,  \
+      k<<<grid, blk::bwd_threads(ZZ), smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out,  \
                                           lf.Win, lf.bin, lf.n, za_img, vg, ldz);                                          \
     }
 #define PDEPHI_BWD_LAUNCH(GG, WW, HH) { if (vg) PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, true) else PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, false) }

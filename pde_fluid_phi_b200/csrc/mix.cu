@@ -574,6 +574,142 @@ rational_dpq_kernel(const float* __restrict__ G, const float* __restrict__ R, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Phase B, pipelined: the same sums with the G / R tiles ([256 pairs][32 modes], 128-byte row pieces) and the monomial tile
+// staged by cp.async two tiles deep, so the loads of tile n+1 run under the 1280 FMAs per thread of tile n.  The version above
+// loads a tile into registers, synchronises, computes, synchronises: 0.33 ms for 0.57 GB at the 128^3 / width-64 shape and
+// 2.5 ms for 4.4 GB at 64^3 modes (1.7 TB/s) against ~0.1 / 0.75 ms of HBM or FMA time.  Needs 16-byte aligned rows
+// (M % 4 == 0) and a k-major monomial table (monoT [M][T4], transposed once per call by mono_transpose_kernel).
+// Rows are padded to 36 floats: thread = pair reads its row as float4, and 16-byte chunk index 9 p mod 8 = p mod 8 is
+// conflict-free per quarter warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int KT2 = 32;
+constexpr int ROWF = KT2 + 4;
+__device__ __forceinline__ void dpq_cp16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__global__ void mono_transpose_kernel(const float* __restrict__ mono, float* __restrict__ monoT, int TN, int T4, long long M) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over M * T4
+  if (i >= M * T4) return;
+  const long long k = i / T4;
+  const int t = (int)(i - k * T4);
+  monoT[i] = t < TN ? __ldg(mono + (size_t)t * M + k) : 0.f;
+}
+template <int OP, int OQ>
+struct DpqSmem {
+  static constexpr int TP4 = Tri<OP>::TP4, TQ4 = Tri<OQ>::TP4;
+  static constexpr bool SAME = (OP == OQ);
+  static constexpr int G = 0, R = DPQ_THREADS * ROWF * 4, MP = 2 * DPQ_THREADS * ROWF * 4, MQ = MP + KT2 * TP4 * 4;
+  static constexpr int STAGE = MQ + (SAME ? 0 : KT2 * TQ4 * 4);
+  static constexpr int TOTAL = 2 * STAGE;
+};
+
+template <int OP, int OQ>
+__global__ void __launch_bounds__(DPQ_THREADS, 1)
+rational_dpq_pipe_kernel(const float* __restrict__ G, const float* __restrict__ R, const float* __restrict__ monoPT,
+                         const float* __restrict__ monoQT, float* __restrict__ partial, long long npairs, long long M,
+                         long long kchunk) {
+  constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
+  constexpr int TP4 = Tri<OP>::TP4, TQ4 = Tri<OQ>::TP4;
+  constexpr bool SAME = (OP == OQ);
+  using L = DpqSmem<OP, OQ>;
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dsm);
+  const long long q0 = (long long)blockIdx.x * DPQ_THREADS;
+  const long long qraw = q0 + threadIdx.x;
+  const long long k_lo = (long long)blockIdx.y * kchunk;
+  const long long k_hi = min(M, k_lo + kchunk);
+  const int ntiles = k_hi > k_lo ? (int)((k_hi - k_lo + KT2 - 1) / KT2) : 0;
+
+  auto issue = [&](int tile) {
+    const long long k0 = k_lo + (long long)tile * KT2;
+    const uint32_t st = sbase + (uint32_t)(tile & 1) * L::STAGE;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                      // 256 rows x 8 chunks per tensor, 8 per thread: a warp = 4 rows x 128 B
+      const int c = threadIdx.x + j * DPQ_THREADS, row = c >> 3, ch = c & 7;
+      const long long qq = min(q0 + row, npairs - 1);
+      const long long k = k0 + ch * 4;
+      const int nb = k >= k_hi ? 0 : (int)min(4LL, k_hi - k) * 4;      // bytes of this chunk inside the k range (rest zero-filled)
+      const size_t off = (size_t)qq * M + (nb ? k : k_lo);
+      dpq_cp16(st + L::G + (uint32_t)(row * ROWF + ch * 4) * 4, G + off, nb);
+      dpq_cp16(st + L::R + (uint32_t)(row * ROWF + ch * 4) * 4, R + off, nb);
+    }
+    for (int c = threadIdx.x; c < KT2 * TP4 / 4; c += DPQ_THREADS) {       // monoT rows k0 .. k0+31: contiguous
+      const long long k = k0 + (c * 4) / TP4;
+      const int nb = k < M ? 16 : 0;
+      dpq_cp16(st + L::MP + c * 16, monoPT + (nb ? (size_t)k0 * TP4 + c * 4 : 0), nb);
+    }
+    if (!SAME) {
+      for (int c = threadIdx.x; c < KT2 * TQ4 / 4; c += DPQ_THREADS) {
+        const long long k = k0 + (c * 4) / TQ4;
+        const int nb = k < M ? 16 : 0;
+        dpq_cp16(st + L::MQ + c * 16, monoQT + (nb ? (size_t)k0 * TQ4 + c * 4 : 0), nb);
+      }
+    }
+  };
+
+  float ap[TPN], aq[TQN];
+#pragma unroll
+  for (int t = 0; t < TPN; ++t) ap[t] = 0.f;
+#pragma unroll
+  for (int t = 0; t < TQN; ++t) aq[t] = 0.f;
+  if (ntiles > 0) issue(0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int tile = 0; tile < ntiles; ++tile) {
+    if (tile + 1 < ntiles) issue(tile + 1);            // its buffer was released by the barrier that ended tile - 1
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // tile `tile` has landed (this thread's copies) ...
+    __syncthreads();                                   // ... and everybody else's
+    const uint8_t* st = dsm + (tile & 1) * L::STAGE;
+    const float* Gs = reinterpret_cast<const float*>(st + L::G) + threadIdx.x * ROWF;
+    const float* Rs = reinterpret_cast<const float*>(st + L::R) + threadIdx.x * ROWF;
+    const float* mPs = reinterpret_cast<const float*>(st + L::MP);
+    const float* mQs = reinterpret_cast<const float*>(st + L::MQ);
+#pragma unroll 2
+    for (int k4 = 0; k4 < KT2 / 4; ++k4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(Gs + 4 * k4);
+      const float4 r4 = *reinterpret_cast<const float4*>(Rs + 4 * k4);
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kk = 4 * k4 + e;
+        const float g = gg[e];
+        const float h = -g * rr[e];
+        const float4* p4 = reinterpret_cast<const float4*>(mPs + kk * TP4);
+#pragma unroll
+        for (int t4 = 0; t4 < TP4 / 4; ++t4) {
+          const float4 m = p4[t4];
+          const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            if (4 * t4 + x < TPN) ap[4 * t4 + x] = fmaf(g, mm[x], ap[4 * t4 + x]);
+            if (SAME && 4 * t4 + x < TQN) aq[4 * t4 + x] = fmaf(h, mm[x], aq[4 * t4 + x]);
+          }
+        }
+        if (!SAME) {
+          const float4* q4 = reinterpret_cast<const float4*>(mQs + kk * TQ4);
+#pragma unroll
+          for (int t4 = 0; t4 < TQ4 / 4; ++t4) {
+            const float4 m = q4[t4];
+            const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+              if (4 * t4 + x < TQN) aq[4 * t4 + x] = fmaf(h, mm[x], aq[4 * t4 + x]);
+          }
+        }
+      }
+    }
+    __syncthreads();                                   // this buffer may be refilled (by issue(tile + 2) next iteration)
+  }
+  if (qraw < npairs) {
+    float* dst = partial + ((size_t)blockIdx.y * npairs + qraw) * (TPN + TQN);
+#pragma unroll
+    for (int t = 0; t < TPN; ++t) dst[t] = ap[t];
+#pragma unroll
+    for (int t = 0; t < TQN; ++t) dst[TPN + t] = aq[t];
+  }
+}
+
 // one thread per (pair, monomial): coalesced over the 2T partials of a pair, fixed-order sum over the k splits;
 // dP / dQ are zero-filled beforehand so the unused (a+b+c >= order) entries read 0 like autograd's
 __global__ void dpq_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dP, float* __restrict__ dQ,
@@ -711,6 +847,20 @@ static void dpq_geometry(int I, int O, long long M, int* pair_blocks, int* KS, l
   *KS = (int)((M + chunk - 1) / chunk);
   *kchunk = chunk;
 }
+// pipelined kernel: one CTA per SM (152 KB of shared memory), so one wave of pair_blocks x KS CTAs; chunks are multiples of 32
+static bool dpq_pipe_ok(long long M) { return M % 4 == 0 && M >= 4 * KT2; }
+static void dpq_pipe_geometry(int I, int O, long long M, int* pair_blocks, int* KS, long long* kchunk) {
+  const long long npairs = (long long)O * I;
+  *pair_blocks = (int)((npairs + DPQ_THREADS - 1) / DPQ_THREADS);
+  long long ks = 148 / *pair_blocks;
+  if (ks < 1) ks = 1;
+  const long long max_ks = (M + 4 * KT2 - 1) / (4 * KT2);      // at least four tiles per CTA
+  if (ks > max_ks) ks = max_ks;
+  long long chunk = (M + ks - 1) / ks;
+  chunk = (chunk + KT2 - 1) / KT2 * KT2;
+  *KS = (int)((M + chunk - 1) / chunk);
+  *kchunk = chunk;
+}
 static size_t dpq_partial_bytes(int op, int oq, int I, int O, long long M) {
   int pair_blocks, KS;
   long long kchunk;
@@ -721,11 +871,12 @@ static size_t dpq_partial_bytes(int op, int oq, int I, int O, long long M) {
 template <int OP, int OQ>
 static int launch_dpq(const float2* X, const float2* dY, const float* R, const float* Qe, const float* monoP,
                       const float* monoQ, float* dP, float* dQ, int B, int I, int O, long long M, float* partial,
-                      float* G, const MonoOffsets& offs, cudaStream_t st) {
+                      float* G, float* monoT, const MonoOffsets& offs, cudaStream_t st) {
   int pair_blocks, KS;
   long long kchunk;
   dpq_geometry(I, O, M, &pair_blocks, &KS, &kchunk);
   constexpr int TPN = Tri<OP>::T, TQN = Tri<OQ>::T;
+  constexpr int TP4 = Tri<OP>::TP4, TQ4 = Tri<OQ>::TP4;
   const long long npairs = (long long)O * I;
   if ((O + GO - 1) / GO > 65535) return fail(PDEPHI_ERR_UNSUPPORTED, "rational_mix_bwd: too many output channels");
   {
@@ -738,11 +889,26 @@ static int launch_dpq(const float2* X, const float2* dY, const float* R, const f
     else rational_g_kernel<false><<<grid, MIX_THREADS, 0, st>>>(X, dY, Qe, G, B, I, O, M);
   }
   PDEPHI_LAUNCH_CHECK("rational_g_kernel");
-  {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (dpq_pipe_ok(M) && al16(G) && al16(R) && monoT && al16(monoT)) {
+    // pipelined reduction: k-major monomial tables first (a few MB), then one wave of CTAs with cp.async double buffering
+    dpq_pipe_geometry(I, O, M, &pair_blocks, &KS, &kchunk);
+    float* monoPT = monoT;
+    float* monoQT = monoT + (size_t)M * TP4;
+    {
+      ProfScope ps(K_RATIONAL_DPQ, st);
+      mono_transpose_kernel<<<(unsigned)((M * TP4 + 255) / 256), 256, 0, st>>>(monoP, monoPT, TPN, TP4, M);
+      if (OP != OQ) mono_transpose_kernel<<<(unsigned)((M * TQ4 + 255) / 256), 256, 0, st>>>(monoQ, monoQT, TQN, TQ4, M);
+      auto k = rational_dpq_pipe_kernel<OP, OQ>;
+      PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DpqSmem<OP, OQ>::TOTAL));
+      k<<<dim3(pair_blocks, KS), DPQ_THREADS, DpqSmem<OP, OQ>::TOTAL, st>>>(G, R, monoPT, monoQT, partial, npairs, M, kchunk);
+    }
+    PDEPHI_LAUNCH_CHECK("rational_dpq_pipe_kernel");
+  } else {
     ProfScope ps(K_RATIONAL_DPQ, st);
     rational_dpq_kernel<OP, OQ><<<dim3(pair_blocks, KS), DPQ_THREADS, 0, st>>>(G, R, monoP, monoQ, partial, npairs, M, kchunk);
+    PDEPHI_LAUNCH_CHECK("rational_dpq_kernel");
   }
-  PDEPHI_LAUNCH_CHECK("rational_dpq_kernel");
   PDEPHI_CUDA(cudaMemsetAsync(dP, 0, (size_t)npairs * OP * OP * OP * sizeof(float), st));
   PDEPHI_CUDA(cudaMemsetAsync(dQ, 0, (size_t)npairs * OQ * OQ * OQ * sizeof(float), st));
   {
@@ -891,8 +1057,10 @@ extern "C" int pdephi_projection_bwd_sharded(const float* dZ, const float* Y, co
 
 extern "C" size_t pdephi_rational_mix_bwd_workspace_bytes(int order_p, int order_q, int I, int O, long long M) {
   if (I <= 0 || O <= 0 || M <= 0 || order_p < 1 || order_q < 1) return 0;
-  // per-k-split partials of dP/dQ followed by the G = dR/Qe matrix [O, I, M]
-  return dpq_partial_bytes(order_p, order_q, I, O, M) + align_up((size_t)O * I * M * sizeof(float), 256);
+  // per-k-split partials of dP/dQ, the G = dR/Qe matrix [O, I, M], the k-major monomial tables of the pipelined reduction
+  const size_t t4p = (size_t)(tri(order_p) + 3) / 4 * 4, t4q = (size_t)(tri(order_q) + 3) / 4 * 4;
+  return dpq_partial_bytes(order_p, order_q, I, O, M) + align_up((size_t)O * I * M * sizeof(float), 256) +
+         align_up((size_t)M * (t4p + t4q) * sizeof(float), 256);
 }
 
 extern "C" int pdephi_rational_mix_bwd(const float* X, const float* dY, const float* R, const float* Qe,
@@ -919,10 +1087,11 @@ extern "C" int pdephi_rational_mix_bwd(const float* X, const float* dY, const fl
   fill_offsets(order_p, offs.p);
   fill_offsets(order_q, offs.q);
   float* Gbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + dpq_partial_bytes(order_p, order_q, I, O, M));
+  float* monoT = reinterpret_cast<float*>(reinterpret_cast<char*>(Gbuf) + align_up((size_t)O * I * M * sizeof(float), 256));
 #define CASE(a, b)                                                                                          \
   if (order_p == a && order_q == b)                                                                         \
     return launch_dpq<a, b>((const float2*)X, (const float2*)dY, R, Qe, monoP, monoQ, dP, dQ, B, I, O, M,    \
-                            (float*)workspace, Gbuf, offs, st);
+                            (float*)workspace, Gbuf, monoT, offs, st);
   ORDER_CASES
 #undef CASE
   return fail(PDEPHI_ERR_UNSUPPORTED, "rational order (%d,%d) is not instantiated (supported: every (p,q) in 2..4, and (1,1), (5,5), (6,6))", order_p, order_q);

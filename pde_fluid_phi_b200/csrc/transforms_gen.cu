@@ -53,7 +53,8 @@ __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
 //   kind 1  z synthesis B  K-major [R = zN rows][K]        col k: mode k>>1, (k&1 ? -w sin : w cos)(2 pi mode r / N)
 //   kind 2  axis analysis A  plain [128][N]                row r: mode r&63, (r>>6 ? sin : cos)(2 pi mode (k+off) / Nt)
 //   kind 3/4 axis synthesis A K-major [R = N rows][K = mk]  (cos / sin)(2 pi k (r+off) / Nt)
-//   kind 5  z analysis as a plain [R][K = zN] A operand (TMEM-resident, fused block backward): rows as kind 0
+//   kind 5  z analysis as a plain [R][K = zN] A operand (TMEM-resident, fused block backward): rows as kind 0; the LAST row
+//           is all ones (the tile sums of gu = the bias gradient of the block's convolution ride in the same product)
 // wmode 0: w = 1, 1: w = c_k / total (c_k = 1 for k = 0 and Nyquist, else 2), 2: w = 1 / total
 // ------------------------------------------------------------------------------------------------
 __global__ void gen_image_kernel(float* __restrict__ img, int kind, int R, int K, int Nt, int off, int m, int wmode, int nyq,
@@ -82,6 +83,7 @@ __global__ void gen_image_kernel(float* __restrict__ img, int kind, int R, int K
     v = (kind <= 1 || kind == 5) ? (sine ? -w * s : w * c) : (sine ? s : c);
     v *= comp;
   }
+  if (kind == 5 && rimg == R - 1) v = 1.0;
   float f = to_tf32((float)v);
   if (part == 1) f = to_tf32((float)(v - (double)f));
   if (kind == 2 || kind == 5) img[(size_t)rimg * K + k] = f;

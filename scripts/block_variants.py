@@ -41,10 +41,15 @@ cases = {
     "bwd middle": (lambda: pf.block_tail_bwd(g, u, h, W, True), 5 * act),
     "bwd first  <lift, no t>": (lambda: pf.block_tail_bwd(g, u, x, W, True, write_t=False, lift=(Win, bin_)), 3 * act + small),
     "bwd last   <proj>": (lambda: pf.block_tail_bwd(gout, u, h, W, True, head_w=Wp), 4 * act + small),
+    # fused backward (z stage of the adjoint analysis inside the kernel): gu is not stored, the z-analysed gu (Vg) is
+    "bwdz middle": (lambda: pf.block_spectral_bwd(g, u, h, W, mh, True), 4 * act + V),
+    "bwdz first  <lift, no t>": (lambda: pf.block_spectral_bwd(g, u, x, W, mh, True, write_t=False, lift=(Win, bin_)), 2 * act + small + V),
+    "bwdz last   <proj>": (lambda: pf.block_spectral_bwd(gout, u, h, W, mh, True, head_w=Wp), 3 * act + small + V),
 }
 res = {}
 for name, (fn, nbytes) in cases.items():
-    kname = "block_spectral_fwd_kernel" if name.startswith("fwd") else "block_tail_bwd_kernel"
+    kname = ("block_spectral_fwd_kernel" if name.startswith("fwd") else
+             "block_spectral_bwd_kernel" if name.startswith("bwdz") else "block_tail_bwd_kernel")
     for _ in range(2):
         fn()
     torch.cuda.synchronize()

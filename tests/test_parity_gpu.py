@@ -985,7 +985,8 @@ def test_fno3d_other_activation_runs_the_block_in_the_library(activation):
 @pytest.mark.parametrize("B,grid,modes_h", [(2, (32, 128, 128), (16, 32, 17)), (1, (64, 128, 128), (5, 12, 20)),
                                             (1, (128, 128, 128), (32, 32, 17))])
 def test_fused_block_backward_vs_unfused_kernels(variant, B, grid, modes_h):
-    """t, dWc, dbc and G are the SAME arithmetic as the unfused block-tail backward (bit-identical); dZ is the ADJOINT
+    """t, dWc and G are the SAME arithmetic as the unfused block-tail backward (bit-identical); dbc comes out of a tensor-core
+    product over the TF32-rounded gu tile instead of fp32 running sums (TF32 gate); dZ is the ADJOINT
     analysis of a gu that never reaches HBM: against the fp32-grade (split-TF32) analysis of the stored gu at the TF32 gate,
     and no further from it than the unfused single-pass analysis is (x 1.5)."""
     if variant != "middle" and grid[0] == 128:
@@ -1014,7 +1015,7 @@ def test_fused_block_backward_vs_unfused_kernels(variant, B, grid, modes_h):
     _cabi.profile(False, True)
     assert rep.get("block_spectral_bwd_kernel", (0,))[0] == 2 and "block_tail_bwd_kernel" not in rep, rep     # kernel + reduce
     assert "analysis_zy_tc_kernel" not in rep and rep.get("gen_axis_analysis_kernel", (0,))[0] == 1, rep      # y stage only
-    assert torch.equal(dW1, dW0) and torch.equal(db1, db0)
+    assert torch.equal(dW1, dW0) and rel(db1, db0) < 1e-3, rel(db1, db0)
     if write_t:
         assert torch.equal(t1, t0)
     else:
