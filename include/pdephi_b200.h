@@ -300,8 +300,13 @@ int pdephi_wide_block_tail_bwd(const float* g, const float* u, const float* h, c
 
 /* ---- run-time options ------------------------------------------------------------------------------
  * PDEPHI_OPT_TF32_XSTAGE_SPLIT (default 1): on the single-pass TF32 route the x stage -- which works on the pruned
- * intermediate, 6.6 % of an activation -- runs split (fp32-grade), removing one of the transform's three TF32 roundings. */
-enum pdephi_option { PDEPHI_OPT_TF32_XSTAGE_SPLIT = 0 };
+ * intermediate, 6.6 % of an activation -- runs split (fp32-grade), removing one of the transform's three TF32 roundings.
+ * PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE (default 1): the `u` output of the width-64 block-tail FORWARD kernels (pdephi_block_tail_*_fwd,
+ * pdephi_block_spectral_*_fwd) holds gelu'(pre-activation) instead of the pre-activation, and the backward kernels read it as
+ * such: the backward needs u for nothing else, the forward has the Gaussian CDF / density in registers anyway (two more
+ * instructions per element), and the backward's compute warps -- its bound -- drop ~25 instructions per element.  Same bits
+ * in gu either way.  Set 0 to get the pre-activation itself (both directions must run under the same setting). */
+enum pdephi_option { PDEPHI_OPT_TF32_XSTAGE_SPLIT = 0, PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE = 1 };
 int pdephi_set_option(int key, int value);
 int pdephi_get_option(int key);
 

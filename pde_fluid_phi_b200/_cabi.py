@@ -21,6 +21,7 @@ PREC_AUTO = -1    # host-side only: TF32X3 where the plan supports it, FP32 (FFM
 FORWARD, ADJOINT = 0, 1
 STAGES_ZY, STAGES_X, STAGES_ALL = 1, 2, 3
 OPT_TF32_XSTAGE_SPLIT = 0
+OPT_BLOCK_SAVES_DERIVATIVE = 1
 ACTIVATIONS = {"identity": 0, "gelu": 1, "relu": 2, "tanh": 3, "silu": 4, "sigmoid": 5, "leaky_relu": 6, "elu": 7}
 ROUTE_NONE, ROUTE_FFMA, ROUTE_FUSED_TC, ROUTE_PER_AXIS_TC = 0, 1, 2, 3
 PER_AXIS_SPLIT_MIN_POINTS = 1 << 25      # 'auto': below this many points per call the FFMA kernels beat the per-axis split route
@@ -230,6 +231,14 @@ def on_device(device):
     microseconds per use, which adds up over the ~10 library calls of one small layer)."""
     import torch
     return _no_switch if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+
+def set_option(key: int, value: int) -> int:
+    """pdephi_set_option; returns the previous value."""
+    lib = load()
+    old = lib.pdephi_get_option(key)
+    check(lib.pdephi_set_option(key, int(value)), "set_option")
+    return old
 
 
 def profile(enable: bool = True, reset: bool = True):

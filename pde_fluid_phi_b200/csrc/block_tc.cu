@@ -83,6 +83,13 @@ __device__ __forceinline__ float gelu_f(float u) {
   gelu_parts(u, cdf, e);
   return u * cdf;
 }
+// gelu(u) and gelu'(u) from the same CDF / density
+__device__ __forceinline__ float gelu_both_f(float u, float& grad) {
+  float cdf, e;
+  gelu_parts(u, cdf, e);
+  grad = fmaf(u * 0.3989422804014327f, e, cdf);
+  return u * cdf;
+}
 __device__ __forceinline__ float gelu_grad_f(float u) {
   float cdf, e;
   gelu_parts(u, cdf, e);
@@ -236,7 +243,8 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
                       const float* __restrict__ bc, float* __restrict__ u_out, float* __restrict__ h_out,
                       long long tiles_per_batch, long long ntiles, long long S, const float* __restrict__ bzimg, int ldz,
                       int contiguous, const float* __restrict__ Wp, const float* __restrict__ bp, float* __restrict__ proj_out,
-                      int NP, const float* __restrict__ Win, const float* __restrict__ bin, int n_in) {
+                      int NP, const float* __restrict__ Win, const float* __restrict__ bin, int n_in, int save_du) {
+  // save_du: u_out receives gelu'(u) -- all the backward needs u for -- instead of u (PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -421,8 +429,9 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < CPW; ++j) {
         const float u = fmaf(v[j], TF32_COMP, bsr[j]) + pre[j];
-        __stcs(up, u);
-        const float hv = gelu_f(u);
+        float du;
+        const float hv = gelu_both_f(u, du);
+        __stcs(up, save_du ? du : u);
         *hp = hv;
         if (PROJ) {
           const float4 w = reinterpret_cast<const float4*>(sm + L.wp)[part * CPW + j];
@@ -508,7 +517,8 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
                       const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
                       float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S, int contiguous,
                       const float* __restrict__ Wp, int NP, const float* __restrict__ Win, const float* __restrict__ bin, int n_in,
-                      const float* __restrict__ za_img, float* __restrict__ vg_out, int ldz) {
+                      const float* __restrict__ za_img, float* __restrict__ vg_out, int ldz, int u_is_du) {
+  // u_is_du: u_in holds gelu'(u) as the forward kernels store it under PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -718,16 +728,20 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       uint8_t* tgk = tg + 2 * TILE;
       mbar_wait(bar(BB_FULL + s), (uint32_t)((it / B_STAGES) & 1));
       float* gp = gu_out + ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
-#pragma unroll
-      for (int j = 0; j < CPW; ++j) {
+      auto element = [&](int j, float dact) {     // dact = gelu'(u) of this element
         const uint32_t off = xc[j & 3] + j * 128, offk = xk[j & 7] + j * 128;
-        const float gv = *reinterpret_cast<const float*>(tg + off);
-        const float uv = *reinterpret_cast<const float*>(tgk + offk);
-        r[j] = gv * gelu_grad_f(uv);
+        r[j] = *reinterpret_cast<const float*>(tg + off) * dact;
         if (WT) *reinterpret_cast<float*>(tg + off) = r[j];
         *reinterpret_cast<float*>(tgk + offk) = to_tf32(r[j]);
         if (!ZA) { *gp = r[j]; gp += S; }
         if (DB_REGS) db[j] += r[j];
+      };
+      if (u_is_du) {       // the forward stored the derivative: one multiply per element instead of the erf / density evaluation
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) element(j, *reinterpret_cast<const float*>(tgk + xk[j & 7] + j * 128));
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) element(j, gelu_grad_f(*reinterpret_cast<const float*>(tgk + xk[j & 7] + j * 128)));
       }
       fence_proxy_async();
       __syncwarp();
@@ -932,7 +946,7 @@ static int check_proj(const ProjArgs& pr, const char* who) {
     auto k = blk::block_tail_fwd_kernel<FF, PP, HH>;                                                                       \
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
     k<<<grid, blk::THREADS, smem, st>>>(h, SPEC, Wc, bc, u, hout, tpb, ntiles, S, BZ, LDZ, tile_order(), pr.Wp, pr.bp, pr.out, \
-                                        pr.n, lf.Win, lf.bin, lf.n);                                                       \
+                                        pr.n, lf.Win, lf.bin, lf.n, option_get(OPT_BLOCK_SAVES_DERIVATIVE));               \
   }
 
 static int block_tail_fwd_launch(const float* h, const float* spec, const float* Wc, const float* bc, float* u, float* hout,
@@ -1019,7 +1033,7 @@ int block_tail_bwd_launch(const float* g, const float* u, const float* h, const 
       auto k = blk::block_tail_bwd_kernel<GG, WW, HH, ZZ>;                                                                 \
       PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
       k<<<grid, blk::bwd_threads(ZZ), smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out,  \
-                                          lf.Win, lf.bin, lf.n, za_img, vg, ldz);                                          \
+                                          lf.Win, lf.bin, lf.n, za_img, vg, ldz, option_get(OPT_BLOCK_SAVES_DERIVATIVE));  \
     }
 #define PDEPHI_BWD_LAUNCH(GG, WW, HH) { if (vg) PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, true) else PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, false) }
     if (lf.Win) { if (t) PDEPHI_BWD_LAUNCH(false, true, true) else PDEPHI_BWD_LAUNCH(false, false, true) }

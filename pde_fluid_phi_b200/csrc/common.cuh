@@ -120,7 +120,7 @@ enum KernelId {
   K_RATIONAL_TRANSFER, K_RATIONAL_MIX_APPLY, K_COUNT
 };
 // run-time options (pdephi_set_option)
-enum { OPT_TF32_XSTAGE_SPLIT = 0, OPT_COUNT };
+enum { OPT_TF32_XSTAGE_SPLIT = 0, OPT_BLOCK_SAVES_DERIVATIVE = 1, OPT_COUNT };
 int option_get(int key);
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);

@@ -85,7 +85,9 @@ def _generic_block(activation, spectral: nn.Module, local: nn.Module, h: torch.T
     kernel (any width <= 64, the usual activations: pointwise_wide.cu); beyond that torch's own convolution and activation
     around the spectral layer, with both adds in the synthesis kernel's epilogue."""
     code = wide_activation_code(activation)
-    if code is not None and getattr(spectral, "slab", None) is None and wide_block_tail_supported(h, local):
+    # (also under a slab decomposition: the tail is pointwise, its weight gradients are slab-local sums like every other
+    # pointwise layer's, and the single-GPU and the slab run of one model then share the same fp32 arithmetic)
+    if code is not None and wide_block_tail_supported(h, local):
         return library_call(WideBlockTailFn, spectral(h), h, local.weight, local.bias, code)
     return activation(spectral.forward_fused(h, local(h)))
 

@@ -550,10 +550,24 @@ def test_fused_block_tail_vs_torch():
         ref.backward(g)
     finally:
         torch.backends.cudnn.allow_tf32 = old
-    u, hout = pf.block_tail_fwd(h.detach(), spec.detach(), conv.weight.detach().reshape(C, C).contiguous(), conv.bias.detach())
-    assert rel(hout, ref) < TOL["tf32"]
-    assert rel(u, (spec + conv(h) + h)) < TOL["tf32"]
-    gu, t, dW, db = pf.block_tail_bwd(g, u, h.detach(), conv.weight.detach().reshape(C, C).contiguous(), True)
+    Wc2 = conv.weight.detach().reshape(C, C).contiguous()
+    # the pre-activation itself (PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE off) ...
+    old_opt = _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, 0)
+    try:
+        u, hout = pf.block_tail_fwd(h.detach(), spec.detach(), Wc2, conv.bias.detach())
+        assert rel(hout, ref) < TOL["tf32"]
+        assert rel(u, (spec + conv(h) + h)) < TOL["tf32"]
+        gu0 = pf.block_tail_bwd(g, u, h.detach(), Wc2, True)[0]
+    finally:
+        _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, old_opt)
+    # ... and, by default, gelu'(u): all the backward needs u for; same bits in gu
+    assert _cabi.load().pdephi_get_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE) == 1
+    u, hout = pf.block_tail_fwd(h.detach(), spec.detach(), Wc2, conv.bias.detach())
+    upre = (spec + conv(h) + h).detach().double()
+    dref = 0.5 * (1 + torch.erf(upre / 2 ** 0.5)) + upre * torch.exp(-0.5 * upre * upre) / (2 * torch.pi) ** 0.5
+    assert rel(u, dref) < TOL["tf32"] and rel(hout, ref) < TOL["tf32"]
+    gu, t, dW, db = pf.block_tail_bwd(g, u, h.detach(), Wc2, True)
+    assert torch.equal(gu, gu0)
     assert rel(gu, spec.grad) < TOL["tf32"]                  # d/d spec = g * gelu'(u)
     assert rel(t, h.grad) < TOL["tf32"]                      # d/d h (conv + residual branches)
     assert rel(dW, conv.weight.grad.reshape(C, C)) < TOL["tf32"]
@@ -578,14 +592,20 @@ def test_fused_spectral_block_forward(B, grid, modes):
     rs = torch.rand(B * C, 4, device=DEV) + 0.5
     spec = pf.synthesis(Y, grid, mask, rs[:, 2], None, None, _cabi.FORWARD, _cabi.PREC_FP32).double()
     rest = torch.einsum("oc,bcxyz->boxyz", Wc.double(), h.double()) + bc.double().view(1, C, 1, 1, 1) + h.double()
-    u, hout = pf.block_spectral_fwd(Y, mask, rs[:, 2], h, Wc, bc)
-    assert float(spec.norm()) > float(rest.norm())
-    assert rel(u, spec + rest) < TOL["tf32"]
-    assert rel(u.double() - rest, spec) < TOL["tf32"]                        # the spectral branch on its own
-    assert rel(hout, torch.nn.functional.gelu(spec + rest)) < TOL["tf32"]
-    u2, _ = pf.block_spectral_fwd(Y, None, None, h, Wc, None)                   # no scaling, no bias (FNO3D's block)
-    spec2 = pf.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, _cabi.PREC_FP32).double()
-    assert rel(u2, spec2 + rest - bc.double().view(1, C, 1, 1, 1)) < TOL["tf32"]
+    old_opt = _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, 0)      # `u` = the pre-activation itself for this check
+    try:
+        u, hout = pf.block_spectral_fwd(Y, mask, rs[:, 2], h, Wc, bc)
+        assert float(spec.norm()) > float(rest.norm())
+        assert rel(u, spec + rest) < TOL["tf32"]
+        assert rel(u.double() - rest, spec) < TOL["tf32"]                        # the spectral branch on its own
+        assert rel(hout, torch.nn.functional.gelu(spec + rest)) < TOL["tf32"]
+        u2, _ = pf.block_spectral_fwd(Y, None, None, h, Wc, None)                   # no scaling, no bias (FNO3D's block)
+        spec2 = pf.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, _cabi.PREC_FP32).double()
+        assert rel(u2, spec2 + rest - bc.double().view(1, C, 1, 1, 1)) < TOL["tf32"]
+    finally:
+        _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, old_opt)
+    du, hout2 = pf.block_spectral_fwd(Y, mask, rs[:, 2], h, Wc, bc)              # default: gelu'(u) in its place
+    assert torch.equal(hout2, hout) and not torch.equal(du, u)
 
 
 def test_whole_block_model_on_the_fused_spectral_route():
