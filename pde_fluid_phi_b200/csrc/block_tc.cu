@@ -475,27 +475,46 @@ constexpr int B_STAGES = 2;
 // the kernel at 80, where the extra epilogue of the fused z analysis spilled ~300 bytes per thread onto the critical path of
 // the compute warps (3.67 / 4.04 / 3.97 ms for the first / middle / last block at 80 registers, 2.85 / 3.67 / 3.53 ms at 96).
 // The forward kernels and the plain backward keep four loaders (they are loader-bound: 2.49 -> 2.62 ms with three).
-__host__ __device__ constexpr int bwd_ld_warps(bool za) { return za ? 3 : LD_WARPS; }
-__host__ __device__ constexpr int bwd_threads(bool za) { return 32 * (1 + bwd_ld_warps(za) + EPI_WARPS); }
+// The last block's variant (GENG: its loader warps GENERATE the g' tile from gout) keeps four -- there the loaders set the pace
+// (3.57 ms with three, 3.35 ms with four at 80 registers, same box; forming g' in step 1 of the compute warps instead, with
+// three loaders and 96 registers: 3.43 ms).
+// The last block's variant (GENG: the g' tile is generated from gout, not staged) has two forms, chosen at compile time:
+// PDEPHI_GENG_STEP1 = 0: its LOADER warps generate the tile -- they then set the pace, so the variant keeps four loaders and
+// the 80-register allocation; = 1: the loaders stage the gout rows plain and the compute warps form g' = Wp^T gout in step 1
+// (4 FMAs per element), three loaders and 96 registers like the other ZA variants.  Same-box timings, cfg-2 shape: loaders x3
+// 3.57 ms, loaders x4 3.35-3.60 ms depending on what the register allocator spills at 80, step 1 3.43 ms; prefetching gout a
+// tile ahead in the loaders: 3.72-3.94 ms (its 16 registers spill in the compute warps).
+#ifndef PDEPHI_GENG_STEP1
+#define PDEPHI_GENG_STEP1 1
+#endif
+constexpr bool GENG_STEP1 = PDEPHI_GENG_STEP1 != 0;
+__host__ __device__ constexpr int bwd_ld_warps(bool za, bool geng) { return (za && (!geng || GENG_STEP1)) ? 3 : LD_WARPS; }
+__host__ __device__ constexpr int bwd_threads(bool za, bool geng) { return 32 * (1 + bwd_ld_warps(za, geng) + EPI_WARPS); }
 constexpr int AUX = 4096;        // per stage: the x rows as a K-major [8 rows][128 points] operand (LIFT_G)
-struct BSmem { uint32_t stage[B_STAGES], aux[B_STAGES], wt, red, wp, lift, bars, tmem_slot, total; };
-__host__ __device__ inline BSmem bwd_smem() {
+// lift_g (first block of a model whose input needs no gradient: no h tile, no t): a stage is two tiles instead of three and the
+// Wc^T image is not needed, so the ring runs THREE stages -- that variant moves 10 GB per launch and the two-stage chain
+// (load latency -> step 1 -> MMAs -> release) paced it at 4.0 TB/s.
+constexpr int B_MAXST = 3;
+struct BSmem { uint32_t stage[B_MAXST], aux[B_MAXST], wt, red, wp, lift, bars, tmem_slot, total; int nst, uoff; };
+__host__ __device__ inline BSmem bwd_smem(bool lift_g = false) {
   BSmem s; uint32_t o = 0;
-  for (int i = 0; i < B_STAGES; ++i) { s.stage[i] = o; o += 3 * TILE; }   // g' (-> gu, MN layout), h (K layout), u (-> gu, K layout)
-  for (int i = 0; i < B_STAGES; ++i) { s.aux[i] = o; o += AUX; }
-  s.wt = o; o += 2 * BOX;
+  s.nst = lift_g ? 3 : B_STAGES;
+  s.uoff = lift_g ? TILE : 2 * TILE;                                       // offset of the u (-> gu, K layout) tile in a stage
+  for (int i = 0; i < B_MAXST; ++i) { s.stage[i] = o; if (i < s.nst) o += lift_g ? 2 * TILE : 3 * TILE; }   // g' (-> gu, MN), [h (K),] u (-> gu, K)
+  for (int i = 0; i < B_MAXST; ++i) { s.aux[i] = o; if (i < s.nst) o += AUX; }
+  s.wt = o; o += lift_g ? 0 : 2 * BOX;
   s.red = o; o += 4 * C * 4;
   s.wp = o; o += C * 16;                                                   // GENG: [64] float4 columns of the projection weight
   s.lift = o; o += C * 16 + C * 4;                                         // GENH: lift weights + bias
-  s.bars = o; o += 128;
+  s.bars = o; o += 256;
   s.tmem_slot = o; o += 64;
   s.total = o;
   return s;
 }
 // GUREADY / TFULL / TEMPTY are per parity of the tile index (two each): the compute warps run step 1 of tile i+1
 // before the epilogue of tile i, so two tiles are in flight between them and the MMA warp.
-enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2 * B_STAGES + 2, BB_TEMPTY = 2 * B_STAGES + 4,
-       BB_DWDONE = 2 * B_STAGES + 6, BB_ZAFULL = 2 * B_STAGES + 7, BB_ZAEMPTY = 2 * B_STAGES + 9 };
+enum { BB_FULL = 0, BB_EMPTY = B_MAXST, BB_GUREADY = 2 * B_MAXST, BB_TFULL = 2 * B_MAXST + 2, BB_TEMPTY = 2 * B_MAXST + 4,
+       BB_DWDONE = 2 * B_MAXST + 6, BB_ZAFULL = 2 * B_MAXST + 7, BB_ZAEMPTY = 2 * B_MAXST + 9 };
 
 // GENG: the incoming gradient g' = Wp^T gout of the LAST block (the output projection's input gradient) is generated by the
 // loader warps from gout [B, n_out <= 4, S] instead of being read: the 4.3 GB g' is neither written nor read.  (Forming it
@@ -512,7 +531,7 @@ enum { BB_FULL = 0, BB_EMPTY = B_STAGES, BB_GUREADY = 2 * B_STAGES, BB_TFULL = 2
 // folded in) . gu^T -- and gu itself is never stored.  Vg has the layout of the per-axis route's z-analysed intermediate
 // ([B*64][Nx][Ny][ldz]), so the y and x stages follow unchanged (transforms_gen.cu: pdephi_block_spectral_bwd).
 template <bool GENG, bool WT, bool GENH, bool ZA>
-__global__ void __launch_bounds__(bwd_threads(ZA), 1)
+__global__ void __launch_bounds__(bwd_threads(ZA, GENG), 1)
 block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
                       const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
                       float* __restrict__ partial, long long tiles_per_batch, long long ntiles, long long S, int contiguous,
@@ -523,13 +542,14 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const BSmem L = bwd_smem();
+  const BSmem L = bwd_smem(GENH && !WT);
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   constexpr bool LIFT_G = GENH && !WT;
-  constexpr int NLW = bwd_ld_warps(ZA), NTHR = bwd_threads(ZA), BEPI0 = 1 + NLW;      // loader warps / threads / first compute warp
-  build_w_image(sm + L.wt, Wc, true, threadIdx.x, NTHR, TF32_COMP);      // rows c, K = o : (Wc^T)
+  constexpr int NST = LIFT_G ? 3 : B_STAGES, UOFF = LIFT_G ? TILE : 2 * TILE;     // ring depth, offset of the u tile in a stage
+  constexpr int NLW = bwd_ld_warps(ZA, GENG), NTHR = bwd_threads(ZA, GENG), BEPI0 = 1 + NLW;      // loader warps / threads / first compute warp
+  if (WT) build_w_image(sm + L.wt, Wc, true, threadIdx.x, NTHR, TF32_COMP);      // rows c, K = o : (Wc^T)
   if (GENG) {
     float* wp = reinterpret_cast<float*>(sm + L.wp);
     for (int i = threadIdx.x; i < C * MAXP; i += NTHR) wp[i] = ((i & 3) < NP) ? __ldg(Wp + (i & 3) * C + (i >> 2)) : 0.f;
@@ -548,11 +568,16 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   constexpr bool DB_ZA = ZA && !LIFT_G, DB_REGS = !ZA && !LIFT_G;
   if (LIFT_G) {
     float* z = reinterpret_cast<float*>(sm + L.aux[0]);
-    for (int i = threadIdx.x; i < B_STAGES * AUX / 4; i += NTHR) z[i] = (((i >> 5) & 7) == 7) ? 1.f : 0.f;
+    for (int i = threadIdx.x; i < NST * AUX / 4; i += NTHR) z[i] = (((i >> 5) & 7) == 7) ? 1.f : 0.f;
+  }
+
+  if (GENG && GENG_STEP1) {  // gout rows beyond NP are never staged and meet zero weights: keep them finite
+    float* z = reinterpret_cast<float*>(sm + L.aux[0]);
+    for (int i = threadIdx.x; i < NST * AUX / 4; i += NTHR) z[i] = 0.f;
   }
   if (threadIdx.x < 4 * C) reinterpret_cast<float*>(sm + L.red)[threadIdx.x] = 0.f;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar(BB_FULL + i), 32 * NLW); mbar_init(bar(BB_EMPTY + i), 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(bar(BB_FULL + i), 32 * NLW); mbar_init(bar(BB_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(BB_GUREADY + i), EPI_WARPS);
       mbar_init(bar(BB_TFULL + i), 1);
@@ -605,11 +630,13 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
     const int lw = warp - 1;
     auto issue = [&](long long it) {
       const long long t = tile0 + it * tstep;
-      const int s = (int)(it % B_STAGES);
-      mbar_wait(bar(BB_EMPTY + s), (uint32_t)(((it / B_STAGES) & 1) ^ 1));
+      const int s = (int)(it % NST);
+      mbar_wait(bar(BB_EMPTY + s), (uint32_t)(((it / NST) & 1) ^ 1));
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       float4 gv[MAXP];
-      if (GENG) {        // g_in = gout: this lane's four points of every output channel, issued ahead of the bulk copies
+      if (GENG && GENG_STEP1) {   // g_in = gout [B, NP <= 4, S]: its rows go plain into aux[s]; the compute warps form g' = Wp^T gout
+        if (lw == 0) stage_small_rows(base + L.aux[s], g_in, NP, b, s0, S, lane);
+      } else if (GENG) {          // ... or the loader warps do: this lane's four points of every output channel, issued ahead of the copies
 #pragma unroll
         for (int n = 0; n < MAXP; ++n)
           gv[n] = (n < NP) ? __ldg(reinterpret_cast<const float4*>(g_in + ((size_t)b * NP + n) * S + s0) + lane)
@@ -631,8 +658,8 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       } else {
         stage_rows<true, NLW>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
       }
-      stage_rows<true, NLW>(base + L.stage[s] + 2 * TILE, u_in, b, s0, S, lw, lane);
-      if (GENG) {
+      stage_rows<true, NLW>(base + L.stage[s] + UOFF, u_in, b, s0, S, lw, lane);
+      if (GENG && !GENG_STEP1) {
         uint8_t* dst = sm + L.stage[s];
 #pragma unroll
         for (int i = 0; i < (C + NLW - 1) / NLW; ++i) {
@@ -648,15 +675,15 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         }
       }
     };
-    for (int pre = 0; pre < B_STAGES - 1; ++pre) {
+    for (int pre = 0; pre < NST - 1; ++pre) {
       if (pre < my_tiles) issue(pre);
       cp_async_commit();
     }
     for (long long it = 0; it < my_tiles; ++it) {
-      cp_async_wait<B_STAGES - 2>();
+      cp_async_wait<NST - 2>();
       fence_proxy_async();
-      mbar_arrive(bar(BB_FULL + (int)(it % B_STAGES)));
-      if (it + B_STAGES - 1 < my_tiles) issue(it + B_STAGES - 1);
+      mbar_arrive(bar(BB_FULL + (int)(it % NST)));
+      if (it + NST - 1 < my_tiles) issue(it + NST - 1);
       cp_async_commit();
     }
   } else if (warp == 0) {
@@ -664,13 +691,13 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       constexpr uint32_t id_t = idesc_tf32(TS, C, 1, 0);     // T[128 x 64] = GU^T (MN-major A) . WcT (K-major B)
       constexpr uint32_t id_w = idesc_tf32(C, C, 0, 0);      // dW[64 x 64] += GU (K-major A) . H (K-major B)
       for (long long it = 0; it < my_tiles; ++it) {
-        const int s = (int)(it % B_STAGES);
+        const int s = (int)(it % NST);
         const int d = (int)(it & 1);
         const uint32_t ph = (uint32_t)((it >> 1) & 1);
         mbar_wait(bar(BB_GUREADY + d), ph);                  // gu written in place over g' (implies the tile landed)
         mbar_wait(bar(BB_TEMPTY + d), ph ^ 1);
         tc_fence_after();
-        const uint32_t gu = base + L.stage[s], hh = gu + TILE, guk = gu + 2 * TILE;
+        const uint32_t gu = base + L.stage[s], hh = gu + TILE, guk = gu + UOFF;
         if (WT) {
 #pragma unroll
           for (int k = 0; k < C / 8; ++k)
@@ -722,15 +749,28 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
     //      stays in registers (r) for the epilogue ----
     auto step1 = [&](long long it, float* r) {
       const long long t = tile0 + it * tstep;
-      const int s = (int)(it % B_STAGES), d = (int)(it & 1);
+      const int s = (int)(it % NST), d = (int)(it & 1);
       const long long b = t / tiles_per_batch, s0 = (t - b * tiles_per_batch) * TS;
       uint8_t* tg = sm + L.stage[s];
-      uint8_t* tgk = tg + 2 * TILE;
-      mbar_wait(bar(BB_FULL + s), (uint32_t)((it / B_STAGES) & 1));
+      uint8_t* tgk = tg + UOFF;
+      mbar_wait(bar(BB_FULL + s), (uint32_t)((it / NST) & 1));
       float* gp = gu_out + ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
+      float go[MAXP];
+      if (GENG && GENG_STEP1) {
+        const float* gs = reinterpret_cast<const float*>(sm + L.aux[s]) + 32 * q + lane;
+#pragma unroll
+        for (int n = 0; n < MAXP; ++n) go[n] = gs[n * TS];
+      }
       auto element = [&](int j, float dact) {     // dact = gelu'(u) of this element
         const uint32_t off = xc[j & 3] + j * 128, offk = xk[j & 7] + j * 128;
-        r[j] = *reinterpret_cast<const float*>(tg + off) * dact;
+        float gin;
+        if (GENG && GENG_STEP1) {
+          const float4 w = reinterpret_cast<const float4*>(sm + L.wp)[part * CPW + j];
+          gin = fmaf(w.w, go[3], fmaf(w.z, go[2], fmaf(w.y, go[1], w.x * go[0])));
+        } else {
+          gin = *reinterpret_cast<const float*>(tg + off);
+        }
+        r[j] = gin * dact;
         if (WT) *reinterpret_cast<float*>(tg + off) = r[j];
         *reinterpret_cast<float*>(tgk + offk) = to_tf32(r[j]);
         if (!ZA) { *gp = r[j]; gp += S; }
@@ -1021,7 +1061,7 @@ int block_tail_bwd_launch(const float* g, const float* u, const float* h, const 
     if (rc) return rc;
   }
   const long long tpb = S / blk::TS, ntiles = tpb * B;
-  const size_t smem = blk::bwd_smem().total + 1024;
+  const size_t smem = blk::bwd_smem(lf.Win != nullptr && t == nullptr).total + 1024;
   int sms = num_sms();
   if (sms > 1024) sms = 1024;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
@@ -1032,7 +1072,7 @@ int block_tail_bwd_launch(const float* g, const float* u, const float* h, const 
     {                                                                                                                      \
       auto k = blk::block_tail_bwd_kernel<GG, WW, HH, ZZ>;                                                                 \
       PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
-      k<<<grid, blk::bwd_threads(ZZ), smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out,  \
+      k<<<grid, blk::bwd_threads(ZZ, GG), smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out,  \
                                           lf.Win, lf.bin, lf.n, za_img, vg, ldz, option_get(OPT_BLOCK_SAVES_DERIVATIVE));  \
     }
 #define PDEPHI_BWD_LAUNCH(GG, WW, HH) { if (vg) PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, true) else PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, false) }

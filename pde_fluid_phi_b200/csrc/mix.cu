@@ -85,6 +85,8 @@ constexpr int MIX_THREADS = 128;
 constexpr int UT = 4;
 constexpr int BT = 8;
 
+// (Forcing four or five CTAs per SM with __launch_bounds__ was measured: 128 / 96 registers, 573 / 933 us against 497 us at
+// the compiler's own 158 registers and three CTAs.)
 template <int OP, int OQ, bool TR, int BTV = BT>   // BTV: batch entries per thread (fewer for small batches)
 __global__ void __launch_bounds__(MIX_THREADS)
 rational_mix_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float* __restrict__ P,
