@@ -471,8 +471,17 @@ def cfg3_dp_block(dev, rank: int, world: int, steps: int = 8):
         torch.nn.functional.mse_loss(model(x), y).backward()
         allreduce_gradients(params, world) if mode == "flat" else reducer.finish()
         grads[mode] = [p.grad.clone() for p in params]
+    # Two ranks: one addition per element, the two reductions agree bit for bit.  More ranks: NCCL picks its algorithm (ring /
+    # tree / NVLS, i.e. the order of the additions) by message size, and the flat buffer and the per-tensor in-place
+    # reductions have different sizes -- same sums up to fp32 rounding, which is what is checked.
     same = all(torch.equal(a, b) for a, b in zip(grads["flat"], grads["overlapped"]))
+    def _rel(a, b):
+        a, b = torch.view_as_real(a) if a.is_complex() else a, torch.view_as_real(b) if b.is_complex() else b
+        return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300))
+    worst = max(_rel(a, b) for a, b in zip(grads["overlapped"], grads["flat"]))
     res["overlapped_equals_flat"] = bool(same)
+    res["overlapped_vs_flat_max_relL2"] = float(f"{worst:.3e}")
+    same = same or worst < 1e-6
     res["samples_s"] = round(B * world / res["ms_per_step_overlapped"] * 1e3, 1)
     res["samples_s_flat"] = round(B * world / res["ms_per_step_flat"] * 1e3, 1)
     res["efficiency"] = round(res["ms_per_step_none"] / res["ms_per_step_overlapped"], 4)
@@ -480,8 +489,7 @@ def cfg3_dp_block(dev, rank: int, world: int, steps: int = 8):
     reducer.remove()
     del model, opt, x, y, grads
     torch.cuda.empty_cache()
-    if not (same and res["loss_finite"]):
-        raise SystemExit(f"cfg-3 data-parallel step failed its checks: {res}")
+    res["checks_ok"] = bool(same and res["loss_finite"])      # False: bench.py prints the line and exits with code 3
     return res
 
 
@@ -732,12 +740,13 @@ def run_native(args):
         try:
             slab = slab_block(dev, rank, world, args.precision if args.precision in ("tf32", "fp32") else "tf32")
             blocks_ok = blocks_ok and slab.get("parity_ok", True)
-        except Exception as e:      # noqa: BLE001 -- reported in the line
+        except BaseException as e:  # noqa: BLE001 -- SystemExit included: reported in the line, never instead of the line
             slab = {"error": f"{type(e).__name__}: {e}"}
             blocks_ok = False
         try:
             cfg3 = cfg3_dp_block(dev, rank, world)
-        except Exception as e:      # noqa: BLE001
+            blocks_ok = blocks_ok and cfg3.get("checks_ok", True)
+        except BaseException as e:  # noqa: BLE001
             cfg3 = {"error": f"{type(e).__name__}: {e}"}
             blocks_ok = False
         dog.cancel()
