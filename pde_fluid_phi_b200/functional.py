@@ -529,15 +529,19 @@ def synthesis_x(Z: torch.Tensor, grid, mode_scale, row_scale, precision: int) ->
     return T
 
 
-def synthesis_zy(T: torch.Tensor, mx: int, grid_local, addend0, addend1, direction: int, precision: int, nx_total: int):
-    """(y,z) stages of K3 on an x slab: T [B,C,Nxl,my,mzh] complex64 -> out [B,C,Nxl,Ny,Nz] float32 (+ addends)."""
+def synthesis_zy(T: torch.Tensor, mx: int, grid_local, addend0, addend1, direction: int, precision: int, nx_total: int, out=None):
+    """(y,z) stages of K3 on an x slab: T [B,C,Nxl,my,mzh] complex64 -> out [B,C,Nxl,Ny,Nz] float32 (+ addends).
+    out: a contiguous [B,C,Nxl,Ny,Nz] tensor (e.g. a channel chunk of the whole result) to write into."""
     T = T.contiguous()
     B, C, Nxl, my, mzh = T.shape
     a0 = addend0.contiguous() if addend0 is not None else None
     a1 = addend1.contiguous() if addend1 is not None else None
     with _cabi.on_device(T.device):
         plan = _cabi.get_plan(T.device.index, tuple(grid_local), (mx, my, mzh), (nx_total, 0))
-        out = torch.empty((B, C, *grid_local), dtype=torch.float32, device=T.device)
+        if out is None:
+            out = torch.empty((B, C, *grid_local), dtype=torch.float32, device=T.device)
+        elif tuple(out.shape) != (B, C, *grid_local) or not out.is_contiguous():
+            raise ValueError("synthesis_zy: `out` must be a contiguous [B,C,Nxl,Ny,Nz] tensor")
         _run_stages("synthesis", plan, T, out, B * C, direction, precision, _cabi.STAGES_ZY, a0, a1)
     return out
 
@@ -563,6 +567,14 @@ def exchange_ky_to_x(U: torch.Tensor, group, world: int) -> torch.Tensor:
     recv = torch.empty_like(send)
     dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=group)  # recv[j]: rank j's ky chunk
     return recv.permute(1, 2, 3, 0, 4, 5).reshape(B, C, nxl, world * myl, mzh)
+
+
+# The all-to-all slab route can move each exchange in this many groups of volumes, transposing group g on a side stream while
+# the stage kernels of group g+1 run.  Off (1) by default: measured on the cfg-5 layer at 2 GPUs with 4 groups the transposes
+# did overlap (1.05 of their 1.42 ms), but the stage kernels -- persistent, one CTA per SM -- lost 1.24 ms to the NCCL kernels
+# they then share SMs with and to the smaller launches: 7.04 ms against 6.88 ms unpipelined.
+SLAB_PIPELINE_GROUPS = 1
+_comm_streams = {}
 
 
 class _Slab:
@@ -591,6 +603,20 @@ class _Slab:
     def sharded(self) -> bool:
         return self.mode == "alltoall"
 
+    def _groups(self, volumes: int, cuda: bool) -> int:
+        """Groups of volumes the all-to-all route is pipelined over (SLAB_PIPELINE_GROUPS; 1 = the plain three-step form)."""
+        g = SLAB_PIPELINE_GROUPS if cuda else 1
+        while g > 1 and (volumes % g or volumes // g < 4):
+            g //= 2
+        return max(g, 1)
+
+    @staticmethod
+    def _comm_stream(device):
+        st = _comm_streams.get(device.index)
+        if st is None:
+            st = _comm_streams[device.index] = torch.cuda.Stream(device=device)
+        return st
+
     def local_modes(self, t: torch.Tensor, modes_h, lead: int = 0) -> torch.Tensor:
         """This rank's ky chunk of a per-mode table [..lead dims.., mx*my*mzh] (flattened modes) as a contiguous copy."""
         mx, my, mzh = modes_h
@@ -607,16 +633,73 @@ class _Slab:
             if self.active:
                 _allreduce_modes(X, self.group)     # partial sums over the x slabs -> every rank holds the full modes
             return X
-        T = analysis_zy(x, modes_h, direction, precision, self.nx_total)
-        T = exchange_x_to_ky(T, self.group, self.world)
-        return analysis_x(T, modes_h[0], (self.nx_total, x.shape[3], x.shape[4]), precision)
+        B, C = x.shape[:2]
+        G = self._groups(B * C, x.is_cuda)
+        if G == 1:
+            T = analysis_zy(x, modes_h, direction, precision, self.nx_total)
+            T = exchange_x_to_ky(T, self.group, self.world)
+            return analysis_x(T, modes_h[0], (self.nx_total, x.shape[3], x.shape[4]), precision)
+        # Pipelined over groups of volumes: the transpose of group g (its two permute copies and the NCCL all-to-all, on a side
+        # stream) runs under the (z,y) stage of group g+1; only the last group's transpose is exposed before the x stages.
+        main, comm = torch.cuda.current_stream(), self._comm_stream(x.device)
+        xv = x.contiguous().reshape(1, B * C, *x.shape[2:])
+        landed = []
+        for xc in xv.chunk(G, dim=1):
+            T = analysis_zy(xc, modes_h, direction, precision, self.nx_total)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                R = exchange_x_to_ky(T, self.group, self.world)
+                T.record_stream(comm)
+                done = torch.cuda.Event()
+                done.record(comm)
+            landed.append((R, done))
+        parts = []
+        for R, done in landed:
+            main.wait_event(done)
+            R.record_stream(main)
+            parts.append(analysis_x(R, modes_h[0], (self.nx_total, x.shape[3], x.shape[4]), precision))
+        X = torch.cat(parts, dim=1)
+        return X.reshape(B, C, *X.shape[2:])
 
     def synthesis(self, Z, grid, mode_scale, row_scale, add0, add1, direction, precision):
         if not self.sharded:
             return synthesis(Z, grid, mode_scale, row_scale, add0, add1, direction, precision, self.plan)
-        U = synthesis_x(Z, (self.nx_total, grid[1], grid[2]), mode_scale, row_scale, precision)
-        U = exchange_ky_to_x(U, self.group, self.world)
-        return synthesis_zy(U, Z.shape[2], grid, add0, add1, direction, precision, self.nx_total)
+        B, C = Z.shape[:2]
+        G = self._groups(B * C, Z.is_cuda)
+        if G == 1:
+            U = synthesis_x(Z, (self.nx_total, grid[1], grid[2]), mode_scale, row_scale, precision)
+            U = exchange_ky_to_x(U, self.group, self.world)
+            return synthesis_zy(U, Z.shape[2], grid, add0, add1, direction, precision, self.nx_total)
+        # the mirror pipeline: x stage of group g+1 under the transpose of group g, (y,z) stages as the groups land, each
+        # writing its channel chunk of the result in place
+        main, comm = torch.cuda.current_stream(), self._comm_stream(Z.device)
+        Zv = Z.contiguous().reshape(1, B * C, *Z.shape[2:])
+        out = torch.empty((1, B * C, *grid), dtype=torch.float32, device=Z.device)
+        a0 = add0.contiguous().reshape(1, B * C, *grid) if add0 is not None else None
+        a1 = add1.contiguous().reshape(1, B * C, *grid) if add1 is not None else None
+        n = (B * C) // G
+        landed = []
+        for g, Zc in enumerate(Zv.chunk(G, dim=1)):
+            rs = row_scale[g * n:(g + 1) * n] if row_scale is not None else None
+            U = synthesis_x(Zc, (self.nx_total, grid[1], grid[2]), mode_scale, rs, precision)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                R = exchange_ky_to_x(U, self.group, self.world)
+                U.record_stream(comm)
+                done = torch.cuda.Event()
+                done.record(comm)
+            landed.append((R, done))
+        for g, (R, done) in enumerate(landed):
+            main.wait_event(done)
+            R.record_stream(main)
+            sl = slice(g * n, (g + 1) * n)
+            synthesis_zy(R, Z.shape[2], grid, a0[:, sl] if a0 is not None else None, a1[:, sl] if a1 is not None else None,
+                         direction, precision, self.nx_total, out=out[:, sl])
+        return out.reshape(B, C, *grid)
 
     def complete_stats(self, stats, eps: float):
         """Sharded modes: each rank's {a, b} are sums over its ky chunk (+eps); sum them over the group, redo s."""
