@@ -275,6 +275,21 @@ int pdephi_block_spectral_bwd(pdephi_plan_t plan, const float* g, const float* u
                               const float* bin, int n_in, float* G, void* tail_workspace, size_t tail_workspace_bytes,
                               void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
 
+/* ---- fused block forward that also starts the NEXT layer's analysis ---------------------------------------------------------
+ * pdephi_block_spectral_fwd_z = pdephi_block_spectral_fwd (Win == NULL) or pdephi_block_spectral_lift_fwd, plus: the z stage of
+ * the FORWARD analysis of the block's output hout runs inside the kernel (the epilogue also writes hout, rounded to TF32, into a
+ * K-major tile; one more tcgen05 contraction against a TMEM-resident twiddle operand) and leaves vz, the per-axis route's
+ * z-analysed intermediate [B*C][Nx*Ny][ldz] (pdephi_block_spectral_vz_bytes).  pdephi_analysis_from_z finishes that analysis
+ * (y stage, split x stage): X [BC,mx,my,mzh] complex64 = what pdephi_analysis_r2c(hout, PDEPHI_FORWARD, TF32) returns to the
+ * TF32 gate -- the next block reads 1.2 GB instead of the 4.3 GB activation.  workspace of both: as pdephi_block_spectral_fwd. */
+size_t pdephi_block_spectral_vz_bytes(pdephi_plan_t plan, int B, int C);
+int pdephi_block_spectral_fwd_z(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                                long long row_scale_stride, const float* h, const float* Win, const float* bin, int n_in,
+                                const float* Wc, const float* bc, float* u, float* hout, float* vz, int B, int C, void* workspace,
+                                size_t workspace_bytes, pdephi_stream_t stream);
+int pdephi_analysis_from_z(pdephi_plan_t plan, const float* vz, float* X, long long BC, void* workspace, size_t workspace_bytes,
+                           pdephi_stream_t stream);
+
 /* ---- pointwise maps with up to 64 channels on BOTH sides, fp32 FFMA, any spatial size (pointwise_wide.cu) --------------
  * wide_linear: out[b,o,s] = bias[o] + sum_i W(o,i) x[b,i,s] (+ add0 + add1, each [B,Cout,S] or NULL);
  * W(o,i) = transpose_w ? W[i*Cout + o] : W[o*Cin + i].  Replaces rearrange -> nn.Linear -> rearrange for the lift / projection

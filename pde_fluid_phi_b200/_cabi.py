@@ -100,6 +100,11 @@ SIGNATURES = {
     "pdephi_block_spectral_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
                                           c_void_p, c_size_t, c_void_p]),
+    "pdephi_block_spectral_vz_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "pdephi_block_spectral_fwd_z": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_int,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
+                                            c_void_p]),
+    "pdephi_analysis_from_z": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p]),
     "pdephi_wide_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int,
                                    c_void_p]),
     "pdephi_wide_wgrad_workspace_bytes": (c_size_t, [c_int, c_longlong]),

@@ -220,12 +220,17 @@ constexpr int F_STAGES = 3;
 // the epilogue: every thread reduces its 16 channels, the four channel groups meet through shared memory.  The separate
 // projection kernel and its 4.3 GB read of h' disappear (h' is still written: the projection's weight gradient reads it).
 constexpr int MAXP = 4;
-struct FSmem { uint32_t stage[F_STAGES], w, bz, bias, wp, red, lift, bars, tmem_slot, total; };
-__host__ __device__ inline FSmem fwd_smem(bool fused, bool proj = false, bool genh = false) {
+// ZF: the z stage of the NEXT layer's forward analysis runs inside this kernel, on the block's output h' = gelu(u): the
+// epilogue threads also write h' (rounded to TF32) into a K-major tile, and  D'[128 x 64 ch] = A (TMEM-resident, rows
+// 2 kz + (re | im) of e^{-i theta}) . h'^T  leaves the per-axis route's z-analysed intermediate Vh [B*64][Nx*Ny][ldz] -- the
+// next block's analysis then reads 1.2 GB instead of the 4.3 GB activation (mirror of the fused backward, ZA).
+struct FSmem { uint32_t stage[F_STAGES], w, bz, bias, wp, red, lift, hk, bars, tmem_slot, total; };
+__host__ __device__ inline FSmem fwd_smem(bool fused, bool proj = false, bool genh = false, bool zf = false) {
   FSmem s; uint32_t o = 0;
   for (int i = 0; i < F_STAGES; ++i) { s.stage[i] = o; o += fused ? TILE + 2 * BOX : 2 * TILE; }
   s.w = o; o += 2 * BOX;
   s.bz = o; o += fused ? 2 * TS * 128 : 0;
+  s.hk = o; o += zf ? TILE : 0;                            // ZF: h' as a K-major [64 ch][128 points] operand tile (1024-aligned here)
   s.bias = o; o += 256;
   s.wp = o; o += proj ? C * 16 + 16 : 0;                   // [64] float4 (w_0..w_3 of channel c) + bias float4
   s.red = o; o += proj ? 2 * 4 * MAXP * TS * 4 : 0;        // [tile parity][channel group][output][point]
@@ -235,21 +240,23 @@ __host__ __device__ inline FSmem fwd_smem(bool fused, bool proj = false, bool ge
   s.total = o;
   return s;
 }
-enum { FB_FULL = 0, FB_EMPTY = F_STAGES, FB_DFULL = 2 * F_STAGES, FB_DEMPTY = 2 * F_STAGES + 2 };
+enum { FB_FULL = 0, FB_EMPTY = F_STAGES, FB_DFULL = 2 * F_STAGES, FB_DEMPTY = 2 * F_STAGES + 2, FB_HREADY = 2 * F_STAGES + 4,
+       FB_ZFFULL = 2 * F_STAGES + 5 };
 
-template <bool FUSED, bool PROJ, bool GENH>
+template <bool FUSED, bool PROJ, bool GENH, bool ZF = false>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ spec_in, const float* __restrict__ Wc,
                       const float* __restrict__ bc, float* __restrict__ u_out, float* __restrict__ h_out,
                       long long tiles_per_batch, long long ntiles, long long S, const float* __restrict__ bzimg, int ldz,
                       int contiguous, const float* __restrict__ Wp, const float* __restrict__ bp, float* __restrict__ proj_out,
-                      int NP, const float* __restrict__ Win, const float* __restrict__ bin, int n_in, int save_du) {
+                      int NP, const float* __restrict__ Win, const float* __restrict__ bin, int n_in, int save_du,
+                      const float* __restrict__ za_img, float* __restrict__ vh_out) {
   // save_du: u_out receives gelu'(u) -- all the backward needs u for -- instead of u (PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const FSmem L = fwd_smem(FUSED, PROJ, GENH);
+  const FSmem L = fwd_smem(FUSED, PROJ, GENH, ZF);
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -279,14 +286,37 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < F_STAGES; ++i) { mbar_init(bar(FB_FULL + i), LD_THREADS); mbar_init(bar(FB_EMPTY + i), 1 + EPI_WARPS); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(FB_DFULL + i), 1); mbar_init(bar(FB_DEMPTY + i), EPI_WARPS); }
+    mbar_init(bar(FB_HREADY), EPI_WARPS);
+    mbar_init(bar(FB_ZFFULL), 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(base + L.tmem_slot, 128);
+  constexpr uint32_t TMEM_COLS = ZF ? 512 : 128;
+  if (warp == 0) tmem_alloc(base + L.tmem_slot, TMEM_COLS);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
+  const uint32_t tmem_zf = tmem + 2 * C, tmem_a = tmem + 4 * C;      // ZF: accumulator D' [128 x 64], A image [128 x 128]
+  if (ZF) {
+    if (warp >= EPI0 && warp < EPI0 + 4) {       // four consecutive warps cover the four TMEM lane quarters
+      const int q = warp & 3;
+      const float* row = za_img + (size_t)(32 * q + lane) * TS;
+      for (int c0 = 0; c0 < TS; c0 += 32) {
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(row + c0) + j);
+          r[4 * j] = t4.x; r[4 * j + 1] = t4.y; r[4 * j + 2] = t4.z; r[4 * j + 3] = t4.w;
+        }
+        tmem_st32(tmem_a + ((uint32_t)(q * 32) << 16) + c0, r);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   // every CTA walks a CONTIGUOUS range of tiles (PDEPHI_TILE_ORDER=0: round-robin): consecutive tiles extend the same 64
   // channel rows, so the 512-byte pieces a tile writes to each row meet their neighbours in L2 within one tile time
   const long long tq = ntiles / gridDim.x, tr = ntiles % gridDim.x;
@@ -371,6 +401,24 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
         }
         mma_commit(bar(FB_EMPTY + s));
         mma_commit(bar(FB_DFULL + d));
+        if (ZF && it > 0) {      // z analysis of the PREVIOUS tile's h' (its epilogue has written the operand tile by now)
+          constexpr uint32_t id_z = idesc_tf32(TS, C, 0, 0);
+          mbar_wait(bar(FB_HREADY), (uint32_t)((it - 1) & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < TS / 8; ++k)
+            mma_ts(tmem_zf, tmem_a + 8 * k, umma_desc(base + L.hk + (k >> 2) * BOX + (k & 3) * 32, 1024), id_z, k ? 1u : 0u);
+          mma_commit(bar(FB_ZFFULL));
+        }
+      }
+      if (ZF && my_tiles > 0) {
+        constexpr uint32_t id_z = idesc_tf32(TS, C, 0, 0);
+        mbar_wait(bar(FB_HREADY), (uint32_t)((my_tiles - 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TS / 8; ++k)
+          mma_ts(tmem_zf, tmem_a + 8 * k, umma_desc(base + L.hk + (k >> 2) * BOX + (k & 3) * 32, 1024), id_z, k ? 1u : 0u);
+        mma_commit(bar(FB_ZFFULL));
       }
     }
   } else {
@@ -385,6 +433,30 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
     uint32_t xc[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) xc[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 3) ^ r) & 3) << 5) + (lane & 7) * 4);
+    // ZF: offsets of this thread's elements in the K-major (16-byte-chunk swizzle) h' tile; the swizzle term depends on o & 7
+    uint32_t xk[ZF ? 8 : 1];
+    if (ZF) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) xk[r] = (uint32_t)(q * BOX + part * CPW * 128 + ((((lane >> 2) ^ r) & 7) << 4) + (lane & 3) * 4);
+    }
+    // rows kz' = 32 q + lane of D' (quarters 0 and 1: ldz <= 64) of tile `tz` -> Vh [B*64 volumes][tiles of a volume][ldz]
+    auto store_vh = [&](long long tz, uint32_t phase) {
+      mbar_wait(bar(FB_ZFFULL), phase);
+      tc_fence_after();
+      float z[CPW];
+      if (q < 2) {
+        tmem_ld16(tmem_zf + lane_base + part * CPW, z);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      if (q < 2 && 32 * q + lane < ldz) {
+        const long long b = tz / tiles_per_batch, tib = tz - b * tiles_per_batch;
+        float* vp = vh_out + (((size_t)b * C + part * CPW) * tiles_per_batch + tib) * ldz + 32 * q + lane;
+        const size_t cs = (size_t)tiles_per_batch * ldz;
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) vp[(size_t)j * cs] = z[j];
+      }
+    };
     for (long long it = 0; it < my_tiles; ++it) {
       const long long t = tile0 + it * tstep;
       const int s = (int)(it % F_STAGES), d = (int)(it & 1);
@@ -422,6 +494,8 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(FB_EMPTY + s));
+      // ZF: the previous tile's D' must be out of TMEM (and its MMAs done with the h' tile) before this tile overwrites the tile
+      if (ZF && it > 0) store_vh(t - tstep, (uint32_t)((it - 1) & 1));
       const size_t g0 = ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
       float* up = u_out + g0;
       float* hp = h_out + g0;
@@ -433,6 +507,7 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
         const float hv = gelu_both_f(u, du);
         __stcs(up, save_du ? du : u);
         *hp = hv;
+        if (ZF) *reinterpret_cast<float*>(sm + L.hk + xk[j & 7] + j * 128) = to_tf32(hv);
         if (PROJ) {
           const float4 w = reinterpret_cast<const float4*>(sm + L.wp)[part * CPW + j];
           pj[0] = fmaf(w.x, hv, pj[0]); pj[1] = fmaf(w.y, hv, pj[1]);
@@ -440,6 +515,11 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
         }
         up += S;
         hp += S;
+      }
+      if (ZF) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(FB_HREADY));
       }
       if (PROJ) {
         // two buffers by tile parity and one barrier per tile: a buffer is rewritten two tiles later, after every warp has
@@ -461,9 +541,28 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
       }
     }
   }
+  if (ZF && warp >= EPI0 && my_tiles > 0) {       // the last tile's D'
+    const int q = warp & 3, part = (warp - EPI0) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    mbar_wait(bar(FB_ZFFULL), (uint32_t)((my_tiles - 1) & 1));
+    tc_fence_after();
+    float z[CPW];
+    if (q < 2) {
+      tmem_ld16(tmem_zf + lane_base + part * CPW, z);
+      tmem_ld_wait();
+    }
+    if (q < 2 && 32 * q + lane < ldz) {
+      const long long tz = tile0 + (my_tiles - 1) * tstep;
+      const long long b = tz / tiles_per_batch, tib = tz - b * tiles_per_batch;
+      float* vp = vh_out + (((size_t)b * C + part * CPW) * tiles_per_batch + tib) * ldz + 32 * q + lane;
+      const size_t cs = (size_t)tiles_per_batch * ldz;
+#pragma unroll
+      for (int j = 0; j < CPW; ++j) vp[(size_t)j * cs] = z[j];
+    }
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -981,13 +1080,14 @@ static int check_proj(const ProjArgs& pr, const char* who) {
   return PDEPHI_OK;
 }
 
-#define PDEPHI_FWD_LAUNCH(FF, PP, HH, SPEC, BZ, LDZ)                                                                        \
+#define PDEPHI_FWD_LAUNCH_Z(FF, PP, HH, ZZ, SPEC, BZ, LDZ, ZAIMG, VH)                                                       \
   {                                                                                                                        \
-    auto k = blk::block_tail_fwd_kernel<FF, PP, HH>;                                                                       \
+    auto k = blk::block_tail_fwd_kernel<FF, PP, HH, ZZ>;                                                                   \
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
     k<<<grid, blk::THREADS, smem, st>>>(h, SPEC, Wc, bc, u, hout, tpb, ntiles, S, BZ, LDZ, tile_order(), pr.Wp, pr.bp, pr.out, \
-                                        pr.n, lf.Win, lf.bin, lf.n, option_get(OPT_BLOCK_SAVES_DERIVATIVE));               \
+                                        pr.n, lf.Win, lf.bin, lf.n, option_get(OPT_BLOCK_SAVES_DERIVATIVE), ZAIMG, VH);    \
   }
+#define PDEPHI_FWD_LAUNCH(FF, PP, HH, SPEC, BZ, LDZ) PDEPHI_FWD_LAUNCH_Z(FF, PP, HH, false, SPEC, BZ, LDZ, nullptr, nullptr)
 
 static int block_tail_fwd_launch(const float* h, const float* spec, const float* Wc, const float* bc, float* u, float* hout,
                                  int B, long long S, const ProjArgs& pr, const LiftArgs& lf, cudaStream_t st) {
@@ -1012,9 +1112,11 @@ static int block_tail_fwd_launch(const float* h, const float* spec, const float*
 
 // Block tail with the z stage of the synthesis fused in (transforms_gen.cu: pdephi_block_spectral_fwd).
 // V [B*S/128 tiles][64][ldz] float, bzimg = the plan's z-synthesis operand image for Nz = 128.
+// za_img / vh: additionally run the z stage of the next layer's FORWARD analysis on h' (ZF variants; not with the projection)
 int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const float* bzimg, const float* Wc, const float* bc,
                                 float* u, float* hout, int B, long long S, const float* Wp, const float* bp, float* proj_out,
-                                int n_out, const float* Win, const float* bin, int n_in, cudaStream_t st) {
+                                int n_out, const float* Win, const float* bin, int n_in, cudaStream_t st,
+                                const float* za_img, float* vh) {
   int rc = check_shape(B, blk::C, S, "block_spectral_fwd");
   if (rc) return rc;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -1027,12 +1129,16 @@ int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const f
   rc = check_lift(lf, &pr, "block_spectral_fwd");
   if (rc) return rc;
   const long long tpb = S / blk::TS, ntiles = tpb * B;
-  const bool proj = Wp != nullptr, genh = Win != nullptr;
-  const size_t smem = blk::fwd_smem(true, proj, genh).total + 1024;
+  const bool proj = Wp != nullptr, genh = Win != nullptr, zf = vh != nullptr;
+  if (zf && (proj || !za_img || (reinterpret_cast<uintptr_t>(za_img) & 15)))
+    return fail(PDEPHI_ERR_INVALID, "block_spectral_fwd: the fused z analysis of the output needs an operand image and no projection");
+  const size_t smem = blk::fwd_smem(true, proj, genh, zf).total + 1024;
   const int sms = num_sms();
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   ProfScope ps(K_BLOCK_SPECTRAL_FWD, st);
-  if (genh) PDEPHI_FWD_LAUNCH(true, false, true, V, bzimg, ldz)
+  if (zf && genh) PDEPHI_FWD_LAUNCH_Z(true, false, true, true, V, bzimg, ldz, za_img, vh)
+  else if (zf) PDEPHI_FWD_LAUNCH_Z(true, false, false, true, V, bzimg, ldz, za_img, vh)
+  else if (genh) PDEPHI_FWD_LAUNCH(true, false, true, V, bzimg, ldz)
   else if (proj) PDEPHI_FWD_LAUNCH(true, true, false, V, bzimg, ldz)
   else PDEPHI_FWD_LAUNCH(true, false, false, V, bzimg, ldz)
   PDEPHI_LAUNCH_CHECK("block_tail_fwd_kernel<fused>");

@@ -44,6 +44,7 @@ struct GenPlan {
   float* za[2];             // z analysis  B images [direction]
   float* zs[2];             // z synthesis B images [direction]
   float* za_plain;          // adjoint z analysis as a plain [128][128] TMEM-resident A operand (fused block backward; zN = 128 only)
+  float* za_plain_fwd;      // the same for the FORWARD direction (plain e^{-i theta}): z analysis of a block's output in the fused forward
   float* ya; float* ysc; float* yss;   // y axis: analysis A (plain [128][Ny]), synthesis cos / sin images
   float* xa; float* xsc; float* xss;   // x axis
   // split-TF32 (fp32-grade) variant of the route: lo parts of the axis images, stacked [hi | lo] z images per column block

@@ -1320,7 +1320,7 @@ int gen_plan_init(Plan* p) {
   const size_t n_ya = two_d ? 0 : (size_t)128 * p->Ny, n_ys = two_d ? 0 : (size_t)pad128(p->Ny) * g.mky;
   const size_t n_xa = (size_t)128 * p->Nx, n_xs = (size_t)pad128(p->Nx) * g.mkx;
   const size_t n_zap = (!two_d && g.zN == 128) ? (size_t)128 * 128 : 0;
-  const size_t total = (2 * n_za + 2 * n_zs + n_ya + 2 * n_ys + n_xa + 2 * n_xs + n_zap) * sizeof(float);
+  const size_t total = (2 * n_za + 2 * n_zs + n_ya + 2 * n_ys + n_xa + 2 * n_xs + 2 * n_zap) * sizeof(float);
   PDEPHI_CUDA(cudaMalloc(&p->gen_arena, total));
   PDEPHI_CUDA(cudaMemset(p->gen_arena, 0, total));
   float* f = (float*)p->gen_arena;
@@ -1329,6 +1329,7 @@ int gen_plan_init(Plan* p) {
   g.ya = f; f += n_ya; g.ysc = f; f += n_ys; g.yss = f; f += n_ys;
   g.xa = f; f += n_xa; g.xsc = f; f += n_xs; g.xss = f; f += n_xs;
   g.za_plain = n_zap ? f : nullptr; f += n_zap;
+  g.za_plain_fwd = n_zap ? f : nullptr; f += n_zap;
   const double inv_total = 1.0 / ((double)p->Nx_total * p->Ny * p->Nz);
   const int nyq = (!two_d && p->Nz % 2 == 0 && p->mzh - 1 == p->Nz / 2) ? p->Nz / 2 : -1;
   const double comp = 1.0;                    // truncation bias of the data operands: undone in the epilogues (PDEPHI_GEN_COMP)
@@ -1342,6 +1343,7 @@ int gen_plan_init(Plan* p) {
   genimg(g.zs[0], 1, g.zN, NKBK * 32, g.zN, 0, g.zm, wnorm);  // synthesis FORWARD: c_k / total
   genimg(g.zs[1], 1, g.zN, NKBK * 32, g.zN, 0, g.zm, 0);      // synthesis ADJOINT: plain
   if (g.za_plain) genimg(g.za_plain, 5, 128, 128, g.zN, 0, g.zm, wnorm);   // analysis ADJOINT, rows >= 2 zm zero
+  if (g.za_plain_fwd) genimg(g.za_plain_fwd, 5, 128, 128, g.zN, 0, g.zm, 0);   // analysis FORWARD
   if (!two_d) {
     genimg(g.ya, 2, 128, p->Ny, p->Ny, 0, p->my, 0);
     genimg(g.ysc, 3, pad128(p->Ny), g.mky, p->Ny, 0, p->my, 0);
@@ -1730,7 +1732,8 @@ int synthesis_gen(const Plan* p, const float2* Z, float* out, const float* add0,
 
 int block_tail_fwd_fused_launch(const float* h, const float* V, int ldz, const float* bzimg, const float* Wc, const float* bc,
                                 float* u, float* hout, int B, long long S, const float* Wp, const float* bp, float* proj_out,
-                                int n_out, const float* Win, const float* bin, int n_in, cudaStream_t st);
+                                int n_out, const float* Win, const float* bin, int n_in, cudaStream_t st,
+                                const float* za_img, float* vh);
 
 // The fused block forward is available when the per-axis kernels cover the shape and a 128-point tile of the block
 // tail is exactly one z line.
@@ -1756,7 +1759,8 @@ extern "C" size_t pdephi_block_spectral_fwd_workspace_bytes(pdephi_plan_t plan, 
 static int block_spectral_run(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
                               long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u, float* hout,
                               const float* Wp, const float* bp, int n_out, float* proj_out, const float* Win, const float* bin,
-                              int n_in, int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream);
+                              int n_in, int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream,
+                              float* vz = nullptr);
 
 extern "C" int pdephi_block_spectral_fwd(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
                                          long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u,
@@ -1842,10 +1846,57 @@ extern "C" int pdephi_block_spectral_bwd(pdephi_plan_t plan, const float* g, con
                              gp.xa_lo, gp.xa_st, st);
 }
 
+// ---- the z stage of the NEXT layer's forward analysis inside the fused forward (vz), and the analysis from it ----
+extern "C" size_t pdephi_block_spectral_vz_bytes(pdephi_plan_t plan, int B, int C) {
+  const Plan* p = (const Plan*)plan;
+  if (!p || !block_spectral_ok(p, C) || !p->g.za_plain_fwd || B <= 0) return 0;
+  return (size_t)B * C * p->Nx * p->Ny * p->g.ldz * sizeof(float);
+}
+
+extern "C" int pdephi_block_spectral_fwd_z(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
+                                           long long row_scale_stride, const float* h, const float* Win, const float* bin, int n_in,
+                                           const float* Wc, const float* bc, float* u, float* hout, float* vz, int B, int C,
+                                           void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
+  const Plan* p = (const Plan*)plan;
+  PDEPHI_REQUIRE(p && vz, "block_spectral_fwd_z: null pointer");
+  if (!block_spectral_ok(p, C) || !p->g.za_plain_fwd)
+    return fail(PDEPHI_ERR_UNSUPPORTED, "block_spectral_fwd_z: needs width 64, Nz = 128 and a shape of the per-axis tensor-core route");
+  return block_spectral_run(plan, Y, mode_scale, row_scale, row_scale_stride, h, Wc, bc, u, hout, nullptr, nullptr, 0, nullptr, Win,
+                            bin, n_in, B, C, workspace, workspace_bytes, stream, vz);
+}
+
+extern "C" int pdephi_analysis_from_z(pdephi_plan_t plan, const float* vz, float* X, long long BC, void* workspace,
+                                      size_t workspace_bytes, pdephi_stream_t stream) {
+  const Plan* p = (const Plan*)plan;
+  PDEPHI_REQUIRE(p && vz && X && BC > 0, "analysis_from_z: null pointer");
+  if (!p->gen_ok || !p->g.has_mid) return fail(PDEPHI_ERR_UNSUPPORTED, "analysis_from_z: not a shape of the per-axis tensor-core route");
+  const size_t need = gen_workspace_bytes(p, BC);
+  if (!workspace || workspace_bytes < need)
+    return fail(PDEPHI_ERR_WORKSPACE, "analysis_from_z: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const GenPlan& gp = p->g;
+  const GenWs w = gen_ws(p, BC);
+  char* wb = (char*)workspace;
+  float* W2 = (float*)(wb + w.w2);       // [BC, Nx, my, mzh] after the y stage
+  float* W2lo = (float*)(wb + w.w2lo);
+  const bool x_fused = xstage_analysis_tc3_ok(p);
+  const bool xsplit = !x_fused && gp.x3_ok != 0;
+  int rc;
+  if (!xsplit && plane_analysis_ok(p, p->Ny, gp.ldz, p->mzh))
+    rc = launch_plane_analysis(p, vz, BC * p->Nx, p->my, gp.ldz, p->mzh, (float2*)W2, gp.ya, K_GEN_AXIS_ANALYSIS, st);
+  else
+    rc = launch_axis_analysis(p, vz, BC * p->Nx, p->Ny, p->my, gp.ldz, p->mzh, (float2*)W2, gp.ya, gp.ya_st, K_GEN_AXIS_ANALYSIS, st,
+                              PDEPHI_GEN_COMP, 0, xsplit ? (float2*)W2lo : nullptr);
+  if (rc) return rc;
+  if (x_fused) return xstage_analysis_cols(p, (const float2*)W2, (float2*)X, BC, p->my * p->mzh, true, st);
+  return axis_analysis_stage(p, xsplit, W2, W2lo, BC, p->Nx, p->mx, 2 * p->my * p->mzh, p->my * p->mzh, (float2*)X, nullptr, gp.xa,
+                             gp.xa_lo, gp.xa_st, st);
+}
+
 static int block_spectral_run(pdephi_plan_t plan, const float* Y, const float* mode_scale, const float* row_scale,
                               long long row_scale_stride, const float* h, const float* Wc, const float* bc, float* u, float* hout,
                               const float* Wp, const float* bp, int n_out, float* proj_out, const float* Win, const float* bin,
-                              int n_in, int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream) {
+                              int n_in, int B, int C, void* workspace, size_t workspace_bytes, pdephi_stream_t stream, float* vz) {
   const Plan* p = (const Plan*)plan;
   PDEPHI_REQUIRE(p && Y && h && Wc && u && hout, "block_spectral_fwd: null pointer");
   if (!block_spectral_ok(p, C))
@@ -1880,5 +1931,5 @@ static int block_spectral_run(pdephi_plan_t plan, const float* Y, const float* m
                              K_GEN_AXIS_SYNTHESIS, st);
   if (rc) return rc;
   return block_tail_fwd_fused_launch(h, V, g.ldz, g.zs[PDEPHI_FORWARD], Wc, bc, u, hout, B, (long long)p->Nx * p->Ny * p->Nz, Wp, bp,
-                                     proj_out, n_out, Win, bin, n_in, st);
+                                     proj_out, n_out, Win, bin, n_in, st, vz ? g.za_plain_fwd : nullptr, vz);
 }

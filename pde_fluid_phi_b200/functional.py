@@ -358,9 +358,11 @@ def block_spectral_supported(h: torch.Tensor, modes_h, precision: int, width: in
         return bool(_cabi.load().pdephi_block_spectral_supported(plan, 64))
 
 
-def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None, lift=None):
+def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None, lift=None, want_vz: bool = False):
     """u = S(Y * mode_scale * row_scale) + (Wc h + bc) + h, hout = gelu(u): x / y stages of the synthesis as per-axis
-    tensor-core contractions, z stage inside the block-tail kernel.  head: see block_tail_fwd."""
+    tensor-core contractions, z stage inside the block-tail kernel.  head: see block_tail_fwd.
+    want_vz (not with `head`): a third result vz, the z stage of the FORWARD analysis of hout, computed inside the same kernel
+    (analysis_from_z(vz) == analysis(hout) to the TF32 gate): what the next block's spectral layer starts from."""
     B, C = Y.shape[:2]
     lib = _cabi.load()
     rs_stride = row_scale.stride(0) if row_scale is not None else 0
@@ -370,6 +372,15 @@ def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None, lift=None
         hout = torch.empty_like(u)
         nbytes = lib.pdephi_block_spectral_fwd_workspace_bytes(plan, B, C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+        if want_vz:
+            if head is not None:
+                raise ValueError("block_spectral_fwd: want_vz and head are exclusive (the last block has no next layer)")
+            vz = torch.empty(lib.pdephi_block_spectral_vz_bytes(plan, B, C) // 4, dtype=torch.float32, device=h.device)
+            Win, bin_ = lift if lift is not None else (None, None)
+            _cabi.check(lib.pdephi_block_spectral_fwd_z(plan, _p(Y), _p(mode_scale), _p(row_scale), rs_stride, _p(h), _p(Win), _p(bin_),
+                                                        Win.shape[1] if Win is not None else 0, _p(Wc), _p(bc), _p(u), _p(hout),
+                                                        _p(vz), B, C, _p(ws), nbytes, _stream()), "block_spectral_fwd_z")
+            return u, hout, vz
         if lift is not None:            # h is the model input x; the block's input Win x + bin is generated in the kernel
             Win, bin_ = lift
             _cabi.check(lib.pdephi_block_spectral_lift_fwd(plan, _p(Y), _p(mode_scale), _p(row_scale), rs_stride, _p(h), _p(Win),
@@ -386,6 +397,19 @@ def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None, lift=None
                                                        _p(u), _p(hout), _p(Wp), _p(bp), Wp.shape[0], _p(out), B, C, _p(ws),
                                                        nbytes, _stream()), "block_spectral_proj_fwd")
     return u, hout, out
+
+
+def analysis_from_z(vz: torch.Tensor, B: int, C: int, grid, modes_h) -> torch.Tensor:
+    """X [B,C,mx,my,mzh] complex64 from the z-analysed intermediate a fused block forward left (block_spectral_fwd(want_vz=True)):
+    the y stage and the split x stage of the forward analysis."""
+    lib = _cabi.load()
+    with _cabi.on_device(vz.device):
+        plan = _cabi.get_plan(vz.device.index, tuple(grid), tuple(modes_h))
+        X = torch.empty((B, C, *modes_h), dtype=torch.complex64, device=vz.device)
+        nbytes = lib.pdephi_block_spectral_fwd_workspace_bytes(plan, B, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=vz.device)
+        _cabi.check(lib.pdephi_analysis_from_z(plan, _p(vz), _p(X), B * C, _p(ws), nbytes, _stream()), "analysis_from_z")
+    return X
 
 
 def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None, write_t: bool = True, lift=None):
@@ -425,6 +449,13 @@ def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None, write_t: bool = Tr
 # kernel and gu never touches HBM (pdephi_block_spectral_bwd).  False: the block-tail backward writes gu and the fused (z,y)
 # analysis kernel reads it back (the route before this one; kept for A/B measurements and as the reference of the tests).
 FUSED_BLOCK_BACKWARD = True
+# The forward of a block on the fused route CAN also run the z stage of the NEXT block's analysis, on its output tile
+# (pdephi_block_spectral_fwd_z): the next block's spectral layer then starts from the 1.2 GB z-analysed intermediate instead of
+# reading the 4.3 GB activation.  Correct (same error as the (z,y) kernel, tests/test_parity_gpu.py) but OFF: the forward
+# kernel's epilogue warps are its bound, and the extra work there -- h' written a second time, as the operand tile; a wait for the
+# 16 MMAs between two tiles, because that tile is single-buffered (shared memory is full); 112 bytes of spills at the 80-register
+# cap -- costs 1.6 ms per launch (2.51 -> 4.12 ms) against the 0.4 ms the next block's analysis saves: 43.9 vs 41.5 ms per step.
+FUSED_FORWARD_ANALYSIS = False
 
 
 def block_spectral_bwd(g, u, h, Wc, modes_h, want_bias: bool, head_w=None, write_t: bool = True, lift=None):
@@ -1121,7 +1152,9 @@ class RationalBlockFn(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, h, P, Q, mask, monoP, monoQ, modes, eps, precision, Wc, bc, slab=None, Wp=None, bp=None, Win=None,
-                bin_=None, proj=None, cache=None):
+                bin_=None, proj=None, cache=None, vz_in=None, want_vz=False):
+        # vz_in: the z-analysed `h` the previous block's fused forward left (block_spectral_fwd(want_vz=True)): the analysis then
+        # starts from it.  want_vz: return (result, vz of this block's output) for the next block (vz is None off the fused route).
         # Wp / bp: the model's output projection, fused into this (the last) block: the result is then Wp h' + bp
         # Win / bin_: the model's input lift, taken into this (the first) block: `h` is then the model input x
         for t, n in ((h, "x"), (P, "P_coeffs"), (Q, "Q_coeffs"), (Wc, "conv weight")):
@@ -1141,6 +1174,8 @@ class RationalBlockFn(torch.autograd.Function):
             x_in, Win, Ax, X = _lift_forward(h, Win, bin_, modes_h, precision)
             h = x_in
             lift = (Win, bin_.contiguous() if bin_ is not None else None)
+        elif vz_in is not None and not sl.active:
+            X = analysis_from_z(vz_in, h.shape[0], h.shape[1], grid, modes_h)
         else:
             X = sl.analysis(h, modes_h, _cabi.FORWARD, _tf32_route(precision, "forward_analysis", h.device, grid, modes_h, sl))
         need_grad = any(ctx.needs_input_grad)
@@ -1149,8 +1184,12 @@ class RationalBlockFn(torch.autograd.Function):
                                            shard=(sl.rank, sl.world) if sl.sharded else None)
         stats = sl.complete_stats(stats, proj_eps) if energy else _unit_stats(stats)
         head = _head_tuple(Wp, bp)
+        vz = None
         if not sl.active and block_spectral_supported(h, modes_h, precision, Y.shape[1]):
-            res = block_spectral_fwd(Y, mask, stats[:, 2], h, Wc, bc, head, lift)    # `spec` never touches HBM
+            res = block_spectral_fwd(Y, mask, stats[:, 2], h, Wc, bc, head, lift,     # `spec` never touches HBM
+                                     want_vz=bool(want_vz) and head is None and FUSED_FORWARD_ANALYSIS)
+            if head is None and len(res) == 3:
+                vz = res[2]
         else:
             spec = sl.synthesis(Y, grid, mask, stats[:, 2], None, None, _cabi.FORWARD, precision)
             res = block_tail_fwd(h, spec, Wc, bc, head, lift)
@@ -1160,12 +1199,16 @@ class RationalBlockFn(torch.autograd.Function):
                                   *((Ax, Win, *((lift[1],) if lift[1] is not None else ())) if lifted else ()))
         ctx.meta = (modes_h, grid, (tuple(P.shape), tuple(Q.shape)), precision, bc is not None, sl, head is not None,
                     bp is not None, lifted, bin_ is not None)
+        if want_vz:
+            if vz is not None:
+                ctx.mark_non_differentiable(vz)
+            return hout, vz
         return res[2] if head else hout
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     @once_differentiable
-    def backward(ctx, g):
+    def backward(ctx, g, _gvz=None):
         X, Y, stats, R, Qe, mask, monoP, monoQ, u, h, Wc = ctx.saved_tensors[:11]
         modes_h, grid, coeff_shapes, precision, has_bias, sl, has_head, head_bias, lifted, lift_bias = ctx.meta
         g = g.contiguous()
@@ -1205,7 +1248,8 @@ class RationalBlockFn(torch.autograd.Function):
                 dh, dWin, dbin = _pointwise_linear_backward(x_in, Win, gh0, True, True, lift_bias)
         else:
             dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, prec_syn)
-        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin, None, None)
+        return (dh, dP, dQ, None, None, None, None, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin, None, None,
+                None, None)
 
 
 class ComplexBlockFn(torch.autograd.Function):
@@ -1213,7 +1257,7 @@ class ComplexBlockFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, h, W, modes, precision, Wc, bc, slab=None, Wp=None, bp=None, Win=None, bin_=None):
+    def forward(ctx, h, W, modes, precision, Wc, bc, slab=None, Wp=None, bp=None, Win=None, bin_=None, vz_in=None, want_vz=False):
         _require_cuda_f32(h, "x")
         _require_cuda_f32(W, "weights", complex_ok=True)
         h = h.contiguous()
@@ -1229,12 +1273,18 @@ class ComplexBlockFn(torch.autograd.Function):
             x_in, Win, Ax, X = _lift_forward(h, Win, bin_, modes_h, precision)
             h = x_in
             lift = (Win, bin_.contiguous() if bin_ is not None else None)
+        elif vz_in is not None and not sl.active:
+            X = analysis_from_z(vz_in, h.shape[0], h.shape[1], grid, modes_h)
         else:
             X = sl.analysis(h, modes_h, _cabi.FORWARD, _tf32_route(precision, "forward_analysis", h.device, grid, modes_h, sl))
         Y = complex_mix_fwd(X, Wl, modes_h[2])
         head = _head_tuple(Wp, bp)
+        vz = None
         if not sl.active and block_spectral_supported(h, modes_h, precision, Y.shape[1]):
-            res = block_spectral_fwd(Y, None, None, h, Wc, bc, head, lift)
+            res = block_spectral_fwd(Y, None, None, h, Wc, bc, head, lift,
+                                     want_vz=bool(want_vz) and head is None and FUSED_FORWARD_ANALYSIS)
+            if head is None and len(res) == 3:
+                vz = res[2]
         else:
             spec = sl.synthesis(Y, grid, None, None, None, None, _cabi.FORWARD, precision)
             res = block_tail_fwd(h, spec, Wc, bc, head, lift)
@@ -1242,12 +1292,16 @@ class ComplexBlockFn(torch.autograd.Function):
         ctx.save_for_backward(X, Wl, W, u, h, Wc, *((hout, head[0]) if head else ()),
                               *((Ax, Win, *((lift[1],) if lift[1] is not None else ())) if lifted else ()))
         ctx.meta = (modes_h, grid, precision, bc is not None, sl, head is not None, bp is not None, lifted, bin_ is not None)
+        if want_vz:
+            if vz is not None:
+                ctx.mark_non_differentiable(vz)
+            return hout, vz
         return res[2] if head else hout
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     @once_differentiable
-    def backward(ctx, g):
+    def backward(ctx, g, _gvz=None):
         X, Wl, W, u, h, Wc = ctx.saved_tensors[:6]
         modes_h, grid, precision, has_bias, sl, has_head, head_bias, lifted, lift_bias = ctx.meta
         g = g.contiguous()
@@ -1286,4 +1340,4 @@ class ComplexBlockFn(torch.autograd.Function):
                 dh, dWin, dbin = _pointwise_linear_backward(x_in, Win, gh0, True, True, lift_bias)
         else:
             dh = sl.synthesis(dX, grid, None, None, t, None, _cabi.ADJOINT, prec_syn)
-        return dh, dW, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin
+        return dh, dW, None, None, dWc.view_as(Wc), dbc, None, dWp, dbp, dWin, dbin, None, None

@@ -140,12 +140,12 @@ class RationalFourierOperator3D(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         gelu = self.activation is F.gelu
         last = len(self.rational_layers) - 1
-        out = None
+        out = vz = None
         first = 0
         if (gelu and self.fuse_lift and last > 0 and x.dim() == 5 and x.shape[1] == self.input_proj.in_features
                 and self.rational_layers[0].lifted_block_supported(x, self.local_convs[0], self.input_proj)):
             # the lift rides in the first block: its analysis and (x needs no gradient) its backward run in mode space
-            h = self.rational_layers[0].forward_block(x, self.local_convs[0], None, self.input_proj)
+            h, vz = self.rational_layers[0].forward_block(x, self.local_convs[0], None, self.input_proj, want_vz=True)
             first = 1
         else:
             h = _lift(x, self.input_proj)
@@ -153,12 +153,14 @@ class RationalFourierOperator3D(nn.Module):
             if i < first:
                 continue
             if gelu and spectral.block_supported(h, local):
+                # vz: the z stage of this block's forward analysis, left by the previous block's fused kernel (None off that route)
                 if i == last and self.fuse_head and head_supported(self.output_proj):
-                    out = spectral.forward_block(h, local, self.output_proj)   # ... and the output projection with it
+                    out = spectral.forward_block(h, local, self.output_proj, vz_in=vz)   # ... and the output projection with it
                 else:
-                    h = spectral.forward_block(h, local)      # whole block in the library (TF32 path, width 64)
+                    res = spectral.forward_block(h, local, vz_in=vz, want_vz=i < last)  # whole block in the library (width 64)
+                    h, vz = res if i < last else (res, None)
             else:
-                h = _generic_block(self.activation, spectral, local, h)
+                h, vz = _generic_block(self.activation, spectral, local, h), None
         if out is None:
             out = _lift(h, self.output_proj)
         return self.final_activation(out) if self.final_activation is not None else out
@@ -272,11 +274,11 @@ class FNO3D(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         gelu = self.activation is F.gelu
         last = len(self.spectral_layers) - 1
-        out = None
+        out = vz = None
         first = 0
         if (gelu and self.fuse_lift and last > 0 and x.dim() == 5 and x.shape[1] == self.input_proj.in_features
                 and self.spectral_layers[0].lifted_block_supported(x, self.local_layers[0], self.input_proj)):
-            h = self.spectral_layers[0].forward_block(x, self.local_layers[0], None, self.input_proj)
+            h, vz = self.spectral_layers[0].forward_block(x, self.local_layers[0], None, self.input_proj, want_vz=True)
             first = 1
         else:
             h = _lift(x, self.input_proj)
@@ -285,11 +287,12 @@ class FNO3D(nn.Module):
                 continue
             if gelu and spectral.block_supported(h, local):
                 if i == last and self.fuse_head and head_supported(self.output_proj):
-                    out = spectral.forward_block(h, local, self.output_proj)
+                    out = spectral.forward_block(h, local, self.output_proj, vz_in=vz)
                 else:
-                    h = spectral.forward_block(h, local)
+                    res = spectral.forward_block(h, local, vz_in=vz, want_vz=i < last)
+                    h, vz = res if i < last else (res, None)
             else:
-                h = _generic_block(self.activation, spectral, local, h)
+                h, vz = _generic_block(self.activation, spectral, local, h), None
         if out is None:
             out = _lift(h, self.output_proj)
         return self.final_activation(out) if self.final_activation is not None else out

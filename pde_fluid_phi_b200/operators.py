@@ -208,13 +208,15 @@ class RationalFourierLayer(nn.Module):
         return _lifted_ok(self, x, conv, lift)
 
     def forward_block(self, x: torch.Tensor, conv: nn.Conv3d, head: Optional[nn.Linear] = None,
-                      lift: Optional[nn.Linear] = None) -> torch.Tensor:
+                      lift: Optional[nn.Linear] = None, vz_in=None, want_vz: bool = False):
         """gelu(layer(x) + conv(x) + x): the whole block of rational_fourier.py:263-271 in the library
         (TF32 path, width 64): spectral layer, then the 1x1x1 convolution as a tcgen05 channel GEMM whose
         epilogue applies bias, both residual adds and the exact GELU.  `head`: the model's output projection, applied
         to the result inside the same kernel (the last block of the model): returns head(gelu(...)) channels-first.
         `lift`: the model's input lift; `x` is then the model input and the block starts from lift(x) (the first block:
-        its analysis and, when x needs no gradient, the lift's backward run in mode space -- functional._lift_forward)."""
+        its analysis and, when x needs no gradient, the lift's backward run in mode space -- functional._lift_forward).
+        `want_vz`: returns (result, vz) with vz the z stage of the forward analysis of the result, formed inside the block kernel
+        (None where that route does not apply); `vz_in`: that tensor from the previous block -- this block's analysis starts from it."""
         if lift is None:
             _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
         return library_call(RationalBlockFn, x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
@@ -222,7 +224,7 @@ class RationalFourierLayer(nn.Module):
                             self._precision_code(), conv.weight, conv.bias, self.slab,
                             head.weight if head is not None else None, head.bias if head is not None else None,
                             lift.weight if lift is not None else None, lift.bias if lift is not None else None,
-                            self._projection(), self._transfer_cache)
+                            self._projection(), self._transfer_cache, vz_in, bool(want_vz))
 
 
 class SpectralConv3D(nn.Module):
@@ -268,11 +270,11 @@ class SpectralConv3D(nn.Module):
         return _lifted_ok(self, x, conv, lift)
 
     def forward_block(self, x: torch.Tensor, conv: nn.Conv3d, head: Optional[nn.Linear] = None,
-                      lift: Optional[nn.Linear] = None) -> torch.Tensor:
-        """gelu(spectral_conv(x) + conv(x) + x): the whole block of models/fno3d.py:91-97 in the library; `head`, `lift` as
-        in RationalFourierLayer.forward_block."""
+                      lift: Optional[nn.Linear] = None, vz_in=None, want_vz: bool = False):
+        """gelu(spectral_conv(x) + conv(x) + x): the whole block of models/fno3d.py:91-97 in the library; `head`, `lift`, `vz_in`,
+        `want_vz` as in RationalFourierLayer.forward_block."""
         if lift is None:
             _check_input(x, self.in_channels, self.modes, "SpectralConv3D", self.slab)
         return library_call(ComplexBlockFn, x, self.weights, tuple(self.modes), self._precision_code(), conv.weight, conv.bias,
                             self.slab, head.weight if head is not None else None, head.bias if head is not None else None,
-                            lift.weight if lift is not None else None, lift.bias if lift is not None else None)
+                            lift.weight if lift is not None else None, lift.bias if lift is not None else None, vz_in, bool(want_vz))

@@ -38,6 +38,9 @@ cases = {
     "fwd middle <fused>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], h, W, b), 3 * act + V),
     "fwd first  <fused,lift>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], x, W, b, lift=(Win, bin_)), 2 * act + V + small),
     "fwd last   <fused,proj>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], h, W, b, head=(Wp, bp)), 3 * act + V + small),
+    # fused forward that also runs the z stage of the next layer's analysis on its output (vz out)
+    "fwdz middle <fused>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], h, W, b, want_vz=True), 3 * act + 2 * V),
+    "fwdz first  <fused,lift>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], x, W, b, lift=(Win, bin_), want_vz=True), 2 * act + 2 * V + small),
     "bwd middle": (lambda: pf.block_tail_bwd(g, u, h, W, True), 5 * act),
     "bwd first  <lift, no t>": (lambda: pf.block_tail_bwd(g, u, x, W, True, write_t=False, lift=(Win, bin_)), 3 * act + small),
     "bwd last   <proj>": (lambda: pf.block_tail_bwd(gout, u, h, W, True, head_w=Wp), 4 * act + small),

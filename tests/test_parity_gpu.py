@@ -1168,3 +1168,80 @@ def test_transfer_cache_hits_misses_and_data_writes():
     assert cache.misses == misses + 1 and "rational_mix_kernel" in rep5
     (o4,), _ = run()
     assert torch.equal(o4, o3)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused block forward that also runs the z stage of the next layer's analysis (pdephi_block_spectral_fwd_z)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lifted", [False, True])
+@pytest.mark.parametrize("B,grid,modes_h", [(2, (32, 128, 128), (16, 32, 17)), (1, (64, 128, 128), (5, 12, 20)),
+                                            (1, (128, 128, 128), (32, 32, 17))])
+def test_fused_forward_analysis_of_the_block_output(lifted, B, grid, modes_h):
+    """u and hout are bit-identical to the plain fused forward; analysis_from_z(vz) is the FORWARD analysis of hout: against the
+    fp32-grade (split-TF32) analysis at the TF32 gate, and no further from it than the single-pass (z,y) kernel is (x 1.5)."""
+    if lifted and grid[0] == 128:
+        pytest.skip("the lifted variant is covered at the smaller shapes")
+    torch.manual_seed(19)
+    C = 64
+    h = torch.randn(B, 3 if lifted else C, *grid, device=DEV)
+    hh = torch.empty(B, C, *grid, device=DEV)
+    assert pf.block_spectral_supported(hh, modes_h, _cabi.PREC_TF32)
+    n = float(np.prod(grid))
+    Y = torch.randn(B, C, *modes_h, device=DEV, dtype=torch.complex64) * (n / np.sqrt(np.prod(modes_h)))
+    Wc = torch.randn(C, C, device=DEV) * 0.1
+    bc = torch.randn(C, device=DEV)
+    lift = (torch.randn(C, 3, device=DEV) * 0.3, torch.randn(C, device=DEV) * 0.1) if lifted else None
+    u0, h0 = pf.block_spectral_fwd(Y, None, None, h, Wc, bc, lift=lift)
+    _cabi.profile(True, True)
+    u1, h1, vz = pf.block_spectral_fwd(Y, None, None, h, Wc, bc, lift=lift, want_vz=True)
+    X1 = pf.analysis_from_z(vz, B, C, grid, modes_h)
+    torch.cuda.synchronize()
+    rep = _cabi.profile_report(timed=False)
+    _cabi.profile(False, True)
+    assert "analysis_zy_tc_kernel" not in rep and rep.get("gen_axis_analysis_kernel", (0,))[0] == 1, rep
+    assert torch.equal(u1, u0) and torch.equal(h1, h0)
+    X_ref = pf.analysis(h0, modes_h, _cabi.FORWARD, _cabi.PREC_TF32X3)
+    X_old = pf.analysis(h0, modes_h, _cabi.FORWARD, _cabi.PREC_TF32)
+    e_new = rel(torch.view_as_real(X1), torch.view_as_real(X_ref))
+    e_old = rel(torch.view_as_real(X_old), torch.view_as_real(X_ref))
+    print(f"\nfused forward analysis [lifted={lifted}] X vs fp32-grade analysis of hout: fused {e_new:.2e}, (z,y) kernel {e_old:.2e}")
+    assert e_new < TOL["tf32"] and e_new < 1.5 * e_old + 1e-6
+
+
+def test_fused_forward_analysis_model_vs_plain_route():
+    """Whole width-64 model with the next layer's z analysis inside the block forward on and off: outputs and every parameter
+    gradient within the TF32 gate of each other; the analysis kernels that ran are the expected ones."""
+    torch.manual_seed(6)
+    modes, grid = (16, 32, 32), (32, 128, 128)
+    model = pb.RationalFourierOperator3D(modes=modes, width=64, n_layers=3).to(DEV).set_precision("tf32")
+    with torch.no_grad():
+        for layer in model.rational_layers:
+            q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+            layer.Q_coeffs.mul_(1e-4)
+            layer.Q_coeffs[..., 0, 0, 0] = q0
+            layer.P_coeffs.mul_(1e-2)
+    x = torch.randn(2, 3, *grid, device=DEV)
+    y = torch.randn(2, 3, *grid, device=DEV)
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        _cabi.profile(True, True)
+        out = model(x)
+        F.mse_loss(out, y).backward()
+        torch.cuda.synchronize()
+        rep = _cabi.profile_report(timed=False)
+        _cabi.profile(False, True)
+        return out.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters()}, rep
+
+    assert not pf.FUSED_FORWARD_ANALYSIS                        # measured slower (functional.py): an option, off by default
+    o0, g0, rep0 = run()
+    assert rep0.get("analysis_zy_tc_kernel", (0,))[0] == 2, rep0
+    pf.FUSED_FORWARD_ANALYSIS = True
+    try:
+        o1, g1, rep1 = run()
+    finally:
+        pf.FUSED_FORWARD_ANALYSIS = False
+    assert "analysis_zy_tc_kernel" not in rep1, rep1            # neither direction runs the (z,y) analysis kernel then
+    errs = {"out": rel(o1, o0), **{n: rel(g1[n], g0[n]) for n in g1}}
+    print("\nfused vs plain forward analysis (rel L2):", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < SELF_TOL["fused_block"][1], errs
