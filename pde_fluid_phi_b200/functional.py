@@ -21,10 +21,11 @@ from . import _cabi
 
 
 def _opaque(fn):
-    """torch.compile must treat a call into the library as one opaque eager op: dynamo cannot trace ctypes, and there is
-    nothing for it to fuse below this seam.  The reference wraps its models in torch.compile(mode='max-autotune')
-    (optimization/performance_optimization.py:466-486); with this the wrapper graph-breaks around the spectral layers
-    and runs the same kernels."""
+    """dynamo cannot trace ctypes, and there is nothing for it to fuse below this seam: an eager call into the library stays
+    one opaque op.  (When a model is traced by torch.compile -- the reference wraps its models in it,
+    optimization/performance_optimization.py:466-486 -- the modules do not come here at all: they route their spectral layers
+    through the torch.library custom ops of compile_ops.py, so the compiled model is a single graph.  This wrapper covers
+    what those ops do not: a direct call of one of the Functions below from traced user code graph-breaks around it.)"""
     disable = getattr(getattr(torch, "compiler", None), "disable", None)
     return disable(fn, recursive=True) if disable is not None else fn
 

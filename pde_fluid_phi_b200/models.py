@@ -22,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _cabi
+from . import compile_ops
 from .functional import (PointwiseLinearFn, WideBlockTailFn, head_supported, library_call, pointwise_linear_supported,
                          spectral_resample, wide_activation_code, wide_block_tail_supported)
 from .operators import RationalFourierLayer, SpectralConv3D
@@ -70,6 +71,8 @@ def _lift(x: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
         raise ValueError(f"expected a [batch, channels, Nx, Ny, Nz] field, got shape {tuple(x.shape)}")
     if x.shape[1] != linear.in_features:
         raise RuntimeError(f"input has {x.shape[1]} channels, the model was built for {linear.in_features}")
+    if compile_ops.compiling():      # torch.compile: the reference's own formulation, for the compiler to lower
+        return linear(x.permute(0, 2, 3, 4, 1)).permute(0, 4, 1, 2, 3)
     if pointwise_linear_supported(x, linear.weight):
         return library_call(PointwiseLinearFn, x, linear.weight, linear.bias)
     if x.is_cuda and x.dtype == torch.float32:
@@ -84,6 +87,8 @@ def _generic_block(activation, spectral: nn.Module, local: nn.Module, h: torch.T
     """activation(spectral(h) + local(h) + h) where the tcgen05 block kernels do not apply: the block tail as one fp32 library
     kernel (any width <= 64, the usual activations: pointwise_wide.cu); beyond that torch's own convolution and activation
     around the spectral layer, with both adds in the synthesis kernel's epilogue."""
+    if compile_ops.compiling():      # torch.compile: spectral layer = one custom op (adds in its epilogue), the rest is traced
+        return activation(spectral.forward_fused(h, local(h)))
     code = wide_activation_code(activation)
     # (also under a slab decomposition: the tail is pointwise, its weight gradients are slab-local sums like every other
     # pointwise layer's, and the single-GPU and the slab run of one model then share the same fp32 arithmetic)

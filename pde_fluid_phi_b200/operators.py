@@ -16,7 +16,7 @@ from typing import Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
-from . import _cabi
+from . import _cabi, compile_ops
 from .functional import (ComplexBlockFn, ComplexSpectralFn, RationalBlockFn, RationalSpectralFn, TransferCache, block_tail_supported,
                          library_call, monomial_exponents, monomial_table)
 
@@ -52,7 +52,7 @@ def get_grid(modes: Tuple[int, int, int], device: Union[str, torch.device] = "cp
 
 def _lifted_ok(layer, x: torch.Tensor, conv: nn.Module, lift: nn.Module) -> bool:
     from .functional import block_tail_supported_shape, lift_supported, pointwise_linear_supported
-    return (layer.slab is None and isinstance(lift, nn.Linear) and isinstance(x, torch.Tensor) and x.dim() == 5
+    return (not compile_ops.compiling() and layer.slab is None and isinstance(lift, nn.Linear) and isinstance(x, torch.Tensor) and x.dim() == 5
             and x.shape[1] == lift.in_features and lift.out_features == layer.in_channels
             and pointwise_linear_supported(x, lift.weight) and lift_supported(lift)
             and isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.groups == 1
@@ -186,6 +186,10 @@ class RationalFourierLayer(nn.Module):
         _check_input(x, self.in_channels, self.modes, "RationalFourierLayer", self.slab)
         if self.in_channels != self.out_channels:
             raise RuntimeError("RationalFourierLayer needs in_channels == out_channels (as the reference does)")
+        if self.slab is None and compile_ops.compiling():      # torch.compile: one opaque custom op, no graph break
+            return compile_ops.rational_spectral(x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
+                                                 self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
+                                                 self._precision_code(), skip0, residual, self._projection())
         return library_call(RationalSpectralFn, x, self.P_coeffs, self.Q_coeffs, self.stability_projection.decay_mask,
                                         self._mono_p, self._mono_q, tuple(self.modes), float(self.stability_eps),
                                         self._precision_code(), skip0, residual, self.slab, self._projection(), self._transfer_cache)
@@ -199,7 +203,9 @@ class RationalFourierLayer(nn.Module):
         return self._run(x, x_local, True)
 
     def block_supported(self, x: torch.Tensor, conv: nn.Module) -> bool:
-        return (isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.groups == 1
+        # (not while torch.compile traces: the fused block is an eager route; a traced model runs the spectral layer as a custom
+        # op with both adds in its epilogue and leaves the convolution and the activation to the compiler)
+        return (not compile_ops.compiling() and isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.groups == 1
                 and conv.in_channels == conv.out_channels == self.in_channels == self.out_channels
                 and block_tail_supported(x, self._precision_code()))
 
@@ -251,6 +257,8 @@ class SpectralConv3D(nn.Module):
         _check_input(x, self.in_channels, self.modes, "SpectralConv3D", self.slab)
         if residual and self.in_channels != self.out_channels:
             raise RuntimeError("fused residual needs in_channels == out_channels")
+        if self.slab is None and compile_ops.compiling():
+            return compile_ops.complex_spectral(x, self.weights, tuple(self.modes), self._precision_code(), skip0, residual)
         return library_call(ComplexSpectralFn, x, self.weights, tuple(self.modes), self._precision_code(), skip0, residual,
                                        self.slab)
 
@@ -262,7 +270,7 @@ class SpectralConv3D(nn.Module):
         return self._run(x, x_local, True)
 
     def block_supported(self, x: torch.Tensor, conv: nn.Module) -> bool:
-        return (isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.groups == 1
+        return (not compile_ops.compiling() and isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.groups == 1
                 and conv.in_channels == conv.out_channels == self.in_channels == self.out_channels
                 and block_tail_supported(x, self._precision_code()))
 

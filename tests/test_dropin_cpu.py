@@ -156,3 +156,29 @@ def test_fused_route_guards_are_host_side():
         layer._projection()
     layer.stability_projection = pb.StabilityProjection((4, 4, 4), eps=1e-3, energy_conserving=False)
     assert layer._projection() == (1e-3, False)
+
+
+@pytest.mark.parametrize("cls", ["rfno", "fno"])
+def test_models_trace_as_one_graph_under_torch_compile(cls):
+    """The reference wraps its models in torch.compile (optimization/performance_optimization.py:466-486).  While dynamo
+    traces, the mirror modules route their spectral layers through the pdephi_b200:: custom ops (compile_ops.py): the whole
+    model is ONE graph (fullgraph=True: no graph break), forward and backward.  Traced here on meta tensors -- no GPU needed:
+    the ops' fake implementations supply the shapes."""
+    import pde_fluid_phi_b200 as pb
+    torch.manual_seed(0)
+    kw = dict(modes=(4, 4, 4), width=8, n_layers=2)
+    model = (pb.RationalFourierOperator3D(**kw) if cls == "rfno" else pb.FNO3D(**kw)).to("meta")
+    graphs = []
+
+    def backend(gm, example_inputs):
+        graphs.append(gm)
+        return gm.forward
+
+    compiled = torch.compile(model, backend=backend, fullgraph=True)
+    out = compiled(torch.empty(2, 3, 8, 8, 8, device="meta"))
+    out.sum().backward()
+    assert tuple(out.shape) == (2, 3, 8, 8, 8) and len(graphs) == 1
+    targets = [str(n.target) for n in graphs[0].graph.nodes if n.op == "call_function"]
+    want = "rational_spectral_fwd" if cls == "rfno" else "complex_spectral_fwd"
+    assert sum(want in t for t in targets) == 2, targets                       # one opaque op per spectral layer
+    assert all(p.grad is not None and p.grad.shape == p.shape for p in model.parameters())

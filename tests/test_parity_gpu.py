@@ -1245,3 +1245,68 @@ def test_fused_forward_analysis_model_vs_plain_route():
     errs = {"out": rel(o1, o0), **{n: rel(g1[n], g0[n]) for n in g1}}
     print("\nfused vs plain forward analysis (rel L2):", {k: f"{v:.1e}" for k, v in errs.items()})
     assert max(errs.values()) < SELF_TOL["fused_block"][1], errs
+
+
+# ------------------------------------------------------------------------------------------------
+# torch.compile: the spectral layers as torch.library custom ops (compile_ops.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cls", ["rfno", "fno"])
+def test_compiled_model_matches_eager(cls):
+    """torch.compile(model, fullgraph=True) -- the reference's own wrapper (performance_optimization.py:466-486) -- runs the
+    spectral layers as pdephi_b200:: custom ops in one graph: outputs and every parameter gradient agree with the eager model
+    (same kernels for the spectral layers; the pointwise part is torch's on the compiled side)."""
+    torch.manual_seed(12)
+    kw = dict(modes=(8, 8, 8), width=16, n_layers=2)
+    model = (pb.RationalFourierOperator3D(**kw) if cls == "rfno" else pb.FNO3D(**kw)).to(DEV).set_precision("fp32")
+    if cls == "rfno":
+        with torch.no_grad():
+            for layer in model.rational_layers:
+                q0 = layer.Q_coeffs[..., 0, 0, 0].clone()
+                layer.Q_coeffs.mul_(1e-3)
+                layer.Q_coeffs[..., 0, 0, 0] = q0
+    x = torch.randn(2, 3, 32, 32, 32, device=DEV)
+    y = torch.randn(2, 3, 32, 32, 32, device=DEV)
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out_e = model(x)
+        F.mse_loss(out_e, y).backward()
+        ge = {n: p.grad.clone() for n, p in model.named_parameters()}
+        model.zero_grad(set_to_none=True)
+        compiled = torch.compile(model, backend="aot_eager", fullgraph=True)
+        _cabi.profile(True, True)
+        out_c = compiled(x)
+        F.mse_loss(out_c, y).backward()
+        torch.cuda.synchronize()
+        rep = _cabi.profile_report(timed=False)
+        _cabi.profile(False, True)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert any(k.startswith("analysis_zy") for k in rep) and any(k.startswith("synthesis_zy") for k in rep), rep   # library kernels ran
+    errs = {"out": rel(out_c, out_e), **{n: rel(p.grad, ge[n]) for n, p in model.named_parameters()}}
+    print(f"\ncompiled vs eager [{cls}] (rel L2):", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < 5e-5, errs
+
+
+def test_custom_ops_pass_opcheck():
+    """torch.library.opcheck: schema, fake implementation and autograd registration of the four custom ops."""
+    from pde_fluid_phi_b200 import compile_ops
+    torch.manual_seed(2)
+    C, modes, grid = 4, (4, 4, 4), (8, 8, 8)
+    layer = pb.RationalFourierLayer(C, C, modes).to(DEV)
+    conv = pb.SpectralConv3D(C, C, modes).to(DEV)
+    x = torch.randn(2, C, *grid, device=DEV, requires_grad=True)
+    skip = torch.randn(2, C, *grid, device=DEV)
+    tests = ("test_schema", "test_faketensor", "test_autograd_registration")
+    args = (x, layer.P_coeffs, layer.Q_coeffs, layer.stability_projection.decay_mask, layer._mono_p, layer._mono_q, list(modes), 1e-6,
+            _cabi.PREC_FP32, skip, True, 1e-6, True, True)
+    torch.library.opcheck(compile_ops.rational_spectral_fwd, args, test_utils=tests)
+    out, X, Y, stats, R, Qe = compile_ops.rational_spectral_fwd(*args)
+    torch.library.opcheck(compile_ops.rational_spectral_bwd,
+                          (torch.randn_like(out), X, Y, stats, R, Qe, layer.stability_projection.decay_mask, layer._mono_p,
+                           layer._mono_q, list(grid), _cabi.PREC_FP32, True, 4, 4, True), test_utils=("test_schema", "test_faketensor"))
+    cargs = (x, conv.weights, list(modes), _cabi.PREC_FP32, None, False)
+    torch.library.opcheck(compile_ops.complex_spectral_fwd, cargs, test_utils=tests)
+    o2, X2 = compile_ops.complex_spectral_fwd(*cargs)
+    torch.library.opcheck(compile_ops.complex_spectral_bwd, (torch.randn_like(o2), X2, conv.weights.detach(), list(grid), _cabi.PREC_FP32,
+                                                              False, True), test_utils=("test_schema", "test_faketensor"))
