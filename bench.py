@@ -195,7 +195,7 @@ NCU_NAME = {"analysis_zy_tc_kernel": "tc::analysis_zy_tc_kernel", "synthesis_zy_
             "block_tail_bwd_kernel": "blk::block_tail_bwd_kernel", "block_spectral_bwd_kernel": "blk::block_tail_bwd_kernel",
             "gen_axis_analysis_kernel": "gen::gen_plane_analysis_kernel", "rational_mix_kernel": "rational_mix_kernel",
             "mix_from_R_kernel": "mix_from_R_kernel", "rational_g_kernel": "rational_g_kernel",
-            "rational_dpq_kernel": "rational_dpq_kernel", "projection_stats_kernel": "projection_stats_kernel",
+            "rational_dpq_kernel": "rational_dpq", "projection_stats_kernel": "projection_stats_kernel",
             "projection_bwd_kernel": "projection_bwd_kernel", "gen_axis_synthesis_kernel": "gen::gen_axis_synthesis_kernel",
             "analysis_zy_tc3_kernel": "tc3::analysis_zy_tc3_kernel", "synthesis_zy_tc3_kernel": "tc3::synthesis_zy_tc3_kernel",
             "pointwise_wgrad_kernel": "pointwise_wgrad_kernel"}
