@@ -193,6 +193,16 @@ class TransferCache:
     def clear(self):
         self.__init__()
 
+    # a cache is never part of a copy or a pickle of its layer (torch.save(model), copy.deepcopy(model)): it is rebuilt on use
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    def __deepcopy__(self, memo):
+        return TransferCache()
+
     @staticmethod
     def _key(P, Q, monoP, eps, shard):
         return (P.data_ptr(), Q.data_ptr(), P._version, Q._version, tuple(P.shape), tuple(Q.shape), monoP.shape[-1], float(eps),

@@ -182,3 +182,19 @@ def test_models_trace_as_one_graph_under_torch_compile(cls):
     want = "rational_spectral_fwd" if cls == "rfno" else "complex_spectral_fwd"
     assert sum(want in t for t in targets) == 2, targets                       # one opaque op per spectral layer
     assert all(p.grad is not None and p.grad.shape == p.shape for p in model.parameters())
+
+
+def test_transfer_cache_is_not_copied_or_pickled():
+    """The layer's transfer-function cache (functional.TransferCache: R(k), Q(k)+eps of the last forward, hundreds of MB on
+    the device) is not part of a deepcopy or a pickle of the layer, and never part of the state_dict."""
+    import copy
+    import pickle
+    import pde_fluid_phi_b200 as pb
+    layer = pb.RationalFourierLayer(2, 2, (4, 4, 4))
+    layer._transfer_cache.R = torch.zeros(3)            # stand-in for a filled cache
+    layer._transfer_cache.key = ("k",)
+    assert not any("transfer" in k or k in ("R", "Qe") for k in layer.state_dict())
+    for clone in (copy.deepcopy(layer), pickle.loads(pickle.dumps(layer))):
+        assert clone._transfer_cache is not layer._transfer_cache
+        assert clone._transfer_cache.key is None and clone._transfer_cache.R is None
+        assert torch.equal(clone.P_coeffs, layer.P_coeffs)
