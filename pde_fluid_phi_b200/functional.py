@@ -1113,12 +1113,33 @@ class WideBlockTailFn(torch.autograd.Function):
 #   dW_in[c,j] = Re sum_{b,k} conj(A(x)[b,j,k]) dX[b,c,k] + ((I + Wc^T) G)[c,j],   G[o,j] = sum_{b,s} gu[b,o,s] x[b,j,s]
 #   db_in[c]   = N sum_b Re dX[b,c,0] + ((I + Wc^T) sum_{b,s} gu)[c]
 # without the adjoint synthesis (8.9 GB), without storing t (4.3 GB) and without gh0 ever existing.
+def _small_linear(x3, W, transpose_w: bool = False):
+    """out[b,o,s] = sum_c W(o,c) x3[b,c,s] on a contiguous real [B,Cin,S] tensor through the library's pointwise kernels
+    (pointwise.cu when one side has at most 8 channels and S % 4 == 0, pointwise_wide.cu otherwise): the few small products
+    around the lifted first block run in the library too, not in cuBLAS."""
+    B, Cin, S = x3.shape
+    Cout = W.shape[1] if transpose_w else W.shape[0]
+    lib = _cabi.load()
+    out = torch.empty((B, Cout, S), dtype=torch.float32, device=x3.device)
+    with _cabi.on_device(x3.device):
+        if _narrow(Cin, Cout, S):
+            _cabi.check(lib.pdephi_pointwise_linear(_p(x3), _p(W), _p(None), _p(out), B, Cin, Cout, S, 1 if transpose_w else 0,
+                                                    _stream()), "pointwise_linear(small)")
+        else:
+            _cabi.check(lib.pdephi_wide_linear(_p(x3), _p(W), None, None, None, _p(out), B, Cin, Cout, S, 1 if transpose_w else 0,
+                                               _stream()), "wide_linear(small)")
+    return out
+
+
 def _lift_forward(x, Win, bin_, modes_h, precision):
     x = x.contiguous()
     Win = Win.contiguous()
     S = x[0, 0].numel()
     Ax = analysis(x, modes_h, _cabi.FORWARD, _tf32_route(precision, "lift_analysis", x.device, x.shape[2:], modes_h))   # [B, Cin, mx, my, mzh]
-    X = torch.einsum("cj,bjxyz->bcxyz", Win.to(torch.complex64), Ax).contiguous()    # a few MB: glue, not a pass over a volume
+    B, Cin = Ax.shape[:2]
+    # X = W_in A(x): a real map applied to the (re, im) pairs of a few MB of modes -- the lift's own kernel on [B, Cin, 2M]
+    Xr = _small_linear(torch.view_as_real(Ax).reshape(B, Cin, -1), Win)
+    X = torch.view_as_complex(Xr.view(B, Win.shape[0], *modes_h, 2))
     if bin_ is not None:
         X[:, :, 0, 0, 0] += bin_ * float(S)
     return x, Win, Ax, X       # h0 = Win x + bin itself is generated tile by tile inside the block-tail kernels
@@ -1126,12 +1147,33 @@ def _lift_forward(x, Win, bin_, modes_h, precision):
 
 def _lift_backward(x, Ax, G, gsum, dX, Wc, has_bias):
     """(dW_in, db_in) from the first block's G = sum gu (x) x, gsum = sum gu (both from the block-tail backward) and dX (see
-    above); Wc [64,64] is the block's 1x1x1 conv weight.  A few 64 x 64 products: glue, not a pass over a volume."""
-    Cout = G.shape[0]
+    above); Wc [64,64] is the block's 1x1x1 conv weight.  A few 64 x 64 products and one skinny reduction over the modes, all
+    through the library's pointwise kernels."""
+    Cout, Cin = G.shape
     S = x[0, 0].numel()
-    A = Wc.reshape(Cout, Cout).t() + torch.eye(Cout, dtype=torch.float32, device=x.device)      # I + Wc^T
-    dWin = A @ G + torch.einsum("bjxyz,bcxyz->cj", Ax.conj(), dX).real
-    dbin = (A @ gsum + float(S) * dX[:, :, 0, 0, 0].real.sum(0)) if has_bias else None
+    B = Ax.shape[0]
+    lib = _cabi.load()
+    A = (Wc.reshape(Cout, Cout).t() + torch.eye(Cout, dtype=torch.float32, device=x.device)).contiguous()      # I + Wc^T
+    # Re sum_{b,k} conj(A(x)[b,j,k]) dX[b,c,k] = sum over the (re, im) pairs: the lift's weight-gradient kernel on [B, ., 2M]
+    Axr = torch.view_as_real(Ax).reshape(B, Cin, -1)
+    dXr = torch.view_as_real(dX.contiguous()).reshape(B, Cout, -1)
+    S2 = Axr.shape[2]
+    with _cabi.on_device(x.device):
+        mode_term = torch.empty((Cout, Cin), dtype=torch.float32, device=x.device)
+        if _narrow(Cin, Cout, S2):
+            nbytes = lib.pdephi_pointwise_wgrad_workspace_bytes(Cin, Cout, S2)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _cabi.check(lib.pdephi_pointwise_wgrad(_p(Axr), _p(dXr), _p(mode_term), _p(None), B, Cin, Cout, S2, _p(ws), nbytes,
+                                                   _stream()), "pointwise_wgrad(lift, mode space)")
+        else:
+            nbytes = lib.pdephi_wide_wgrad_workspace_bytes(B, S2)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _cabi.check(lib.pdephi_wide_wgrad(_p(Axr), _p(dXr), _p(mode_term), _p(None), B, Cin, Cout, S2, _p(ws), nbytes, _stream()),
+                        "wide_wgrad(lift, mode space)")
+    dWin = _small_linear(G.reshape(1, Cout, Cin).contiguous(), A).reshape(Cout, Cin) + mode_term
+    dbin = None
+    if has_bias:
+        dbin = _small_linear(gsum.reshape(1, Cout, 1).contiguous(), A).reshape(Cout) + float(S) * dX[:, :, 0, 0, 0].real.sum(0)
     return dWin, dbin
 
 
