@@ -795,6 +795,10 @@ def kernel_rooflines(prof, total_ms, B, n, precision, fused_ends, peak, traffic)
     fused_bwd = "block_spectral_bwd_kernel" in prof      # backward analysis of gu: z stage inside the block-tail kernel
     if fused_bwd:
         a_launch = 1.0                                   # analysis_zy_tc: the L - 1 full-size forward analyses only
+    # the block kernels' `u` buffer: gelu'(pre-activation) as packed binary16 under PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE = 2
+    # (the default), half an activation; a full fp32 activation otherwise
+    from pde_fluid_phi_b200 import _cabi as _cabi_opt
+    ub = act * (0.5 if _cabi_opt.load().pdephi_get_option(_cabi_opt.OPT_BLOCK_SAVES_DERIVATIVE) == 2 else 1.0)
     alg = {
         "analysis_zy_tc_kernel": (act + mid) * a_launch, "analysis_zy_kernel": act + mid,
         # tf32 route with fused ends: the split kernel runs the 3-channel lift analysis only
@@ -806,14 +810,14 @@ def kernel_rooflines(prof, total_ms, B, n, precision, fused_ends, peak, traffic)
         # an adjoint one with one addend (the unfused forward launches, if any, carry none: counted from the launches)
         "synthesis_zy_tc_kernel": act + mid + act,
         "synthesis_zy_kernel": act + mid + 1.5 * act,   # fp32 route: forward fuses both skip addends, adjoint one
-        "block_tail_fwd_kernel": 4 * act,            # read h, spec; write u, h'
+        "block_tail_fwd_kernel": 3 * act + ub,       # read h, spec; write u, h'
         # fused forward: read h and V; write u, h' (first block: h generated from the input, one activation less)
-        "block_spectral_fwd_kernel": (3 * act * (L - 1) + 2 * act) / L + vbytes if fused_ends else 3 * act + vbytes,
-        # read g', u, h; write gu, t -- first block: no h read, no t write (3 activations); last block: g' generated (4)
-        "block_tail_bwd_kernel": (5 * act * (L - 2) + 3 * act + 4 * act) / L if fused_ends else 5 * act,
-        # fused backward: gu is not stored; the z-analysed gu (Vg, the size of V) is.  Middle: read g', u, h, write t (4);
-        # first block: read g', u (2: no h, no t); last block: read u, h, write t (3: g' generated)
-        "block_spectral_bwd_kernel": ((4 * act * (L - 2) + 2 * act + 3 * act) / L if fused_ends else 4 * act) + vbytes,
+        "block_spectral_fwd_kernel": ((2 * act * (L - 1) + act) / L if fused_ends else 2 * act) + ub + vbytes,
+        # read g', u, h; write gu, t -- first block: no h read, no t write (2 activations + u); last block: g' generated (3 + u)
+        "block_tail_bwd_kernel": ((4 * act * (L - 2) + 2 * act + 3 * act) / L if fused_ends else 4 * act) + ub,
+        # fused backward: gu is not stored; the z-analysed gu (Vg, the size of V) is.  Middle: read g', u, h, write t (3 + u);
+        # first block: read g', u (1 + u: no h, no t); last block: read u, h, write t (2 + u: g' generated)
+        "block_spectral_bwd_kernel": ((3 * act * (L - 2) + act + 2 * act) / L if fused_ends else 3 * act) + ub + vbytes,
         "gen_axis_analysis_kernel": vbytes + mid,    # y stage of the fused backward: Vg in, [BC,Nx,my,mzh] out
         "analysis_x_tc_kernel": mid + modes_b, "synthesis_x_tc_kernel": mid + modes_b,
         # K2.  SURVEY.md section 8d counts 0.145 GB forward / 0.29 GB backward for an evaluation that
@@ -844,6 +848,8 @@ def kernel_rooflines(prof, total_ms, B, n, precision, fused_ends, peak, traffic)
             avg_ms = v[1] / (v[0] / 2)           # the tiny partial-sum reduce kernel shares the counter
         if k == "pointwise_wgrad_kernel":
             avg_ms = v[1] / (v[0] / 2)           # ... and so does this one's
+            if fused_ends:                       # ... and, with the lift in the first block, so do the (kernel, reduce) launches
+                avg_ms = v[1] / (v[0] / 4)       # of its weight gradient on the MODES (71 MB): one activation-sized pass per step
         a = alg[k]
         if k == "synthesis_zy_tc_kernel" and "block_spectral_fwd_kernel" not in prof:
             a = act + mid + 0.5 * act            # unfused forward: half the launches carry no addend

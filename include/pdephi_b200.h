@@ -320,7 +320,13 @@ int pdephi_wide_block_tail_bwd(const float* g, const float* u, const float* h, c
  * pdephi_block_spectral_*_fwd) holds gelu'(pre-activation) instead of the pre-activation, and the backward kernels read it as
  * such: the backward needs u for nothing else, the forward has the Gaussian CDF / density in registers anyway (two more
  * instructions per element), and the backward's compute warps -- its bound -- drop ~25 instructions per element.  Same bits
- * in gu either way.  Set 0 to get the pre-activation itself (both directions must run under the same setting). */
+ * in gu either way.  Set 0 to get the pre-activation itself (both directions must run under the same setting).
+ * Value 2 (the default): the derivative is stored as IEEE binary16, one 32-bit word per channel PAIR and point -- `u` is then
+ * an opaque buffer of B*(C/2)*S words, laid out [B][C/2][S], low half = channel 2p, high half = channel 2p+1 -- which takes
+ * half an activation off the forward's writes and the backward's reads.  These kernels contract in single-pass TF32
+ * whichever route calls them; binary16 carries the 11 significant bits of a TF32 operand, gelu' lies in [-0.13, 1.13], and
+ * gu = g gelu'(u) is a TF32 operand of every product of the backward (the residual term of t sees the 2^-12 rounding
+ * directly).  Value 1 keeps it in fp32. */
 enum pdephi_option { PDEPHI_OPT_TF32_XSTAGE_SPLIT = 0, PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE = 1 };
 int pdephi_set_option(int key, int value);
 int pdephi_get_option(int key);

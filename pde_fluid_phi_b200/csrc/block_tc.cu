@@ -13,6 +13,7 @@
 // Replaces cuDNN conv fwd/bwd + bias reductions + GELU fwd/bwd +
 // residual / gradient-accumulation adds (about 56 GB of HBM traffic per layer) with two passes (21.5 GB each).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -90,6 +91,17 @@ __device__ __forceinline__ float gelu_both_f(float u, float& grad) {
   grad = fmaf(u * 0.3989422804014327f, e, cdf);
   return u * cdf;
 }
+// PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE = 2: gelu'(u) of a channel PAIR (2p, 2p+1) at one point travels as one 32-bit word of two
+// binary16 values, [B][32 pairs][S] words.  binary16 has the 11 significant bits of a TF32 operand -- and the one product the
+// derivative enters, gu = g' gelu'(u), is a TF32 operand of every contraction of the backward -- and gelu' lies in
+// [-0.13, 1.13], far inside its range (below 6e-5 in magnitude the spacing is 6e-8 absolute).  The word of pair p at a point
+// sits, in the backward's staged K-major tile, in the 4-byte slot of row 2p at that point: the slot the same thread later
+// overwrites with gu, so the unpacking needs no exchange between threads.
+__device__ __forceinline__ uint32_t pack_du(float even, float odd) {
+  const __half2 h = __floats2half2_rn(even, odd);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_du(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 __device__ __forceinline__ float gelu_grad_f(float u) {
   float cdf, e;
   gelu_parts(u, cdf, e);
@@ -137,6 +149,18 @@ __device__ __forceinline__ void stage_rows(uint32_t dst, const float* __restrict
     const int r = lw + NW * i;
     if (C % NW == 0 || r < C)
       cp_async16(dst + (KMAJOR ? chunk_off_k(r, lane) : chunk_off_mn(r, lane)), src + (size_t)i * NW * S);
+  }
+}
+
+// the packed derivative ([B*32 pair rows][S] words, see pack_du): pair row p lands in row 2p of the K-major tile
+template <int NW>
+__device__ __forceinline__ void stage_pair_rows(uint32_t dst, const float* __restrict__ t, long long b, long long s0, long long S,
+                                                int lw, int lane) {
+  const float* src = t + ((size_t)b * (C / 2) + lw) * S + s0 + lane * 4;
+#pragma unroll
+  for (int i = 0; i < (C / 2 + NW - 1) / NW; ++i) {
+    const int p = lw + NW * i;
+    if ((C / 2) % NW == 0 || p < C / 2) cp_async16(dst + chunk_off_k(2 * p, lane), src + (size_t)i * NW * S);
   }
 }
 
@@ -499,13 +523,21 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
       const size_t g0 = ((size_t)b * C + part * CPW) * S + s0 + 32 * q + lane;
       float* up = u_out + g0;
       float* hp = h_out + g0;
+      // save_du == 2: one word per channel PAIR and point (see pack_du) -- this thread holds both channels of each of its pairs
+      uint32_t* up2 = reinterpret_cast<uint32_t*>(u_out) + ((size_t)b * (C / 2) + part * (CPW / 2)) * S + s0 + 32 * q + lane;
+      float du_even = 0.f;
       float pj[MAXP] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < CPW; ++j) {
         const float u = fmaf(v[j], TF32_COMP, bsr[j]) + pre[j];
         float du;
         const float hv = gelu_both_f(u, du);
-        __stcs(up, save_du ? du : u);
+        if (save_du == 2) {
+          if (j & 1) { __stcs(up2, pack_du(du_even, du)); up2 += S; }
+          else du_even = du;
+        } else {
+          __stcs(up, save_du ? du : u);
+        }
         *hp = hv;
         if (ZF) *reinterpret_cast<float*>(sm + L.hk + xk[j & 7] + j * 128) = to_tf32(hv);
         if (PROJ) {
@@ -757,7 +789,8 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       } else {
         stage_rows<true, NLW>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
       }
-      stage_rows<true, NLW>(base + L.stage[s] + UOFF, u_in, b, s0, S, lw, lane);
+      if (u_is_du == 2) stage_pair_rows<NLW>(base + L.stage[s] + UOFF, u_in, b, s0, S, lw, lane);
+      else stage_rows<true, NLW>(base + L.stage[s] + UOFF, u_in, b, s0, S, lw, lane);
       if (GENG && !GENG_STEP1) {
         uint8_t* dst = sm + L.stage[s];
 #pragma unroll
@@ -875,7 +908,14 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         if (!ZA) { *gp = r[j]; gp += S; }
         if (DB_REGS) db[j] += r[j];
       };
-      if (u_is_du) {       // the forward stored the derivative: one multiply per element instead of the erf / density evaluation
+      if (u_is_du == 2) {  // ... as binary16 pairs in the even rows' slots (pack_du): read the word, then overwrite both rows' slots
+#pragma unroll
+        for (int j = 0; j < CPW; j += 2) {
+          const float2 dd = unpack_du(*reinterpret_cast<const uint32_t*>(tgk + xk[j & 7] + j * 128));
+          element(j, dd.x);
+          element(j + 1, dd.y);
+        }
+      } else if (u_is_du) {       // the forward stored the derivative: one multiply per element instead of the erf / density evaluation
 #pragma unroll
         for (int j = 0; j < CPW; ++j) element(j, *reinterpret_cast<const float*>(tgk + xk[j & 7] + j * 128));
       } else {

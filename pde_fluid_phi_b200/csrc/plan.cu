@@ -32,7 +32,7 @@ static const char* const kKernelNames[K_COUNT] = {
     "block_spectral_bwd_kernel", "rational_transfer_kernel", "mix_apply_kernel"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 // option defaults: the x stage of the single-pass TF32 route runs split (fp32-grade) -- see pdephi_set_option
-static std::atomic<int> g_options[OPT_COUNT] = {{1}, {1}};
+static std::atomic<int> g_options[OPT_COUNT] = {{1}, {2}};
 static std::atomic<long long> g_launches[K_COUNT];
 static std::atomic<bool> g_prof_on{false};
 static std::mutex g_prof_mu;

@@ -331,6 +331,37 @@ def lift_supported(linear) -> bool:
             and linear.weight.is_cuda and linear.weight.dtype == torch.float32)
 
 
+def _block_u_empty(B: int, C: int, spatial, device) -> torch.Tensor:
+    """The `u` buffer a width-64 block forward kernel fills and the matching backward kernel reads.  What it holds follows
+    PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE: 0 the pre-activation, 1 gelu'(pre-activation), both fp32 [B,C,...]; 2 (default) gelu'
+    as binary16, channel pairs interleaved per point -- an opaque buffer of half the bytes, allocated as float16 [B,C,...]
+    (decode with unpack_block_derivative)."""
+    packed = _cabi.load().pdephi_get_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE) == 2
+    return torch.empty((B, C, *spatial), dtype=torch.float16 if packed else torch.float32, device=device)
+
+
+def unpack_block_derivative(u: torch.Tensor) -> torch.Tensor:
+    """fp32 [B,C,...] view of what a block forward kernel left in `u` (the packed layout of option value 2 is
+    [B][C/2 channel pairs][S points][2]: pack_du of block_tc.cu); a copy for float16 buffers, `u` itself otherwise."""
+    if u.dtype != torch.float16:
+        return u
+    B, C = u.shape[:2]
+    return u.reshape(B, C // 2, -1, 2).permute(0, 1, 3, 2).reshape(u.shape).float()
+
+
+def pack_block_derivative(du: torch.Tensor) -> torch.Tensor:
+    """Inverse of unpack_block_derivative: fp32 [B,C,...] -> the packed binary16 buffer of option value 2."""
+    B, C = du.shape[:2]
+    return du.to(torch.float16).reshape(B, C // 2, 2, -1).permute(0, 1, 3, 2).contiguous().reshape(du.shape)
+
+
+def _check_block_u(u: torch.Tensor, who: str) -> None:
+    packed = _cabi.load().pdephi_get_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE) == 2
+    if packed != (u.dtype == torch.float16):
+        raise RuntimeError(f"{who}: `u` was written under another PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE setting than the one in force "
+                           f"(dtype {u.dtype}, option now {'2' if packed else '0/1'}): forward and backward must agree")
+
+
 def block_tail_fwd(h, spec, Wc, bc, head=None, lift=None):
     """u = spec + (Wc h + bc) + h, hout = gelu(u) on [B,64,...] tensors (tcgen05 TF32 channel GEMM, fused epilogue).
     head = (Wp [n,64], bp [n] | None): additionally returns out = Wp hout + bp, computed in the same epilogue.
@@ -341,7 +372,7 @@ def block_tail_fwd(h, spec, Wc, bc, head=None, lift=None):
     S = h[0, 0].numel()
     lib = _cabi.load()
     with _cabi.on_device(h.device):
-        u = torch.empty_like(spec)
+        u = _block_u_empty(B, C, spec.shape[2:], spec.device)
         hout = torch.empty_like(spec)
         if lift is not None:
             Win, bin_ = lift
@@ -379,8 +410,8 @@ def block_spectral_fwd(Y, mode_scale, row_scale, h, Wc, bc, head=None, lift=None
     rs_stride = row_scale.stride(0) if row_scale is not None else 0
     with _cabi.on_device(h.device):
         plan = _cabi.get_plan(h.device.index, tuple(h.shape[2:]), tuple(Y.shape[2:]))
-        u = torch.empty((B, C, *h.shape[2:]), dtype=torch.float32, device=h.device)
-        hout = torch.empty_like(u)
+        u = _block_u_empty(B, C, h.shape[2:], h.device)
+        hout = torch.empty((B, C, *h.shape[2:]), dtype=torch.float32, device=h.device)
         nbytes = lib.pdephi_block_spectral_fwd_workspace_bytes(plan, B, C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
         if want_vz:
@@ -432,9 +463,10 @@ def block_tail_bwd(g, u, h, Wc, want_bias: bool, head_w=None, write_t: bool = Tr
     B, C = u.shape[:2]
     S = u[0, 0].numel()
     lib = _cabi.load()
+    _check_block_u(u, "block_tail_bwd")
     with _cabi.on_device(h.device):
-        gu = torch.empty_like(u)
-        t = torch.empty_like(u) if write_t else None
+        gu = torch.empty(u.shape, dtype=torch.float32, device=h.device)
+        t = torch.empty_like(gu) if write_t else None
         dW = torch.empty((C, C), dtype=torch.float32, device=h.device)
         db = torch.empty(C, dtype=torch.float32, device=h.device) if (want_bias or (lift is not None and not write_t)) else None
         nbytes = lib.pdephi_block_tail_bwd_workspace_bytes(C)
@@ -474,9 +506,10 @@ def block_spectral_bwd(g, u, h, Wc, modes_h, want_bias: bool, head_w=None, write
     dZ [B,64,mx,my,mzh] complex64 = analysis(gu, ADJOINT); t / G as in block_tail_bwd.  gu is never materialised."""
     B, C = u.shape[:2]
     lib = _cabi.load()
+    _check_block_u(u, "block_spectral_bwd")
     with _cabi.on_device(u.device):
         plan = _cabi.get_plan(u.device.index, tuple(u.shape[2:]), tuple(modes_h))
-        t = torch.empty_like(u) if write_t else None
+        t = torch.empty(u.shape, dtype=torch.float32, device=u.device) if write_t else None
         dW = torch.empty((C, C), dtype=torch.float32, device=u.device)
         need_db = want_bias or (lift is not None and not write_t)
         db = torch.empty(C, dtype=torch.float32, device=u.device) if need_db else None

@@ -16,6 +16,8 @@ mh = (32, 32, 17)
 act = 4.0 * B * C * n ** 3
 small = 4.0 * B * 3 * n ** 3
 V = 4.0 * B * n * n * C * 36
+# the `u` buffer: packed binary16 derivative (half an activation) under PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE = 2 (the default)
+ub = act * (0.5 if _cabi.load().pdephi_get_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE) == 2 else 1.0)
 
 h = torch.randn(B, C, n, n, n, device=dev)
 x = torch.randn(B, 3, n, n, n, device=dev)
@@ -35,19 +37,19 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 cases = {
     # name: (callable, algorithmic bytes of the block kernel itself)
-    "fwd middle <fused>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], h, W, b), 3 * act + V),
-    "fwd first  <fused,lift>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], x, W, b, lift=(Win, bin_)), 2 * act + V + small),
-    "fwd last   <fused,proj>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], h, W, b, head=(Wp, bp)), 3 * act + V + small),
+    "fwd middle <fused>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], h, W, b), 2 * act + ub + V),
+    "fwd first  <fused,lift>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], x, W, b, lift=(Win, bin_)), act + ub + V + small),
+    "fwd last   <fused,proj>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], h, W, b, head=(Wp, bp)), 2 * act + ub + V + small),
     # fused forward that also runs the z stage of the next layer's analysis on its output (vz out)
-    "fwdz middle <fused>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], h, W, b, want_vz=True), 3 * act + 2 * V),
-    "fwdz first  <fused,lift>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], x, W, b, lift=(Win, bin_), want_vz=True), 2 * act + 2 * V + small),
-    "bwd middle": (lambda: pf.block_tail_bwd(g, u, h, W, True), 5 * act),
-    "bwd first  <lift, no t>": (lambda: pf.block_tail_bwd(g, u, x, W, True, write_t=False, lift=(Win, bin_)), 3 * act + small),
-    "bwd last   <proj>": (lambda: pf.block_tail_bwd(gout, u, h, W, True, head_w=Wp), 4 * act + small),
+    "fwdz middle <fused>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], h, W, b, want_vz=True), 2 * act + ub + 2 * V),
+    "fwdz first  <fused,lift>": (lambda: pf.block_spectral_fwd(Y, ms, rs[:, 2], x, W, b, lift=(Win, bin_), want_vz=True), act + ub + 2 * V + small),
+    "bwd middle": (lambda: pf.block_tail_bwd(g, u, h, W, True), 4 * act + ub),
+    "bwd first  <lift, no t>": (lambda: pf.block_tail_bwd(g, u, x, W, True, write_t=False, lift=(Win, bin_)), 2 * act + ub + small),
+    "bwd last   <proj>": (lambda: pf.block_tail_bwd(gout, u, h, W, True, head_w=Wp), 3 * act + ub + small),
     # fused backward (z stage of the adjoint analysis inside the kernel): gu is not stored, the z-analysed gu (Vg) is
-    "bwdz middle": (lambda: pf.block_spectral_bwd(g, u, h, W, mh, True), 4 * act + V),
-    "bwdz first  <lift, no t>": (lambda: pf.block_spectral_bwd(g, u, x, W, mh, True, write_t=False, lift=(Win, bin_)), 2 * act + small + V),
-    "bwdz last   <proj>": (lambda: pf.block_spectral_bwd(gout, u, h, W, mh, True, head_w=Wp), 3 * act + small + V),
+    "bwdz middle": (lambda: pf.block_spectral_bwd(g, u, h, W, mh, True), 3 * act + ub + V),
+    "bwdz first  <lift, no t>": (lambda: pf.block_spectral_bwd(g, u, x, W, mh, True, write_t=False, lift=(Win, bin_)), act + ub + small + V),
+    "bwdz last   <proj>": (lambda: pf.block_spectral_bwd(gout, u, h, W, mh, True, head_w=Wp), 2 * act + ub + small + V),
 }
 res = {}
 for name, (fn, nbytes) in cases.items():

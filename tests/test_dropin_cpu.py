@@ -198,3 +198,18 @@ def test_transfer_cache_is_not_copied_or_pickled():
         assert clone._transfer_cache is not layer._transfer_cache
         assert clone._transfer_cache.key is None and clone._transfer_cache.R is None
         assert torch.equal(clone.P_coeffs, layer.P_coeffs)
+
+
+def test_packed_block_derivative_layout_round_trips():
+    """The host-side view of PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE = 2 (block_tc.cu pack_du): one 32-bit word per channel pair and
+    point, low half = even channel; pack / unpack are inverse up to the binary16 rounding and keep the logical [B,C,...] shape."""
+    from pde_fluid_phi_b200 import functional as pf
+    torch.manual_seed(0)
+    du = torch.rand(2, 64, 4, 8, 16) * 1.26 - 0.13           # the range of gelu'
+    packed = pf.pack_block_derivative(du)
+    assert packed.dtype == torch.float16 and packed.shape == du.shape and packed.element_size() * packed.numel() == du.numel() * 2
+    words = packed.reshape(2, 32, -1, 2)
+    assert torch.equal(words[1, 5, 77, 0], du[1, 10].reshape(-1)[77].half()) and torch.equal(words[1, 5, 77, 1], du[1, 11].reshape(-1)[77].half())
+    back = pf.unpack_block_derivative(packed)
+    assert back.dtype == torch.float32 and torch.equal(back, du.half().float())
+    assert float((back - du).abs().max()) <= 2.0 ** -11 * 1.13 and pf.unpack_block_derivative(du) is du

@@ -560,14 +560,27 @@ def test_fused_block_tail_vs_torch():
         gu0 = pf.block_tail_bwd(g, u, h.detach(), Wc2, True)[0]
     finally:
         _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, old_opt)
-    # ... and, by default, gelu'(u): all the backward needs u for; same bits in gu
-    assert _cabi.load().pdephi_get_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE) == 1
-    u, hout = pf.block_tail_fwd(h.detach(), spec.detach(), Wc2, conv.bias.detach())
+    # ... gelu'(u) in fp32 (value 1): all the backward needs u for; same bits in gu
     upre = (spec + conv(h) + h).detach().double()
     dref = 0.5 * (1 + torch.erf(upre / 2 ** 0.5)) + upre * torch.exp(-0.5 * upre * upre) / (2 * torch.pi) ** 0.5
-    assert rel(u, dref) < TOL["tf32"] and rel(hout, ref) < TOL["tf32"]
+    _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, 1)
+    try:
+        u1, hout1 = pf.block_tail_fwd(h.detach(), spec.detach(), Wc2, conv.bias.detach())
+        assert u1.dtype == torch.float32 and rel(u1, dref) < TOL["tf32"] and torch.equal(hout1, hout)
+        assert torch.equal(pf.block_tail_bwd(g, u1, h.detach(), Wc2, True)[0], gu0)
+        with pytest.raises(RuntimeError, match="SAVES_DERIVATIVE"):      # a buffer written under one setting, read under another
+            _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, 2)
+            pf.block_tail_bwd(g, u1, h.detach(), Wc2, True)
+    finally:
+        _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, old_opt)
+    # ... and, by default (value 2), gelu'(u) as binary16 -- the 11 significant bits of the TF32 operand it becomes -- packed in
+    # channel pairs: half the bytes
+    assert _cabi.load().pdephi_get_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE) == 2
+    u, hout = pf.block_tail_fwd(h.detach(), spec.detach(), Wc2, conv.bias.detach())
+    assert u.dtype == torch.float16 and u.shape == hout.shape and torch.equal(hout, hout1)
+    assert rel(pf.unpack_block_derivative(u), u1) < 2.0 ** -11 and rel(hout, ref) < TOL["tf32"]
     gu, t, dW, db = pf.block_tail_bwd(g, u, h.detach(), Wc2, True)
-    assert torch.equal(gu, gu0)
+    assert rel(gu, gu0) < 2.0 ** -11
     assert rel(gu, spec.grad) < TOL["tf32"]                  # d/d spec = g * gelu'(u)
     assert rel(t, h.grad) < TOL["tf32"]                      # d/d h (conv + residual branches)
     assert rel(dW, conv.weight.grad.reshape(C, C)) < TOL["tf32"]
@@ -605,7 +618,7 @@ def test_fused_spectral_block_forward(B, grid, modes):
     finally:
         _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, old_opt)
     du, hout2 = pf.block_spectral_fwd(Y, mask, rs[:, 2], h, Wc, bc)              # default: gelu'(u) in its place
-    assert torch.equal(hout2, hout) and not torch.equal(du, u)
+    assert torch.equal(hout2, hout) and not torch.equal(pf.unpack_block_derivative(du), u)
 
 
 def test_whole_block_model_on_the_fused_spectral_route():
@@ -1006,19 +1019,33 @@ def test_fno3d_other_activation_runs_the_block_in_the_library(activation):
                                             (1, (128, 128, 128), (32, 32, 17)),
                                             # Ny != 128: the y stage falls back to the general (TMA-staged) axis kernel
                                             (1, (32, 64, 128), (8, 16, 17)), (1, (32, 256, 128), (8, 24, 9))])
-def test_fused_block_backward_vs_unfused_kernels(variant, B, grid, modes_h):
+@pytest.mark.parametrize("du_mode", [2, 1])
+def test_fused_block_backward_vs_unfused_kernels(variant, B, grid, modes_h, du_mode):
     """t, dWc and G are the SAME arithmetic as the unfused block-tail backward (bit-identical); dbc comes out of a tensor-core
     product over the TF32-rounded gu tile instead of fp32 running sums (TF32 gate); dZ is the ADJOINT
     analysis of a gu that never reaches HBM: against the fp32-grade (split-TF32) analysis of the stored gu at the TF32 gate,
     and no further from it than the unfused single-pass analysis is (x 1.5)."""
     if variant != "middle" and (grid[0] == 128 or grid[1] != 128):
         pytest.skip("end-block variants are covered at the smaller shapes")
+    if du_mode == 1 and grid != (32, 128, 128):
+        pytest.skip("the fp32 derivative buffer (option value 1) is covered at one shape")
     torch.manual_seed(7)
     C = 64
-    u = torch.randn(B, C, *grid, device=DEV)
+    u = torch.randn(B, C, *grid, device=DEV)          # stands for gelu'(pre-activation): what the forward kernels leave in `u`
     Wc = torch.randn(C, C, device=DEV) * 0.1
     if not pf.block_spectral_supported(u, modes_h, _cabi.PREC_TF32):
         pytest.skip("fused block route not available for this shape")
+    old_opt = _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, du_mode)
+    try:
+        if du_mode == 2:
+            u = pf.pack_block_derivative(u)
+            assert u.dtype == torch.float16 and torch.equal(pf.pack_block_derivative(pf.unpack_block_derivative(u)), u)
+        _fused_block_backward_checks(variant, B, C, grid, modes_h, u, Wc)
+    finally:
+        _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, old_opt)
+
+
+def _fused_block_backward_checks(variant, B, C, grid, modes_h, u, Wc):
     head_w = lift = None
     write_t = True
     g = torch.randn(B, 3 if variant == "head" else C, *grid, device=DEV)
