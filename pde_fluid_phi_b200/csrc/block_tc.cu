@@ -267,7 +267,9 @@ __host__ __device__ inline FSmem fwd_smem(bool fused, bool proj = false, bool ge
 enum { FB_FULL = 0, FB_EMPTY = F_STAGES, FB_DFULL = 2 * F_STAGES, FB_DEMPTY = 2 * F_STAGES + 2, FB_HREADY = 2 * F_STAGES + 4,
        FB_ZFFULL = 2 * F_STAGES + 5 };
 
-template <bool FUSED, bool PROJ, bool GENH, bool ZF = false>
+// PACKDU: the instantiation for PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE = 2 (a template parameter, not a run-time test: a branch per
+// element in the epilogue loop kept ptxas from interleaving the sixteen elements' erf / exp chains)
+template <bool FUSED, bool PROJ, bool GENH, bool ZF = false, bool PACKDU = false>
 __global__ void __launch_bounds__(THREADS, 1)
 block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ spec_in, const float* __restrict__ Wc,
                       const float* __restrict__ bc, float* __restrict__ u_out, float* __restrict__ h_out,
@@ -532,7 +534,7 @@ block_tail_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ 
         const float u = fmaf(v[j], TF32_COMP, bsr[j]) + pre[j];
         float du;
         const float hv = gelu_both_f(u, du);
-        if (save_du == 2) {
+        if (PACKDU) {
           if (j & 1) { __stcs(up2, pack_du(du_even, du)); up2 += S; }
           else du_even = du;
         } else {
@@ -661,7 +663,8 @@ enum { BB_FULL = 0, BB_EMPTY = B_MAXST, BB_GUREADY = 2 * B_MAXST, BB_TFULL = 2 *
 // one more GEMM on the staged K-layout gu tile -- D'[128 x 64 ch] = A (TMEM-resident, rows kz' = 2 kz + (re | im), c_kz / N
 // folded in) . gu^T -- and gu itself is never stored.  Vg has the layout of the per-axis route's z-analysed intermediate
 // ([B*64][Nx][Ny][ldz]), so the y and x stages follow unchanged (transforms_gen.cu: pdephi_block_spectral_bwd).
-template <bool GENG, bool WT, bool GENH, bool ZA>
+// PACKDU: the instantiation for PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE = 2 (u_in = packed binary16 derivative)
+template <bool GENG, bool WT, bool GENH, bool ZA, bool PACKDU = false>
 __global__ void __launch_bounds__(bwd_threads(ZA, GENG), 1)
 block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ h_in, const float* __restrict__ u_in,
                       const float* __restrict__ Wc, float* __restrict__ gu_out, float* __restrict__ t_out,
@@ -789,7 +792,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       } else {
         stage_rows<true, NLW>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
       }
-      if (u_is_du == 2) stage_pair_rows<NLW>(base + L.stage[s] + UOFF, u_in, b, s0, S, lw, lane);
+      if (PACKDU) stage_pair_rows<NLW>(base + L.stage[s] + UOFF, u_in, b, s0, S, lw, lane);
       else stage_rows<true, NLW>(base + L.stage[s] + UOFF, u_in, b, s0, S, lw, lane);
       if (GENG && !GENG_STEP1) {
         uint8_t* dst = sm + L.stage[s];
@@ -908,7 +911,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         if (!ZA) { *gp = r[j]; gp += S; }
         if (DB_REGS) db[j] += r[j];
       };
-      if (u_is_du == 2) {  // ... as binary16 pairs in the even rows' slots (pack_du): read the word, then overwrite both rows' slots
+      if (PACKDU) {        // ... as binary16 pairs in the even rows' slots (pack_du): read the word, then overwrite both rows' slots
 #pragma unroll
         for (int j = 0; j < CPW; j += 2) {
           const float2 dd = unpack_du(*reinterpret_cast<const uint32_t*>(tgk + xk[j & 7] + j * 128));
@@ -975,15 +978,14 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
     };
     // Step 1 of tile i+1 runs BEFORE the epilogue of tile i: the Wc^T gu GEMM of tile i (and its commit / barrier round
     // trip, ~1000 clocks) is then hidden behind useful work instead of being waited for by all sixteen warps.
+    // (order s0 s1 e0 s2 e1 s3 e2 ...; written so that each of the two register sets has ONE inlined copy of step 1 and of the
+    // epilogue -- the kernel is ~100 KB of code with a third copy of step 1)
     float ra[CPW], rb[CPW];
-    if (my_tiles > 0) step1(0, ra);
-    for (long long it = 0; it < my_tiles; it += 2) {
+    for (long long it = 0; it <= my_tiles; it += 2) {
+      if (it < my_tiles) step1(it, ra);
+      if (it >= 1) epilogue(it - 1, rb);
       if (it + 1 < my_tiles) step1(it + 1, rb);
-      epilogue(it, ra);
-      if (it + 1 < my_tiles) {
-        if (it + 2 < my_tiles) step1(it + 2, ra);
-        epilogue(it + 1, rb);
-      }
+      if (it < my_tiles) epilogue(it, ra);
     }
     // ---- per-CTA partials: the bias gradient (see DB_ZA / DB_REGS / LIFT_G above) and dW or G (TMEM) ----
     float* red = reinterpret_cast<float*>(sm + L.red);      // DB_REGS: [4 quarters][64];  DB_ZA: [64]
@@ -1122,10 +1124,11 @@ static int check_proj(const ProjArgs& pr, const char* who) {
 
 #define PDEPHI_FWD_LAUNCH_Z(FF, PP, HH, ZZ, SPEC, BZ, LDZ, ZAIMG, VH)                                                       \
   {                                                                                                                        \
-    auto k = blk::block_tail_fwd_kernel<FF, PP, HH, ZZ>;                                                                   \
+    const int du_mode = option_get(OPT_BLOCK_SAVES_DERIVATIVE);                                                            \
+    auto k = du_mode == 2 ? blk::block_tail_fwd_kernel<FF, PP, HH, ZZ, true> : blk::block_tail_fwd_kernel<FF, PP, HH, ZZ, false>; \
     PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
     k<<<grid, blk::THREADS, smem, st>>>(h, SPEC, Wc, bc, u, hout, tpb, ntiles, S, BZ, LDZ, tile_order(), pr.Wp, pr.bp, pr.out, \
-                                        pr.n, lf.Win, lf.bin, lf.n, option_get(OPT_BLOCK_SAVES_DERIVATIVE), ZAIMG, VH);    \
+                                        pr.n, lf.Win, lf.bin, lf.n, du_mode, ZAIMG, VH);                                   \
   }
 #define PDEPHI_FWD_LAUNCH(FF, PP, HH, SPEC, BZ, LDZ) PDEPHI_FWD_LAUNCH_Z(FF, PP, HH, false, SPEC, BZ, LDZ, nullptr, nullptr)
 
@@ -1212,14 +1215,15 @@ int block_tail_bwd_launch(const float* g, const float* u, const float* h, const 
   if (sms > 1024) sms = 1024;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   const int kid = vg ? K_BLOCK_SPECTRAL_BWD : K_BLOCK_TAIL_BWD;
+  const int du_mode = option_get(OPT_BLOCK_SAVES_DERIVATIVE);
   {
     ProfScope ps(kid, st);
 #define PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, ZZ)                                                                                \
     {                                                                                                                      \
-      auto k = blk::block_tail_bwd_kernel<GG, WW, HH, ZZ>;                                                                 \
+      auto k = du_mode == 2 ? blk::block_tail_bwd_kernel<GG, WW, HH, ZZ, true> : blk::block_tail_bwd_kernel<GG, WW, HH, ZZ, false>; \
       PDEPHI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
       k<<<grid, blk::bwd_threads(ZZ, GG), smem, st>>>(g, h, u, Wc, gu, t, (float*)workspace, tpb, ntiles, S, tile_order(), Wp, n_out,  \
-                                          lf.Win, lf.bin, lf.n, za_img, vg, ldz, option_get(OPT_BLOCK_SAVES_DERIVATIVE));  \
+                                          lf.Win, lf.bin, lf.n, za_img, vg, ldz, du_mode);                                 \
     }
 #define PDEPHI_BWD_LAUNCH(GG, WW, HH) { if (vg) PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, true) else PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, false) }
     if (lf.Win) { if (t) PDEPHI_BWD_LAUNCH(false, true, true) else PDEPHI_BWD_LAUNCH(false, false, true) }
