@@ -21,7 +21,7 @@ PREC_AUTO = -1    # host-side only: TF32X3 where the plan supports it, FP32 (FFM
 FORWARD, ADJOINT = 0, 1
 STAGES_ZY, STAGES_X, STAGES_ALL = 1, 2, 3
 OPT_TF32_XSTAGE_SPLIT = 0
-OPT_BLOCK_SAVES_DERIVATIVE = 1
+OPT_BLOCK_SAVES_DERIVATIVE = 1         # option key; values 0 / 1 / 2 (default 2: packed binary16, see include/pdephi_b200.h)
 ACTIVATIONS = {"identity": 0, "gelu": 1, "relu": 2, "tanh": 3, "silu": 4, "sigmoid": 5, "leaky_relu": 6, "elu": 7}
 ROUTE_NONE, ROUTE_FFMA, ROUTE_FUSED_TC, ROUTE_PER_AXIS_TC = 0, 1, 2, 3
 PER_AXIS_SPLIT_MIN_POINTS = 1 << 25      # 'auto': below this many points per call the FFMA kernels beat the per-axis split route

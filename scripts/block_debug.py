@@ -2,8 +2,9 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from pde_fluid_phi_b200 import functional as pf
+from pde_fluid_phi_b200 import functional as pf, _cabi
 from oracle.spectral_oracle import rel_l2
+_cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, 0)      # this helper inspects the pre-activation itself in `u`
 torch.manual_seed(0)
 B, C, grid = 2, 64, (8, 8, 16)
 dev = "cuda"
