@@ -230,11 +230,11 @@ def ncu_traffic_from_profiles():
             name = r[0].replace("pdephi::", "")
             for bench_name, prefix in NCU_NAME.items():
                 if bench_name.startswith("block_") and "bwd" in bench_name:
-                    # block_tail_bwd_kernel<GENG, WT, GENH, ZA>: the ZA instantiations are the fused backward
+                    # block_tail_bwd_kernel<GENG, WT, GENH, ZA[, PACKDU]>: the ZA instantiations are the fused backward
                     # (block_spectral_bwd_kernel in the library's profile), the others (or the 3-parameter name of the
                     # round-1 captures) the plain block-tail backward
                     args = name[name.find("<") + 1:name.rfind(">")].replace(" ", "").split(",") if "<" in name else []
-                    za = len(args) == 4 and args[3] in ("1", "true")
+                    za = len(args) >= 4 and args[3] in ("1", "true")       # (a fifth argument, PACKDU, since the packed derivative)
                     if za != (bench_name == "block_spectral_bwd_kernel"):
                         continue
                 if name.startswith(prefix) or name.startswith(prefix.split("::")[-1]):
