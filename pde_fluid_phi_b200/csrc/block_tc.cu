@@ -628,12 +628,24 @@ constexpr int AUX = 4096;        // per stage: the x rows as a K-major [8 rows][
 // Wc^T image is not needed, so the ring runs THREE stages -- that variant moves 10 GB per launch and the two-stage chain
 // (load latency -> step 1 -> MMAs -> release) paced it at 4.0 TB/s.
 constexpr int B_MAXST = 3;
+// last3 (PDEPHI_LAST3; the LAST block on the fused route, whose g' is generated, not loaded): the MN-major copy of gu exists only
+// as the A operand of the Wc^T gu product, and a tcgen05 A operand may live in TMEM in exactly the layout the compute threads
+// hold gu in (lane = point, columns = channels).  They store it there (64 columns, single-buffered), the stage shrinks to
+// [h][u -> gu K-major] = 64 KB and the ring runs three stages: two tiles' loads in flight instead of one.
+#ifndef PDEPHI_LAST3
+#define PDEPHI_LAST3 1
+#endif
+constexpr bool LAST3_ON = PDEPHI_LAST3 != 0 && GENG_STEP1;
+// (The same for a MIDDLE block -- g' landing in the K-major tile, gu overwriting it slot by slot, the packed derivative fetched
+// by the compute threads themselves one tile ahead in registers, stage = [h][g' -> gu] = 64 KB x 3 -- was built and measured:
+// bit-identical, but 3.27 ms against 3.03 ms: the sixteen registers of the two word sets spill (44 / 124 bytes) and the
+// threads' own loads cost more than the third stage gains.  Not kept.)
 struct BSmem { uint32_t stage[B_MAXST], aux[B_MAXST], wt, red, wp, lift, bars, tmem_slot, total; int nst, uoff; };
-__host__ __device__ inline BSmem bwd_smem(bool lift_g = false) {
+__host__ __device__ inline BSmem bwd_smem(bool lift_g = false, bool last3 = false) {
   BSmem s; uint32_t o = 0;
-  s.nst = lift_g ? 3 : B_STAGES;
-  s.uoff = lift_g ? TILE : 2 * TILE;                                       // offset of the u (-> gu, K layout) tile in a stage
-  for (int i = 0; i < B_MAXST; ++i) { s.stage[i] = o; if (i < s.nst) o += lift_g ? 2 * TILE : 3 * TILE; }   // g' (-> gu, MN), [h (K),] u (-> gu, K)
+  s.nst = (lift_g || last3) ? 3 : B_STAGES;
+  s.uoff = (lift_g || last3) ? TILE : 2 * TILE;                            // offset of the u (-> gu, K layout) tile in a stage
+  for (int i = 0; i < B_MAXST; ++i) { s.stage[i] = o; if (i < s.nst) o += (lift_g || last3) ? 2 * TILE : 3 * TILE; }   // g' (-> gu, MN), [h (K),] u (-> gu, K); last3: h, u
   for (int i = 0; i < B_MAXST; ++i) { s.aux[i] = o; if (i < s.nst) o += AUX; }
   s.wt = o; o += lift_g ? 0 : 2 * BOX;
   s.red = o; o += 4 * C * 4;
@@ -676,12 +688,15 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const BSmem L = bwd_smem(GENH && !WT);
+  constexpr bool LAST3 = LAST3_ON && GENG && WT && !GENH;            // see bwd_smem (with or without the fused z analysis)
+  constexpr bool TMEMA = LAST3;                                      // gu^T as the TMEM A operand of the Wc^T gu product
+  const BSmem L = bwd_smem(GENH && !WT, TMEMA);
   auto bar = [&](int i) { return base + L.bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   constexpr bool LIFT_G = GENH && !WT;
-  constexpr int NST = LIFT_G ? 3 : B_STAGES, UOFF = LIFT_G ? TILE : 2 * TILE;     // ring depth, offset of the u tile in a stage
+  constexpr int NST = (LIFT_G || TMEMA) ? 3 : B_STAGES, UOFF = (LIFT_G || TMEMA) ? TILE : 2 * TILE;     // ring depth, offset of the u tile in a stage
+  constexpr int HOFF = TMEMA ? 0 : TILE;                               // offset of the h tile in a stage
   constexpr int NLW = bwd_ld_warps(ZA, GENG), NTHR = bwd_threads(ZA, GENG), BEPI0 = 1 + NLW;      // loader warps / threads / first compute warp
   if (WT) build_w_image(sm + L.wt, Wc, true, threadIdx.x, NTHR, TF32_COMP);      // rows c, K = o : (Wc^T)
   if (GENG) {
@@ -731,6 +746,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.tmem_slot);
   const uint32_t tmem_t[2] = {tmem, tmem + C}, tmem_dw = tmem + 2 * C;
   const uint32_t tmem_za[2] = {tmem + 3 * C, tmem + 4 * C}, tmem_a = tmem + 6 * C;   // ZA: accumulators, A image [128 x 128]
+  const uint32_t tmem_gu = tmem + (ZA ? 5 : 3) * C;                                  // TMEMA: gu^T [128 points x 64 channels]
   if (ZA) {
     if (warp >= BEPI0 && warp < BEPI0 + 4) {       // four consecutive warps cover the four TMEM lane quarters
       const int q = warp & 3;
@@ -790,7 +806,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         load_x(xv, h_in, n_in, b, s0, S, lane);
         generate_rows<true, NLW>(sm + L.stage[s] + TILE, xv, sm + L.lift, lw, lane);
       } else {
-        stage_rows<true, NLW>(base + L.stage[s] + TILE, h_in, b, s0, S, lw, lane);
+        stage_rows<true, NLW>(base + L.stage[s] + HOFF, h_in, b, s0, S, lw, lane);
       }
       if (PACKDU) stage_pair_rows<NLW>(base + L.stage[s] + UOFF, u_in, b, s0, S, lw, lane);
       else stage_rows<true, NLW>(base + L.stage[s] + UOFF, u_in, b, s0, S, lw, lane);
@@ -832,8 +848,13 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
         mbar_wait(bar(BB_GUREADY + d), ph);                  // gu written in place over g' (implies the tile landed)
         mbar_wait(bar(BB_TEMPTY + d), ph ^ 1);
         tc_fence_after();
-        const uint32_t gu = base + L.stage[s], hh = gu + TILE, guk = gu + UOFF;
-        if (WT) {
+        const uint32_t gu = base + L.stage[s], hh = gu + HOFF, guk = gu + UOFF;
+        if (WT && TMEMA) {       // A = gu^T from TMEM (K-major by construction: lane = point, column = channel o)
+          constexpr uint32_t id_ta = idesc_tf32(TS, C, 0, 0);
+#pragma unroll
+          for (int k = 0; k < C / 8; ++k)
+            mma_ts(tmem_t[d], tmem_gu + 8 * k, umma_desc(base + L.wt + (k >> 2) * BOX + (k & 3) * 32, 1024), id_ta, k ? 1u : 0u);
+        } else if (WT) {
 #pragma unroll
           for (int k = 0; k < C / 8; ++k)
             mma_ss(tmem_t[d], umma_desc_mn(gu + k * 1024, BOX), umma_desc(base + L.wt + (k >> 2) * BOX + (k & 3) * 32, 1024), id_t,
@@ -906,7 +927,7 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
           gin = *reinterpret_cast<const float*>(tg + off);
         }
         r[j] = gin * dact;
-        if (WT) *reinterpret_cast<float*>(tg + off) = r[j];
+        if (WT && !TMEMA) *reinterpret_cast<float*>(tg + off) = r[j];
         *reinterpret_cast<float*>(tgk + offk) = to_tf32(r[j]);
         if (!ZA) { *gp = r[j]; gp += S; }
         if (DB_REGS) db[j] += r[j];
@@ -924,6 +945,14 @@ block_tail_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ 
       } else {
 #pragma unroll
         for (int j = 0; j < CPW; ++j) element(j, gelu_grad_f(*reinterpret_cast<const float*>(tgk + xk[j & 7] + j * 128)));
+      }
+      if (TMEMA) {         // gu^T -> TMEM, once the previous tile's Wc^T gu product has read the (single) buffer -- it was issued a
+                           // whole step 1 ago, so this wait does not block in steady state
+        if (it > 0) mbar_wait(bar(BB_TFULL + (int)((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));
+        tc_fence_after();
+        tmem_st16(tmem_gu + lane_base + part * CPW, r);
+        tmem_st_wait();
+        tc_fence_before();
       }
       fence_proxy_async();
       __syncwarp();
@@ -1210,12 +1239,13 @@ int block_tail_bwd_launch(const float* g, const float* u, const float* h, const 
     if (rc) return rc;
   }
   const long long tpb = S / blk::TS, ntiles = tpb * B;
-  const size_t smem = blk::bwd_smem(lf.Win != nullptr && t == nullptr).total + 1024;
+  const int du_mode = option_get(OPT_BLOCK_SAVES_DERIVATIVE);
+  const bool last3 = blk::LAST3_ON && Wp != nullptr && t != nullptr && lf.Win == nullptr;
+  const size_t smem = blk::bwd_smem(lf.Win != nullptr && t == nullptr, last3).total + 1024;
   int sms = num_sms();
   if (sms > 1024) sms = 1024;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   const int kid = vg ? K_BLOCK_SPECTRAL_BWD : K_BLOCK_TAIL_BWD;
-  const int du_mode = option_get(OPT_BLOCK_SAVES_DERIVATIVE);
   {
     ProfScope ps(kid, st);
 #define PDEPHI_BWD_LAUNCH_Z(GG, WW, HH, ZZ)                                                                                \
