@@ -213,3 +213,27 @@ def test_packed_block_derivative_layout_round_trips():
     back = pf.unpack_block_derivative(packed)
     assert back.dtype == torch.float32 and torch.equal(back, du.half().float())
     assert float((back - du).abs().max()) <= 2.0 ** -11 * 1.13 and pf.unpack_block_derivative(du) is du
+
+
+def test_block_derivative_option_governs_the_u_buffer():
+    """PDEPHI_OPT_BLOCK_SAVES_DERIVATIVE (host-side state of the library, no GPU needed): default 2 = packed binary16 buffer of
+    half the bytes; 0 / 1 = an fp32 activation; a buffer written under one setting is refused under another."""
+    from pde_fluid_phi_b200 import functional as pf
+    lib = _cabi.load()
+    assert lib.pdephi_get_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE) == 2
+    u2 = pf._block_u_empty(2, 64, (4, 4, 128), "cpu")
+    assert u2.dtype == torch.float16 and tuple(u2.shape) == (2, 64, 4, 4, 128)
+    pf._check_block_u(u2, "test")
+    old = _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, 1)
+    try:
+        assert old == 2
+        u1 = pf._block_u_empty(2, 64, (4, 4, 128), "cpu")
+        assert u1.dtype == torch.float32 and u1.numel() * u1.element_size() == 2 * u2.numel() * u2.element_size()
+        pf._check_block_u(u1, "test")
+        with pytest.raises(RuntimeError, match="SAVES_DERIVATIVE"):
+            pf._check_block_u(u2, "test")
+    finally:
+        _cabi.set_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE, old)
+    with pytest.raises(RuntimeError, match="SAVES_DERIVATIVE"):
+        pf._check_block_u(u1, "test")
+    assert lib.pdephi_get_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE) == 2
