@@ -723,7 +723,13 @@ def run_native(args):
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": rooflines,
                 "cpu_baseline": cpu, "gpu_incumbent": incumbent, "layer_fwd_bwd_us": layer_us, "other_precision": other,
                 "k2_share_of_step": round(k2 / total_ms, 4), "kernels": per_kernel, "first_loss": first_loss,
-                "final_loss": final_loss}
+                "final_loss": final_loss,
+                # what is NOT fp32 in memory: stated with the line (include/pdephi_b200.h)
+                "storage": {"activations_parameters_gradients_optimizer": "fp32",
+                            "block_saved_derivative": {0: "pre-activation u, fp32", 1: "gelu'(u), fp32",
+                                                       2: "gelu'(u) as binary16 (the 11 significant bits of the TF32 operand it "
+                                                          "becomes), one 32-bit word per channel pair and point"}.get(
+                                _cabi.load().pdephi_get_option(_cabi.OPT_BLOCK_SAVES_DERIVATIVE), "?")}}
     else:
         line = None
     # N > 1: the slab-decomposed cfg-5 layer (all-to-all transpose) and cfg 3's data-parallel step with real gradient volume.
